@@ -1,0 +1,227 @@
+/*
+ * cspb200.h — C-ABI of libcspb200.so, the B200 (sm_100a) drop-in engine behind nextPYP's
+ * closed CPU binaries  external/cistem2/{refine3d,reconstruct3d,local_merge3d,merge3d}  and
+ * external/CSP/csp.
+ *
+ * The reference has NO in-process API for this path: pyp spawns those executables and talks
+ * to them through argv / a stdin heredoc / files.  The entry points below are
+ * therefore what a cisTEM-style executable (or pyp itself, through ctypes) binds INSTEAD of the
+ * numerics that live inside the binaries.  Each one cites the reference interface it replaces
+ * (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success or a negative CSPB_E_*;
+ *     cspb_last_error(ctx) gives the text.  No exceptions cross the boundary.
+ *   - caller allocates every buffer.  `loc` arguments say where a buffer lives:
+ *     CSPB_HOST (pageable or pinned host memory) or CSPB_DEVICE (device pointer on ctx's GPU).
+ *   - parameter rows are the packed 128-byte little-endian rows of a `.cistem` projection table
+ *     (src/pyp/inout/metadata/cistem_star_file.py:596-628, layout in SURVEY.md Appendix B);
+ *     `cspb_row` below is that exact layout, so a file can be mmapped and handed over unchanged.
+ *   - image stacks are MRC mode-2 payloads: float32, x fastest, n*n per projection
+ *     (src/pyp/inout/image/mrc.py:113-156,537-559).
+ *   - a context is bound to one GPU; one process per GPU; a context is not thread-safe,
+ *     different contexts are independent.
+ *   - there is no CPU fallback: every call fails with CSPB_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef CSPB200_H
+#define CSPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSPB_ABI_VERSION 1
+
+enum { CSPB_HOST = 0, CSPB_DEVICE = 1 };
+
+enum {
+    CSPB_OK = 0,
+    CSPB_E_ARG = -1,    /* invalid argument / state              */
+    CSPB_E_CUDA = -2,   /* CUDA runtime error / no usable device */
+    CSPB_E_NOMEM = -3,  /* host or device allocation failed      */
+    CSPB_E_STATE = -4,  /* call order violated (e.g. no reference set) */
+};
+
+/* One projection row of a .cistem table — cistem_star_file.py:596-628 (column order),
+ * :127-185 (types).  Units: angles deg, shifts Angstrom, defocus Angstrom, pixel Angstrom,
+ * voltage kV, Cs mm (src/pyp/inout/metadata/core.py:2891-2923). */
+typedef struct cspb_row {
+    uint32_t position_in_stack; /* 1-based */
+    float psi, theta, phi;
+    float x_shift, y_shift;
+    float defocus_1, defocus_2, defocus_angle, phase_shift;
+    int32_t image_is_active;    /* pyp re-uses it as film index (cistem_star_file.py:1516) */
+    float occupancy, logp, sigma, score;
+    float pixel_size, voltage_kv, cs_mm, amplitude_contrast;
+    float beam_tilt_x, beam_tilt_y, image_shift_x, image_shift_y;
+    float original_x, original_y;
+    int32_t imind, pind, tind, rind, find;
+    float fshift_x, fshift_y;
+} cspb_row; /* sizeof == 128 */
+
+typedef struct cspb_ctx cspb_ctx;
+
+/* ------------------------------------------------------------------ lifecycle */
+int cspb_abi_version(void);
+/* Bind a context to CUDA device `device`. */
+int cspb_create(int device, cspb_ctx **out);
+int cspb_destroy(cspb_ctx *ctx);
+const char *cspb_last_error(const cspb_ctx *ctx);
+/* Block until all work queued on the context's stream has finished. */
+int cspb_sync(cspb_ctx *ctx);
+/* Raw cudaStream_t of the context (for CUDA-event timing and NCCL plumbing on the same stream). */
+int cspb_stream(cspb_ctx *ctx, void **stream_out);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t cspb_launch_count(const cspb_ctx *ctx);
+
+/* ------------------------------------------------------------------ refine3d
+ * Replaces the numerics of external/cistem2/refine3d as driven by
+ * src/pyp/refine/frealign/frealign.py:3918-3994 (prompt order in SURVEY.md Appendix A.2).
+ * Field comments give the prompt number that carries the value. */
+typedef struct cspb_refine_cfg {
+    int32_t box;               /* n: image edge in pixels (from the stack header)              */
+    int32_t pad;               /* prompt 35 padding factor refine_iblow (1 or 2)               */
+    float pixel_size;          /* prompt 15, Angstrom                                          */
+    float mask_radius;         /* prompt 18 outer mask radius (particle_rad), Angstrom         */
+    float low_res_limit;       /* prompt 19 refine_rlref, Angstrom                             */
+    float high_res_limit;      /* prompt 20 get_rhref(), Angstrom                              */
+    float signed_cc_limit;     /* prompt 21 (30.0 or refine_fboostlim), Angstrom; 0 = always signed */
+    float search_mask_radius;  /* prompt 23 global-search mask radius, Angstrom                */
+    float search_high_res;     /* prompt 24 high-res limit for the global search, Angstrom     */
+    float angular_step;        /* prompt 25 refine_dang, degrees                               */
+    int32_t best_matches;      /* prompt 26 number of global-search matches to refine (20)     */
+    float search_range_x;      /* prompt 27, Angstrom                                          */
+    float search_range_y;      /* prompt 28, Angstrom                                          */
+    float defocus_range;       /* prompt 33, Angstrom                                          */
+    float defocus_step;        /* prompt 34, Angstrom                                          */
+    int32_t global_search;     /* prompt 36                                                    */
+    int32_t local_refine;      /* prompt 37                                                    */
+    int32_t refine_psi, refine_theta, refine_phi, refine_x, refine_y; /* prompts 38-42         */
+    int32_t refine_defocus;    /* prompt 45                                                    */
+    int32_t apply_mask;        /* prompt 44 apply 2-D masking: 0 none, 1 soft circular mask    */
+    int32_t normalize;         /* prompt 46 normalise particles                                */
+    int32_t invert_contrast;   /* prompt 47                                                    */
+    int32_t whiten;            /* 1 = whiten with the stack's noise power curve (cisTEM default) */
+    int32_t symmetry_order;    /* number of symmetry matrices handed to cspb_set_symmetry (1 = C1) */
+    int32_t local_iterations;  /* batched local-optimiser iterations (ours; default 6)         */
+    int32_t reserved[7];
+} cspb_refine_cfg;
+
+/* Fill a config with the defaults pyp passes for a plain local refinement. */
+int cspb_refine_cfg_default(cspb_refine_cfg *cfg, int box, float pixel_size);
+
+/* Configure the scorer; builds the polar-patch band plan for (box, low_res, high_res). */
+int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg);
+
+/* Optional per-ring SSNR weights (prompt 5/6, statistics_rNN.txt part_SSNR column mapped to
+ * rings of the box); n_rings = box/2+1.  NULL resets to all-ones. */
+int cspb_refine_set_ring_weights(cspb_ctx *ctx, const float *w, int n_rings);
+
+/* Upload the reference map (prompt 4, n^3 float32, x fastest) and build the padded, centred,
+ * band-cropped Fourier half-volume in HBM. */
+int cspb_set_reference(cspb_ctx *ctx, const float *vol, int n, int loc);
+
+/* Symmetry matrices (row-major 3x3 each) for prompt 11 (refine) / 9 (reconstruct). */
+int cspb_set_symmetry(cspb_ctx *ctx, const float *mats, int n_mats);
+
+/* Load `n_images` projections (stack slices first..last) and preprocess them on the GPU:
+ * normalise -> FFT -> whiten -> mask -> band-pack.  `images` is n_images*box*box float32.
+ * May be called repeatedly with append=1 to stream a stack in chunks. */
+int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n_images, int loc, int append);
+int cspb_refine_num_images(const cspb_ctx *ctx);
+
+/* Score every loaded image at the pose in its row (one evaluation per image).
+ * rows[k] belongs to loaded image k.  scores_out: n floats (SCORE column, 100*CC). */
+int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, float *scores_out);
+
+/* Generic evaluation list: eval e scores image image_index[e] at
+ * poses[e] = {psi, theta, phi (deg), shift_x, shift_y (Angstrom), defocus delta (Angstrom)}.
+ * Evaluations should be sorted by image for best locality.  This is the objective function
+ * that csp (external/CSP/csp, src/pyp/system/local_run.py:364-376) sums over tilts. */
+int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int n_rows,
+                            const int32_t *image_index, const float *poses6, int n_evals,
+                            float *scores_out);
+
+/* Full refine3d pass over the loaded images: optional global search, then batched local
+ * refinement of the masked parameters.  rows are updated in place (PSI, THETA, PHI, X_SHIFT,
+ * Y_SHIFT, [DEFOCUS], LOGP, SIGMA, SCORE, score change is returned in changes_out if non-NULL).
+ * n_evals_out receives the number of (image,pose) objective evaluations performed. */
+int cspb_refine_run(cspb_ctx *ctx, cspb_row *rows, int n, cspb_row *changes_out,
+                    int64_t *n_evals_out);
+
+/* Asynchronous resident variant used by the benchmark: rows live in device memory, nothing is
+ * copied, the work is only enqueued on the context stream. */
+int cspb_refine_run_device(cspb_ctx *ctx, cspb_row *rows_dev, int n, int64_t *n_evals_out);
+
+/* Noise power curve used for whitening (box/2+1 floats); estimated by load_images when the
+ * context has none yet, or set explicitly (multi-GPU: all-reduce the partial sums first). */
+int cspb_refine_get_noise_curve(cspb_ctx *ctx, float *curve_out, int n_rings);
+int cspb_refine_set_noise_curve(cspb_ctx *ctx, const float *curve, int n_rings);
+
+/* ------------------------------------------------------------------ reconstruct3d
+ * Replaces external/cistem2/reconstruct3d as driven by frealign.py:1780-1824
+ * (SURVEY.md Appendix A.3). */
+typedef struct cspb_recon_cfg {
+    int32_t box;               /* n                                                     */
+    int32_t pad;               /* prompt 25 padding (pyp always passes 1)               */
+    float pixel_size;          /* prompt 12                                             */
+    float mask_radius;         /* prompt 15 outer radius rad_rec, Angstrom              */
+    float resolution_limit;    /* prompt 16 res_rec, Angstrom (2*pixel = Nyquist)       */
+    float score_bfactor;       /* prompt 18 refine_bsc, score -> B-factor constant      */
+    int32_t score_weighting;   /* prompt 19                                             */
+    float score_threshold;     /* prompt 23                                             */
+    int32_t normalize;         /* prompt 26                                             */
+    int32_t invert_contrast;   /* prompt 28                                             */
+    int32_t per_particle_split;/* prompt 32: halves by PIND parity instead of stack parity */
+    float average_score;       /* mean SCORE of the contributing rows (for score weighting) */
+    int32_t reserved[8];
+} cspb_recon_cfg;
+
+int cspb_recon_cfg_default(cspb_recon_cfg *cfg, int box, float pixel_size);
+
+/* Allocate and zero the two Fourier half-accumulators {re, im, ctf^2 weight, pad} per voxel. */
+int cspb_recon_begin(cspb_ctx *ctx, const cspb_recon_cfg *cfg);
+
+/* Insert n_images projections (OCC > 0 rows only contribute) with CTF multiplication and
+ * CTF^2 weight accumulation, for every symmetry matrix set with cspb_set_symmetry. */
+int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_row *rows, int n_images,
+                      int loc);
+
+/* Accumulator geometry: voxels = (np/2+1)*np*np, 4 floats per voxel. */
+int cspb_recon_dims(const cspb_ctx *ctx, int *np_out, int64_t *floats_per_half_out);
+/* Device pointer of half h (0/1) — hand it to ncclReduce / torch.distributed. */
+int cspb_recon_device_ptr(cspb_ctx *ctx, int half, void **ptr_out);
+/* Dump / add-dump: the file-mode collective of local_merge3d (frealign.py:1878-1888). */
+int cspb_recon_get_dump(cspb_ctx *ctx, int half, float *out, int loc);
+int cspb_recon_add_dump(cspb_ctx *ctx, int half, const float *in, int loc);
+
+/* merge3d (frealign.py:2075-2093): symmetrise, per-shell statistics, optimal-filter
+ * normalisation, inverse FFT, gridding correction, outer mask.
+ * half1/half2/map: n^3 float32 each (may be NULL); stats: n_shells*7 floats, rows
+ * {shell, resolution A, ring radius (1/A * ... ), FSC, Part_FSC, Part_SSNR^.5, Rec_SSNR^.5}. */
+int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, float outer_radius_a,
+                        float *half1, float *half2, float *map, float *stats, int n_shells,
+                        int loc);
+int cspb_recon_end(cspb_ctx *ctx);
+
+/* ------------------------------------------------------------------ building blocks
+ * Exposed for parity tests against the oracle and cuFFT. */
+/* Batched 2-D real-to-complex FFT, unnormalised, output n*(n/2+1) complex per image. */
+int cspb_fft2_r2c(cspb_ctx *ctx, const float *in, float *out_complex, int n, int batch, int loc);
+int cspb_fft2_c2r(cspb_ctx *ctx, const float *in_complex, float *out, int n, int batch, int loc);
+/* Same through cuFFT (comparison baseline only; never on the product path). */
+int cspb_cufft2_r2c(cspb_ctx *ctx, const float *in, float *out_complex, int n, int batch, int loc);
+/* CTF values on the half-plane grid for one row: out n*(n/2+1) floats. */
+int cspb_ctf_image(cspb_ctx *ctx, const cspb_row *row, int n, float *out);
+/* Central slice of the current reference at one pose: out n*(n/2+1) complex (zero outside band). */
+int cspb_project(cspb_ctx *ctx, float psi, float theta, float phi, float *out_complex);
+/* Band plan introspection: number of lattice samples inside the band / padded slots. */
+int cspb_band_counts(const cspb_ctx *ctx, int *n_band, int *n_slots);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPB200_H */

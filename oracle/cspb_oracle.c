@@ -1,0 +1,761 @@
+/*
+ * cspb_oracle.c — CPU restatement of the CSP refine3d / reconstruct3d hot path (plain C).
+ * TEST INFRASTRUCTURE ONLY — see the header of cspb_oracle.h.  "Parity unpinned": the
+ * reference arithmetic is in closed LFS binaries; definitions are in oracle/SEMANTICS.md.
+ *
+ * Deliberately written differently from the CUDA path so the two check each other:
+ *   - natural (j, i) half-plane loops with a per-pixel bin index, the shape of cisTEM's
+ *     Image::GetWeightedCorrelationWithImage (published source; contract at
+ *     src/pyp/refine/frealign/frealign.py:3918-3994), not the GPU's polar-patch band plan;
+ *   - explicit 8-weight trilinear interpolation on a plain FFT-ordered padded volume;
+ *   - a recursive mixed-radix FFT in double precision.
+ * Arithmetic is fp32 where cisTEM's is (images, CTF, correlation sums), as the reference is.
+ */
+#include "cspb_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PI_D 3.14159265358979323846
+#define PI_F 3.14159265358979323846f
+
+/* ================================================================ FFT (double, mixed radix) */
+typedef struct { double re, im; } cd;
+
+static void fft_rec(const cd *in, cd *out, int n, int stride, int sign, const cd *tw, int tw_n) {
+    /* decimation in time; radix = smallest prime factor of n; tw = exp(sign*2 pi i k / tw_n) */
+    if (n == 1) { out[0] = in[0]; return; }
+    int p = 2;
+    while (n % p) ++p;
+    const int m = n / p;
+    for (int q = 0; q < p; ++q) fft_rec(in + (size_t)q * stride, out + (size_t)q * m, m, stride * p, sign, tw, tw_n);
+    cd *tmp = (cd *)malloc(sizeof(cd) * (size_t)n);
+    const int tstep = tw_n / n;
+    for (int k = 0; k < m; ++k)
+        for (int r = 0; r < p; ++r) {
+            /* X[k + r m] = sum_q W_n^{q (k + r m)} E_q[k] */
+            double sr = 0, si = 0;
+            for (int q = 0; q < p; ++q) {
+                const int e = (int)(((long long)q * (k + r * m)) % n) * tstep;
+                const cd w = tw[e];
+                const cd v = out[(size_t)q * m + k];
+                sr += w.re * v.re - w.im * v.im;
+                si += w.re * v.im + w.im * v.re;
+            }
+            tmp[k + r * m].re = sr;
+            tmp[k + r * m].im = si;
+        }
+    memcpy(out, tmp, sizeof(cd) * (size_t)n);
+    free(tmp);
+}
+
+static cd *make_tw(int n, int sign) {
+    cd *tw = (cd *)malloc(sizeof(cd) * (size_t)n);
+    for (int k = 0; k < n; ++k) {
+        const double a = sign * 2.0 * PI_D * k / n;
+        tw[k].re = cos(a);
+        tw[k].im = sin(a);
+    }
+    return tw;
+}
+
+/* in-place strided 1-D transform of `count` lines */
+static void fft_lines(cd *data, int n, size_t estride, size_t lstride, size_t count, int sign) {
+    cd *tw = make_tw(n, sign);
+#pragma omp parallel
+    {
+        cd *a = (cd *)malloc(sizeof(cd) * (size_t)n), *b = (cd *)malloc(sizeof(cd) * (size_t)n);
+#pragma omp for schedule(static)
+        for (long long l = 0; l < (long long)count; ++l) {
+            cd *base = data + (size_t)l * lstride;
+            for (int e = 0; e < n; ++e) a[e] = base[(size_t)e * estride];
+            fft_rec(a, b, n, 1, sign, tw, n);
+            for (int e = 0; e < n; ++e) base[(size_t)e * estride] = b[e];
+        }
+        free(a);
+        free(b);
+    }
+    free(tw);
+}
+
+/* full complex n-D transforms on double arrays (x fastest) */
+static void fft2_full(cd *d, int n, int sign) {
+    fft_lines(d, n, 1, (size_t)n, (size_t)n, sign);
+    for (int x = 0; x < n; ++x) fft_lines(d + x, n, (size_t)n, 0, 1, sign);
+}
+
+void orc_fft2_r2c(const float *img, int n, float *out_c) {
+    const int nh = n / 2 + 1;
+    cd *d = (cd *)malloc(sizeof(cd) * (size_t)n * n);
+    for (int k = 0; k < n * n; ++k) { d[k].re = img[k]; d[k].im = 0; }
+    fft2_full(d, n, -1);
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < nh; ++x) {
+            out_c[2 * ((size_t)y * nh + x)] = (float)d[(size_t)y * n + x].re;
+            out_c[2 * ((size_t)y * nh + x) + 1] = (float)d[(size_t)y * n + x].im;
+        }
+    free(d);
+}
+
+void orc_fft2_c2r(const float *in_c, int n, float *out) {
+    const int nh = n / 2 + 1;
+    cd *d = (cd *)malloc(sizeof(cd) * (size_t)n * n);
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            if (x < nh) {
+                d[(size_t)y * n + x].re = in_c[2 * ((size_t)y * nh + x)];
+                d[(size_t)y * n + x].im = in_c[2 * ((size_t)y * nh + x) + 1];
+            } else {
+                const int my = (n - y) % n, mx = n - x;
+                d[(size_t)y * n + x].re = in_c[2 * ((size_t)my * nh + mx)];
+                d[(size_t)y * n + x].im = -in_c[2 * ((size_t)my * nh + mx) + 1];
+            }
+        }
+    fft2_full(d, n, +1);
+    for (int k = 0; k < n * n; ++k) out[k] = (float)d[k].re;
+    free(d);
+}
+
+/* 3-D transforms on a full complex cube */
+static void fft3_full(cd *d, int n, int sign) {
+    fft_lines(d, n, 1, (size_t)n, (size_t)n * n, sign);                      /* x */
+    for (int z = 0; z < n; ++z)                                              /* y */
+        fft_lines(d + (size_t)z * n * n, n, (size_t)n, 1, (size_t)n, sign);
+    fft_lines(d, n, (size_t)n * n, 1, (size_t)n * n, sign);                  /* z */
+}
+
+/* ================================================================ Euler, CTF */
+void orc_euler_matrix(float psi, float theta, float phi, float *r) {
+    /* FREALIGN / cisTEM ZYZ: R = Rz(phi) Ry(theta) Rz(psi); pyp decodes the same angles from its
+       left-handed matrix at src/pyp/analysis/geometry/core.py:222-247 */
+    const float d2r = PI_F / 180.f;
+    const float cps = cosf(psi * d2r), sps = sinf(psi * d2r);
+    const float cth = cosf(theta * d2r), sth = sinf(theta * d2r);
+    const float cph = cosf(phi * d2r), sph = sinf(phi * d2r);
+    r[0] = cph * cth * cps - sph * sps;  r[1] = -cph * cth * sps - sph * cps;  r[2] = cph * sth;
+    r[3] = sph * cth * cps + cph * sps;  r[4] = -sph * cth * sps + cph * cps;  r[5] = sph * sth;
+    r[6] = -sth * cps;                   r[7] = sth * sps;                     r[8] = cth;
+}
+
+typedef struct { float a, b, c2, s2, c4, ph0, dstep; } ctfc;
+
+static ctfc ctf_make(const orc_row *row, int box) {
+    /* units: src/pyp/inout/metadata/core.py:2891-2923 (defocus A, voltage kV, Cs mm, pixel A) */
+    ctfc c;
+    const float v = row->voltage_kv * 1000.f;
+    const float lambda = 12.2639f / sqrtf(v + 0.97845e-6f * v * v);
+    const float l = (float)box * row->pixel_size;
+    const float s2u = 1.f / (l * l);
+    c.a = PI_F * lambda * 0.5f * (row->defocus_1 + row->defocus_2) * s2u;
+    c.b = PI_F * lambda * 0.5f * (row->defocus_1 - row->defocus_2) * s2u;
+    c.c2 = cosf(2.f * row->defocus_angle * (PI_F / 180.f));
+    c.s2 = sinf(2.f * row->defocus_angle * (PI_F / 180.f));
+    c.c4 = -0.5f * PI_F * lambda * lambda * lambda * (row->cs_mm * 1.0e7f) * s2u * s2u;
+    c.ph0 = row->phase_shift + atanf(row->amplitude_contrast / sqrtf(1.f - row->amplitude_contrast * row->amplitude_contrast));
+    c.dstep = PI_F * lambda * s2u;
+    return c;
+}
+
+static float ctf_eval(const ctfc *c, int i, int j, float ddef_a) {
+    const float fi = (float)i, fj = (float)j, r2 = fi * fi + fj * fj;
+    float cos2 = 0.f, sin2 = 0.f;
+    if (r2 > 0.f) { cos2 = (fi * fi - fj * fj) / r2; sin2 = 2.f * fi * fj / r2; }
+    const float chi = r2 * (c->a + ddef_a * c->dstep + c->b * (cos2 * c->c2 + sin2 * c->s2)) + c->c4 * r2 * r2 + c->ph0;
+    return -sinf(chi);
+}
+
+void orc_ctf_image(const orc_row *row, int n, float *out) {
+    const int nh = n / 2 + 1;
+    const ctfc c = ctf_make(row, n);
+    for (int jj = 0; jj < n; ++jj)
+        for (int i = 0; i < nh; ++i) {
+            const int j = jj >= n / 2 ? jj - n : jj;
+            out[(size_t)jj * nh + i] = ctf_eval(&c, i, j, 0.f);
+        }
+}
+
+float orc_band_limits(const orc_refine_cfg *cfg, float *r_lo, float *r_hi) {
+    const float npx = (float)cfg->box * cfg->pixel_size;
+    float lo = npx / cfg->low_res_limit, hi = npx / cfg->high_res_limit;
+    const float cap = (float)(cfg->box / 2 - 2);
+    if (hi > cap) hi = cap;
+    if (r_lo) *r_lo = lo;
+    if (r_hi) *r_hi = hi;
+    return hi;
+}
+
+int orc_band_count(const orc_refine_cfg *cfg) {
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    const int n = cfg->box;
+    int c = 0;
+    for (int j = -n / 2; j < n / 2; ++j)
+        for (int i = 0; i <= n / 2; ++i) {
+            const float r2 = (float)(i * i + j * j);
+            if (r2 >= lo * lo && r2 <= hi * hi) ++c;
+        }
+    return c;
+}
+
+/* ================================================================ reference volume */
+struct orc_ref {
+    int n, pad, np, xh;
+    float *v; /* complex [z][y][x], x in [0,np/2], y,z FFT order, centred phase applied */
+};
+
+static float sinc2c(int d, int np) {
+    if (d == 0) return 1.f;
+    const float a = PI_F * (float)d / (float)np;
+    const float s = sinf(a) / a;
+    return s * s;
+}
+
+orc_ref *orc_ref_create(const float *vol, int n, int pad) {
+    orc_ref *r = (orc_ref *)calloc(1, sizeof(orc_ref));
+    r->n = n; r->pad = pad; r->np = n * pad; r->xh = r->np / 2 + 1;
+    const int np = r->np, off = (np - n) / 2;
+    cd *d = (cd *)calloc((size_t)np * np * np, sizeof(cd));
+    for (int z = 0; z < n; ++z)
+        for (int y = 0; y < n; ++y)
+            for (int x = 0; x < n; ++x) {
+                const int X = x + off, Y = y + off, Z = z + off;
+                const float g = sinc2c(X - np / 2, np) * sinc2c(Y - np / 2, np) * sinc2c(Z - np / 2, np);
+                d[((size_t)Z * np + Y) * np + X].re = vol[((size_t)z * n + y) * n + x] / g;
+            }
+    fft3_full(d, np, -1);
+    r->v = (float *)malloc(sizeof(float) * 2 * (size_t)r->xh * np * np);
+    for (int z = 0; z < np; ++z)
+        for (int y = 0; y < np; ++y)
+            for (int x = 0; x < r->xh; ++x) {
+                const cd c = d[((size_t)z * np + y) * np + x];
+                const float sg = ((x + y + z) & 1) ? -1.f : 1.f; /* box centre at np/2 */
+                const size_t o = 2 * (((size_t)z * np + y) * r->xh + x);
+                r->v[o] = sg * (float)c.re;
+                r->v[o + 1] = sg * (float)c.im;
+            }
+    free(d);
+    return r;
+}
+
+void orc_ref_free(orc_ref *r) { if (r) { free(r->v); free(r); } }
+
+static void ref_at(const orc_ref *r, int x, int y, int z, float *re, float *im) {
+    /* integer lattice lookup with Friedel symmetry and FFT-order wrap */
+    float sg = 1.f;
+    if (x < 0) { x = -x; y = -y; z = -z; sg = -1.f; }
+    const int np = r->np;
+    if (x > np / 2 || y < -np / 2 || y > np / 2 || z < -np / 2 || z > np / 2) { *re = 0; *im = 0; return; }
+    const int iy = ((y % np) + np) % np, iz = ((z % np) + np) % np;
+    const size_t o = 2 * (((size_t)iz * np + iy) * r->xh + x);
+    *re = r->v[o];
+    *im = sg * r->v[o + 1];
+}
+
+static void ref_interp(const orc_ref *r, float x, float y, float z, float *re, float *im) {
+    /* cisTEM ExtractSlice: trilinear interpolation over the 8 neighbours */
+    const int x0 = (int)floorf(x), y0 = (int)floorf(y), z0 = (int)floorf(z);
+    const float fx = x - x0, fy = y - y0, fz = z - z0;
+    float sr = 0.f, si = 0.f;
+    for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                const float w = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (dz ? fz : 1.f - fz);
+                float a, b;
+                ref_at(r, x0 + dx, y0 + dy, z0 + dz, &a, &b);
+                sr += w * a;
+                si += w * b;
+            }
+    *re = sr;
+    *im = si;
+}
+
+void orc_project(const orc_ref *r, float psi, float theta, float phi, float r_hi, float *out_c) {
+    const int n = r->n, nh = n / 2 + 1;
+    float m[9];
+    orc_euler_matrix(psi, theta, phi, m);
+    for (int jj = 0; jj < n; ++jj)
+        for (int i = 0; i < nh; ++i) {
+            const int j = jj >= n / 2 ? jj - n : jj;
+            float re = 0.f, im = 0.f;
+            if ((float)(i * i + j * j) <= r_hi * r_hi)
+                ref_interp(r, (m[0] * i + m[1] * j) * r->pad, (m[3] * i + m[4] * j) * r->pad, (m[6] * i + m[7] * j) * r->pad, &re, &im);
+            out_c[2 * ((size_t)jj * nh + i)] = re;
+            out_c[2 * ((size_t)jj * nh + i) + 1] = im;
+        }
+}
+
+/* ================================================================ particle preprocessing */
+static float cos_edge(float r, float radius, float width) {
+    const float lo = radius - 0.5f * width, hi = radius + 0.5f * width;
+    if (r <= lo) return 1.f;
+    if (r >= hi) return 0.f;
+    return 0.5f * (1.f + cosf(PI_F * (r - lo) / width));
+}
+
+/* mean / std of the pixels outside `radius` (analysis/image.py:320-338,406-417 convention) */
+static void edge_stats(const float *img, int n, float radius, double *mean, double *var) {
+    const int c = n / 2;
+    const int use_all = radius * radius >= 2.f * c * c;
+    double s = 0, cnt = 0;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x)
+            if (use_all || (float)((x - c) * (x - c) + (y - c) * (y - c)) > radius * radius) { s += img[y * n + x]; cnt += 1; }
+    const double m = cnt > 0 ? s / cnt : 0;
+    double v = 0;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x)
+            if (use_all || (float)((x - c) * (x - c) + (y - c) * (y - c)) > radius * radius) { const double d = img[y * n + x] - m; v += d * d; }
+    *mean = m;
+    *var = cnt > 0 ? v / cnt : 0;
+}
+
+static void normalized_copy(const float *img, int n, float radius, int normalize, int invert, float *out) {
+    float off = 0.f, scl = invert ? -1.f : 1.f;
+    if (normalize) {
+        double m, v;
+        edge_stats(img, n, radius, &m, &v);
+        off = (float)m;
+        if (v > 0) scl *= (float)(1.0 / sqrt(v));
+    }
+    for (int k = 0; k < n * n; ++k) out[k] = (img[k] - off) * scl;
+}
+
+void orc_noise_curve(const float *imgs, int count, const orc_refine_cfg *cfg, float *curve) {
+    /* mean |F|^2 per nearest-integer ring over every step-th image (step = count/1024, >= 1) */
+    const int n = cfg->box, nh = n / 2 + 1, nr = n + 1;
+    const int step = count > 1024 ? count / 1024 : 1;
+    double *sum = (double *)calloc(nr, sizeof(double));
+    double *cnt = (double *)calloc(nr, sizeof(double));
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)n * n);
+    float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)n * nh);
+    int ns = 0;
+    for (int k = 0; k < count; k += step, ++ns) {
+        normalized_copy(imgs + (size_t)k * n * n, n, cfg->mask_radius / cfg->pixel_size, cfg->normalize, cfg->invert_contrast, tmp);
+        orc_fft2_r2c(tmp, n, spec);
+        for (int jj = 0; jj < n; ++jj)
+            for (int i = 0; i < nh; ++i) {
+                const int j = jj >= n / 2 ? jj - n : jj;
+                const int ring = (int)(sqrtf((float)(i * i + j * j)) + 0.5f);
+                const float re = spec[2 * ((size_t)jj * nh + i)], im = spec[2 * ((size_t)jj * nh + i) + 1];
+                sum[ring] += (double)(re * re + im * im);
+                if (ns == 0) cnt[ring] += 1;
+            }
+    }
+    for (int r = 0; r < nr; ++r) curve[r] = cnt[r] > 0 ? (float)(sum[r] / (cnt[r] * ns)) : 0.f;
+    free(sum); free(cnt); free(tmp); free(spec);
+}
+
+void orc_prepare_image(const float *img, const orc_refine_cfg *cfg, const float *noise_curve, const float *ring_weights, float *spec) {
+    /* normalise -> FFT -> whiten -> (inverse FFT, soft mask, FFT) -> centre -> ring weights */
+    const int n = cfg->box, nh = n / 2 + 1;
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)n * n);
+    normalized_copy(img, n, cfg->mask_radius / cfg->pixel_size, cfg->normalize, cfg->invert_contrast, tmp);
+    orc_fft2_r2c(tmp, n, spec);
+    const int whiten = cfg->whiten && noise_curve;
+    if (whiten)
+        for (int jj = 0; jj < n; ++jj)
+            for (int i = 0; i < nh; ++i) {
+                const int j = jj >= n / 2 ? jj - n : jj;
+                const int ring = (int)(sqrtf((float)(i * i + j * j)) + 0.5f);
+                const float w = noise_curve[ring] > 0.f ? 1.f / sqrtf(noise_curve[ring]) : 0.f;
+                spec[2 * ((size_t)jj * nh + i)] *= w;
+                spec[2 * ((size_t)jj * nh + i) + 1] *= w;
+            }
+    if (cfg->apply_mask) {
+        orc_fft2_c2r(spec, n, tmp);
+        const float rad = cfg->mask_radius / cfg->pixel_size, wid = 20.f / cfg->pixel_size;
+        const float sc = 1.f / ((float)n * (float)n);
+        for (int y = 0; y < n; ++y)
+            for (int x = 0; x < n; ++x) {
+                const float r = sqrtf((float)((x - n / 2) * (x - n / 2) + (y - n / 2) * (y - n / 2)));
+                tmp[y * n + x] *= sc * cos_edge(r, rad, wid);
+            }
+        orc_fft2_r2c(tmp, n, spec);
+    }
+    for (int jj = 0; jj < n; ++jj)
+        for (int i = 0; i < nh; ++i) {
+            const int j = jj >= n / 2 ? jj - n : jj;
+            float w = ((i + j) & 1) ? -1.f : 1.f;
+            if (ring_weights) w *= ring_weights[(int)sqrtf((float)(i * i + j * j))];
+            spec[2 * ((size_t)jj * nh + i)] *= w;
+            spec[2 * ((size_t)jj * nh + i) + 1] *= w;
+        }
+    free(tmp);
+}
+
+/* ================================================================ score */
+float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg, float *out4) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    const int nb = 2 * n;
+    float *cross = (float *)calloc(nb, sizeof(float));
+    float suma = 0.f, sumb = 0.f;
+    float m[9];
+    orc_euler_matrix(pose6[0], pose6[1], pose6[2], m);
+    const ctfc c = ctf_make(row, n);
+    const float k2 = 2.f * PI_F / ((float)n * row->pixel_size);
+    for (int j = -n / 2; j < n / 2; ++j)
+        for (int i = 0; i <= n / 2; ++i) {
+            const float r2 = (float)(i * i + j * j);
+            if (r2 < lo * lo || r2 > hi * hi) continue;
+            const int bin = (int)sqrtf(r2);
+            const int jj = j < 0 ? j + n : j;
+            const float fr = spec[2 * ((size_t)jj * nh + i)], fim = spec[2 * ((size_t)jj * nh + i) + 1];
+            float pr, pi;
+            ref_interp(r, (m[0] * i + m[1] * j) * r->pad, (m[3] * i + m[4] * j) * r->pad, (m[6] * i + m[7] * j) * r->pad, &pr, &pi);
+            const float ctf = ctf_eval(&c, i, j, pose6[5]);
+            pr *= ctf;
+            pi *= ctf;
+            const float ph = (i * pose6[3] + j * pose6[4]) * k2;
+            const float cs = cosf(ph), sn = sinf(ph);
+            const float gr = fr * cs - fim * sn, gi = fr * sn + fim * cs;
+            cross[bin] += gr * pr + gi * pi;
+            suma += fr * fr + fim * fim;
+            sumb += pr * pr + pi * pi;
+        }
+    const int limit = cfg->signed_cc_limit > 0.f ? (int)floorf((float)n * cfg->pixel_size / cfg->signed_cc_limit) : 0x7fffffff;
+    float num = 0.f, xs = 0.f;
+    for (int b = 0; b < nb; ++b) {
+        xs += cross[b];
+        num += (b > limit) ? fabsf(cross[b]) : cross[b];
+    }
+    free(cross);
+    if (out4) { out4[0] = num; out4[1] = xs; out4[2] = suma; out4[3] = sumb; }
+    const float den = suma * sumb;
+    return den > 0.f ? 100.f * num / sqrtf(den) : 0.f;
+}
+
+/* ================================================================ local refinement */
+#define NP 6
+#define NL 3
+static float wrap360(float a) { a = fmodf(a, 360.f); if (a < 0.f) a += 360.f; return a; }
+
+static void stats_from(const float *v, int ns, float *sigma, float *logp) {
+    const float X = v[1], A = v[2], B = v[3];
+    const float alpha = B > 0.f ? X / B : 0.f;
+    float resid = A - 2.f * alpha * X + alpha * alpha * B;
+    if (resid < 0.f) resid = 0.f;
+    const float sig2 = alpha * alpha * B;
+    *sigma = sig2 > 0.f ? sqrtf(resid / sig2) : 0.f;
+    const float n = (float)(ns > 0 ? ns : 1);
+    const float var = resid / n;
+    *logp = var > 0.f ? -0.5f * n * (1.f + logf(2.f * PI_F * var)) : 0.f;
+}
+
+long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    int freem[NP] = {cfg->refine_psi, cfg->refine_theta, cfg->refine_phi, cfg->refine_x, cfg->refine_y, cfg->refine_defocus};
+    int n_free = 0;
+    for (int m = 0; m < NP; ++m) n_free += freem[m] ? 1 : 0;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    const float h_ang = 0.5f * 57.29578f / hi;
+    const float h_shift = 0.1f * (float)n / hi * cfg->pixel_size;
+    const float h_def = cfg->defocus_step > 0.f ? cfg->defocus_step : 50.f;
+    const int iters = n_free > 0 ? (cfg->local_iterations > 0 ? cfg->local_iterations : 6) : 0;
+    const int nband = orc_band_count(cfg);
+    long long evals = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : evals)
+    for (int k = 0; k < n_img; ++k) {
+        const float *spec = specs + 2 * (size_t)k * n * nh;
+        orc_row *row = &rows[k];
+        float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f};
+        float h[NP] = {h_ang, h_ang, h_ang, h_shift, h_shift, h_def};
+        float d[NP];
+        float q[NP], o4[4];
+        for (int it = 0; it < iters; ++it) {
+            const float f0 = orc_score(r, spec, row, x, cfg, o4) * 0.01f;
+            evals++;
+            float fbest = f0;
+            int mbest = -1, sbest = 0;
+            for (int m = 0; m < NP; ++m) {
+                d[m] = 0.f;
+                if (!freem[m]) continue;
+                memcpy(q, x, sizeof q);
+                q[m] = x[m] + h[m];
+                const float fp = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+                q[m] = x[m] - h[m];
+                const float fm = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+                evals += 2;
+                if (fp > fbest) { fbest = fp; mbest = m; sbest = +1; }
+                if (fm > fbest) { fbest = fm; mbest = m; sbest = -1; }
+                const float g = (fp - fm) / (2.f * h[m]);
+                const float c = (fp - 2.f * f0 + fm) / (h[m] * h[m]);
+                float dd;
+                if (c < 0.f) dd = -g / c;
+                else dd = (g > 0.f ? 2.f : (g < 0.f ? -2.f : 0.f)) * h[m];
+                const float dmax = 4.f * h[m];
+                if (dd > dmax) dd = dmax;
+                if (dd < -dmax) dd = -dmax;
+                d[m] = dd;
+            }
+            if (mbest >= 0) { x[mbest] += sbest * h[mbest]; d[mbest] -= sbest * h[mbest]; }
+            const float tl[NL] = {0.5f, 1.f, 2.f};
+            int lbest = -1;
+            for (int l = 0; l < NL; ++l) {
+                for (int m = 0; m < NP; ++m) q[m] = x[m] + tl[l] * d[m];
+                const float f = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+                evals++;
+                if (f > fbest) { fbest = f; lbest = l; }
+            }
+            if (lbest >= 0)
+                for (int m = 0; m < NP; ++m) x[m] += tl[lbest] * d[m];
+            for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
+        }
+        const float sc = orc_score(r, spec, row, x, cfg, o4);
+        evals++;
+        row->psi = wrap360(x[0]);
+        row->theta = x[1];
+        row->phi = wrap360(x[2]);
+        row->x_shift = x[3];
+        row->y_shift = x[4];
+        if (cfg->refine_defocus) { row->defocus_1 += x[5]; row->defocus_2 += x[5]; }
+        row->score = sc;
+        stats_from(o4, nband, &row->sigma, &row->logp);
+    }
+    return evals;
+}
+
+/* ================================================================ reconstruction */
+struct orc_recon {
+    orc_recon_cfg cfg;
+    int np, xh;
+    float *acc[2]; /* float4 per voxel, centred y,z */
+};
+
+orc_recon *orc_recon_create(const orc_recon_cfg *cfg) {
+    orc_recon *rc = (orc_recon *)calloc(1, sizeof(orc_recon));
+    rc->cfg = *cfg;
+    rc->np = cfg->box * cfg->pad;
+    rc->xh = rc->np / 2 + 1;
+    for (int h = 0; h < 2; ++h) rc->acc[h] = (float *)calloc((size_t)rc->xh * rc->np * rc->np * 4, sizeof(float));
+    return rc;
+}
+
+void orc_recon_free(orc_recon *rc) { if (rc) { free(rc->acc[0]); free(rc->acc[1]); free(rc); } }
+
+static void add_corner(orc_recon *rc, float *acc, int x, int y, int z, float w, float re, float im, float wt) {
+    const int c = rc->np / 2;
+    if (x > c || y < -c || y >= c || z < -c || z >= c) return;
+    float *p = acc + 4 * (((size_t)(z + c) * rc->np + (y + c)) * rc->xh + x);
+    p[0] += w * re;
+    p[1] += w * im;
+    p[2] += w * wt;
+}
+
+void orc_recon_insert(orc_recon *rc, const float *imgs, const orc_row *rows, int count, const float *sym, int n_sym) {
+    /* cisTEM Reconstruct3D::InsertSliceWithCTF shape: i = 0 column only for j >= 0 */
+    const orc_recon_cfg *c = &rc->cfg;
+    const int n = c->box, nh = n / 2 + 1;
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)n * n);
+    float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)n * nh);
+    float rmax = (float)n * c->pixel_size / (c->resolution_limit > 0.f ? c->resolution_limit : 2.f * c->pixel_size);
+    if (rmax > (float)(n / 2)) rmax = (float)(n / 2);
+    const float l = (float)n * c->pixel_size, s2u = 1.f / (l * l);
+    const float bk = c->score_weighting ? c->score_bfactor * 0.25f * s2u : 0.f;
+    const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (!sym || n_sym < 1) { sym = id; n_sym = 1; }
+    for (int k = 0; k < count; ++k) {
+        const orc_row *row = &rows[k];
+        if (!(row->occupancy > 0.f) || row->score < c->score_threshold) continue;
+        normalized_copy(imgs + (size_t)k * n * n, n, c->mask_radius / c->pixel_size, c->normalize, c->invert_contrast, tmp);
+        orc_fft2_r2c(tmp, n, spec);
+        const ctfc cc = ctf_make(row, n);
+        float m[9];
+        orc_euler_matrix(row->psi, row->theta, row->phi, m);
+        const int half = c->per_particle_split ? (row->pind & 1) : ((row->position_in_stack & 1u) ? 0 : 1);
+        float *acc = rc->acc[half];
+        const float k2 = 2.f * PI_F / ((float)n * row->pixel_size);
+        for (int j = -n / 2; j < n / 2; ++j)
+            for (int i = 0; i <= n / 2; ++i) {
+                if (i == 0 && j < 0) continue;
+                const float r2 = (float)(i * i + j * j);
+                if (r2 > rmax * rmax) continue;
+                const int jj = j < 0 ? j + n : j;
+                const float sg = ((i + j) & 1) ? -1.f : 1.f;
+                const float fr = sg * spec[2 * ((size_t)jj * nh + i)], fim = sg * spec[2 * ((size_t)jj * nh + i) + 1];
+                const float ctf = ctf_eval(&cc, i, j, 0.f);
+                float w = row->occupancy * 0.01f;
+                if (bk != 0.f) w *= expf(-bk * (c->average_score - row->score) * r2);
+                const float ph = (i * row->x_shift + j * row->y_shift) * k2;
+                const float cs = cosf(ph), sn = sinf(ph);
+                const float re = (fr * cs - fim * sn) * ctf, im = (fr * sn + fim * cs) * ctf;
+                const float wt = ctf * ctf;
+                for (int s = 0; s < n_sym; ++s) {
+                    const float *S = sym + 9 * s;
+                    float R[9];
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b) R[3 * a + b] = S[3 * a] * m[b] + S[3 * a + 1] * m[3 + b] + S[3 * a + 2] * m[6 + b];
+                    float x = (R[0] * i + R[1] * j) * c->pad, y = (R[3] * i + R[4] * j) * c->pad, z = (R[6] * i + R[7] * j) * c->pad;
+                    float vim = im;
+                    if (x < 0.f) { x = -x; y = -y; z = -z; vim = -im; }
+                    const int x0 = (int)floorf(x), y0 = (int)floorf(y), z0 = (int)floorf(z);
+                    const float fx = x - x0, fy = y - y0, fz = z - z0;
+                    for (int dz = 0; dz < 2; ++dz)
+                        for (int dy = 0; dy < 2; ++dy)
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const float ww = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (dz ? fz : 1.f - fz);
+                                add_corner(rc, acc, x0 + dx, y0 + dy, z0 + dz, w * ww, re, vim, wt);
+                            }
+                }
+            }
+    }
+    free(tmp);
+    free(spec);
+}
+
+void orc_recon_get_dump(const orc_recon *rc, int half, float *out) {
+    memcpy(out, rc->acc[half], sizeof(float) * 4 * (size_t)rc->xh * rc->np * rc->np);
+}
+
+static void symmetrize_x0(float *acc, int np, int xh) {
+    const int c = np / 2;
+    for (int z = -c + 1; z < c; ++z)
+        for (int y = -c + 1; y < c; ++y) {
+            if (!(z > 0 || (z == 0 && y >= 0))) continue;
+            float *p = acc + 4 * (((size_t)(z + c) * np + (y + c)) * xh);
+            float *q = acc + 4 * (((size_t)(-z + c) * np + (-y + c)) * xh);
+            const float re = p[0] + q[0], im = p[1] - q[1], w = p[2] + q[2];
+            p[0] = re; p[1] = im; p[2] = w;
+            q[0] = re; q[1] = -im; q[2] = w;
+        }
+}
+
+void orc_recon_finalize(orc_recon *rc, float mw_kda, float outer_radius_a, float *half1, float *half2, float *map, float *stats) {
+    const orc_recon_cfg *c = &rc->cfg;
+    const int n = c->box, np = rc->np, xh = rc->xh, ns = n / 2 + 1, cen = np / 2;
+    const size_t nvox = (size_t)xh * np * np;
+    float *a[2];
+    for (int h = 0; h < 2; ++h) {
+        a[h] = (float *)malloc(sizeof(float) * 4 * nvox);
+        memcpy(a[h], rc->acc[h], sizeof(float) * 4 * nvox);
+        symmetrize_x0(a[h], np, xh);
+    }
+    double *sh = (double *)calloc((size_t)ns * 7, sizeof(double));
+    for (int z = -cen; z < cen; ++z)
+        for (int y = -cen; y < cen; ++y)
+            for (int x = 0; x < xh; ++x) {
+                const float r = sqrtf((float)(x * x + y * y + z * z)) / (float)c->pad;
+                const int s = (int)(r + 0.5f);
+                if (s >= ns) continue;
+                const size_t o = 4 * (((size_t)(z + cen) * np + (y + cen)) * xh + x);
+                const float *p = a[0] + o, *q = a[1] + o;
+                if (!(p[2] > 0.f) || !(q[2] > 0.f)) continue;
+                const double mult = x == 0 ? 0.5 : 1.0;
+                const float v1x = p[0] / p[2], v1y = p[1] / p[2], v2x = q[0] / q[2], v2y = q[1] / q[2];
+                double *d = sh + (size_t)s * 7;
+                d[0] += mult * (v1x * v2x + v1y * v2y);
+                d[1] += mult * (v1x * v1x + v1y * v1y);
+                d[2] += mult * (v2x * v2x + v2y * v2y);
+                d[3] += mult * (p[2] + q[2]);
+                d[4] += mult;
+                d[5] += mult * p[2];
+                d[6] += mult * q[2];
+            }
+    const float box_a = (float)n * c->pixel_size;
+    const float rad_a = outer_radius_a > 0.f ? outer_radius_a : 0.5f * box_a;
+    double mask_vol = 4.0 / 3.0 * PI_D * (double)rad_a * rad_a * rad_a;
+    const double box_vol = (double)box_a * box_a * box_a;
+    if (mask_vol > box_vol) mask_vol = box_vol;
+    double frac = mw_kda > 0.f ? ((double)mw_kda * 1000.0 / 0.81) / mask_vol : 1.0;
+    if (frac > 1.0 || frac <= 0.0) frac = 1.0;
+    float *term = (float *)calloc((size_t)3 * ns, sizeof(float));
+    for (int s = 0; s < ns; ++s) {
+        const double *q = sh + (size_t)s * 7;
+        double fsc = 0.0;
+        if (q[1] > 0.0 && q[2] > 0.0) fsc = q[0] / sqrt(q[1] * q[2]);
+        if (s == 0 && q[4] > 0.0) fsc = 1.0;
+        double f = fsc;
+        if (f > 0.9999) f = 0.9999;
+        if (f < 0.0) f = 0.0;
+        const double rec = 2.0 * f / (1.0 - f), part = rec / frac, pfsc = part / (2.0 + part);
+        const double cnt = q[4] > 0.0 ? q[4] : 1.0;
+        const double floor_ = 1e-4;
+        term[s] = (float)((q[3] / cnt) / (rec > floor_ ? rec : floor_));
+        const double hs = 0.5 * rec > floor_ ? 0.5 * rec : floor_;
+        term[ns + s] = (float)((q[5] / cnt) / hs);
+        term[2 * ns + s] = (float)((q[6] / cnt) / hs);
+        if (stats) {
+            float *o = stats + (size_t)s * 7;
+            o[0] = (float)s; o[1] = s > 0 ? box_a / (float)s : 0.f; o[2] = (float)s / (float)n;
+            o[3] = (float)fsc; o[4] = (float)pfsc; o[5] = (float)sqrt(part); o[6] = (float)sqrt(rec);
+        }
+    }
+    float *outs[3] = {map, half1, half2};
+    cd *d = (cd *)malloc(sizeof(cd) * (size_t)np * np * np);
+    for (int mode = 0; mode < 3; ++mode) {
+        if (!outs[mode]) continue;
+        for (int iz = 0; iz < np; ++iz)
+            for (int iy = 0; iy < np; ++iy)
+                for (int ix = 0; ix < np; ++ix) {
+                    /* full Hermitian cube from the stored half */
+                    const int x = ix > cen ? ix - np : ix;
+                    const int y = iy >= cen ? iy - np : iy, z = iz >= cen ? iz - np : iz;
+                    float sg = 1.f;
+                    int hx = x, hy = y, hz = z;
+                    if (x < 0) { hx = -x; hy = -y; hz = -z; sg = -1.f; }
+                    if (hy == cen) hy = -cen; /* Nyquist index is its own mate */
+                    if (hz == cen) hz = -cen;
+                    double re = 0, im = 0;
+                    if (hy >= -cen && hy < cen && hz >= -cen && hz < cen) {
+                        const float r = sqrtf((float)(hx * hx + hy * hy + hz * hz)) / (float)c->pad;
+                        const int s = (int)(r + 0.5f);
+                        if (s < ns) {
+                            const size_t o = 4 * (((size_t)(hz + cen) * np + (hy + cen)) * xh + hx);
+                            float vr, vi, w;
+                            if (mode == 0) { vr = a[0][o] + a[1][o]; vi = a[0][o + 1] + a[1][o + 1]; w = a[0][o + 2] + a[1][o + 2]; }
+                            else { const float *p = a[mode - 1] + o; vr = p[0]; vi = p[1]; w = p[2]; }
+                            const float den = w + term[(size_t)mode * ns + s];
+                            if (w > 0.f && den > 0.f) {
+                                const float cs = ((hx + hy + hz) & 1) ? -1.f : 1.f;
+                                re = cs * vr / den;
+                                im = sg * cs * vi / den;
+                            }
+                        }
+                    }
+                    d[((size_t)iz * np + iy) * np + ix].re = re;
+                    d[((size_t)iz * np + iy) * np + ix].im = im;
+                }
+        fft3_full(d, np, +1);
+        const int off = (np - n) / 2;
+        const float scale = 1.f / ((float)np * (float)np * (float)np);
+        const float rad = rad_a / c->pixel_size, wid = 20.f / c->pixel_size;
+        for (int z = 0; z < n; ++z)
+            for (int y = 0; y < n; ++y)
+                for (int x = 0; x < n; ++x) {
+                    const int dx = x - n / 2, dy = y - n / 2, dz = z - n / 2;
+                    float v = (float)d[((size_t)(z + off) * np + (y + off)) * np + (x + off)].re * scale;
+                    v /= sinc2c(dx, np) * sinc2c(dy, np) * sinc2c(dz, np);
+                    v *= cos_edge(sqrtf((float)(dx * dx + dy * dy + dz * dz)), rad, wid);
+                    outs[mode][((size_t)z * n + y) * n + x] = v;
+                }
+    }
+    free(d);
+    free(term);
+    free(sh);
+    free(a[0]);
+    free(a[1]);
+}
+
+void orc_fsc(const float *va, const float *vb, int n, float *fsc_out) {
+    const int ns = n / 2 + 1;
+    cd *a = (cd *)malloc(sizeof(cd) * (size_t)n * n * n), *b = (cd *)malloc(sizeof(cd) * (size_t)n * n * n);
+    for (size_t k = 0; k < (size_t)n * n * n; ++k) { a[k].re = va[k]; a[k].im = 0; b[k].re = vb[k]; b[k].im = 0; }
+    fft3_full(a, n, -1);
+    fft3_full(b, n, -1);
+    double *s = (double *)calloc((size_t)ns * 3, sizeof(double));
+    for (int iz = 0; iz < n; ++iz)
+        for (int iy = 0; iy < n; ++iy)
+            for (int ix = 0; ix < n; ++ix) {
+                const int x = ix >= n / 2 ? ix - n : ix, y = iy >= n / 2 ? iy - n : iy, z = iz >= n / 2 ? iz - n : iz;
+                const int sh = (int)(sqrt((double)(x * x + y * y + z * z)) + 0.5);
+                if (sh >= ns) continue;
+                const cd p = a[((size_t)iz * n + iy) * n + ix], q = b[((size_t)iz * n + iy) * n + ix];
+                s[3 * sh] += p.re * q.re + p.im * q.im;
+                s[3 * sh + 1] += p.re * p.re + p.im * p.im;
+                s[3 * sh + 2] += q.re * q.re + q.im * q.im;
+            }
+    for (int k = 0; k < ns; ++k) fsc_out[k] = (s[3 * k + 1] > 0 && s[3 * k + 2] > 0) ? (float)(s[3 * k] / sqrt(s[3 * k + 1] * s[3 * k + 2])) : 0.f;
+    free(s); free(a); free(b);
+}

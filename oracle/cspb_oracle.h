@@ -1,0 +1,107 @@
+/*
+ * cspb_oracle.h — CPU restatement of the CSP refine3d / reconstruct3d hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing on the product path may import, link or call this; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * PARITY STATUS: "parity unpinned" for the numerics.  The reference's arithmetic for this path
+ * lives in closed git-LFS binaries (external/cistem2/{refine3d,reconstruct3d,merge3d},
+ * external/CSP/csp — 133-byte pointer stubs in /root/reference) built from the
+ * un-vendored pyp fork of cisTEM 2.0.0-alpha (banner quoted at
+ * src/pyp/inout/image/mrc.py:646-651).  This file restates the published cisTEM/FREALIGN
+ * algorithm (Grant, Rohou & Grigorieff, eLife 2018; Grigorieff, Methods Enzymol. 2016) with
+ * every choice written down in oracle/SEMANTICS.md.  What IS pinned against the reference
+ * tree: the `.cistem` row layout (cistem_star_file.py:596-628), the MRC container
+ * (mrc.py:113-156), the Euler decode (geometry/core.py:222-247) and the prompt orders
+ * (frealign.py:3918-3994,1780-1824) — see tests/golden/.
+ */
+#ifndef CSPB_ORACLE_H
+#define CSPB_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the 128-byte .cistem projection row — cistem_star_file.py:596-628 */
+typedef struct orc_row {
+    uint32_t position_in_stack;
+    float psi, theta, phi, x_shift, y_shift;
+    float defocus_1, defocus_2, defocus_angle, phase_shift;
+    int32_t image_is_active;
+    float occupancy, logp, sigma, score;
+    float pixel_size, voltage_kv, cs_mm, amplitude_contrast;
+    float beam_tilt_x, beam_tilt_y, image_shift_x, image_shift_y;
+    float original_x, original_y;
+    int32_t imind, pind, tind, rind, find;
+    float fshift_x, fshift_y;
+} orc_row;
+
+/* refine3d answers that matter to the numerics — frealign.py:3918-3994 (same fields as
+ * cspb_refine_cfg in include/cspb200.h) */
+typedef struct orc_refine_cfg {
+    int32_t box, pad;
+    float pixel_size, mask_radius, low_res_limit, high_res_limit, signed_cc_limit;
+    float defocus_step;
+    int32_t refine_psi, refine_theta, refine_phi, refine_x, refine_y, refine_defocus;
+    int32_t apply_mask, normalize, invert_contrast, whiten, local_iterations;
+} orc_refine_cfg;
+
+typedef struct orc_recon_cfg {
+    int32_t box, pad;
+    float pixel_size, mask_radius, resolution_limit, score_bfactor;
+    int32_t score_weighting;
+    float score_threshold;
+    int32_t normalize, invert_contrast, per_particle_split;
+    float average_score;
+} orc_recon_cfg;
+
+typedef struct orc_ref orc_ref;      /* padded centred Fourier reference */
+typedef struct orc_recon orc_recon;  /* two half accumulators */
+
+/* ---- FFT (double precision inside) */
+void orc_fft2_r2c(const float *img, int n, float *out_c /* n*(n/2+1) complex */);
+void orc_fft2_c2r(const float *in_c, int n, float *out /* unnormalised inverse */);
+
+/* ---- Euler / CTF */
+void orc_euler_matrix(float psi, float theta, float phi, float *r9);
+void orc_ctf_image(const orc_row *row, int n, float *out /* n*(n/2+1) */);
+float orc_band_limits(const orc_refine_cfg *cfg, float *r_lo, float *r_hi); /* returns r_hi; also n_band via orc_band_count */
+int orc_band_count(const orc_refine_cfg *cfg);
+
+/* ---- reference */
+orc_ref *orc_ref_create(const float *vol, int n, int pad);
+void orc_ref_free(orc_ref *r);
+void orc_project(const orc_ref *r, float psi, float theta, float phi, float r_hi, float *out_c);
+
+/* ---- particle preprocessing: image -> prepared half spectrum n*(n/2+1) complex */
+void orc_noise_curve(const float *imgs, int count, const orc_refine_cfg *cfg, float *curve /* n+1 */);
+void orc_prepare_image(const float *img, const orc_refine_cfg *cfg, const float *noise_curve /* or NULL */,
+                       const float *ring_weights /* or NULL */, float *spec_out);
+
+/* ---- score: out4 = {numerator, signed cross, image power, projection power}; returns 100*CC */
+float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6,
+                const orc_refine_cfg *cfg, float *out4);
+
+/* ---- batched local refinement of n particles (specs: n prepared spectra).  OpenMP over
+ * particles when built with -fopenmp.  Returns number of objective evaluations. */
+long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n,
+                           const orc_refine_cfg *cfg);
+
+/* ---- reconstruction */
+orc_recon *orc_recon_create(const orc_recon_cfg *cfg);
+void orc_recon_free(orc_recon *rc);
+void orc_recon_insert(orc_recon *rc, const float *imgs, const orc_row *rows, int count,
+                      const float *sym /* n_sym*9 */, int n_sym);
+/* raw accumulators, same layout as the GPU dump: [z][y][x] float4 {re, im, w, 0}, centred y,z */
+void orc_recon_get_dump(const orc_recon *rc, int half, float *out);
+void orc_recon_finalize(orc_recon *rc, float molecular_mass_kda, float outer_radius_a, float *half1,
+                        float *half2, float *map, float *stats /* (n/2+1)*7 */);
+
+/* FSC curve between two real n^3 volumes (n/2+1 shells, nearest-integer shells) */
+void orc_fsc(const float *a, const float *b, int n, float *fsc_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,146 @@
+"""ctypes binding of libcspb200.so (include/cspb200.h).
+
+The library is the product: there is no Python / CPU fallback.  Importing this module fails
+loudly when the shared object has not been built (run ``python -c 'import __graft_entry__ as g;
+g.build()'`` or ``pyp_b200/csrc/build.sh``), and every call raises :class:`CspbError` when the
+CUDA side reports an error (for instance no sm_100 GPU).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcspb200.so")
+
+HOST, DEVICE = 0, 1
+
+# .cistem projection row — src/pyp/inout/metadata/cistem_star_file.py:596-628 (order),
+# :127-185 (types); 128 bytes, little endian.
+ROW_DTYPE = np.dtype(
+    [
+        ("position_in_stack", "<u4"),
+        ("psi", "<f4"), ("theta", "<f4"), ("phi", "<f4"),
+        ("x_shift", "<f4"), ("y_shift", "<f4"),
+        ("defocus_1", "<f4"), ("defocus_2", "<f4"), ("defocus_angle", "<f4"), ("phase_shift", "<f4"),
+        ("image_is_active", "<i4"),
+        ("occupancy", "<f4"), ("logp", "<f4"), ("sigma", "<f4"), ("score", "<f4"),
+        ("pixel_size", "<f4"), ("voltage_kv", "<f4"), ("cs_mm", "<f4"), ("amplitude_contrast", "<f4"),
+        ("beam_tilt_x", "<f4"), ("beam_tilt_y", "<f4"), ("image_shift_x", "<f4"), ("image_shift_y", "<f4"),
+        ("original_x", "<f4"), ("original_y", "<f4"),
+        ("imind", "<i4"), ("pind", "<i4"), ("tind", "<i4"), ("rind", "<i4"), ("find", "<i4"),
+        ("fshift_x", "<f4"), ("fshift_y", "<f4"),
+    ]
+)
+assert ROW_DTYPE.itemsize == 128
+
+
+class RefineCfg(C.Structure):
+    _fields_ = [
+        ("box", C.c_int32), ("pad", C.c_int32),
+        ("pixel_size", C.c_float), ("mask_radius", C.c_float),
+        ("low_res_limit", C.c_float), ("high_res_limit", C.c_float), ("signed_cc_limit", C.c_float),
+        ("search_mask_radius", C.c_float), ("search_high_res", C.c_float), ("angular_step", C.c_float),
+        ("best_matches", C.c_int32),
+        ("search_range_x", C.c_float), ("search_range_y", C.c_float),
+        ("defocus_range", C.c_float), ("defocus_step", C.c_float),
+        ("global_search", C.c_int32), ("local_refine", C.c_int32),
+        ("refine_psi", C.c_int32), ("refine_theta", C.c_int32), ("refine_phi", C.c_int32),
+        ("refine_x", C.c_int32), ("refine_y", C.c_int32), ("refine_defocus", C.c_int32),
+        ("apply_mask", C.c_int32), ("normalize", C.c_int32), ("invert_contrast", C.c_int32),
+        ("whiten", C.c_int32), ("symmetry_order", C.c_int32), ("local_iterations", C.c_int32),
+        ("reserved", C.c_int32 * 7),
+    ]
+
+
+class ReconCfg(C.Structure):
+    _fields_ = [
+        ("box", C.c_int32), ("pad", C.c_int32),
+        ("pixel_size", C.c_float), ("mask_radius", C.c_float), ("resolution_limit", C.c_float),
+        ("score_bfactor", C.c_float), ("score_weighting", C.c_int32), ("score_threshold", C.c_float),
+        ("normalize", C.c_int32), ("invert_contrast", C.c_int32), ("per_particle_split", C.c_int32),
+        ("average_score", C.c_float),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class CspbError(RuntimeError):
+    pass
+
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_SIGNATURES = {
+    "cspb_abi_version": (C.c_int, []),
+    "cspb_create": (_i, [_i, C.POINTER(_vp)]),
+    "cspb_destroy": (_i, [_vp]),
+    "cspb_last_error": (C.c_char_p, [_vp]),
+    "cspb_sync": (_i, [_vp]),
+    "cspb_stream": (_i, [_vp, C.POINTER(_vp)]),
+    "cspb_launch_count": (_i64, [_vp]),
+    "cspb_refine_cfg_default": (_i, [C.POINTER(RefineCfg), _i, _f]),
+    "cspb_refine_configure": (_i, [_vp, C.POINTER(RefineCfg)]),
+    "cspb_refine_set_ring_weights": (_i, [_vp, _vp, _i]),
+    "cspb_set_reference": (_i, [_vp, _vp, _i, _i]),
+    "cspb_set_symmetry": (_i, [_vp, _vp, _i]),
+    "cspb_refine_load_images": (_i, [_vp, _vp, _i, _i, _i]),
+    "cspb_refine_num_images": (_i, [_vp]),
+    "cspb_refine_score": (_i, [_vp, _vp, _i, _vp]),
+    "cspb_refine_score_poses": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "cspb_refine_run": (_i, [_vp, _vp, _i, _vp, C.POINTER(_i64)]),
+    "cspb_refine_run_device": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),
+    "cspb_refine_get_noise_curve": (_i, [_vp, _vp, _i]),
+    "cspb_refine_set_noise_curve": (_i, [_vp, _vp, _i]),
+    "cspb_recon_cfg_default": (_i, [C.POINTER(ReconCfg), _i, _f]),
+    "cspb_recon_begin": (_i, [_vp, C.POINTER(ReconCfg)]),
+    "cspb_recon_insert": (_i, [_vp, _vp, _vp, _i, _i]),
+    "cspb_recon_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64)]),
+    "cspb_recon_device_ptr": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "cspb_recon_get_dump": (_i, [_vp, _i, _vp, _i]),
+    "cspb_recon_add_dump": (_i, [_vp, _i, _vp, _i]),
+    "cspb_recon_finalize": (_i, [_vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i]),
+    "cspb_recon_end": (_i, [_vp]),
+    "cspb_fft2_r2c": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "cspb_fft2_c2r": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "cspb_cufft2_r2c": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "cspb_ctf_image": (_i, [_vp, _vp, _i, _vp]),
+    "cspb_project": (_i, [_vp, _f, _f, _f, _vp]),
+    "cspb_band_counts": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+}
+
+# every symbol include/cspb200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+
+def load():
+    """Load libcspb200.so and attach the prototypes.  Raises if the library is not built."""
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA engine has not been built. "
+            "Run pyp_b200/csrc/build.sh (nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load()
+    return _lib
+
+
+def ptr(a):
+    """Raw pointer of a numpy array (must be C-contiguous) or an int device pointer."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return C.c_void_p(a.ctypes.data)

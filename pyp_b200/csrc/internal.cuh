@@ -1,0 +1,159 @@
+// internal.cuh — shared declarations of libcspb200 (not part of the C-ABI).
+// Everything here is ours; the reference has no source for this path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/cspb200.h"
+
+#define CSPB_PI_F 3.14159265358979323846f
+#define CSPB_PI_D 3.14159265358979323846
+
+// ---------------------------------------------------------------- device buffer (grow-only)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    // returns false on allocation failure
+    bool reserve(size_t want) {
+        if (want <= bytes) return true;
+        release();
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return false;
+        }
+        bytes = want;
+        return true;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---------------------------------------------------------------- band plan
+// The half-plane lattice samples inside the scoring band, re-ordered into "polar patches":
+// ring-bands of 4 consecutive rings; inside a band slot = base + a*4 + k holds the a-th sample
+// (by angle) of ring ring0+k, so a warp's 32 slots are an 8(angle) x 4(ring) patch and lane%4
+// is the ring offset.  Rings are padded to a common length with dummy slots.
+#define CSPB_DUMMY_I 0x7FFF
+struct BandDesc {
+    int slot_start;  // multiple of 32
+    int n_iter;      // slots/32
+    int ring0;       // first ring of the band (4 rings per band)
+    int pad_;
+};
+struct BandPlan {
+    int n = 0;
+    float r_lo = 0, r_hi = 0;
+    int ring_min = 0, ring_max = 0;
+    int n_band = 0;   // real samples
+    int n_slots = 0;  // padded slots (multiple of 32)
+    int n_bands = 0;
+    std::vector<int32_t> slot_ij;  // i | (j << 16)
+    std::vector<BandDesc> bands;
+    DevBuf d_slot_ij, d_bands;
+};
+bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi);
+
+// ---------------------------------------------------------------- reference volume (scoring)
+// Cropped, centred (y,z shifted by +rc), x-paired Fourier half-volume:
+// ref4[(z*sy + y)*sx + x] = { V(x,y,z), V(x+1,y,z) } as float4.
+struct RefVolume {
+    int n = 0, pad = 1, np = 0;
+    int rc = 0;          // centre offset: y,z in [-rc, rc]
+    int sx = 0, sy = 0;  // sx = rc+1, sy = sz = 2rc+1
+    DevBuf d_ref4;
+    bool ready = false;
+};
+
+// per-image CTF coefficients (device): chi = s2*(a + b*(c2a*cos2ast + s2a*sin2ast)) + c4*s2*s2 + ph0
+// with s2 = (i^2+j^2) in Fourier-pixel^2 units (pixel size folded in).
+struct CtfCoef {
+    float a, b, cos2ast, sin2ast, c4, ph0, dstep, pad_;  // dstep: d(a)/d(defocus Angstrom)
+};
+
+// ---------------------------------------------------------------- context
+struct cspb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    // refine state
+    bool refine_ready = false;
+    cspb_refine_cfg rcfg{};
+    BandPlan plan;
+    RefVolume ref;
+    DevBuf d_ring_w;        // per-ring weights (n/2+1 .. n)
+    bool have_ring_w = false;
+    DevBuf d_noise;         // whitening filter 1/sqrt(P) per ring (n+1 floats)
+    std::vector<float> noise_curve;  // P(ring)
+    bool have_noise = false;
+    int n_images = 0;
+    int img_capacity = 0;
+    DevBuf d_packed;        // n_images * n_slots float2
+    std::vector<float> sym; // 9*n_sym
+    DevBuf d_sym;
+    int n_sym = 1;
+
+    // scratch
+    DevBuf d_stage, d_work0, d_work1, d_work2, d_stats, d_rows, d_evals, d_units, d_out, d_opt;
+    DevBuf d_tw;  // twiddle tables
+    std::vector<int> tw_n;      // sizes cached
+    std::vector<size_t> tw_off; // offsets (in float2)
+    size_t tw_used = 0;
+
+    // recon state
+    bool recon_ready = false;
+    cspb_recon_cfg ccfg{};
+    int rnp = 0;
+    DevBuf d_acc[2];
+    int64_t recon_inserted = 0;
+};
+
+int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...);
+
+#define CU_TRY(ctx, expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return cspb_fail(ctx, CSPB_E_CUDA, "%s failed: %s (%s:%d)", #expr,             \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define KERNEL_CHECK(ctx)                                                                  \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess)                                                             \
+            return cspb_fail(ctx, CSPB_E_CUDA, "kernel launch failed: %s (%s:%d)",         \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define RESERVE(ctx, buf, bytes_)                                                          \
+    do {                                                                                   \
+        if (!(buf).reserve(bytes_))                                                        \
+            return cspb_fail(ctx, CSPB_E_NOMEM, "device allocation of %zu bytes failed",   \
+                             (size_t)(bytes_));                                            \
+    } while (0)
+
+// ---------------------------------------------------------------- FFT (fft.cu)
+// twiddle table W_n^k = exp(-2 pi i k / n), k < n, cached per n on the device
+int fft_get_twiddles(cspb_ctx *ctx, int n, const float2 **tw_out);
+// batched 2-D R2C / C2R on device buffers; out pitch = n/2+1 complex per row
+// scale/offset: optional per-image affine applied while loading rows: v = (x - off[b]) * scl[b]
+int fft2_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int n, int batch,
+                 const float *offs, const float *scls);
+int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch);
+// 3-D R2C / C2R of an np^3 volume (in-place complex work buffer of (np/2+1)*np*np)
+int fft3_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int np);
+int fft3_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int np);
+
+// ---------------------------------------------------------------- helpers
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,78 @@
+// plan.cu — host-side builders: polar-patch band plan and ring lists.
+//
+// The band is the set of half-plane lattice points (i in [0,n/2], j in [-n/2,n/2-1]) with
+// r_lo <= sqrt(i^2+j^2) <= r_hi, r in Fourier pixels (= n*pixel/resolution), the same set
+// cisTEM's weighted correlation loops over (bin index = int(r)); SURVEY.md §8d counts it as
+// n_band.  Order is ours: ring-bands of 4 rings, angle-sorted, dummy-padded (see internal.cuh).
+#include <algorithm>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include "internal.cuh"
+
+int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi) {
+    plan.n = n;
+    plan.r_lo = r_lo;
+    plan.r_hi = r_hi;
+    plan.slot_ij.clear();
+    plan.bands.clear();
+    const int nh = n / 2;
+    const float lo2 = r_lo * r_lo, hi2 = r_hi * r_hi;
+    const int ring_min = (int)floorf(r_lo), ring_max = std::min((int)floorf(r_hi), (int)(nh * 1.5f));
+    plan.ring_min = ring_min;
+    plan.ring_max = ring_max;
+    if (ring_max < ring_min) return false;
+    std::vector<std::vector<std::pair<float, int32_t>>> rings(ring_max - ring_min + 1);
+    int n_band = 0;
+    for (int j = -nh; j < nh; ++j)
+        for (int i = 0; i <= nh; ++i) {
+            const float r2 = (float)(i * i + j * j);
+            if (r2 < lo2 || r2 > hi2) continue;
+            const int ring = (int)floorf(sqrtf(r2));
+            if (ring < ring_min || ring > ring_max) continue;
+            const float ang = atan2f((float)j, (float)i);
+            const int32_t packed = (int32_t)((uint32_t)(i & 0xFFFF) | ((uint32_t)(j & 0xFFFF) << 16));
+            rings[ring - ring_min].push_back(std::make_pair(ang, packed));
+            ++n_band;
+        }
+    plan.n_band = n_band;
+    for (auto &r : rings) std::sort(r.begin(), r.end());
+    const int32_t dummy = (int32_t)CSPB_DUMMY_I;  // i = 0x7FFF, j = 0
+    const int n_rings = ring_max - ring_min + 1;
+    int slot = 0;
+    for (int r0 = 0; r0 < n_rings; r0 += 4) {
+        size_t lmax = 0;
+        for (int k = 0; k < 4 && r0 + k < n_rings; ++k) lmax = std::max(lmax, rings[r0 + k].size());
+        if (lmax == 0) continue;
+        const int L = (int)((lmax + 7) / 8) * 8;
+        BandDesc bd;
+        bd.slot_start = slot;
+        bd.n_iter = 4 * L / 32;
+        bd.ring0 = ring_min + r0;
+        bd.pad_ = 0;
+        plan.slot_ij.resize(slot + 4 * L, dummy);
+        for (int k = 0; k < 4 && r0 + k < n_rings; ++k) {
+            const auto &r = rings[r0 + k];
+            const int nk = (int)r.size();
+            for (int m = 0; m < nk; ++m) {
+                const int a = (int)(((long long)m * L) / nk);  // spread dummies evenly along the arc
+                plan.slot_ij[slot + a * 4 + k] = r[m].second;
+            }
+        }
+        slot += 4 * L;
+        plan.bands.push_back(bd);
+    }
+    plan.n_slots = slot;
+    plan.n_bands = (int)plan.bands.size();
+    return plan.n_slots > 0;
+}

@@ -1,0 +1,1087 @@
+// refine.cu — the projection-matching scorer: reference preparation, particle preprocessing,
+// the fused central-slice x CTF x weighted-correlation kernel and the batched local optimiser.
+//
+// Replaces the numerics of external/cistem2/refine3d (closed LFS binary); the contract is the
+// stdin answer list built at src/pyp/refine/frealign/frealign.py:3918-3994 and the `.cistem`
+// rows of src/pyp/inout/metadata/cistem_star_file.py:596-628.  Semantics that the reference
+// tree cannot pin (score definition, whitening, mask) are fixed in oracle/SEMANTICS.md and
+// restated on the CPU in oracle/cspb_oracle.c, against which these kernels are tested.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "device_math.cuh"
+#include "internal.cuh"
+
+// ================================================================== reference preparation
+namespace {
+
+// real n^3 -> padded np^3 (centred, zero padded)
+__global__ void pad_volume_kernel(const float *__restrict__ vol, float *__restrict__ out, int n, int np) {
+    const long long total = (long long)np * np * np;
+    const int off = (np - n) / 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % np);
+        const int y = (int)((idx / np) % np);
+        const int z = (int)(idx / ((long long)np * np));
+        const int sx = x - off, sy = y - off, sz = z - off;
+        float v = 0.f;
+        if (sx >= 0 && sx < n && sy >= 0 && sy < n && sz >= 0 && sz < n) {
+            // pre-compensate the trilinear interpolation of the slice gather (sinc^2 per axis)
+            const float g = sinc2_corr(x - np / 2, np) * sinc2_corr(y - np / 2, np) * sinc2_corr(z - np / 2, np);
+            v = vol[((long long)sz * n + sy) * n + sx] / g;
+        }
+        out[idx] = v;
+    }
+}
+
+// FFT-ordered half spectrum [z][y][xh] -> cropped centred x-paired float4 volume
+__global__ void crop_pair_kernel(const float2 *__restrict__ spec, float4 *__restrict__ ref4, int np, int rc,
+                                 int sx, int sy) {
+    const long long total = (long long)sx * sy * sy;
+    const int xh = np / 2 + 1;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % sx);
+        const int yy = (int)((idx / sx) % sy);
+        const int zz = (int)(idx / ((long long)sx * sy));
+        const int y = yy - rc, z = zz - rc;
+        float2 v[2];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int xx = x + d;
+            float2 t = make_float2(0.f, 0.f);
+            if (xx < xh && y >= -np / 2 && y < np / 2 && z >= -np / 2 && z < np / 2) {
+                const int iy = y < 0 ? y + np : y, iz = z < 0 ? z + np : z;
+                t = spec[((long long)iz * np + iy) * xh + xx];
+                if ((xx + y + z) & 1) {  // real-space centre at np/2 -> (-1)^(x+y+z)
+                    t.x = -t.x;
+                    t.y = -t.y;
+                }
+            }
+            v[d] = t;
+        }
+        ref4[idx] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    }
+}
+
+// ================================================================== particle preprocessing
+// per-image mean / variance of the pixels outside radius R (all pixels if none are outside)
+__global__ void image_stats_kernel(const float *__restrict__ img, int n, float radius, int normalize,
+                                   int invert, float *__restrict__ offs, float *__restrict__ scls) {
+    __shared__ float red[64];
+    __shared__ float s_mean;
+    const float *p = img + (long long)blockIdx.x * n * n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float sgn = invert ? -1.f : 1.f;
+    if (!normalize) {
+        if (tid == 0) {
+            offs[blockIdx.x] = 0.f;
+            scls[blockIdx.x] = sgn;
+        }
+        return;
+    }
+    const float r2lim = radius * radius;
+    const int c = n / 2;
+    bool use_all = (radius * radius >= 2.f * c * c);
+    float s = 0.f, cnt = 0.f;
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int x = idx % n - c, y = idx / n - c;
+        if (use_all || (float)(x * x + y * y) > r2lim) {
+            s += p[idx];
+            cnt += 1.f;
+        }
+    }
+    s = block_sum(s, red);
+    cnt = block_sum(cnt, red);
+    if (tid == 0) s_mean = cnt > 0.f ? s / cnt : 0.f;
+    __syncthreads();
+    const float mean = s_mean;
+    float v = 0.f;
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int x = idx % n - c, y = idx / n - c;
+        if (use_all || (float)(x * x + y * y) > r2lim) {
+            const float d = p[idx] - mean;
+            v += d * d;
+        }
+    }
+    v = block_sum(v, red);
+    if (tid == 0) {
+        const float var = cnt > 0.f ? v / cnt : 0.f;
+        offs[blockIdx.x] = mean;
+        scls[blockIdx.x] = var > 0.f ? sgn * rsqrtf(var) : sgn;
+    }
+}
+
+// per-image ring power: one warp per ring walks a host-built CSR list of the half-plane samples
+// (deterministic order).  ring = nearest integer radius.  out[img*n_rings + ring] = sum |F|^2
+__global__ void ring_power_kernel(const float2 *__restrict__ spec, int n, const int *__restrict__ ring_off,
+                                  const int *__restrict__ ring_idx, int n_rings, float *__restrict__ out) {
+    const int nh = n / 2 + 1;
+    const float2 *f = spec + (long long)blockIdx.x * n * nh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = warp; r < n_rings; r += nw) {
+        float s = 0.f;
+        for (int k = ring_off[r] + lane; k < ring_off[r + 1]; k += 32) {
+            const float2 v = f[ring_idx[k]];
+            s += v.x * v.x + v.y * v.y;
+        }
+        s = warp_sum(s);
+        if (lane == 0) out[(long long)blockIdx.x * n_rings + r] = s;
+    }
+}
+
+__global__ void sum_over_images_kernel(const float *__restrict__ in, int n_img, int n_rings, float *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rings) return;
+    float s = 0.f;
+    for (int i = 0; i < n_img; ++i) s += in[(long long)i * n_rings + r];
+    out[r] = s;
+}
+
+// multiply a half spectrum by a radial filter indexed by nearest ring
+__global__ void radial_filter_kernel(float2 *__restrict__ spec, int n, int batch, const float *__restrict__ filt) {
+    const int nh = n / 2 + 1;
+    const long long total = (long long)batch * n * nh;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % nh);
+        int j = (int)((idx / nh) % n);
+        if (j >= n / 2) j -= n;
+        const int ring = (int)(sqrtf((float)(i * i + j * j)) + 0.5f);
+        const float w = filt[ring];
+        float2 v = spec[idx];
+        v.x *= w;
+        v.y *= w;
+        spec[idx] = v;
+    }
+}
+
+// real-space soft circular mask (cosine edge of width `width` centred on `radius`) and 1/n^2
+__global__ void mask_kernel(float *__restrict__ img, int n, int batch, float radius, float width, float scale) {
+    const long long total = (long long)batch * n * n;
+    const int c = n / 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % n) - c, y = (int)((idx / n) % n) - c;
+        const float r = sqrtf((float)(x * x + y * y));
+        img[idx] *= scale * cosine_edge(r, radius, width);
+    }
+}
+
+// band-pack: packed[img][slot] = sign(i+j) * F[img][j][i] * filt[nearest ring] * ringw[ring]
+__global__ void pack_kernel(const float2 *__restrict__ spec, int n, int n_slots, const int32_t *__restrict__ slot_ij,
+                            const float *__restrict__ filt, const float *__restrict__ ringw,
+                            float2 *__restrict__ packed) {
+    const int nh = n / 2 + 1;
+    const float2 *f = spec + (long long)blockIdx.y * n * nh;
+    float2 *o = packed + (long long)blockIdx.y * n_slots;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        const int32_t ij = slot_ij[s];
+        const int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+        float2 v = make_float2(0.f, 0.f);
+        if (i != CSPB_DUMMY_I) {
+            const int jj = j < 0 ? j + n : j;
+            v = f[jj * nh + i];
+            const float r = sqrtf((float)(i * i + j * j));
+            float w = ((i + j) & 1) ? -1.f : 1.f;
+            if (filt) w *= filt[(int)(r + 0.5f)];
+            if (ringw) w *= ringw[(int)r];
+            v.x *= w;
+            v.y *= w;
+        }
+        o[s] = v;
+    }
+}
+
+// ================================================================== CTF coefficients
+__global__ void ctf_coef_kernel(const cspb_row *__restrict__ rows, int n_rows, int box, CtfCoef *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_rows) return;
+    out[k] = make_ctf_coef(rows[k].defocus_1, rows[k].defocus_2, rows[k].defocus_angle, rows[k].phase_shift,
+                           rows[k].pixel_size, rows[k].voltage_kv, rows[k].cs_mm, rows[k].amplitude_contrast, box);
+}
+
+// ================================================================== the scorer
+struct ScoreUnit {
+    int image;       // index into packed images / ctf coefficients
+    int first_eval;  // index of the unit's first evaluation
+    int count;       // number of poses (<= PB)
+    int pad_;
+};
+
+struct ScoreArgs {
+    const float4 *ref4;
+    int sx, sy, rc;
+    float padf;
+    const int32_t *slot_ij;
+    const BandDesc *bands;
+    int n_bands;
+    int n_slots;
+    const float2 *packed;
+    const CtfCoef *ctf;
+    const ScoreUnit *units;
+    int n_units;
+    const float *poses6;  // per eval: psi, theta, phi (deg), shift x, y (Angstrom), defocus delta (Angstrom)
+    float inv_npx2;       // 2 / (n * pixel): shift (A) * frequency index -> phase in units of pi
+    int limit_ring;       // rings above use |X_r| (signed-CC limit); INT_MAX = always signed
+    float4 *out;          // per eval: {numerator, signed X total, A, B}
+};
+
+// One warp per unit = (image, up to PB poses).  Lanes walk the polar-patch band plan:
+// coalesced 8-byte reads of the packed image, CTF synthesised once per sample and shared by the
+// unit's poses, trilinear gather as 4 x 16-byte loads from the x-paired reference, per-ring sums
+// kept in one register per pose (lane%4 = ring offset inside the 4-ring band).
+template <int PB, bool DDEF>
+__global__ void __launch_bounds__(128) score_kernel(const ScoreArgs A) {
+    __shared__ float s_pose[4][PB][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = blockIdx.x * 4 + warp;
+    if (u >= A.n_units) return;
+    const ScoreUnit un = A.units[u];
+    const CtfCoef cc = A.ctf[un.image];
+    if (lane < PB) {
+        float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (lane < un.count) {
+            const float *q = A.poses6 + (long long)(un.first_eval + lane) * 6;
+            float r[9];
+            euler_matrix(q[0], q[1], q[2], r);
+            m[0] = r[0] * A.padf; m[1] = r[1] * A.padf;   // x = m00 i + m01 j
+            m[2] = r[3] * A.padf; m[3] = r[4] * A.padf;   // y = m10 i + m11 j
+            m[4] = r[6] * A.padf; m[5] = r[7] * A.padf;   // z = m20 i + m21 j
+            m[6] = q[3] * A.inv_npx2;
+            m[7] = q[4] * A.inv_npx2;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_pose[warp][lane][k] = m[k];
+    }
+    __syncwarp();
+    float ddef[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p)
+        ddef[p] = (DDEF && p < un.count) ? A.poses6[(long long)(un.first_eval + p) * 6 + 5] * cc.dstep : 0.f;
+
+    const float2 *img = A.packed + (long long)un.image * A.n_slots;
+    const long long sxy = (long long)A.sx * A.sy;
+    float accB[PB], num[PB], xs[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) accB[p] = num[p] = xs[p] = 0.f;
+    float accA = 0.f;
+
+    for (int b = 0; b < A.n_bands; ++b) {
+        const BandDesc bd = A.bands[b];
+        float accX[PB];
+#pragma unroll
+        for (int p = 0; p < PB; ++p) accX[p] = 0.f;
+        for (int it = 0; it < bd.n_iter; ++it) {
+            const int slot = bd.slot_start + it * 32 + lane;
+            const int32_t ij = __ldg(A.slot_ij + slot);
+            const float2 F = __ldg(img + slot);
+            int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+            const bool valid = (i != CSPB_DUMMY_I);
+            if (!valid) { i = 0; j = 0; }
+            const float fi = (float)i, fj = (float)j;
+            const float r2 = fi * fi + fj * fj;
+            const float chi0 = ctf_chi(cc, fi, fj, r2);
+            float ctfv = 0.f;
+            if (!DDEF) ctfv = valid ? -sinpif(chi0 * (1.f / CSPB_PI_F)) : 0.f;
+            accA += F.x * F.x + F.y * F.y;
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (p < un.count) {
+                    const float4 ma = *reinterpret_cast<const float4 *>(&s_pose[warp][p][0]);
+                    const float4 mb = *reinterpret_cast<const float4 *>(&s_pose[warp][p][4]);
+                    float x = ma.x * fi + ma.y * fj;
+                    float y = ma.z * fi + ma.w * fj;
+                    float z = mb.x * fi + mb.y * fj;
+                    const bool flip = x < 0.f;
+                    if (flip) { x = -x; y = -y; z = -z; }
+                    const float x0 = floorf(x), y0 = floorf(y), z0 = floorf(z);
+                    const float fx = x - x0, fy = y - y0, fz = z - z0;
+                    const long long idx = ((long long)((int)z0 + A.rc) * A.sy + ((int)y0 + A.rc)) * A.sx + (int)x0;
+                    const float4 a00 = __ldg(A.ref4 + idx);
+                    const float4 a10 = __ldg(A.ref4 + idx + A.sx);
+                    const float4 a01 = __ldg(A.ref4 + idx + sxy);
+                    const float4 a11 = __ldg(A.ref4 + idx + sxy + A.sx);
+                    const float v00x = a00.x + fx * (a00.z - a00.x), v00y = a00.y + fx * (a00.w - a00.y);
+                    const float v10x = a10.x + fx * (a10.z - a10.x), v10y = a10.y + fx * (a10.w - a10.y);
+                    const float v01x = a01.x + fx * (a01.z - a01.x), v01y = a01.y + fx * (a01.w - a01.y);
+                    const float v11x = a11.x + fx * (a11.z - a11.x), v11y = a11.y + fx * (a11.w - a11.y);
+                    const float v0x = v00x + fy * (v10x - v00x), v0y = v00y + fy * (v10y - v00y);
+                    const float v1x = v01x + fy * (v11x - v01x), v1y = v01y + fy * (v11y - v01y);
+                    float px = v0x + fz * (v1x - v0x), py = v0y + fz * (v1y - v0y);
+                    if (flip) py = -py;
+                    float cv = ctfv;
+                    if (DDEF) cv = valid ? -sinpif((chi0 + r2 * ddef[p]) * (1.f / CSPB_PI_F)) : 0.f;
+                    px *= cv;
+                    py *= cv;
+                    float sn, cs;
+                    sincospif(fi * mb.z + fj * mb.w, &sn, &cs);
+                    const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
+                    accX[p] += gr * px + gi * py;
+                    accB[p] += px * px + py * py;
+                }
+            }
+        }
+        const int ring = bd.ring0 + (lane & 3);
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            float v = accX[p];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 4) {
+                xs[p] += v;
+                num[p] += (ring > A.limit_ring) ? fabsf(v) : v;
+            }
+        }
+    }
+    accA = warp_sum(accA);
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        const float bsum = warp_sum(accB[p]);
+        float nv = num[p], xv = xs[p];
+        nv += __shfl_xor_sync(0xffffffffu, nv, 1);
+        nv += __shfl_xor_sync(0xffffffffu, nv, 2);
+        xv += __shfl_xor_sync(0xffffffffu, xv, 1);
+        xv += __shfl_xor_sync(0xffffffffu, xv, 2);
+        if (lane == 0 && p < un.count) A.out[un.first_eval + p] = make_float4(nv, xv, accA, bsum);
+    }
+}
+
+// central slice on the full half-plane grid (building block / test helper)
+__global__ void project_kernel(const float4 *__restrict__ ref4, int sx, int sy, int rc, float padf, int n,
+                               float r_hi, float psi, float theta, float phi, float2 *__restrict__ out) {
+    const int nh = n / 2 + 1;
+    float r[9];
+    euler_matrix(psi, theta, phi, r);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * nh; idx += gridDim.x * blockDim.x) {
+        const int i = idx % nh;
+        int j = idx / nh;
+        if (j >= n / 2) j -= n;
+        float2 v = make_float2(0.f, 0.f);
+        const float fi = (float)i, fj = (float)j;
+        if (fi * fi + fj * fj <= r_hi * r_hi) {
+            float x = (r[0] * fi + r[1] * fj) * padf, y = (r[3] * fi + r[4] * fj) * padf,
+                  z = (r[6] * fi + r[7] * fj) * padf;
+            v = gather_trilinear(ref4, sx, sy, rc, x, y, z);
+        }
+        out[idx] = v;
+    }
+}
+
+__global__ void ctf_image_kernel(CtfCoef cc, int n, float *__restrict__ out) {
+    const int nh = n / 2 + 1;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * nh; idx += gridDim.x * blockDim.x) {
+        const int i = idx % nh;
+        int j = idx / nh;
+        if (j >= n / 2) j -= n;
+        const float fi = (float)i, fj = (float)j;
+        out[idx] = -sinpif(ctf_chi(cc, fi, fj, fi * fi + fj * fj) * (1.f / CSPB_PI_F));
+    }
+}
+
+// ================================================================== batched local optimiser
+// Per image: x = {psi, theta, phi, shift x, shift y, defocus delta}, masked by `free`.
+// Every iteration = central-difference stencil (1+2M evals) -> diagonal Newton step with a
+// trust region -> 3-point line search -> keep the best point seen.  All images in lockstep.
+#define OPT_NP 6
+#define OPT_NL 3
+struct OptState {
+    float x[OPT_NP];
+    float h[OPT_NP];
+    float d[OPT_NP];
+    float f;       // current best CC
+    float f0;      // CC at entry (for the changes file)
+    float pad_;
+};
+
+__global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n, OptState *__restrict__ st, float h_ang,
+                                float h_shift, float h_def) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    OptState s;
+    s.x[0] = rows[k].psi; s.x[1] = rows[k].theta; s.x[2] = rows[k].phi;
+    s.x[3] = rows[k].x_shift; s.x[4] = rows[k].y_shift; s.x[5] = 0.f;
+    s.h[0] = s.h[1] = s.h[2] = h_ang;
+    s.h[3] = s.h[4] = h_shift;
+    s.h[5] = h_def;
+    for (int m = 0; m < OPT_NP; ++m) s.d[m] = 0.f;
+    s.f = -2.f; s.f0 = -2.f; s.pad_ = 0.f;
+    st[k] = s;
+}
+
+// free_mask bit m set -> parameter m is refined.  n_free = popcount.  evals per image NE = 1+2*n_free
+__global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int free_mask, int NE, int PB,
+                                   float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const OptState s = st[k];
+    float *q = poses6 + (long long)k * NE * 6;
+    for (int m = 0; m < OPT_NP; ++m) q[m] = s.x[m];
+    int e = 1;
+    for (int m = 0; m < OPT_NP; ++m) {
+        if (!((free_mask >> m) & 1)) continue;
+        for (int sgn = 0; sgn < 2; ++sgn, ++e) {
+            float *qe = q + e * 6;
+            for (int t = 0; t < OPT_NP; ++t) qe[t] = s.x[t];
+            qe[m] += sgn ? -s.h[m] : s.h[m];
+        }
+    }
+    const int upi = (NE + PB - 1) / PB;
+    for (int c = 0; c < upi; ++c) {
+        ScoreUnit un;
+        un.image = k;
+        un.first_eval = k * NE + c * PB;
+        un.count = min(PB, NE - c * PB);
+        un.pad_ = 0;
+        units[(long long)k * upi + c] = un;
+    }
+}
+
+__device__ __forceinline__ float cc_of(const float4 v) {
+    const float den = v.z * v.w;
+    return den > 0.f ? v.x * rsqrtf(den) : 0.f;
+}
+
+// consume stencil scores, propose the Newton direction, emit line-search poses
+__global__ void opt_step_kernel(OptState *__restrict__ st, int n, int free_mask, int NE, const float4 *__restrict__ sc,
+                                float *__restrict__ poses6_ls, ScoreUnit *__restrict__ units_ls) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    OptState s = st[k];
+    const float4 *v = sc + (long long)k * NE;
+    const float f0 = cc_of(v[0]);
+    if (s.f0 < -1.5f) s.f0 = f0;
+    float fbest = f0;
+    int ebest = 0;
+    int e = 1;
+    for (int m = 0; m < OPT_NP; ++m) {
+        s.d[m] = 0.f;
+        if (!((free_mask >> m) & 1)) continue;
+        const float fp = cc_of(v[e]), fm = cc_of(v[e + 1]);
+        if (fp > fbest) { fbest = fp; ebest = e; }
+        if (fm > fbest) { fbest = fm; ebest = e + 1; }
+        const float h = s.h[m];
+        const float g = (fp - fm) / (2.f * h);
+        const float c = (fp - 2.f * f0 + fm) / (h * h);
+        float d;
+        if (c < 0.f) d = -g / c;
+        else d = (g > 0.f ? 2.f : (g < 0.f ? -2.f : 0.f)) * h;
+        const float dmax = 4.f * h;
+        d = fminf(fmaxf(d, -dmax), dmax);
+        s.d[m] = d;
+        e += 2;
+    }
+    // if a stencil point beats the centre, move there first (keeps the best point seen)
+    if (ebest > 0) {
+        int ee = 1;
+        for (int m = 0; m < OPT_NP; ++m) {
+            if (!((free_mask >> m) & 1)) continue;
+            if (ebest == ee) { s.x[m] += s.h[m]; s.d[m] -= s.h[m]; }
+            if (ebest == ee + 1) { s.x[m] -= s.h[m]; s.d[m] += s.h[m]; }
+            ee += 2;
+        }
+    }
+    s.f = fbest;
+    st[k] = s;
+    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
+    float *q = poses6_ls + (long long)k * OPT_NL * 6;
+    for (int l = 0; l < OPT_NL; ++l)
+        for (int m = 0; m < OPT_NP; ++m) q[l * 6 + m] = s.x[m] + tl[l] * s.d[m];
+    ScoreUnit un;
+    un.image = k; un.first_eval = k * OPT_NL; un.count = OPT_NL; un.pad_ = 0;
+    units_ls[k] = un;
+}
+
+__global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4 *__restrict__ sc_ls, float shrink) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    OptState s = st[k];
+    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
+    float fbest = s.f;
+    int lbest = -1;
+    for (int l = 0; l < OPT_NL; ++l) {
+        const float f = cc_of(sc_ls[(long long)k * OPT_NL + l]);
+        if (f > fbest) { fbest = f; lbest = l; }
+    }
+    if (lbest >= 0)
+        for (int m = 0; m < OPT_NP; ++m) s.x[m] += tl[lbest] * s.d[m];
+    s.f = fbest;
+    for (int m = 0; m < OPT_NP; ++m) s.h[m] *= shrink;
+    st[k] = s;
+}
+
+// final: one more evaluation at x gives {num, xs, A, B}; write rows
+__global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, float *__restrict__ poses6,
+                                       ScoreUnit *__restrict__ units) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    for (int m = 0; m < OPT_NP; ++m) poses6[(long long)k * 6 + m] = st[k].x[m];
+    ScoreUnit un;
+    un.image = k; un.first_eval = k; un.count = 1; un.pad_ = 0;
+    units[k] = un;
+}
+
+__device__ __forceinline__ float wrap360(float a) {
+    a = fmodf(a, 360.f);
+    if (a < 0.f) a += 360.f;
+    return a;
+}
+
+__global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n, const float4 *__restrict__ sc,
+                                      int n_samples, int refine_defocus, cspb_row *__restrict__ rows,
+                                      cspb_row *__restrict__ changes) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const OptState s = st[k];
+    cspb_row r = rows[k];
+    const cspb_row old = r;
+    r.psi = wrap360(s.x[0]);
+    r.theta = s.x[1];
+    r.phi = wrap360(s.x[2]);
+    r.x_shift = s.x[3];
+    r.y_shift = s.x[4];
+    if (refine_defocus) {
+        r.defocus_1 += s.x[5];
+        r.defocus_2 += s.x[5];
+    }
+    const float4 v = sc[k];
+    float sigma, logp;
+    score_stats(v, n_samples, &sigma, &logp);
+    r.score = 100.f * cc_of(v);
+    r.sigma = sigma;
+    r.logp = logp;
+    rows[k] = r;
+    if (changes) {
+        cspb_row c = r;
+        c.psi = r.psi - old.psi; c.theta = r.theta - old.theta; c.phi = r.phi - old.phi;
+        c.x_shift = r.x_shift - old.x_shift; c.y_shift = r.y_shift - old.y_shift;
+        c.defocus_1 = r.defocus_1 - old.defocus_1; c.defocus_2 = r.defocus_2 - old.defocus_2;
+        c.score = r.score - 100.f * s.f0;
+        c.logp = r.logp - old.logp; c.sigma = r.sigma - old.sigma;
+        changes[k] = c;
+    }
+}
+
+__global__ void scores_from_out_kernel(const float4 *__restrict__ sc, int n, float *__restrict__ scores) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) scores[k] = 100.f * cc_of(sc[k]);
+}
+
+// build units from an image-sorted eval list: consecutive evals of one image, <= PB per unit
+int build_units_host(const int32_t *image_index, int n_evals, int PB, std::vector<ScoreUnit> &units) {
+    units.clear();
+    int e = 0;
+    while (e < n_evals) {
+        int c = 1;
+        while (c < PB && e + c < n_evals && image_index[e + c] == image_index[e]) ++c;
+        ScoreUnit un;
+        un.image = image_index[e]; un.first_eval = e; un.count = c; un.pad_ = 0;
+        units.push_back(un);
+        e += c;
+    }
+    return (int)units.size();
+}
+
+int grid_for(long long total, int block, int sm) {
+    long long g = (total + block - 1) / block;
+    const long long cap = (long long)sm * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, const float *d_poses6,
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef) {
+    if (n_units <= 0) return 0;
+    ScoreArgs a;
+    a.ref4 = ctx->ref.d_ref4.as<float4>();
+    a.sx = ctx->ref.sx; a.sy = ctx->ref.sy; a.rc = ctx->ref.rc;
+    a.padf = (float)ctx->ref.pad;
+    a.slot_ij = ctx->plan.d_slot_ij.as<int32_t>();
+    a.bands = ctx->plan.d_bands.as<BandDesc>();
+    a.n_bands = ctx->plan.n_bands;
+    a.n_slots = ctx->plan.n_slots;
+    a.packed = ctx->d_packed.as<float2>();
+    a.ctf = d_ctf;
+    a.units = d_units;
+    a.n_units = n_units;
+    a.poses6 = d_poses6;
+    a.inv_npx2 = 2.f / ((float)ctx->rcfg.box * ctx->rcfg.pixel_size);
+    const float lim = ctx->rcfg.signed_cc_limit;
+    a.limit_ring = lim > 0.f ? (int)floorf((float)ctx->rcfg.box * ctx->rcfg.pixel_size / lim) : 0x7fffffff;
+    a.out = d_out;
+    const int grid = ceil_div(n_units, 4);
+    if (PB == 1) {
+        if (ddef) score_kernel<1, true><<<grid, 128, 0, ctx->stream>>>(a);
+        else score_kernel<1, false><<<grid, 128, 0, ctx->stream>>>(a);
+    } else {
+        if (ddef) score_kernel<4, true><<<grid, 128, 0, ctx->stream>>>(a);
+        else score_kernel<4, false><<<grid, 128, 0, ctx->stream>>>(a);
+    }
+    KERNEL_CHECK(ctx);
+    return 0;
+}
+
+// nearest-ring CSR of the full half plane (for the noise power curve)
+void build_ring_csr(int n, std::vector<int> &off, std::vector<int> &idx, std::vector<int> &count) {
+    const int nh = n / 2 + 1, n_rings = n + 1;
+    count.assign(n_rings, 0);
+    std::vector<int> ring_of((size_t)n * nh);
+    for (int jj = 0; jj < n; ++jj)
+        for (int i = 0; i < nh; ++i) {
+            const int j = jj >= n / 2 ? jj - n : jj;
+            const int r = (int)(sqrtf((float)(i * i + j * j)) + 0.5f);
+            ring_of[(size_t)jj * nh + i] = r;
+            count[r]++;
+        }
+    off.assign(n_rings + 1, 0);
+    for (int r = 0; r < n_rings; ++r) off[r + 1] = off[r] + count[r];
+    idx.resize((size_t)n * nh);
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for (size_t k = 0; k < ring_of.size(); ++k) idx[cur[ring_of[k]]++] = (int)k;
+}
+
+}  // namespace
+
+// ================================================================== C-ABI: refine
+extern "C" int cspb_refine_cfg_default(cspb_refine_cfg *cfg, int box, float pixel_size) {
+    if (!cfg || box <= 0 || pixel_size <= 0.f) return CSPB_E_ARG;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->box = box;
+    cfg->pad = 1;
+    cfg->pixel_size = pixel_size;
+    cfg->mask_radius = 0.375f * box * pixel_size;
+    cfg->low_res_limit = 100.f;   // config/pyp_config.toml refine.rlref default
+    cfg->high_res_limit = 2.5f * pixel_size;
+    cfg->signed_cc_limit = 30.f;  // frealign.py:3879
+    cfg->search_mask_radius = 1.5f * cfg->mask_radius;
+    cfg->search_high_res = 8.f * pixel_size;
+    cfg->angular_step = 20.f;
+    cfg->best_matches = 20;
+    cfg->search_range_x = cfg->search_range_y = 0.125f * box * pixel_size;
+    cfg->defocus_range = 500.f;
+    cfg->defocus_step = 50.f;
+    cfg->global_search = 0;
+    cfg->local_refine = 1;
+    cfg->refine_psi = cfg->refine_theta = cfg->refine_phi = cfg->refine_x = cfg->refine_y = 1;
+    cfg->refine_defocus = 0;
+    cfg->apply_mask = 1;
+    cfg->normalize = 1;
+    cfg->invert_contrast = 0;
+    cfg->whiten = 1;
+    cfg->symmetry_order = 1;
+    cfg->local_iterations = 6;
+    return 0;
+}
+
+extern "C" int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg) {
+    if (!ctx || !cfg) return CSPB_E_ARG;
+    if (cfg->box < 16 || (cfg->box & 1) || cfg->pixel_size <= 0.f || (cfg->pad != 1 && cfg->pad != 2))
+        return cspb_fail(ctx, CSPB_E_ARG, "bad box/pixel/pad");
+    if (cfg->high_res_limit <= 0.f || cfg->low_res_limit <= cfg->high_res_limit)
+        return cspb_fail(ctx, CSPB_E_ARG, "need low_res_limit > high_res_limit > 0");
+    ctx->rcfg = *cfg;
+    const float npx = (float)cfg->box * cfg->pixel_size;
+    float r_lo = npx / cfg->low_res_limit, r_hi = npx / cfg->high_res_limit;
+    const float r_cap = (float)(cfg->box / 2 - 2);  // keep every trilinear corner below Nyquist
+    if (r_hi > r_cap) r_hi = r_cap;
+    if (!build_band_plan(ctx->plan, cfg->box, r_lo, r_hi)) return cspb_fail(ctx, CSPB_E_ARG, "empty band");
+    BandPlan &pl = ctx->plan;
+    RESERVE(ctx, pl.d_slot_ij, pl.slot_ij.size() * sizeof(int32_t));
+    RESERVE(ctx, pl.d_bands, pl.bands.size() * sizeof(BandDesc));
+    CU_TRY(ctx, cudaMemcpyAsync(pl.d_slot_ij.p, pl.slot_ij.data(), pl.slot_ij.size() * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pl.d_bands.p, pl.bands.data(), pl.bands.size() * sizeof(BandDesc),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->refine_ready = true;
+    ctx->ref.ready = false;
+    ctx->n_images = 0;
+    ctx->have_noise = false;
+    ctx->have_ring_w = false;
+    return 0;
+}
+
+extern "C" int cspb_band_counts(const cspb_ctx *ctx, int *n_band, int *n_slots) {
+    if (!ctx || !ctx->refine_ready) return CSPB_E_STATE;
+    if (n_band) *n_band = ctx->plan.n_band;
+    if (n_slots) *n_slots = ctx->plan.n_slots;
+    return 0;
+}
+
+extern "C" int cspb_refine_set_ring_weights(cspb_ctx *ctx, const float *w, int n_rings) {
+    if (!ctx || !ctx->refine_ready) return CSPB_E_STATE;
+    if (!w) { ctx->have_ring_w = false; return 0; }
+    const int need = ctx->rcfg.box + 1;
+    std::vector<float> h(need, 0.f);
+    for (int i = 0; i < need; ++i) h[i] = i < n_rings ? w[i] : (n_rings > 0 ? w[n_rings - 1] : 1.f);
+    RESERVE(ctx, ctx->d_ring_w, need * sizeof(float));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_ring_w.p, h.data(), need * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_ring_w = true;
+    return 0;
+}
+
+extern "C" int cspb_set_symmetry(cspb_ctx *ctx, const float *mats, int n_mats) {
+    if (!ctx || !mats || n_mats < 1) return CSPB_E_ARG;
+    ctx->sym.assign(mats, mats + 9 * (size_t)n_mats);
+    ctx->n_sym = n_mats;
+    RESERVE(ctx, ctx->d_sym, ctx->sym.size() * sizeof(float));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_sym.p, ctx->sym.data(), ctx->sym.size() * sizeof(float),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cspb_set_reference(cspb_ctx *ctx, const float *vol, int n, int loc) {
+    if (!ctx || !vol) return CSPB_E_ARG;
+    if (!ctx->refine_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_refine_configure first");
+    if (n != ctx->rcfg.box) return cspb_fail(ctx, CSPB_E_ARG, "reference edge %d != box %d", n, ctx->rcfg.box);
+    RefVolume &rv = ctx->ref;
+    rv.n = n;
+    rv.pad = ctx->rcfg.pad;
+    rv.np = n * rv.pad;
+    const int np = rv.np, xh = np / 2 + 1;
+    rv.rc = (int)ceilf(rv.pad * ctx->plan.r_hi) + 2;
+    rv.sx = rv.rc + 1;
+    rv.sy = 2 * rv.rc + 1;
+    const size_t vol_bytes = (size_t)n * n * n * sizeof(float);
+    const float *d_vol = vol;
+    if (loc == CSPB_HOST) {
+        RESERVE(ctx, ctx->d_stage, vol_bytes);
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage.p, vol, vol_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_vol = ctx->d_stage.as<float>();
+    }
+    RESERVE(ctx, ctx->d_work0, (size_t)np * np * np * sizeof(float));
+    RESERVE(ctx, ctx->d_work1, (size_t)xh * np * np * sizeof(float2));
+    pad_volume_kernel<<<grid_for((long long)np * np * np, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        d_vol, ctx->d_work0.as<float>(), n, np);
+    KERNEL_CHECK(ctx);
+    int rc = fft3_r2c_dev(ctx, ctx->d_work0.as<float>(), ctx->d_work1.as<float2>(), np);
+    if (rc) return rc;
+    const size_t ref_bytes = (size_t)rv.sx * rv.sy * rv.sy * sizeof(float4);
+    RESERVE(ctx, rv.d_ref4, ref_bytes);
+    crop_pair_kernel<<<grid_for((long long)rv.sx * rv.sy * rv.sy, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        ctx->d_work1.as<float2>(), rv.d_ref4.as<float4>(), np, rv.rc, rv.sx, rv.sy);
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    rv.ready = true;
+    return 0;
+}
+
+// FFT a chunk of images held on the device into d_work1 (half spectra), optionally estimating
+// the noise curve.  Returns device pointer of the spectra.
+static int preprocess_chunk(cspb_ctx *ctx, const float *d_img, int count, float2 **spec_out) {
+    const cspb_refine_cfg &c = ctx->rcfg;
+    const int n = c.box, nh = n / 2 + 1;
+    RESERVE(ctx, ctx->d_stats, (size_t)2 * count * sizeof(float));
+    float *offs = ctx->d_stats.as<float>(), *scls = offs + count;
+    image_stats_kernel<<<count, 256, 0, ctx->stream>>>(d_img, n, c.mask_radius / c.pixel_size, c.normalize,
+                                                       c.invert_contrast, offs, scls);
+    KERNEL_CHECK(ctx);
+    RESERVE(ctx, ctx->d_work1, (size_t)count * n * nh * sizeof(float2));
+    float2 *spec = ctx->d_work1.as<float2>();
+    int rc = fft2_r2c_dev(ctx, d_img, spec, n, count, offs, scls);
+    if (rc) return rc;
+    *spec_out = spec;
+    return 0;
+}
+
+static int estimate_noise_from_spectra(cspb_ctx *ctx, const float2 *spec, int count) {
+    const int n = ctx->rcfg.box, n_rings = n + 1;
+    std::vector<int> off, idx, cnt;
+    build_ring_csr(n, off, idx, cnt);
+    DevBuf d_off, d_idx;
+    RESERVE(ctx, d_off, off.size() * sizeof(int));
+    RESERVE(ctx, d_idx, idx.size() * sizeof(int));
+    CU_TRY(ctx, cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int step = count > 1024 ? count / 1024 : 1;
+    const int n_s = (count + step - 1) / step;
+    // sample every `step`-th image: gather pointers by launching per sampled image
+    RESERVE(ctx, ctx->d_work2, ((size_t)n_s * n_rings + n_rings) * sizeof(float));
+    float *per = ctx->d_work2.as<float>();
+    const int nh = n / 2 + 1;
+    for (int s = 0; s < n_s; ++s) {
+        ring_power_kernel<<<1, 256, 0, ctx->stream>>>(spec + (long long)s * step * n * nh, n, d_off.as<int>(),
+                                                      d_idx.as<int>(), n_rings, per + (long long)s * n_rings);
+        KERNEL_CHECK(ctx);
+    }
+    float *tot = per + (long long)n_s * n_rings;
+    sum_over_images_kernel<<<ceil_div(n_rings, 128), 128, 0, ctx->stream>>>(per, n_s, n_rings, tot);
+    KERNEL_CHECK(ctx);
+    std::vector<float> h(n_rings);
+    CU_TRY(ctx, cudaMemcpyAsync(h.data(), tot, n_rings * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->noise_curve.assign(n_rings, 0.f);
+    for (int r = 0; r < n_rings; ++r)
+        ctx->noise_curve[r] = cnt[r] > 0 ? h[r] / ((float)cnt[r] * (float)n_s) : 0.f;
+    return cspb_refine_set_noise_curve(ctx, ctx->noise_curve.data(), n_rings);
+}
+
+extern "C" int cspb_refine_set_noise_curve(cspb_ctx *ctx, const float *curve, int n_rings) {
+    if (!ctx || !ctx->refine_ready) return CSPB_E_STATE;
+    const int need = ctx->rcfg.box + 1;
+    if (!curve || n_rings != need) return cspb_fail(ctx, CSPB_E_ARG, "noise curve needs box+1 = %d rings", need);
+    ctx->noise_curve.assign(curve, curve + need);
+    std::vector<float> filt(need);
+    for (int r = 0; r < need; ++r) filt[r] = curve[r] > 0.f ? 1.f / sqrtf(curve[r]) : 0.f;
+    RESERVE(ctx, ctx->d_noise, need * sizeof(float));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_noise.p, filt.data(), need * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_noise = true;
+    return 0;
+}
+
+extern "C" int cspb_refine_get_noise_curve(cspb_ctx *ctx, float *curve_out, int n_rings) {
+    if (!ctx || !ctx->refine_ready || !ctx->have_noise) return CSPB_E_STATE;
+    if (!curve_out || n_rings != ctx->rcfg.box + 1) return CSPB_E_ARG;
+    memcpy(curve_out, ctx->noise_curve.data(), n_rings * sizeof(float));
+    return 0;
+}
+
+extern "C" int cspb_refine_num_images(const cspb_ctx *ctx) { return ctx ? ctx->n_images : 0; }
+
+extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n_images, int loc, int append) {
+    if (!ctx || !images || n_images < 0) return CSPB_E_ARG;
+    if (!ctx->refine_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_refine_configure first");
+    const cspb_refine_cfg &c = ctx->rcfg;
+    const int n = c.box, nh = n / 2 + 1, n_slots = ctx->plan.n_slots;
+    const int base = append ? ctx->n_images : 0;
+    const int total = base + n_images;
+    if (total > ctx->img_capacity) {
+        const int cap = append ? (total * 3 / 2 > 1024 ? total * 3 / 2 : 1024) : total;
+        DevBuf nb;
+        RESERVE(ctx, nb, (size_t)cap * n_slots * sizeof(float2));
+        if (base > 0)
+            CU_TRY(ctx, cudaMemcpyAsync(nb.p, ctx->d_packed.p, (size_t)base * n_slots * sizeof(float2),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d_packed.release();
+        ctx->d_packed.p = nb.p;
+        ctx->d_packed.bytes = nb.bytes;
+        nb.p = nullptr;
+        nb.bytes = 0;
+        ctx->img_capacity = cap;
+    }
+    // chunk so that the spectra + staging stay bounded (~1 GB)
+    const size_t per_img = (size_t)n * n * 4 + (size_t)n * nh * 8;
+    int chunk = (int)((size_t)1 << 30) / (int)per_img;
+    if (chunk < 1) chunk = 1;
+    if (chunk > 8192) chunk = 8192;
+    for (int s = 0; s < n_images; s += chunk) {
+        const int cnt = n_images - s < chunk ? n_images - s : chunk;
+        const float *d_img = images + (size_t)s * n * n;
+        if (loc == CSPB_HOST) {
+            RESERVE(ctx, ctx->d_stage, (size_t)chunk * n * n * sizeof(float));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage.p, d_img, (size_t)cnt * n * n * sizeof(float),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+            d_img = ctx->d_stage.as<float>();
+        }
+        float2 *spec;
+        int rc = preprocess_chunk(ctx, d_img, cnt, &spec);
+        if (rc) return rc;
+        if (c.whiten && !ctx->have_noise) {
+            rc = estimate_noise_from_spectra(ctx, spec, cnt);
+            if (rc) return rc;
+        }
+        const float *filt = c.whiten ? ctx->d_noise.as<float>() : nullptr;
+        const long long tot_c = (long long)cnt * n * nh;
+        if (c.apply_mask) {
+            if (filt) {
+                radial_filter_kernel<<<grid_for(tot_c, 256, ctx->sm_count), 256, 0, ctx->stream>>>(spec, n, cnt, filt);
+                KERNEL_CHECK(ctx);
+            }
+            RESERVE(ctx, ctx->d_work0, (size_t)cnt * n * n * sizeof(float));
+            float *real = ctx->d_work0.as<float>();
+            rc = fft2_c2r_dev(ctx, spec, real, n, cnt);
+            if (rc) return rc;
+            mask_kernel<<<grid_for((long long)cnt * n * n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+                real, n, cnt, c.mask_radius / c.pixel_size, 20.f / c.pixel_size, 1.f / ((float)n * (float)n));
+            KERNEL_CHECK(ctx);
+            rc = fft2_r2c_dev(ctx, real, spec, n, cnt, nullptr, nullptr);
+            if (rc) return rc;
+            filt = nullptr;
+        }
+        dim3 grid(ceil_div(n_slots, 256), cnt);
+        pack_kernel<<<grid, 256, 0, ctx->stream>>>(spec, n, n_slots, ctx->plan.d_slot_ij.as<int32_t>(), filt,
+                                                   ctx->have_ring_w ? ctx->d_ring_w.as<float>() : nullptr,
+                                                   ctx->d_packed.as<float2>() + (size_t)(base + s) * n_slots);
+        KERNEL_CHECK(ctx);
+        if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+    }
+    ctx->n_images = total;
+    return 0;
+}
+
+static int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, CtfCoef **d_ctf) {
+    RESERVE(ctx, ctx->d_rows, (size_t)n * (sizeof(cspb_row) + sizeof(CtfCoef)));
+    *d_rows = ctx->d_rows.as<cspb_row>();
+    *d_ctf = reinterpret_cast<CtfCoef *>(*d_rows + n);
+    CU_TRY(ctx, cudaMemcpyAsync(*d_rows, rows, (size_t)n * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
+    ctf_coef_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(*d_rows, n, ctx->rcfg.box, *d_ctf);
+    KERNEL_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int n_rows, const int32_t *image_index,
+                                       const float *poses6, int n_evals, float *scores_out) {
+    if (!ctx || !rows || !image_index || !poses6 || !scores_out || n_evals < 0) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (n_rows != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n_rows, ctx->n_images);
+    for (int e = 0; e < n_evals; ++e)
+        if (image_index[e] < 0 || image_index[e] >= n_rows) return cspb_fail(ctx, CSPB_E_ARG, "image index out of range");
+    if (n_evals == 0) return 0;
+    cspb_row *d_rows;
+    CtfCoef *d_ctf;
+    int rc = upload_rows(ctx, rows, n_rows, &d_rows, &d_ctf);
+    if (rc) return rc;
+    std::vector<ScoreUnit> units;
+    bool ddef = false;
+    for (int e = 0; e < n_evals && !ddef; ++e) ddef = poses6[(size_t)e * 6 + 5] != 0.f;
+    const int PB = (n_evals >= 2 * n_rows) ? 4 : 1;
+    const int n_units = build_units_host(image_index, n_evals, PB, units);
+    RESERVE(ctx, ctx->d_evals, (size_t)n_evals * 6 * sizeof(float));
+    RESERVE(ctx, ctx->d_units, (size_t)n_units * sizeof(ScoreUnit));
+    RESERVE(ctx, ctx->d_out, (size_t)n_evals * (sizeof(float4) + sizeof(float)));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_evals.p, poses6, (size_t)n_evals * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), (size_t)n_units * sizeof(ScoreUnit), cudaMemcpyHostToDevice, ctx->stream));
+    float4 *d_out = ctx->d_out.as<float4>();
+    float *d_sc = reinterpret_cast<float *>(d_out + n_evals);
+    rc = launch_score(ctx, ctx->d_units.as<ScoreUnit>(), n_units, PB, ctx->d_evals.as<float>(), d_ctf, d_out, ddef);
+    if (rc) return rc;
+    scores_from_out_kernel<<<ceil_div(n_evals, 256), 256, 0, ctx->stream>>>(d_out, n_evals, d_sc);
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaMemcpyAsync(scores_out, d_sc, (size_t)n_evals * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, float *scores_out) {
+    if (!ctx || !rows || !scores_out || n < 0) return CSPB_E_ARG;
+    std::vector<int32_t> idx(n);
+    std::vector<float> poses((size_t)n * 6);
+    for (int k = 0; k < n; ++k) {
+        idx[k] = k;
+        float *q = &poses[(size_t)k * 6];
+        q[0] = rows[k].psi; q[1] = rows[k].theta; q[2] = rows[k].phi;
+        q[3] = rows[k].x_shift; q[4] = rows[k].y_shift; q[5] = 0.f;
+    }
+    return cspb_refine_score_poses(ctx, rows, n, idx.data(), poses.data(), n, scores_out);
+}
+
+// enqueue the whole local refinement on the stream; rows/ctf already on the device
+static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_ctf, int n, cspb_row *d_changes,
+                                int64_t *n_evals_out) {
+    const cspb_refine_cfg &c = ctx->rcfg;
+    int free_mask = 0;
+    if (c.refine_psi) free_mask |= 1;
+    if (c.refine_theta) free_mask |= 2;
+    if (c.refine_phi) free_mask |= 4;
+    if (c.refine_x) free_mask |= 8;
+    if (c.refine_y) free_mask |= 16;
+    if (c.refine_defocus) free_mask |= 32;
+    int n_free = 0;
+    for (int m = 0; m < OPT_NP; ++m) n_free += (free_mask >> m) & 1;
+    const int NE = 1 + 2 * n_free, PB = 4;
+    const int upi = (NE + PB - 1) / PB;
+    const bool ddef = c.refine_defocus != 0;
+    const int iters = (c.local_refine && n_free > 0) ? (c.local_iterations > 0 ? c.local_iterations : 6) : 0;
+    RESERVE(ctx, ctx->d_opt, (size_t)n * sizeof(OptState));
+    RESERVE(ctx, ctx->d_evals, (size_t)n * (NE + OPT_NL) * 6 * sizeof(float));
+    RESERVE(ctx, ctx->d_units, (size_t)n * (upi + 1) * sizeof(ScoreUnit));
+    RESERVE(ctx, ctx->d_out, (size_t)n * (NE + OPT_NL) * sizeof(float4));
+    OptState *st = ctx->d_opt.as<OptState>();
+    float *ev = ctx->d_evals.as<float>(), *ev_ls = ev + (size_t)n * NE * 6;
+    ScoreUnit *un = ctx->d_units.as<ScoreUnit>(), *un_ls = un + (size_t)n * upi;
+    float4 *out = ctx->d_out.as<float4>(), *out_ls = out + (size_t)n * NE;
+    const float r_hi = ctx->plan.r_hi;
+    const float h_ang = 0.5f * 57.29578f / r_hi;                       // half the angular resolution at r_hi
+    const float h_shift = 0.1f * (float)c.box / r_hi * c.pixel_size;   // Angstrom
+    const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
+    const int g = ceil_div(n, 128);
+    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, n, st, h_ang, h_shift, h_def);
+    KERNEL_CHECK(ctx);
+    int64_t evals = 0;
+    for (int it = 0; it < iters; ++it) {
+        opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, n, free_mask, NE, PB, ev, un);
+        KERNEL_CHECK(ctx);
+        int rc = launch_score(ctx, un, n * upi, PB, ev, d_ctf, out, ddef);
+        if (rc) return rc;
+        opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, n, free_mask, NE, out, ev_ls, un_ls);
+        KERNEL_CHECK(ctx);
+        rc = launch_score(ctx, un_ls, n, PB, ev_ls, d_ctf, out_ls, ddef);
+        if (rc) return rc;
+        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out_ls, 0.6f);
+        KERNEL_CHECK(ctx);
+        evals += (int64_t)n * (NE + OPT_NL);
+    }
+    opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, n, ev, un);
+    KERNEL_CHECK(ctx);
+    int rc = launch_score(ctx, un, n, 1, ev, d_ctf, out, ddef);
+    if (rc) return rc;
+    evals += n;
+    opt_write_rows_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes);
+    KERNEL_CHECK(ctx);
+    if (n_evals_out) *n_evals_out = evals;
+    return 0;
+}
+
+extern "C" int cspb_refine_run_device(cspb_ctx *ctx, cspb_row *rows_dev, int n, int64_t *n_evals_out) {
+    if (!ctx || !rows_dev) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (n != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n, ctx->n_images);
+    RESERVE(ctx, ctx->d_rows, (size_t)n * (sizeof(cspb_row) + sizeof(CtfCoef)));
+    CtfCoef *d_ctf = reinterpret_cast<CtfCoef *>(ctx->d_rows.as<cspb_row>() + n);
+    ctf_coef_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(rows_dev, n, ctx->rcfg.box, d_ctf);
+    KERNEL_CHECK(ctx);
+    return refine_local_enqueue(ctx, rows_dev, d_ctf, n, nullptr, n_evals_out);
+}
+
+extern "C" int cspb_refine_run(cspb_ctx *ctx, cspb_row *rows, int n, cspb_row *changes_out, int64_t *n_evals_out) {
+    if (!ctx || !rows) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (n != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n, ctx->n_images);
+    if (n == 0) { if (n_evals_out) *n_evals_out = 0; return 0; }
+    cspb_row *d_rows;
+    CtfCoef *d_ctf;
+    int rc = upload_rows(ctx, rows, n, &d_rows, &d_ctf);
+    if (rc) return rc;
+    DevBuf d_chg;
+    if (changes_out) RESERVE(ctx, d_chg, (size_t)n * sizeof(cspb_row));
+    rc = refine_local_enqueue(ctx, d_rows, d_ctf, n, changes_out ? d_chg.as<cspb_row>() : nullptr, n_evals_out);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(rows, d_rows, (size_t)n * sizeof(cspb_row), cudaMemcpyDeviceToHost, ctx->stream));
+    if (changes_out)
+        CU_TRY(ctx, cudaMemcpyAsync(changes_out, d_chg.p, (size_t)n * sizeof(cspb_row), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ================================================================== building blocks
+extern "C" int cspb_ctf_image(cspb_ctx *ctx, const cspb_row *row, int n, float *out) {
+    if (!ctx || !row || !out || n < 2) return CSPB_E_ARG;
+    const int nh = n / 2 + 1;
+    RESERVE(ctx, ctx->d_work2, (size_t)n * nh * sizeof(float));
+    const CtfCoef cc = make_ctf_coef(row->defocus_1, row->defocus_2, row->defocus_angle, row->phase_shift,
+                                     row->pixel_size, row->voltage_kv, row->cs_mm, row->amplitude_contrast, n);
+    ctf_image_kernel<<<grid_for((long long)n * nh, 256, ctx->sm_count), 256, 0, ctx->stream>>>(cc, n, ctx->d_work2.as<float>());
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_work2.p, (size_t)n * nh * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cspb_project(cspb_ctx *ctx, float psi, float theta, float phi, float *out_complex) {
+    if (!ctx || !out_complex) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    const int n = ctx->rcfg.box, nh = n / 2 + 1;
+    RESERVE(ctx, ctx->d_work2, (size_t)n * nh * sizeof(float2));
+    project_kernel<<<grid_for((long long)n * nh, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        ctx->ref.d_ref4.as<float4>(), ctx->ref.sx, ctx->ref.sy, ctx->ref.rc, (float)ctx->ref.pad, n, ctx->plan.r_hi,
+        psi, theta, phi, ctx->d_work2.as<float2>());
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaMemcpyAsync(out_complex, ctx->d_work2.p, (size_t)n * nh * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

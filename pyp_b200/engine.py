@@ -1,0 +1,268 @@
+"""Python face of the C-ABI (include/cspb200.h): one :class:`Engine` = one GPU context.
+
+This is the host-side mirror of what the reference reaches by spawning
+``external/cistem2/{refine3d,reconstruct3d,local_merge3d,merge3d}``
+(src/pyp/refine/frealign/frealign.py:3918-3994, 1780-1824, 1878-1888, 2075-2093): same
+parameter tables (``.cistem`` rows as a numpy structured array, :data:`ROW_DTYPE`), same image
+stacks (MRC mode-2 payload as float32 arrays), the numerics done by hand-written sm_100a kernels.
+No CPU fallback exists; without the CUDA library / a B200 every call raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DEVICE, HOST, ROW_DTYPE, CspbError, ReconCfg, RefineCfg, ptr
+from .symmetry import symmetry_matrices
+
+__all__ = ["Engine", "ROW_DTYPE", "RefineCfg", "ReconCfg", "CspbError", "HOST", "DEVICE", "new_rows"]
+
+
+def new_rows(n, pixel_size=1.0, voltage_kv=300.0, cs_mm=2.7, amplitude_contrast=0.07):
+    """Fresh projection rows with the defaults pyp writes for new SPA particles
+    (src/pyp/inout/metadata/core.py:1352-1374: angles/shifts 0, OCC 100, SIGMA 0.5, SCORE 0.5)."""
+    rows = np.zeros(n, dtype=ROW_DTYPE)
+    rows["position_in_stack"] = np.arange(1, n + 1, dtype=np.uint32)
+    rows["occupancy"] = 100.0
+    rows["sigma"] = 0.5
+    rows["score"] = 0.5
+    rows["pixel_size"] = pixel_size
+    rows["voltage_kv"] = voltage_kv
+    rows["cs_mm"] = cs_mm
+    rows["amplitude_contrast"] = amplitude_contrast
+    rows["image_is_active"] = 1
+    return rows
+
+
+def _loc_ptr(a):
+    """(pointer, location) of a numpy array (host) or torch CUDA tensor (device)."""
+    if isinstance(a, np.ndarray):
+        return ptr(np.ascontiguousarray(a)), HOST
+    if hasattr(a, "data_ptr"):  # torch tensor
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr()), (DEVICE if a.is_cuda else HOST)
+    raise TypeError(type(a))
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._l = _lib.lib()
+        h = C.c_void_p()
+        rc = self._l.cspb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise CspbError(
+                f"cspb_create(device={device}) failed with {rc}: no usable sm_100 GPU "
+                "(libcspb200 has no CPU fallback)"
+            )
+        self._h = h
+        self.device = int(device)
+        self.box = None
+        self._keep = []  # host arrays that must outlive async calls
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.cspb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._l.cspb_last_error(self._h)
+            raise CspbError(f"libcspb200 error {rc}: {msg.decode() if msg else ''}")
+
+    def sync(self):
+        self._ck(self._l.cspb_sync(self._h))
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        self._ck(self._l.cspb_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def launches(self):
+        return int(self._l.cspb_launch_count(self._h))
+
+    # ------------------------------------------------------------------ refine3d
+    @staticmethod
+    def refine_defaults(box, pixel_size):
+        cfg = RefineCfg()
+        rc = _lib.lib().cspb_refine_cfg_default(C.byref(cfg), int(box), float(pixel_size))
+        if rc != 0:
+            raise CspbError(f"cspb_refine_cfg_default failed: {rc}")
+        return cfg
+
+    def refine_configure(self, cfg: RefineCfg):
+        self._ck(self._l.cspb_refine_configure(self._h, C.byref(cfg)))
+        self.box = cfg.box
+        self.rcfg = cfg
+
+    def band_counts(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self._l.cspb_band_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_reference(self, vol):
+        p, loc = _loc_ptr(vol if not isinstance(vol, np.ndarray) else np.ascontiguousarray(vol, dtype=np.float32))
+        n = vol.shape[0]
+        assert tuple(vol.shape) == (n, n, n)
+        self._ck(self._l.cspb_set_reference(self._h, p, n, loc))
+
+    def set_symmetry(self, symbol_or_mats):
+        mats = symmetry_matrices(symbol_or_mats) if isinstance(symbol_or_mats, str) else np.ascontiguousarray(symbol_or_mats, dtype=np.float32)
+        self._ck(self._l.cspb_set_symmetry(self._h, ptr(mats), int(mats.shape[0])))
+        return int(mats.shape[0])
+
+    def set_ring_weights(self, w):
+        if w is None:
+            self._ck(self._l.cspb_refine_set_ring_weights(self._h, None, 0))
+        else:
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            self._ck(self._l.cspb_refine_set_ring_weights(self._h, ptr(w), int(w.size)))
+
+    def noise_curve(self):
+        out = np.zeros(self.box + 1, dtype=np.float32)
+        self._ck(self._l.cspb_refine_get_noise_curve(self._h, ptr(out), out.size))
+        return out
+
+    def set_noise_curve(self, curve):
+        curve = np.ascontiguousarray(curve, dtype=np.float32)
+        self._ck(self._l.cspb_refine_set_noise_curve(self._h, ptr(curve), curve.size))
+
+    def load_images(self, images, append=False):
+        if isinstance(images, np.ndarray):
+            images = np.ascontiguousarray(images, dtype=np.float32)
+        p, loc = _loc_ptr(images)
+        n_img = int(images.shape[0])
+        assert tuple(images.shape[1:]) == (self.box, self.box)
+        self._ck(self._l.cspb_refine_load_images(self._h, p, n_img, loc, 1 if append else 0))
+
+    @property
+    def num_images(self):
+        return int(self._l.cspb_refine_num_images(self._h))
+
+    def score(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        out = np.zeros(rows.size, dtype=np.float32)
+        self._ck(self._l.cspb_refine_score(self._h, ptr(rows), rows.size, ptr(out)))
+        return out
+
+    def score_poses(self, rows, image_index, poses6):
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        idx = np.ascontiguousarray(image_index, dtype=np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
+        assert poses.shape[0] == idx.size
+        out = np.zeros(idx.size, dtype=np.float32)
+        self._ck(self._l.cspb_refine_score_poses(self._h, ptr(rows), rows.size, ptr(idx), ptr(poses), idx.size, ptr(out)))
+        return out
+
+    def refine(self, rows, want_changes=False):
+        """Run refine3d's search over the loaded images.  Returns (rows, changes|None, n_evals)."""
+        rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+        changes = np.zeros_like(rows) if want_changes else None
+        ne = C.c_int64(0)
+        self._ck(self._l.cspb_refine_run(self._h, ptr(rows), rows.size, ptr(changes), C.byref(ne)))
+        return rows, changes, int(ne.value)
+
+    def refine_device(self, rows_dev_ptr, n):
+        """Enqueue the refinement with rows resident on the device (benchmark path)."""
+        ne = C.c_int64(0)
+        self._ck(self._l.cspb_refine_run_device(self._h, C.c_void_p(int(rows_dev_ptr)), int(n), C.byref(ne)))
+        return int(ne.value)
+
+    # ------------------------------------------------------------------ reconstruct3d / merge3d
+    @staticmethod
+    def recon_defaults(box, pixel_size):
+        cfg = ReconCfg()
+        rc = _lib.lib().cspb_recon_cfg_default(C.byref(cfg), int(box), float(pixel_size))
+        if rc != 0:
+            raise CspbError(f"cspb_recon_cfg_default failed: {rc}")
+        return cfg
+
+    def recon_begin(self, cfg: ReconCfg):
+        self._ck(self._l.cspb_recon_begin(self._h, C.byref(cfg)))
+        self.ccfg = cfg
+
+    def recon_insert(self, images, rows):
+        if isinstance(images, np.ndarray):
+            images = np.ascontiguousarray(images, dtype=np.float32)
+            rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+            self._ck(self._l.cspb_recon_insert(self._h, ptr(images), ptr(rows), int(images.shape[0]), HOST))
+        else:  # torch CUDA tensors; rows = device pointer (int) or uint8 tensor of packed rows
+            rp = rows if isinstance(rows, int) else rows.data_ptr()
+            self._ck(self._l.cspb_recon_insert(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(rp), int(images.shape[0]), DEVICE))
+
+    def recon_dims(self):
+        npad, nf = C.c_int(), C.c_int64()
+        self._ck(self._l.cspb_recon_dims(self._h, C.byref(npad), C.byref(nf)))
+        return npad.value, int(nf.value)
+
+    def recon_device_ptr(self, half):
+        p = C.c_void_p()
+        self._ck(self._l.cspb_recon_device_ptr(self._h, int(half), C.byref(p)))
+        return p.value
+
+    def recon_get_dump(self, half):
+        npad, nf = self.recon_dims()
+        out = np.zeros((npad, npad, npad // 2 + 1, 4), dtype=np.float32)
+        self._ck(self._l.cspb_recon_get_dump(self._h, int(half), ptr(out), HOST))
+        return out
+
+    def recon_add_dump(self, half, dump):
+        dump = np.ascontiguousarray(dump, dtype=np.float32)
+        npad, nf = self.recon_dims()
+        assert dump.size == nf, "dump size does not match the accumulator"
+        self._ck(self._l.cspb_recon_add_dump(self._h, int(half), ptr(dump), HOST))
+
+    def recon_finalize(self, molecular_mass_kda=0.0, outer_radius=0.0, want_halves=True):
+        n = self.ccfg.box
+        ns = n // 2 + 1
+        vol = np.zeros((n, n, n), dtype=np.float32)
+        h1 = np.zeros_like(vol) if want_halves else None
+        h2 = np.zeros_like(vol) if want_halves else None
+        stats = np.zeros((ns, 7), dtype=np.float32)
+        self._ck(self._l.cspb_recon_finalize(self._h, float(molecular_mass_kda), float(outer_radius), ptr(h1), ptr(h2), ptr(vol), ptr(stats), ns, HOST))
+        return vol, h1, h2, stats
+
+    def recon_end(self):
+        self._ck(self._l.cspb_recon_end(self._h))
+
+    # ------------------------------------------------------------------ building blocks
+    def fft2_r2c(self, images):
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        b, n = images.shape[0], images.shape[1]
+        out = np.zeros((b, n, n // 2 + 1), dtype=np.complex64)
+        self._ck(self._l.cspb_fft2_r2c(self._h, ptr(images), ptr(out), n, b, HOST))
+        return out
+
+    def fft2_c2r(self, spec):
+        spec = np.ascontiguousarray(spec, dtype=np.complex64)
+        b, n = spec.shape[0], spec.shape[1]
+        out = np.zeros((b, n, n), dtype=np.float32)
+        self._ck(self._l.cspb_fft2_c2r(self._h, ptr(spec), ptr(out), n, b, HOST))
+        return out
+
+    def cufft2_r2c(self, images):
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        b, n = images.shape[0], images.shape[1]
+        out = np.zeros((b, n, n // 2 + 1), dtype=np.complex64)
+        self._ck(self._l.cspb_cufft2_r2c(self._h, ptr(images), ptr(out), n, b, HOST))
+        return out
+
+    def ctf_image(self, row, n):
+        row = np.ascontiguousarray(row, dtype=ROW_DTYPE).reshape(1)
+        out = np.zeros((n, n // 2 + 1), dtype=np.float32)
+        self._ck(self._l.cspb_ctf_image(self._h, ptr(row), int(n), ptr(out)))
+        return out
+
+    def project(self, psi, theta, phi):
+        n = self.box
+        out = np.zeros((n, n // 2 + 1), dtype=np.complex64)
+        self._ck(self._l.cspb_project(self._h, float(psi), float(theta), float(phi), ptr(out)))
+        return out
