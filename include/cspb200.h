@@ -77,6 +77,15 @@ int cspb_stream(cspb_ctx *ctx, void **stream_out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cspb_launch_count(const cspb_ctx *ctx);
 
+/* Live kernel timing for the roofline (bench.py): when enabled, every launch of the scoring
+ * kernel (kind 0) and of the insertion kernel (kind 1) is bracketed by CUDA events on the
+ * context stream.  cspb_profile_get synchronises and returns the summed device time, the
+ * number of launches and the units processed (kind 0: (image,pose) evaluations; kind 1:
+ * projection x symmetry-operator insertions) since the last enable. */
+enum { CSPB_PROF_SCORE = 0, CSPB_PROF_INSERT = 1, CSPB_PROF_KINDS = 2 };
+int cspb_profile_enable(cspb_ctx *ctx, int on);
+int cspb_profile_get(cspb_ctx *ctx, int kind, double *total_ms, int64_t *launches, int64_t *units);
+
 /* ------------------------------------------------------------------ refine3d
  * Replaces the numerics of external/cistem2/refine3d as driven by
  * src/pyp/refine/frealign/frealign.py:3918-3994 (prompt order in SURVEY.md Appendix A.2).

@@ -443,6 +443,45 @@ static void stats_from(const float *v, int ns, float *sigma, float *logp) {
     *logp = var > 0.f ? -0.5f * n * (1.f + logf(2.f * PI_F * var)) : 0.f;
 }
 
+
+/* diagonal Newton step from a central-difference stencil, continuous in (f0, fp, fm):
+   d = g / max(-c, |g| / dmax) with dmax = 4h (trust region) */
+static float newton_step(float f0, float fp, float fm, float h) {
+    const float g = (fp - fm) / (2.f * h);
+    const float c = (fp - 2.f * f0 + fm) / (h * h);
+    const float dmax = 4.f * h;
+    float den = -c;
+    const float floor_ = fabsf(g) / dmax;
+    if (den < floor_) den = floor_;
+    return den > 0.f ? g / den : 0.f;
+}
+
+/* step length from f(0) and f at t = 0.5, 1, 2: least-squares parabola, maximiser clamped to
+   [0, 2.5]; falls back to the best sampled t when the fit is not concave */
+static const float LS_T[3] = {0.5f, 1.f, 2.f};
+static float line_step(float f0, const float *fl) {
+    /* fit f(t) - f0 = a t^2 + b t on the three samples (normal equations, 2x2) */
+    float s22 = 0.f, s23 = 0.f, s33 = 0.f, r2 = 0.f, r3 = 0.f;
+    for (int l = 0; l < 3; ++l) {
+        const float t = LS_T[l], y = fl[l] - f0;
+        s22 += t * t; s23 += t * t * t; s33 += t * t * t * t;
+        r2 += t * y; r3 += t * t * y;
+    }
+    const float det = s22 * s33 - s23 * s23;
+    const float b = (r2 * s33 - r3 * s23) / det;
+    const float a = (r3 * s22 - r2 * s23) / det;
+    if (a < 0.f) {
+        float t = -b / (2.f * a);
+        if (t < 0.f) t = 0.f;
+        if (t > 2.5f) t = 2.5f;
+        return t;
+    }
+    float best = f0, tb = 0.f;
+    for (int l = 0; l < 3; ++l)
+        if (fl[l] > best) { best = fl[l]; tb = LS_T[l]; }
+    return tb;
+}
+
 long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg) {
     const int n = cfg->box, nh = n / 2 + 1;
     int freem[NP] = {cfg->refine_psi, cfg->refine_theta, cfg->refine_phi, cfg->refine_x, cfg->refine_y, cfg->refine_defocus};
@@ -464,11 +503,10 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
         float h[NP] = {h_ang, h_ang, h_ang, h_shift, h_shift, h_def};
         float d[NP];
         float q[NP], o4[4];
+        const float x_start[NP] = {x[0], x[1], x[2], x[3], x[4], x[5]};
         for (int it = 0; it < iters; ++it) {
             const float f0 = orc_score(r, spec, row, x, cfg, o4) * 0.01f;
             evals++;
-            float fbest = f0;
-            int mbest = -1, sbest = 0;
             for (int m = 0; m < NP; ++m) {
                 d[m] = 0.f;
                 if (!freem[m]) continue;
@@ -478,33 +516,24 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
                 q[m] = x[m] - h[m];
                 const float fm = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
                 evals += 2;
-                if (fp > fbest) { fbest = fp; mbest = m; sbest = +1; }
-                if (fm > fbest) { fbest = fm; mbest = m; sbest = -1; }
-                const float g = (fp - fm) / (2.f * h[m]);
-                const float c = (fp - 2.f * f0 + fm) / (h[m] * h[m]);
-                float dd;
-                if (c < 0.f) dd = -g / c;
-                else dd = (g > 0.f ? 2.f : (g < 0.f ? -2.f : 0.f)) * h[m];
-                const float dmax = 4.f * h[m];
-                if (dd > dmax) dd = dmax;
-                if (dd < -dmax) dd = -dmax;
-                d[m] = dd;
+                d[m] = newton_step(f0, fp, fm, h[m]);
             }
-            if (mbest >= 0) { x[mbest] += sbest * h[mbest]; d[mbest] -= sbest * h[mbest]; }
-            const float tl[NL] = {0.5f, 1.f, 2.f};
-            int lbest = -1;
+            float fl[NL];
             for (int l = 0; l < NL; ++l) {
-                for (int m = 0; m < NP; ++m) q[m] = x[m] + tl[l] * d[m];
-                const float f = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+                for (int m = 0; m < NP; ++m) q[m] = x[m] + LS_T[l] * d[m];
+                fl[l] = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
                 evals++;
-                if (f > fbest) { fbest = f; lbest = l; }
             }
-            if (lbest >= 0)
-                for (int m = 0; m < NP; ++m) x[m] += tl[lbest] * d[m];
+            const float t = line_step(f0, fl);
+            for (int m = 0; m < NP; ++m) x[m] += t * d[m];
             for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
         }
-        const float sc = orc_score(r, spec, row, x, cfg, o4);
-        evals++;
+        /* final: score the refined and the starting pose, never return a worse one */
+        float o4s[4];
+        float sc = orc_score(r, spec, row, x, cfg, o4);
+        const float sc_start = orc_score(r, spec, row, x_start, cfg, o4s);
+        evals += 2;
+        if (sc < sc_start) { memcpy(x, x_start, sizeof x); memcpy(o4, o4s, sizeof o4); sc = sc_start; }
         row->psi = wrap360(x[0]);
         row->theta = x[1];
         row->phi = wrap360(x[2]);

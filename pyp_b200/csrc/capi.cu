@@ -123,3 +123,49 @@ extern "C" int cspb_cufft2_r2c(cspb_ctx *ctx, const float *in, float *out_comple
     }
     return 0;
 }
+
+// ---------------------------------------------------------------- live kernel timing
+void prof_begin(cspb_ctx *ctx, int kind, int64_t units) {
+    if (!ctx->prof_on) return;
+    ProfRec r;
+    r.kind = kind;
+    r.units = units;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof.push_back(r);
+}
+
+void prof_end(cspb_ctx *ctx) {
+    if (!ctx->prof_on || ctx->prof.empty()) return;
+    cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}
+
+extern "C" int cspb_profile_enable(cspb_ctx *ctx, int on) {
+    if (!ctx) return CSPB_E_ARG;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    ctx->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int cspb_profile_get(cspb_ctx *ctx, int kind, double *total_ms, int64_t *launches, int64_t *units) {
+    if (!ctx || kind < 0 || kind >= CSPB_PROF_KINDS) return CSPB_E_ARG;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double t = 0.0;
+    int64_t n = 0, u = 0;
+    for (auto &r : ctx->prof) {
+        if (r.kind != kind) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) t += ms;
+        ++n;
+        u += r.units;
+    }
+    if (total_ms) *total_ms = t;
+    if (launches) *launches = n;
+    if (units) *units = u;
+    return 0;
+}

@@ -77,8 +77,17 @@ struct CtfCoef {
     float a, b, cos2ast, sin2ast, c4, ph0, dstep, pad_;  // dstep: d(a)/d(defocus Angstrom)
 };
 
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kind;
+    int64_t units;
+};
+
 // ---------------------------------------------------------------- context
 struct cspb_ctx {
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -118,6 +127,9 @@ struct cspb_ctx {
 };
 
 int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...);
+// event bracket helpers (no-ops unless profiling is enabled)
+void prof_begin(cspb_ctx *ctx, int kind, int64_t units);
+void prof_end(cspb_ctx *ctx);
 
 #define CU_TRY(ctx, expr)                                                                  \
     do {                                                                                   \

@@ -348,7 +348,9 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
         a.acc0 = ctx->d_acc[0].as<float4>();
         a.acc1 = ctx->d_acc[1].as<float4>();
         a.tiles = ceil_div((long long)n * nh, 256);
+        prof_begin(ctx, CSPB_PROF_INSERT, (int64_t)cnt * ctx->n_sym);
         insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
+        prof_end(ctx);
         KERNEL_CHECK(ctx);
         if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }

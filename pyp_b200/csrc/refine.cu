@@ -391,9 +391,9 @@ struct OptState {
     float x[OPT_NP];
     float h[OPT_NP];
     float d[OPT_NP];
-    float f;       // current best CC
-    float f0;      // CC at entry (for the changes file)
-    float pad_;
+    float x0[OPT_NP];  // starting pose
+    float f;           // CC at the current centre
+    float pad_[3];
 };
 
 __global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n, OptState *__restrict__ st, float h_ang,
@@ -406,8 +406,8 @@ __global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n, OptSta
     s.h[0] = s.h[1] = s.h[2] = h_ang;
     s.h[3] = s.h[4] = h_shift;
     s.h[5] = h_def;
-    for (int m = 0; m < OPT_NP; ++m) s.d[m] = 0.f;
-    s.f = -2.f; s.f0 = -2.f; s.pad_ = 0.f;
+    for (int m = 0; m < OPT_NP; ++m) { s.d[m] = 0.f; s.x0[m] = s.x[m]; }
+    s.f = 0.f; s.pad_[0] = s.pad_[1] = s.pad_[2] = 0.f;
     st[k] = s;
 }
 
@@ -444,6 +444,42 @@ __device__ __forceinline__ float cc_of(const float4 v) {
     return den > 0.f ? v.x * rsqrtf(den) : 0.f;
 }
 
+// diagonal Newton step, continuous in (f0, fp, fm): d = g / max(-c, |g|/dmax), dmax = 4h
+__device__ __forceinline__ float newton_step(float f0, float fp, float fm, float h) {
+    const float g = (fp - fm) / (2.f * h);
+    const float c = (fp - 2.f * f0 + fm) / (h * h);
+    const float dmax = 4.f * h;
+    float den = -c;
+    const float floor_ = fabsf(g) / dmax;
+    if (den < floor_) den = floor_;
+    return den > 0.f ? g / den : 0.f;
+}
+
+// step length from f(0) and f(0.5), f(1), f(2): least-squares parabola through the origin
+// offset, maximiser clamped to [0, 2.5]; best sampled t when the fit is not concave
+__device__ __forceinline__ float line_step(float f0, const float *fl) {
+    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
+    float s22 = 0.f, s23 = 0.f, s33 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+    for (int l = 0; l < OPT_NL; ++l) {
+        const float t = tl[l], y = fl[l] - f0;
+        s22 += t * t; s23 += t * t * t; s33 += t * t * t * t;
+        r2 += t * y; r3 += t * t * y;
+    }
+    const float det = s22 * s33 - s23 * s23;
+    const float b = (r2 * s33 - r3 * s23) / det;
+    const float a = (r3 * s22 - r2 * s23) / det;
+    if (a < 0.f) {
+        float t = -b / (2.f * a);
+        return fminf(fmaxf(t, 0.f), 2.5f);
+    }
+    float best = f0, tb = 0.f;
+#pragma unroll
+    for (int l = 0; l < OPT_NL; ++l)
+        if (fl[l] > best) { best = fl[l]; tb = tl[l]; }
+    return tb;
+}
+
 // consume stencil scores, propose the Newton direction, emit line-search poses
 __global__ void opt_step_kernel(OptState *__restrict__ st, int n, int free_mask, int NE, const float4 *__restrict__ sc,
                                 float *__restrict__ poses6_ls, ScoreUnit *__restrict__ units_ls) {
@@ -452,38 +488,14 @@ __global__ void opt_step_kernel(OptState *__restrict__ st, int n, int free_mask,
     OptState s = st[k];
     const float4 *v = sc + (long long)k * NE;
     const float f0 = cc_of(v[0]);
-    if (s.f0 < -1.5f) s.f0 = f0;
-    float fbest = f0;
-    int ebest = 0;
     int e = 1;
     for (int m = 0; m < OPT_NP; ++m) {
         s.d[m] = 0.f;
         if (!((free_mask >> m) & 1)) continue;
-        const float fp = cc_of(v[e]), fm = cc_of(v[e + 1]);
-        if (fp > fbest) { fbest = fp; ebest = e; }
-        if (fm > fbest) { fbest = fm; ebest = e + 1; }
-        const float h = s.h[m];
-        const float g = (fp - fm) / (2.f * h);
-        const float c = (fp - 2.f * f0 + fm) / (h * h);
-        float d;
-        if (c < 0.f) d = -g / c;
-        else d = (g > 0.f ? 2.f : (g < 0.f ? -2.f : 0.f)) * h;
-        const float dmax = 4.f * h;
-        d = fminf(fmaxf(d, -dmax), dmax);
-        s.d[m] = d;
+        s.d[m] = newton_step(f0, cc_of(v[e]), cc_of(v[e + 1]), s.h[m]);
         e += 2;
     }
-    // if a stencil point beats the centre, move there first (keeps the best point seen)
-    if (ebest > 0) {
-        int ee = 1;
-        for (int m = 0; m < OPT_NP; ++m) {
-            if (!((free_mask >> m) & 1)) continue;
-            if (ebest == ee) { s.x[m] += s.h[m]; s.d[m] -= s.h[m]; }
-            if (ebest == ee + 1) { s.x[m] -= s.h[m]; s.d[m] += s.h[m]; }
-            ee += 2;
-        }
-    }
-    s.f = fbest;
+    s.f = f0;
     st[k] = s;
     const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
     float *q = poses6_ls + (long long)k * OPT_NL * 6;
@@ -498,28 +510,25 @@ __global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     OptState s = st[k];
-    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
-    float fbest = s.f;
-    int lbest = -1;
-    for (int l = 0; l < OPT_NL; ++l) {
-        const float f = cc_of(sc_ls[(long long)k * OPT_NL + l]);
-        if (f > fbest) { fbest = f; lbest = l; }
-    }
-    if (lbest >= 0)
-        for (int m = 0; m < OPT_NP; ++m) s.x[m] += tl[lbest] * s.d[m];
-    s.f = fbest;
+    float fl[OPT_NL];
+    for (int l = 0; l < OPT_NL; ++l) fl[l] = cc_of(sc_ls[(long long)k * OPT_NL + l]);
+    const float t = line_step(s.f, fl);
+    for (int m = 0; m < OPT_NP; ++m) s.x[m] += t * s.d[m];
     for (int m = 0; m < OPT_NP; ++m) s.h[m] *= shrink;
     st[k] = s;
 }
 
-// final: one more evaluation at x gives {num, xs, A, B}; write rows
+// final: evaluate the refined pose and the starting pose (2 evals per image)
 __global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, float *__restrict__ poses6,
                                        ScoreUnit *__restrict__ units) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    for (int m = 0; m < OPT_NP; ++m) poses6[(long long)k * 6 + m] = st[k].x[m];
+    for (int m = 0; m < OPT_NP; ++m) {
+        poses6[(long long)k * 12 + m] = st[k].x[m];
+        poses6[(long long)k * 12 + 6 + m] = st[k].x0[m];
+    }
     ScoreUnit un;
-    un.image = k; un.first_eval = k; un.count = 1; un.pad_ = 0;
+    un.image = k; un.first_eval = 2 * k; un.count = 2; un.pad_ = 0;
     units[k] = un;
 }
 
@@ -537,16 +546,19 @@ __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n, co
     const OptState s = st[k];
     cspb_row r = rows[k];
     const cspb_row old = r;
-    r.psi = wrap360(s.x[0]);
-    r.theta = s.x[1];
-    r.phi = wrap360(s.x[2]);
-    r.x_shift = s.x[3];
-    r.y_shift = s.x[4];
+    float4 v = sc[2 * k];
+    const float4 v0 = sc[2 * k + 1];
+    const float *x = s.x;
+    if (100.f * cc_of(v) < 100.f * cc_of(v0)) { v = v0; x = s.x0; }  // never return a worse pose
+    r.psi = wrap360(x[0]);
+    r.theta = x[1];
+    r.phi = wrap360(x[2]);
+    r.x_shift = x[3];
+    r.y_shift = x[4];
     if (refine_defocus) {
-        r.defocus_1 += s.x[5];
-        r.defocus_2 += s.x[5];
+        r.defocus_1 += x[5];
+        r.defocus_2 += x[5];
     }
-    const float4 v = sc[k];
     float sigma, logp;
     score_stats(v, n_samples, &sigma, &logp);
     r.score = 100.f * cc_of(v);
@@ -558,7 +570,7 @@ __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n, co
         c.psi = r.psi - old.psi; c.theta = r.theta - old.theta; c.phi = r.phi - old.phi;
         c.x_shift = r.x_shift - old.x_shift; c.y_shift = r.y_shift - old.y_shift;
         c.defocus_1 = r.defocus_1 - old.defocus_1; c.defocus_2 = r.defocus_2 - old.defocus_2;
-        c.score = r.score - 100.f * s.f0;
+        c.score = r.score - 100.f * cc_of(v0);
         c.logp = r.logp - old.logp; c.sigma = r.sigma - old.sigma;
         changes[k] = c;
     }
@@ -591,7 +603,7 @@ int grid_for(long long total, int block, int sm) {
 }
 
 int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef) {
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals) {
     if (n_units <= 0) return 0;
     ScoreArgs a;
     a.ref4 = ctx->ref.d_ref4.as<float4>();
@@ -611,6 +623,7 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, c
     a.limit_ring = lim > 0.f ? (int)floorf((float)ctx->rcfg.box * ctx->rcfg.pixel_size / lim) : 0x7fffffff;
     a.out = d_out;
     const int grid = ceil_div(n_units, 4);
+    prof_begin(ctx, CSPB_PROF_SCORE, n_evals);
     if (PB == 1) {
         if (ddef) score_kernel<1, true><<<grid, 128, 0, ctx->stream>>>(a);
         else score_kernel<1, false><<<grid, 128, 0, ctx->stream>>>(a);
@@ -618,6 +631,7 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, c
         if (ddef) score_kernel<4, true><<<grid, 128, 0, ctx->stream>>>(a);
         else score_kernel<4, false><<<grid, 128, 0, ctx->stream>>>(a);
     }
+    prof_end(ctx);
     KERNEL_CHECK(ctx);
     return 0;
 }
@@ -948,7 +962,7 @@ extern "C" int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int 
     CU_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), (size_t)n_units * sizeof(ScoreUnit), cudaMemcpyHostToDevice, ctx->stream));
     float4 *d_out = ctx->d_out.as<float4>();
     float *d_sc = reinterpret_cast<float *>(d_out + n_evals);
-    rc = launch_score(ctx, ctx->d_units.as<ScoreUnit>(), n_units, PB, ctx->d_evals.as<float>(), d_ctf, d_out, ddef);
+    rc = launch_score(ctx, ctx->d_units.as<ScoreUnit>(), n_units, PB, ctx->d_evals.as<float>(), d_ctf, d_out, ddef, n_evals);
     if (rc) return rc;
     scores_from_out_kernel<<<ceil_div(n_evals, 256), 256, 0, ctx->stream>>>(d_out, n_evals, d_sc);
     KERNEL_CHECK(ctx);
@@ -988,9 +1002,9 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     const bool ddef = c.refine_defocus != 0;
     const int iters = (c.local_refine && n_free > 0) ? (c.local_iterations > 0 ? c.local_iterations : 6) : 0;
     RESERVE(ctx, ctx->d_opt, (size_t)n * sizeof(OptState));
-    RESERVE(ctx, ctx->d_evals, (size_t)n * (NE + OPT_NL) * 6 * sizeof(float));
+    RESERVE(ctx, ctx->d_evals, (size_t)n * (NE + OPT_NL + 2) * 6 * sizeof(float));
     RESERVE(ctx, ctx->d_units, (size_t)n * (upi + 1) * sizeof(ScoreUnit));
-    RESERVE(ctx, ctx->d_out, (size_t)n * (NE + OPT_NL) * sizeof(float4));
+    RESERVE(ctx, ctx->d_out, (size_t)n * (NE + OPT_NL + 2) * sizeof(float4));
     OptState *st = ctx->d_opt.as<OptState>();
     float *ev = ctx->d_evals.as<float>(), *ev_ls = ev + (size_t)n * NE * 6;
     ScoreUnit *un = ctx->d_units.as<ScoreUnit>(), *un_ls = un + (size_t)n * upi;
@@ -1006,11 +1020,11 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     for (int it = 0; it < iters; ++it) {
         opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, n, free_mask, NE, PB, ev, un);
         KERNEL_CHECK(ctx);
-        int rc = launch_score(ctx, un, n * upi, PB, ev, d_ctf, out, ddef);
+        int rc = launch_score(ctx, un, n * upi, PB, ev, d_ctf, out, ddef, (int64_t)n * NE);
         if (rc) return rc;
         opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, n, free_mask, NE, out, ev_ls, un_ls);
         KERNEL_CHECK(ctx);
-        rc = launch_score(ctx, un_ls, n, PB, ev_ls, d_ctf, out_ls, ddef);
+        rc = launch_score(ctx, un_ls, n, PB, ev_ls, d_ctf, out_ls, ddef, (int64_t)n * OPT_NL);
         if (rc) return rc;
         opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out_ls, 0.6f);
         KERNEL_CHECK(ctx);
@@ -1018,9 +1032,9 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     }
     opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, n, ev, un);
     KERNEL_CHECK(ctx);
-    int rc = launch_score(ctx, un, n, 1, ev, d_ctf, out, ddef);
+    int rc = launch_score(ctx, un, n, 4, ev, d_ctf, out, ddef, 2 * (int64_t)n);
     if (rc) return rc;
-    evals += n;
+    evals += 2 * (int64_t)n;
     opt_write_rows_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes);
     KERNEL_CHECK(ctx);
     if (n_evals_out) *n_evals_out = evals;

@@ -89,6 +89,15 @@ class Engine:
     def launches(self):
         return int(self._l.cspb_launch_count(self._h))
 
+    def profile_enable(self, on=True):
+        self._ck(self._l.cspb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_get(self, kind):
+        """(total_ms, launches, units) of kind 0 = scoring kernel, 1 = insertion kernel."""
+        t, n, u = C.c_double(), C.c_int64(), C.c_int64()
+        self._ck(self._l.cspb_profile_get(self._h, int(kind), C.byref(t), C.byref(n), C.byref(u)))
+        return t.value, int(n.value), int(u.value)
+
     # ------------------------------------------------------------------ refine3d
     @staticmethod
     def refine_defaults(box, pixel_size):
@@ -229,6 +238,15 @@ class Engine:
         stats = np.zeros((ns, 7), dtype=np.float32)
         self._ck(self._l.cspb_recon_finalize(self._h, float(molecular_mass_kda), float(outer_radius), ptr(h1), ptr(h2), ptr(vol), ptr(stats), ns, HOST))
         return vol, h1, h2, stats
+
+    def recon_finalize_device(self, out_maps, molecular_mass_kda=0.0, outer_radius=0.0):
+        """merge3d finalise with the three output volumes (map, half1, half2) as CUDA tensors."""
+        n = self.ccfg.box
+        ns = n // 2 + 1
+        stats = np.zeros((ns, 7), dtype=np.float32)
+        m, h1, h2 = out_maps
+        self._ck(self._l.cspb_recon_finalize(self._h, float(molecular_mass_kda), float(outer_radius), C.c_void_p(h1.data_ptr()), C.c_void_p(h2.data_ptr()), C.c_void_p(m.data_ptr()), ptr(stats), ns, DEVICE))
+        return stats
 
     def recon_end(self):
         self._ck(self._l.cspb_recon_end(self._h))
