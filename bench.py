@@ -57,7 +57,7 @@ def workload_cfgs(box, pixel):
     rcfg.low_res_limit = 100.0            # refine_rlref default
     rcfg.high_res_limit = 2.5 * pixel     # fixed benchmark band, SURVEY.md §8d
     rcfg.mask_radius = 0.38 * box * pixel
-    rcfg.local_iterations = 6
+    rcfg.local_iterations = 8
     ccfg = Engine.recon_defaults(box, pixel)
     return rcfg, ccfg
 

@@ -115,7 +115,7 @@ typedef struct cspb_refine_cfg {
     int32_t invert_contrast;   /* prompt 47                                                    */
     int32_t whiten;            /* 1 = whiten with the stack's noise power curve (cisTEM default) */
     int32_t symmetry_order;    /* number of symmetry matrices handed to cspb_set_symmetry (1 = C1) */
-    int32_t local_iterations;  /* batched local-optimiser iterations (ours; default 6)         */
+    int32_t local_iterations;  /* batched local-optimiser iterations (ours; default 8)         */
     int32_t reserved[7];
 } cspb_refine_cfg;
 

@@ -457,7 +457,7 @@ static float newton_step(float f0, float fp, float fm, float h) {
 }
 
 /* step length from f(0) and f at t = 0.5, 1, 2: least-squares parabola, maximiser clamped to
-   [0, 2.5]; falls back to the best sampled t when the fit is not concave */
+   [0, 2.5]; a convex fit takes the better end of the interval */
 static const float LS_T[3] = {0.5f, 1.f, 2.f};
 static float line_step(float f0, const float *fl) {
     /* fit f(t) - f0 = a t^2 + b t on the three samples (normal equations, 2x2) */
@@ -476,10 +476,7 @@ static float line_step(float f0, const float *fl) {
         if (t > 2.5f) t = 2.5f;
         return t;
     }
-    float best = f0, tb = 0.f;
-    for (int l = 0; l < 3; ++l)
-        if (fl[l] > best) { best = fl[l]; tb = LS_T[l]; }
-    return tb;
+    return (a * 2.5f + b > 0.f) ? 2.5f : 0.f; /* convex fit: best end of [0, 2.5] under the model */
 }
 
 long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg) {
@@ -489,10 +486,11 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
     for (int m = 0; m < NP; ++m) n_free += freem[m] ? 1 : 0;
     float lo, hi;
     orc_band_limits(cfg, &lo, &hi);
-    const float h_ang = 0.5f * 57.29578f / hi;
-    const float h_shift = 0.1f * (float)n / hi * cfg->pixel_size;
+    const float h_ang = 0.35f * 57.29578f / hi;                 /* ~1/3 of the angular resolution at r_hi */
+    const float h_shift = 0.07f * (float)n / hi * cfg->pixel_size; /* Angstrom */
     const float h_def = cfg->defocus_step > 0.f ? cfg->defocus_step : 50.f;
-    const int iters = n_free > 0 ? (cfg->local_iterations > 0 ? cfg->local_iterations : 6) : 0;
+    const int iters = n_free > 0 ? (cfg->local_iterations > 0 ? cfg->local_iterations : 8) : 0;
+    const int late = iters / 2 + 1; /* stencil steps stay constant for the first half, then shrink */
     const int nband = orc_band_count(cfg);
     long long evals = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : evals)
@@ -526,7 +524,8 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
             }
             const float t = line_step(f0, fl);
             for (int m = 0; m < NP; ++m) x[m] += t * d[m];
-            for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
+            if (it + 1 >= late)
+                for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
         }
         /* final: score the refined and the starting pose, never return a worse one */
         float o4s[4];

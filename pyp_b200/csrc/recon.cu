@@ -41,11 +41,30 @@ __device__ __forceinline__ void add_corner(float4 *acc, int np, int xh, int x, i
     atomicAdd(acc + idx, make_float4(w * re, w * im, w * wt, 0.f));
 }
 
+#define INSERT_MAX_SYM 64
 __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
+    __shared__ float s_mat[INSERT_MAX_SYM][6];  // first two columns of pad * S_k * M
+    __shared__ CtfCoef s_ctf;
     const int img = blockIdx.x / A.tiles, tile = blockIdx.x - img * A.tiles;
     const cspb_row row = A.rows[img];
     if (!(row.occupancy > 0.f) || row.score < A.score_threshold) return;
     const int n = A.n, nh = n / 2 + 1;
+    if (threadIdx.x < A.n_sym) {
+        float m[9];
+        euler_matrix(row.psi, row.theta, row.phi, m);
+        const float *S = A.sym + 9 * threadIdx.x;
+        float *o = s_mat[threadIdx.x];
+        o[0] = (S[0] * m[0] + S[1] * m[3] + S[2] * m[6]) * A.padf;
+        o[1] = (S[0] * m[1] + S[1] * m[4] + S[2] * m[7]) * A.padf;
+        o[2] = (S[3] * m[0] + S[4] * m[3] + S[5] * m[6]) * A.padf;
+        o[3] = (S[3] * m[1] + S[4] * m[4] + S[5] * m[7]) * A.padf;
+        o[4] = (S[6] * m[0] + S[7] * m[3] + S[8] * m[6]) * A.padf;
+        o[5] = (S[6] * m[1] + S[7] * m[4] + S[8] * m[7]) * A.padf;
+    }
+    if (threadIdx.x == 255)
+        s_ctf = make_ctf_coef(row.defocus_1, row.defocus_2, row.defocus_angle, row.phase_shift, row.pixel_size,
+                              row.voltage_kv, row.cs_mm, row.amplitude_contrast, n);
+    __syncthreads();
     const int idx = tile * blockDim.x + threadIdx.x;
     if (idx >= n * nh) return;
     const int i = idx % nh;
@@ -57,9 +76,7 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     if (r2 > A.rmax2) return;
     float2 F = A.spec[(long long)img * n * nh + idx];
     if ((i + j) & 1) { F.x = -F.x; F.y = -F.y; }  // box centre at n/2
-    const CtfCoef cc = make_ctf_coef(row.defocus_1, row.defocus_2, row.defocus_angle, row.phase_shift,
-                                     row.pixel_size, row.voltage_kv, row.cs_mm, row.amplitude_contrast, n);
-    const float ctf = -sinpif(ctf_chi(cc, fi, fj, r2) * (1.f / CSPB_PI_F));
+    const float ctf = -sinpif(ctf_chi(s_ctf, fi, fj, r2) * (1.f / CSPB_PI_F));
     float w = row.occupancy * 0.01f;
     if (A.bfac_k != 0.f) w *= expf(-A.bfac_k * (A.avg_score - row.score) * r2);
     // undo the particle shift: multiply by exp(+2 pi i (i sx + j sy) / n), shifts in pixels
@@ -70,14 +87,9 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     const float wt = ctf * ctf;
     const int half = A.per_particle ? (row.pind & 1) : ((row.position_in_stack & 1u) ? 0 : 1);
     float4 *acc = half ? A.acc1 : A.acc0;
-    float m[9];
-    euler_matrix(row.psi, row.theta, row.phi, m);
     for (int s = 0; s < A.n_sym; ++s) {
-        const float *S = A.sym + 9 * s;
-        // R = S * M ; only columns 0 and 1 of R are needed
-        float x = ((S[0] * m[0] + S[1] * m[3] + S[2] * m[6]) * fi + (S[0] * m[1] + S[1] * m[4] + S[2] * m[7]) * fj) * A.padf;
-        float y = ((S[3] * m[0] + S[4] * m[3] + S[5] * m[6]) * fi + (S[3] * m[1] + S[4] * m[4] + S[5] * m[7]) * fj) * A.padf;
-        float z = ((S[6] * m[0] + S[7] * m[3] + S[8] * m[6]) * fi + (S[6] * m[1] + S[7] * m[4] + S[8] * m[7]) * fj) * A.padf;
+        const float *o = s_mat[s];
+        float x = o[0] * fi + o[1] * fj, y = o[2] * fi + o[3] * fj, z = o[4] * fi + o[5] * fj;
         float vim = im;
         if (x < 0.f) { x = -x; y = -y; z = -z; vim = -im; }
         const float x0f = floorf(x), y0f = floorf(y), z0f = floorf(z);
@@ -310,6 +322,8 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
     int chunk = (int)(((size_t)1 << 30) / per_img);
     if (chunk < 1) chunk = 1;
     if (chunk > 8192) chunk = 8192;
+    if (n_images > chunk) chunk = ceil_div(n_images, ceil_div(n_images, chunk));  // even chunks
+    if (ctx->n_sym > INSERT_MAX_SYM) return cspb_fail(ctx, CSPB_E_ARG, "more than %d symmetry operators", INSERT_MAX_SYM);
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;

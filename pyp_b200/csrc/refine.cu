@@ -115,10 +115,10 @@ __global__ void image_stats_kernel(const float *__restrict__ img, int n, float r
 
 // per-image ring power: one warp per ring walks a host-built CSR list of the half-plane samples
 // (deterministic order).  ring = nearest integer radius.  out[img*n_rings + ring] = sum |F|^2
-__global__ void ring_power_kernel(const float2 *__restrict__ spec, int n, const int *__restrict__ ring_off,
+__global__ void ring_power_kernel(const float2 *__restrict__ spec, int n, int img_step, const int *__restrict__ ring_off,
                                   const int *__restrict__ ring_idx, int n_rings, float *__restrict__ out) {
     const int nh = n / 2 + 1;
-    const float2 *f = spec + (long long)blockIdx.x * n * nh;
+    const float2 *f = spec + (long long)blockIdx.x * img_step * n * nh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int r = warp; r < n_rings; r += nw) {
         float s = 0.f;
@@ -456,7 +456,7 @@ __device__ __forceinline__ float newton_step(float f0, float fp, float fm, float
 }
 
 // step length from f(0) and f(0.5), f(1), f(2): least-squares parabola through the origin
-// offset, maximiser clamped to [0, 2.5]; best sampled t when the fit is not concave
+// offset, maximiser clamped to [0, 2.5]; a convex fit takes the better end of the interval
 __device__ __forceinline__ float line_step(float f0, const float *fl) {
     const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
     float s22 = 0.f, s23 = 0.f, s33 = 0.f, r2 = 0.f, r3 = 0.f;
@@ -473,11 +473,7 @@ __device__ __forceinline__ float line_step(float f0, const float *fl) {
         float t = -b / (2.f * a);
         return fminf(fmaxf(t, 0.f), 2.5f);
     }
-    float best = f0, tb = 0.f;
-#pragma unroll
-    for (int l = 0; l < OPT_NL; ++l)
-        if (fl[l] > best) { best = fl[l]; tb = tl[l]; }
-    return tb;
+    return (a * 2.5f + b > 0.f) ? 2.5f : 0.f;  // convex fit: better end of [0, 2.5] under the model
 }
 
 // consume stencil scores, propose the Newton direction, emit line-search poses
@@ -684,7 +680,7 @@ extern "C" int cspb_refine_cfg_default(cspb_refine_cfg *cfg, int box, float pixe
     cfg->invert_contrast = 0;
     cfg->whiten = 1;
     cfg->symmetry_order = 1;
-    cfg->local_iterations = 6;
+    cfg->local_iterations = 8;
     return 0;
 }
 
@@ -815,12 +811,8 @@ static int estimate_noise_from_spectra(cspb_ctx *ctx, const float2 *spec, int co
     // sample every `step`-th image: gather pointers by launching per sampled image
     RESERVE(ctx, ctx->d_work2, ((size_t)n_s * n_rings + n_rings) * sizeof(float));
     float *per = ctx->d_work2.as<float>();
-    const int nh = n / 2 + 1;
-    for (int s = 0; s < n_s; ++s) {
-        ring_power_kernel<<<1, 256, 0, ctx->stream>>>(spec + (long long)s * step * n * nh, n, d_off.as<int>(),
-                                                      d_idx.as<int>(), n_rings, per + (long long)s * n_rings);
-        KERNEL_CHECK(ctx);
-    }
+    ring_power_kernel<<<n_s, 256, 0, ctx->stream>>>(spec, n, step, d_off.as<int>(), d_idx.as<int>(), n_rings, per);
+    KERNEL_CHECK(ctx);
     float *tot = per + (long long)n_s * n_rings;
     sum_over_images_kernel<<<ceil_div(n_rings, 128), 128, 0, ctx->stream>>>(per, n_s, n_rings, tot);
     KERNEL_CHECK(ctx);
@@ -883,6 +875,7 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
     int chunk = (int)((size_t)1 << 30) / (int)per_img;
     if (chunk < 1) chunk = 1;
     if (chunk > 8192) chunk = 8192;
+    if (n_images > chunk) chunk = ceil_div(n_images, ceil_div(n_images, chunk));  // even chunks
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;
@@ -1000,7 +993,8 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     const int NE = 1 + 2 * n_free, PB = 4;
     const int upi = (NE + PB - 1) / PB;
     const bool ddef = c.refine_defocus != 0;
-    const int iters = (c.local_refine && n_free > 0) ? (c.local_iterations > 0 ? c.local_iterations : 6) : 0;
+    const int iters = (c.local_refine && n_free > 0) ? (c.local_iterations > 0 ? c.local_iterations : 8) : 0;
+    const int late = iters / 2 + 1;  // stencil steps stay constant for the first half, then shrink
     RESERVE(ctx, ctx->d_opt, (size_t)n * sizeof(OptState));
     RESERVE(ctx, ctx->d_evals, (size_t)n * (NE + OPT_NL + 2) * 6 * sizeof(float));
     RESERVE(ctx, ctx->d_units, (size_t)n * (upi + 1) * sizeof(ScoreUnit));
@@ -1010,8 +1004,8 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     ScoreUnit *un = ctx->d_units.as<ScoreUnit>(), *un_ls = un + (size_t)n * upi;
     float4 *out = ctx->d_out.as<float4>(), *out_ls = out + (size_t)n * NE;
     const float r_hi = ctx->plan.r_hi;
-    const float h_ang = 0.5f * 57.29578f / r_hi;                       // half the angular resolution at r_hi
-    const float h_shift = 0.1f * (float)c.box / r_hi * c.pixel_size;   // Angstrom
+    const float h_ang = 0.35f * 57.29578f / r_hi;                      // ~1/3 of the angular resolution at r_hi
+    const float h_shift = 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
     const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
     const int g = ceil_div(n, 128);
     opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, n, st, h_ang, h_shift, h_def);
@@ -1026,7 +1020,7 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
         KERNEL_CHECK(ctx);
         rc = launch_score(ctx, un_ls, n, PB, ev_ls, d_ctf, out_ls, ddef, (int64_t)n * OPT_NL);
         if (rc) return rc;
-        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out_ls, 0.6f);
+        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out_ls, it + 1 >= late ? 0.6f : 1.f);
         KERNEL_CHECK(ctx);
         evals += (int64_t)n * (NE + OPT_NL);
     }
