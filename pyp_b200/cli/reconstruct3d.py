@@ -1,0 +1,149 @@
+"""reconstruct3d drop-in: stdin contract of external/cistem2/reconstruct3d as pyp drives it
+(src/pyp/refine/frealign/frealign.py:1780-1824), including the
+conditional 4-line expansion of the dose-weighting answer (:1731-1753)."""
+import sys
+import time
+
+import numpy as np
+
+from ..formats import cistem, dump, mrc
+from .prompts import Answers, PromptError, banner, pick_device
+from .refine3d import select_rows
+
+
+def parse(ans: Answers):
+    p = {}
+    p["stack"] = ans.text("input particle images")
+    p["parameters"] = ans.text("input cisTEM parameter file")
+    p["global_stat"] = ans.text("global statistics parameter file")
+    p["reference"] = ans.text("input reconstruction")
+    p["out_map1"] = ans.text("output reconstruction 1")
+    p["out_map2"] = ans.text("output reconstruction 2")
+    p["out_filtered"] = ans.text("output filtered reconstruction")
+    p["out_statistics"] = ans.text("output resolution statistics")
+    p["symmetry"] = ans.text("particle symmetry")
+    p["first"] = ans.integer("first particle to include")
+    p["last"] = ans.integer("last particle to include")
+    p["pixel_size"] = ans.number("pixel size of images")
+    p["molecular_mass"] = ans.number("molecular mass of particle (kDa)")
+    p["inner_mask_radius"] = ans.number("inner mask radius")
+    p["outer_mask_radius"] = ans.number("outer mask radius")
+    p["resolution_limit"] = ans.number("resolution limit for reconstruction")
+    p["resolution_ref"] = ans.number("resolution limit of reference")
+    p["score_bfactor"] = ans.number("particle weighting factor (score to B-factor)")
+    p["score_weighting"] = ans.yesno("score weighting")
+    p["min_tilt_score"] = ans.number("minimum tilt-particle score")
+    p["max_tilt_score"] = ans.number("maximum tilt-particle score")
+    p["dose_weighting"] = ans.yesno("dose weighting")
+    if p["dose_weighting"]:
+        p["dose_weights_file"] = ans.text("external weights file")
+        p["dose_multiply"] = ans.yesno("multiply weights")
+        p["dose_fraction"] = ans.number("dose weighting fraction")
+        p["dose_transition"] = ans.number("dose weighting transition")
+    p["score_threshold"] = ans.number("score threshold")
+    p["smoothing"] = ans.number("tuning parameter: smoothing factor")
+    p["padding"] = ans.number("tuning parameter: padding factor")
+    p["normalize"] = ans.yesno("normalize particles")
+    p["adjust_scores"] = ans.yesno("adjust scores for defocus dependence")
+    p["invert"] = ans.yesno("invert particle contrast")
+    p["exclude_edges"] = ans.yesno("exclude images with blank edges")
+    p["crop"] = ans.yesno("crop particle images")
+    p["split_even_odd"] = ans.yesno("FSC calculation with even/odd particles")
+    p["per_particle_split"] = ans.yesno("per-particle splitting")
+    p["center_mass"] = ans.yesno("center mass")
+    p["likelihood_blurring"] = ans.yesno("apply likelihood blurring")
+    p["threshold_input"] = ans.yesno("threshold input reconstruction")
+    p["dump"] = ans.yesno("dump intermediate arrays")
+    p["dump1"] = ans.text("output dump filename for odd particles")
+    p["dump2"] = ans.text("output dump filename for even particles")
+    p["max_threads"] = ans.integer("max threads") if not ans.done() else 1
+    return p
+
+
+def dose_weights(p, rows):
+    """Per-projection multiplicative weights from the external file: one float per scan-order
+    (tilt) index = mean SCORE of that index, -1 if none (inout/metadata/core.py:3039-3075).
+    w = 1 for the best `fraction` of indices, falling off over `transition` (ours, SEMANTICS.md)."""
+    if not p.get("dose_weighting"):
+        return None
+    try:
+        w = np.loadtxt(p["dose_weights_file"], ndmin=1)
+    except OSError:
+        return None
+    valid = w >= 0
+    if not valid.any():
+        return None
+    rel = np.where(valid, w / w[valid].max(), 0.0)
+    idx = np.clip(rows["tind"].astype(np.int64), 0, w.size - 1)
+    out = rel[idx]
+    return np.clip(out, 0.0, 1.0).astype(np.float32)
+
+
+def run(p, out=sys.stdout):
+    from ..engine import Engine
+
+    t0 = time.time()
+    hdr = mrc.read_header(p["stack"])
+    box = hdr["nx"]
+    first, last = p["first"], (min(p["last"], hdr["nz"]) if p["last"] > 0 else hdr["nz"])
+    if first < 1 or first > last:
+        raise ValueError(f"particle range {first}..{last} outside the stack (1..{hdr['nz']})")
+    rows_all = cistem.read_parameters(p["parameters"])
+    sel = select_rows(rows_all, first, last)
+    rows = rows_all[sel].copy()
+    dw = dose_weights(p, rows)
+    if dw is not None:
+        rows["occupancy"] = rows["occupancy"] * dw if p.get("dose_multiply", True) else np.where(dw > 0, rows["occupancy"], 0)
+    eng = Engine(pick_device(first, last - first + 1))
+    cfg = Engine.recon_defaults(box, p["pixel_size"])
+    cfg.pad = 2 if p["padding"] >= 1.5 else 1
+    cfg.mask_radius = p["outer_mask_radius"]
+    cfg.resolution_limit = p["resolution_limit"]
+    cfg.score_bfactor = p["score_bfactor"]
+    cfg.score_weighting = int(p["score_weighting"])
+    cfg.score_threshold = p["score_threshold"]
+    cfg.normalize, cfg.invert_contrast = int(p["normalize"]), int(p["invert"])
+    cfg.per_particle_split = int(p["per_particle_split"])
+    used = rows[rows["occupancy"] > 0]
+    cfg.average_score = float(used["score"].mean()) if used.size else 0.0
+    eng.set_symmetry(p["symmetry"])
+    eng.recon_begin(cfg)
+    if rows.size:
+        pos = rows["position_in_stack"].astype(np.int64)
+        _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max()))
+        chunk = 8192
+        for s in range(0, rows.size, chunk):
+            e = min(rows.size, s + chunk)
+            eng.recon_insert(np.ascontiguousarray(data[pos[s:e] - pos.min()]), rows[s:e])
+    n_used = int(used.size)
+    if p["dump"]:
+        for h, path in ((0, p["dump1"]), (1, p["dump2"])):
+            dump.write(path, eng.recon_get_dump(h), box, cfg.pad, h, p["pixel_size"], n_used)
+    else:
+        from ..formats import statistics
+
+        vol, h1, h2, st = eng.recon_finalize(p["molecular_mass"], p["outer_mask_radius"])
+        mrc.write(p["out_map1"], h1, p["pixel_size"])
+        mrc.write(p["out_map2"], h2, p["pixel_size"])
+        mrc.write(p["out_filtered"], vol, p["pixel_size"])
+        with open(p["out_statistics"], "w") as f:
+            f.write(statistics.HEADER + statistics.format_table(st) + "\n")
+    out.write(banner("Reconstruct3D"))
+    out.write(f"\nInserted {n_used} of {rows.size} particles ({first}..{last}), symmetry {p['symmetry']}, "
+              f"box {box}, padding {cfg.pad}, {time.time() - t0:.2f} s\n")
+    out.write("\nReconstruct3D: Normal termination\n")
+    eng.close()
+
+
+def main(argv=None):
+    try:
+        run(parse(Answers(program="reconstruct3d")))
+    except (PromptError, ValueError, OSError, RuntimeError, ImportError) as e:
+        # pyp greps the log for the word "caught" (src/pyp/refine/csp/particle_cspt.py:812-818)
+        sys.stderr.write(f"reconstruct3d: caught error: {e}\n")
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,154 @@
+"""refine3d drop-in: same stdin answer list as external/cistem2/refine3d
+(src/pyp/refine/frealign/frealign.py:3918-3994), numerics on the GPU.
+
+Reads: particle stack (MRC), input `.cistem`, optional `_stat.cistem`, reference map, statistics.
+Writes: `<out>.cistem` with the rows of [first, last] (PSI, THETA, PHI, X_SHIFT, Y_SHIFT, LOGP,
+SIGMA, SCORE updated) and `<out>_changes.cistem`.  Exit status 0 on success, non-zero with the
+word `caught` on stderr otherwise (pyp only checks the output files, frealign.py:3086-3094).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+from ..formats import cistem, mrc, statistics
+from .prompts import Answers, PromptError, banner, pick_device
+
+
+def parse(ans: Answers):
+    p = {}
+    p["stack"] = ans.text("input particle images")
+    p["parameters"] = ans.text("input cisTEM parameter file")
+    p["global_stat"] = ans.text("global statistics parameter file")
+    p["reference"] = ans.text("input reconstruction")
+    p["statistics"] = ans.text("input data statistics")
+    p["use_statistics"] = ans.yesno("use statistics")
+    p["use_priors"] = ans.yesno("use priors")
+    p["matching_out"] = ans.text("output matching projections")
+    p["out_parameters"] = ans.text("output parameter file")
+    p["out_changes"] = ans.text("output parameter changes")
+    p["symmetry"] = ans.text("particle symmetry")
+    p["first"] = ans.integer("first particle to refine")
+    p["last"] = ans.integer("last particle to refine")
+    p["percent_used"] = ans.number("percent of particles to use")
+    p["pixel_size"] = ans.number("pixel size of reconstruction")
+    p["molecular_mass"] = ans.number("molecular mass of particle (kDa)")
+    p["inner_mask_radius"] = ans.number("inner mask radius")
+    p["outer_mask_radius"] = ans.number("outer mask radius")
+    p["low_res_limit"] = ans.number("low resolution limit")
+    p["high_res_limit"] = ans.number("high resolution limit")
+    p["signed_cc_limit"] = ans.number("resolution limit for signed CC")
+    p["class_res_limit"] = ans.number("resolution limit for classification")
+    p["search_mask_radius"] = ans.number("mask radius for global search")
+    p["search_high_res"] = ans.number("approx. resolution limit for search")
+    p["angular_step"] = ans.number("angular step")
+    p["best_matches"] = ans.integer("number of top hits to refine")
+    p["search_range_x"] = ans.number("search range in X")
+    p["search_range_y"] = ans.number("search range in Y")
+    p["mask_2d"] = [ans.number(f"2D mask {k}") for k in ("X", "Y", "Z", "radius")]
+    p["defocus_range"] = ans.number("defocus search range")
+    p["defocus_step"] = ans.number("defocus step")
+    p["padding"] = ans.number("tuning parameter: padding factor")
+    p["global_search"] = ans.yesno("global search")
+    p["local_refine"] = ans.yesno("local refinement")
+    for k in ("psi", "theta", "phi", "x", "y"):
+        p[f"refine_{k}"] = ans.yesno(f"refine {k}")
+    p["calc_matching"] = ans.yesno("calculate matching projections")
+    p["apply_2d_masking"] = ans.yesno("apply 2D masking")
+    p["refine_defocus"] = ans.yesno("refine defocus")
+    p["normalize"] = ans.yesno("normalize particles")
+    p["invert"] = ans.yesno("invert particle contrast")
+    p["exclude_edges"] = ans.yesno("exclude images with blank edges")
+    p["normalize_rec"] = ans.yesno("normalize input reconstruction")
+    p["threshold_rec"] = ans.yesno("threshold input reconstruction")
+    return p
+
+
+def select_rows(rows, first, last):
+    """Rows whose POSITION_IN_STACK lies in the 1-based inclusive range (local_run.py:513-516)."""
+    pos = rows["position_in_stack"].astype(np.int64)
+    sel = np.nonzero((pos >= first) & (pos <= last))[0]
+    return sel[np.argsort(pos[sel], kind="stable")]
+
+
+def build_cfg(p, box):
+    from ..engine import Engine
+
+    cfg = Engine.refine_defaults(box, p["pixel_size"])
+    cfg.pad = 2 if p["padding"] >= 1.5 else 1
+    cfg.mask_radius = p["outer_mask_radius"]
+    cfg.low_res_limit = p["low_res_limit"]
+    cfg.high_res_limit = p["high_res_limit"]
+    cfg.signed_cc_limit = p["signed_cc_limit"]
+    cfg.search_mask_radius = p["search_mask_radius"]
+    cfg.search_high_res = p["search_high_res"]
+    cfg.angular_step = p["angular_step"]
+    cfg.best_matches = p["best_matches"]
+    cfg.search_range_x, cfg.search_range_y = p["search_range_x"], p["search_range_y"]
+    cfg.defocus_range, cfg.defocus_step = p["defocus_range"], p["defocus_step"]
+    cfg.global_search, cfg.local_refine = int(p["global_search"]), int(p["local_refine"])
+    cfg.refine_psi, cfg.refine_theta, cfg.refine_phi = int(p["refine_psi"]), int(p["refine_theta"]), int(p["refine_phi"])
+    cfg.refine_x, cfg.refine_y = int(p["refine_x"]), int(p["refine_y"])
+    cfg.refine_defocus = int(p["refine_defocus"])
+    cfg.normalize, cfg.invert_contrast = int(p["normalize"]), int(p["invert"])
+    return cfg
+
+
+def run(p, out=sys.stdout):
+    from ..engine import Engine
+
+    t0 = time.time()
+    hdr = mrc.read_header(p["stack"])
+    box = hdr["nx"]
+    if hdr["ny"] != box:
+        raise ValueError("particle images must be square")
+    first, last = p["first"], min(p["last"], hdr["nz"]) if p["last"] > 0 else hdr["nz"]
+    if first < 1 or first > last:
+        raise ValueError(f"particle range {first}..{last} outside the stack (1..{hdr['nz']})")
+    rows_all = cistem.read_parameters(p["parameters"])
+    sel = select_rows(rows_all, first, last)
+    rows = rows_all[sel]
+    _, vol = mrc.read(p["reference"])
+    if vol.shape != (box, box, box):
+        raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
+    eng = Engine(pick_device(first, last - first + 1))
+    cfg = build_cfg(p, box)
+    eng.refine_configure(cfg)
+    if p["use_statistics"] and os.path.exists(p["statistics"]) and os.path.getsize(p["statistics"]) > 0:
+        st = statistics.read_statistics(p["statistics"])
+        if st.size:
+            eng.set_ring_weights(statistics.ring_weights_from_statistics(st, box, p["pixel_size"]))
+    eng.set_symmetry(p["symmetry"])
+    eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+    pos = rows["position_in_stack"].astype(np.int64)
+    _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max())) if rows.size else (None, np.zeros((0, box, box), np.float32))
+    images = np.ascontiguousarray(data[pos - pos.min()]) if rows.size else data
+    chunk = 16384
+    for s in range(0, rows.size, chunk):
+        eng.load_images(images[s:s + chunk], append=s > 0)
+    refined, changes, n_evals = eng.refine(rows, want_changes=True) if rows.size else (rows, rows.copy(), 0)
+    cistem.write_parameters(p["out_parameters"], refined)
+    cistem.write_parameters(p["out_changes"], changes)
+    dt = time.time() - t0
+    out.write(banner("Refine3D"))
+    out.write(f"\nRefining particles {first} to {last} ({rows.size} rows), box {box}, pixel {p['pixel_size']}\n")
+    if rows.size:
+        out.write(f"Mean score {float(refined['score'].mean()):.4f}, mean change {float(changes['score'].mean()):+.4f}, "
+                  f"{n_evals} projections scored in {dt:.2f} s\n")
+    out.write("\nRefine3D: Normal termination\n")
+    eng.close()
+    return refined
+
+
+def main(argv=None):
+    try:
+        run(parse(Answers(program="refine3d")))
+    except (PromptError, ValueError, OSError, RuntimeError, ImportError) as e:
+        sys.stderr.write(f"refine3d: caught error: {e}\n")
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

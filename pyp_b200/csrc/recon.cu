@@ -31,6 +31,7 @@ struct InsertArgs {
     int n_sym;
     float4 *acc0, *acc1;
     int tiles;            // tiles per image
+    int half_sel;         // insert only particles of this half (keeps the touched accumulator L2-resident)
 };
 
 __device__ __forceinline__ void add_corner(float4 *acc, int np, int xh, int x, int y, int z, float w, float re,
@@ -48,6 +49,8 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     const int img = blockIdx.x / A.tiles, tile = blockIdx.x - img * A.tiles;
     const cspb_row row = A.rows[img];
     if (!(row.occupancy > 0.f) || row.score < A.score_threshold) return;
+    const int half = A.per_particle ? (row.pind & 1) : ((row.position_in_stack & 1u) ? 0 : 1);
+    if (half != A.half_sel) return;
     const int n = A.n, nh = n / 2 + 1;
     if (threadIdx.x < A.n_sym) {
         float m[9];
@@ -85,7 +88,6 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     sincospif((fi * row.x_shift + fj * row.y_shift) * k2, &sn, &cs);
     const float re = (F.x * cs - F.y * sn) * ctf, im = (F.x * sn + F.y * cs) * ctf;
     const float wt = ctf * ctf;
-    const int half = A.per_particle ? (row.pind & 1) : ((row.position_in_stack & 1u) ? 0 : 1);
     float4 *acc = half ? A.acc1 : A.acc0;
     for (int s = 0; s < A.n_sym; ++s) {
         const float *o = s_mat[s];
@@ -362,10 +364,15 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
         a.acc0 = ctx->d_acc[0].as<float4>();
         a.acc1 = ctx->d_acc[1].as<float4>();
         a.tiles = ceil_div((long long)n * nh, 256);
-        prof_begin(ctx, CSPB_PROF_INSERT, (int64_t)cnt * ctx->n_sym);
-        insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
-        prof_end(ctx);
-        KERNEL_CHECK(ctx);
+        // one pass per half: the voxels one half touches (a half-sphere of radius np/2, 16 B each)
+        // then fit in L2 and the vector atomics stop spilling to HBM
+        for (int h = 0; h < 2; ++h) {
+            a.half_sel = h;
+            prof_begin(ctx, CSPB_PROF_INSERT, h == 0 ? (int64_t)cnt * ctx->n_sym : 0);
+            insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
+            prof_end(ctx);
+            KERNEL_CHECK(ctx);
+        }
         if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     ctx->recon_inserted += n_images;

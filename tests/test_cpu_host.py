@@ -1,0 +1,139 @@
+"""Host-side logic that needs no GPU: prompt parsing of the drop-in front-ends, range
+partitioning, and the multi-process (gloo, world_size 2) gather / reduce plumbing."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from pyp_b200 import dist as pd
+from pyp_b200.cli import local_merge3d, merge3d, prompts, reconstruct3d, refine3d
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _refine3d_heredoc(first=1, last=100, sym="O", mode_local=True):
+    """Answer list exactly as frealign.mrefine_version assembles it (frealign.py:3918-3994)."""
+    mask = ["yes"] * 5
+    lines = ["../T20S_stack.mrc", "T20S_r01.cistem", "null", "T20S_r01.mrc", "statistics_r01.txt", "no", "no",
+             "T20S_r01_match.mrc_0000001_0000100", "T20S_r01_0000001_0000100.cistem", "T20S_r01_0000001_0000100_changes.cistem",
+             sym, str(first), str(last), "1", "1.35", "700.0", "0", "80", "100.0", "8.0", "30.0", "8.0", "120.0", "8.0", "20.0", "20",
+             "0", "0", "0", "0", "0", "0", "500", "50.0", "1", "no" if mode_local else "yes", "yes" if mode_local else "no"] + mask + \
+            ["no", "no", "no", "yes", "no", "no", "no", "no"]
+    return "\n".join(lines) + "\n"
+
+
+def test_refine3d_prompt_order():
+    p = refine3d.parse(prompts.Answers(_refine3d_heredoc(), "refine3d"))
+    assert p["stack"] == "../T20S_stack.mrc" and p["out_changes"].endswith("_changes.cistem")
+    assert (p["first"], p["last"], p["symmetry"]) == (1, 100, "O")
+    assert p["pixel_size"] == 1.35 and p["outer_mask_radius"] == 80 and p["low_res_limit"] == 100.0
+    assert p["high_res_limit"] == 8.0 and p["signed_cc_limit"] == 30.0 and p["angular_step"] == 20.0 and p["best_matches"] == 20
+    assert p["mask_2d"] == [0, 0, 0, 0] and p["defocus_range"] == 500 and p["padding"] == 1
+    assert p["global_search"] is False and p["local_refine"] is True and p["refine_y"] is True
+    assert p["normalize"] is True and p["invert"] is False and p["threshold_rec"] is False
+    p = refine3d.parse(prompts.Answers(_refine3d_heredoc(mode_local=False), "refine3d"))
+    assert p["global_search"] is True and p["local_refine"] is False
+    with pytest.raises(prompts.PromptError):
+        refine3d.parse(prompts.Answers("a\nb\n", "refine3d"))
+    bad = _refine3d_heredoc().replace("\n1.35\n", "\nnot-a-number\n")
+    with pytest.raises(prompts.PromptError):
+        refine3d.parse(prompts.Answers(bad, "refine3d"))
+
+
+def _reconstruct_heredoc(dose=False):
+    """frealign.split_reconstruction (frealign.py:1780-1824), optional dose-weighting expansion."""
+    dw = ["yes", "/scratch/global_weight.txt", "yes", "4", "0.75"] if dose else ["no"]
+    lines = ["/scratch/T20S_stack.mrc", "../T20S_r01_used.cistem", "null", "../T20S_r01.mrc", "T20S_r01_map1.mrc", "T20S_r01_map2.mrc",
+             "output.mrc", "T20S_r01_n1.res", "C1", "1", "50", "1.35", "700.0", "0", "86.4", "2.7", "0", "2.0", "no", "0", "-1"] + dw + \
+            ["0", "1", "1", "yes", "no", "no", "no", "no", "yes", "no", "no", "no", "no", "yes", "/scratch/T20S_r01_map1_n1.mrc",
+             "/scratch/T20S_r01_map2_n1.mrc", "1"]
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("dose", [False, True])
+def test_reconstruct3d_prompt_order(dose):
+    p = reconstruct3d.parse(prompts.Answers(_reconstruct_heredoc(dose), "reconstruct3d"))
+    assert p["parameters"] == "../T20S_r01_used.cistem" and p["out_statistics"] == "T20S_r01_n1.res"
+    assert (p["first"], p["last"], p["symmetry"]) == (1, 50, "C1")
+    assert p["outer_mask_radius"] == 86.4 and p["resolution_limit"] == 2.7 and p["score_bfactor"] == 2.0
+    assert p["dose_weighting"] is dose
+    if dose:
+        assert p["dose_weights_file"] == "/scratch/global_weight.txt" and p["dose_fraction"] == 4 and p["dose_transition"] == 0.75
+    assert p["padding"] == 1 and p["normalize"] is True and p["split_even_odd"] is True and p["dump"] is True
+    assert p["dump1"].endswith("_map1_n1.mrc") and p["dump2"].endswith("_map2_n1.mrc") and p["max_threads"] == 1
+
+
+def test_merge_prompt_order():
+    p = local_merge3d.parse(prompts.Answers("dumpfile_map1.mrc\ndumpfile_map2.mrc\ntemp_map1_n.mrc\ntemp_map2_n.mrc\n4\n", "local_merge3d"))
+    assert p == {"out1": "dumpfile_map1.mrc", "out2": "dumpfile_map2.mrc", "seed1": "temp_map1_n.mrc", "seed2": "temp_map2_n.mrc", "count": 4}
+    p = merge3d.parse(prompts.Answers("a_half1.mrc\na_half2.mrc\na.mrc\na_statistics.txt\n700.0\n0\n86.4\ns/a_map1_n.mrc\ns/a_map2_n.mrc\n3\n", "merge3d"))
+    assert p["filtered"] == "a.mrc" and p["molecular_mass"] == 700.0 and p["outer_radius"] == 86.4 and p["count"] == 3
+
+
+def test_select_rows_and_device_pick(monkeypatch):
+    from pyp_b200._lib import ROW_DTYPE
+
+    rows = np.zeros(10, ROW_DTYPE)
+    rows["position_in_stack"] = [5, 1, 9, 3, 7, 2, 10, 4, 8, 6]
+    sel = refine3d.select_rows(rows, 3, 6)
+    assert list(rows["position_in_stack"][sel]) == [3, 4, 5, 6]
+    assert refine3d.select_rows(rows, 11, 20).size == 0
+    monkeypatch.setenv("CSPB_NUM_DEVICES", "8")
+    assert [prompts.pick_device(f, 100) for f in (1, 101, 201, 801)] == [0, 1, 2, 0]
+    monkeypatch.setenv("CSPB_DEVICE", "3")
+    assert prompts.pick_device(1, 100) == 3
+
+
+def test_range_split_matches_reference_quirk():
+    # local_run.py:507-516: increment = ceil(frames/cores); ranges step by increment + 1
+    assert pd.split_ranges(10, 3) == [(1, 5), (6, 10)]
+    assert pd.split_ranges(100, 8) == [(1, 14), (15, 28), (29, 42), (43, 56), (57, 70), (71, 84), (85, 98), (99, 100)]
+    assert pd.split_ranges(0, 4) == []
+    for n, w in [(10, 3), (7, 8), (100000, 8), (5, 1)]:
+        shards = [pd.shard_range(1, n, r, w) for r in range(w)]
+        covered = [i for lo, hi in shards for i in range(lo, hi + 1)]
+        assert covered == list(range(1, n + 1))
+        sizes = [hi - lo + 1 for lo, hi in shards]
+        assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from pyp_b200 import dist as pd
+from pyp_b200._lib import ROW_DTYPE
+dist.init_process_group("gloo")
+rank, ws = dist.get_rank(), dist.get_world_size()
+n = 11
+lo, hi = pd.shard_range(1, n, rank, ws)
+rows = np.zeros(hi - lo + 1, ROW_DTYPE)
+rows["position_in_stack"] = np.arange(lo, hi + 1)[::-1]          # deliberately unsorted
+rows["score"] = rows["position_in_stack"] * 1.5
+allrows = pd.gather_rows(rows, dst=0)
+acc = torch.full((64,), float(rank + 1))
+pd.reduce_sum(acc, dst=0)
+curve = pd.allreduce_noise_curve(np.full(5, float(rank + 1) * (hi - lo + 1)), hi - lo + 1)
+if rank == 0:
+    assert list(allrows["position_in_stack"]) == list(range(1, n + 1)), allrows["position_in_stack"]
+    assert np.allclose(allrows["score"], np.arange(1, n + 1) * 1.5)
+    assert torch.all(acc == sum(range(1, ws + 1)))
+else:
+    assert allrows is None
+want = sum((r + 1) * (pd.shard_range(1, n, r, ws)[1] - pd.shard_range(1, n, r, ws)[0] + 1) for r in range(ws)) / n
+assert np.allclose(curve, want), (curve, want)
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,143 @@
+"""Known-answer tests of the CPU oracle itself ("parity unpinned": no reference binary or golden
+vector exists for the numerics, SURVEY.md §4, so the restatement is anchored on analytic facts)."""
+import numpy as np
+import pytest
+
+from common import angular_distance, pose_of, small_case
+from pyp_b200 import synth
+
+
+@pytest.mark.parametrize("n", [16, 48, 64, 96])
+def test_fft_matches_numpy(oracle, n):
+    rng = np.random.default_rng(n)
+    img = rng.normal(size=(n, n)).astype(np.float32)
+    got = oracle.fft2_r2c(img)
+    want = np.fft.rfft2(img.astype(np.float64))
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-6
+    assert np.abs(oracle.fft2_c2r(got) / (n * n) - img).max() < 1e-5
+
+
+def test_ctf_matches_float64_formula(oracle):
+    _, _, rows, _ = small_case(n=64, n_part=3)
+    for r in rows:
+        got = oracle.ctf_image(r.astype(oracle.ROW_DTYPE), 64)
+        want = synth.ctf_2d(64, float(r["pixel_size"]), r["defocus_1"], r["defocus_2"], r["defocus_angle"])
+        keep = np.ones(64, bool)
+        keep[32] = False
+        assert np.abs(got[keep, :32] - want[keep, :32]).max() < 5e-3
+    assert abs(got[0, 0] - (-0.07)) < 1e-6  # CTF(0) = -amplitude contrast
+
+
+def test_band_count_matches_survey(oracle):
+    cfg = oracle.RefineCfg(box=128, pad=1, pixel_size=1.35, low_res_limit=100.0, high_res_limit=2.5 * 1.35)
+    assert oracle.band_count(cfg) == 4168
+    cfg = oracle.RefineCfg(box=256, pad=1, pixel_size=1.0, low_res_limit=100.0, high_res_limit=2.5)
+    assert oracle.band_count(cfg) == 16558
+
+
+@pytest.mark.parametrize("pad,tol", [(1, 0.98), (2, 0.999)])
+def test_central_slice_theorem(oracle, pad, tol):
+    """Fourier slice of the rendered phantom == FT of its analytic real-space projection."""
+    n = 64
+    ph = synth.Phantom(n, n_blobs=40, sigma=1.5)
+    ref = oracle.Reference(ph.volume(), pad)
+    jj, ii = np.meshgrid(np.arange(n), np.arange(n // 2 + 1), indexing="ij")
+    j = np.where(jj >= n // 2, jj - n, jj)
+    r = np.hypot(ii, j)
+    m = (r <= 20) & (r >= 1)
+    for pose in [(0, 0, 0), (0, 40, 70), (25, 60, 110), (200, 130, 300)]:
+        P = ref.project(*pose, 24.0)
+        F = np.fft.rfft2(ph.project(*pose)) * (-1.0) ** (ii + jj)
+        cc = np.real(np.vdot(P[m], F[m])) / np.sqrt(np.vdot(P[m], P[m]).real * np.vdot(F[m], F[m]).real)
+        assert cc > tol, (pose, cc)
+    # the transposed convention must NOT match
+    P = ref.project(25, 60, 110, 24.0)
+    F = np.fft.rfft2(ph.project(110, 60, 25)) * (-1.0) ** (ii + jj)
+    cc = np.real(np.vdot(P[m], F[m])) / np.sqrt(np.vdot(P[m], P[m]).real * np.vdot(F[m], F[m]).real)
+    assert cc < 0.7
+
+
+def _cfg(oracle, n, px, **kw):
+    d = dict(box=n, pad=1, pixel_size=px, mask_radius=0.38 * n * px, low_res_limit=60.0, high_res_limit=4.0 * px, signed_cc_limit=30.0,
+             defocus_step=50.0, refine_psi=1, refine_theta=1, refine_phi=1, refine_x=1, refine_y=1, refine_defocus=0, apply_mask=1,
+             normalize=1, invert_contrast=0, whiten=1, local_iterations=8)
+    d.update(kw)
+    return oracle.RefineCfg(**d)
+
+
+def test_score_peaks_at_true_pose_and_shift_sign(oracle):
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=6, snr=1.0)
+    rows = rows.astype(oracle.ROW_DTYPE)
+    cfg = _cfg(oracle, n, px)
+    specs = oracle.prepare_images(stack, cfg, oracle.noise_curve(stack, cfg))
+    ref = oracle.Reference(vol, 1)
+    for k in range(rows.size):
+        p0 = np.array(pose_of(rows[k]), dtype=np.float32)
+        s0, _ = oracle.score(ref, specs[k], rows[k], p0, cfg)
+        assert s0 > 40
+        for d in ([6, 0, 0, 0, 0, 0], [0, 6, 0, 0, 0, 0], [0, 0, 0, 3 * px, 0, 0], [0, 0, 0, 0, -3 * px, 0]):
+            s1, _ = oracle.score(ref, specs[k], rows[k], p0 + np.array(d, np.float32), cfg)
+            assert s1 < s0 - 1.0, (k, d, s0, s1)
+        wrong = p0.copy()
+        wrong[3:5] *= -1  # flipped shift sign
+        if np.hypot(*p0[3:5]) > 1.5 * px:
+            assert oracle.score(ref, specs[k], rows[k], wrong, cfg)[0] < s0 - 1.0
+
+
+def test_local_refinement_recovers_poses(oracle):
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=32, snr=0.5)
+    cfg = _cfg(oracle, n, px)
+    specs = oracle.prepare_images(stack, cfg, oracle.noise_curve(stack, cfg))
+    ref = oracle.Reference(vol, 1)
+    start = synth.perturb_rows(rows, 2.0, 1.0).astype(oracle.ROW_DTYPE)
+    out, n_evals = oracle.refine_local(ref, specs, start, cfg)
+    assert n_evals == rows.size * (8 * (11 + 3) + 2)
+    before, after = angular_distance(start, rows), angular_distance(out, rows)
+    assert np.median(after) < 0.5 * np.median(before)
+    sh = np.hypot(out["x_shift"] - rows["x_shift"], out["y_shift"] - rows["y_shift"]) / px
+    assert np.median(sh) < 0.35
+    assert (out["score"] >= 0).all() and (out["sigma"] > 0).all() and (out["logp"] < 0).all()
+    # masked parameters stay untouched
+    cfg2 = _cfg(oracle, n, px, refine_psi=0, refine_theta=0, refine_phi=0)
+    out2, _ = oracle.refine_local(ref, specs, start, cfg2)
+    assert np.allclose(out2["theta"], start["theta"]) and not np.allclose(out2["x_shift"], start["x_shift"])
+
+
+def test_reconstruction_recovers_phantom_and_symmetry(oracle):
+    from pyp_b200.symmetry import symmetry_matrices
+
+    n, px = 32, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=240, n_blobs=20, snr=None)
+    cfg = oracle.ReconCfg(box=n, pad=1, pixel_size=px, mask_radius=px * n / 2, resolution_limit=2 * px, score_bfactor=2.0, normalize=0)
+    rc = oracle.Recon(cfg)
+    rc.insert(stack, rows.astype(oracle.ROW_DTYPE))
+    m, h1, h2, st = rc.finalize(50.0, 0.0)
+    f = oracle.fsc(m, vol)
+    assert f[1:8].min() > 0.95  # noiseless projections reproduce the phantom
+    assert oracle.fsc(h1, h2)[1:8].min() > 0.9
+    assert st.shape == (17, 7) and st[1, 1] == pytest.approx(n * px) and st[1, 3] > 0.9
+    # x = 0 plane: dump keeps raw sums; the halves split by stack parity
+    d0, d1 = rc.dump(0), rc.dump(1)
+    assert d0[..., 2].sum() > 0 and d1[..., 2].sum() > 0 and np.all(d0[..., 3] == 0)
+    # C2 symmetry doubles the accumulated weight
+    rc2 = oracle.Recon(cfg)
+    rc2.insert(stack[:20], rows[:20].astype(oracle.ROW_DTYPE), symmetry_matrices("C2"))
+    rc1 = oracle.Recon(cfg)
+    rc1.insert(stack[:20], rows[:20].astype(oracle.ROW_DTYPE))
+    assert rc2.dump(0)[..., 2].sum() == pytest.approx(2 * rc1.dump(0)[..., 2].sum(), rel=1e-4)
+
+
+def test_symmetry_groups_close():
+    from pyp_b200.symmetry import symmetry_matrices
+
+    for sym, order in [("C1", 1), ("C7", 7), ("D2", 4), ("D7", 14), ("T", 12), ("O", 24), ("I", 60)]:
+        m = symmetry_matrices(sym).astype(np.float64)
+        assert m.shape == (order, 3, 3)
+        assert np.allclose(np.linalg.det(m), 1.0, atol=1e-5)
+        prods = np.einsum("aij,bjk->abik", m, m).reshape(-1, 3, 3)
+        for p in prods[:: max(1, order // 3)]:
+            assert np.min(np.abs(m - p).reshape(order, -1).max(axis=1)) < 1e-5
+    with pytest.raises(ValueError):
+        symmetry_matrices("X3")
