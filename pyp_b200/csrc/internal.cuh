@@ -123,6 +123,7 @@ struct cspb_ctx {
     cspb_recon_cfg ccfg{};
     int rnp = 0;
     DevBuf d_acc[2];
+    DevBuf d_shell;  // per-shell sums, Wiener terms, statistics rows
     int64_t recon_inserted = 0;
 };
 

@@ -118,21 +118,19 @@ __global__ void add_volume_kernel(float4 *__restrict__ dst, const float4 *__rest
     }
 }
 
-// x = 0 plane: add the Friedel mate (0,-y,-z) conj to (0,y,z) and vice versa, once per pair
-__global__ void symmetrize_x0_kernel(float4 *__restrict__ acc, int np, int xh) {
+// x = 0 plane of the Hermitian half-volume: every inserted sample also stands for its Friedel
+// mate, which lands on (0,-y,-z) conjugated.  Readers fold the mate in on the fly, so the
+// accumulators themselves stay pure sums (dumps can be merged in any order).
+__device__ __forceinline__ float4 load_sym(const float4 *__restrict__ acc, int np, int xh, int x, int y, int z) {
     const int c = np / 2;
-    const long long total = (long long)np * np;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(k % np) - c, z = (int)(k / np) - c;
-        if (y == -c || z == -c) continue;  // mate outside the stored range
-        if (!(z > 0 || (z == 0 && y >= 0))) continue;
-        const long long p = ((long long)(z + c) * np + (y + c)) * xh;
-        const long long q = ((long long)(-z + c) * np + (-y + c)) * xh;
-        const float4 a = acc[p], b = acc[q];
-        const float re = a.x + b.x, im = a.y - b.y, w = a.z + b.z;
-        acc[p] = make_float4(re, im, w, 0.f);
-        acc[q] = make_float4(re, -im, w, 0.f);
+    float4 a = acc[((long long)(z + c) * np + (y + c)) * xh + x];
+    if (x == 0 && y != -c && z != -c) {
+        const float4 b = acc[((long long)(-z + c) * np + (-y + c)) * xh];
+        a.x += b.x;
+        a.y -= b.y;
+        a.z += b.z;
     }
+    return a;
 }
 
 // per-shell sums for FSC: {sum Re(V1 V2*), sum |V1|^2, sum |V2|^2, sum (W1+W2), count, sumW1, sumW2}
@@ -149,7 +147,7 @@ __global__ void shell_stats_kernel(const float4 *__restrict__ a0, const float4 *
         const float r = sqrtf((float)(x * x + y * y + z * z)) * inv_pad;
         const int s = (int)(r + 0.5f);
         if (s >= n_shells) continue;
-        const float4 p = a0[k], q = a1[k];
+        const float4 p = load_sym(a0, np, xh, x, y, z), q = load_sym(a1, np, xh, x, y, z);
         if (!(p.z > 0.f) || !(q.z > 0.f)) continue;
         const float mult = (x == 0) ? 0.5f : 1.f;  // x = 0 plane stores both Friedel mates
         const float v1x = p.x / p.z, v1y = p.y / p.z, v2x = q.x / q.z, v2y = q.y / q.z;
@@ -167,6 +165,38 @@ __global__ void shell_stats_kernel(const float4 *__restrict__ a0, const float4 *
         if (sh[k] != 0.f) atomicAdd(out + k, (double)sh[k]);
 }
 
+// per-shell FSC -> SSNR -> Wiener terms and the 7-column statistics row (one thread per shell)
+__global__ void shell_terms_kernel(const double *__restrict__ sh, int ns, double frac, float box_a, int n,
+                                   float *__restrict__ term, float *__restrict__ stats) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const double *q = sh + (size_t)s * SHELL_Q;
+    double fsc = 0.0;
+    if (q[1] > 0.0 && q[2] > 0.0) fsc = q[0] / sqrt(q[1] * q[2]);
+    if (s == 0 && q[4] > 0.0) fsc = 1.0;
+    double f = fsc;
+    if (f > 0.9999) f = 0.9999;
+    if (f < 0.0) f = 0.0;
+    const double rec_ssnr = 2.0 * f / (1.0 - f);
+    const double part_ssnr = rec_ssnr / frac;
+    const double part_fsc = part_ssnr / (2.0 + part_ssnr);
+    const double cntv = q[4] > 0.0 ? q[4] : 1.0;
+    const double mw = q[3] / cntv, mw0 = q[5] / cntv, mw1 = q[6] / cntv;
+    const double ssnr_floor = 1e-4;
+    term[s] = (float)(mw / (rec_ssnr > ssnr_floor ? rec_ssnr : ssnr_floor));
+    const double half_ssnr = 0.5 * rec_ssnr > ssnr_floor ? 0.5 * rec_ssnr : ssnr_floor;
+    term[ns + s] = (float)(mw0 / half_ssnr);
+    term[2 * ns + s] = (float)(mw1 / half_ssnr);
+    float *o = stats + (size_t)s * 7;
+    o[0] = (float)s;
+    o[1] = s > 0 ? box_a / (float)s : 0.f;
+    o[2] = (float)s / (float)n;
+    o[3] = (float)fsc;
+    o[4] = (float)part_fsc;
+    o[5] = (float)sqrt(part_ssnr);
+    o[6] = (float)sqrt(rec_ssnr);
+}
+
 // accumulators -> FFT-ordered half spectrum ready for the inverse transform
 // mode 0: (a0+a1)/(w0+w1+term), 1: a0/(w0+term), 2: a1/(w1+term); term indexed by shell
 __global__ void filter_to_fft_kernel(const float4 *__restrict__ a0, const float4 *__restrict__ a1, int np, int xh,
@@ -181,13 +211,12 @@ __global__ void filter_to_fft_kernel(const float4 *__restrict__ a0, const float4
         const int s = (int)(r + 0.5f);
         float2 v = make_float2(0.f, 0.f);
         if (s < n_shells) {
-            const long long src = ((long long)(z + c) * np + (y + c)) * xh + x;
             float re, im, w;
             if (mode == 0) {
-                const float4 p = a0[src], q = a1[src];
+                const float4 p = load_sym(a0, np, xh, x, y, z), q = load_sym(a1, np, xh, x, y, z);
                 re = p.x + q.x; im = p.y + q.y; w = p.z + q.z;
             } else {
-                const float4 p = (mode == 1 ? a0 : a1)[src];
+                const float4 p = load_sym(mode == 1 ? a0 : a1, np, xh, x, y, z);
                 re = p.x; im = p.y; w = p.z;
             }
             const float den = w + term[s];
@@ -412,72 +441,31 @@ extern "C" int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, floa
     const int ns = n / 2 + 1;
     if (stats && n_shells != ns) return cspb_fail(ctx, CSPB_E_ARG, "stats needs box/2+1 = %d shells", ns);
     const long long nvox = (long long)xh * np * np;
-    // work on copies so the accumulators stay pure sums (finalize may be called again after more inserts)
-    DevBuf w0, w1;
-    RESERVE(ctx, w0, (size_t)nvox * sizeof(float4));
-    RESERVE(ctx, w1, (size_t)nvox * sizeof(float4));
-    CU_TRY(ctx, cudaMemcpyAsync(w0.p, ctx->d_acc[0].p, (size_t)nvox * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(w1.p, ctx->d_acc[1].p, (size_t)nvox * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-    float4 *a0 = w0.as<float4>(), *a1 = w1.as<float4>();
-    const int gp = grid_for((long long)np * np, 256, ctx->sm_count);
-    symmetrize_x0_kernel<<<gp, 256, 0, ctx->stream>>>(a0, np, xh);
-    KERNEL_CHECK(ctx);
-    symmetrize_x0_kernel<<<gp, 256, 0, ctx->stream>>>(a1, np, xh);
-    KERNEL_CHECK(ctx);
-    // shell statistics
-    DevBuf d_sh;
-    RESERVE(ctx, d_sh, (size_t)ns * SHELL_Q * sizeof(double) + (size_t)3 * ns * sizeof(float));
-    CU_TRY(ctx, cudaMemsetAsync(d_sh.p, 0, (size_t)ns * SHELL_Q * sizeof(double), ctx->stream));
+    const float4 *a0 = ctx->d_acc[0].as<float4>(), *a1 = ctx->d_acc[1].as<float4>();
+    // shell statistics -> Wiener terms, all on the device (oracle/SEMANTICS.md §merge3d)
+    const size_t sh_bytes = (size_t)ns * SHELL_Q * sizeof(double);
+    RESERVE(ctx, ctx->d_shell, sh_bytes + (size_t)(3 + 7) * ns * sizeof(float));
+    double *d_sh = ctx->d_shell.as<double>();
+    float *d_term = reinterpret_cast<float *>(d_sh + (size_t)ns * SHELL_Q);
+    float *d_stats = d_term + (size_t)3 * ns;
+    CU_TRY(ctx, cudaMemsetAsync(d_sh, 0, sh_bytes, ctx->stream));
     shell_stats_kernel<<<grid_for(nvox, 256, ctx->sm_count) / 4 + 1, 256, ns * SHELL_Q * sizeof(float), ctx->stream>>>(
-        a0, a1, np, xh, 1.f / (float)c.pad, ns, d_sh.as<double>());
+        a0, a1, np, xh, 1.f / (float)c.pad, ns, d_sh);
     KERNEL_CHECK(ctx);
-    std::vector<double> sh((size_t)ns * SHELL_Q);
-    CU_TRY(ctx, cudaMemcpyAsync(sh.data(), d_sh.p, sh.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    // FSC -> SSNR -> Wiener terms (oracle/SEMANTICS.md §merge3d)
     const float box_a = (float)n * c.pixel_size;
-    float rad_a = outer_radius_a > 0.f ? outer_radius_a : 0.5f * box_a;
+    const float rad_a = outer_radius_a > 0.f ? outer_radius_a : 0.5f * box_a;
     double mask_vol = 4.0 / 3.0 * CSPB_PI_D * (double)rad_a * rad_a * rad_a;
     const double box_vol = (double)box_a * box_a * box_a;
     if (mask_vol > box_vol) mask_vol = box_vol;
     double frac = molecular_mass_kda > 0.f ? ((double)molecular_mass_kda * 1000.0 / 0.81) / mask_vol : 1.0;
-    if (frac > 1.0) frac = 1.0;
-    if (frac <= 0.0) frac = 1.0;
-    std::vector<float> term((size_t)3 * ns, 0.f);
-    for (int s = 0; s < ns; ++s) {
-        const double *q = &sh[(size_t)s * SHELL_Q];
-        double fsc = 0.0;
-        if (q[1] > 0.0 && q[2] > 0.0) fsc = q[0] / sqrt(q[1] * q[2]);
-        if (s == 0 && q[4] > 0.0) fsc = 1.0;
-        double f = fsc;
-        if (f > 0.9999) f = 0.9999;
-        if (f < 0.0) f = 0.0;
-        const double rec_ssnr = 2.0 * f / (1.0 - f);
-        const double part_ssnr = rec_ssnr / frac;
-        const double part_fsc = part_ssnr / (2.0 + part_ssnr);
-        const double cntv = q[4] > 0.0 ? q[4] : 1.0;
-        const double mw = q[3] / cntv, mw0 = q[5] / cntv, mw1 = q[6] / cntv;
-        const double ssnr_floor = 1e-4;
-        term[s] = (float)(mw / (rec_ssnr > ssnr_floor ? rec_ssnr : ssnr_floor));
-        const double half_ssnr = 0.5 * rec_ssnr > ssnr_floor ? 0.5 * rec_ssnr : ssnr_floor;
-        term[ns + s] = (float)(mw0 / half_ssnr);
-        term[2 * ns + s] = (float)(mw1 / half_ssnr);
-        if (stats) {
-            float *o = stats + (size_t)s * 7;
-            o[0] = (float)s;
-            o[1] = s > 0 ? box_a / (float)s : 0.f;
-            o[2] = (float)s / (float)n;
-            o[3] = (float)fsc;
-            o[4] = (float)part_fsc;
-            o[5] = (float)sqrt(part_ssnr);
-            o[6] = (float)sqrt(rec_ssnr);
-        }
-    }
-    float *d_term = reinterpret_cast<float *>(d_sh.as<double>() + (size_t)ns * SHELL_Q);
-    CU_TRY(ctx, cudaMemcpyAsync(d_term, term.data(), term.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (frac > 1.0 || frac <= 0.0) frac = 1.0;
+    shell_terms_kernel<<<ceil_div(ns, 128), 128, 0, ctx->stream>>>(d_sh, ns, frac, box_a, n, d_term, d_stats);
+    KERNEL_CHECK(ctx);
+    if (stats)
+        CU_TRY(ctx, cudaMemcpyAsync(stats, d_stats, (size_t)ns * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     RESERVE(ctx, ctx->d_work1, (size_t)nvox * sizeof(float2));
     RESERVE(ctx, ctx->d_work0, (size_t)np * np * np * sizeof(float));
-    RESERVE(ctx, ctx->d_work2, (size_t)n * n * n * sizeof(float));
+    if (loc == CSPB_HOST) RESERVE(ctx, ctx->d_work2, (size_t)n * n * n * sizeof(float));
     float *outs[3] = {map, half1, half2};
     for (int mode = 0; mode < 3; ++mode) {
         if (!outs[mode]) continue;
@@ -491,11 +479,12 @@ extern "C" int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, floa
             ctx->d_work0.as<float>(), np, n, 1.f / ((float)np * (float)np * (float)np), rad_a / c.pixel_size,
             20.f / c.pixel_size, dst);
         KERNEL_CHECK(ctx);
-        if (loc == CSPB_HOST)
+        if (loc == CSPB_HOST) {
             CU_TRY(ctx, cudaMemcpyAsync(outs[mode], dst, (size_t)n * n * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // d_work2 is reused by the next map
+        }
     }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (loc == CSPB_HOST || stats) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
