@@ -370,7 +370,7 @@ def run_b200_arm(a):
     peak, peak_src = measured_peaks()
     bytes_per_eval = 72.0 * n_band                       # 64 B gather + 8 B image per band sample
     score_gbs = (bytes_per_eval * score_units) / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
-    ins_bytes = 96.0 * (ccfg.pad ** 2) * _recon_band(n)  # per projection per symmetry operator
+    ins_bytes = 96.0 * (ccfg.pad ** 2) * _recon_band(n)  # per projection per literally inserted operator
     ins_gbs = (ins_bytes * ins_units) / (ins_ms * 1e-3) / 1e9 if ins_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -412,7 +412,7 @@ def _recon_band(n):
         for i in range(0, n // 2 + 1):
             if i == 0 and j < 0:
                 continue
-            if i * i + j * j <= (n // 2) ** 2:
+            if i * i + j * j <= (n // 2 - 1) ** 2:
                 c += 1
     return c
 

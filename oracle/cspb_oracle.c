@@ -579,7 +579,7 @@ void orc_recon_insert(orc_recon *rc, const float *imgs, const orc_row *rows, int
     float *tmp = (float *)malloc(sizeof(float) * (size_t)n * n);
     float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)n * nh);
     float rmax = (float)n * c->pixel_size / (c->resolution_limit > 0.f ? c->resolution_limit : 2.f * c->pixel_size);
-    if (rmax > (float)(n / 2)) rmax = (float)(n / 2);
+    if (rmax > (float)(n / 2 - 1)) rmax = (float)(n / 2 - 1); /* no weight ever lands on the Nyquist planes */
     const float l = (float)n * c->pixel_size, s2u = 1.f / (l * l);
     const float bk = c->score_weighting ? c->score_bfactor * 0.25f * s2u : 0.f;
     const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -107,9 +107,16 @@ struct cspb_ctx {
     int n_images = 0;
     int img_capacity = 0;
     DevBuf d_packed;        // n_images * n_slots float2
-    std::vector<float> sym; // 9*n_sym
+    std::vector<float> sym; // 9*n_sym, the full group as given
     DevBuf d_sym;
     int n_sym = 1;
+    // reconstruction-side decomposition G = H * R: H = operators that permute the voxel lattice
+    // (signed permutation matrices), applied once to the accumulated volume; R = right-coset
+    // representatives, applied per sample by the insertion kernel.
+    std::vector<float> sym_lit;  // 9*n_lit
+    std::vector<int> sym_lat_t;  // 9*n_lat, transposed (= inverse) integer matrices
+    DevBuf d_sym_lit, d_sym_lat;
+    int n_lit = 1, n_lat = 1;
 
     // scratch
     DevBuf d_stage, d_work0, d_work1, d_work2, d_stats, d_rows, d_evals, d_units, d_out, d_opt;
@@ -123,6 +130,8 @@ struct cspb_ctx {
     cspb_recon_cfg ccfg{};
     int rnp = 0;
     DevBuf d_acc[2];
+    DevBuf d_raw[2];      // deferred-symmetry accumulators (only when n_lat > 1)
+    bool raw_dirty = false;
     DevBuf d_shell;  // per-shell sums, Wiener terms, statistics rows
     int64_t recon_inserted = 0;
 };
@@ -131,6 +140,8 @@ int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...);
 // event bracket helpers (no-ops unless profiling is enabled)
 void prof_begin(cspb_ctx *ctx, int kind, int64_t units);
 void prof_end(cspb_ctx *ctx);
+// fold pending deferred-symmetry inserts into the main accumulators (recon.cu)
+int recon_flush_deferred(cspb_ctx *ctx);
 
 #define CU_TRY(ctx, expr)                                                                  \
     do {                                                                                   \

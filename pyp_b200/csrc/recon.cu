@@ -133,6 +133,35 @@ __device__ __forceinline__ float4 load_sym(const float4 *__restrict__ acc, int n
     return a;
 }
 
+// acc[v] += sum_h raw[h^-1 v] over the lattice-preserving symmetry operators (exact: trilinear
+// weights are invariant under signed axis permutations).  Sources are read through load_sym so the
+// x = 0 plane arrives complete; destinations on x = 0 are stored halved so that load_sym's later
+// folding restores the total.
+__global__ void lattice_sym_kernel(const float4 *__restrict__ raw, float4 *__restrict__ acc, int np, int xh,
+                                   const int *__restrict__ ht, int n_lat) {
+    const int c = np / 2;
+    const long long total = (long long)xh * np * np;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(k % xh), y = (int)((k / xh) % np) - c, z = (int)(k / ((long long)xh * np)) - c;
+        float sx = 0.f, sy = 0.f, sw = 0.f;
+        for (int h = 0; h < n_lat; ++h) {
+            const int *m = ht + 9 * h;
+            int ux = m[0] * x + m[1] * y + m[2] * z, uy = m[3] * x + m[4] * y + m[5] * z, uz = m[6] * x + m[7] * y + m[8] * z;
+            float sg = 1.f;
+            if (ux < 0) { ux = -ux; uy = -uy; uz = -uz; sg = -1.f; }
+            if (ux > c || uy < -c || uy >= c || uz < -c || uz >= c) continue;
+            const float4 v = load_sym(raw, np, xh, ux, uy, uz);
+            sx += v.x;
+            sy += sg * v.y;
+            sw += v.z;
+        }
+        if (x == 0 && y != -c && z != -c) { sx *= 0.5f; sy *= 0.5f; sw *= 0.5f; }
+        float4 a = acc[k];
+        a.x += sx; a.y += sy; a.z += sw;
+        acc[k] = a;
+    }
+}
+
 // per-shell sums for FSC: {sum Re(V1 V2*), sum |V1|^2, sum |V2|^2, sum (W1+W2), count, sumW1, sumW2}
 #define SHELL_Q 7
 __global__ void shell_stats_kernel(const float4 *__restrict__ a0, const float4 *__restrict__ a1, int np, int xh,
@@ -325,8 +354,28 @@ extern "C" int cspb_recon_begin(cspb_ctx *ctx, const cspb_recon_cfg *cfg) {
         int rc = cspb_set_symmetry(ctx, id, 1);
         if (rc) return rc;
     }
+    if (ctx->n_lat > 1)
+        for (int h = 0; h < 2; ++h) {
+            RESERVE(ctx, ctx->d_raw[h], bytes);
+            CU_TRY(ctx, cudaMemsetAsync(ctx->d_raw[h].p, 0, bytes, ctx->stream));
+        }
+    ctx->raw_dirty = false;
     ctx->recon_ready = true;
     ctx->recon_inserted = 0;
+    return 0;
+}
+
+int recon_flush_deferred(cspb_ctx *ctx) {
+    if (!ctx->recon_ready || !ctx->raw_dirty) return 0;
+    const int np = ctx->rnp, xh = np / 2 + 1;
+    const long long nvox = (long long)xh * np * np;
+    for (int h = 0; h < 2; ++h) {
+        lattice_sym_kernel<<<grid_for(nvox, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+            ctx->d_raw[h].as<float4>(), ctx->d_acc[h].as<float4>(), np, xh, ctx->d_sym_lat.as<int>(), ctx->n_lat);
+        KERNEL_CHECK(ctx);
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_raw[h].p, 0, (size_t)nvox * sizeof(float4), ctx->stream));
+    }
+    ctx->raw_dirty = false;
     return 0;
 }
 
@@ -340,6 +389,8 @@ extern "C" int cspb_recon_dims(const cspb_ctx *ctx, int *np_out, int64_t *floats
 
 extern "C" int cspb_recon_device_ptr(cspb_ctx *ctx, int half, void **ptr_out) {
     if (!ctx || !ctx->recon_ready || half < 0 || half > 1 || !ptr_out) return CSPB_E_ARG;
+    int rcf = recon_flush_deferred(ctx);
+    if (rcf) return rcf;
     *ptr_out = ctx->d_acc[half].p;
     return 0;
 }
@@ -354,7 +405,8 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
     if (chunk < 1) chunk = 1;
     if (chunk > 8192) chunk = 8192;
     if (n_images > chunk) chunk = ceil_div(n_images, ceil_div(n_images, chunk));  // even chunks
-    if (ctx->n_sym > INSERT_MAX_SYM) return cspb_fail(ctx, CSPB_E_ARG, "more than %d symmetry operators", INSERT_MAX_SYM);
+    if (ctx->n_lit > INSERT_MAX_SYM) return cspb_fail(ctx, CSPB_E_ARG, "more than %d symmetry operators", INSERT_MAX_SYM);
+    const bool deferred = ctx->n_lat > 1;
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;
@@ -381,35 +433,38 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
         a.n = n; a.count = cnt; a.np = np; a.xh = xh;
         a.padf = (float)c.pad;
         float rmax = (float)n * c.pixel_size / (c.resolution_limit > 0.f ? c.resolution_limit : 2.f * c.pixel_size);
-        if (rmax > (float)(n / 2)) rmax = (float)(n / 2);
+        if (rmax > (float)(n / 2 - 1)) rmax = (float)(n / 2 - 1);  // no weight ever lands on the Nyquist planes
         a.rmax2 = rmax * rmax;
         const float s2u = 1.f / (((float)n * c.pixel_size) * ((float)n * c.pixel_size));
         a.bfac_k = c.score_weighting ? c.score_bfactor * 0.25f * s2u : 0.f;
         a.avg_score = c.average_score;
         a.score_threshold = c.score_threshold;
         a.per_particle = c.per_particle_split;
-        a.sym = ctx->d_sym.as<float>();
-        a.n_sym = ctx->n_sym;
-        a.acc0 = ctx->d_acc[0].as<float4>();
-        a.acc1 = ctx->d_acc[1].as<float4>();
+        a.sym = ctx->d_sym_lit.as<float>();
+        a.n_sym = ctx->n_lit;
+        a.acc0 = (deferred ? ctx->d_raw[0] : ctx->d_acc[0]).as<float4>();
+        a.acc1 = (deferred ? ctx->d_raw[1] : ctx->d_acc[1]).as<float4>();
         a.tiles = ceil_div((long long)n * nh, 256);
         // one pass per half: the voxels one half touches (a half-sphere of radius np/2, 16 B each)
         // then fit in L2 and the vector atomics stop spilling to HBM
         for (int h = 0; h < 2; ++h) {
             a.half_sel = h;
-            prof_begin(ctx, CSPB_PROF_INSERT, h == 0 ? (int64_t)cnt * ctx->n_sym : 0);
+            prof_begin(ctx, CSPB_PROF_INSERT, h == 0 ? (int64_t)cnt * ctx->n_lit : 0);
             insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
             prof_end(ctx);
             KERNEL_CHECK(ctx);
         }
         if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    if (deferred && n_images > 0) ctx->raw_dirty = true;
     ctx->recon_inserted += n_images;
     return 0;
 }
 
 extern "C" int cspb_recon_get_dump(cspb_ctx *ctx, int half, float *out, int loc) {
     if (!ctx || !ctx->recon_ready || half < 0 || half > 1 || !out) return CSPB_E_ARG;
+    int rcf = recon_flush_deferred(ctx);
+    if (rcf) return rcf;
     const int np = ctx->rnp, xh = np / 2 + 1;
     const size_t bytes = (size_t)xh * np * np * sizeof(float4);
     CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_acc[half].p, bytes, loc == CSPB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
@@ -440,6 +495,8 @@ extern "C" int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, floa
     const int n = c.box, np = ctx->rnp, xh = np / 2 + 1;
     const int ns = n / 2 + 1;
     if (stats && n_shells != ns) return cspb_fail(ctx, CSPB_E_ARG, "stats needs box/2+1 = %d shells", ns);
+    int rcf = recon_flush_deferred(ctx);
+    if (rcf) return rcf;
     const long long nvox = (long long)xh * np * np;
     const float4 *a0 = ctx->d_acc[0].as<float4>(), *a1 = ctx->d_acc[1].as<float4>();
     // shell statistics -> Wiener terms, all on the device (oracle/SEMANTICS.md §merge3d)
@@ -492,6 +549,9 @@ extern "C" int cspb_recon_end(cspb_ctx *ctx) {
     if (!ctx) return CSPB_E_ARG;
     ctx->d_acc[0].release();
     ctx->d_acc[1].release();
+    ctx->d_raw[0].release();
+    ctx->d_raw[1].release();
+    ctx->raw_dirty = false;
     ctx->recon_ready = false;
     return 0;
 }

@@ -732,14 +732,79 @@ extern "C" int cspb_refine_set_ring_weights(cspb_ctx *ctx, const float *w, int n
     return 0;
 }
 
+static bool is_lattice_op(const float *m) {
+    for (int k = 0; k < 9; ++k) {
+        const float v = m[k], r = roundf(v);
+        if (fabsf(v - r) > 1e-4f || fabsf(r) > 1.f) return false;
+    }
+    return true;
+}
+
 extern "C" int cspb_set_symmetry(cspb_ctx *ctx, const float *mats, int n_mats) {
     if (!ctx || !mats || n_mats < 1) return CSPB_E_ARG;
+    if (ctx->recon_ready && ctx->raw_dirty) {
+        int rc = recon_flush_deferred(ctx);  // pending inserts belong to the previous group
+        if (rc) return rc;
+    }
     ctx->sym.assign(mats, mats + 9 * (size_t)n_mats);
     ctx->n_sym = n_mats;
+    // split G into lattice-preserving H and right-coset representatives R (g = h r)
+    std::vector<int> H;
+    for (int g = 0; g < n_mats; ++g)
+        if (is_lattice_op(mats + 9 * g)) H.push_back(g);
+    std::vector<int> R;
+    if (H.size() > 1) {
+        for (int g = 0; g < n_mats; ++g) {
+            bool covered = false;
+            for (int r : R) {
+                // q = g * r^T ; covered if q is in H
+                float q[9];
+                const float *G = mats + 9 * g, *Rm = mats + 9 * r;
+                for (int a = 0; a < 3; ++a)
+                    for (int c = 0; c < 3; ++c) q[3 * a + c] = G[3 * a] * Rm[3 * c] + G[3 * a + 1] * Rm[3 * c + 1] + G[3 * a + 2] * Rm[3 * c + 2];
+                if (!is_lattice_op(q)) continue;
+                for (int h : H) {
+                    float d = 0.f;
+                    for (int k = 0; k < 9; ++k) d = fmaxf(d, fabsf(q[k] - mats[9 * h + k]));
+                    if (d < 1e-3f) { covered = true; break; }
+                }
+                if (covered) break;
+            }
+            if (!covered) R.push_back(g);
+        }
+    }
+    ctx->sym_lit.clear();
+    ctx->sym_lat_t.clear();
+    if (H.size() > 1 && H.size() * R.size() == (size_t)n_mats) {
+        for (int r : R) ctx->sym_lit.insert(ctx->sym_lit.end(), mats + 9 * r, mats + 9 * r + 9);
+        for (int h : H)
+            for (int a = 0; a < 3; ++a)
+                for (int c = 0; c < 3; ++c) ctx->sym_lat_t.push_back((int)roundf(mats[9 * h + 3 * c + a]));  // transpose
+        ctx->n_lit = (int)R.size();
+        ctx->n_lat = (int)H.size();
+    } else {
+        ctx->sym_lit = ctx->sym;
+        ctx->n_lit = n_mats;
+        ctx->n_lat = 1;
+        const int id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        ctx->sym_lat_t.assign(id, id + 9);
+    }
     RESERVE(ctx, ctx->d_sym, ctx->sym.size() * sizeof(float));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_sym.p, ctx->sym.data(), ctx->sym.size() * sizeof(float),
-                                cudaMemcpyHostToDevice, ctx->stream));
+    RESERVE(ctx, ctx->d_sym_lit, ctx->sym_lit.size() * sizeof(float));
+    RESERVE(ctx, ctx->d_sym_lat, ctx->sym_lat_t.size() * sizeof(int));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_sym.p, ctx->sym.data(), ctx->sym.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_sym_lit.p, ctx->sym_lit.data(), ctx->sym_lit.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_sym_lat.p, ctx->sym_lat_t.data(), ctx->sym_lat_t.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->recon_ready && ctx->n_lat > 1) {
+        const int np = ctx->rnp, xh = np / 2 + 1;
+        const size_t bytes = (size_t)xh * np * np * sizeof(float4);
+        for (int h = 0; h < 2; ++h)
+            if (ctx->d_raw[h].bytes < bytes) {
+                RESERVE(ctx, ctx->d_raw[h], bytes);
+                CU_TRY(ctx, cudaMemsetAsync(ctx->d_raw[h].p, 0, bytes, ctx->stream));
+            }
+    }
     return 0;
 }
 
