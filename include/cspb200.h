@@ -154,6 +154,11 @@ int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int n_rows,
                             const int32_t *image_index, const float *poses6, int n_evals,
                             float *scores_out);
 
+/* Orientation grid of the global search (prompt 36/25): n_orient x {psi, theta, phi} degrees.
+ * The host builds it from the angular step and the symmetry symbol (pyp_b200/search_grid.py),
+ * the same grid is handed to the CPU oracle. */
+int cspb_refine_set_search_grid(cspb_ctx *ctx, const float *angles3, int n_orient);
+
 /* Full refine3d pass over the loaded images: optional global search, then batched local
  * refinement of the masked parameters.  rows are updated in place (PSI, THETA, PHI, X_SHIFT,
  * Y_SHIFT, [DEFOCUS], LOGP, SIGMA, SCORE, score change is returned in changes_out if non-NULL).

@@ -479,18 +479,71 @@ static float line_step(float f0, const float *fl) {
     return (a * 2.5f + b > 0.f) ? 2.5f : 0.f; /* convex fit: best end of [0, 2.5] under the model */
 }
 
-long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg) {
-    const int n = cfg->box, nh = n / 2 + 1;
-    int freem[NP] = {cfg->refine_psi, cfg->refine_theta, cfg->refine_phi, cfg->refine_x, cfg->refine_y, cfg->refine_defocus};
-    int n_free = 0;
-    for (int m = 0; m < NP; ++m) n_free += freem[m] ? 1 : 0;
+/* refine one starting pose x[6] in place; returns the final score (x100) and its band sums in o4.
+   The better of {refined, start} is kept.  *evals is incremented per objective evaluation. */
+static float refine_one(const orc_ref *r, const float *spec, const orc_row *row, float *x, const int *freem,
+                        const orc_refine_cfg *cfg, float *o4, long long *evals) {
+    const int n = cfg->box;
     float lo, hi;
     orc_band_limits(cfg, &lo, &hi);
-    const float h_ang = 0.35f * 57.29578f / hi;                 /* ~1/3 of the angular resolution at r_hi */
+    int n_free = 0;
+    for (int m = 0; m < NP; ++m) n_free += freem[m] ? 1 : 0;
+    const float h_ang = 0.35f * 57.29578f / hi;                    /* ~1/3 of the angular resolution at r_hi */
     const float h_shift = 0.07f * (float)n / hi * cfg->pixel_size; /* Angstrom */
     const float h_def = cfg->defocus_step > 0.f ? cfg->defocus_step : 50.f;
     const int iters = n_free > 0 ? (cfg->local_iterations > 0 ? cfg->local_iterations : 8) : 0;
     const int late = iters / 2 + 1; /* stencil steps stay constant for the first half, then shrink */
+    float h[NP] = {h_ang, h_ang, h_ang, h_shift, h_shift, h_def};
+    float d[NP], q[NP];
+    const float x_start[NP] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+    for (int it = 0; it < iters; ++it) {
+        const float f0 = orc_score(r, spec, row, x, cfg, o4) * 0.01f;
+        (*evals)++;
+        for (int m = 0; m < NP; ++m) {
+            d[m] = 0.f;
+            if (!freem[m]) continue;
+            memcpy(q, x, sizeof q);
+            q[m] = x[m] + h[m];
+            const float fp = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+            q[m] = x[m] - h[m];
+            const float fm = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+            (*evals) += 2;
+            d[m] = newton_step(f0, fp, fm, h[m]);
+        }
+        float fl[NL];
+        for (int l = 0; l < NL; ++l) {
+            for (int m = 0; m < NP; ++m) q[m] = x[m] + LS_T[l] * d[m];
+            fl[l] = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+            (*evals)++;
+        }
+        const float t = line_step(f0, fl);
+        for (int m = 0; m < NP; ++m) x[m] += t * d[m];
+        if (it + 1 >= late)
+            for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
+    }
+    /* final: score the refined and the starting pose, never return a worse one */
+    float o4s[4];
+    float sc = orc_score(r, spec, row, x, cfg, o4);
+    const float sc_start = orc_score(r, spec, row, x_start, cfg, o4s);
+    (*evals) += 2;
+    if (sc < sc_start) { memcpy(x, x_start, sizeof x_start); memcpy(o4, o4s, sizeof o4s); sc = sc_start; }
+    return sc;
+}
+
+static void write_row(orc_row *row, const float *x, float sc, const float *o4, int nband, int refine_defocus) {
+    row->psi = wrap360(x[0]);
+    row->theta = x[1];
+    row->phi = wrap360(x[2]);
+    row->x_shift = x[3];
+    row->y_shift = x[4];
+    if (refine_defocus) { row->defocus_1 += x[5]; row->defocus_2 += x[5]; }
+    row->score = sc;
+    stats_from(o4, nband, &row->sigma, &row->logp);
+}
+
+long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    const int freem[NP] = {cfg->refine_psi, cfg->refine_theta, cfg->refine_phi, cfg->refine_x, cfg->refine_y, cfg->refine_defocus};
     const int nband = orc_band_count(cfg);
     long long evals = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : evals)
@@ -498,50 +551,150 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
         const float *spec = specs + 2 * (size_t)k * n * nh;
         orc_row *row = &rows[k];
         float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f};
-        float h[NP] = {h_ang, h_ang, h_ang, h_shift, h_shift, h_def};
-        float d[NP];
-        float q[NP], o4[4];
-        const float x_start[NP] = {x[0], x[1], x[2], x[3], x[4], x[5]};
-        for (int it = 0; it < iters; ++it) {
-            const float f0 = orc_score(r, spec, row, x, cfg, o4) * 0.01f;
-            evals++;
-            for (int m = 0; m < NP; ++m) {
-                d[m] = 0.f;
-                if (!freem[m]) continue;
-                memcpy(q, x, sizeof q);
-                q[m] = x[m] + h[m];
-                const float fp = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
-                q[m] = x[m] - h[m];
-                const float fm = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
-                evals += 2;
-                d[m] = newton_step(f0, fp, fm, h[m]);
-            }
-            float fl[NL];
-            for (int l = 0; l < NL; ++l) {
-                for (int m = 0; m < NP; ++m) q[m] = x[m] + LS_T[l] * d[m];
-                fl[l] = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
-                evals++;
-            }
-            const float t = line_step(f0, fl);
-            for (int m = 0; m < NP; ++m) x[m] += t * d[m];
-            if (it + 1 >= late)
-                for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
-        }
-        /* final: score the refined and the starting pose, never return a worse one */
-        float o4s[4];
-        float sc = orc_score(r, spec, row, x, cfg, o4);
-        const float sc_start = orc_score(r, spec, row, x_start, cfg, o4s);
-        evals += 2;
-        if (sc < sc_start) { memcpy(x, x_start, sizeof x); memcpy(o4, o4s, sizeof o4); sc = sc_start; }
-        row->psi = wrap360(x[0]);
-        row->theta = x[1];
-        row->phi = wrap360(x[2]);
-        row->x_shift = x[3];
-        row->y_shift = x[4];
-        if (cfg->refine_defocus) { row->defocus_1 += x[5]; row->defocus_2 += x[5]; }
-        row->score = sc;
-        stats_from(o4, nband, &row->sigma, &row->logp);
+        float o4[4];
+        long long ev = 0;
+        const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev);
+        evals += ev;
+        write_row(row, x, sc, o4, nband, cfg->refine_defocus);
     }
+    return evals;
+}
+
+/* ================================================================ global search */
+static int pick_reduced_box(int need, int n) {
+    const int sizes[] = {16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024};
+    for (unsigned k = 0; k < sizeof sizes / sizeof sizes[0]; ++k)
+        if (sizes[k] >= need) return sizes[k] < n ? sizes[k] : n;
+    return n;
+}
+
+typedef struct { float score, sx, sy; int orient; } hit_t;
+
+/* cisTEM-style global search (refine3d prompt 36): every grid orientation is scored by the peak
+   of the cross-correlation map over shifts, computed by FFT in a box reduced to the search
+   resolution; the K best hits are refined locally and the best refined pose wins. */
+long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg,
+                            const float *angles3, int n_orient) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    const float npx = (float)n * cfg->pixel_size;
+    float r_s = cfg->search_high_res > 0.f ? npx / cfg->search_high_res : hi;
+    if (r_s > hi) r_s = hi;
+    if (r_s < lo + 2.f) r_s = fminf(lo + 2.f, hi);
+    /* search samples */
+    int n_ss = 0, i_max = 0;
+    int *si = (int *)malloc(sizeof(int) * (size_t)n * nh), *sj = (int *)malloc(sizeof(int) * (size_t)n * nh);
+    for (int j = -n / 2; j < n / 2; ++j)
+        for (int i = 0; i <= n / 2; ++i) {
+            const float r2 = (float)(i * i + j * j);
+            if (r2 < lo * lo || r2 > hi * hi || r2 > r_s * r_s) continue;
+            si[n_ss] = i; sj[n_ss] = j; ++n_ss;
+            if (i > i_max) i_max = i;
+            if (abs(j) > i_max) i_max = abs(j);
+        }
+    const int nb = pick_reduced_box(2 * (i_max + 2), n);
+    const float red = (float)nb / (float)n;
+    int wx = (int)ceilf(cfg->search_range_x / cfg->pixel_size * red), wy = (int)ceilf(cfg->search_range_y / cfg->pixel_size * red);
+    const int wmax = nb / 2 - 2;
+    if (wx < 1) wx = 1;
+    if (wy < 1) wy = 1;
+    if (wx > wmax) wx = wmax;
+    if (wy > wmax) wy = wmax;
+    const int wxs = 2 * wx + 1, wys = 2 * wy + 1;
+    int K = cfg->best_matches > 0 ? cfg->best_matches : 20;
+    if (K > n_orient) K = n_orient;
+    const float shift_scale = cfg->pixel_size / red;
+    const int nband = orc_band_count(cfg);
+    /* slices are particle independent */
+    float *Pall = (float *)malloc(sizeof(float) * 2 * (size_t)n_orient * n_ss);
+    for (int o = 0; o < n_orient; ++o) {
+        float m[9];
+        orc_euler_matrix(angles3[3 * o], angles3[3 * o + 1], angles3[3 * o + 2], m);
+        for (int s = 0; s < n_ss; ++s)
+            ref_interp(r, (m[0] * si[s] + m[1] * sj[s]) * r->pad, (m[3] * si[s] + m[4] * sj[s]) * r->pad,
+                       (m[6] * si[s] + m[7] * sj[s]) * r->pad, &Pall[2 * ((size_t)o * n_ss + s)], &Pall[2 * ((size_t)o * n_ss + s) + 1]);
+    }
+    long long evals = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : evals)
+    for (int k = 0; k < n_img; ++k) {
+        const float *spec = specs + 2 * (size_t)k * n * nh;
+        orc_row *row = &rows[k];
+        const ctfc c = ctf_make(row, n);
+        float *G = (float *)malloc(sizeof(float) * 2 * (size_t)n_ss), *c2m = (float *)malloc(sizeof(float) * (size_t)n_ss);
+        float A = 0.f;
+        for (int s = 0; s < n_ss; ++s) {
+            const int jj = sj[s] < 0 ? sj[s] + n : sj[s];
+            const float fr = spec[2 * ((size_t)jj * nh + si[s])], fi = spec[2 * ((size_t)jj * nh + si[s]) + 1];
+            const float ctf = ctf_eval(&c, si[s], sj[s], 0.f);
+            const float mult = si[s] > 0 ? 2.f : 1.f;
+            G[2 * s] = fr * ctf; G[2 * s + 1] = fi * ctf;
+            c2m[s] = ctf * ctf * mult;
+            A += mult * (fr * fr + fi * fi);
+        }
+        hit_t *top = (hit_t *)malloc(sizeof(hit_t) * (size_t)K);
+        for (int t = 0; t < K; ++t) { top[t].score = -1e30f; top[t].sx = top[t].sy = 0.f; top[t].orient = -1; }
+        cd *S = (cd *)malloc(sizeof(cd) * (size_t)nb * nb);
+        for (int o = 0; o < n_orient; ++o) {
+            const float *P = Pall + 2 * (size_t)o * n_ss;
+            memset(S, 0, sizeof(cd) * (size_t)nb * nb);
+            float B = 0.f;
+            for (int s = 0; s < n_ss; ++s) {
+                const float pr = P[2 * s], pi = P[2 * s + 1];
+                const float xr = G[2 * s] * pr + G[2 * s + 1] * pi, xi = G[2 * s + 1] * pr - G[2 * s] * pi;
+                const int i = si[s], j = sj[s];
+                const int iy = j < 0 ? j + nb : j;
+                S[(size_t)iy * nb + i].re = xr;
+                S[(size_t)iy * nb + i].im = xi;
+                if (i > 0) { /* Friedel mate fills the other half plane */
+                    const int my = (nb - iy) % nb, mx = nb - i;
+                    S[(size_t)my * nb + mx].re = xr;
+                    S[(size_t)my * nb + mx].im = -xi;
+                }
+                B += c2m[s] * (pr * pr + pi * pi);
+            }
+            fft2_full(S, nb, +1);
+            float best = -1e30f;
+            int bidx = 0;
+            for (int w = 0; w < wxs * wys; ++w) {
+                const int dy = w / wxs - wy, dx = w % wxs - wx;
+                const float v = (float)S[(size_t)((dy + nb) % nb) * nb + ((dx + nb) % nb)].re;
+                if (v > best) { best = v; bidx = w; }
+            }
+            const int dy = bidx / wxs - wy, dx = bidx % wxs - wx;
+#define AT(ddx, ddy) ((float)S[(size_t)(((ddy) + nb) % nb) * nb + (((ddx) + nb) % nb)].re)
+            const float v0 = best, xm = AT(dx - 1, dy), xp = AT(dx + 1, dy), ym = AT(dx, dy - 1), yp = AT(dx, dy + 1);
+#undef AT
+            float ox = 0.f, oy = 0.f, peak = v0;
+            const float cx = xm - 2.f * v0 + xp, cy = ym - 2.f * v0 + yp;
+            if (cx < 0.f) { ox = 0.5f * (xm - xp) / cx; if (ox < -0.5f) ox = -0.5f; if (ox > 0.5f) ox = 0.5f; peak -= 0.25f * (xm - xp) * ox; }
+            if (cy < 0.f) { oy = 0.5f * (ym - yp) / cy; if (oy < -0.5f) oy = -0.5f; if (oy > 0.5f) oy = 0.5f; peak -= 0.25f * (ym - yp) * oy; }
+            const float den = A * B;
+            const float score = den > 0.f ? 100.f * peak / sqrtf(den) : 0.f;
+            if (score > top[K - 1].score) {
+                int t = K - 1;
+                while (t > 0 && score > top[t - 1].score) { top[t] = top[t - 1]; --t; }
+                top[t].score = score; top[t].sx = ((float)dx + ox) * shift_scale; top[t].sy = ((float)dy + oy) * shift_scale; top[t].orient = o;
+            }
+        }
+        long long ev = n_orient;
+        /* refine every hit in all five pose parameters; keep the best */
+        const int freem[NP] = {1, 1, 1, 1, 1, cfg->refine_defocus};
+        float bestsc = -1e30f, xb[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f}, ob[4] = {0, 0, 0, 0};
+        for (int t = 0; t < K; ++t) {
+            float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f}, o4[4];
+            if (top[t].orient >= 0) {
+                x[0] = angles3[3 * top[t].orient]; x[1] = angles3[3 * top[t].orient + 1]; x[2] = angles3[3 * top[t].orient + 2];
+                x[3] = top[t].sx; x[4] = top[t].sy;
+            }
+            const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev);
+            if (sc > bestsc) { bestsc = sc; memcpy(xb, x, sizeof xb); memcpy(ob, o4, sizeof ob); }
+        }
+        evals += ev;
+        write_row(row, xb, bestsc, ob, nband, cfg->refine_defocus);
+        free(S); free(top); free(G); free(c2m);
+    }
+    free(Pall); free(si); free(sj);
     return evals;
 }
 

@@ -45,6 +45,9 @@ typedef struct orc_refine_cfg {
     float defocus_step;
     int32_t refine_psi, refine_theta, refine_phi, refine_x, refine_y, refine_defocus;
     int32_t apply_mask, normalize, invert_contrast, whiten, local_iterations;
+    /* global search (prompts 24-28, 36) */
+    float search_high_res, search_range_x, search_range_y;
+    int32_t best_matches, global_search;
 } orc_refine_cfg;
 
 typedef struct orc_recon_cfg {
@@ -87,6 +90,11 @@ float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const f
  * particles when built with -fopenmp.  Returns number of objective evaluations. */
 long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n,
                            const orc_refine_cfg *cfg);
+
+/* ---- global search over the orientation grid angles3 (n_orient x psi,theta,phi), then local
+ * refinement of the best_matches hits.  Returns number of objective evaluations. */
+long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows, int n,
+                            const orc_refine_cfg *cfg, const float *angles3, int n_orient);
 
 /* ---- reconstruction */
 orc_recon *orc_recon_create(const orc_recon_cfg *cfg);

@@ -38,6 +38,8 @@ class RefineCfg(C.Structure):
         ("refine_x", C.c_int32), ("refine_y", C.c_int32), ("refine_defocus", C.c_int32),
         ("apply_mask", C.c_int32), ("normalize", C.c_int32), ("invert_contrast", C.c_int32),
         ("whiten", C.c_int32), ("local_iterations", C.c_int32),
+        ("search_high_res", C.c_float), ("search_range_x", C.c_float), ("search_range_y", C.c_float),
+        ("best_matches", C.c_int32), ("global_search", C.c_int32),
     ]
 
 
@@ -95,6 +97,7 @@ def lib():
             "orc_prepare_image": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
+            "orc_global_search": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg), vp, i]),
             "orc_recon_create": (vp, [C.POINTER(ReconCfg)]),
             "orc_recon_free": (None, [vp]),
             "orc_recon_insert": (None, [vp, vp, vp, i, vp, i]),
@@ -206,6 +209,14 @@ def refine_local(ref, specs, rows, cfg):
     specs = np.ascontiguousarray(specs, dtype=np.complex64)
     rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
     ne = lib().orc_refine_local(ref._h, _p(specs), _p(rows), rows.size, C.byref(cfg))
+    return rows, int(ne)
+
+
+def global_search(ref, specs, rows, cfg, angles3):
+    specs = np.ascontiguousarray(specs, dtype=np.complex64)
+    rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+    ang = _f32(angles3).reshape(-1, 3)
+    ne = lib().orc_global_search(ref._h, _p(specs), _p(rows), rows.size, C.byref(cfg), _p(ang), ang.shape[0])
     return rows, int(ne)
 
 

@@ -120,6 +120,10 @@ def run(p, out=sys.stdout):
         if st.size:
             eng.set_ring_weights(statistics.ring_weights_from_statistics(st, box, p["pixel_size"]))
     eng.set_symmetry(p["symmetry"])
+    if p["global_search"]:
+        from ..search_grid import search_grid
+
+        eng.set_search_grid(search_grid(p["angular_step"], p["symmetry"]))
     eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
     pos = rows["position_in_stack"].astype(np.int64)
     _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max())) if rows.size else (None, np.zeros((0, box, box), np.float32))

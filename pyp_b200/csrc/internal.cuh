@@ -118,6 +118,10 @@ struct cspb_ctx {
     DevBuf d_sym_lit, d_sym_lat;
     int n_lit = 1, n_lat = 1;
 
+    // global-search orientation grid (psi, theta, phi) and hit buffer
+    DevBuf d_grid, d_hits;
+    int n_grid = 0;
+
     // scratch
     DevBuf d_stage, d_work0, d_work1, d_work2, d_stats, d_rows, d_evals, d_units, d_out, d_opt;
     DevBuf d_tw;  // twiddle tables

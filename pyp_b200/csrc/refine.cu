@@ -396,13 +396,28 @@ struct OptState {
     float pad_[3];
 };
 
-__global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n, OptState *__restrict__ st, float h_ang,
-                                float h_shift, float h_def) {
+struct SearchHit {
+    float score, sx, sy;
+    int orient;
+};
+
+// state k belongs to image k / K.  With hits (global search) the state starts at candidate k % K.
+__global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n_states, int K, const SearchHit *__restrict__ hits,
+                                const float *__restrict__ angles3, OptState *__restrict__ st, float h_ang, float h_shift,
+                                float h_def) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= n_states) return;
+    const cspb_row row = rows[k / K];
     OptState s;
-    s.x[0] = rows[k].psi; s.x[1] = rows[k].theta; s.x[2] = rows[k].phi;
-    s.x[3] = rows[k].x_shift; s.x[4] = rows[k].y_shift; s.x[5] = 0.f;
+    s.x[0] = row.psi; s.x[1] = row.theta; s.x[2] = row.phi;
+    s.x[3] = row.x_shift; s.x[4] = row.y_shift; s.x[5] = 0.f;
+    if (hits) {
+        const SearchHit h = hits[k];
+        if (h.orient >= 0) {
+            s.x[0] = angles3[3 * h.orient]; s.x[1] = angles3[3 * h.orient + 1]; s.x[2] = angles3[3 * h.orient + 2];
+            s.x[3] = h.sx; s.x[4] = h.sy;
+        }
+    }
     s.h[0] = s.h[1] = s.h[2] = h_ang;
     s.h[3] = s.h[4] = h_shift;
     s.h[5] = h_def;
@@ -412,7 +427,7 @@ __global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n, OptSta
 }
 
 // free_mask bit m set -> parameter m is refined.  n_free = popcount.  evals per image NE = 1+2*n_free
-__global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int free_mask, int NE, int PB,
+__global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int K, int free_mask, int NE, int PB,
                                    float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -431,7 +446,7 @@ __global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int f
     const int upi = (NE + PB - 1) / PB;
     for (int c = 0; c < upi; ++c) {
         ScoreUnit un;
-        un.image = k;
+        un.image = k / K;
         un.first_eval = k * NE + c * PB;
         un.count = min(PB, NE - c * PB);
         un.pad_ = 0;
@@ -477,7 +492,7 @@ __device__ __forceinline__ float line_step(float f0, const float *fl) {
 }
 
 // consume stencil scores, propose the Newton direction, emit line-search poses
-__global__ void opt_step_kernel(OptState *__restrict__ st, int n, int free_mask, int NE, const float4 *__restrict__ sc,
+__global__ void opt_step_kernel(OptState *__restrict__ st, int n, int K, int free_mask, int NE, const float4 *__restrict__ sc,
                                 float *__restrict__ poses6_ls, ScoreUnit *__restrict__ units_ls) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -498,7 +513,7 @@ __global__ void opt_step_kernel(OptState *__restrict__ st, int n, int free_mask,
     for (int l = 0; l < OPT_NL; ++l)
         for (int m = 0; m < OPT_NP; ++m) q[l * 6 + m] = s.x[m] + tl[l] * s.d[m];
     ScoreUnit un;
-    un.image = k; un.first_eval = k * OPT_NL; un.count = OPT_NL; un.pad_ = 0;
+    un.image = k / K; un.first_eval = k * OPT_NL; un.count = OPT_NL; un.pad_ = 0;
     units_ls[k] = un;
 }
 
@@ -515,7 +530,7 @@ __global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4
 }
 
 // final: evaluate the refined pose and the starting pose (2 evals per image)
-__global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, float *__restrict__ poses6,
+__global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, int K, float *__restrict__ poses6,
                                        ScoreUnit *__restrict__ units) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -524,7 +539,7 @@ __global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, f
         poses6[(long long)k * 12 + 6 + m] = st[k].x0[m];
     }
     ScoreUnit un;
-    un.image = k; un.first_eval = 2 * k; un.count = 2; un.pad_ = 0;
+    un.image = k / K; un.first_eval = 2 * k; un.count = 2; un.pad_ = 0;
     units[k] = un;
 }
 
@@ -534,41 +549,57 @@ __device__ __forceinline__ float wrap360(float a) {
     return a;
 }
 
-__global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n, const float4 *__restrict__ sc,
+// one thread per image: among its K refined candidates (and each candidate's starting pose) keep
+// the best score; ties keep the earlier candidate
+__global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n_images, int K, const float4 *__restrict__ sc,
                                       int n_samples, int refine_defocus, cspb_row *__restrict__ rows,
                                       cspb_row *__restrict__ changes) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const OptState s = st[k];
-    cspb_row r = rows[k];
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= n_images) return;
+    cspb_row r = rows[img];
     const cspb_row old = r;
-    float4 v = sc[2 * k];
-    const float4 v0 = sc[2 * k + 1];
-    const float *x = s.x;
-    if (100.f * cc_of(v) < 100.f * cc_of(v0)) { v = v0; x = s.x0; }  // never return a worse pose
-    r.psi = wrap360(x[0]);
-    r.theta = x[1];
-    r.phi = wrap360(x[2]);
-    r.x_shift = x[3];
-    r.y_shift = x[4];
+    float best = -1e30f;
+    float4 vbest = make_float4(0.f, 0.f, 0.f, 0.f);
+    float xb[OPT_NP] = {r.psi, r.theta, r.phi, r.x_shift, r.y_shift, 0.f};
+    float start_score = 0.f;
+    for (int c = 0; c < K; ++c) {
+        const int k = img * K + c;
+        const OptState s = st[k];
+        float4 v = sc[2 * k];
+        const float4 v0 = sc[2 * k + 1];
+        const float *x = s.x;
+        if (100.f * cc_of(v) < 100.f * cc_of(v0)) { v = v0; x = s.x0; }  // never return a worse pose
+        if (c == 0) start_score = 100.f * cc_of(v0);
+        const float f = 100.f * cc_of(v);
+        if (f > best) {
+            best = f;
+            vbest = v;
+            for (int m = 0; m < OPT_NP; ++m) xb[m] = x[m];
+        }
+    }
+    r.psi = wrap360(xb[0]);
+    r.theta = xb[1];
+    r.phi = wrap360(xb[2]);
+    r.x_shift = xb[3];
+    r.y_shift = xb[4];
     if (refine_defocus) {
-        r.defocus_1 += x[5];
-        r.defocus_2 += x[5];
+        r.defocus_1 += xb[5];
+        r.defocus_2 += xb[5];
     }
     float sigma, logp;
-    score_stats(v, n_samples, &sigma, &logp);
-    r.score = 100.f * cc_of(v);
+    score_stats(vbest, n_samples, &sigma, &logp);
+    r.score = best;
     r.sigma = sigma;
     r.logp = logp;
-    rows[k] = r;
+    rows[img] = r;
     if (changes) {
         cspb_row c = r;
         c.psi = r.psi - old.psi; c.theta = r.theta - old.theta; c.phi = r.phi - old.phi;
         c.x_shift = r.x_shift - old.x_shift; c.y_shift = r.y_shift - old.y_shift;
         c.defocus_1 = r.defocus_1 - old.defocus_1; c.defocus_2 = r.defocus_2 - old.defocus_2;
-        c.score = r.score - 100.f * cc_of(v0);
+        c.score = r.score - start_score;
         c.logp = r.logp - old.logp; c.sigma = r.sigma - old.sigma;
-        changes[k] = c;
+        changes[img] = c;
     }
 }
 
@@ -1042,7 +1073,10 @@ extern "C" int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, flo
     return cspb_refine_score_poses(ctx, rows, n, idx.data(), poses.data(), n, scores_out);
 }
 
-// enqueue the whole local refinement on the stream; rows/ctf already on the device
+int search_enqueue(cspb_ctx *ctx, const CtfCoef *d_ctf, const float *d_angles3, int n_orient, int K, void *d_hits);
+
+// enqueue the whole refinement on the stream; rows/ctf already on the device.  With global search
+// the grid is searched first and the K best hits per image are refined as separate states.
 static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_ctf, int n, cspb_row *d_changes,
                                 int64_t *n_evals_out) {
     const cspb_refine_cfg &c = ctx->rcfg;
@@ -1053,50 +1087,77 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     if (c.refine_x) free_mask |= 8;
     if (c.refine_y) free_mask |= 16;
     if (c.refine_defocus) free_mask |= 32;
+    int64_t evals = 0;
+    int K = 1;
+    const SearchHit *d_hits = nullptr;
+    const float *d_angles = nullptr;
+    if (c.global_search) {
+        if (ctx->n_grid <= 0) return cspb_fail(ctx, CSPB_E_STATE, "global search needs cspb_refine_set_search_grid first");
+        K = c.best_matches > 0 ? c.best_matches : 20;
+        if (K > ctx->n_grid) K = ctx->n_grid;
+        RESERVE(ctx, ctx->d_hits, (size_t)n * K * sizeof(SearchHit));
+        d_angles = ctx->d_grid.as<float>();
+        int rc = search_enqueue(ctx, d_ctf, d_angles, ctx->n_grid, K, ctx->d_hits.p);
+        if (rc) return rc;
+        d_hits = ctx->d_hits.as<SearchHit>();
+        evals += (int64_t)n * ctx->n_grid;
+        free_mask |= 31;  // the hits are refined in all five pose parameters
+    }
     int n_free = 0;
     for (int m = 0; m < OPT_NP; ++m) n_free += (free_mask >> m) & 1;
+    const int ns = n * K;  // optimiser states
     const int NE = 1 + 2 * n_free, PB = 4;
     const int upi = (NE + PB - 1) / PB;
     const bool ddef = c.refine_defocus != 0;
-    const int iters = (c.local_refine && n_free > 0) ? (c.local_iterations > 0 ? c.local_iterations : 8) : 0;
+    const bool do_local = (c.local_refine || c.global_search) && n_free > 0;
+    const int iters = do_local ? (c.local_iterations > 0 ? c.local_iterations : 8) : 0;
     const int late = iters / 2 + 1;  // stencil steps stay constant for the first half, then shrink
-    RESERVE(ctx, ctx->d_opt, (size_t)n * sizeof(OptState));
-    RESERVE(ctx, ctx->d_evals, (size_t)n * (NE + OPT_NL + 2) * 6 * sizeof(float));
-    RESERVE(ctx, ctx->d_units, (size_t)n * (upi + 1) * sizeof(ScoreUnit));
-    RESERVE(ctx, ctx->d_out, (size_t)n * (NE + OPT_NL + 2) * sizeof(float4));
+    RESERVE(ctx, ctx->d_opt, (size_t)ns * sizeof(OptState));
+    RESERVE(ctx, ctx->d_evals, (size_t)ns * (NE + OPT_NL + 2) * 6 * sizeof(float));
+    RESERVE(ctx, ctx->d_units, (size_t)ns * (upi + 1) * sizeof(ScoreUnit));
+    RESERVE(ctx, ctx->d_out, (size_t)ns * (NE + OPT_NL + 2) * sizeof(float4));
     OptState *st = ctx->d_opt.as<OptState>();
-    float *ev = ctx->d_evals.as<float>(), *ev_ls = ev + (size_t)n * NE * 6;
-    ScoreUnit *un = ctx->d_units.as<ScoreUnit>(), *un_ls = un + (size_t)n * upi;
-    float4 *out = ctx->d_out.as<float4>(), *out_ls = out + (size_t)n * NE;
+    float *ev = ctx->d_evals.as<float>(), *ev_ls = ev + (size_t)ns * NE * 6;
+    ScoreUnit *un = ctx->d_units.as<ScoreUnit>(), *un_ls = un + (size_t)ns * upi;
+    float4 *out = ctx->d_out.as<float4>(), *out_ls = out + (size_t)ns * NE;
     const float r_hi = ctx->plan.r_hi;
     const float h_ang = 0.35f * 57.29578f / r_hi;                      // ~1/3 of the angular resolution at r_hi
     const float h_shift = 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
     const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
-    const int g = ceil_div(n, 128);
-    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, n, st, h_ang, h_shift, h_def);
+    const int g = ceil_div(ns, 128);
+    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, ns, K, d_hits, d_angles, st, h_ang, h_shift, h_def);
     KERNEL_CHECK(ctx);
-    int64_t evals = 0;
     for (int it = 0; it < iters; ++it) {
-        opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, n, free_mask, NE, PB, ev, un);
+        opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, PB, ev, un);
         KERNEL_CHECK(ctx);
-        int rc = launch_score(ctx, un, n * upi, PB, ev, d_ctf, out, ddef, (int64_t)n * NE);
+        int rc = launch_score(ctx, un, ns * upi, PB, ev, d_ctf, out, ddef, (int64_t)ns * NE);
         if (rc) return rc;
-        opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, n, free_mask, NE, out, ev_ls, un_ls);
+        opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, out, ev_ls, un_ls);
         KERNEL_CHECK(ctx);
-        rc = launch_score(ctx, un_ls, n, PB, ev_ls, d_ctf, out_ls, ddef, (int64_t)n * OPT_NL);
+        rc = launch_score(ctx, un_ls, ns, PB, ev_ls, d_ctf, out_ls, ddef, (int64_t)ns * OPT_NL);
         if (rc) return rc;
-        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out_ls, it + 1 >= late ? 0.6f : 1.f);
+        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, out_ls, it + 1 >= late ? 0.6f : 1.f);
         KERNEL_CHECK(ctx);
-        evals += (int64_t)n * (NE + OPT_NL);
+        evals += (int64_t)ns * (NE + OPT_NL);
     }
-    opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, n, ev, un);
+    opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, ev, un);
     KERNEL_CHECK(ctx);
-    int rc = launch_score(ctx, un, n, 4, ev, d_ctf, out, ddef, 2 * (int64_t)n);
+    int rc = launch_score(ctx, un, ns, 4, ev, d_ctf, out, ddef, 2 * (int64_t)ns);
     if (rc) return rc;
-    evals += 2 * (int64_t)n;
-    opt_write_rows_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes);
+    evals += 2 * (int64_t)ns;
+    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes);
     KERNEL_CHECK(ctx);
     if (n_evals_out) *n_evals_out = evals;
+    return 0;
+}
+
+extern "C" int cspb_refine_set_search_grid(cspb_ctx *ctx, const float *angles3, int n_orient) {
+    if (!ctx || (!angles3 && n_orient > 0) || n_orient < 0) return CSPB_E_ARG;
+    ctx->n_grid = n_orient;
+    if (n_orient == 0) return 0;
+    RESERVE(ctx, ctx->d_grid, (size_t)n_orient * 3 * sizeof(float));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_grid.p, angles3, (size_t)n_orient * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

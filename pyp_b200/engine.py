@@ -171,6 +171,12 @@ class Engine:
         self._ck(self._l.cspb_refine_score_poses(self._h, ptr(rows), rows.size, ptr(idx), ptr(poses), idx.size, ptr(out)))
         return out
 
+    def set_search_grid(self, angles3):
+        """Global-search orientation grid: (n, 3) array of (psi, theta, phi) in degrees."""
+        a = np.ascontiguousarray(angles3, dtype=np.float32).reshape(-1, 3)
+        self._ck(self._l.cspb_refine_set_search_grid(self._h, ptr(a), int(a.shape[0])))
+        return int(a.shape[0])
+
     def refine(self, rows, want_changes=False):
         """Run refine3d's search over the loaded images.  Returns (rows, changes|None, n_evals)."""
         rows = np.array(rows, dtype=ROW_DTYPE, copy=True)

@@ -167,6 +167,35 @@ def test_local_refinement_matches_oracle(engine, oracle):
     assert np.allclose(changes["psi"], got["psi"] - start["psi"], atol=1e-4)
 
 
+def test_global_search_matches_oracle(engine, oracle):
+    """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally.
+    Same grid, same band, same box reduction on both sides; the best orientation/shift choice must
+    be identical for >= 99.9 % of the particles."""
+    from pyp_b200.search_grid import search_grid
+
+    px = 1.35
+    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(
+        engine, oracle, n_part=24, global_search=1, local_refine=0, search_high_res=8 * px, search_range_x=6 * px,
+        search_range_y=6 * px, best_matches=5)
+    grid = search_grid(20.0, "C1")
+    engine.set_search_grid(grid)
+    start = rows.copy()
+    for k in ("psi", "theta", "phi", "x_shift", "y_shift"):
+        start[k] = 0
+    got, _, n_ev = engine.refine(start)
+    want, n_ev_o = oracle.global_search(ref, specs, start.astype(oracle.ROW_DTYPE), ocfg, grid)
+    assert n_ev == n_ev_o == rows.size * (grid.shape[0] + 5 * (8 * 14 + 2))
+    ang = angular_distance(got, want)
+    sh = np.hypot(got["x_shift"] - want["x_shift"], got["y_shift"] - want["y_shift"])
+    same = (ang < 2e-2) & (sh < 2e-2)
+    assert same.mean() >= 0.999, (np.sort(ang)[-3:], np.sort(sh)[-3:])
+    rel = np.abs(got["score"] - want["score"]) / np.abs(want["score"])
+    assert rel.max() <= SCORE_RTOL
+    # and the search finds the true poses from scratch
+    assert np.median(angular_distance(got, rows)) < 2.0
+    assert np.median(np.hypot(got["x_shift"] - rows["x_shift"], got["y_shift"] - rows["y_shift"])) < 0.3 * px
+
+
 def fold_x0(d):
     """Fold the Friedel mates of the x = 0 plane: (0,y,z) += conj (0,-y,-z), as every reader does."""
     d = d.copy()
