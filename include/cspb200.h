@@ -175,6 +175,76 @@ int cspb_refine_run_device(cspb_ctx *ctx, cspb_row *rows_dev, int n, int64_t *n_
 int cspb_refine_get_noise_curve(cspb_ctx *ctx, float *curve_out, int n_rings);
 int cspb_refine_set_noise_curve(cspb_ctx *ctx, const float *curve, int n_rings);
 
+/* ------------------------------------------------------------------ csp
+ * Replaces the numerics of external/CSP/csp (closed LFS binary) as driven by
+ * src/pyp/system/local_run.py:306-467 (argv: par, extended par, mode, first, last, flag, images,
+ * stack) and src/pyp/align/core.py:883-1248.  The extended tables are the two blocks of
+ * `<par>_extended.cistem` (src/pyp/inout/metadata/cistem_star_file.py:247-248); the structs below
+ * are those packed rows, so the file blocks can be handed over unchanged. */
+typedef struct cspb_particle {
+    int32_t pind;
+    float shift_x, shift_y, shift_z;   /* PSHIFT_X/Y/Z, Angstrom */
+    float psi, theta, phi;             /* PPSI, PTHETA, PPHI, degrees */
+    float x_position_3d, y_position_3d, z_position_3d; /* ORIGINAL_*_POSITION_3D, pixels */
+    float score, occ;                  /* PSCORE, POCC */
+} cspb_particle; /* sizeof == 48 */
+
+typedef struct cspb_tilt {
+    int32_t tind, rind;
+    float shift_x, shift_y;            /* TSHIFT_X/Y, Angstrom */
+    float angle, axis;                 /* TILTANG, TILTAXIS, degrees */
+} cspb_tilt; /* sizeof == 24 */
+
+/* csp_* keys of .pyp_config.toml (config/pyp_config.toml [tabs.csp], lines 6241-6640) */
+typedef struct cspb_csp_cfg {
+    int32_t mode;             /* argv mode: 0 tilt angle+axis, 1 particle angles, 2 particle shifts,
+                                 3 tilt shifts, 4 tilt defocus offset, 5 particle angles+shifts,
+                                 6 tilt angle+axis+shifts (align/core.py:1015-1023, local_run.py:332-335) */
+    int32_t window_min;       /* csp_UseImagesForRefinementMin (TIND window of the objective)       */
+    int32_t window_max;       /* csp_UseImagesForRefinementMax, -1 = open (cistem_star_file.py:965) */
+    int32_t iterations;       /* csp_OptimizerMaxIter                                               */
+    int32_t random_evals;     /* csp_NumberOfRandomIterations: exhaustive-stage candidates          */
+    int32_t grid_search;      /* csp_GridSearch: lattice instead of random candidates               */
+    float angle_step;         /* csp_AngleStep, degrees                                             */
+    float shift_step;         /* csp_ShiftStep, Angstrom                                            */
+    float tol_particle_psi, tol_particle_theta, tol_particle_phi; /* csp_ToleranceParticles{Psi,Theta,Phi} */
+    float tol_particle_shift; /* csp_ToleranceParticlesShifts                                       */
+    float tol_tilt_angle;     /* csp_ToleranceMicrographTiltAngles                                  */
+    float tol_tilt_axis;      /* csp_ToleranceMicrographTiltAxisAngles                              */
+    float tol_tilt_shift;     /* csp_ToleranceMicrographShifts                                      */
+    float tol_defocus;        /* csp_ToleranceMicrographDefocus1                                    */
+    uint32_t seed;            /* random-search seed (counter-based generator, same on GPU and oracle) */
+    int32_t min_projections;  /* csp_RefineProjectionCutoff                                         */
+    int32_t reserved[6];
+} cspb_csp_cfg;
+
+int cspb_csp_cfg_default(cspb_csp_cfg *cfg);
+
+/* Constrained refinement of the entities first..last (PIND for the particle modes 1/2/5, TIND for
+ * the tilt modes 0/3/4/6; last < 0 = no upper bound).  rows[k] belongs to loaded image k
+ * (cspb_refine_load_images); every row's PIND and (TIND, RIND) must exist in the tables.  The
+ * objective of an entity is the mean score of its projections inside the exposure window
+ * (update_particle_score, cistem_star_file.py:936-986).  On return the refined entities, the
+ * poses / scores of all their rows and PSCORE are updated in place. */
+int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_particle *particles, int n_particles,
+                 cspb_tilt *tilts, int n_tilts, const cspb_csp_cfg *cfg, int first, int last,
+                 int64_t *n_evals_out);
+
+/* Pose of one projection from its particle and tilt (src/pyp/analysis/geometry/core.py:1081-1217):
+ * out5 = psi, theta, phi (deg), x, y shift (Angstrom).  Host-side helper, no GPU needed. */
+int cspb_csp_compose(const cspb_particle *p, const cspb_particle *p0, const cspb_tilt *t,
+                     const cspb_tilt *t0, const float *centre3, float pixel_size, float base_x,
+                     float base_y, float *out5);
+
+/* csp mode -2 (align/core.py:958-964, local_run.py:449): cut n_rows boxes of edge `box_in` out of a
+ * tilt series (n_tilt images of nx*ny, float32), centred on (ORIGINAL_X_POSITION, ORIGINAL_Y_POSITION)
+ * of each row on image IMIND, bin them by bin x bin real-space averaging (the reference's own
+ * "real" method, src/pyp/extract/core.py:180-203) and write box_in/bin-pixel particles to
+ * `stack_out` (n_rows * (box_in/bin)^2 floats).  Pixels outside the image are filled with the
+ * image mean; a box entirely outside is zero (extract/core.py:100-155). */
+int cspb_csp_extract(cspb_ctx *ctx, const float *images, int nx, int ny, int n_tilt, const cspb_row *rows,
+                     int n_rows, int box_in, int bin, float *stack_out, int loc);
+
 /* ------------------------------------------------------------------ reconstruct3d
  * Replaces external/cistem2/reconstruct3d as driven by frealign.py:1780-1824
  * (SURVEY.md Appendix A.3). */

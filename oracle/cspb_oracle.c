@@ -698,6 +698,343 @@ long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows,
     return evals;
 }
 
+/* ================================================================ CSP (external/CSP/csp)
+ * Constrained refinement of tilt series: every projection pose is a function of its particle's
+ * parameters (PPSI, PTHETA, PPHI, PSHIFT_X/Y/Z) and its tilt's parameters (TILTANG, TILTAXIS,
+ * TSHIFT_X/Y) — composition pinned to src/pyp/analysis/geometry/core.py:1081-1217 by
+ * tests/golden/csp_euler.npy — and the objective of an entity is the mean score of its
+ * projections inside the exposure window (cistem_star_file.py:936-986, update_particle_score).
+ * Modes as passed on argv (local_run.py:332-335,411-431; align/core.py:1015-1023):
+ *   0 tilt angle+axis, 1 particle angles, 2 particle shifts, 3 tilt shifts, 4 tilt defocus offset,
+ *   5 particle angles+shifts, 6 tilt angle+axis+shifts.  SEMANTICS.md §11. */
+static void csp_decode(const float *m, float *psi, float *theta, float *phi) {
+    const float sth = hypotf(m[6], m[7]);
+    const float r2d = 180.f / PI_F;
+    if (sth > 1e-6f) {
+        *theta = atan2f(sth, m[8]) * r2d;
+        *psi = atan2f(m[7], -m[6]) * r2d;
+        *phi = atan2f(m[5], m[2]) * r2d;
+    } else if (m[8] > 0.f) {
+        *theta = 0.f; *psi = 0.f; *phi = atan2f(m[3], m[0]) * r2d;
+    } else {
+        *theta = 180.f; *psi = 0.f; *phi = atan2f(-m[3], -m[0]) * r2d;
+    }
+}
+
+/* first two rows of Rz(axis) Ry(angle) */
+static void csp_projector(float angle, float axis, float *a6) {
+    const float d2r = PI_F / 180.f;
+    const float c = cosf(angle * d2r), s = sinf(angle * d2r), cb = cosf(axis * d2r), sb = sinf(axis * d2r);
+    a6[0] = cb * c; a6[1] = -sb; a6[2] = cb * s;
+    a6[3] = sb * c; a6[4] = cb;  a6[5] = sb * s;
+}
+
+void orc_csp_compose(const orc_particle *p, const orc_particle *p0, const orc_tilt *t, const orc_tilt *t0,
+                     const float *centre3, float pixel, float bx, float by, float *out5) {
+    float e[9], q[9], m[9];
+    orc_euler_matrix(-p->psi, -p->theta, -p->phi, e);
+    const float d2r = PI_F / 180.f;
+    const float c = cosf(t->angle * d2r), s = sinf(t->angle * d2r), cb = cosf(t->axis * d2r), sb = sinf(t->axis * d2r);
+    /* Ry(-angle) Rz(-axis) */
+    q[0] = c * cb; q[1] = c * sb; q[2] = -s;
+    q[3] = -sb;    q[4] = cb;     q[5] = 0.f;
+    q[6] = s * cb; q[7] = s * sb; q[8] = c;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) m[3 * a + b] = e[3 * a] * q[b] + e[3 * a + 1] * q[3 + b] + e[3 * a + 2] * q[6 + b];
+    csp_decode(m, &out5[0], &out5[1], &out5[2]);
+    float A[6], A0[6];
+    csp_projector(t->angle, t->axis, A);
+    csp_projector(t0->angle, t0->axis, A0);
+    const float X[3] = {(p->x_position_3d - centre3[0]) * pixel, (p->y_position_3d - centre3[1]) * pixel,
+                        (p->z_position_3d - centre3[2]) * pixel};
+    const float v[3] = {X[0] - p->shift_x, X[1] - p->shift_y, X[2] - p->shift_z};
+    const float v0[3] = {X[0] - p0->shift_x, X[1] - p0->shift_y, X[2] - p0->shift_z};
+    out5[3] = bx + (A[0] * v[0] + A[1] * v[1] + A[2] * v[2]) - (A0[0] * v0[0] + A0[1] * v0[1] + A0[2] * v0[2]) + (t->shift_x - t0->shift_x);
+    out5[4] = by + (A[3] * v[0] + A[4] * v[1] + A[5] * v[2]) - (A0[3] * v0[0] + A0[4] * v0[1] + A0[5] * v0[2]) + (t->shift_y - t0->shift_y);
+}
+
+static uint32_t csp_mix(uint32_t a) {
+    a ^= a >> 16; a *= 0x7feb352du; a ^= a >> 15; a *= 0x846ca68bu; a ^= a >> 16;
+    return a;
+}
+/* uniform in [-1, 1): counter-based, identical on the GPU */
+static float csp_uniform(uint32_t seed, uint32_t ent, uint32_t k, uint32_t dim) {
+    const uint32_t h = csp_mix(seed ^ csp_mix(ent * 0x9E3779B9u + k) ^ (dim * 0x85EBCA6Bu + 0x27d4eb2fu));
+    return (float)(h >> 8) * (1.f / 8388608.f) - 1.f;
+}
+
+typedef struct {
+    int kind;            /* 0 particle entity, 1 tilt entity */
+    int freem[NP];
+    float tol[NP], h[NP], gstep[NP];
+} csp_plan;
+
+static int csp_make_plan(const orc_refine_cfg *cfg, const orc_csp_cfg *c, csp_plan *pl) {
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    const float h_ang = 0.35f * 57.29578f / hi;
+    const float h_shift = 0.07f * (float)cfg->box / hi * cfg->pixel_size;
+    const float h_def = cfg->defocus_step > 0.f ? cfg->defocus_step : 50.f;
+    memset(pl, 0, sizeof *pl);
+    switch (c->mode) {
+    case 1: case 2: case 5: pl->kind = 0; break;
+    case 0: case 3: case 4: case 6: pl->kind = 1; break;
+    default: return -1;
+    }
+    if (pl->kind == 0) {
+        const float tol[NP] = {c->tol_particle_psi, c->tol_particle_theta, c->tol_particle_phi, c->tol_particle_shift,
+                               c->tol_particle_shift, c->tol_particle_shift};
+        const float h[NP] = {h_ang, h_ang, h_ang, h_shift, h_shift, h_shift};
+        const float g[NP] = {c->angle_step, c->angle_step, c->angle_step, c->shift_step, c->shift_step, c->shift_step};
+        memcpy(pl->tol, tol, sizeof tol); memcpy(pl->h, h, sizeof h); memcpy(pl->gstep, g, sizeof g);
+        const int ang = c->mode == 1 || c->mode == 5, sh = c->mode == 2 || c->mode == 5;
+        for (int m = 0; m < 3; ++m) { pl->freem[m] = ang; pl->freem[3 + m] = sh; }
+    } else {
+        const float tol[NP] = {c->tol_tilt_angle, c->tol_tilt_axis, c->tol_tilt_shift, c->tol_tilt_shift, c->tol_defocus, 0.f};
+        const float h[NP] = {h_ang, h_ang, h_shift, h_shift, h_def, 0.f};
+        const float g[NP] = {c->angle_step, c->angle_step, c->shift_step, c->shift_step, 0.25f * c->tol_defocus, 0.f};
+        memcpy(pl->tol, tol, sizeof tol); memcpy(pl->h, h, sizeof h); memcpy(pl->gstep, g, sizeof g);
+        const int ang = c->mode == 0 || c->mode == 6, sh = c->mode == 3 || c->mode == 6;
+        pl->freem[0] = pl->freem[1] = ang;
+        pl->freem[2] = pl->freem[3] = sh;
+        pl->freem[4] = c->mode == 4;
+    }
+    return 0;
+}
+
+/* number of exhaustive candidates (candidate 0 = the input parameters) */
+static long long csp_num_candidates(const csp_plan *pl, const orc_csp_cfg *c, int *counts) {
+    if (!c->grid_search) {
+        for (int m = 0; m < NP; ++m) counts[m] = 1;
+        return c->random_evals > 0 ? c->random_evals : 0;
+    }
+    long long total = 1;
+    for (int m = 0; m < NP; ++m) {
+        counts[m] = 1;
+        if (pl->freem[m] && pl->gstep[m] > 0.f && pl->tol[m] > 0.f) counts[m] = 2 * (int)floorf(pl->tol[m] / pl->gstep[m]) + 1;
+        total *= counts[m];
+    }
+    return total;
+}
+
+static void csp_candidate(const csp_plan *pl, const orc_csp_cfg *c, const int *counts, const float *x0, uint32_t ent,
+                          long long k, float *x) {
+    memcpy(x, x0, NP * sizeof(float));
+    if (k == 0) return;
+    if (!c->grid_search) {
+        for (int m = 0; m < NP; ++m)
+            if (pl->freem[m]) x[m] = x0[m] + pl->tol[m] * csp_uniform(c->seed, ent, (uint32_t)k, (uint32_t)m);
+    } else {
+        /* candidate 0 is the centre; k >= 1 walks the lattice in mixed radix, skipping nothing
+           (the centre is visited twice, harmless) */
+        long long q = k - 1;
+        for (int m = 0; m < NP; ++m) {
+            const int d = (int)(q % counts[m]);
+            q /= counts[m];
+            x[m] = x0[m] + (float)(d - counts[m] / 2) * pl->gstep[m];
+        }
+    }
+}
+
+typedef struct {
+    const orc_ref *r; const float *specs; const orc_row *rows; const orc_refine_cfg *cfg;
+    const orc_particle *particles; const orc_tilt *tilts;   /* input tables (p0 / t0) */
+    const int *row_part, *row_tilt;                         /* per row: index into the tables */
+    const float *centre3;
+    int kind, ent;                                          /* entity being refined */
+    const int *members; int n_members;                      /* row indices, window rows first */
+    int n_window;
+} csp_group;
+
+/* pose6 of member row k for entity parameters x */
+static void csp_member_pose(const csp_group *g, int row, const float *x, float *pose6) {
+    const orc_row *rw = &g->rows[row];
+    orc_particle p = g->particles[g->row_part[row]];
+    orc_tilt t = g->tilts[g->row_tilt[row]];
+    const orc_particle p0 = p;
+    const orc_tilt t0 = t;
+    float ddef = 0.f;
+    if (g->kind == 0) {
+        p.psi = x[0]; p.theta = x[1]; p.phi = x[2]; p.shift_x = x[3]; p.shift_y = x[4]; p.shift_z = x[5];
+    } else {
+        t.angle = x[0]; t.axis = x[1]; t.shift_x = x[2]; t.shift_y = x[3]; ddef = x[4];
+    }
+    float o5[5];
+    orc_csp_compose(&p, &p0, &t, &t0, g->centre3, rw->pixel_size, rw->x_shift, rw->y_shift, o5);
+    memcpy(pose6, o5, 5 * sizeof(float));
+    pose6[5] = ddef;
+}
+
+/* mean cc over the first `count` members; optionally keeps the per-member band sums */
+static float csp_objective(const csp_group *g, const float *x, int count, float *o4_all, long long *evals) {
+    const int n = g->cfg->box, nh = n / 2 + 1;
+    float sum = 0.f;
+    for (int k = 0; k < count; ++k) {
+        const int row = g->members[k];
+        float pose[6], o4[4];
+        csp_member_pose(g, row, x, pose);
+        const float sc = orc_score(g->r, g->specs + 2 * (size_t)row * n * nh, &g->rows[row], pose, g->cfg, o4);
+        if (o4_all) memcpy(o4_all + 4 * k, o4, sizeof o4);
+        if (k < g->n_window) sum += sc * 0.01f;
+        (*evals)++;
+    }
+    return g->n_window > 0 ? sum / (float)g->n_window : 0.f;
+}
+
+static void csp_clamp(const csp_plan *pl, const float *x0, float *x) {
+    for (int m = 0; m < NP; ++m) {
+        if (!pl->freem[m] || pl->tol[m] <= 0.f) continue;
+        if (x[m] > x0[m] + pl->tol[m]) x[m] = x0[m] + pl->tol[m];
+        if (x[m] < x0[m] - pl->tol[m]) x[m] = x0[m] - pl->tol[m];
+    }
+}
+
+long long orc_csp_run(const orc_ref *r, const float *specs, orc_row *rows, int n_rows, orc_particle *particles,
+                      int n_particles, orc_tilt *tilts, int n_tilts, const orc_refine_cfg *cfg,
+                      const orc_csp_cfg *csp, int first, int last) {
+    csp_plan pl;
+    if (csp_make_plan(cfg, csp, &pl)) return -1;
+    const int nband = orc_band_count(cfg);
+    /* row -> table indices */
+    int *row_part = (int *)malloc(sizeof(int) * (size_t)(n_rows > 0 ? n_rows : 1));
+    int *row_tilt = (int *)malloc(sizeof(int) * (size_t)(n_rows > 0 ? n_rows : 1));
+    long long bad = 0;
+    for (int k = 0; k < n_rows; ++k) {
+        row_part[k] = row_tilt[k] = -1;
+        for (int a = 0; a < n_particles; ++a)
+            if (particles[a].pind == rows[k].pind) { row_part[k] = a; break; }
+        for (int a = 0; a < n_tilts; ++a)
+            if (tilts[a].tind == rows[k].tind && tilts[a].rind == rows[k].rind) { row_tilt[k] = a; break; }
+        if (row_part[k] < 0 || row_tilt[k] < 0) bad++;
+    }
+    if (bad) { free(row_part); free(row_tilt); return -2; }
+    float centre3[3] = {0.f, 0.f, 0.f};
+    for (int a = 0; a < n_particles; ++a) {
+        centre3[0] += particles[a].x_position_3d; centre3[1] += particles[a].y_position_3d; centre3[2] += particles[a].z_position_3d;
+    }
+    if (n_particles > 0) for (int d = 0; d < 3; ++d) centre3[d] /= (float)n_particles;
+    /* the search reads the INPUT tables and rows; results go to copies */
+    orc_row *rows_out = (orc_row *)malloc(sizeof(orc_row) * (size_t)(n_rows > 0 ? n_rows : 1));
+    memcpy(rows_out, rows, sizeof(orc_row) * (size_t)n_rows);
+    const int n_ent = pl.kind == 0 ? n_particles : n_tilts;
+    float *ent_x = (float *)malloc(sizeof(float) * NP * (size_t)(n_ent > 0 ? n_ent : 1));
+    float *ent_f = (float *)malloc(sizeof(float) * (size_t)(n_ent > 0 ? n_ent : 1));
+    char *ent_done = (char *)calloc((size_t)(n_ent > 0 ? n_ent : 1), 1);
+    int counts[NP];
+    const long long n_cand = csp_num_candidates(&pl, csp, counts);
+    int n_free = 0;
+    for (int m = 0; m < NP; ++m) n_free += pl.freem[m];
+    const int iters = n_free > 0 && csp->iterations > 0 ? csp->iterations : 0;
+    const int late = iters / 2 + 1;
+    long long evals = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : evals)
+    for (int e = 0; e < n_ent; ++e) {
+        const int id = pl.kind == 0 ? particles[e].pind : tilts[e].tind;
+        if (id < first || (last >= 0 && id > last)) continue;
+        /* members: window rows first, both in row order */
+        int *members = (int *)malloc(sizeof(int) * (size_t)(n_rows > 0 ? n_rows : 1));
+        int nm = 0, nw = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int k = 0; k < n_rows; ++k) {
+                if ((pl.kind == 0 ? row_part[k] : row_tilt[k]) != e) continue;
+                const int t = rows[k].tind;
+                const int in_w = !(t < csp->window_min || (csp->window_max != -1 && t > csp->window_max));
+                if (in_w == (pass == 0)) { members[nm++] = k; if (pass == 0) nw++; }
+            }
+        if (nm == 0) { free(members); continue; }
+        csp_group g = {r, specs, rows, cfg, particles, tilts, row_part, row_tilt, centre3, pl.kind, e, members, nm, nw};
+        float x0[NP], x[NP];
+        if (pl.kind == 0) {
+            const orc_particle *p = &particles[e];
+            const float v[NP] = {p->psi, p->theta, p->phi, p->shift_x, p->shift_y, p->shift_z};
+            memcpy(x0, v, sizeof v);
+        } else {
+            const orc_tilt *t = &tilts[e];
+            const float v[NP] = {t->angle, t->axis, t->shift_x, t->shift_y, 0.f, 0.f};
+            memcpy(x0, v, sizeof v);
+        }
+        memcpy(x, x0, sizeof x0);
+        long long ev = 0;
+        const int active = nw > 0 && nw >= csp->min_projections;
+        if (active) {
+            /* exhaustive stage: best of n_cand candidates, ties keep the lowest index */
+            float best = -1e30f;
+            long long kbest = 0;
+            for (long long k = 0; k < n_cand; ++k) {
+                float xc[NP];
+                csp_candidate(&pl, csp, counts, x0, (uint32_t)id, k, xc);
+                const float f = csp_objective(&g, xc, nw, NULL, &ev);
+                if (f > best) { best = f; kbest = k; }
+            }
+            if (n_cand > 0) csp_candidate(&pl, csp, counts, x0, (uint32_t)id, kbest, x);
+            /* local stage: the batched stencil/Newton/line-search optimiser of refine3d in entity space */
+            float h[NP], d[NP], q[NP];
+            memcpy(h, pl.h, sizeof h);
+            for (int it = 0; it < iters; ++it) {
+                const float f0 = csp_objective(&g, x, nw, NULL, &ev);
+                for (int m = 0; m < NP; ++m) {
+                    d[m] = 0.f;
+                    if (!pl.freem[m]) continue;
+                    memcpy(q, x, sizeof q);
+                    q[m] = x[m] + h[m];
+                    const float fp = csp_objective(&g, q, nw, NULL, &ev);
+                    q[m] = x[m] - h[m];
+                    const float fm = csp_objective(&g, q, nw, NULL, &ev);
+                    d[m] = newton_step(f0, fp, fm, h[m]);
+                }
+                float fl[NL];
+                for (int l = 0; l < NL; ++l) {
+                    for (int m = 0; m < NP; ++m) q[m] = x[m] + LS_T[l] * d[m];
+                    fl[l] = csp_objective(&g, q, nw, NULL, &ev);
+                }
+                const float t = line_step(f0, fl);
+                for (int m = 0; m < NP; ++m) x[m] += t * d[m];
+                csp_clamp(&pl, x0, x);
+                if (it + 1 >= late)
+                    for (int m = 0; m < NP; ++m) h[m] *= 0.6f;
+            }
+        }
+        /* final: refined and input parameters over ALL members; never return a worse objective */
+        float *o4a = (float *)malloc(sizeof(float) * 4 * (size_t)nm), *o4b = (float *)malloc(sizeof(float) * 4 * (size_t)nm);
+        float fa = csp_objective(&g, x, nm, o4a, &ev);
+        const float fb = csp_objective(&g, x0, nm, o4b, &ev);
+        if (fa < fb) { memcpy(x, x0, sizeof x0); memcpy(o4a, o4b, sizeof(float) * 4 * (size_t)nm); fa = fb; }
+        for (int k = 0; k < nm; ++k) {
+            const int row = members[k];
+            float pose[6];
+            csp_member_pose(&g, row, x, pose);
+            orc_row *o = &rows_out[row];
+            o->psi = wrap360(pose[0]); o->theta = pose[1]; o->phi = wrap360(pose[2]);
+            o->x_shift = pose[3]; o->y_shift = pose[4];
+            o->defocus_1 += pose[5]; o->defocus_2 += pose[5];
+            const float *v = o4a + 4 * k;
+            const float den = v[2] * v[3];
+            o->score = den > 0.f ? 100.f * v[0] / sqrtf(den) : 0.f;
+            stats_from(v, nband, &o->sigma, &o->logp);
+        }
+        memcpy(ent_x + NP * (size_t)e, x, sizeof x);
+        ent_f[e] = fa;
+        ent_done[e] = 1;
+        evals += ev;
+        free(o4a); free(o4b); free(members);
+    }
+    memcpy(rows, rows_out, sizeof(orc_row) * (size_t)n_rows);
+    for (int e = 0; e < n_ent; ++e) {
+        if (!ent_done[e]) continue;
+        const float *x = ent_x + NP * (size_t)e;
+        if (pl.kind == 0) {
+            orc_particle *p = &particles[e];
+            p->psi = x[0]; p->theta = x[1]; p->phi = x[2]; p->shift_x = x[3]; p->shift_y = x[4]; p->shift_z = x[5];
+            p->score = 100.f * ent_f[e];
+        } else {
+            orc_tilt *t = &tilts[e];
+            t->angle = x[0]; t->axis = x[1]; t->shift_x = x[2]; t->shift_y = x[3];
+        }
+    }
+    free(rows_out); free(ent_x); free(ent_f); free(ent_done); free(row_part); free(row_tilt);
+    return evals;
+}
+
 /* ================================================================ reconstruction */
 struct orc_recon {
     orc_recon_cfg cfg;

@@ -96,6 +96,37 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
 long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows, int n,
                             const orc_refine_cfg *cfg, const float *angles3, int n_orient);
 
+/* ---- constrained single-particle refinement (external/CSP/csp; argv contract at
+ * src/pyp/system/local_run.py:364-376,392-404,451-463).  Extended tables as in
+ * cistem_star_file.py:247-248.  Same fields as cspb_particle / cspb_tilt / cspb_csp_cfg. */
+typedef struct orc_particle {
+    int32_t pind;
+    float shift_x, shift_y, shift_z, psi, theta, phi, x_position_3d, y_position_3d, z_position_3d, score, occ;
+} orc_particle;
+typedef struct orc_tilt {
+    int32_t tind, rind;
+    float shift_x, shift_y, angle, axis;
+} orc_tilt;
+typedef struct orc_csp_cfg {
+    int32_t mode, window_min, window_max, iterations, random_evals, grid_search;
+    float angle_step, shift_step;
+    float tol_particle_psi, tol_particle_theta, tol_particle_phi, tol_particle_shift;
+    float tol_tilt_angle, tol_tilt_axis, tol_tilt_shift, tol_defocus;
+    uint32_t seed;
+    int32_t min_projections;
+    int32_t reserved[6];
+} orc_csp_cfg;
+/* pose of one projection from its particle and tilt parameters (geometry/core.py:1081-1217):
+ * out5 = psi, theta, phi (deg), x, y (same unit as the inputs) for base shift (bx, by);
+ * p0/t0 are the input (extraction-time) parameters the base shift belongs to. */
+void orc_csp_compose(const orc_particle *p, const orc_particle *p0, const orc_tilt *t, const orc_tilt *t0,
+                     const float *centre3, float pixel, float bx, float by, float *out5);
+/* refine entities first..last (PIND for particle modes 1/2/5, TIND for tilt modes 0/3/4/6; last < 0 = open)
+ * in place; rows[k] belongs to specs[k].  Returns the number of objective evaluations, < 0 on error. */
+long long orc_csp_run(const orc_ref *r, const float *specs, orc_row *rows, int n_rows, orc_particle *particles,
+                      int n_particles, orc_tilt *tilts, int n_tilts, const orc_refine_cfg *cfg,
+                      const orc_csp_cfg *csp, int first, int last);
+
 /* ---- reconstruction */
 orc_recon *orc_recon_create(const orc_recon_cfg *cfg);
 void orc_recon_free(orc_recon *rc);

@@ -53,6 +53,31 @@ class ReconCfg(C.Structure):
     ]
 
 
+PARTICLE_DTYPE = np.dtype([("pind", "<i4"), ("shift_x", "<f4"), ("shift_y", "<f4"), ("shift_z", "<f4"), ("psi", "<f4"), ("theta", "<f4"),
+                           ("phi", "<f4"), ("x_position_3d", "<f4"), ("y_position_3d", "<f4"), ("z_position_3d", "<f4"), ("score", "<f4"), ("occ", "<f4")])
+TILT_DTYPE = np.dtype([("tind", "<i4"), ("rind", "<i4"), ("shift_x", "<f4"), ("shift_y", "<f4"), ("angle", "<f4"), ("axis", "<f4")])
+
+
+class CspCfg(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("window_min", C.c_int32), ("window_max", C.c_int32), ("iterations", C.c_int32),
+        ("random_evals", C.c_int32), ("grid_search", C.c_int32),
+        ("angle_step", C.c_float), ("shift_step", C.c_float),
+        ("tol_particle_psi", C.c_float), ("tol_particle_theta", C.c_float), ("tol_particle_phi", C.c_float),
+        ("tol_particle_shift", C.c_float),
+        ("tol_tilt_angle", C.c_float), ("tol_tilt_axis", C.c_float), ("tol_tilt_shift", C.c_float), ("tol_defocus", C.c_float),
+        ("seed", C.c_uint32), ("min_projections", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
+def csp_cfg_from(gpu_cfg) -> CspCfg:
+    o = CspCfg()
+    for name, _ in CspCfg._fields_:
+        if name != "reserved":
+            setattr(o, name, getattr(gpu_cfg, name))
+    return o
+
+
 def refine_cfg_from(gpu_cfg) -> RefineCfg:
     """Copy the shared fields of a pyp_b200 RefineCfg (or any object with those attributes)."""
     o = RefineCfg()
@@ -98,6 +123,8 @@ def lib():
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
             "orc_global_search": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg), vp, i]),
+            "orc_csp_compose": (None, [vp, vp, vp, vp, vp, f, f, f, vp]),
+            "orc_csp_run": (C.c_longlong, [vp, vp, vp, i, vp, i, vp, i, C.POINTER(RefineCfg), C.POINTER(CspCfg), i, i]),
             "orc_recon_create": (vp, [C.POINTER(ReconCfg)]),
             "orc_recon_free": (None, [vp]),
             "orc_recon_insert": (None, [vp, vp, vp, i, vp, i]),
@@ -218,6 +245,31 @@ def global_search(ref, specs, rows, cfg, angles3):
     ang = _f32(angles3).reshape(-1, 3)
     ne = lib().orc_global_search(ref._h, _p(specs), _p(rows), rows.size, C.byref(cfg), _p(ang), ang.shape[0])
     return rows, int(ne)
+
+
+def csp_compose(particle, particle0, tilt, tilt0, centre3, pixel, base_xy):
+    """Projection pose (psi, theta, phi, x, y) from extended-table entries (numpy records)."""
+    p = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+    p0 = np.ascontiguousarray(particle0, dtype=PARTICLE_DTYPE).reshape(1)
+    t = np.ascontiguousarray(tilt, dtype=TILT_DTYPE).reshape(1)
+    t0 = np.ascontiguousarray(tilt0, dtype=TILT_DTYPE).reshape(1)
+    c3 = _f32(centre3)
+    out = np.zeros(5, dtype=np.float32)
+    lib().orc_csp_compose(_p(p), _p(p0), _p(t), _p(t0), _p(c3), float(pixel), float(base_xy[0]), float(base_xy[1]), _p(out))
+    return out
+
+
+def csp_run(ref, specs, rows, particles, tilts, cfg, csp_cfg, first, last):
+    """external/CSP/csp numerics on the CPU; returns (rows, particles, tilts, n_evals)."""
+    specs = np.ascontiguousarray(specs, dtype=np.complex64)
+    rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+    particles = np.array(particles, dtype=PARTICLE_DTYPE, copy=True)
+    tilts = np.array(tilts, dtype=TILT_DTYPE, copy=True)
+    ne = lib().orc_csp_run(ref._h, _p(specs), _p(rows), rows.size, _p(particles), particles.size, _p(tilts), tilts.size,
+                           C.byref(cfg), C.byref(csp_cfg), int(first), int(last))
+    if ne < 0:
+        raise ValueError(f"orc_csp_run failed ({ne})")
+    return rows, particles, tilts, int(ne)
 
 
 class Recon:

@@ -64,6 +64,26 @@ class ReconCfg(C.Structure):
     ]
 
 
+# `_extended.cistem` blocks — cistem_star_file.py:247-248
+PARTICLE_DTYPE = np.dtype([("pind", "<i4"), ("shift_x", "<f4"), ("shift_y", "<f4"), ("shift_z", "<f4"), ("psi", "<f4"), ("theta", "<f4"),
+                           ("phi", "<f4"), ("x_position_3d", "<f4"), ("y_position_3d", "<f4"), ("z_position_3d", "<f4"), ("score", "<f4"), ("occ", "<f4")])
+TILT_DTYPE = np.dtype([("tind", "<i4"), ("rind", "<i4"), ("shift_x", "<f4"), ("shift_y", "<f4"), ("angle", "<f4"), ("axis", "<f4")])
+assert PARTICLE_DTYPE.itemsize == 48 and TILT_DTYPE.itemsize == 24
+
+
+class CspCfg(C.Structure):
+    """csp_* keys of .pyp_config.toml (include/cspb200.h cspb_csp_cfg)."""
+    _fields_ = [
+        ("mode", C.c_int32), ("window_min", C.c_int32), ("window_max", C.c_int32), ("iterations", C.c_int32),
+        ("random_evals", C.c_int32), ("grid_search", C.c_int32),
+        ("angle_step", C.c_float), ("shift_step", C.c_float),
+        ("tol_particle_psi", C.c_float), ("tol_particle_theta", C.c_float), ("tol_particle_phi", C.c_float),
+        ("tol_particle_shift", C.c_float),
+        ("tol_tilt_angle", C.c_float), ("tol_tilt_axis", C.c_float), ("tol_tilt_shift", C.c_float), ("tol_defocus", C.c_float),
+        ("seed", C.c_uint32), ("min_projections", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
 class CspbError(RuntimeError):
     pass
 
@@ -93,6 +113,10 @@ _SIGNATURES = {
     "cspb_refine_run_device": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),
     "cspb_refine_get_noise_curve": (_i, [_vp, _vp, _i]),
     "cspb_refine_set_noise_curve": (_i, [_vp, _vp, _i]),
+    "cspb_csp_cfg_default": (_i, [C.POINTER(CspCfg)]),
+    "cspb_csp_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, C.POINTER(CspCfg), _i, _i, C.POINTER(_i64)]),
+    "cspb_csp_compose": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
+    "cspb_csp_extract": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i]),
     "cspb_recon_cfg_default": (_i, [C.POINTER(ReconCfg), _i, _f]),
     "cspb_recon_begin": (_i, [_vp, C.POINTER(ReconCfg)]),
     "cspb_recon_insert": (_i, [_vp, _vp, _vp, _i, _i]),

@@ -77,6 +77,14 @@ struct CtfCoef {
     float a, b, cos2ast, sin2ast, c4, ph0, dstep, pad_;  // dstep: d(a)/d(defocus Angstrom)
 };
 
+// one warp of the scoring kernel = one unit = (image, up to PB candidate poses)
+struct ScoreUnit {
+    int image;       // index into packed images / ctf coefficients
+    int first_eval;  // index of the unit's first evaluation
+    int count;       // number of poses (<= PB)
+    int pad_;
+};
+
 struct ProfRec {
     cudaEvent_t a, b;
     int kind;
@@ -170,6 +178,14 @@ int recon_flush_deferred(cspb_ctx *ctx);
             return cspb_fail(ctx, CSPB_E_NOMEM, "device allocation of %zu bytes failed",   \
                              (size_t)(bytes_));                                            \
     } while (0)
+
+// ---------------------------------------------------------------- scorer (refine.cu)
+// enqueue the scoring kernel over `n_units` units; poses6 per eval = psi, theta, phi (deg), shift x, y
+// (Angstrom), defocus delta (Angstrom); out per eval = {numerator, signed X, A, B}
+int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, const float *d_poses6,
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals);
+// upload rows next to their CTF coefficients (ctx->d_rows)
+int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, CtfCoef **d_ctf);
 
 // ---------------------------------------------------------------- FFT (fft.cu)
 // twiddle table W_n^k = exp(-2 pi i k / n), k < n, cached per n on the device

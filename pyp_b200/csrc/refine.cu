@@ -11,6 +11,7 @@
 #include <string.h>
 #include "device_math.cuh"
 #include "internal.cuh"
+#include "opt.cuh"
 
 // ================================================================== reference preparation
 namespace {
@@ -203,13 +204,6 @@ __global__ void ctf_coef_kernel(const cspb_row *__restrict__ rows, int n_rows, i
 }
 
 // ================================================================== the scorer
-struct ScoreUnit {
-    int image;       // index into packed images / ctf coefficients
-    int first_eval;  // index of the unit's first evaluation
-    int count;       // number of poses (<= PB)
-    int pad_;
-};
-
 struct ScoreArgs {
     const float4 *ref4;
     int sx, sy, rc;
@@ -381,21 +375,7 @@ __global__ void ctf_image_kernel(CtfCoef cc, int n, float *__restrict__ out) {
     }
 }
 
-// ================================================================== batched local optimiser
-// Per image: x = {psi, theta, phi, shift x, shift y, defocus delta}, masked by `free`.
-// Every iteration = central-difference stencil (1+2M evals) -> diagonal Newton step with a
-// trust region -> 3-point line search -> keep the best point seen.  All images in lockstep.
-#define OPT_NP 6
-#define OPT_NL 3
-struct OptState {
-    float x[OPT_NP];
-    float h[OPT_NP];
-    float d[OPT_NP];
-    float x0[OPT_NP];  // starting pose
-    float f;           // CC at the current centre
-    float pad_[3];
-};
-
+// ================================================================== batched local optimiser (shared pieces in opt.cuh)
 struct SearchHit {
     float score, sx, sy;
     int orient;
@@ -426,109 +406,6 @@ __global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n_states,
     st[k] = s;
 }
 
-// free_mask bit m set -> parameter m is refined.  n_free = popcount.  evals per image NE = 1+2*n_free
-__global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int K, int free_mask, int NE, int PB,
-                                   float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const OptState s = st[k];
-    float *q = poses6 + (long long)k * NE * 6;
-    for (int m = 0; m < OPT_NP; ++m) q[m] = s.x[m];
-    int e = 1;
-    for (int m = 0; m < OPT_NP; ++m) {
-        if (!((free_mask >> m) & 1)) continue;
-        for (int sgn = 0; sgn < 2; ++sgn, ++e) {
-            float *qe = q + e * 6;
-            for (int t = 0; t < OPT_NP; ++t) qe[t] = s.x[t];
-            qe[m] += sgn ? -s.h[m] : s.h[m];
-        }
-    }
-    const int upi = (NE + PB - 1) / PB;
-    for (int c = 0; c < upi; ++c) {
-        ScoreUnit un;
-        un.image = k / K;
-        un.first_eval = k * NE + c * PB;
-        un.count = min(PB, NE - c * PB);
-        un.pad_ = 0;
-        units[(long long)k * upi + c] = un;
-    }
-}
-
-__device__ __forceinline__ float cc_of(const float4 v) {
-    const float den = v.z * v.w;
-    return den > 0.f ? v.x * rsqrtf(den) : 0.f;
-}
-
-// diagonal Newton step, continuous in (f0, fp, fm): d = g / max(-c, |g|/dmax), dmax = 4h
-__device__ __forceinline__ float newton_step(float f0, float fp, float fm, float h) {
-    const float g = (fp - fm) / (2.f * h);
-    const float c = (fp - 2.f * f0 + fm) / (h * h);
-    const float dmax = 4.f * h;
-    float den = -c;
-    const float floor_ = fabsf(g) / dmax;
-    if (den < floor_) den = floor_;
-    return den > 0.f ? g / den : 0.f;
-}
-
-// step length from f(0) and f(0.5), f(1), f(2): least-squares parabola through the origin
-// offset, maximiser clamped to [0, 2.5]; a convex fit takes the better end of the interval
-__device__ __forceinline__ float line_step(float f0, const float *fl) {
-    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
-    float s22 = 0.f, s23 = 0.f, s33 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-    for (int l = 0; l < OPT_NL; ++l) {
-        const float t = tl[l], y = fl[l] - f0;
-        s22 += t * t; s23 += t * t * t; s33 += t * t * t * t;
-        r2 += t * y; r3 += t * t * y;
-    }
-    const float det = s22 * s33 - s23 * s23;
-    const float b = (r2 * s33 - r3 * s23) / det;
-    const float a = (r3 * s22 - r2 * s23) / det;
-    if (a < 0.f) {
-        float t = -b / (2.f * a);
-        return fminf(fmaxf(t, 0.f), 2.5f);
-    }
-    return (a * 2.5f + b > 0.f) ? 2.5f : 0.f;  // convex fit: better end of [0, 2.5] under the model
-}
-
-// consume stencil scores, propose the Newton direction, emit line-search poses
-__global__ void opt_step_kernel(OptState *__restrict__ st, int n, int K, int free_mask, int NE, const float4 *__restrict__ sc,
-                                float *__restrict__ poses6_ls, ScoreUnit *__restrict__ units_ls) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    OptState s = st[k];
-    const float4 *v = sc + (long long)k * NE;
-    const float f0 = cc_of(v[0]);
-    int e = 1;
-    for (int m = 0; m < OPT_NP; ++m) {
-        s.d[m] = 0.f;
-        if (!((free_mask >> m) & 1)) continue;
-        s.d[m] = newton_step(f0, cc_of(v[e]), cc_of(v[e + 1]), s.h[m]);
-        e += 2;
-    }
-    s.f = f0;
-    st[k] = s;
-    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
-    float *q = poses6_ls + (long long)k * OPT_NL * 6;
-    for (int l = 0; l < OPT_NL; ++l)
-        for (int m = 0; m < OPT_NP; ++m) q[l * 6 + m] = s.x[m] + tl[l] * s.d[m];
-    ScoreUnit un;
-    un.image = k / K; un.first_eval = k * OPT_NL; un.count = OPT_NL; un.pad_ = 0;
-    units_ls[k] = un;
-}
-
-__global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4 *__restrict__ sc_ls, float shrink) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    OptState s = st[k];
-    float fl[OPT_NL];
-    for (int l = 0; l < OPT_NL; ++l) fl[l] = cc_of(sc_ls[(long long)k * OPT_NL + l]);
-    const float t = line_step(s.f, fl);
-    for (int m = 0; m < OPT_NP; ++m) s.x[m] += t * s.d[m];
-    for (int m = 0; m < OPT_NP; ++m) s.h[m] *= shrink;
-    st[k] = s;
-}
-
 // final: evaluate the refined pose and the starting pose (2 evals per image)
 __global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, int K, float *__restrict__ poses6,
                                        ScoreUnit *__restrict__ units) {
@@ -541,12 +418,6 @@ __global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, i
     ScoreUnit un;
     un.image = k / K; un.first_eval = 2 * k; un.count = 2; un.pad_ = 0;
     units[k] = un;
-}
-
-__device__ __forceinline__ float wrap360(float a) {
-    a = fmodf(a, 360.f);
-    if (a < 0.f) a += 360.f;
-    return a;
 }
 
 // one thread per image: among its K refined candidates (and each candidate's starting pose) keep
@@ -629,6 +500,8 @@ int grid_for(long long total, int block, int sm) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+}  // namespace
+
 int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, const float *d_poses6,
                  const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals) {
     if (n_units <= 0) return 0;
@@ -662,6 +535,8 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, c
     KERNEL_CHECK(ctx);
     return 0;
 }
+
+namespace {
 
 // nearest-ring CSR of the full half plane (for the noise power curve)
 void build_ring_csr(int n, std::vector<int> &off, std::vector<int> &idx, std::vector<int> &count) {
@@ -1017,7 +892,7 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
     return 0;
 }
 
-static int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, CtfCoef **d_ctf) {
+int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, CtfCoef **d_ctf) {
     RESERVE(ctx, ctx->d_rows, (size_t)n * (sizeof(cspb_row) + sizeof(CtfCoef)));
     *d_rows = ctx->d_rows.as<cspb_row>();
     *d_ctf = reinterpret_cast<CtfCoef *>(*d_rows + n);

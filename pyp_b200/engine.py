@@ -12,10 +12,10 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import DEVICE, HOST, ROW_DTYPE, CspbError, ReconCfg, RefineCfg, ptr
+from ._lib import DEVICE, HOST, PARTICLE_DTYPE, ROW_DTYPE, TILT_DTYPE, CspbError, CspCfg, ReconCfg, RefineCfg, ptr
 from .symmetry import symmetry_matrices
 
-__all__ = ["Engine", "ROW_DTYPE", "RefineCfg", "ReconCfg", "CspbError", "HOST", "DEVICE", "new_rows"]
+__all__ = ["Engine", "ROW_DTYPE", "PARTICLE_DTYPE", "TILT_DTYPE", "RefineCfg", "ReconCfg", "CspCfg", "CspbError", "HOST", "DEVICE", "new_rows"]
 
 
 def new_rows(n, pixel_size=1.0, voltage_kv=300.0, cs_mm=2.7, amplitude_contrast=0.07):
@@ -190,6 +190,51 @@ class Engine:
         ne = C.c_int64(0)
         self._ck(self._l.cspb_refine_run_device(self._h, C.c_void_p(int(rows_dev_ptr)), int(n), C.byref(ne)))
         return int(ne.value)
+
+    # ------------------------------------------------------------------ csp (external/CSP/csp)
+    @staticmethod
+    def csp_defaults(mode=5):
+        cfg = CspCfg()
+        rc = _lib.lib().cspb_csp_cfg_default(C.byref(cfg))
+        if rc != 0:
+            raise CspbError(f"cspb_csp_cfg_default failed: {rc}")
+        cfg.mode = int(mode)
+        return cfg
+
+    def csp_run(self, rows, particles, tilts, cfg: CspCfg, first=0, last=-1):
+        """Constrained refinement of particles / tilts first..last over the loaded images
+        (rows[k] <-> image k).  Returns (rows, particles, tilts, n_evals), inputs untouched."""
+        rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+        particles = np.array(particles, dtype=PARTICLE_DTYPE, copy=True)
+        tilts = np.array(tilts, dtype=TILT_DTYPE, copy=True)
+        ne = C.c_int64(0)
+        self._ck(self._l.cspb_csp_run(self._h, ptr(rows), rows.size, ptr(particles), particles.size, ptr(tilts), tilts.size,
+                                      C.byref(cfg), int(first), int(last), C.byref(ne)))
+        return rows, particles, tilts, int(ne.value)
+
+    @staticmethod
+    def csp_compose(particle, particle0, tilt, tilt0, centre3, pixel_size, base_xy):
+        p = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+        p0 = np.ascontiguousarray(particle0, dtype=PARTICLE_DTYPE).reshape(1)
+        t = np.ascontiguousarray(tilt, dtype=TILT_DTYPE).reshape(1)
+        t0 = np.ascontiguousarray(tilt0, dtype=TILT_DTYPE).reshape(1)
+        c3 = np.ascontiguousarray(centre3, dtype=np.float32)
+        out = np.zeros(5, dtype=np.float32)
+        rc = _lib.lib().cspb_csp_compose(ptr(p), ptr(p0), ptr(t), ptr(t0), ptr(c3), float(pixel_size), float(base_xy[0]), float(base_xy[1]), ptr(out))
+        if rc != 0:
+            raise CspbError(f"cspb_csp_compose failed: {rc}")
+        return out
+
+    def csp_extract(self, images, rows, box_in, binning=1):
+        """csp mode -2: cut (and bin) the particle boxes of `rows` out of a tilt series
+        (n_tilt, ny, nx) float32; returns the stack (n_rows, box_in/bin, box_in/bin)."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        nt, ny, nx = images.shape
+        bo = int(box_in) // int(binning)
+        out = np.zeros((rows.size, bo, bo), dtype=np.float32)
+        self._ck(self._l.cspb_csp_extract(self._h, ptr(images), nx, ny, nt, ptr(rows), rows.size, int(box_in), int(binning), ptr(out), HOST))
+        return out
 
     # ------------------------------------------------------------------ reconstruct3d / merge3d
     @staticmethod

@@ -11,7 +11,7 @@ structured array (:data:`ROW_DTYPE`, 128 bytes) that goes to the GPU unchanged.
 """
 import numpy as np
 
-from .._lib import ROW_DTYPE
+from .._lib import PARTICLE_DTYPE, ROW_DTYPE, TILT_DTYPE
 
 # type codes — cistem_star_file.py:18-27
 INTEGER, FLOAT, LONG, CHAR, INTEGER_UNSIGNED = 2, 3, 5, 7, 9
@@ -32,10 +32,7 @@ _ROW_TYPES = {name: (INTEGER_UNSIGNED if ROW_DTYPE[name].kind == "u" else INTEGE
 
 PIND_BLOCK, TIND_BLOCK = 15, 35
 # extended blocks — cistem_star_file.py:247-248
-PARTICLE_DTYPE = np.dtype([("pind", "<i4"), ("shift_x", "<f4"), ("shift_y", "<f4"), ("shift_z", "<f4"), ("psi", "<f4"), ("theta", "<f4"),
-                           ("phi", "<f4"), ("x_position_3d", "<f4"), ("y_position_3d", "<f4"), ("z_position_3d", "<f4"), ("score", "<f4"), ("occ", "<f4")])
 _PARTICLE_IDS = [15, 3, 9, 27, 81, 273, 819, 2457, 7371, 22113, 66339, 199017]
-TILT_DTYPE = np.dtype([("tind", "<i4"), ("rind", "<i4"), ("shift_x", "<f4"), ("shift_y", "<f4"), ("angle", "<f4"), ("axis", "<f4")])
 _TILT_IDS = [35, 70, 7, 49, 343, 2401]
 _HDR = np.dtype([("id", "<i8"), ("type", "<i1")])
 

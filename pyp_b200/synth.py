@@ -130,3 +130,100 @@ def perturb_rows(rows, ang_sigma=2.0, shift_sigma_px=1.0, seed=3):
     out["x_shift"] = rows["x_shift"] + rng.normal(0, shift_sigma_px, rows.size) * rows["pixel_size"]
     out["y_shift"] = rows["y_shift"] + rng.normal(0, shift_sigma_px, rows.size) * rows["pixel_size"]
     return out
+
+
+def make_tilt_series(n_particles, pixel, tilt_angles=None, tilt_axis=0.0, seed=1, shift_a=6.0, defocus=25000.0,
+                     extent_px=300.0, thickness_px=60.0, handedness=1.0, dtype=None):
+    """Synthetic sub-tomogram tilt series (BASELINE configs[2]): every particle is seen at every
+    tilt; the projection rows are composed from the extended tables exactly as the reference does
+    (pyp_b200/csp_geometry.py, pinned to geometry/core.py:1081-1217) and carry a per-tilt,
+    per-particle defocus following inout/metadata/core.py:2831-2865.
+
+    Returns (rows, particles, tilts); rows are particle-major (all tilts of particle 0 first),
+    POSITION_IN_STACK 1..n, TIND = acquisition (scan) order index of the tilt."""
+    from . import csp_geometry as G
+    from .formats.cistem import PARTICLE_DTYPE, TILT_DTYPE
+    from ._lib import ROW_DTYPE
+
+    rng = np.random.default_rng(seed)
+    if tilt_angles is None:
+        tilt_angles = np.arange(-60.0, 60.1, 3.0)
+    tilt_angles = np.asarray(tilt_angles, dtype=np.float64)
+    nt = tilt_angles.size
+    # dose-symmetric acquisition order: 0, +3, -3, +6, -6 ...  (scan-order index = TIND)
+    order = np.argsort(np.abs(tilt_angles) + 1e-3 * (tilt_angles < 0), kind="stable")
+    tind_of = np.empty(nt, dtype=int)
+    tind_of[order] = np.arange(nt)
+    tilts = np.zeros(nt, dtype=TILT_DTYPE)
+    for k in range(nt):
+        tilts[tind_of[k]] = (tind_of[k], 0, 0.0, 0.0, tilt_angles[k], tilt_axis)
+    particles = np.zeros(n_particles, dtype=PARTICLE_DTYPE)
+    particles["pind"] = np.arange(n_particles)
+    particles["psi"] = rng.uniform(0, 360, n_particles)
+    particles["theta"] = np.degrees(np.arccos(rng.uniform(-1, 1, n_particles)))
+    particles["phi"] = rng.uniform(0, 360, n_particles)
+    for k in ("shift_x", "shift_y", "shift_z"):
+        particles[k] = rng.uniform(-shift_a, shift_a, n_particles)
+    particles["x_position_3d"] = rng.uniform(-extent_px, extent_px, n_particles) + 2000.0
+    particles["y_position_3d"] = rng.uniform(-extent_px, extent_px, n_particles) + 2000.0
+    particles["z_position_3d"] = rng.uniform(-thickness_px, thickness_px, n_particles) + 150.0
+    particles["occ"] = 100.0
+    centre = np.array([particles["x_position_3d"].mean(), particles["y_position_3d"].mean(), particles["z_position_3d"].mean()])
+    rows = np.zeros(n_particles * nt, dtype=dtype or ROW_DTYPE)
+    k = 0
+    for p in particles:
+        pos = (np.array([p["x_position_3d"], p["y_position_3d"], p["z_position_3d"]]) - centre) * pixel
+        for t in tilts:
+            ang = G.compose_pose((p["psi"], p["theta"], p["phi"]), (t["angle"], t["axis"]))
+            sh = G.compose_shift((p["shift_x"], p["shift_y"], p["shift_z"]), (t["angle"], t["axis"]))
+            r = rows[k]
+            r["position_in_stack"] = k + 1
+            r["psi"], r["theta"], r["phi"] = ang
+            r["x_shift"], r["y_shift"] = sh + (t["shift_x"], t["shift_y"])
+            # height of the particle above the tilt axis plane changes the defocus
+            # (inout/metadata/core.py:2857-2865: -z cos(t) + x sin(t) terms)
+            a = math.radians(handedness * t["angle"])
+            dz = -pos[2] * math.cos(a) + pos[0] * math.sin(a)
+            r["defocus_1"] = defocus + dz + 150.0
+            r["defocus_2"] = defocus + dz - 150.0
+            r["defocus_angle"] = 35.0
+            r["occupancy"], r["sigma"], r["score"] = 100.0, 1.0, 0.5
+            r["pixel_size"], r["voltage_kv"], r["cs_mm"], r["amplitude_contrast"] = pixel, 300.0, 2.7, 0.07
+            r["image_is_active"] = 0
+            r["pind"], r["tind"], r["rind"], r["find"] = p["pind"], t["tind"], 0, 0
+            r["imind"] = t["tind"]
+            r["original_x"], r["original_y"] = p["x_position_3d"], p["y_position_3d"]
+            k += 1
+    return rows, particles, tilts
+
+
+def perturb_particles(particles, ang_sigma=2.0, shift_sigma_a=1.5, seed=5):
+    rng = np.random.default_rng(seed)
+    out = particles.copy()
+    for k in ("psi", "theta", "phi"):
+        out[k] = particles[k] + rng.normal(0, ang_sigma, particles.size)
+    for k in ("shift_x", "shift_y", "shift_z"):
+        out[k] = particles[k] + rng.normal(0, shift_sigma_a, particles.size)
+    return out
+
+
+def rows_from_tables(rows, particles0, tilts0, particles, tilts):
+    """Re-compose every projection row after its particle / tilt parameters changed (float64
+    restatement of the CSP pose model, SEMANTICS.md §11) — used to build perturbed inputs."""
+    from . import csp_geometry as G
+
+    out = rows.copy()
+    pi = {int(p["pind"]): k for k, p in enumerate(particles)}
+    ti = {(int(t["tind"]), int(t["rind"])): k for k, t in enumerate(tilts)}
+    centre = np.array([particles["x_position_3d"].mean(), particles["y_position_3d"].mean(), particles["z_position_3d"].mean()], dtype=np.float64)
+    for r in out:
+        p, p0 = particles[pi[int(r["pind"])]], particles0[pi[int(r["pind"])]]
+        t, t0 = tilts[ti[(int(r["tind"]), int(r["rind"]))]], tilts0[ti[(int(r["tind"]), int(r["rind"]))]]
+        X = (np.array([p["x_position_3d"], p["y_position_3d"], p["z_position_3d"]], dtype=np.float64) - centre) * float(r["pixel_size"])
+        v = X - np.array([p["shift_x"], p["shift_y"], p["shift_z"]], dtype=np.float64)
+        v0 = X - np.array([p0["shift_x"], p0["shift_y"], p0["shift_z"]], dtype=np.float64)
+        s = G.tilt_projector(t["angle"], t["axis"]) @ v - G.tilt_projector(t0["angle"], t0["axis"]) @ v0
+        r["psi"], r["theta"], r["phi"] = G.compose_pose((p["psi"], p["theta"], p["phi"]), (t["angle"], t["axis"]))
+        r["x_shift"] += s[0] + t["shift_x"] - t0["shift_x"]
+        r["y_shift"] += s[1] + t["shift_y"] - t0["shift_y"]
+    return out

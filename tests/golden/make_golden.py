@@ -13,6 +13,9 @@ What gets pinned:
       left-handed matrices that eulerTwoZYZtoOneZYZ composes (geometry/core.py:174-219)
   spa_euler.npy — spa_euler_angles inputs/outputs (geometry/core.py:250-441), the tilt/particle
       pose composition that CSP uses.
+  csp_euler.npy — csp_euler_angles (geometry/core.py:1081-1217): tilt angle, axis, csp angles and
+      3DAVG translation in; projection (psi, theta, phi, sx, sy) and the stored particle
+      parameters (-ppsi, -ptheta, -pphi, px, py, pz) out.  Pins pyp_b200/csp_geometry.py.
 """
 import os
 import sys
@@ -140,6 +143,18 @@ def main():
         res, pres = geo.spa_euler_angles(tilt, axis, normal, list(np.asarray(mm).ravel()), 0.0)
         spa.append(np.concatenate([[tilt, axis], normal, np.asarray(mm).ravel(), np.asarray(res, dtype=float), np.asarray(pres, dtype=float)]))
     np.save(os.path.join(HERE, "spa_euler.npy"), np.array(spa))
+
+    csp = []
+    for k in range(64):
+        tilt, axis = rng.uniform(-70, 70), rng.uniform(-180, 180)
+        ang = [rng.uniform(0, 360), rng.uniform(0, 180), rng.uniform(0, 360)]
+        if k == 0:
+            tilt, axis, ang = 0.0, 0.0, [30.0, 40.0, 50.0]      # SPA limit: no tilt geometry
+        mm = np.eye(4)
+        mm[:3, 3] = rng.uniform(-6, 6, 3)
+        fp, nm = geo.csp_euler_angles(tilt, axis, [0.0, 0.0, 0.0], list(mm.ravel()), 0.0, ang)
+        csp.append(np.concatenate([[tilt, axis], ang, mm[:3, 3], np.asarray(fp, dtype=float), np.asarray(nm, dtype=float)]))
+    np.save(os.path.join(HERE, "csp_euler.npy"), np.array(csp))
     print("golden fixtures written to", HERE)
 
 

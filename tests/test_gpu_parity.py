@@ -193,8 +193,19 @@ def test_global_search_matches_oracle(engine, oracle):
     same = (ang < 5e-2) & (sh < 5e-2)
     assert same.mean() >= 0.999, (np.sort(ang)[-3:], np.sort(sh)[-3:])
     assert np.median(ang) < 5e-3
+    # scorer parity at the GPU's own optimum: the oracle evaluated at the pose the GPU returned
+    # must reproduce the GPU score to 1e-4 for EVERY particle
+    at_got = np.array([oracle.score(ref, specs[k], got[k].astype(oracle.ROW_DTYPE), pose_of(got[k]), ocfg)[0]
+                       for k in range(got.size)])
+    assert (np.abs(got["score"] - at_got) / np.abs(at_got)).max() <= SCORE_RTOL
+    # optimiser agreement: where both optimisers stopped within 0.02 deg / 0.02 A of each other (the
+    # local test's "identical" radius) the scores agree to 1e-4; a pair that stopped 0.02-0.05 apart
+    # sits on a slightly different point of the same peak, bounded by 5e-4
     rel = np.abs(got["score"] - want["score"]) / np.abs(want["score"])
-    assert rel.max() <= SCORE_RTOL
+    tight = (ang < 2e-2) & (sh < 2e-2)
+    assert tight.mean() >= 0.9
+    assert rel[tight].max() <= SCORE_RTOL
+    assert rel.max() <= 5 * SCORE_RTOL
     # and the search finds the true poses from scratch
     assert np.median(angular_distance(got, rows)) < 2.0
     assert np.median(np.hypot(got["x_shift"] - rows["x_shift"], got["y_shift"] - rows["y_shift"])) < 0.3 * px
