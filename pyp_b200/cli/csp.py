@@ -1,0 +1,225 @@
+"""csp drop-in: same argv as external/CSP/csp (src/pyp/system/local_run.py:364-376,392-404,
+451-463), numerics on the GPU.
+
+    csp <par.cistem> <par_extended.cistem> <mode> <first> <last> <flag> <images> <stack>  > log
+
+cwd is the film's scratch directory; numeric options come from ``./.pyp_config.toml`` which the
+driver re-saves right before every mode (src/pyp/align/core.py:1055); the reference map is
+``$PYP_SCRATCH/<data_set>_frames_CSP_01.mrc`` (align/core.py:921-931).
+
+Modes (align/core.py:1015-1023 after the mapping at local_run.py:332-335,411-431):
+  -2  extract particles first..last from the tilt series `images` into `stack`
+   0/3/6  tilt angle+axis / tilt shifts / both, for TIND first..last (last = -1: all)
+   1/2/5  particle angles / shifts / both, for PIND first..last
+   4  per-tilt defocus offset
+Outputs: ``<par minus .cistem>_<first:06d>_<last:06d>.cistem`` with the rows of the refined
+entities and ``..._extended.cistem`` with the refined entities only, which is what
+merge_alignment_parameters globs and Parameters.merge overlays on the input tables
+(src/pyp/refine/csp/particle_cspt.py:95-138; cistem_star_file.py:656-692).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+from ..formats import cistem, mrc
+from .prompts import PromptError, banner, pick_device
+
+try:
+    import tomllib
+except ImportError:  # pragma: no cover
+    tomllib = None
+
+# defaults of config/pyp_config.toml for the keys the binary needs
+DEFAULTS = {
+    "csp_UseImagesForRefinementMin": 0, "csp_UseImagesForRefinementMax": 20, "csp_RefineProjectionCutoff": 0,
+    "csp_NumberOfRandomIterations": 0, "csp_OptimizerMaxIter": 5, "csp_GridSearch": False, "csp_AngleStep": 20.0, "csp_ShiftStep": 6.0,
+    "csp_ToleranceMicrographTiltAngles": 1.5, "csp_ToleranceMicrographTiltAxisAngles": 1.0, "csp_ToleranceMicrographShifts": 100.0,
+    "csp_ToleranceParticlesPhi": 30.0, "csp_ToleranceParticlesPsi": 30.0, "csp_ToleranceParticlesTheta": 30.0,
+    "csp_ToleranceParticlesShifts": 20.0, "csp_ToleranceMicrographDefocus1": 750.0,
+    "refine_rlref": 100.0, "refine_rhref": "10", "refine_iter": 2, "refine_fboost": False, "refine_fboostlim": 0.0,
+    "refine_iblow": "1", "extract_bin": 1, "data_bin": 1, "particle_sym": "C1",
+}
+
+
+def param(value, iteration):
+    """Per-iteration colon lists (src/pyp/system/project_params.py:362-373)."""
+    if isinstance(value, str):
+        listed = value.split(":")
+        return listed[min(iteration - 2, len(listed) - 1)]
+    return value
+
+
+def load_config(path=".pyp_config.toml"):
+    cfg = dict(DEFAULTS)
+    if os.path.exists(path):
+        if tomllib is None:
+            raise ValueError("tomllib is unavailable; cannot read .pyp_config.toml")
+        with open(path, "rb") as f:
+            cfg.update(tomllib.load(f))
+    return cfg
+
+
+def csp_cfg_from(config, mode):
+    from ..engine import Engine
+
+    c = Engine.csp_defaults(mode)
+    it = int(config.get("refine_iter", 2))
+    c.window_min = int(param(config["csp_UseImagesForRefinementMin"], it))
+    c.window_max = int(param(config["csp_UseImagesForRefinementMax"], it))
+    c.iterations = int(config["csp_OptimizerMaxIter"])
+    c.random_evals = int(config["csp_NumberOfRandomIterations"])
+    c.grid_search = 1 if config["csp_GridSearch"] else 0
+    c.angle_step, c.shift_step = float(config["csp_AngleStep"]), float(config["csp_ShiftStep"])
+    c.tol_particle_psi = float(config["csp_ToleranceParticlesPsi"])
+    c.tol_particle_theta = float(config["csp_ToleranceParticlesTheta"])
+    c.tol_particle_phi = float(config["csp_ToleranceParticlesPhi"])
+    c.tol_particle_shift = float(config["csp_ToleranceParticlesShifts"])
+    c.tol_tilt_angle = float(config["csp_ToleranceMicrographTiltAngles"])
+    c.tol_tilt_axis = float(config["csp_ToleranceMicrographTiltAxisAngles"])
+    c.tol_tilt_shift = float(config["csp_ToleranceMicrographShifts"])
+    c.tol_defocus = float(config["csp_ToleranceMicrographDefocus1"])
+    c.min_projections = int(config["csp_RefineProjectionCutoff"])
+    c.seed = int(config.get("csp_seed", 0)) & 0xFFFFFFFF
+    return c
+
+
+def refine_cfg_from(config, box, pixel):
+    from ..engine import Engine
+
+    it = int(config.get("refine_iter", 2))
+    cfg = Engine.refine_defaults(box, pixel)
+    cfg.low_res_limit = float(param(config["refine_rlref"], it))
+    rh = float(param(config["refine_rhref"], it))
+    cfg.high_res_limit = rh if rh > 0 else 16.0          # postprocess/core.py:16-69 falls back to 16 A
+    cfg.high_res_limit = max(cfg.high_res_limit, 2.0 * pixel)
+    rad = config.get("particle_rad")
+    if rad:
+        cfg.mask_radius = float(rad)
+    cfg.signed_cc_limit = float(config["refine_fboostlim"]) if config.get("refine_fboost") else 30.0  # frealign.py:3879-3881
+    cfg.pad = 2 if float(param(config["refine_iblow"], it)) >= 1.5 else 1
+    return cfg
+
+
+def out_paths(par, first, last):
+    """particle_cspt.py:113-122: `<par>.strip('.cistem') + '_%06d_%06d' + '.cistem'`."""
+    stem = par[:-len(".cistem")] if par.endswith(".cistem") else par
+    tag = f"{stem}_{int(first):06d}_{int(last):06d}"
+    return tag + ".cistem", tag + "_extended.cistem"
+
+
+def reference_path(config):
+    scratch = os.environ.get("PYP_SCRATCH", ".")
+    return os.path.join(scratch, f"{config.get('data_set', 'dataset')}_frames_CSP_01.mrc")
+
+
+def entity_rows(rows, particles, tilts, mode, first, last):
+    """Index of the rows that belong to the entities first..last (PIND or TIND; last < 0 = open)."""
+    key = rows["pind"] if mode in (1, 2, 5, -2) else rows["tind"]
+    sel = key >= first
+    if last >= 0:
+        sel &= key <= last
+    return np.nonzero(sel)[0]
+
+
+def run_extract(par, mode, first, last, images, stack, config, out):
+    from ..engine import Engine
+
+    rows_all = cistem.read_parameters(par)
+    idx = entity_rows(rows_all, None, None, -2, first, last)
+    rows = rows_all[idx]
+    rows = rows[np.argsort(rows["position_in_stack"], kind="stable")]
+    box = int(config.get("extract_box", 0))
+    binning = int(config.get("extract_bin", 1))
+    if box <= 0:
+        raise ValueError("extract_box missing from .pyp_config.toml")
+    if rows.size == 0:
+        out.write(f"csp: no projections for particles {first}..{last}; nothing extracted\n")
+        return
+    _, series = mrc.read(images)
+    eng = Engine(pick_device(first + 1, max(1, last - first + 1)))
+    got = eng.csp_extract(np.ascontiguousarray(series, dtype=np.float32), rows, box * binning, binning)
+    eng.close()
+    os.makedirs(os.path.dirname(stack) or ".", exist_ok=True)
+    mrc.write(stack, got, pixel_size=float(rows["pixel_size"][0]))
+    out.write(f"Extracted {rows.size} projections of particles {first}..{last} into {stack} ({box} px, bin {binning})\n")
+
+
+def run_refine(par, ext, mode, first, last, stack, config, out):
+    from ..engine import Engine
+
+    t0 = time.time()
+    rows_all = cistem.read_parameters(par)
+    particles, tilts = cistem.read_extended(ext)
+    idx = entity_rows(rows_all, particles, tilts, mode, first, last)
+    out_par, out_ext = out_paths(par, first, last)
+    if idx.size == 0:
+        cistem.write_parameters(out_par, rows_all[:0])
+        cistem.write_extended(out_ext, particles[:0], tilts[:0])
+        out.write(f"csp: nothing to refine for {first}..{last}\n")
+        return
+    rows = rows_all[idx]
+    order = np.argsort(rows["position_in_stack"], kind="stable")
+    rows = rows[order]
+    hdr = mrc.read_header(stack)
+    box = hdr["nx"]
+    pixel = float(rows["pixel_size"][0])
+    ref_path = reference_path(config)
+    _, vol = mrc.read(ref_path)
+    if vol.shape != (box, box, box):
+        raise ValueError(f"reference {ref_path} {vol.shape} does not match the {box}-pixel stack")
+    eng = Engine(pick_device(first + 1, max(1, last - first + 1)))
+    eng.refine_configure(refine_cfg_from(config, box, pixel))
+    eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+    pos = rows["position_in_stack"].astype(np.int64)
+    if pos.min() < 1 or pos.max() > hdr["nz"]:
+        raise ValueError(f"POSITION_IN_STACK {pos.min()}..{pos.max()} outside the stack (1..{hdr['nz']})")
+    _, data = mrc.read(stack, first=int(pos.min()), last=int(pos.max()))
+    chunk = 16384
+    for s in range(0, rows.size, chunk):
+        eng.load_images(np.ascontiguousarray(data[pos[s:s + chunk] - pos.min()]), append=s > 0)
+    ccfg = csp_cfg_from(config, mode)
+    new_rows, new_p, new_t, n_evals = eng.csp_run(rows, particles, tilts, ccfg, first, last)
+    eng.close()
+    cistem.write_parameters(out_par, new_rows)
+    if mode in (1, 2, 5):
+        sel = (particles["pind"] >= first) & ((particles["pind"] <= last) if last >= 0 else True)
+        cistem.write_extended(out_ext, new_p[sel], new_t[:0])
+    else:
+        sel = (tilts["tind"] >= first) & ((tilts["tind"] <= last) if last >= 0 else True)
+        cistem.write_extended(out_ext, new_p[:0], new_t[sel])
+    dt = time.time() - t0
+    out.write(f"mode {mode}: entities {first}..{last}, {rows.size} projections, exposures {ccfg.window_min}..{ccfg.window_max}\n")
+    out.write(f"mean score {float(rows['score'].mean()):.4f} -> {float(new_rows['score'].mean()):.4f}, "
+              f"{n_evals} projections scored in {dt:.2f} s\n")
+
+
+def main(argv=None, out=sys.stdout):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    try:
+        if len(argv) != 8:
+            raise PromptError("usage: csp <par.cistem> <par_extended.cistem> <mode> <first> <last> <flag> <images> <stack>")
+        par, ext, mode, first, last, _flag, images, stack = argv
+        mode = int(float(mode))
+        first, last = int(first), int(last)
+        out.write(banner("CSP"))
+        config = load_config()
+        if mode == -1:
+            pass
+        elif mode == -2:
+            run_extract(par, mode, first, last, images, stack, config, out)
+        elif mode in (0, 1, 2, 3, 4, 5, 6):
+            run_refine(par, ext, mode, first, last, stack, config, out)
+        else:
+            raise PromptError(f"csp: unknown mode {mode}")
+        out.write("\nCSP: Normal termination\n")
+    except (PromptError, ValueError, OSError, RuntimeError, ImportError) as e:
+        sys.stderr.write(f"csp: caught error: {e}\n")
+        out.write("PYP (cspswarm) failed\n")
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

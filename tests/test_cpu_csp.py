@@ -159,3 +159,31 @@ def test_oracle_csp_random_search_is_deterministic_and_helps(oracle):
     assert _pose_err(a[1], particles).mean() < _pose_err(start_p, particles).mean()
     with pytest.raises(ValueError):
         oracle.csp_run(ref, specs, start_rows, start_p[:1], tilts, cfg, csp, 0, -1)  # a row's particle is missing
+
+
+def test_csp_cli_host_logic(tmp_path, monkeypatch):
+    """argv / config / naming logic of bin/csp that needs no GPU."""
+    from pyp_b200.cli import csp as cli
+
+    assert cli.out_paths("frealign/maps/ts_r01_02.cistem", 3, 17) == (
+        "frealign/maps/ts_r01_02_000003_000017.cistem", "frealign/maps/ts_r01_02_000003_000017_extended.cistem")
+    assert cli.out_paths("x/ts_r01_02_region0004.cistem", 0, -1)[0] == "x/ts_r01_02_region0004_000000_-00001.cistem"
+    # per-iteration colon lists: element min(iter - 2, len - 1) (project_params.py:362-373)
+    assert cli.param("8:6:4", 2) == "8" and cli.param("8:6:4", 3) == "6" and cli.param("8:6:4", 9) == "4" and cli.param(5, 3) == 5
+    monkeypatch.chdir(tmp_path)
+    cfg = cli.load_config()
+    assert cfg["csp_UseImagesForRefinementMax"] == 20 and cfg["csp_OptimizerMaxIter"] == 5  # pyp_config.toml defaults
+    (tmp_path / ".pyp_config.toml").write_text('data_set = "abc"\ncsp_NumberOfRandomIterations = 50000\nrefine_iter = 4\nrefine_rhref = "8:6:4"\n')
+    cfg = cli.load_config()
+    assert cfg["csp_NumberOfRandomIterations"] == 50000
+    monkeypatch.setenv("PYP_SCRATCH", "/scr")
+    assert cli.reference_path(cfg) == "/scr/abc_frames_CSP_01.mrc"  # align/core.py:921-931
+    rows = np.zeros(6, dtype=[("pind", "<i4"), ("tind", "<i4")])
+    rows["pind"], rows["tind"] = [0, 0, 1, 1, 2, 2], [0, 1, 0, 1, 0, 1]
+    assert list(cli.entity_rows(rows, None, None, 5, 1, 2)) == [2, 3, 4, 5]
+    assert list(cli.entity_rows(rows, None, None, 6, 1, 1)) == [1, 3, 5]
+    assert list(cli.entity_rows(rows, None, None, 3, 0, -1)) == [0, 1, 2, 3, 4, 5]
+    # wrong argv is an error with pyp's failure token, not a crash
+    import io
+    out = io.StringIO()
+    assert cli.main(["a", "b"], out=out) == 1 and "PYP (cspswarm) failed" in out.getvalue()

@@ -85,3 +85,82 @@ def test_refine_reconstruct_merge_chain(tmp_path):
     # error convention: bad input -> non-zero exit and the word "caught" in the log
     assert sh("reconstruct3d", ["missing.mrc"], d, "bad.log") != 0
     assert "caught" in open(f"{d}/bad.log").read()
+
+
+def test_csp_cli_extract_and_refine(tmp_path):
+    """bin/csp driven as create_csp_split_commands does (local_run.py:364-376,451-463): mode -2
+    extraction from the tilt series, mode 5 over two particle ranges, mode 6 for one tilt, then the
+    merge pyp performs (particle_cspt.py:95-138)."""
+    from test_cpu_csp import _pose_err
+
+    n, px, n_part = 64, 1.6, 4
+    tilt_angles = np.array([-40.0, -20.0, 0.0, 20.0, 40.0])
+    ph = synth.Phantom(n, n_blobs=60, sigma=1.5)
+    rows, particles, tilts = synth.make_tilt_series(n_part, px, tilt_angles=tilt_angles, shift_a=3.0, extent_px=60.0, thickness_px=12.0,
+                                                    defocus=22000.0)
+    stack = synth.make_stack(ph, rows, snr=0.5, seed=21)
+    # tilt-series images: every particle box pasted at its (ORIGINAL_X, ORIGINAL_Y) on image IMIND
+    nt, ny, nx = tilts.size, 2 * n + 20, n_part * (n + 8) + 20
+    series = np.zeros((nt, ny, nx), dtype=np.float32)
+    for k, r in enumerate(rows):
+        cx, cy = 10 + n // 2 + int(r["pind"]) * (n + 8), 10 + n // 2 + (int(r["tind"]) % 2) * n
+        rows["original_x"][k], rows["original_y"][k] = cx, cy
+        series[int(r["imind"]), cy - n // 2:cy + n // 2, cx - n // 2:cx + n // 2] = stack[k]
+    start_p = synth.perturb_particles(particles, 2.0, 1.5)
+    start_rows = synth.rows_from_tables(rows, particles, tilts, start_p, tilts)
+    d = str(tmp_path)
+    os.makedirs(f"{d}/frealign/maps")
+    os.makedirs(f"{d}/scratch")
+    par, ext = "frealign/maps/ts_r01_02.cistem", "frealign/maps/ts_r01_02_extended.cistem"
+    cistem.write_parameters(f"{d}/{par}", start_rows)
+    cistem.write_extended(f"{d}/{ext}", start_p, tilts)
+    mrc.write(f"{d}/frealign/ts.mrc", series, px)
+    mrc.write(f"{d}/scratch/ds_frames_CSP_01.mrc", ph.volume(), px)
+    with open(f"{d}/.pyp_config.toml", "w") as f:
+        f.write('data_set = "ds"\nextract_box = %d\nextract_bin = 1\nparticle_rad = %.2f\nrefine_rhref = "8:6.4"\nrefine_rlref = 80.0\n'
+                'refine_iter = 3\ncsp_UseImagesForRefinementMin = 0\ncsp_UseImagesForRefinementMax = -1\ncsp_OptimizerMaxIter = 6\n' % (n, 0.38 * n * px))
+    env = dict(os.environ, PYP_SCRATCH=f"{d}/scratch")
+
+    def csp(*args, log="csp.log"):
+        cmd = f"{BIN}/csp " + " ".join(str(a) for a in args) + f" > {log}"
+        return subprocess.run(cmd, shell=True, cwd=d, env=env, timeout=600).returncode
+
+    # mode -2 in two chunks, merged like mrc.merge_fast
+    assert csp(par, ext, -2, 0, 1, 1, "frealign/ts.mrc", "frealign/ts_stack_0000_0001.mrc") == 0
+    assert csp(par, ext, -2, 2, 3, 1, "frealign/ts.mrc", "frealign/ts_stack_0002_0003.mrc") == 0
+    _, a = mrc.read(f"{d}/frealign/ts_stack_0000_0001.mrc")
+    _, b = mrc.read(f"{d}/frealign/ts_stack_0002_0003.mrc")
+    merged = np.concatenate([a, b])
+    assert np.array_equal(merged, stack)
+    mrc.write(f"{d}/frealign/ts_stack.mrc", merged, px)
+
+    # mode 5 (particles) over two ranges
+    for first, last in ((0, 1), (2, 3)):
+        assert csp(par, ext, 5, first, last, 1, "frealign/ts.mrc", "frealign/ts_stack.mrc", log="ts_csp_%06d_%06d.log" % (first, last)) == 0
+    assert "CSP: Normal termination" in open(f"{d}/ts_csp_000000_000001.log").read()
+    outs = sorted(f"{d}/frealign/maps/{f}" for f in os.listdir(f"{d}/frealign/maps") if f.startswith("ts_r01_02_0") and not f.endswith("_extended.cistem"))
+    assert [os.path.basename(o) for o in outs] == ["ts_r01_02_000000_000001.cistem", "ts_r01_02_000002_000003.cistem"]
+    merged_rows = cistem.merge(outs)
+    assert list(merged_rows["position_in_stack"]) == list(range(1, rows.size + 1))
+    new_p = start_p.copy()
+    for o in outs:  # dict.update semantics of Parameters.merge for the extended blocks
+        pp, tt = cistem.read_extended(o.replace(".cistem", "_extended.cistem"))
+        assert tt.size == 0 and pp.size == 2
+        for p in pp:
+            new_p[np.nonzero(new_p["pind"] == p["pind"])[0][0]] = p
+    assert _pose_err(new_p, particles).mean() < 0.5 * _pose_err(start_p, particles).mean()
+    assert merged_rows["score"].mean() > 0
+    for p in new_p:  # PSCORE = mean score over the exposure window (update_particle_score)
+        assert abs(p["score"] - merged_rows["score"][merged_rows["pind"] == p["pind"]].mean()) < 1e-3
+
+    # mode 6 (micrographs): one tilt per process
+    cistem.write_parameters(f"{d}/{par}", merged_rows)
+    cistem.write_extended(f"{d}/{ext}", new_p, tilts)
+    assert csp(par, ext, 6, 2, 2, 1, "frealign/ts.mrc", "frealign/ts_stack.mrc", log="/dev/null") == 0
+    r6 = cistem.read_parameters(f"{d}/frealign/maps/ts_r01_02_000002_000002.cistem")
+    p6, t6 = cistem.read_extended(f"{d}/frealign/maps/ts_r01_02_000002_000002_extended.cistem")
+    assert p6.size == 0 and t6.size == 1 and int(t6["tind"][0]) == 2 and set(r6["tind"]) == {2} and r6.size == n_part
+    assert abs(t6["angle"][0] - tilts["angle"][2]) <= 1.5 + 1e-4  # csp_ToleranceMicrographTiltAngles
+    # an unknown mode fails loudly with pyp's failure token
+    assert csp(par, ext, 9, 0, 0, 1, "frealign/ts.mrc", "frealign/ts_stack.mrc", log="bad.log") != 0
+    assert "PYP (cspswarm) failed" in open(f"{d}/bad.log").read()
