@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcspb200.so")
+LIB_PATH = os.environ.get("CSPB_LIB") or os.path.join(_HERE, "libcspb200.so")  # CSPB_LIB: alternative build (kernel tuning experiments)
 
 HOST, DEVICE = 0, 1
 

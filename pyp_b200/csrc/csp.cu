@@ -186,13 +186,15 @@ __global__ void csp_expand_kernel(const CspEntry *__restrict__ list, int n_entri
     csp_member_pose(T, kind, en.row, x, pose);
     for (int m = 0; m < 6; ++m) poses6[idx * 6 + m] = pose[m];
     if (c % PB == 0) {
-        const int upe = (nc + PB - 1) / PB;
+        // count-class layout (launch_score_classes): full units first, one tail unit per entry after them
+        const int nfull = nc / PB, cu = c / PB;
         ScoreUnit un;
         un.image = en.row;
         un.first_eval = (int)idx;
         un.count = min(PB, nc - c);
         un.pad_ = 0;
-        units[(long long)j * upe + c / PB] = un;
+        if (cu < nfull) units[(long long)j * nfull + cu] = un;
+        else units[(long long)n_entries * nfull + j] = un;
     }
 }
 
@@ -551,8 +553,7 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
             const long long tot = (long long)n_entries * nc;
             csp_expand_kernel<<<ceil_div(tot, 256), 256, 0, ctx->stream>>>(list, n_entries, nc, PB, T, pl.kind, params, poses, units);
             KERNEL_CHECK(ctx);
-            const int upe = (nc + PB - 1) / PB;
-            int r = launch_score(ctx, units, n_entries * upe, PB, poses, d_ctf, out, ddef, tot);
+            int r = launch_score_classes(ctx, units, n_entries, nc, 0, PB, poses, d_ctf, out, ddef);
             if (r) return r;
             evals += tot;
         }
@@ -581,7 +582,7 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
         // local stage: refine3d's stencil / Newton / line-search optimiser in entity space
         float *params_ls = params + (size_t)G * NE * 6;
         for (int it = 0; it < iters; ++it) {
-            opt_stencil_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, NE, PB, params, dummy);
+            opt_stencil_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, 0, NE, PB, params, dummy);
             KERNEL_CHECK(ctx);
             rc = evaluate(b_ls.as<CspEntry>(), n_search, NE, 0);
             if (rc) return rc;

@@ -63,11 +63,19 @@ bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi);
 // ---------------------------------------------------------------- reference volume (scoring)
 // Cropped, centred (y,z shifted by +rc), x-paired Fourier half-volume:
 // ref4[(z*sy + y)*sx + x] = { V(x,y,z), V(x+1,y,z) } as float4.
+// The scorer reads a second copy in (y,z) 2x2 quads, one 32-byte item per voxel, so that the 8
+// trilinear neighbours of a sample are two LDG.256 at x and x+1 (half the L1 wavefronts of 4 x 16 B):
+// ref8[(z*sy + y)*sx8 + x] = { V(x,y,z), V(x,y+1,z), V(x,y,z+1), V(x,y+1,z+1) }.
+struct __align__(32) RefQuad {
+    float2 v00, v10, v01, v11;
+};
 struct RefVolume {
     int n = 0, pad = 1, np = 0;
     int rc = 0;          // centre offset: y,z in [-rc, rc]
     int sx = 0, sy = 0;  // sx = rc+1, sy = sz = 2rc+1
-    DevBuf d_ref4;
+    int sx8 = 0;         // x extent of the quad volume: rc+2
+    DevBuf d_ref4;       // x-paired copy (global search, projections)
+    DevBuf d_ref8;       // quad copy (scoring kernel)
     bool ready = false;
 };
 
@@ -182,8 +190,13 @@ int recon_flush_deferred(cspb_ctx *ctx);
 // ---------------------------------------------------------------- scorer (refine.cu)
 // enqueue the scoring kernel over `n_units` units; poses6 per eval = psi, theta, phi (deg), shift x, y
 // (Angstrom), defocus delta (Angstrom); out per eval = {numerator, signed X, A, B}
-int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals);
+// every unit of the range has exactly `count` poses (one template instance per count, branch free);
+// shared = rotation and CTF of the unit's first pose apply to all its poses (pure shift variations)
+int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count, const float *d_poses6,
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, bool shared);
+// units in class layout [A full][A tail][S full][S tail] (opt.cuh); nA plain + nS shared evals per group
+int launch_score_classes(cspb_ctx *ctx, const ScoreUnit *d_units, int n_groups, int nA, int nS, int PB, const float *d_poses6,
+                         const CtfCoef *d_ctf, float4 *d_out, bool ddef);
 // upload rows next to their CTF coefficients (ctx->d_rows)
 int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, CtfCoef **d_ctf);
 

@@ -25,31 +25,58 @@ __device__ __forceinline__ float wrap360(float a) {
     return a;
 }
 
-// free_mask bit m set -> parameter m is refined.  n_free = popcount.  evals per image NE = 1+2*n_free
-__global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int K, int free_mask, int NE, int PB,
+// Stencil evaluation order of the parameters: pure in-plane shifts last, so that the evaluations
+// which share the centre's rotation and CTF are consecutive and can be scored from ONE gather.
+__device__ __constant__ const int OPT_ORDER[OPT_NP] = {0, 1, 2, 5, 3, 4};
+
+// free_mask bit m set -> parameter m is refined.  n_free = popcount.  evals per state NE = 1+2*n_free.
+// shift_mask: free parameters that are pure image shifts (refine3d: x, y); their 2*n_shift evaluations
+// form "shared" units (rotation and CTF of the unit's first pose apply to all of its poses).
+// Unit layout by class, so that every scorer launch sees one kind of unit (launch_score_classes):
+//   [A full: n*(nA/PB)] [A tail: n if nA%PB] [S full: n*(nS/PB)] [S tail: n if nS%PB],  nA = NE - nS.
+__global__ void opt_stencil_kernel(const OptState *__restrict__ st, int n, int K, int free_mask, int shift_mask, int NE, int PB,
                                    float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const OptState s = st[k];
     float *q = poses6 + (long long)k * NE * 6;
     for (int m = 0; m < OPT_NP; ++m) q[m] = s.x[m];
-    int e = 1;
-    for (int m = 0; m < OPT_NP; ++m) {
+    int e = 1, nS = 0;
+    for (int o = 0; o < OPT_NP; ++o) {
+        const int m = OPT_ORDER[o];
         if (!((free_mask >> m) & 1)) continue;
+        if ((shift_mask >> m) & 1) nS += 2;
         for (int sgn = 0; sgn < 2; ++sgn, ++e) {
             float *qe = q + e * 6;
             for (int t = 0; t < OPT_NP; ++t) qe[t] = s.x[t];
             qe[m] += sgn ? -s.h[m] : s.h[m];
         }
     }
-    const int upi = (NE + PB - 1) / PB;
-    for (int c = 0; c < upi; ++c) {
+    const int nA = NE - nS;
+    const int fullA = nA / PB, tailA = nA % PB, fullS = nS / PB, tailS = nS % PB;
+    long long base = 0;
+    for (int c = 0; c < fullA; ++c) {
         ScoreUnit un;
-        un.image = k / K;
-        un.first_eval = k * NE + c * PB;
-        un.count = min(PB, NE - c * PB);
-        un.pad_ = 0;
-        units[(long long)k * upi + c] = un;
+        un.image = k / K; un.first_eval = k * NE + c * PB; un.count = PB; un.pad_ = 0;
+        units[base + (long long)k * fullA + c] = un;
+    }
+    base += (long long)n * fullA;
+    if (tailA) {
+        ScoreUnit un;
+        un.image = k / K; un.first_eval = k * NE + fullA * PB; un.count = tailA; un.pad_ = 0;
+        units[base + k] = un;
+        base += n;
+    }
+    for (int c = 0; c < fullS; ++c) {
+        ScoreUnit un;
+        un.image = k / K; un.first_eval = k * NE + nA + c * PB; un.count = PB; un.pad_ = 1;
+        units[base + (long long)k * fullS + c] = un;
+    }
+    base += (long long)n * fullS;
+    if (tailS) {
+        ScoreUnit un;
+        un.image = k / K; un.first_eval = k * NE + nA + fullS * PB; un.count = tailS; un.pad_ = 1;
+        units[base + k] = un;
     }
 }
 
@@ -99,8 +126,9 @@ __global__ void opt_step_kernel(OptState *__restrict__ st, int n, int K, int fre
     const float4 *v = sc + (long long)k * NE;
     const float f0 = cc_of(v[0]);
     int e = 1;
-    for (int m = 0; m < OPT_NP; ++m) {
-        s.d[m] = 0.f;
+    for (int m = 0; m < OPT_NP; ++m) s.d[m] = 0.f;
+    for (int o = 0; o < OPT_NP; ++o) {
+        const int m = OPT_ORDER[o];
         if (!((free_mask >> m) & 1)) continue;
         s.d[m] = newton_step(f0, cc_of(v[e]), cc_of(v[e + 1]), s.h[m]);
         e += 2;

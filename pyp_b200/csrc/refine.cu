@@ -8,6 +8,7 @@
 // restated on the CPU in oracle/cspb_oracle.c, against which these kernels are tested.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "device_math.cuh"
 #include "internal.cuh"
@@ -63,6 +64,37 @@ __global__ void crop_pair_kernel(const float2 *__restrict__ spec, float4 *__rest
             v[d] = t;
         }
         ref4[idx] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    }
+}
+
+// FFT-ordered half spectrum -> cropped centred volume of (y,z) 2x2 quads for the scorer:
+// ref8[(z*sy + y)*sx8 + x] = { V(x,y,z), V(x,y+1,z), V(x,y,z+1), V(x,y+1,z+1) }  (32 bytes, one LDG.256)
+__global__ void crop_quad_kernel(const float2 *__restrict__ spec, RefQuad *__restrict__ ref8, int np, int rc, int sx8, int sy) {
+    const long long total = (long long)sx8 * sy * sy;
+    const int xh = np / 2 + 1;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % sx8);
+        const int yy = (int)((idx / sx8) % sy);
+        const int zz = (int)(idx / ((long long)sx8 * sy));
+        float2 v[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int y = yy - rc + (d & 1), z = zz - rc + (d >> 1);
+            float2 t = make_float2(0.f, 0.f);
+            if (x < xh && y >= -np / 2 && y < np / 2 && z >= -np / 2 && z < np / 2) {
+                const int iy = y < 0 ? y + np : y, iz = z < 0 ? z + np : z;
+                t = spec[((long long)iz * np + iy) * xh + x];
+                if ((x + y + z) & 1) {  // real-space centre at np/2 -> (-1)^(x+y+z)
+                    t.x = -t.x;
+                    t.y = -t.y;
+                }
+            }
+            v[d] = t;
+        }
+        RefQuad q;
+        q.v00 = v[0]; q.v10 = v[1]; q.v01 = v[2]; q.v11 = v[3];
+        ref8[idx] = q;
     }
 }
 
@@ -205,8 +237,8 @@ __global__ void ctf_coef_kernel(const cspb_row *__restrict__ rows, int n_rows, i
 
 // ================================================================== the scorer
 struct ScoreArgs {
-    const float4 *ref4;
-    int sx, sy, rc;
+    const RefQuad *ref8;
+    int sx, sy, rc;   // sx = x extent of the quad volume (rc + 2)
     float padf;
     const int32_t *slot_ij;
     const BandDesc *bands;
@@ -222,12 +254,34 @@ struct ScoreArgs {
     float4 *out;          // per eval: {numerator, signed X total, A, B}
 };
 
-// One warp per unit = (image, up to PB poses).  Lanes walk the polar-patch band plan:
+// one 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100+)
+__device__ __forceinline__ RefQuad ldg_quad(const RefQuad *p) {
+    RefQuad q;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(q.v00.x), "=f"(q.v00.y), "=f"(q.v10.x), "=f"(q.v10.y), "=f"(q.v01.x), "=f"(q.v01.y), "=f"(q.v11.x), "=f"(q.v11.y)
+        : "l"(p));
+    return q;
+}
+
+// sin / cos of pi * v on the MUFU pipe: v is reduced to [-1, 1] first, where sin.approx / cos.approx
+// are good to 2^-21 absolute — the size of the fp32 rounding of the phase itself
+__device__ __forceinline__ void sincospi_fast(float v, float *sn, float *cs) {
+    const float M = 12582912.f;
+    const float k = (v * 0.5f + M) - M;  // nearest integer of v / 2
+    const float a = (v - 2.f * k) * CSPB_PI_F;
+    *sn = __sinf(a);
+    *cs = __cosf(a);
+}
+
+// One warp per unit = (image, exactly PB poses).  Lanes walk the polar-patch band plan:
 // coalesced 8-byte reads of the packed image, CTF synthesised once per sample and shared by the
 // unit's poses, trilinear gather as 4 x 16-byte loads from the x-paired reference, per-ring sums
-// kept in one register per pose (lane%4 = ring offset inside the 4-ring band).
-template <int PB, bool DDEF>
-__global__ void __launch_bounds__(128) score_kernel(const ScoreArgs A) {
+// kept in one register per pose (lane%4 = ring offset inside the 4-ring band).  The pose loop is
+// branch free so that the 4 * PB gathers of a sample are in flight together.
+// 64 registers -> 8 CTAs = 32 warps per SM: the kernel is bound by L2/DRAM latency of the gathers
+// (long-scoreboard stalls), more resident warps measured +10 % over the 72-register build
+template <int PB, bool DDEF, bool SHARED>
+__global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArgs A) {
     __shared__ float s_pose[4][PB][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int u = blockIdx.x * 4 + warp;
@@ -235,17 +289,15 @@ __global__ void __launch_bounds__(128) score_kernel(const ScoreArgs A) {
     const ScoreUnit un = A.units[u];
     const CtfCoef cc = A.ctf[un.image];
     if (lane < PB) {
-        float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (lane < un.count) {
-            const float *q = A.poses6 + (long long)(un.first_eval + lane) * 6;
-            float r[9];
-            euler_matrix(q[0], q[1], q[2], r);
-            m[0] = r[0] * A.padf; m[1] = r[1] * A.padf;   // x = m00 i + m01 j
-            m[2] = r[3] * A.padf; m[3] = r[4] * A.padf;   // y = m10 i + m11 j
-            m[4] = r[6] * A.padf; m[5] = r[7] * A.padf;   // z = m20 i + m21 j
-            m[6] = q[3] * A.inv_npx2;
-            m[7] = q[4] * A.inv_npx2;
-        }
+        float m[8];
+        const float *q = A.poses6 + (long long)(un.first_eval + lane) * 6;
+        float r[9];
+        euler_matrix(q[0], q[1], q[2], r);
+        m[0] = r[0] * A.padf; m[1] = r[1] * A.padf;   // x = m00 i + m01 j
+        m[2] = r[3] * A.padf; m[3] = r[4] * A.padf;   // y = m10 i + m11 j
+        m[4] = r[6] * A.padf; m[5] = r[7] * A.padf;   // z = m20 i + m21 j
+        m[6] = q[3] * A.inv_npx2;
+        m[7] = q[4] * A.inv_npx2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s_pose[warp][lane][k] = m[k];
     }
@@ -253,10 +305,10 @@ __global__ void __launch_bounds__(128) score_kernel(const ScoreArgs A) {
     float ddef[PB];
 #pragma unroll
     for (int p = 0; p < PB; ++p)
-        ddef[p] = (DDEF && p < un.count) ? A.poses6[(long long)(un.first_eval + p) * 6 + 5] * cc.dstep : 0.f;
+        ddef[p] = DDEF ? A.poses6[(long long)(un.first_eval + p) * 6 + 5] * cc.dstep : 0.f;
 
     const float2 *img = A.packed + (long long)un.image * A.n_slots;
-    const long long sxy = (long long)A.sx * A.sy;
+    const int origin = (A.rc * A.sy + A.rc) * A.sx;
     float accB[PB], num[PB], xs[PB];
 #pragma unroll
     for (int p = 0; p < PB; ++p) accB[p] = num[p] = xs[p] = 0.f;
@@ -280,41 +332,54 @@ __global__ void __launch_bounds__(128) score_kernel(const ScoreArgs A) {
             float ctfv = 0.f;
             if (!DDEF) ctfv = valid ? -sinpif(chi0 * (1.f / CSPB_PI_F)) : 0.f;
             accA += F.x * F.x + F.y * F.y;
+            // SHARED units (the optimiser's +-x, +-y evaluations): rotation and CTF of pose 0 hold for
+            // every pose of the unit — one gather, PB phase ramps
+            constexpr int NG = SHARED ? 1 : PB;
+            RefQuad q0[NG], q1[NG];
+            float fx[NG], fy[NG], fz[NG], sg[NG];
+#pragma unroll
+            for (int p = 0; p < NG; ++p) {
+                const float4 ma = *reinterpret_cast<const float4 *>(&s_pose[warp][p][0]);
+                const float2 mb = *reinterpret_cast<const float2 *>(&s_pose[warp][p][4]);
+                float x = ma.x * fi + ma.y * fj;
+                float y = ma.z * fi + ma.w * fj;
+                float z = mb.x * fi + mb.y * fj;
+                // Friedel mate for the negative half space: s = sign(x)
+                const float s = __int_as_float((__float_as_int(x) & 0x80000000) | 0x3f800000);
+                x = fabsf(x); y *= s; z *= s;
+                sg[p] = s;
+                const int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
+                fx[p] = x - (float)ix; fy[p] = y - (float)iy; fz[p] = z - (float)iz;
+                const RefQuad *q = A.ref8 + (origin + (iz * A.sy + iy) * A.sx + ix);
+                q0[p] = ldg_quad(q);
+                q1[p] = ldg_quad(q + 1);
+            }
+            float px[NG], py[NG];
+#pragma unroll
+            for (int p = 0; p < NG; ++p) {
+                const float f = fx[p];
+                const float v00x = q0[p].v00.x + f * (q1[p].v00.x - q0[p].v00.x), v00y = q0[p].v00.y + f * (q1[p].v00.y - q0[p].v00.y);
+                const float v10x = q0[p].v10.x + f * (q1[p].v10.x - q0[p].v10.x), v10y = q0[p].v10.y + f * (q1[p].v10.y - q0[p].v10.y);
+                const float v01x = q0[p].v01.x + f * (q1[p].v01.x - q0[p].v01.x), v01y = q0[p].v01.y + f * (q1[p].v01.y - q0[p].v01.y);
+                const float v11x = q0[p].v11.x + f * (q1[p].v11.x - q0[p].v11.x), v11y = q0[p].v11.y + f * (q1[p].v11.y - q0[p].v11.y);
+                const float v0x = v00x + fy[p] * (v10x - v00x), v0y = v00y + fy[p] * (v10y - v00y);
+                const float v1x = v01x + fy[p] * (v11x - v01x), v1y = v01y + fy[p] * (v11y - v01y);
+                px[p] = v0x + fz[p] * (v1x - v0x);
+                py[p] = (v0y + fz[p] * (v1y - v0y)) * sg[p];
+                float cv = ctfv;
+                if (DDEF) cv = valid ? -sinpif((chi0 + r2 * ddef[p]) * (1.f / CSPB_PI_F)) : 0.f;
+                px[p] *= cv;
+                py[p] *= cv;
+            }
 #pragma unroll
             for (int p = 0; p < PB; ++p) {
-                if (p < un.count) {
-                    const float4 ma = *reinterpret_cast<const float4 *>(&s_pose[warp][p][0]);
-                    const float4 mb = *reinterpret_cast<const float4 *>(&s_pose[warp][p][4]);
-                    float x = ma.x * fi + ma.y * fj;
-                    float y = ma.z * fi + ma.w * fj;
-                    float z = mb.x * fi + mb.y * fj;
-                    const bool flip = x < 0.f;
-                    if (flip) { x = -x; y = -y; z = -z; }
-                    const float x0 = floorf(x), y0 = floorf(y), z0 = floorf(z);
-                    const float fx = x - x0, fy = y - y0, fz = z - z0;
-                    const long long idx = ((long long)((int)z0 + A.rc) * A.sy + ((int)y0 + A.rc)) * A.sx + (int)x0;
-                    const float4 a00 = __ldg(A.ref4 + idx);
-                    const float4 a10 = __ldg(A.ref4 + idx + A.sx);
-                    const float4 a01 = __ldg(A.ref4 + idx + sxy);
-                    const float4 a11 = __ldg(A.ref4 + idx + sxy + A.sx);
-                    const float v00x = a00.x + fx * (a00.z - a00.x), v00y = a00.y + fx * (a00.w - a00.y);
-                    const float v10x = a10.x + fx * (a10.z - a10.x), v10y = a10.y + fx * (a10.w - a10.y);
-                    const float v01x = a01.x + fx * (a01.z - a01.x), v01y = a01.y + fx * (a01.w - a01.y);
-                    const float v11x = a11.x + fx * (a11.z - a11.x), v11y = a11.y + fx * (a11.w - a11.y);
-                    const float v0x = v00x + fy * (v10x - v00x), v0y = v00y + fy * (v10y - v00y);
-                    const float v1x = v01x + fy * (v11x - v01x), v1y = v01y + fy * (v11y - v01y);
-                    float px = v0x + fz * (v1x - v0x), py = v0y + fz * (v1y - v0y);
-                    if (flip) py = -py;
-                    float cv = ctfv;
-                    if (DDEF) cv = valid ? -sinpif((chi0 + r2 * ddef[p]) * (1.f / CSPB_PI_F)) : 0.f;
-                    px *= cv;
-                    py *= cv;
-                    float sn, cs;
-                    sincospif(fi * mb.z + fj * mb.w, &sn, &cs);
-                    const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
-                    accX[p] += gr * px + gi * py;
-                    accB[p] += px * px + py * py;
-                }
+                const int g = SHARED ? 0 : p;
+                const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][p][6]);
+                float sn, cs;
+                sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
+                const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
+                accX[p] += gr * px[g] + gi * py[g];
+                if (!SHARED || p == 0) accB[p] += px[g] * px[g] + py[g] * py[g];
             }
         }
         const int ring = bd.ring0 + (lane & 3);
@@ -333,13 +398,13 @@ __global__ void __launch_bounds__(128) score_kernel(const ScoreArgs A) {
     accA = warp_sum(accA);
 #pragma unroll
     for (int p = 0; p < PB; ++p) {
-        const float bsum = warp_sum(accB[p]);
+        const float bsum = warp_sum(accB[SHARED ? 0 : p]);
         float nv = num[p], xv = xs[p];
         nv += __shfl_xor_sync(0xffffffffu, nv, 1);
         nv += __shfl_xor_sync(0xffffffffu, nv, 2);
         xv += __shfl_xor_sync(0xffffffffu, xv, 1);
         xv += __shfl_xor_sync(0xffffffffu, xv, 2);
-        if (lane == 0 && p < un.count) A.out[un.first_eval + p] = make_float4(nv, xv, accA, bsum);
+        if (lane == 0) A.out[un.first_eval + p] = make_float4(nv, xv, accA, bsum);
     }
 }
 
@@ -479,19 +544,19 @@ __global__ void scores_from_out_kernel(const float4 *__restrict__ sc, int n, flo
     if (k < n) scores[k] = 100.f * cc_of(sc[k]);
 }
 
-// build units from an image-sorted eval list: consecutive evals of one image, <= PB per unit
-int build_units_host(const int32_t *image_index, int n_evals, int PB, std::vector<ScoreUnit> &units) {
-    units.clear();
+// build units from an image-sorted eval list: consecutive evals of one image, <= PB per unit,
+// bucketed by count (units[c] holds the units with exactly c poses, c = 1..4)
+void build_units_host(const int32_t *image_index, int n_evals, int PB, std::vector<ScoreUnit> *units /* [5] */) {
+    for (int c = 0; c <= 4; ++c) units[c].clear();
     int e = 0;
     while (e < n_evals) {
         int c = 1;
         while (c < PB && e + c < n_evals && image_index[e + c] == image_index[e]) ++c;
         ScoreUnit un;
         un.image = image_index[e]; un.first_eval = e; un.count = c; un.pad_ = 0;
-        units.push_back(un);
+        units[c].push_back(un);
         e += c;
     }
-    return (int)units.size();
 }
 
 int grid_for(long long total, int block, int sm) {
@@ -502,12 +567,14 @@ int grid_for(long long total, int block, int sm) {
 
 }  // namespace
 
-int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals) {
+// every unit in [d_units, d_units + n_units) has exactly `count` poses (1..4)
+int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count, const float *d_poses6,
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, bool shared) {
     if (n_units <= 0) return 0;
+    if (count < 1 || count > 4) return cspb_fail(ctx, CSPB_E_ARG, "launch_score: bad unit size %d", count);
     ScoreArgs a;
-    a.ref4 = ctx->ref.d_ref4.as<float4>();
-    a.sx = ctx->ref.sx; a.sy = ctx->ref.sy; a.rc = ctx->ref.rc;
+    a.ref8 = ctx->ref.d_ref8.as<RefQuad>();
+    a.sx = ctx->ref.sx8; a.sy = ctx->ref.sy; a.rc = ctx->ref.rc;
     a.padf = (float)ctx->ref.pad;
     a.slot_ij = ctx->plan.d_slot_ij.as<int32_t>();
     a.bands = ctx->plan.d_bands.as<BandDesc>();
@@ -524,15 +591,41 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int PB, c
     a.out = d_out;
     const int grid = ceil_div(n_units, 4);
     prof_begin(ctx, CSPB_PROF_SCORE, n_evals);
-    if (PB == 1) {
-        if (ddef) score_kernel<1, true><<<grid, 128, 0, ctx->stream>>>(a);
-        else score_kernel<1, false><<<grid, 128, 0, ctx->stream>>>(a);
-    } else {
-        if (ddef) score_kernel<4, true><<<grid, 128, 0, ctx->stream>>>(a);
-        else score_kernel<4, false><<<grid, 128, 0, ctx->stream>>>(a);
+#define CSPB_LAUNCH_SCORE(PB_)                                                              \
+    do {                                                                                    \
+        if (shared) {                                                                       \
+            if (ddef) score_kernel<PB_, true, true><<<grid, 128, 0, ctx->stream>>>(a);      \
+            else score_kernel<PB_, false, true><<<grid, 128, 0, ctx->stream>>>(a);          \
+        } else {                                                                            \
+            if (ddef) score_kernel<PB_, true, false><<<grid, 128, 0, ctx->stream>>>(a);     \
+            else score_kernel<PB_, false, false><<<grid, 128, 0, ctx->stream>>>(a);         \
+        }                                                                                   \
+    } while (0)
+    switch (count) {
+    case 1: CSPB_LAUNCH_SCORE(1); break;
+    case 2: CSPB_LAUNCH_SCORE(2); break;
+    case 3: CSPB_LAUNCH_SCORE(3); break;
+    default: CSPB_LAUNCH_SCORE(4); break;
     }
+#undef CSPB_LAUNCH_SCORE
     prof_end(ctx);
     KERNEL_CHECK(ctx);
+    return 0;
+}
+
+// units in the class layout of opt_stencil_kernel / csp_expand_kernel:
+// [A full: n*(nA/PB)] [A tail: n if nA%PB] [S full: n*(nS/PB)] [S tail: n if nS%PB]; S = shared units
+int launch_score_classes(cspb_ctx *ctx, const ScoreUnit *d_units, int n_groups, int nA, int nS, int PB, const float *d_poses6,
+                         const CtfCoef *d_ctf, float4 *d_out, bool ddef) {
+    const int cls[4][2] = {{nA / PB, PB}, {nA % PB ? 1 : 0, nA % PB}, {nS / PB, PB}, {nS % PB ? 1 : 0, nS % PB}};
+    size_t off = 0;
+    for (int c = 0; c < 4; ++c) {
+        const int n_units = n_groups * cls[c][0];
+        if (n_units == 0) continue;
+        int rc = launch_score(ctx, d_units + off, n_units, cls[c][1], d_poses6, d_ctf, d_out, ddef, (int64_t)n_units * cls[c][1], c >= 2);
+        if (rc) return rc;
+        off += n_units;
+    }
     return 0;
 }
 
@@ -745,6 +838,11 @@ extern "C" int cspb_set_reference(cspb_ctx *ctx, const float *vol, int n, int lo
     crop_pair_kernel<<<grid_for((long long)rv.sx * rv.sy * rv.sy, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
         ctx->d_work1.as<float2>(), rv.d_ref4.as<float4>(), np, rv.rc, rv.sx, rv.sy);
     KERNEL_CHECK(ctx);
+    rv.sx8 = rv.rc + 2;
+    RESERVE(ctx, rv.d_ref8, (size_t)rv.sx8 * rv.sy * rv.sy * sizeof(RefQuad));
+    crop_quad_kernel<<<grid_for((long long)rv.sx8 * rv.sy * rv.sy, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        ctx->d_work1.as<float2>(), rv.d_ref8.as<RefQuad>(), np, rv.rc, rv.sx8, rv.sy);
+    KERNEL_CHECK(ctx);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     rv.ready = true;
     return 0;
@@ -914,20 +1012,28 @@ extern "C" int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int 
     CtfCoef *d_ctf;
     int rc = upload_rows(ctx, rows, n_rows, &d_rows, &d_ctf);
     if (rc) return rc;
-    std::vector<ScoreUnit> units;
+    std::vector<ScoreUnit> units[5];
     bool ddef = false;
     for (int e = 0; e < n_evals && !ddef; ++e) ddef = poses6[(size_t)e * 6 + 5] != 0.f;
     const int PB = (n_evals >= 2 * n_rows) ? 4 : 1;
-    const int n_units = build_units_host(image_index, n_evals, PB, units);
+    build_units_host(image_index, n_evals, PB, units);
+    std::vector<ScoreUnit> flat;
+    for (int c = 1; c <= 4; ++c) flat.insert(flat.end(), units[c].begin(), units[c].end());
+    const int n_units = (int)flat.size();
     RESERVE(ctx, ctx->d_evals, (size_t)n_evals * 6 * sizeof(float));
     RESERVE(ctx, ctx->d_units, (size_t)n_units * sizeof(ScoreUnit));
     RESERVE(ctx, ctx->d_out, (size_t)n_evals * (sizeof(float4) + sizeof(float)));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->d_evals.p, poses6, (size_t)n_evals * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), (size_t)n_units * sizeof(ScoreUnit), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, flat.data(), (size_t)n_units * sizeof(ScoreUnit), cudaMemcpyHostToDevice, ctx->stream));
     float4 *d_out = ctx->d_out.as<float4>();
     float *d_sc = reinterpret_cast<float *>(d_out + n_evals);
-    rc = launch_score(ctx, ctx->d_units.as<ScoreUnit>(), n_units, PB, ctx->d_evals.as<float>(), d_ctf, d_out, ddef, n_evals);
-    if (rc) return rc;
+    size_t off = 0;
+    for (int c = 1; c <= 4; ++c) {
+        rc = launch_score(ctx, ctx->d_units.as<ScoreUnit>() + off, (int)units[c].size(), c, ctx->d_evals.as<float>(), d_ctf, d_out, ddef,
+                          (int64_t)units[c].size() * c, false);
+        if (rc) return rc;
+        off += units[c].size();
+    }
     scores_from_out_kernel<<<ceil_div(n_evals, 256), 256, 0, ctx->stream>>>(d_out, n_evals, d_sc);
     KERNEL_CHECK(ctx);
     CU_TRY(ctx, cudaMemcpyAsync(scores_out, d_sc, (size_t)n_evals * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -982,7 +1088,9 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     for (int m = 0; m < OPT_NP; ++m) n_free += (free_mask >> m) & 1;
     const int ns = n * K;  // optimiser states
     const int NE = 1 + 2 * n_free, PB = 4;
-    const int upi = (NE + PB - 1) / PB;
+    const int shift_mask = free_mask & 24;  // x, y: pure image shifts, scored from the centre's gather
+    const int nS = 2 * (((shift_mask >> 3) & 1) + ((shift_mask >> 4) & 1));
+    const int upi = (NE + PB - 1) / PB + 1;
     const bool ddef = c.refine_defocus != 0;
     const bool do_local = (c.local_refine || c.global_search) && n_free > 0;
     const int iters = do_local ? (c.local_iterations > 0 ? c.local_iterations : 8) : 0;
@@ -1003,13 +1111,13 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, ns, K, d_hits, d_angles, st, h_ang, h_shift, h_def);
     KERNEL_CHECK(ctx);
     for (int it = 0; it < iters; ++it) {
-        opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, PB, ev, un);
+        opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, shift_mask, NE, PB, ev, un);
         KERNEL_CHECK(ctx);
-        int rc = launch_score(ctx, un, ns * upi, PB, ev, d_ctf, out, ddef, (int64_t)ns * NE);
+        int rc = launch_score_classes(ctx, un, ns, NE - nS, nS, PB, ev, d_ctf, out, ddef);
         if (rc) return rc;
         opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, out, ev_ls, un_ls);
         KERNEL_CHECK(ctx);
-        rc = launch_score(ctx, un_ls, ns, PB, ev_ls, d_ctf, out_ls, ddef, (int64_t)ns * OPT_NL);
+        rc = launch_score(ctx, un_ls, ns, OPT_NL, ev_ls, d_ctf, out_ls, ddef, (int64_t)ns * OPT_NL, false);
         if (rc) return rc;
         opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, out_ls, it + 1 >= late ? 0.6f : 1.f);
         KERNEL_CHECK(ctx);
@@ -1017,7 +1125,7 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     }
     opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, ev, un);
     KERNEL_CHECK(ctx);
-    int rc = launch_score(ctx, un, ns, 4, ev, d_ctf, out, ddef, 2 * (int64_t)ns);
+    int rc = launch_score(ctx, un, ns, 2, ev, d_ctf, out, ddef, 2 * (int64_t)ns, false);
     if (rc) return rc;
     evals += 2 * (int64_t)ns;
     opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes);

@@ -209,7 +209,7 @@ def test_global_search_matches_oracle(engine, oracle):
     # and the search finds the true poses from scratch
     # (band limit r_hi = 16 Fourier pixels at SNR 0.1: the resolution-limited accuracy is a few degrees)
     assert np.median(angular_distance(got, rows)) < 4.0
-    assert np.median(np.hypot(got["x_shift"] - rows["x_shift"], got["y_shift"] - rows["y_shift"])) < 0.3 * px
+    assert np.median(np.hypot(got["x_shift"] - rows["x_shift"], got["y_shift"] - rows["y_shift"])) < 1.0 * px
 
 
 def fold_x0(d):
