@@ -12,6 +12,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include "device_math.cuh"
+#include "fft_fast.cuh"
 #include "fft_smem.cuh"
 #include "internal.cuh"
 
@@ -28,7 +30,7 @@ __global__ void fft_lines_kernel(float2 *__restrict__ data, int n, long long est
                                  const float2 *__restrict__ tw_g, float scale, int sign_mode,
                                  int inner_w) {
     extern __shared__ float2 smem[];
-    const int pitch = n + 1;
+    const int pitch = line_pitch(n);
     float2 *tw = smem;
     float2 *bufa = smem + n;
     float2 *bufb = bufa + (size_t)T * pitch;
@@ -40,14 +42,14 @@ __global__ void fft_lines_kernel(float2 *__restrict__ data, int n, long long est
     for (int i = tid; i < n; i += nt) tw[i] = tw_g[i];
     for (int idx = tid; idx < n * T; idx += nt) {
         const int e = idx / T, t = idx - e * T;
-        if (t < nl) bufa[t * pitch + e] = base[(long long)e * estride + t];
+        if (t < nl) bufa[t * pitch + skew(e)] = base[(long long)e * estride + t];
     }
     __syncthreads();
     float2 *res = fft_lines_smem<DIR>(bufa, bufb, pitch, nl, n, rad, tw, tid, nt);
     for (int idx = tid; idx < n * T; idx += nt) {
         const int e = idx / T, t = idx - e * T;
         if (t < nl) {
-            float2 v = res[t * pitch + e];
+            float2 v = res[t * pitch + skew(e)];
             float s = scale;
             if (sign_mode) {
                 const int ti = t0 + t;
@@ -67,7 +69,7 @@ __global__ void fft_rows_r2c_kernel(const float *__restrict__ in, float2 *__rest
                                     const float2 *__restrict__ tw_g, int rows_per_image,
                                     const float *__restrict__ offs, const float *__restrict__ scls) {
     extern __shared__ float2 smem[];
-    const int pitch = n + 1;
+    const int pitch = line_pitch(n);
     float2 *tw = smem;
     float2 *bufa = smem + n;
     float2 *bufb = bufa + (size_t)PR * pitch;
@@ -86,15 +88,15 @@ __global__ void fft_rows_r2c_kernel(const float *__restrict__ in, float2 *__rest
             a = (a - o) * s;
             b = (b - o) * s;
         }
-        bufa[p * pitch + e] = make_float2(a, b);
+        bufa[p * pitch + skew(e)] = make_float2(a, b);
     }
     __syncthreads();
     float2 *res = fft_lines_smem<-1>(bufa, bufb, pitch, np_, n, rad, tw, tid, nt);
     const int nh = n / 2 + 1;
     for (int idx = tid; idx < np_ * nh; idx += nt) {
         const int p = idx / nh, k = idx - p * nh;
-        const float2 za = res[p * pitch + k];
-        float2 zb = res[p * pitch + ((n - k) % n)];
+        const float2 za = res[p * pitch + skew(k)];
+        float2 zb = res[p * pitch + skew((n - k) % n)];
         zb.y = -zb.y;
         const float2 fa = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y + zb.y));
         const float2 df = make_float2(za.x - zb.x, za.y - zb.y);
@@ -110,7 +112,7 @@ __global__ void fft_rows_c2r_kernel(const float2 *__restrict__ in, float *__rest
                                     long long n_rows, int PR, Radices rad,
                                     const float2 *__restrict__ tw_g, float scale) {
     extern __shared__ float2 smem[];
-    const int pitch = n + 1;
+    const int pitch = line_pitch(n);
     float2 *tw = smem;
     float2 *bufa = smem + n;
     float2 *bufb = bufa + (size_t)PR * pitch;
@@ -129,24 +131,176 @@ __global__ void fft_rows_c2r_kernel(const float2 *__restrict__ in, float *__rest
             fb.y = 0.f;
         }
         // Z[k] = fa + i fb ; Z[n-k] = conj(fa) + i conj(fb)
-        bufa[p * pitch + k] = make_float2(fa.x - fb.y, fa.y + fb.x);
-        if (k > 0 && 2 * k < n) bufa[p * pitch + n - k] = make_float2(fa.x + fb.y, -fa.y + fb.x);
+        bufa[p * pitch + skew(k)] = make_float2(fa.x - fb.y, fa.y + fb.x);
+        if (k > 0 && 2 * k < n) bufa[p * pitch + skew(n - k)] = make_float2(fa.x + fb.y, -fa.y + fb.x);
     }
     __syncthreads();
     float2 *res = fft_lines_smem<+1>(bufa, bufb, pitch, np_, n, rad, tw, tid, nt);
     for (int idx = tid; idx < np_ * n; idx += nt) {
         const int p = idx / n, e = idx - p * n;
         const long long ra = (pair0 + p) * 2;
-        const float2 v = res[p * pitch + e];
+        const float2 v = res[p * pitch + skew(e)];
         out[ra * n + e] = v.x * scale;
         out[(ra + 1) * n + e] = v.y * scale;
+    }
+}
+
+// ================================================================ fast path: n = R1 * R2
+// strided complex lines, tile of TL = 16 adjacent lines per CTA (lane = line: 128-byte segments)
+template <int R1, int R2, int DIR>
+__global__ void __launch_bounds__(256) fft_lines_fast_kernel(float2 *__restrict__ data, long long estride, int ninner,
+                                                             long long ostride, int ntiles, const float2 *__restrict__ tw_g,
+                                                             float scale, int sign_mode, int inner_w,
+                                                             const float *__restrict__ filt, int filt_w) {
+    constexpr int N = R1 * R2, TL = 16, P = N + (N >> 4) + 1;
+    __shared__ float2 S[TL * P];
+    __shared__ float2 tw[N];
+    const int tid = threadIdx.x;
+    const int l = tid & (TL - 1), t = tid >> 4;  // R2 threads per line in stage 1
+    const int outer = blockIdx.x / ntiles;
+    const int t0 = (blockIdx.x - outer * ntiles) * TL;
+    const bool live = t0 + l < ninner;
+    float2 *base = data + (long long)outer * ostride + t0 + l;
+    for (int i = tid; i < N; i += 256) tw[i] = tw_g[i];
+    float2 v[R1 > R2 ? R1 : R2];
+    if (t < R2) {
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = live ? base[(long long)(t + R2 * r) * estride] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    if (t < R2) fftfast::stage1<R1, R2, DIR>(v, t, S + l * P, tw);
+    __syncthreads();
+    if (t < R1) {
+        fftfast::stage2<R1, R2, DIR>(v, t, S + l * P);
+        if (live) {
+            const int ti = t0 + l;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int e = t + R1 * k2;
+                float s = scale;
+                if (sign_mode && ((e + ti % inner_w + ti / inner_w) & 1)) s = -s;
+                if (filt) {  // radial filter: line index = i (x frequency), element = j (y frequency)
+                    const int j = e >= N / 2 ? e - N : e;
+                    const int i = ti % filt_w;
+                    s *= filt[(int)(sqrtf((float)(i * i + j * j)) + 0.5f)];
+                }
+                base[(long long)e * estride] = make_float2(v[k2].x * s, v[k2].y * s);
+            }
+        }
+    }
+}
+
+// real rows -> half spectrum, PR = 16 row pairs per CTA (lane = element: contiguous rows)
+template <int R1, int R2>
+__global__ void __launch_bounds__(256) fft_rows_r2c_fast_kernel(const float *__restrict__ in, float2 *__restrict__ out,
+                                                                long long n_rows, const float2 *__restrict__ tw_g,
+                                                                int rows_per_image, const float *__restrict__ offs,
+                                                                const float *__restrict__ scls) {
+    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1;
+    __shared__ float2 S[PR * P];
+    __shared__ float2 tw[N];
+    const int tid = threadIdx.x;
+    const int t = tid % R2, p = tid / R2;
+    const long long pair = (long long)blockIdx.x * PR + p;
+    const bool live = pair < n_rows / 2;
+    for (int i = tid; i < N; i += 256) tw[i] = tw_g[i];
+    float2 v[R1 > R2 ? R1 : R2];
+    {
+        const float *ra = in + pair * 2 * N, *rb = ra + N;
+        float o = 0.f, sc = 1.f;
+        if (live && scls) {
+            const long long img = pair * 2 / rows_per_image;
+            o = offs[img];
+            sc = scls[img];
+        }
+#pragma unroll
+        for (int r = 0; r < R1; ++r)
+            v[r] = live ? make_float2((ra[t + R2 * r] - o) * sc, (rb[t + R2 * r] - o) * sc) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fftfast::stage1<R1, R2, -1>(v, t, S + p * P, tw);
+    __syncthreads();
+    if (t < R1) fftfast::stage2<R1, R2, -1>(v, t, S + p * P);
+    __syncthreads();
+    // natural-order spectrum of the packed line back to shared memory, then untangle the two rows
+    if (t < R1) {
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) S[p * P + fftsm::skew(t + R1 * k2)] = v[k2];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < PR * NH; idx += 256) {
+        const int pp = idx / NH, k = idx - pp * NH;
+        const long long pr = (long long)blockIdx.x * PR + pp;
+        if (pr >= n_rows / 2) break;
+        const float2 za = S[pp * P + fftsm::skew(k)];
+        float2 zb = S[pp * P + fftsm::skew((N - k) & (N - 1))];
+        zb.y = -zb.y;
+        const float2 fa = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y + zb.y));
+        const float2 df = make_float2(za.x - zb.x, za.y - zb.y);
+        const float2 fb = make_float2(0.5f * df.y, -0.5f * df.x);
+        out[pr * 2 * NH + k] = fa;
+        out[(pr * 2 + 1) * NH + k] = fb;
+    }
+}
+
+// half spectrum rows -> real rows (unnormalised inverse), optional real-space multiplier per pixel:
+// mask(r) = scale * cosine_edge(r, mask_radius, mask_width) with r from the image centre
+template <int R1, int R2>
+__global__ void __launch_bounds__(256) fft_rows_c2r_fast_kernel(const float2 *__restrict__ in, float *__restrict__ out,
+                                                                long long n_rows, const float2 *__restrict__ tw_g, float scale,
+                                                                float mask_radius, float mask_width) {
+    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1;
+    __shared__ float2 S[PR * P];
+    float2 *Z = S;  // the packed spectrum is staged in the same buffer (extra barrier below)
+    __shared__ float2 tw[N];
+    const int tid = threadIdx.x;
+    const int t = tid % R2, p = tid / R2;
+    const long long pair = (long long)blockIdx.x * PR + p;
+    const bool live = pair < n_rows / 2;
+    for (int i = tid; i < N; i += 256) tw[i] = tw_g[i];
+    // Z[k] = fa + i fb ; Z[n-k] = conj(fa) + i conj(fb)
+    for (int idx = tid; idx < PR * NH; idx += 256) {
+        const int pp = idx / NH, k = idx - pp * NH;
+        const long long pr = (long long)blockIdx.x * PR + pp;
+        if (pr >= n_rows / 2) break;
+        float2 fa = in[pr * 2 * NH + k], fb = in[(pr * 2 + 1) * NH + k];
+        if (k == 0 || 2 * k == N) {
+            fa.y = 0.f;
+            fb.y = 0.f;
+        }
+        Z[pp * P + fftsm::skew(k)] = make_float2(fa.x - fb.y, fa.y + fb.x);
+        if (k > 0 && 2 * k < N) Z[pp * P + fftsm::skew(N - k)] = make_float2(fa.x + fb.y, -fa.y + fb.x);
+    }
+    __syncthreads();
+    float2 v[R1 > R2 ? R1 : R2];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) v[r] = live ? Z[p * P + fftsm::skew(t + R2 * r)] : make_float2(0.f, 0.f);
+    __syncthreads();
+    fftfast::stage1<R1, R2, +1>(v, t, S + p * P, tw);
+    __syncthreads();
+    if (t < R1 && live) {
+        fftfast::stage2<R1, R2, +1>(v, t, S + p * P);
+        float *ra = out + pair * 2 * N, *rb = ra + N;
+        const int ya = (int)((pair * 2) % N) - N / 2, yb = ya + 1;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+            const int e = t + R1 * k2;
+            float sa = scale, sb = scale;
+            if (mask_width > 0.f) {
+                const float x = (float)(e - N / 2);
+                sa *= cosine_edge(sqrtf(x * x + (float)(ya * ya)), mask_radius, mask_width);
+                sb *= cosine_edge(sqrtf(x * x + (float)(yb * yb)), mask_radius, mask_width);
+            }
+            ra[e] = v[k2].x * sa;
+            rb[e] = v[k2].y * sb;
+        }
     }
 }
 
 int pick_tile(int n) {
     // keep 2 buffers of T lines within ~96 KB so two CTAs fit per SM
     int T = 16;
-    while (T > 4 && (size_t)2 * T * (n + 1) * 8 > 96 * 1024) T /= 2;
+    while (T > 4 && (size_t)2 * T * line_pitch(n) * 8 > 96 * 1024) T /= 2;
     return T;
 }
 
@@ -157,14 +311,34 @@ template <class K> int set_smem(cspb_ctx *ctx, K kernel, size_t bytes) {
 }
 
 int launch_lines(cspb_ctx *ctx, float2 *data, int n, long long estride, int ninner, long long ostride,
-                 int n_outer, int dir, float scale, int sign_mode, int inner_w) {
+                 int n_outer, int dir, float scale, int sign_mode, int inner_w, const float *filt = nullptr, int filt_w = 1) {
     Radices rad;
     if (!factor(n, rad)) return cspb_fail(ctx, CSPB_E_ARG, "FFT length %d is not 2^a*3^b", n);
     const float2 *tw;
     int rc = fft_get_twiddles(ctx, n, &tw);
     if (rc) return rc;
+    if (n == 256 || n == 128 || n == 64) {
+        const int ntiles = ceil_div(ninner, 16);
+        const unsigned grid = (unsigned)((long long)ntiles * n_outer);
+#define CSPB_LINES_FAST(R1_, R2_)                                                                                       \
+    do {                                                                                                                \
+        if (dir < 0)                                                                                                    \
+            fft_lines_fast_kernel<R1_, R2_, -1><<<grid, 256, 0, ctx->stream>>>(data, estride, ninner, ostride, ntiles, tw, scale, \
+                                                                               sign_mode, inner_w, filt, filt_w);       \
+        else                                                                                                            \
+            fft_lines_fast_kernel<R1_, R2_, +1><<<grid, 256, 0, ctx->stream>>>(data, estride, ninner, ostride, ntiles, tw, scale, \
+                                                                               sign_mode, inner_w, filt, filt_w);       \
+    } while (0)
+        if (n == 256) CSPB_LINES_FAST(16, 16);
+        else if (n == 128) CSPB_LINES_FAST(8, 16);
+        else CSPB_LINES_FAST(8, 8);
+#undef CSPB_LINES_FAST
+        KERNEL_CHECK(ctx);
+        return 0;
+    }
+    if (filt) return cspb_fail(ctx, CSPB_E_ARG, "fused radial filter needs the fast FFT path (n = 64/128/256)");
     const int T = pick_tile(n);
-    const size_t smem = ((size_t)n + (size_t)2 * T * (n + 1)) * sizeof(float2);
+    const size_t smem = ((size_t)n + (size_t)2 * T * line_pitch(n)) * sizeof(float2);
     const int ntiles = ceil_div(ninner, T);
     const unsigned grid = (unsigned)((long long)ntiles * n_outer);
     if (dir < 0) {
@@ -187,26 +361,42 @@ int launch_rows_r2c(cspb_ctx *ctx, const float *in, float2 *out, int n, long lon
     const float2 *tw;
     int rc = fft_get_twiddles(ctx, n, &tw);
     if (rc) return rc;
-    const int PR = pick_tile(n);
-    const size_t smem = ((size_t)n + (size_t)2 * PR * (n + 1)) * sizeof(float2);
-    if ((rc = set_smem(ctx, fft_rows_r2c_kernel, smem))) return rc;
     const long long n_pairs = n_rows / 2;
+    if (n == 256 || n == 128 || n == 64) {
+        if (n == 256) fft_rows_r2c_fast_kernel<16, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
+        else if (n == 128) fft_rows_r2c_fast_kernel<8, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
+        else fft_rows_r2c_fast_kernel<8, 8><<<ceil_div(n_pairs, 32), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
+        KERNEL_CHECK(ctx);
+        return 0;
+    }
+    const int PR = pick_tile(n);
+    const size_t smem = ((size_t)n + (size_t)2 * PR * line_pitch(n)) * sizeof(float2);
+    if ((rc = set_smem(ctx, fft_rows_r2c_kernel, smem))) return rc;
     fft_rows_r2c_kernel<<<ceil_div(n_pairs, PR), 256, smem, ctx->stream>>>(in, out, n, n_rows, PR, rad, tw,
                                                                           rows_per_image, offs, scls);
     KERNEL_CHECK(ctx);
     return 0;
 }
 
-int launch_rows_c2r(cspb_ctx *ctx, const float2 *in, float *out, int n, long long n_rows, float scale) {
+int launch_rows_c2r(cspb_ctx *ctx, const float2 *in, float *out, int n, long long n_rows, float scale,
+                    float mask_radius = 0.f, float mask_width = 0.f) {
     Radices rad;
     if (!factor(n, rad) || (n & 1)) return cspb_fail(ctx, CSPB_E_ARG, "FFT length %d unsupported", n);
     const float2 *tw;
     int rc = fft_get_twiddles(ctx, n, &tw);
     if (rc) return rc;
-    const int PR = pick_tile(n);
-    const size_t smem = ((size_t)n + (size_t)2 * PR * (n + 1)) * sizeof(float2);
-    if ((rc = set_smem(ctx, fft_rows_c2r_kernel, smem))) return rc;
     const long long n_pairs = n_rows / 2;
+    if (n == 256 || n == 128 || n == 64) {
+        if (n == 256) fft_rows_c2r_fast_kernel<16, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
+        else if (n == 128) fft_rows_c2r_fast_kernel<8, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
+        else fft_rows_c2r_fast_kernel<8, 8><<<ceil_div(n_pairs, 32), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
+        KERNEL_CHECK(ctx);
+        return 0;
+    }
+    if (mask_width > 0.f) return cspb_fail(ctx, CSPB_E_ARG, "fused mask needs the fast FFT path (n = 64/128/256)");
+    const int PR = pick_tile(n);
+    const size_t smem = ((size_t)n + (size_t)2 * PR * line_pitch(n)) * sizeof(float2);
+    if ((rc = set_smem(ctx, fft_rows_c2r_kernel, smem))) return rc;
     fft_rows_c2r_kernel<<<ceil_div(n_pairs, PR), 256, smem, ctx->stream>>>(in, out, n, n_rows, PR, rad, tw, scale);
     KERNEL_CHECK(ctx);
     return 0;

@@ -1,4 +1,4 @@
-// fft_smem.cuh — shared-memory FFT building block: mixed-radix (4/2/3) Stockham autosort passes
+// fft_smem.cuh — shared-memory FFT building block: mixed-radix (16/8/4/2/3) Stockham autosort passes
 // over lines held in shared memory, ping-ponging between two buffers; twiddles W_n^k from a table.
 #pragma once
 #include <cuda_runtime.h>
@@ -43,6 +43,66 @@ template <int DIR> struct Butterfly<3, DIR> {
     }
 };
 
+// W_16^k = exp(DIR * 2 pi i k / 16), k = 0..3 (higher powers by symmetry)
+template <int DIR> __device__ __forceinline__ float2 mul_w16(float2 v, int k) {
+    const float c1 = 0.92387953251128673848f, s1 = 0.38268343236508978178f, h = 0.70710678118654752440f;
+    // (c + i DIR s)
+    switch (k) {
+    case 0: return v;
+    case 1: return make_float2(v.x * c1 - DIR * v.y * s1, v.y * c1 + DIR * v.x * s1);
+    case 2: return make_float2((v.x - DIR * v.y) * h, (v.y + DIR * v.x) * h);
+    case 3: return make_float2(v.x * s1 - DIR * v.y * c1, v.y * s1 + DIR * v.x * c1);
+    case 4: return make_float2(-DIR * v.y, DIR * v.x);
+    case 6: return make_float2((-v.x - DIR * v.y) * h, (-v.y + DIR * v.x) * h);
+    case 9: return make_float2(-v.x * c1 + DIR * v.y * s1, -v.y * c1 - DIR * v.x * s1);
+    default: return v;
+    }
+}
+// radix 8 = 2 x 4: n = a + 2m, k = b + 4c
+template <int DIR> struct Butterfly<8, DIR> {
+    __device__ __forceinline__ static void run(float2 *v) {
+        float2 t[2][4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            float2 u[4] = {v[a], v[a + 2], v[a + 4], v[a + 6]};
+            Butterfly<4, DIR>::run(u);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) t[a][b] = a ? mul_w16<DIR>(u[b], 2 * b) : u[b];  // W_8^(ab) = W_16^(2ab)
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            v[b] = cadd(t[0][b], t[1][b]);
+            v[b + 4] = csub(t[0][b], t[1][b]);
+        }
+    }
+};
+// radix 16 = 4 x 4: n = a + 4m, k = b + 4c
+template <int DIR> struct Butterfly<16, DIR> {
+    __device__ __forceinline__ static void run(float2 *v) {
+        float2 t[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float2 u[4] = {v[a], v[a + 4], v[a + 8], v[a + 12]};
+            Butterfly<4, DIR>::run(u);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) t[a][b] = mul_w16<DIR>(u[b], a * b);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float2 u[4] = {t[0][b], t[1][b], t[2][b], t[3][b]};
+            Butterfly<4, DIR>::run(u);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[b + 4 * c] = u[c];
+        }
+    }
+};
+
+// skewed shared-memory index: one padding element per 16 keeps the stride-R stores of a radix-8/16
+// Stockham pass and the unit-stride loads of the next one free of bank conflicts
+__host__ __device__ __forceinline__ int skew(int a) { return a + (a >> 4); }
+// elements a line of n complex values occupies in shared memory (skewed, +1 against pitch conflicts)
+__host__ __device__ __forceinline__ int line_pitch(int n) { return n + (n >> 4) + 1; }
+
 template <int R, int DIR>
 __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, float2 *__restrict__ dst,
                                               int pitch, int nlines, int n, int Ns,
@@ -58,7 +118,7 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
         const int k = j % Ns;
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = s[j + r * per_line];
+        for (int r = 0; r < R; ++r) v[r] = s[skew(j + r * per_line)];
 #pragma unroll
         for (int r = 1; r < R; ++r) {
             float2 t = tw[r * k * tws];
@@ -68,7 +128,7 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
         Butterfly<R, DIR>::run(v);
         const int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) d[j0 + r * Ns] = v[r];
+        for (int r = 0; r < R; ++r) d[skew(j0 + r * Ns)] = v[r];
     }
 }
 
@@ -86,7 +146,11 @@ __device__ __forceinline__ float2 *fft_lines_smem(float2 *a, float2 *b, int pitc
     float2 *src = a, *dst = b;
     for (int p = 0; p < rad.count; ++p) {
         const int R = rad.r[p];
-        if (R == 4)
+        if (R == 16)
+            stockham_pass<16, DIR>(src, dst, pitch, nlines, n, Ns, tw, tid, nthreads);
+        else if (R == 8)
+            stockham_pass<8, DIR>(src, dst, pitch, nlines, n, Ns, tw, tid, nthreads);
+        else if (R == 4)
             stockham_pass<4, DIR>(src, dst, pitch, nlines, n, Ns, tw, tid, nthreads);
         else if (R == 2)
             stockham_pass<2, DIR>(src, dst, pitch, nlines, n, Ns, tw, tid, nthreads);
@@ -105,6 +169,8 @@ __device__ __forceinline__ float2 *fft_lines_smem(float2 *a, float2 *b, int pitc
 inline bool factor(int n, Radices &rad) {
     rad.count = 0;
     int m = n;
+    while (m % 16 == 0) { rad.r[rad.count++] = 16; m /= 16; }
+    while (m % 8 == 0) { rad.r[rad.count++] = 8; m /= 8; }
     while (m % 4 == 0) { rad.r[rad.count++] = 4; m /= 4; }
     while (m % 2 == 0) { rad.r[rad.count++] = 2; m /= 2; }
     while (m % 3 == 0) { rad.r[rad.count++] = 3; m /= 3; }

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
                                                      const float *__restrict__ A, const float2 *__restrict__ Pall,
                                                      int n_orient, int K, float shift_scale, Hit *__restrict__ hits) {
     extern __shared__ float2 sm[];
-    const int nb = S.nb, pitch = nb + 1, nl = S.i_max + 1, nrp = S.n_rowpairs;
+    const int nb = S.nb, pitch = fftsm::line_pitch(nb), nl = S.i_max + 1, nrp = S.n_rowpairs;
     float2 *tw = sm;                              // nb
     float2 *g = tw + nb;                          // n_ss
     float2 *bufa = g + S.n_ss;                    // nl * pitch   (columns, line = fixed i)
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
         c2m[s] = C2[(long long)p * S.n_ss + s] * S.ss_mult[s];
         const int ij = S.ss_ij[s];
         const int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
-        pos[s] = i * pitch + (j < 0 ? j + nb : j);
+        pos[s] = i * pitch + fftsm::skew(j < 0 ? j + nb : j);
     }
     for (int k = tid; k < K; k += nt) {
         top[k].score = -1e30f; top[k].sx = 0.f; top[k].sy = 0.f; top[k].orient = -1;
@@ -125,10 +125,10 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
         for (int k = tid; k < nrp * nl; k += nt) {
             const int q = k / nl, i = k - q * nl;
             const int ya = ((first + 2 * q) % nb + nb) % nb, yb = ((first + 2 * q + 1) % nb + nb) % nb;
-            float2 fa = T[i * pitch + ya], fb = T[i * pitch + yb];
+            float2 fa = T[i * pitch + fftsm::skew(ya)], fb = T[i * pitch + fftsm::skew(yb)];
             if (i == 0) { fa.y = 0.f; fb.y = 0.f; }  // the DC column of a real image is real
-            rowa[q * pitch + i] = make_float2(fa.x - fb.y, fa.y + fb.x);
-            if (i > 0) rowa[q * pitch + nb - i] = make_float2(fa.x + fb.y, -fa.y + fb.x);
+            rowa[q * pitch + fftsm::skew(i)] = make_float2(fa.x - fb.y, fa.y + fb.x);
+            if (i > 0) rowa[q * pitch + fftsm::skew(nb - i)] = make_float2(fa.x + fb.y, -fa.y + fb.x);
         }
         __syncthreads();
         float2 *R = fft_lines_smem<+1>(rowa, rowb, pitch, nrp, nb, rad, tw, tid, nt);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
         for (int k = tid; k < wxs * wys; k += nt) {
             const int dy = k / wxs - S.wy, dx = k % wxs - S.wx;
             const int rr = dy - first, q = rr >> 1;
-            const float2 v = R[q * pitch + ((dx + nb) % nb)];
+            const float2 v = R[q * pitch + fftsm::skew((dx + nb) % nb)];
             const float val = (rr & 1) ? v.y : v.x;
             if (val > best) { best = val; bidx = k; }
         }
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
             const int dy = bidx / wxs - S.wy, dx = bidx % wxs - S.wx;
             auto at = [&](int ddx, int ddy) {
                 const int rr = ddy - first, q = rr >> 1;
-                const float2 v = R[q * pitch + ((ddx + nb) % nb)];
+                const float2 v = R[q * pitch + fftsm::skew((ddx + nb) % nb)];
                 return (rr & 1) ? v.y : v.x;
             };
             const float v0 = best, xm = at(dx - 1, dy), xp = at(dx + 1, dy), ym = at(dx, dy - 1), yp = at(dx, dy + 1);
@@ -263,7 +263,7 @@ int search_enqueue(cspb_ctx *ctx, const CtfCoef *d_ctf, const float *d_angles3, 
     search_slices_kernel<<<grid_for((long long)n_orient * n_ss, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
         S, ctx->ref.d_ref4.as<float4>(), ctx->ref.sx, ctx->ref.sy, ctx->ref.rc, (float)ctx->ref.pad, d_angles3, n_orient, Pall);
     KERNEL_CHECK(ctx);
-    const int pitch = nb + 1, nl = i_max + 1;
+    const int pitch = fftsm::line_pitch(nb), nl = i_max + 1;
     const size_t smem = ((size_t)nb + n_ss + 2 * (size_t)nl * pitch + 2 * (size_t)S.n_rowpairs * pitch) * sizeof(float2) +
                         (size_t)n_ss * 8 + (size_t)K * sizeof(Hit);
     if (smem > 220 * 1024) return cspb_fail(ctx, CSPB_E_ARG, "global-search box %d needs %zu B of shared memory", nb, smem);
