@@ -428,19 +428,22 @@ int fft_get_twiddles(cspb_ctx *ctx, int n, const float2 **tw_out) {
     return 0;
 }
 
+bool fft_has_fast_path(int n) { return n == 64 || n == 128 || n == 256; }
+
 int fft2_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int n, int batch, const float *offs,
-                 const float *scls) {
+                 const float *scls, const float *radial_filter) {
     int rc = launch_rows_r2c(ctx, in, out, n, (long long)batch * n, n, offs, scls);
     if (rc) return rc;
     const int nh = n / 2 + 1;
-    return launch_lines(ctx, out, n, nh, nh, (long long)n * nh, batch, -1, 1.f, 0, nh);
+    return launch_lines(ctx, out, n, nh, nh, (long long)n * nh, batch, -1, 1.f, 0, nh, radial_filter, nh);
 }
 
-int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch) {
+int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch, float scale, float mask_radius,
+                 float mask_width) {
     const int nh = n / 2 + 1;
     int rc = launch_lines(ctx, inout_c, n, nh, nh, (long long)n * nh, batch, +1, 1.f, 0, nh);
     if (rc) return rc;
-    return launch_rows_c2r(ctx, inout_c, out, n, (long long)batch * n, 1.f);
+    return launch_rows_c2r(ctx, inout_c, out, n, (long long)batch * n, scale, mask_radius, mask_width);
 }
 
 int fft3_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int np) {

@@ -205,9 +205,13 @@ int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, C
 int fft_get_twiddles(cspb_ctx *ctx, int n, const float2 **tw_out);
 // batched 2-D R2C / C2R on device buffers; out pitch = n/2+1 complex per row
 // scale/offset: optional per-image affine applied while loading rows: v = (x - off[b]) * scl[b]
+// radial_filter (fast path only, see fft_has_fast_path): multiply the spectrum by filt[nearest ring]
 int fft2_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int n, int batch,
-                 const float *offs, const float *scls);
-int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch);
+                 const float *offs, const float *scls, const float *radial_filter = nullptr);
+// scale and (fast path only) a soft circular real-space mask are applied while the rows are written
+int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch, float scale = 1.f,
+                 float mask_radius = 0.f, float mask_width = 0.f);
+bool fft_has_fast_path(int n);
 // 3-D R2C / C2R of an np^3 volume (in-place complex work buffer of (np/2+1)*np*np)
 int fft3_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int np);
 int fft3_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int np);

@@ -850,7 +850,7 @@ extern "C" int cspb_set_reference(cspb_ctx *ctx, const float *vol, int n, int lo
 
 // FFT a chunk of images held on the device into d_work1 (half spectra), optionally estimating
 // the noise curve.  Returns device pointer of the spectra.
-static int preprocess_chunk(cspb_ctx *ctx, const float *d_img, int count, float2 **spec_out) {
+static int preprocess_chunk(cspb_ctx *ctx, const float *d_img, int count, float2 **spec_out, const float *fused_filter) {
     const cspb_refine_cfg &c = ctx->rcfg;
     const int n = c.box, nh = n / 2 + 1;
     RESERVE(ctx, ctx->d_stats, (size_t)2 * count * sizeof(float));
@@ -860,7 +860,7 @@ static int preprocess_chunk(cspb_ctx *ctx, const float *d_img, int count, float2
     KERNEL_CHECK(ctx);
     RESERVE(ctx, ctx->d_work1, (size_t)count * n * nh * sizeof(float2));
     float2 *spec = ctx->d_work1.as<float2>();
-    int rc = fft2_r2c_dev(ctx, d_img, spec, n, count, offs, scls);
+    int rc = fft2_r2c_dev(ctx, d_img, spec, n, count, offs, scls, fused_filter);
     if (rc) return rc;
     *spec_out = spec;
     return 0;
@@ -955,13 +955,17 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
             d_img = ctx->d_stage.as<float>();
         }
         float2 *spec;
-        int rc = preprocess_chunk(ctx, d_img, cnt, &spec);
+        // whitening filter and soft mask ride on the FFT passes when the box has the fast path and
+        // the noise curve is already known (every chunk but the very first)
+        const bool fast = fft_has_fast_path(n);
+        const bool fused_filt = fast && c.whiten && ctx->have_noise;
+        int rc = preprocess_chunk(ctx, d_img, cnt, &spec, fused_filt ? ctx->d_noise.as<float>() : nullptr);
         if (rc) return rc;
         if (c.whiten && !ctx->have_noise) {
             rc = estimate_noise_from_spectra(ctx, spec, cnt);
             if (rc) return rc;
         }
-        const float *filt = c.whiten ? ctx->d_noise.as<float>() : nullptr;
+        const float *filt = (c.whiten && !fused_filt) ? ctx->d_noise.as<float>() : nullptr;
         const long long tot_c = (long long)cnt * n * nh;
         if (c.apply_mask) {
             if (filt) {
@@ -970,11 +974,17 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
             }
             RESERVE(ctx, ctx->d_work0, (size_t)cnt * n * n * sizeof(float));
             float *real = ctx->d_work0.as<float>();
-            rc = fft2_c2r_dev(ctx, spec, real, n, cnt);
-            if (rc) return rc;
-            mask_kernel<<<grid_for((long long)cnt * n * n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-                real, n, cnt, c.mask_radius / c.pixel_size, 20.f / c.pixel_size, 1.f / ((float)n * (float)n));
-            KERNEL_CHECK(ctx);
+            const float inv_n2 = 1.f / ((float)n * (float)n);
+            if (fast) {
+                rc = fft2_c2r_dev(ctx, spec, real, n, cnt, inv_n2, c.mask_radius / c.pixel_size, 20.f / c.pixel_size);
+                if (rc) return rc;
+            } else {
+                rc = fft2_c2r_dev(ctx, spec, real, n, cnt);
+                if (rc) return rc;
+                mask_kernel<<<grid_for((long long)cnt * n * n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+                    real, n, cnt, c.mask_radius / c.pixel_size, 20.f / c.pixel_size, inv_n2);
+                KERNEL_CHECK(ctx);
+            }
             rc = fft2_r2c_dev(ctx, real, spec, n, cnt, nullptr, nullptr);
             if (rc) return rc;
             filt = nullptr;
