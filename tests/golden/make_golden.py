@@ -13,6 +13,10 @@ What gets pinned:
       left-handed matrices that eulerTwoZYZtoOneZYZ composes (geometry/core.py:174-219)
   spa_euler.npy — spa_euler_angles inputs/outputs (geometry/core.py:250-441), the tilt/particle
       pose composition that CSP uses.
+  shape_spa_{in,out}.cistem, shape_tomo_{in,out}.cistem (+ .json tilt tables) — inputs and outputs of
+      pyp.analysis.scores.shape_phase_residuals (scores.py:300-761), the particle selection between
+      refine3d and reconstruct3d, run with one angular / defocus group (the production default).
+      Pins pyp_b200/select.py.
   csp_euler.npy — csp_euler_angles (geometry/core.py:1081-1217): tilt angle, axis, csp angles and
       3DAVG translation in; projection (psi, theta, phi, sx, sy) and the stored particle
       parameters (-ppsi, -ptheta, -pphi, px, py, pz) out.  Pins pyp_b200/csp_geometry.py.
@@ -47,7 +51,7 @@ def _ensure(name):
 
 
 for _name in ["jsonrpcclient", "jsonrpcclient.requests", "jsonrpcclient.clients.http_client", "matplotlib", "matplotlib.pyplot",
-              "toml", "mrcfile", "seaborn", "pymongo", "colored_traceback", "colorama"]:
+              "toml", "mrcfile", "seaborn", "pymongo", "colored_traceback", "colorama", "skimage", "skimage.color", "trimesh"]:
     _ensure(_name)
 
 import numpy as np  # noqa: E402
@@ -155,6 +159,55 @@ def main():
         fp, nm = geo.csp_euler_angles(tilt, axis, [0.0, 0.0, 0.0], list(mm.ravel()), 0.0, ang)
         csp.append(np.concatenate([[tilt, axis], ang, mm[:3, 3], np.asarray(fp, dtype=float), np.asarray(nm, dtype=float)]))
     np.save(os.path.join(HERE, "csp_euler.npy"), np.array(csp))
+    # ---- score shaping (scores.py:300-761), run in a scratch directory (it writes next to its input)
+    import json
+    import shutil
+    import tempfile
+
+    os.environ.setdefault("PYP_DIR", "/root/reference")
+    from pyp.analysis import scores as S
+
+    def shape_case(tag, tomo, cutoff, kw):
+        n = 600
+        d = np.zeros((n, 32))
+        d[:, 0] = np.arange(1, n + 1)
+        d[:, 1:4] = rng.uniform(0, 360, (n, 3))
+        d[:, 6] = rng.uniform(5000, 40000, n)
+        d[:, 7] = d[:, 6] - 200
+        d[:, 10] = np.sort(rng.integers(0, 3, n))     # film id; rows are grouped by film as in pyp's merged tables
+                                                      # (scores.py:348-361 builds the tilt column film by film)
+        d[:, 11] = 100
+        d[:, 14] = rng.normal(12, 4, n)
+        d[:, 15] = 1.35
+        nt = 5 if tomo else 1
+        d[:, 26] = np.arange(n) // nt                 # PIND
+        d[:, 27] = np.arange(n) % nt                  # TIND
+        angles = [-40.0, -9.0, 0.0, 8.0, 41.0] if tomo else [0.0]
+        tilts = {str(f): {str(t): a for t, a in enumerate(angles)} for f in range(3)}
+        tmp = tempfile.mkdtemp()
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            par = csf.Parameters()
+            par.set_data(data=d)
+            par.to_binary("x_r01_02.cistem")
+            json.dump(tilts, open("x_r01_02.json", "w"))
+            S.shape_phase_residuals("x_r01_02.cistem", 1, 1, cutoff, kw["mindef"], kw["maxdef"], kw["firstframe"], kw["lastframe"],
+                                    kw["mintilt"], kw["maxtilt"], kw["minazh"], kw["maxazh"], kw["minscore"], kw["maxscore"], 1.0,
+                                    False, False, True, False, False, "x_r01_02_used.cistem")
+            shutil.copy("x_r01_02.cistem", os.path.join(HERE, f"shape_{tag}_in.cistem"))
+            shutil.copy("x_r01_02.json", os.path.join(HERE, f"shape_{tag}_in.json"))
+            shutil.copy("x_r01_02_used.cistem", os.path.join(HERE, f"shape_{tag}_out.cistem"))
+        finally:
+            os.chdir(cwd)
+            shutil.rmtree(tmp)
+        with open(os.path.join(HERE, f"shape_{tag}_args.json"), "w") as f:
+            json.dump(dict(kw, cutoff=cutoff), f)
+
+    shape_case("spa", False, 0.8, dict(mindef=0.0, maxdef=30000.0, firstframe=0, lastframe=-1, mintilt=-90.0, maxtilt=90.0,
+                                      minazh=10.0, maxazh=170.0, minscore=0.05, maxscore=0.98))
+    shape_case("tomo", True, 0.7, dict(mindef=0.0, maxdef=100000.0, firstframe=0, lastframe=3, mintilt=-45.0, maxtilt=90.0,
+                                      minazh=0.0, maxazh=180.0, minscore=0.0, maxscore=1.0))
     print("golden fixtures written to", HERE)
 
 
