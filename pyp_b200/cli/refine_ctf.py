@@ -1,0 +1,118 @@
+"""refine_ctf drop-in: same stdin answer list as external/cistem2/refine_ctf
+(src/pyp/refine/frealign/frealign.py:3995-4041), numerics on the GPU.
+
+Per-particle defocus refinement with the refine3d scorer (pose fixed, defocus offset free).  Writes
+`<out>_refined_ctf.star` / `<out>_changes.star` (merged by pyp with merge_star,
+frealign.py:3133-3154).  Beam-tilt estimation (answer 23) is NOT implemented: the beam-tilt columns
+pass through unchanged, the three diagnostic images are written as zeros and the log says so.
+"""
+import sys
+import time
+
+import numpy as np
+
+from ..formats import cistem, mrc, star
+from .prompts import Answers, PromptError, banner, pick_device
+from .refine3d import select_rows
+
+
+def parse(ans: Answers):
+    p = {}
+    p["stack"] = ans.text("input particle images")
+    p["parameters"] = ans.text("input cisTEM parameter file")
+    p["reference"] = ans.text("input reconstruction")
+    p["statistics"] = ans.text("input data statistics")
+    p["use_statistics"] = ans.yesno("use statistics")
+    p["out_star"] = ans.text("output star file")
+    p["out_changes"] = ans.text("output parameter changes")
+    p["phase_difference"] = ans.text("output phase difference image")
+    p["beamtilt_image"] = ans.text("output beam tilt image")
+    p["difference_image"] = ans.text("output difference image")
+    p["first"] = ans.integer("first particle to refine")
+    p["last"] = ans.integer("last particle to refine")
+    p["pixel_size"] = ans.number("pixel size of reconstruction")
+    p["molecular_mass"] = ans.number("molecular mass of particle (kDa)")
+    p["inner_mask_radius"] = ans.number("inner mask radius")
+    p["outer_mask_radius"] = ans.number("outer mask radius")
+    p["low_res_limit"] = ans.number("low resolution limit")
+    p["high_res_limit"] = ans.number("high resolution limit")
+    p["defocus_range"] = ans.number("defocus search range")
+    p["defocus_step"] = ans.number("defocus step")
+    p["padding"] = ans.number("tuning parameter: padding factor")
+    p["refine_defocus"] = ans.yesno("refine defocus")
+    p["beam_tilt"] = ans.yesno("estimate beam tilt")
+    p["normalize"] = ans.yesno("normalize particles")
+    p["invert"] = ans.yesno("invert particle contrast")
+    p["exclude_edges"] = ans.yesno("exclude images with blank edges")
+    p["normalize_rec"] = ans.yesno("normalize input reconstruction")
+    p["threshold_rec"] = ans.yesno("threshold input reconstruction")
+    return p
+
+
+def run(p, out=sys.stdout):
+    from ..engine import Engine
+
+    t0 = time.time()
+    hdr = mrc.read_header(p["stack"])
+    box = hdr["nx"]
+    first, last = p["first"], min(p["last"], hdr["nz"]) if p["last"] > 0 else hdr["nz"]
+    if first < 1 or first > last:
+        raise ValueError(f"particle range {first}..{last} outside the stack (1..{hdr['nz']})")
+    rows_all = cistem.read_parameters(p["parameters"])
+    rows = rows_all[select_rows(rows_all, first, last)]
+    _, vol = mrc.read(p["reference"])
+    if vol.shape != (box, box, box):
+        raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
+    refined, n_evals = rows.copy(), 0
+    if p["refine_defocus"] and rows.size:
+        eng = Engine(pick_device(first, last - first + 1))
+        cfg = Engine.refine_defaults(box, p["pixel_size"])
+        cfg.pad = 2 if p["padding"] >= 1.5 else 1
+        cfg.mask_radius = p["outer_mask_radius"]
+        cfg.low_res_limit, cfg.high_res_limit = p["low_res_limit"], p["high_res_limit"]
+        cfg.defocus_range, cfg.defocus_step = p["defocus_range"], p["defocus_step"]
+        cfg.global_search, cfg.local_refine = 0, 1
+        cfg.refine_psi = cfg.refine_theta = cfg.refine_phi = cfg.refine_x = cfg.refine_y = 0
+        cfg.refine_defocus = 1
+        cfg.normalize, cfg.invert_contrast = int(p["normalize"]), int(p["invert"])
+        eng.refine_configure(cfg)
+        eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+        pos = rows["position_in_stack"].astype(np.int64)
+        _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max()))
+        for s in range(0, rows.size, 16384):
+            eng.load_images(np.ascontiguousarray(data[pos[s:s + 16384] - pos.min()]), append=s > 0)
+        refined, _, n_evals = eng.refine(rows)
+        # keep the search inside +- defocus_range of the input (answer 19)
+        if p["defocus_range"] > 0:
+            d = np.clip(refined["defocus_1"] - rows["defocus_1"], -p["defocus_range"], p["defocus_range"])
+            refined["defocus_1"], refined["defocus_2"] = rows["defocus_1"] + d, rows["defocus_2"] + d
+        eng.close()
+    changes = refined.copy()
+    for k in ("defocus_1", "defocus_2", "score", "logp", "sigma"):
+        changes[k] = refined[k] - rows[k]
+    star.write_star(p["out_star"], refined)
+    star.write_star(p["out_changes"], changes)
+    zero = np.zeros((1, box, box), dtype=np.float32)
+    for k in ("phase_difference", "beamtilt_image", "difference_image"):
+        mrc.write(p[k], zero, p["pixel_size"])
+    out.write(banner("RefineCTF"))
+    out.write(f"\nRefining defocus of particles {first} to {last} ({rows.size} rows), {n_evals} projections scored in {time.time() - t0:.2f} s\n")
+    if rows.size:
+        out.write(f"Mean defocus change {float(changes['defocus_1'].mean()):+.1f} A, mean score change {float(changes['score'].mean()):+.4f}\n")
+    if p["beam_tilt"]:
+        out.write("Beam tilt estimation is not implemented in cspb200: beam tilt columns unchanged, diagnostic images are zero\n")
+    out.write("\nRefineCTF: Normal termination\n")
+    return refined
+
+
+def main(argv=None):
+    try:
+        run(parse(Answers(program="refine_ctf")))
+    except (PromptError, ValueError, OSError, RuntimeError, ImportError) as e:
+        sys.stderr.write(f"refine_ctf: caught error: {e}\n")
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -17,6 +17,9 @@ What gets pinned:
       pyp.analysis.scores.shape_phase_residuals (scores.py:300-761), the particle selection between
       refine3d and reconstruct3d, run with one angular / defocus group (the production default).
       Pins pyp_b200/select.py.
+  rows_{a,b}.star, rows_star_merged_by_reference.npy — `.star` tables written by pyp_b200/formats/star.py and
+      merged by the reference's merge_star (cistem_star_file.py:1398-1441), i.e. what pyp does with the
+      outputs of refine_ctf (frealign.py:3133-3154).
   csp_euler.npy — csp_euler_angles (geometry/core.py:1081-1217): tilt angle, axis, csp angles and
       3DAVG translation in; projection (psi, theta, phi, sx, sy) and the stored particle
       parameters (-ppsi, -ptheta, -pphi, px, py, pz) out.  Pins pyp_b200/csp_geometry.py.
@@ -208,6 +211,15 @@ def main():
                                       minazh=10.0, maxazh=170.0, minscore=0.05, maxscore=0.98))
     shape_case("tomo", True, 0.7, dict(mindef=0.0, maxdef=100000.0, firstframe=0, lastframe=3, mintilt=-45.0, maxtilt=90.0,
                                       minazh=0.0, maxazh=180.0, minscore=0.0, maxscore=1.0))
+    # ---- star tables: our writer read back by the reference's merge_star / read_star
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from pyp_b200.formats import cistem as our_cistem, star as our_star
+
+    rows = our_cistem.read_parameters(os.path.join(HERE, "params_5x32.cistem"))
+    our_star.write_star(os.path.join(HERE, "rows_a.star"), rows[:3])
+    our_star.write_star(os.path.join(HERE, "rows_b.star"), rows[3:])
+    merged = csf.merge_star([os.path.join(HERE, "rows_a.star"), os.path.join(HERE, "rows_b.star")])
+    np.save(os.path.join(HERE, "rows_star_merged_by_reference.npy"), np.asarray(merged, dtype=np.float64))
     print("golden fixtures written to", HERE)
 
 

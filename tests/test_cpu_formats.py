@@ -152,3 +152,16 @@ def test_dump_roundtrip(tmp_path):
     p.write_bytes(b"x" * 100)
     with pytest.raises(ValueError):
         dump.read(str(p))
+
+
+def test_star_tables_round_trip_and_reference_merge():
+    """rows_{a,b}.star were written by formats/star.py; rows_star_merged_by_reference.npy is what the
+    reference's merge_star (cistem_star_file.py:1398-1441) made of them."""
+    from pyp_b200.formats import star
+
+    rows = cistem.read_parameters(os.path.join(G, "params_5x32.cistem"))
+    merged_ref = np.load(os.path.join(G, "rows_star_merged_by_reference.npy"))
+    for k, name in enumerate(rows.dtype.names):
+        assert np.array_equal(merged_ref[:, k].astype(rows.dtype[name]), rows[name]), name
+    back = np.concatenate([star.read_star(os.path.join(G, "rows_a.star")), star.read_star(os.path.join(G, "rows_b.star"))])
+    assert back.tobytes() == rows.tobytes()

@@ -137,3 +137,16 @@ def test_gloo_world_size_2(tmp_path):
                         "--master-port", "29571", str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_refine_ctf_prompt_order():
+    """28 answers in the order of frealign.py:3998-4038."""
+    from pyp_b200.cli import refine_ctf
+    from pyp_b200.cli.prompts import Answers, PromptError
+
+    a = ["s.mrc", "p.cistem", "r.mrc", "stat.txt", "no", "o.star", "c.star", "pd.mrc", "bt.mrc", "di.mrc", 1, 100, 1.35, 300.0, 0, 120.0,
+         100.0, 6.0, 2000.0, "50.0", 1, "yes", "no", "yes", "no", "no", "no", "no"]
+    p = refine_ctf.parse(Answers("\n".join(str(x) for x in a), "refine_ctf"))
+    assert p["out_star"] == "o.star" and p["last"] == 100 and p["defocus_range"] == 2000.0 and p["refine_defocus"] and not p["beam_tilt"]
+    with pytest.raises(PromptError):
+        refine_ctf.parse(Answers("\n".join(str(x) for x in a[:20]), "refine_ctf"))

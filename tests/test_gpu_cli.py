@@ -164,3 +164,36 @@ def test_csp_cli_extract_and_refine(tmp_path):
     # an unknown mode fails loudly with pyp's failure token
     assert csp(par, ext, 9, 0, 0, 1, "frealign/ts.mrc", "frealign/ts_stack.mrc", log="bad.log") != 0
     assert "PYP (cspswarm) failed" in open(f"{d}/bad.log").read()
+
+
+def test_refine_ctf_cli_recovers_defocus(tmp_path):
+    """bin/refine_ctf with the answer list of frealign.py:3995-4041: a stack whose table carries a
+    defocus error gets its DEFOCUS_1/2 moved back towards the truth; outputs are the star files pyp
+    merges (frealign.py:3133-3154)."""
+    from pyp_b200.formats import star
+
+    n, px, n_part = 64, 1.35, 24
+    ph, vol, rows, stack = small_case(n=n, n_part=n_part, snr=1.0)
+    start = rows.copy()
+    start["defocus_1"] += 400.0
+    start["defocus_2"] += 400.0
+    d = str(tmp_path)
+    mrc.write(f"{d}/ds_stack.mrc", stack, px)
+    mrc.write(f"{d}/ds_r01.mrc", vol, px)
+    cistem.write_parameters(f"{d}/ds_r01.cistem", start)
+    open(f"{d}/statistics_r01.txt", "w").close()
+    a = ["ds_stack.mrc", "ds_r01.cistem", "ds_r01.mrc", "statistics_r01.txt", "no", "ds_r01_0000001_0000024_refined_ctf.star",
+         "ds_r01_0000001_0000024_changes.star", "ds_r01_phase_difference.mrc", "ds_r01_beamtilt_image.mrc", "ds_r01_difference_image.mrc",
+         1, n_part, px, 100.0, 0, 0.38 * n * px, 60.0, 4 * px, 1000.0, "50.0", 1, "yes", "yes", "yes", "no", "no", "no", "no"]
+    assert sh("refine_ctf", a, d, "ctf.log") == 0
+    log = open(f"{d}/ctf.log").read()
+    assert "RefineCTF: Normal termination" in log and "not implemented" in log
+    got = star.read_star(f"{d}/ds_r01_0000001_0000024_refined_ctf.star")
+    assert got.size == n_part and list(got["position_in_stack"]) == list(range(1, n_part + 1))
+    err0 = np.abs(start["defocus_1"] - rows["defocus_1"]).mean()
+    err1 = np.abs(got["defocus_1"] - rows["defocus_1"]).mean()
+    assert err1 < 0.6 * err0
+    assert np.array_equal(got["psi"], start["psi"]) and np.allclose(got["defocus_1"] - got["defocus_2"], start["defocus_1"] - start["defocus_2"], atol=1e-2)
+    chg = star.read_star(f"{d}/ds_r01_0000001_0000024_changes.star")
+    assert np.allclose(chg["defocus_1"], got["defocus_1"] - start["defocus_1"], atol=1e-2)
+    assert os.path.exists(f"{d}/ds_r01_beamtilt_image.mrc")
