@@ -327,12 +327,12 @@ def run_b200_arm(a):
         host_stack.copy_(stack)
         torch.cuda.synchronize()
         hs = host_stack.numpy()
+        host_maps = [torch.empty((n, n, n), dtype=torch.float32, pin_memory=True).numpy() for _ in range(3)] if rank == 0 else None
 
         def host_step():
-            eng.load_images(hs)
-            out, _, n_ev = eng.refine(rows_host)
+            # the public host-buffer call: one upload per projection, copies overlapped with compute
             eng.recon_begin(ccfg)
-            eng.recon_insert(hs, out)
+            out, n_ev = eng.refine_reconstruct(hs, rows_host)
             if world > 1:
                 eng.sync()
                 for h in (0, 1):
@@ -340,7 +340,7 @@ def run_b200_arm(a):
                     dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
                 torch.cuda.synchronize()
             if rank == 0:
-                eng.recon_finalize(molecular_mass_kda=440.0, want_halves=True)
+                eng.recon_finalize(molecular_mass_kda=440.0, want_halves=True, out=host_maps)
             return n_ev
 
         host_step()
@@ -356,7 +356,7 @@ def run_b200_arm(a):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = 2 * P * n * n * 4 + 2 * P * 128          # stack is read by refine3d and again by reconstruct3d
+        h2d = P * n * n * 4 + P * 128                  # every projection is uploaded once (cspb_refine_reconstruct)
         d2h = P * 128 + (3 * n * n * n * 4 if rank == 0 else 0)
         e2e = {"value": world * ev2 / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": k2, "ms_per_step": 1e3 * dt / k2}

@@ -291,6 +291,17 @@ int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, float outer_rad
                         int loc);
 int cspb_recon_end(cspb_ctx *ctx);
 
+/* ------------------------------------------------------------------ streamed host pipeline
+ * refine3d and / or reconstruct3d over a HOST stack (pinned memory for full overlap) with ONE upload
+ * per projection: chunk k+1 is copied on a second stream while chunk k is preprocessed, refined
+ * (rows updated in place, as cspb_refine_run) and inserted (as cspb_recon_insert, with the refined
+ * rows) on the context stream.  Chunks are those of cspb_refine_load_images, so the results are
+ * identical to load_images + refine_run + recon_insert.  Needs cspb_refine_configure +
+ * cspb_set_reference for CSPB_DO_REFINE and cspb_recon_begin for CSPB_DO_INSERT. */
+enum { CSPB_DO_REFINE = 1, CSPB_DO_INSERT = 2 };
+int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images,
+                            int flags, int64_t *n_evals_out);
+
 /* ------------------------------------------------------------------ building blocks
  * Exposed for parity tests against the oracle and cuFFT. */
 /* Batched 2-D real-to-complex FFT, unnormalised, output n*(n/2+1) complex per image. */

@@ -117,6 +117,7 @@ _SIGNATURES = {
     "cspb_csp_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, C.POINTER(CspCfg), _i, _i, C.POINTER(_i64)]),
     "cspb_csp_compose": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
     "cspb_csp_extract": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i]),
+    "cspb_refine_reconstruct": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
     "cspb_recon_cfg_default": (_i, [C.POINTER(ReconCfg), _i, _f]),
     "cspb_recon_begin": (_i, [_vp, C.POINTER(ReconCfg)]),
     "cspb_recon_insert": (_i, [_vp, _vp, _vp, _i, _i]),

@@ -218,3 +218,13 @@ int fft3_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int np);
 
 // ---------------------------------------------------------------- helpers
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// images per processing chunk (staging + half spectra within ~4.5 GB, at most 8192, even chunks).
+// Large chunks matter: a scorer launch over 2048 particles fills less than half of the 148 SMs.
+static inline int chunk_images(int n, int n_images) {
+    const size_t per_img = (size_t)n * n * 4 + (size_t)n * (n / 2 + 1) * 8;
+    long long chunk = (long long)(((size_t)9 << 29) / per_img);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 8192) chunk = 8192;
+    if (n_images > chunk) chunk = ceil_div(n_images, ceil_div(n_images, chunk));
+    return (int)chunk;
+}

@@ -1,0 +1,73 @@
+// pipeline.cu — host-stack pipeline: one upload per projection, copies overlapped with compute.
+//
+// pyp runs refine3d and reconstruct3d as separate processes that each read the particle stack
+// (src/pyp/refine/frealign/frealign.py:3918-3994, 1780-1824).  In process, the two stages can
+// share one host->device copy of every chunk: while chunk k is preprocessed, refined and inserted on
+// the compute stream, chunk k+1 is copied on a second stream into the other staging buffer.
+#include "internal.cuh"
+
+namespace {
+struct StreamPipe {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    DevBuf stage[2], rows;
+    ~StreamPipe() {
+        for (int k = 0; k < 2; ++k) {
+            if (ready[k]) cudaEventDestroy(ready[k]);
+            if (freed[k]) cudaEventDestroy(freed[k]);
+        }
+        if (copy) cudaStreamDestroy(copy);
+    }
+};
+}  // namespace
+
+extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images, int flags,
+                                       int64_t *n_evals_out) {
+    if (!ctx || !images_host || !rows_host || n_images < 0) return CSPB_E_ARG;
+    const bool do_refine = flags & CSPB_DO_REFINE, do_insert = flags & CSPB_DO_INSERT;
+    if (!do_refine && !do_insert) return cspb_fail(ctx, CSPB_E_ARG, "nothing to do (flags = %d)", flags);
+    if (do_refine && (!ctx->refine_ready || !ctx->ref.ready)) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (do_insert && !ctx->recon_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_recon_begin first");
+    const int n = do_refine ? ctx->rcfg.box : ctx->ccfg.box;
+    if (do_refine && do_insert && ctx->ccfg.box != ctx->rcfg.box) return cspb_fail(ctx, CSPB_E_ARG, "refine and reconstruct boxes differ");
+    if (n_evals_out) *n_evals_out = 0;
+    if (n_images == 0) return 0;
+    // same chunking as cspb_refine_load_images / cspb_recon_insert, so the streamed and the staged
+    // APIs see identical chunks (the whitening curve is estimated on the first one)
+    const int chunk = chunk_images(n, n_images);
+    StreamPipe P;
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CU_TRY(ctx, cudaEventCreateWithFlags(&P.ready[k], cudaEventDisableTiming));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&P.freed[k], cudaEventDisableTiming));
+        RESERVE(ctx, P.stage[k], (size_t)chunk * n * n * sizeof(float));
+    }
+    RESERVE(ctx, P.rows, (size_t)n_images * sizeof(cspb_row));
+    CU_TRY(ctx, cudaMemcpyAsync(P.rows.p, rows_host, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t evals = 0;
+    int rc = 0, idx = 0;
+    for (int s = 0; s < n_images && !rc; s += chunk, ++idx) {
+        const int b = idx & 1;
+        const int cnt = n_images - s < chunk ? n_images - s : chunk;
+        if (idx >= 2) CU_TRY(ctx, cudaStreamWaitEvent(P.copy, P.freed[b], 0));
+        CU_TRY(ctx, cudaMemcpyAsync(P.stage[b].p, images_host + (size_t)s * n * n, (size_t)cnt * n * n * sizeof(float),
+                                    cudaMemcpyHostToDevice, P.copy));
+        CU_TRY(ctx, cudaEventRecord(P.ready[b], P.copy));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, P.ready[b], 0));
+        cspb_row *d_rows = P.rows.as<cspb_row>() + s;
+        if (do_refine) {
+            rc = cspb_refine_load_images(ctx, P.stage[b].as<float>(), cnt, CSPB_DEVICE, 0);
+            int64_t ev = 0;
+            if (!rc) rc = cspb_refine_run_device(ctx, d_rows, cnt, &ev);
+            evals += ev;
+        }
+        if (!rc && do_insert) rc = cspb_recon_insert(ctx, P.stage[b].as<float>(), d_rows, cnt, CSPB_DEVICE);
+        if (!rc) CU_TRY(ctx, cudaEventRecord(P.freed[b], ctx->stream));
+    }
+    if (!rc)
+        CU_TRY(ctx, cudaMemcpyAsync(rows_host, P.rows.p, (size_t)n_images * sizeof(cspb_row), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaStreamSynchronize(P.copy);
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_evals_out) *n_evals_out = evals;
+    return rc;
+}

@@ -400,11 +400,7 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
     if (!ctx->recon_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_recon_begin first");
     const cspb_recon_cfg &c = ctx->ccfg;
     const int n = c.box, nh = n / 2 + 1, np = ctx->rnp, xh = np / 2 + 1;
-    const size_t per_img = (size_t)n * n * 4 + (size_t)n * nh * 8;
-    int chunk = (int)(((size_t)1 << 30) / per_img);
-    if (chunk < 1) chunk = 1;
-    if (chunk > 8192) chunk = 8192;
-    if (n_images > chunk) chunk = ceil_div(n_images, ceil_div(n_images, chunk));  // even chunks
+    const int chunk = chunk_images(n, n_images);
     if (ctx->n_lit > INSERT_MAX_SYM) return cspb_fail(ctx, CSPB_E_ARG, "more than %d symmetry operators", INSERT_MAX_SYM);
     const bool deferred = ctx->n_lat > 1;
     for (int s = 0; s < n_images; s += chunk) {

@@ -939,12 +939,7 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         nb.bytes = 0;
         ctx->img_capacity = cap;
     }
-    // chunk so that the spectra + staging stay bounded (~1 GB)
-    const size_t per_img = (size_t)n * n * 4 + (size_t)n * nh * 8;
-    int chunk = (int)((size_t)1 << 30) / (int)per_img;
-    if (chunk < 1) chunk = 1;
-    if (chunk > 8192) chunk = 8192;
-    if (n_images > chunk) chunk = ceil_div(n_images, ceil_div(n_images, chunk));  // even chunks
+    const int chunk = chunk_images(n, n_images);
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;

@@ -191,6 +191,20 @@ class Engine:
         self._ck(self._l.cspb_refine_run_device(self._h, C.c_void_p(int(rows_dev_ptr)), int(n), C.byref(ne)))
         return int(ne.value)
 
+    # ------------------------------------------------------------------ streamed host pipeline
+    DO_REFINE, DO_INSERT = 1, 2
+
+    def refine_reconstruct(self, images, rows, refine=True, insert=True):
+        """refine3d and/or reconstruct3d insertion over a host stack with one upload per projection,
+        copies overlapped with compute (pin the stack for full overlap).  Returns (rows, n_evals)."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+        assert images.shape[0] == rows.size
+        ne = C.c_int64(0)
+        flags = (self.DO_REFINE if refine else 0) | (self.DO_INSERT if insert else 0)
+        self._ck(self._l.cspb_refine_reconstruct(self._h, ptr(images), ptr(rows), rows.size, flags, C.byref(ne)))
+        return rows, int(ne.value)
+
     # ------------------------------------------------------------------ csp (external/CSP/csp)
     @staticmethod
     def csp_defaults(mode=5):
@@ -280,12 +294,19 @@ class Engine:
         assert dump.size == nf, "dump size does not match the accumulator"
         self._ck(self._l.cspb_recon_add_dump(self._h, int(half), ptr(dump), HOST))
 
-    def recon_finalize(self, molecular_mass_kda=0.0, outer_radius=0.0, want_halves=True):
+    def recon_finalize(self, molecular_mass_kda=0.0, outer_radius=0.0, want_halves=True, out=None):
+        """merge3d finalise into host arrays.  `out` = optional (map, half1, half2) float32 arrays of
+        shape (n, n, n) to fill (e.g. pinned buffers that are reused between calls)."""
         n = self.ccfg.box
         ns = n // 2 + 1
-        vol = np.zeros((n, n, n), dtype=np.float32)
-        h1 = np.zeros_like(vol) if want_halves else None
-        h2 = np.zeros_like(vol) if want_halves else None
+        if out is not None:
+            vol, h1, h2 = out
+            for a in (vol, h1, h2):
+                assert a is None or (a.dtype == np.float32 and a.shape == (n, n, n) and a.flags["C_CONTIGUOUS"])
+        else:
+            vol = np.zeros((n, n, n), dtype=np.float32)
+            h1 = np.zeros_like(vol) if want_halves else None
+            h2 = np.zeros_like(vol) if want_halves else None
         stats = np.zeros((ns, 7), dtype=np.float32)
         self._ck(self._l.cspb_recon_finalize(self._h, float(molecular_mass_kda), float(outer_radius), ptr(h1), ptr(h2), ptr(vol), ptr(stats), ns, HOST))
         return vol, h1, h2, stats

@@ -288,3 +288,36 @@ def test_reconstruction_fsc(engine, oracle):
     assert np.abs(got_stats[1:, 3] - want_stats[1:, 3]).max() < 1e-3  # FSC column
     f_truth = oracle.fsc(got_map, vol)
     assert f_truth[1:6].min() > 0.9
+
+
+def test_streamed_pipeline_equals_staged_calls(engine, oracle):
+    """cspb_refine_reconstruct (one upload per projection, copy/compute overlap) must give exactly
+    the rows of load_images + refine and the accumulators of recon_insert."""
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=40)
+    start = __import__("pyp_b200").synth.perturb_rows(rows, 2.0, 1.0)
+    cfg = refine_cfg(n, px)
+    rc = engine.recon_defaults(n, px)
+    engine.set_symmetry("C1")
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    engine.load_images(stack)
+    want_rows, _, n_ev = engine.refine(start)
+    engine.recon_begin(rc)
+    engine.recon_insert(stack, want_rows)
+    want = [engine.recon_get_dump(h) for h in (0, 1)]
+    engine.refine_configure(cfg)      # fresh noise curve, as a new process would have
+    engine.set_reference(vol)
+    engine.recon_begin(rc)
+    got_rows, n_ev2 = engine.refine_reconstruct(stack, start)
+    assert n_ev2 == n_ev and got_rows.tobytes() == want_rows.tobytes()
+    for h in (0, 1):
+        got = engine.recon_get_dump(h)
+        assert np.abs(got - want[h]).max() <= 1e-5 * np.abs(want[h]).max()
+    # stage flags: refine only leaves the accumulators alone, insert only leaves the rows alone
+    engine.recon_begin(rc)
+    r2, _ = engine.refine_reconstruct(stack, start, insert=False)
+    assert r2.tobytes() == want_rows.tobytes() and np.abs(engine.recon_get_dump(0)).max() == 0
+    r3, ne3 = engine.refine_reconstruct(stack, want_rows, refine=False)
+    assert ne3 == 0 and r3.tobytes() == want_rows.tobytes()
+    assert np.abs(engine.recon_get_dump(0) - want[0]).max() <= 1e-5 * np.abs(want[0]).max()
