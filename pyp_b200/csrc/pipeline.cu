@@ -4,6 +4,9 @@
 // (src/pyp/refine/frealign/frealign.py:3918-3994, 1780-1824).  In process, the two stages can
 // share one host->device copy of every chunk: while chunk k is preprocessed, refined and inserted on
 // the compute stream, chunk k+1 is copied on a second stream into the other staging buffer.
+#include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 #include "internal.cuh"
 
 namespace {
@@ -36,6 +39,9 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     // APIs see identical chunks (the whitening curve is estimated on the first one)
     const int chunk = chunk_images(n, n_images);
     StreamPipe P;
+    const bool dbg = getenv("CSPB_PIPE_DEBUG") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     CU_TRY(ctx, cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
         CU_TRY(ctx, cudaEventCreateWithFlags(&P.ready[k], cudaEventDisableTiming));
@@ -43,6 +49,7 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
         RESERVE(ctx, P.stage[k], (size_t)chunk * n * n * sizeof(float));
     }
     RESERVE(ctx, P.rows, (size_t)n_images * sizeof(cspb_row));
+    if (dbg) fprintf(stderr, "pipe: buffers ready at %.1f ms\n", ms_since());
     CU_TRY(ctx, cudaMemcpyAsync(P.rows.p, rows_host, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
     int64_t evals = 0;
     int rc = 0, idx = 0;
@@ -63,11 +70,17 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
         }
         if (!rc && do_insert) rc = cspb_recon_insert(ctx, P.stage[b].as<float>(), d_rows, cnt, CSPB_DEVICE);
         if (!rc) CU_TRY(ctx, cudaEventRecord(P.freed[b], ctx->stream));
+        if (dbg) fprintf(stderr, "pipe: chunk %d (%d images) enqueued at %.1f ms\n", idx, cnt, ms_since());
+    }
+    if (dbg) {
+        cudaStreamSynchronize(P.copy);
+        fprintf(stderr, "pipe: copies done at %.1f ms\n", ms_since());
     }
     if (!rc)
         CU_TRY(ctx, cudaMemcpyAsync(rows_host, P.rows.p, (size_t)n_images * sizeof(cspb_row), cudaMemcpyDeviceToHost, ctx->stream));
     cudaStreamSynchronize(P.copy);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dbg) fprintf(stderr, "pipe: all done at %.1f ms\n", ms_since());
     if (n_evals_out) *n_evals_out = evals;
     return rc;
 }
