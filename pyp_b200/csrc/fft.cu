@@ -147,21 +147,23 @@ __global__ void fft_rows_c2r_kernel(const float2 *__restrict__ in, float *__rest
 
 // ================================================================ fast path: n = R1 * R2
 // strided complex lines, tile of TL = 16 adjacent lines per CTA (lane = line: 128-byte segments)
+// threads per line = max(R1, R2) (R1 <= R2), TL lines per CTA, TL * R2 threads
+template <int R2> struct FastTile { static constexpr int TL = R2 <= 16 ? 16 : 256 / R2; };
 template <int R1, int R2, int DIR>
 __global__ void __launch_bounds__(256) fft_lines_fast_kernel(float2 *__restrict__ data, long long estride, int ninner,
                                                              long long ostride, int ntiles, const float2 *__restrict__ tw_g,
                                                              float scale, int sign_mode, int inner_w,
                                                              const float *__restrict__ filt, int filt_w) {
-    constexpr int N = R1 * R2, TL = 16, P = N + (N >> 4) + 1;
+    constexpr int N = R1 * R2, TL = FastTile<R2>::TL, P = N + (N >> 4) + 1, NT = TL * (R2 < 16 ? 16 : R2);
     __shared__ float2 S[TL * P];
     __shared__ float2 tw[N];
     const int tid = threadIdx.x;
-    const int l = tid & (TL - 1), t = tid >> 4;  // R2 threads per line in stage 1
+    const int l = tid % TL, t = tid / TL;  // R2 threads per line in stage 1
     const int outer = blockIdx.x / ntiles;
     const int t0 = (blockIdx.x - outer * ntiles) * TL;
     const bool live = t0 + l < ninner;
     float2 *base = data + (long long)outer * ostride + t0 + l;
-    for (int i = tid; i < N; i += 256) tw[i] = tw_g[i];
+    for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
     float2 v[R1 > R2 ? R1 : R2];
     if (t < R2) {
 #pragma unroll
@@ -196,14 +198,14 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_fast_kernel(const float *__r
                                                                 long long n_rows, const float2 *__restrict__ tw_g,
                                                                 int rows_per_image, const float *__restrict__ offs,
                                                                 const float *__restrict__ scls) {
-    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1;
+    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1, NT = PR * R2;
     __shared__ float2 S[PR * P];
     __shared__ float2 tw[N];
     const int tid = threadIdx.x;
     const int t = tid % R2, p = tid / R2;
     const long long pair = (long long)blockIdx.x * PR + p;
     const bool live = pair < n_rows / 2;
-    for (int i = tid; i < N; i += 256) tw[i] = tw_g[i];
+    for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
     float2 v[R1 > R2 ? R1 : R2];
     {
         const float *ra = in + pair * 2 * N, *rb = ra + N;
@@ -228,12 +230,12 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_fast_kernel(const float *__r
         for (int k2 = 0; k2 < R2; ++k2) S[p * P + fftsm::skew(t + R1 * k2)] = v[k2];
     }
     __syncthreads();
-    for (int idx = tid; idx < PR * NH; idx += 256) {
+    for (int idx = tid; idx < PR * NH; idx += NT) {
         const int pp = idx / NH, k = idx - pp * NH;
         const long long pr = (long long)blockIdx.x * PR + pp;
         if (pr >= n_rows / 2) break;
         const float2 za = S[pp * P + fftsm::skew(k)];
-        float2 zb = S[pp * P + fftsm::skew((N - k) & (N - 1))];
+        float2 zb = S[pp * P + fftsm::skew(k ? N - k : 0)];
         zb.y = -zb.y;
         const float2 fa = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y + zb.y));
         const float2 df = make_float2(za.x - zb.x, za.y - zb.y);
@@ -249,7 +251,7 @@ template <int R1, int R2>
 __global__ void __launch_bounds__(256) fft_rows_c2r_fast_kernel(const float2 *__restrict__ in, float *__restrict__ out,
                                                                 long long n_rows, const float2 *__restrict__ tw_g, float scale,
                                                                 float mask_radius, float mask_width) {
-    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1;
+    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1, NT = PR * R2;
     __shared__ float2 S[PR * P];
     float2 *Z = S;  // the packed spectrum is staged in the same buffer (extra barrier below)
     __shared__ float2 tw[N];
@@ -257,9 +259,9 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_fast_kernel(const float2 *__
     const int t = tid % R2, p = tid / R2;
     const long long pair = (long long)blockIdx.x * PR + p;
     const bool live = pair < n_rows / 2;
-    for (int i = tid; i < N; i += 256) tw[i] = tw_g[i];
+    for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
     // Z[k] = fa + i fb ; Z[n-k] = conj(fa) + i conj(fb)
-    for (int idx = tid; idx < PR * NH; idx += 256) {
+    for (int idx = tid; idx < PR * NH; idx += NT) {
         const int pp = idx / NH, k = idx - pp * NH;
         const long long pr = (long long)blockIdx.x * PR + pp;
         if (pr >= n_rows / 2) break;
@@ -317,26 +319,30 @@ int launch_lines(cspb_ctx *ctx, float2 *data, int n, long long estride, int ninn
     const float2 *tw;
     int rc = fft_get_twiddles(ctx, n, &tw);
     if (rc) return rc;
-    if (n == 256 || n == 128 || n == 64) {
-        const int ntiles = ceil_div(ninner, 16);
+    if (fft_has_fast_path(n)) {
+        const int TL = n == 512 ? 8 : (n == 384 ? 10 : 16);
+        const int nthreads = n == 384 ? 240 : 256;
+        const int ntiles = ceil_div(ninner, TL);
         const unsigned grid = (unsigned)((long long)ntiles * n_outer);
 #define CSPB_LINES_FAST(R1_, R2_)                                                                                       \
     do {                                                                                                                \
         if (dir < 0)                                                                                                    \
-            fft_lines_fast_kernel<R1_, R2_, -1><<<grid, 256, 0, ctx->stream>>>(data, estride, ninner, ostride, ntiles, tw, scale, \
+            fft_lines_fast_kernel<R1_, R2_, -1><<<grid, nthreads, 0, ctx->stream>>>(data, estride, ninner, ostride, ntiles, tw, scale, \
                                                                                sign_mode, inner_w, filt, filt_w);       \
         else                                                                                                            \
-            fft_lines_fast_kernel<R1_, R2_, +1><<<grid, 256, 0, ctx->stream>>>(data, estride, ninner, ostride, ntiles, tw, scale, \
+            fft_lines_fast_kernel<R1_, R2_, +1><<<grid, nthreads, 0, ctx->stream>>>(data, estride, ninner, ostride, ntiles, tw, scale, \
                                                                                sign_mode, inner_w, filt, filt_w);       \
     } while (0)
-        if (n == 256) CSPB_LINES_FAST(16, 16);
+        if (n == 512) CSPB_LINES_FAST(16, 32);
+        else if (n == 384) CSPB_LINES_FAST(16, 24);
+        else if (n == 256) CSPB_LINES_FAST(16, 16);
         else if (n == 128) CSPB_LINES_FAST(8, 16);
         else CSPB_LINES_FAST(8, 8);
 #undef CSPB_LINES_FAST
         KERNEL_CHECK(ctx);
         return 0;
     }
-    if (filt) return cspb_fail(ctx, CSPB_E_ARG, "fused radial filter needs the fast FFT path (n = 64/128/256)");
+    if (filt) return cspb_fail(ctx, CSPB_E_ARG, "fused radial filter needs the fast FFT path (n = 64/128/256/384/512)");
     const int T = pick_tile(n);
     const size_t smem = ((size_t)n + (size_t)2 * T * line_pitch(n)) * sizeof(float2);
     const int ntiles = ceil_div(ninner, T);
@@ -362,8 +368,10 @@ int launch_rows_r2c(cspb_ctx *ctx, const float *in, float2 *out, int n, long lon
     int rc = fft_get_twiddles(ctx, n, &tw);
     if (rc) return rc;
     const long long n_pairs = n_rows / 2;
-    if (n == 256 || n == 128 || n == 64) {
-        if (n == 256) fft_rows_r2c_fast_kernel<16, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
+    if (fft_has_fast_path(n)) {
+        if (n == 512) fft_rows_r2c_fast_kernel<16, 32><<<ceil_div(n_pairs, 8), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
+        else if (n == 384) fft_rows_r2c_fast_kernel<16, 24><<<ceil_div(n_pairs, 10), 240, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
+        else if (n == 256) fft_rows_r2c_fast_kernel<16, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
         else if (n == 128) fft_rows_r2c_fast_kernel<8, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
         else fft_rows_r2c_fast_kernel<8, 8><<<ceil_div(n_pairs, 32), 256, 0, ctx->stream>>>(in, out, n_rows, tw, rows_per_image, offs, scls);
         KERNEL_CHECK(ctx);
@@ -386,14 +394,16 @@ int launch_rows_c2r(cspb_ctx *ctx, const float2 *in, float *out, int n, long lon
     int rc = fft_get_twiddles(ctx, n, &tw);
     if (rc) return rc;
     const long long n_pairs = n_rows / 2;
-    if (n == 256 || n == 128 || n == 64) {
-        if (n == 256) fft_rows_c2r_fast_kernel<16, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
+    if (fft_has_fast_path(n)) {
+        if (n == 512) fft_rows_c2r_fast_kernel<16, 32><<<ceil_div(n_pairs, 8), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
+        else if (n == 384) fft_rows_c2r_fast_kernel<16, 24><<<ceil_div(n_pairs, 10), 240, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
+        else if (n == 256) fft_rows_c2r_fast_kernel<16, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
         else if (n == 128) fft_rows_c2r_fast_kernel<8, 16><<<ceil_div(n_pairs, 16), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
         else fft_rows_c2r_fast_kernel<8, 8><<<ceil_div(n_pairs, 32), 256, 0, ctx->stream>>>(in, out, n_rows, tw, scale, mask_radius, mask_width);
         KERNEL_CHECK(ctx);
         return 0;
     }
-    if (mask_width > 0.f) return cspb_fail(ctx, CSPB_E_ARG, "fused mask needs the fast FFT path (n = 64/128/256)");
+    if (mask_width > 0.f) return cspb_fail(ctx, CSPB_E_ARG, "fused mask needs the fast FFT path (n = 64/128/256/384/512)");
     const int PR = pick_tile(n);
     const size_t smem = ((size_t)n + (size_t)2 * PR * line_pitch(n)) * sizeof(float2);
     if ((rc = set_smem(ctx, fft_rows_c2r_kernel, smem))) return rc;
@@ -428,7 +438,7 @@ int fft_get_twiddles(cspb_ctx *ctx, int n, const float2 **tw_out) {
     return 0;
 }
 
-bool fft_has_fast_path(int n) { return n == 64 || n == 128 || n == 256; }
+bool fft_has_fast_path(int n) { return n == 64 || n == 128 || n == 256 || n == 384 || n == 512; }
 
 int fft2_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int n, int batch, const float *offs,
                  const float *scls, const float *radial_filter) {

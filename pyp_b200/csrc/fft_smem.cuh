@@ -97,6 +97,59 @@ template <int DIR> struct Butterfly<16, DIR> {
     }
 };
 
+// cos / sin of 2 pi k / 96: compile-time twiddles for the radix-24 (stride 4) and radix-32 (stride 3) butterflies
+__device__ constexpr float W96C[96] = {1.000000000e+00f, 9.978589232e-01f, 9.914448614e-01f, 9.807852804e-01f, 9.659258263e-01f, 9.469301295e-01f, 9.238795325e-01f, 8.968727415e-01f, 8.660254038e-01f, 8.314696123e-01f, 7.933533403e-01f, 7.518398075e-01f, 7.071067812e-01f, 6.593458151e-01f, 6.087614290e-01f, 5.555702330e-01f, 5.000000000e-01f, 4.422886902e-01f, 3.826834324e-01f, 3.214394653e-01f, 2.588190451e-01f, 1.950903220e-01f, 1.305261922e-01f, 6.540312923e-02f, 6.123233996e-17f, -6.540312923e-02f, -1.305261922e-01f, -1.950903220e-01f, -2.588190451e-01f, -3.214394653e-01f, -3.826834324e-01f, -4.422886902e-01f, -5.000000000e-01f, -5.555702330e-01f, -6.087614290e-01f, -6.593458151e-01f, -7.071067812e-01f, -7.518398075e-01f, -7.933533403e-01f, -8.314696123e-01f, -8.660254038e-01f, -8.968727415e-01f, -9.238795325e-01f, -9.469301295e-01f, -9.659258263e-01f, -9.807852804e-01f, -9.914448614e-01f, -9.978589232e-01f, -1.000000000e+00f, -9.978589232e-01f, -9.914448614e-01f, -9.807852804e-01f, -9.659258263e-01f, -9.469301295e-01f, -9.238795325e-01f, -8.968727415e-01f, -8.660254038e-01f, -8.314696123e-01f, -7.933533403e-01f, -7.518398075e-01f, -7.071067812e-01f, -6.593458151e-01f, -6.087614290e-01f, -5.555702330e-01f, -5.000000000e-01f, -4.422886902e-01f, -3.826834324e-01f, -3.214394653e-01f, -2.588190451e-01f, -1.950903220e-01f, -1.305261922e-01f, -6.540312923e-02f, -1.836970199e-16f, 6.540312923e-02f, 1.305261922e-01f, 1.950903220e-01f, 2.588190451e-01f, 3.214394653e-01f, 3.826834324e-01f, 4.422886902e-01f, 5.000000000e-01f, 5.555702330e-01f, 6.087614290e-01f, 6.593458151e-01f, 7.071067812e-01f, 7.518398075e-01f, 7.933533403e-01f, 8.314696123e-01f, 8.660254038e-01f, 8.968727415e-01f, 9.238795325e-01f, 9.469301295e-01f, 9.659258263e-01f, 9.807852804e-01f, 9.914448614e-01f, 9.978589232e-01f};
+__device__ constexpr float W96S[96] = {0.000000000e+00f, 6.540312923e-02f, 1.305261922e-01f, 1.950903220e-01f, 2.588190451e-01f, 3.214394653e-01f, 3.826834324e-01f, 4.422886902e-01f, 5.000000000e-01f, 5.555702330e-01f, 6.087614290e-01f, 6.593458151e-01f, 7.071067812e-01f, 7.518398075e-01f, 7.933533403e-01f, 8.314696123e-01f, 8.660254038e-01f, 8.968727415e-01f, 9.238795325e-01f, 9.469301295e-01f, 9.659258263e-01f, 9.807852804e-01f, 9.914448614e-01f, 9.978589232e-01f, 1.000000000e+00f, 9.978589232e-01f, 9.914448614e-01f, 9.807852804e-01f, 9.659258263e-01f, 9.469301295e-01f, 9.238795325e-01f, 8.968727415e-01f, 8.660254038e-01f, 8.314696123e-01f, 7.933533403e-01f, 7.518398075e-01f, 7.071067812e-01f, 6.593458151e-01f, 6.087614290e-01f, 5.555702330e-01f, 5.000000000e-01f, 4.422886902e-01f, 3.826834324e-01f, 3.214394653e-01f, 2.588190451e-01f, 1.950903220e-01f, 1.305261922e-01f, 6.540312923e-02f, 1.224646799e-16f, -6.540312923e-02f, -1.305261922e-01f, -1.950903220e-01f, -2.588190451e-01f, -3.214394653e-01f, -3.826834324e-01f, -4.422886902e-01f, -5.000000000e-01f, -5.555702330e-01f, -6.087614290e-01f, -6.593458151e-01f, -7.071067812e-01f, -7.518398075e-01f, -7.933533403e-01f, -8.314696123e-01f, -8.660254038e-01f, -8.968727415e-01f, -9.238795325e-01f, -9.469301295e-01f, -9.659258263e-01f, -9.807852804e-01f, -9.914448614e-01f, -9.978589232e-01f, -1.000000000e+00f, -9.978589232e-01f, -9.914448614e-01f, -9.807852804e-01f, -9.659258263e-01f, -9.469301295e-01f, -9.238795325e-01f, -8.968727415e-01f, -8.660254038e-01f, -8.314696123e-01f, -7.933533403e-01f, -7.518398075e-01f, -7.071067812e-01f, -6.593458151e-01f, -6.087614290e-01f, -5.555702330e-01f, -5.000000000e-01f, -4.422886902e-01f, -3.826834324e-01f, -3.214394653e-01f, -2.588190451e-01f, -1.950903220e-01f, -1.305261922e-01f, -6.540312923e-02f};
+// v * exp(DIR * 2 pi i k / 96), k a compile-time constant after unrolling
+template <int DIR> __device__ __forceinline__ float2 mul_w96(float2 v, int k) {
+    const float c = W96C[k % 96], s = DIR * W96S[k % 96];
+    return make_float2(v.x * c - v.y * s, v.y * c + v.x * s);
+}
+// radix 24 = 3 x 8: n = a + 3m, k = b + 8c
+template <int DIR> struct Butterfly<24, DIR> {
+    __device__ __forceinline__ static void run(float2 *v) {
+        float2 t[3][8];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float2 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) u[m] = v[a + 3 * m];
+            Butterfly<8, DIR>::run(u);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) t[a][b] = (a * b) ? mul_w96<DIR>(u[b], 4 * a * b) : u[b];
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            float2 u[3] = {t[0][b], t[1][b], t[2][b]};
+            Butterfly<3, DIR>::run(u);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[b + 8 * c] = u[c];
+        }
+    }
+};
+// radix 32 = 4 x 8: n = a + 4m, k = b + 8c
+template <int DIR> struct Butterfly<32, DIR> {
+    __device__ __forceinline__ static void run(float2 *v) {
+        float2 t[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float2 u[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) u[m] = v[a + 4 * m];
+            Butterfly<8, DIR>::run(u);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) t[a][b] = (a * b) ? mul_w96<DIR>(u[b], 3 * a * b) : u[b];
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            float2 u[4] = {t[0][b], t[1][b], t[2][b], t[3][b]};
+            Butterfly<4, DIR>::run(u);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[b + 8 * c] = u[c];
+        }
+    }
+};
+
 // skewed shared-memory index: one padding element per 16 keeps the stride-R stores of a radix-8/16
 // Stockham pass and the unit-stride loads of the next one free of bank conflicts
 __host__ __device__ __forceinline__ int skew(int a) { return a + (a >> 4); }

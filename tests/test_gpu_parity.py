@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 SCORE_RTOL = 1e-4
 
 
-@pytest.mark.parametrize("n", [32, 64, 96, 128, 256])
+@pytest.mark.parametrize("n", [32, 64, 96, 128, 256, 384, 512])
 def test_fft2_matches_oracle_and_cufft(engine, oracle, n):
     rng = np.random.default_rng(n)
     imgs = rng.normal(size=(5, n, n)).astype(np.float32)
