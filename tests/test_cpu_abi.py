@@ -41,6 +41,21 @@ def test_struct_layouts_match_header():
     assert lib.cspb_recon_cfg_default(ctypes.byref(rc), 128, 1.35) == 0
     assert rc.resolution_limit == pytest.approx(2.7) and rc.mask_radius == pytest.approx(1.35 * 64)
     assert lib.cspb_refine_cfg_default(None, 128, 1.35) != 0
+    # csp: extended-table rows and the csp_* config (defaults of config/pyp_config.toml [tabs.csp])
+    assert _lib.PARTICLE_DTYPE.itemsize == 48 and _lib.TILT_DTYPE.itemsize == 24
+    assert ctypes.sizeof(_lib.CspCfg) == 4 * (18 + 6)
+    cc = _lib.CspCfg()
+    assert lib.cspb_csp_cfg_default(ctypes.byref(cc)) == 0
+    assert (cc.window_min, cc.window_max, cc.iterations, cc.random_evals) == (0, 20, 5, 0)
+    assert cc.tol_particle_psi == 30.0 and cc.tol_tilt_angle == 1.5 and cc.tol_tilt_shift == 100.0 and cc.tol_defocus == 750.0
+    # the host-side pose composition needs no GPU
+    p = np.zeros(1, _lib.PARTICLE_DTYPE)
+    p["psi"], p["theta"], p["phi"] = -30.0, -40.0, -50.0
+    t = np.zeros(1, _lib.TILT_DTYPE)
+    out = np.zeros(5, np.float32)
+    c3 = np.zeros(3, np.float32)
+    assert lib.cspb_csp_compose(_lib.ptr(p), _lib.ptr(p), _lib.ptr(t), _lib.ptr(t), _lib.ptr(c3), 1.0, 0.0, 0.0, _lib.ptr(out)) == 0
+    assert np.allclose(out[:3], [30.0, 40.0, 50.0], atol=1e-3)   # SPA limit: particle = minus the projection angles
 
 
 def test_no_cpu_fallback():

@@ -321,3 +321,68 @@ def test_streamed_pipeline_equals_staged_calls(engine, oracle):
     r3, ne3 = engine.refine_reconstruct(stack, want_rows, refine=False)
     assert ne3 == 0 and r3.tobytes() == want_rows.tobytes()
     assert np.abs(engine.recon_get_dump(0) - want[0]).max() <= 1e-5 * np.abs(want[0]).max()
+
+
+def test_full_size_properties_o_symmetry_256(engine):
+    """BASELINE configs[1] sizes (256-px box, O symmetry): properties that do not need the oracle.
+    (1) a symmetric reference scores symmetry-related poses identically; (2) insertion is additive
+    over disjoint particle sets; (3) projections of the phantom reconstruct it (FSC vs phantom);
+    (4) refinement of the truth stays at the truth."""
+    import torch
+
+    from pyp_b200 import synth_torch
+    from pyp_b200.symmetry import symmetry_matrices
+
+    n, px, P = 256, 1.0, 192
+    dev = torch.device("cuda", 0)
+    centres, amps, sigma = synth_torch.symmetric_phantom(n, "O")
+    vol = synth_torch.volume(n, centres, amps, sigma, dev)
+    truth = __import__("pyp_b200").synth.make_rows(P, px, seed=5)
+    stack = synth_torch.make_stack(n, centres, amps, sigma, truth, snr=0.2, seed=6, device=dev)
+    cfg = engine.refine_defaults(n, px)
+    cfg.low_res_limit, cfg.high_res_limit, cfg.mask_radius = 100.0, 2.5 * px, 0.38 * n * px
+    engine.refine_configure(cfg)
+    engine.set_symmetry("O")
+    engine.set_reference(vol)
+    engine.load_images(stack)
+    s0 = engine.score(truth)
+    assert (s0 > 3.0).all()
+    # (1) pose M and M S^T (S in O) give the same projection of an O-symmetric map
+    mats = symmetry_matrices("O").astype(np.float64)
+    from pyp_b200 import csp_geometry as G
+    from pyp_b200.synth import euler_matrix
+    alt = truth.copy()
+    for k in range(P):
+        m = euler_matrix(truth["psi"][k], truth["theta"][k], truth["phi"][k]) 
+        alt["psi"][k], alt["theta"][k], alt["phi"][k] = G.decode_m(mats[1 + k % 23] @ m)
+    s1 = engine.score(alt)
+    assert np.abs(s1 - s0).max() <= 2e-3 * np.abs(s0).max()
+    # (4) refining from the truth does not walk away and never lowers the score
+    refined, _, _ = engine.refine(truth)
+    from common import angular_distance
+    assert np.median(angular_distance(refined, truth)) < 0.3 and (refined["score"] >= s0 - 1e-3).all()
+    # (2) additivity of the accumulators over disjoint sets, (3) FSC against the phantom
+    rc = engine.recon_defaults(n, px)
+    host = stack.cpu().numpy()
+    engine.recon_begin(rc)
+    engine.recon_insert(host[:96], truth[:96])
+    a = [engine.recon_get_dump(h) for h in (0, 1)]
+    engine.recon_begin(rc)
+    engine.recon_insert(host[96:], truth[96:])
+    b = [engine.recon_get_dump(h) for h in (0, 1)]
+    engine.recon_begin(rc)
+    engine.recon_insert(host, truth)
+    for h in (0, 1):
+        full = engine.recon_get_dump(h)
+        assert np.abs(full - (a[h] + b[h])).max() <= 2e-5 * np.abs(full).max()
+    rec, h1, h2, stats = engine.recon_finalize(molecular_mass_kda=440.0)
+    v = vol.cpu().numpy()
+    fa, fb = np.fft.rfftn(rec.astype(np.float64)), np.fft.rfftn(v.astype(np.float64))
+    kz, ky, kx = np.meshgrid(np.fft.fftfreq(n) * n, np.fft.fftfreq(n) * n, np.fft.rfftfreq(n) * n, indexing="ij")
+    shell = np.rint(np.sqrt(kx ** 2 + ky ** 2 + kz ** 2)).astype(int)
+    num = np.bincount(shell.ravel(), (fa * fb.conj()).real.ravel())
+    den = np.sqrt(np.bincount(shell.ravel(), np.abs(fa).ravel() ** 2) * np.bincount(shell.ravel(), np.abs(fb).ravel() ** 2))
+    fsc = num[2:32] / den[2:32]
+    # 192 particles x 24 operators at SNR 0.2; the sigma = 2 px blobs carry signal to about shell 32 (8 A)
+    assert fsc.min() > 0.9, fsc
+    assert np.isfinite(stats).all()
