@@ -321,7 +321,9 @@ static void normalized_copy(const float *img, int n, float radius, int normalize
 }
 
 void orc_noise_curve(const float *imgs, int count, const orc_refine_cfg *cfg, float *curve) {
-    /* mean |F|^2 per nearest-integer ring over every step-th image (step = count/1024, >= 1) */
+    /* mean |F|^2 per nearest-integer ring over every step-th of the first min(count, 4096) images
+       (step = that count / 1024, >= 1) */
+    if (count > 4096) count = 4096;
     const int n = cfg->box, nh = n / 2 + 1, nr = n + 1;
     const int step = count > 1024 ? count / 1024 : 1;
     double *sum = (double *)calloc(nr, sizeof(double));

@@ -37,6 +37,14 @@ extern "C" int cspb_destroy(cspb_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->pipe_copy) {
+        cudaStreamSynchronize(ctx->pipe_copy);
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->pipe_ready[k]) cudaEventDestroy(ctx->pipe_ready[k]);
+            if (ctx->pipe_freed[k]) cudaEventDestroy(ctx->pipe_freed[k]);
+        }
+        cudaStreamDestroy(ctx->pipe_copy);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -145,6 +145,12 @@ struct cspb_ctx {
     std::vector<size_t> tw_off; // offsets (in float2)
     size_t tw_used = 0;
 
+    // streamed host pipeline (pipeline.cu): copy stream, events, two staging buffers, device rows — kept
+    // between calls (allocating and freeing ~10 GB per call costs tens of milliseconds)
+    cudaStream_t pipe_copy = nullptr;
+    cudaEvent_t pipe_ready[2] = {nullptr, nullptr}, pipe_freed[2] = {nullptr, nullptr};
+    DevBuf pipe_stage[2], pipe_rows;
+
     // recon state
     bool recon_ready = false;
     cspb_recon_cfg ccfg{};

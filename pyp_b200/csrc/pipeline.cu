@@ -7,22 +7,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <chrono>
+#include <vector>
 #include "internal.cuh"
-
-namespace {
-struct StreamPipe {
-    cudaStream_t copy = nullptr;
-    cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-    DevBuf stage[2], rows;
-    ~StreamPipe() {
-        for (int k = 0; k < 2; ++k) {
-            if (ready[k]) cudaEventDestroy(ready[k]);
-            if (freed[k]) cudaEventDestroy(freed[k]);
-        }
-        if (copy) cudaStreamDestroy(copy);
-    }
-};
-}  // namespace
 
 extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images, int flags,
                                        int64_t *n_evals_out) {
@@ -35,27 +21,49 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     if (do_refine && do_insert && ctx->ccfg.box != ctx->rcfg.box) return cspb_fail(ctx, CSPB_E_ARG, "refine and reconstruct boxes differ");
     if (n_evals_out) *n_evals_out = 0;
     if (n_images == 0) return 0;
-    // same chunking as cspb_refine_load_images / cspb_recon_insert, so the streamed and the staged
-    // APIs see identical chunks (the whitening curve is estimated on the first one)
-    const int chunk = chunk_images(n, n_images);
-    StreamPipe P;
+    // per-projection work does not depend on the batching (the whitening curve is estimated on the
+    // first min(n, 4096) images whatever the chunking), so the results equal those of the staged calls
+    // batch schedule: whole waves of the scorer (W = SMs x 8 CTAs x 4 units) and growing — W, 2W, 4W,
+    // ... — so that the first batch is on the device after a short copy while the later, larger ones
+    // lose nothing to wave quantisation; bounded by ~6 GB of staging per buffer
+    const long long W = (long long)ctx->sm_count * 32;
+    long long cap = (long long)(((size_t)6 << 30) / ((size_t)n * n * sizeof(float)));
+    if (cap > 4 * W) cap = 4 * W;
+    if (cap < 1) cap = 1;
+    std::vector<int> sizes;
+    {
+        long long rem = n_images, s = W < cap ? W : cap;
+        while (rem > 0) {
+            long long take = s < rem ? s : rem;
+            if (rem - take < W / 2 && rem <= cap) take = rem;
+            sizes.push_back((int)take);
+            rem -= take;
+            s = 2 * s < cap ? 2 * s : cap;
+        }
+    }
+    int chunk = 0;
+    for (int v : sizes) chunk = v > chunk ? v : chunk;
+    struct { cudaStream_t &copy; cudaEvent_t *ready, *freed; DevBuf *stage; DevBuf &rows; } P = {
+        ctx->pipe_copy, ctx->pipe_ready, ctx->pipe_freed, ctx->pipe_stage, ctx->pipe_rows};
     const bool dbg = getenv("CSPB_PIPE_DEBUG") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
     auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
-    CU_TRY(ctx, cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
-        CU_TRY(ctx, cudaEventCreateWithFlags(&P.ready[k], cudaEventDisableTiming));
-        CU_TRY(ctx, cudaEventCreateWithFlags(&P.freed[k], cudaEventDisableTiming));
-        RESERVE(ctx, P.stage[k], (size_t)chunk * n * n * sizeof(float));
+    if (!P.copy) {
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY(ctx, cudaEventCreateWithFlags(&P.ready[k], cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&P.freed[k], cudaEventDisableTiming));
+        }
     }
+    for (int k = 0; k < 2; ++k) RESERVE(ctx, P.stage[k], (size_t)chunk * n * n * sizeof(float));
     RESERVE(ctx, P.rows, (size_t)n_images * sizeof(cspb_row));
     if (dbg) fprintf(stderr, "pipe: buffers ready at %.1f ms\n", ms_since());
     CU_TRY(ctx, cudaMemcpyAsync(P.rows.p, rows_host, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
     int64_t evals = 0;
     int rc = 0, idx = 0;
-    for (int s = 0; s < n_images && !rc; s += chunk, ++idx) {
+    for (int s = 0; idx < (int)sizes.size() && !rc; s += sizes[idx], ++idx) {
         const int b = idx & 1;
-        const int cnt = n_images - s < chunk ? n_images - s : chunk;
+        const int cnt = sizes[idx];
         if (idx >= 2) CU_TRY(ctx, cudaStreamWaitEvent(P.copy, P.freed[b], 0));
         CU_TRY(ctx, cudaMemcpyAsync(P.stage[b].p, images_host + (size_t)s * n * n, (size_t)cnt * n * n * sizeof(float),
                                     cudaMemcpyHostToDevice, P.copy));

@@ -875,6 +875,10 @@ static int estimate_noise_from_spectra(cspb_ctx *ctx, const float2 *spec, int co
     RESERVE(ctx, d_idx, idx.size() * sizeof(int));
     CU_TRY(ctx, cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(d_idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    // sample: every step-th of the first min(count, 4096) images, so that the curve does not depend on
+    // how the caller chunks the stack (every chunking of the staged and streamed APIs starts with >= 4096
+    // images or with the whole stack)
+    if (count > 4096) count = 4096;
     const int step = count > 1024 ? count / 1024 : 1;
     const int n_s = (count + step - 1) / step;
     // sample every `step`-th image: gather pointers by launching per sampled image
