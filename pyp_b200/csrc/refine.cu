@@ -263,6 +263,15 @@ __device__ __forceinline__ RefQuad ldg_quad(const RefQuad *p) {
     return q;
 }
 
+// predicated variant: lanes with `take` false issue no memory traffic and keep `q` (the quad the
+// unit's first pose already gathered from the same voxel)
+__device__ __forceinline__ void ldg_quad_if(const RefQuad *p, bool take, RefQuad &q) {
+    asm("{\n\t.reg .pred t;\n\tsetp.ne.s32 t, %9, 0;\n\t"
+        "@t ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+        : "+f"(q.v00.x), "+f"(q.v00.y), "+f"(q.v10.x), "+f"(q.v10.y), "+f"(q.v01.x), "+f"(q.v01.y), "+f"(q.v11.x), "+f"(q.v11.y)
+        : "l"(p), "r"((int)take));
+}
+
 // sin / cos of pi * v on the MUFU pipe: v is reduced to [-1, 1] first, where sin.approx / cos.approx
 // are good to 2^-21 absolute — the size of the fp32 rounding of the phase itself
 __device__ __forceinline__ void sincospi_fast(float v, float *sn, float *cs) {
@@ -281,7 +290,10 @@ __device__ __forceinline__ void sincospi_fast(float v, float *sn, float *cs) {
 // 64 registers -> 8 CTAs = 32 warps per SM: the kernel is bound by L2/DRAM latency of the gathers
 // (long-scoreboard stalls), more resident warps measured +10 % over the 72-register build
 template <int PB, bool DDEF, bool SHARED>
-__global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArgs A) {
+#ifndef CSPB_SCORE_MINB
+#define CSPB_SCORE_MINB 6
+#endif
+__global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(const ScoreArgs A) {
     __shared__ float s_pose[4][PB][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int u = blockIdx.x * 4 + warp;
@@ -309,9 +321,15 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArg
 
     const float2 *img = A.packed + (long long)un.image * A.n_slots;
     const int origin = (A.rc * A.sy + A.rc) * A.sx;
-    float accB[PB], num[PB], xs[PB];
+    // per-ring-offset running sums {numerator, signed total} live in shared memory (lanes 0..3 of the
+    // warp own them): they are touched once per ring band and would otherwise pin 2 PB registers
+    __shared__ float2 s_ring[4][PB][4];
+    float accB[PB];
 #pragma unroll
-    for (int p = 0; p < PB; ++p) accB[p] = num[p] = xs[p] = 0.f;
+    for (int p = 0; p < PB; ++p) {
+        accB[p] = 0.f;
+        if (lane < 4) s_ring[warp][p][lane] = make_float2(0.f, 0.f);
+    }
     float accA = 0.f;
 
     for (int b = 0; b < A.n_bands; ++b) {
@@ -319,6 +337,7 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArg
         float accX[PB];
 #pragma unroll
         for (int p = 0; p < PB; ++p) accX[p] = 0.f;
+#pragma unroll 1
         for (int it = 0; it < bd.n_iter; ++it) {
             const int slot = bd.slot_start + it * 32 + lane;
             const int32_t ij = __ldg(A.slot_ij + slot);
@@ -335,8 +354,11 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArg
             // SHARED units (the optimiser's +-x, +-y evaluations): rotation and CTF of pose 0 hold for
             // every pose of the unit — one gather, PB phase ramps
             constexpr int NG = SHARED ? 1 : PB;
-            RefQuad q0[NG], q1[NG];
-            float fx[NG], fy[NG], fz[NG], sg[NG];
+            // The poses of a unit are neighbours (stencil +-h, line search): more often than not pose p
+            // lands in the voxel pose 0 already gathered — those lanes reuse its quads and issue no
+            // load (predicated), which removes their share of the L1 wavefronts.
+            RefQuad qa0, qa1;  // quads of pose 0, kept for the poses that land in the same voxel
+            int off0 = 0;
 #pragma unroll
             for (int p = 0; p < NG; ++p) {
                 const float4 ma = *reinterpret_cast<const float4 *>(&s_pose[warp][p][0]);
@@ -345,41 +367,46 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArg
                 float y = ma.z * fi + ma.w * fj;
                 float z = mb.x * fi + mb.y * fj;
                 // Friedel mate for the negative half space: s = sign(x)
-                const float s = __int_as_float((__float_as_int(x) & 0x80000000) | 0x3f800000);
-                x = fabsf(x); y *= s; z *= s;
-                sg[p] = s;
+                const float sgn = __int_as_float((__float_as_int(x) & 0x80000000) | 0x3f800000);
+                x = fabsf(x); y *= sgn; z *= sgn;
                 const int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
-                fx[p] = x - (float)ix; fy[p] = y - (float)iy; fz[p] = z - (float)iz;
-                const RefQuad *q = A.ref8 + (origin + (iz * A.sy + iy) * A.sx + ix);
-                q0[p] = ldg_quad(q);
-                q1[p] = ldg_quad(q + 1);
-            }
-            float px[NG], py[NG];
-#pragma unroll
-            for (int p = 0; p < NG; ++p) {
-                const float f = fx[p];
-                const float v00x = q0[p].v00.x + f * (q1[p].v00.x - q0[p].v00.x), v00y = q0[p].v00.y + f * (q1[p].v00.y - q0[p].v00.y);
-                const float v10x = q0[p].v10.x + f * (q1[p].v10.x - q0[p].v10.x), v10y = q0[p].v10.y + f * (q1[p].v10.y - q0[p].v10.y);
-                const float v01x = q0[p].v01.x + f * (q1[p].v01.x - q0[p].v01.x), v01y = q0[p].v01.y + f * (q1[p].v01.y - q0[p].v01.y);
-                const float v11x = q0[p].v11.x + f * (q1[p].v11.x - q0[p].v11.x), v11y = q0[p].v11.y + f * (q1[p].v11.y - q0[p].v11.y);
-                const float v0x = v00x + fy[p] * (v10x - v00x), v0y = v00y + fy[p] * (v10y - v00y);
-                const float v1x = v01x + fy[p] * (v11x - v01x), v1y = v01y + fy[p] * (v11y - v01y);
-                px[p] = v0x + fz[p] * (v1x - v0x);
-                py[p] = (v0y + fz[p] * (v1y - v0y)) * sg[p];
+                const float f = x - (float)ix, fyv = y - (float)iy, fzv = z - (float)iz;
+                const int off = origin + (iz * A.sy + iy) * A.sx + ix;
+                const RefQuad *q = A.ref8 + off;
+                RefQuad q0, q1;
+                if (p == 0) {
+                    off0 = off;
+                    qa0 = ldg_quad(q);
+                    qa1 = ldg_quad(q + 1);
+                    q0 = qa0;
+                    q1 = qa1;
+                } else {
+                    q0 = qa0;
+                    q1 = qa1;
+                    ldg_quad_if(q, off != off0, q0);
+                    ldg_quad_if(q + 1, off != off0, q1);
+                }
+                const float v00x = q0.v00.x + f * (q1.v00.x - q0.v00.x), v00y = q0.v00.y + f * (q1.v00.y - q0.v00.y);
+                const float v10x = q0.v10.x + f * (q1.v10.x - q0.v10.x), v10y = q0.v10.y + f * (q1.v10.y - q0.v10.y);
+                const float v01x = q0.v01.x + f * (q1.v01.x - q0.v01.x), v01y = q0.v01.y + f * (q1.v01.y - q0.v01.y);
+                const float v11x = q0.v11.x + f * (q1.v11.x - q0.v11.x), v11y = q0.v11.y + f * (q1.v11.y - q0.v11.y);
+                const float v0x = v00x + fyv * (v10x - v00x), v0y = v00y + fyv * (v10y - v00y);
+                const float v1x = v01x + fyv * (v11x - v01x), v1y = v01y + fyv * (v11y - v01y);
+                float pxv = v0x + fzv * (v1x - v0x), pyv = (v0y + fzv * (v1y - v0y)) * sgn;
                 float cv = ctfv;
                 if (DDEF) cv = valid ? -sinpif((chi0 + r2 * ddef[p]) * (1.f / CSPB_PI_F)) : 0.f;
-                px[p] *= cv;
-                py[p] *= cv;
-            }
+                pxv *= cv;
+                pyv *= cv;
+                accB[p] += pxv * pxv + pyv * pyv;
 #pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                const int g = SHARED ? 0 : p;
-                const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][p][6]);
-                float sn, cs;
-                sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
-                const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
-                accX[p] += gr * px[g] + gi * py[g];
-                if (!SHARED || p == 0) accB[p] += px[g] * px[g] + py[g] * py[g];
+                for (int pp = 0; pp < (SHARED ? PB : 1); ++pp) {
+                    const int e = SHARED ? pp : p;
+                    const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][e][6]);
+                    float sn, cs;
+                    sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
+                    const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
+                    accX[e] += gr * pxv + gi * pyv;
+                }
             }
         }
         const int ring = bd.ring0 + (lane & 3);
@@ -390,8 +417,10 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArg
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             if (lane < 4) {
-                xs[p] += v;
-                num[p] += (ring > A.limit_ring) ? fabsf(v) : v;
+                float2 t = s_ring[warp][p][lane];
+                t.x += (ring > A.limit_ring) ? fabsf(v) : v;
+                t.y += v;
+                s_ring[warp][p][lane] = t;
             }
         }
     }
@@ -399,7 +428,8 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : 8) score_kernel(const ScoreArg
 #pragma unroll
     for (int p = 0; p < PB; ++p) {
         const float bsum = warp_sum(accB[SHARED ? 0 : p]);
-        float nv = num[p], xv = xs[p];
+        const float2 t = s_ring[warp][p][lane & 3];
+        float nv = t.x, xv = t.y;
         nv += __shfl_xor_sync(0xffffffffu, nv, 1);
         nv += __shfl_xor_sync(0xffffffffu, nv, 2);
         xv += __shfl_xor_sync(0xffffffffu, xv, 1);
