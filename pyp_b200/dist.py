@@ -40,6 +40,54 @@ def shard_range(first, last, rank, world):
     return (lo, hi)
 
 
+def shard_entities(ids, rank, world):
+    """CSP shards whole entities: all tilts of a particle (modes 1/2/5) or all particles of a tilt
+    (modes 0/3/4/6) stay on one GPU, because the objective couples them (local_run.py:411-431 hands
+    contiguous index ranges of ptlind_list / scanord_list to its processes).  Returns the sorted
+    unique ids of this rank's contiguous slice."""
+    u = np.unique(np.asarray(ids))
+    lo, hi = shard_range(0, u.size - 1, rank, world)
+    return u[lo:hi + 1]
+
+
+def merge_entity_tables(base, parts, key):
+    """Overlay refined extended-table entries on the input table, the way Parameters.merge updates
+    its particle / tilt dictionaries (cistem_star_file.py:674-690): entries of later parts win."""
+    out = np.array(base, copy=True)
+    keys = key if isinstance(key, (tuple, list)) else (key,)
+    index = {tuple(int(r[k]) for k in keys): i for i, r in enumerate(out)}
+    for part in parts:
+        for r in part:
+            index_key = tuple(int(r[k]) for k in keys)
+            if index_key in index:
+                out[index[index_key]] = r
+    return out
+
+
+def gather_table(table, dst=0):
+    """Gather variable-length structured tables (extended-table entries) on `dst` as a list per rank."""
+    import torch
+
+    d = _dist()
+    rank, ws = world()
+    table = np.ascontiguousarray(table)
+    if ws == 1:
+        return [table]
+    item = table.dtype.itemsize
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(ws)]
+    d.all_gather(counts, torch.tensor([table.size], dtype=torch.int64))
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts + [1])
+    buf = torch.zeros(mx * item, dtype=torch.uint8)
+    if table.size:
+        buf[: table.size * item] = torch.from_numpy(table.view(np.uint8).reshape(-1).copy())
+    bufs = [torch.zeros_like(buf) for _ in range(ws)] if rank == dst else None
+    d.gather(buf, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return [b.numpy()[: c * item].view(table.dtype).copy() for b, c in zip(bufs, counts)]
+
+
 def _dist():
     import torch.distributed as dist
 

@@ -122,6 +122,17 @@ if rank == 0:
     assert torch.all(acc == sum(range(1, ws + 1)))
 else:
     assert allrows is None
+# CSP: whole particles per rank, refined entries gathered and overlaid on the input table
+from pyp_b200._lib import PARTICLE_DTYPE
+pinds = np.repeat(np.arange(7), 5)                      # 7 particles x 5 tilts
+mine = pd.shard_entities(pinds, rank, ws)
+table = np.zeros(7, PARTICLE_DTYPE); table["pind"] = np.arange(7)
+part = table[np.isin(table["pind"], mine)].copy(); part["psi"] = 10.0 + part["pind"]
+parts = pd.gather_table(part, dst=0)
+if rank == 0:
+    assert sorted(int(x) for p in parts for x in p["pind"]) == list(range(7))
+    merged = pd.merge_entity_tables(table, parts, "pind")
+    assert np.allclose(merged["psi"], 10.0 + np.arange(7))
 want = sum((r + 1) * (pd.shard_range(1, n, r, ws)[1] - pd.shard_range(1, n, r, ws)[0] + 1) for r in range(ws)) / n
 assert np.allclose(curve, want), (curve, want)
 dist.destroy_process_group()
