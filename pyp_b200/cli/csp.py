@@ -43,12 +43,7 @@ DEFAULTS = {
 }
 
 
-def param(value, iteration):
-    """Per-iteration colon lists (src/pyp/system/project_params.py:362-373)."""
-    if isinstance(value, str):
-        listed = value.split(":")
-        return listed[min(iteration - 2, len(listed) - 1)]
-    return value
+from ..schedule import get_rhref, param  # noqa: E402  (per-iteration colon lists, project_params.py:362-373)
 
 
 def load_config(path=".pyp_config.toml"):
@@ -70,7 +65,8 @@ def csp_cfg_from(config, mode):
     c.window_max = int(param(config["csp_UseImagesForRefinementMax"], it))
     c.iterations = int(config["csp_OptimizerMaxIter"])
     c.random_evals = int(config["csp_NumberOfRandomIterations"])
-    c.grid_search = 1 if config["csp_GridSearch"] else 0
+    # bin/csp_GS is the grid-search build of the binary (align/core.py:696-701)
+    c.grid_search = 1 if (config["csp_GridSearch"] or os.environ.get("CSPB_CSP_GRID")) else 0
     c.angle_step, c.shift_step = float(config["csp_AngleStep"]), float(config["csp_ShiftStep"])
     c.tol_particle_psi = float(config["csp_ToleranceParticlesPsi"])
     c.tol_particle_theta = float(config["csp_ToleranceParticlesTheta"])
@@ -91,9 +87,8 @@ def refine_cfg_from(config, box, pixel):
     it = int(config.get("refine_iter", 2))
     cfg = Engine.refine_defaults(box, pixel)
     cfg.low_res_limit = float(param(config["refine_rlref"], it))
-    rh = float(param(config["refine_rhref"], it))
-    cfg.high_res_limit = rh if rh > 0 else 16.0          # postprocess/core.py:16-69 falls back to 16 A
-    cfg.high_res_limit = max(cfg.high_res_limit, 2.0 * pixel)
+    sched = {"refine_rhref": config["refine_rhref"], "refine_dataset": config.get("refine_dataset", config.get("data_set", ""))}
+    cfg.high_res_limit = max(float(get_rhref(sched, it, maps_dir=os.path.join("frealign", "maps"))), 2.0 * pixel)  # postprocess/core.py:16-55
     rad = config.get("particle_rad")
     if rad:
         cfg.mask_radius = float(rad)

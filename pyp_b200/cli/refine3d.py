@@ -140,6 +140,10 @@ def run(p, out=sys.stdout):
     if rows.size:
         out.write(f"Mean score {float(refined['score'].mean()):.4f}, mean change {float(changes['score'].mean()):+.4f}, "
                   f"{n_evals} projections scored in {dt:.2f} s\n")
+    if p["use_priors"]:
+        out.write("Note: priors (answer 7) are accepted but not applied by cspb200\n")
+    if p["mask_2d"][3] > 0:
+        out.write("Note: the 2-D focus mask (answers 29-32) is accepted but not applied by cspb200\n")
     out.write("\nRefine3D: Normal termination\n")
     eng.close()
     return refined

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     const float fi = (float)i, fj = (float)j;
     const float r2 = fi * fi + fj * fj;
     if (r2 > A.rmax2) return;
-    float2 F = A.spec[(long long)img * n * nh + idx];
+    float2 F = __ldcs(A.spec + (long long)img * n * nh + idx);  // streamed once: do not displace the accumulators in L2
     if ((i + j) & 1) { F.x = -F.x; F.y = -F.y; }  // box centre at n/2
     const float ctf = -sinpif(ctf_chi(s_ctf, fi, fj, r2) * (1.f / CSPB_PI_F));
     float w = row.occupancy * 0.01f;

@@ -20,6 +20,8 @@ What gets pinned:
   rows_{a,b}.star, rows_star_merged_by_reference.npy — `.star` tables written by pyp_b200/formats/star.py and
       merged by the reference's merge_star (cistem_star_file.py:1398-1441), i.e. what pyp does with the
       outputs of refine_ctf (frealign.py:3133-3154).
+  rhref_cases.json (+ rhref_fsc.txt, rhref_res.txt) — high-resolution limits returned by
+      pyp.postprocess.get_rhref (postprocess/core.py:16-55) for fixed, scheduled and FSC-driven settings.
   csp_euler.npy — csp_euler_angles (geometry/core.py:1081-1217): tilt angle, axis, csp angles and
       3DAVG translation in; projection (psi, theta, phi, sx, sy) and the stored particle
       parameters (-ppsi, -ptheta, -pphi, px, py, pz) out.  Pins pyp_b200/csp_geometry.py.
@@ -211,6 +213,31 @@ def main():
                                       minazh=10.0, maxazh=170.0, minscore=0.05, maxscore=0.98))
     shape_case("tomo", True, 0.7, dict(mindef=0.0, maxdef=100000.0, firstframe=0, lastframe=3, mintilt=-45.0, maxtilt=90.0,
                                       minazh=0.0, maxazh=180.0, minscore=0.0, maxscore=1.0))
+    # ---- resolution schedule: postprocess.get_rhref (postprocess/core.py:16-55) on a synthetic FSC table
+    from pyp import postprocess as PP
+
+    tmp = tempfile.mkdtemp()
+    cwd = os.getcwd()
+    os.makedirs(os.path.join(tmp, "maps"))
+    os.makedirs(os.path.join(tmp, "scratch"))
+    res = np.array([float(r) for r in 1.35 * 128 / np.arange(1, 60)])
+    curves = [1.0 / (1.0 + (8.0 / res) ** 4), 1.0 / (1.0 + (6.0 / res) ** 4), 1.0 / (1.0 + (4.5 / res) ** 4)]
+    np.savetxt(os.path.join(tmp, "maps", "ds_r01_fsc.txt"), np.column_stack([res] + curves))
+    np.savetxt(os.path.join(tmp, "maps", "ds_r01_res.txt"), np.array([[2, 12.0], [3, 9.5], [4, 7.0]]))
+    cases = []
+    os.chdir(os.path.join(tmp, "scratch"))
+    try:
+        for rh, it in (("8:6:4", 2), ("8:6:4", 3), ("8:6:4", 7), ("0", 2), ("0", 3), ("0", 4), ("0", 5), (5.5, 3)):
+            mp = {"refine_rhref": rh, "refine_dataset": "ds"}
+            cases.append({"refine_rhref": rh, "iteration": it, "rhref": float(PP.get_rhref(mp, it))})
+    finally:
+        os.chdir(cwd)
+    shutil.copy(os.path.join(tmp, "maps", "ds_r01_fsc.txt"), os.path.join(HERE, "rhref_fsc.txt"))
+    shutil.copy(os.path.join(tmp, "maps", "ds_r01_res.txt"), os.path.join(HERE, "rhref_res.txt"))
+    shutil.rmtree(tmp)
+    with open(os.path.join(HERE, "rhref_cases.json"), "w") as f:
+        json.dump(cases, f, indent=1)
+
     # ---- star tables: our writer read back by the reference's merge_star / read_star
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     from pyp_b200.formats import cistem as our_cistem, star as our_star

@@ -161,3 +161,31 @@ def test_refine_ctf_prompt_order():
     assert p["out_star"] == "o.star" and p["last"] == 100 and p["defocus_range"] == 2000.0 and p["refine_defocus"] and not p["beam_tilt"]
     with pytest.raises(PromptError):
         refine_ctf.parse(Answers("\n".join(str(x) for x in a[:20]), "refine_ctf"))
+
+
+def test_resolution_schedule_matches_reference(tmp_path):
+    """tests/golden/rhref_cases.json holds what pyp.postprocess.get_rhref (postprocess/core.py:16-55)
+    returned for fixed, scheduled and FSC-driven `refine_rhref` settings."""
+    import json
+    import shutil
+
+    from pyp_b200 import schedule
+
+    g = os.path.join(ROOT, "tests", "golden")
+    maps = tmp_path / "maps"
+    maps.mkdir()
+    shutil.copy(os.path.join(g, "rhref_fsc.txt"), maps / "ds_r01_fsc.txt")
+    shutil.copy(os.path.join(g, "rhref_res.txt"), maps / "ds_r01_res.txt")
+    cases = json.load(open(os.path.join(g, "rhref_cases.json")))
+    assert len(cases) == 8
+    for c in cases:
+        got = schedule.get_rhref({"refine_rhref": c["refine_rhref"], "refine_dataset": "ds"}, c["iteration"], maps_dir=str(maps))
+        assert got == pytest.approx(c["rhref"], rel=1e-12), c
+    # a negative limit is jittered by at most 4 % in reciprocal space
+    class R:
+        @staticmethod
+        def uniform(a, b):
+            return b
+    v = schedule.get_rhref({"refine_rhref": "-8", "refine_dataset": "ds"}, 2, rng=R)
+    assert v == pytest.approx(1.0 / (1.0 / 8 + 1.0 / 8 / 25.0))
+    assert schedule.get_rhref({"refine_rhref": "0", "refine_dataset": "none"}, 5, maps_dir=str(maps)) == 16
