@@ -484,7 +484,7 @@ static float line_step(float f0, const float *fl) {
 /* refine one starting pose x[6] in place; returns the final score (x100) and its band sums in o4.
    The better of {refined, start} is kept.  *evals is incremented per objective evaluation. */
 static float refine_one(const orc_ref *r, const float *spec, const orc_row *row, float *x, const int *freem,
-                        const orc_refine_cfg *cfg, float *o4, long long *evals) {
+                        const orc_refine_cfg *cfg, float *o4, long long *evals, float coarse) {
     const int n = cfg->box;
     float lo, hi;
     orc_band_limits(cfg, &lo, &hi);
@@ -495,7 +495,9 @@ static float refine_one(const orc_ref *r, const float *spec, const orc_row *row,
     const float h_def = cfg->defocus_step > 0.f ? cfg->defocus_step : 50.f;
     const int iters = n_free > 0 ? (cfg->local_iterations > 0 ? cfg->local_iterations : 8) : 0;
     const int late = iters / 2 + 1; /* stencil steps stay constant for the first half, then shrink */
-    float h[NP] = {h_ang, h_ang, h_ang, h_shift, h_shift, h_def};
+    /* coarse >= 1: the pose steps start `coarse` times larger (hits of the global search sit up to
+       half a grid step from the optimum; the stencil then spans the search resolution) */
+    float h[NP] = {h_ang * coarse, h_ang * coarse, h_ang * coarse, h_shift * coarse, h_shift * coarse, h_def};
     float d[NP], q[NP];
     const float x_start[NP] = {x[0], x[1], x[2], x[3], x[4], x[5]};
     for (int it = 0; it < iters; ++it) {
@@ -555,7 +557,7 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
         float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f};
         float o4[4];
         long long ev = 0;
-        const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev);
+        const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, 1.f);
         evals += ev;
         write_row(row, x, sc, o4, nband, cfg->refine_defocus);
     }
@@ -689,7 +691,7 @@ long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows,
                 x[0] = angles3[3 * top[t].orient]; x[1] = angles3[3 * top[t].orient + 1]; x[2] = angles3[3 * top[t].orient + 2];
                 x[3] = top[t].sx; x[4] = top[t].sy;
             }
-            const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev);
+            const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, hi / r_s);
             if (sc > bestsc) { bestsc = sc; memcpy(xb, x, sizeof xb); memcpy(ob, o4, sizeof ob); }
         }
         evals += ev;

@@ -1143,8 +1143,18 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     ScoreUnit *un = ctx->d_units.as<ScoreUnit>(), *un_ls = un + (size_t)ns * upi;
     float4 *out = ctx->d_out.as<float4>(), *out_ls = out + (size_t)ns * NE;
     const float r_hi = ctx->plan.r_hi;
-    const float h_ang = 0.35f * 57.29578f / r_hi;                      // ~1/3 of the angular resolution at r_hi
-    const float h_shift = 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
+    // hits of the global search sit up to half a grid step from the optimum: their pose steps start
+    // r_hi / r_search times larger, so that the first stencils span the search resolution
+    float coarse = 1.f;
+    if (c.global_search) {
+        const float npx = (float)c.box * c.pixel_size;
+        float r_s = c.search_high_res > 0.f ? npx / c.search_high_res : r_hi;
+        if (r_s > r_hi) r_s = r_hi;
+        if (r_s < ctx->plan.r_lo + 2.f) r_s = fminf(ctx->plan.r_lo + 2.f, r_hi);
+        coarse = r_hi / r_s;
+    }
+    const float h_ang = coarse * 0.35f * 57.29578f / r_hi;                      // ~1/3 of the angular resolution at r_hi
+    const float h_shift = coarse * 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
     const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
     const int g = ceil_div(ns, 128);
     opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, ns, K, d_hits, d_angles, st, h_ang, h_shift, h_def);
