@@ -378,6 +378,11 @@ def run_b200_arm(a):
         return
 
     peak, peak_src = measured_peaks()
+    # gather roofline of the scoring kernel: random 32-byte gathers, L2- and L1-resident
+    try:
+        gather_l2, gather_l1 = eng.gather_peak(64 << 20), eng.gather_peak(32 << 10, per_cta=True)
+    except Exception:
+        gather_l2 = gather_l1 = None
     traffic = None
     try:  # DRAM bytes per launch of the scoring kernel, from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -402,7 +407,9 @@ def run_b200_arm(a):
                               "score_kernels": score_ms / a.steps, "insert_kernel": ins_ms / a.steps},
         "roofline": {"bound": "hbm", "kernel": "score_kernel<4,false>", "achieved": score_gbs, "peak": peak, "unit": "GB/s",
                      "frac": score_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                     "note": "gather served by L1/L2 (reference volume L2-resident): algorithmic bytes exceed the HBM peak; the kernel's own limit is the L1 data pipe (profiles/r01_notes.md)",
+                     "note": "gather served by L1/L2 (reference volume L2-resident): algorithmic bytes exceed the HBM peak; the kernel's own ceiling is the SM data pipe, measured live as gather_peak_* (random 32-byte gathers); gather_achieved counts the 64 B/sample of the algorithm, of which the kernel really loads about half (neighbouring poses reuse quads, shift evaluations share one gather)",
+                     "gather_peak_l2_resident": gather_l2, "gather_peak_l1_resident": gather_l1,
+                     "gather_achieved": score_gbs * 64.0 / 72.0, "gather_frac": (score_gbs * 64.0 / 72.0 / gather_l2) if gather_l2 else None,
                      "bytes_per_unit": bytes_per_eval, "units_per_launch": score_units / max(1, score_launches),
                      "avg_launch_ms": score_ms / max(1, score_launches)},
         "roofline_insert": {"bound": "hbm", "kernel": "insert_kernel", "achieved": ins_gbs, "peak": peak, "unit": "GB/s",

@@ -313,6 +313,11 @@ int cspb_cufft2_r2c(cspb_ctx *ctx, const float *in, float *out_complex, int n, i
 int cspb_ctf_image(cspb_ctx *ctx, const cspb_row *row, int n, float *out);
 /* Central slice of the current reference at one pose: out n*(n/2+1) complex (zero outside band). */
 int cspb_project(cspb_ctx *ctx, float psi, float theta, float phi, float *out_complex);
+/* Gather microbenchmark (the roofline denominator of the scoring kernel next to the HBM peak,
+ * SURVEY.md §8d): GB/s of 32-lane gathers of 32-byte items at random positions of a window of
+ * `window_bytes` — per_cta = 1: every CTA has its own window (L1-resident for <= 64 KB),
+ * per_cta = 0: one shared window (L2-resident for tens of MB, HBM for GBs). */
+int cspb_gather_peak(cspb_ctx *ctx, size_t window_bytes, int per_cta, float *gbs_out);
 /* Band plan introspection: number of lattice samples inside the band / padded slots. */
 int cspb_band_counts(const cspb_ctx *ctx, int *n_band, int *n_slots);
 

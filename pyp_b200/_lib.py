@@ -133,6 +133,7 @@ _SIGNATURES = {
     "cspb_ctf_image": (_i, [_vp, _vp, _i, _vp]),
     "cspb_project": (_i, [_vp, _f, _f, _f, _vp]),
     "cspb_band_counts": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "cspb_gather_peak": (_i, [_vp, C.c_size_t, _i, C.POINTER(_f)]),
 }
 
 # every symbol include/cspb200.h declares (checked by tests/test_abi.py)

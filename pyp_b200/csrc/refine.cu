@@ -1251,3 +1251,56 @@ extern "C" int cspb_project(cspb_ctx *ctx, float psi, float theta, float phi, fl
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+// ================================================================== gather microbenchmark
+// The denominator SURVEY.md §8d asks for next to the HBM peak: how fast can 32-lane gathers of
+// 32-byte items (the scorer's access) be served from a window of `window_bytes` — small window =
+// L1-resident, tens of MB = L2-resident, GBs = HBM.  Every lane walks its own LCG sequence.
+namespace {
+__global__ void __launch_bounds__(128, 8) gather_peak_kernel(const RefQuad *__restrict__ buf, unsigned n_items, int iters,
+                                                            unsigned per_cta_window, float *__restrict__ sink) {
+    unsigned state = (blockIdx.x * 128u + threadIdx.x) * 2654435761u + 12345u;
+    // per-CTA window (L1 test) or the whole buffer
+    const unsigned base = per_cta_window ? (unsigned)(((unsigned long long)blockIdx.x * per_cta_window) % (n_items - per_cta_window)) : 0u;
+    const unsigned span = per_cta_window ? per_cta_window : n_items;
+    float acc = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        RefQuad q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            state = state * 1664525u + 1013904223u;
+            q[k] = ldg_quad(buf + base + (state >> 8) % span);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += q[k].v00.x + q[k].v10.y + q[k].v01.x + q[k].v11.y;
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+}  // namespace
+
+extern "C" int cspb_gather_peak(cspb_ctx *ctx, size_t window_bytes, int per_cta, float *gbs_out) {
+    if (!ctx || !gbs_out || window_bytes < 4096) return CSPB_E_ARG;
+    const size_t buf_bytes = per_cta ? ((size_t)256 << 20) : window_bytes;
+    DevBuf buf, sink;
+    RESERVE(ctx, buf, buf_bytes);
+    RESERVE(ctx, sink, 16);
+    CU_TRY(ctx, cudaMemsetAsync(buf.p, 0, buf_bytes, ctx->stream));
+    const unsigned n_items = (unsigned)(buf_bytes / sizeof(RefQuad));
+    const unsigned win = per_cta ? (unsigned)(window_bytes / sizeof(RefQuad)) : 0u;
+    const int grid = ctx->sm_count * 8 * 4, iters = 2000;
+    cudaEvent_t e0, e1;
+    CU_TRY(ctx, cudaEventCreate(&e0));
+    CU_TRY(ctx, cudaEventCreate(&e1));
+    gather_peak_kernel<<<grid, 128, 0, ctx->stream>>>(buf.as<RefQuad>(), n_items, 50, win, sink.as<float>());  // warm-up
+    CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    gather_peak_kernel<<<grid, 128, 0, ctx->stream>>>(buf.as<RefQuad>(), n_items, iters, win, sink.as<float>());
+    CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gbs_out = (float)((double)grid * 128.0 * iters * 4.0 * sizeof(RefQuad) / (ms * 1e-3) / 1e9);
+    return 0;
+}

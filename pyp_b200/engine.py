@@ -351,6 +351,12 @@ class Engine:
         self._ck(self._l.cspb_ctf_image(self._h, ptr(row), int(n), ptr(out)))
         return out
 
+    def gather_peak(self, window_bytes, per_cta=False):
+        """GB/s of random 32-byte gathers from a window (roofline denominator of the scorer)."""
+        g = C.c_float(0)
+        self._ck(self._l.cspb_gather_peak(self._h, C.c_size_t(int(window_bytes)), 1 if per_cta else 0, C.byref(g)))
+        return float(g.value)
+
     def project(self, psi, theta, phi):
         n = self.box
         out = np.zeros((n, n // 2 + 1), dtype=np.complex64)

@@ -386,3 +386,11 @@ def test_full_size_properties_o_symmetry_256(engine):
     # 192 particles x 24 operators at SNR 0.2; the sigma = 2 px blobs carry signal to about shell 32 (8 A)
     assert fsc.min() > 0.9, fsc
     assert np.isfinite(stats).all()
+
+
+def test_gather_peak_microbenchmark(engine):
+    """roofline denominator of the scorer: L1/L2-resident gathers run at TB/s, an HBM-sized window slower"""
+    l1 = engine.gather_peak(32 << 10, per_cta=True)
+    l2 = engine.gather_peak(64 << 20)
+    hbm = engine.gather_peak(2 << 30)
+    assert l1 > 2000 and l2 > 2000 and hbm < l2
