@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
         for (int it = 0; it < bd.n_iter; ++it) {
             const int slot = bd.slot_start + it * 32 + lane;
             const int32_t ij = __ldg(A.slot_ij + slot);
-            const float2 F = __ldg(img + slot);
+            const float2 F = __ldcs(img + slot);  // read once per unit: streaming, keeps the reference in L2
             int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
             const bool valid = (i != CSPB_DUMMY_I);
             if (!valid) { i = 0; j = 0; }
