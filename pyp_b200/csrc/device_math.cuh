@@ -126,3 +126,74 @@ __host__ __device__ __forceinline__ void score_stats(float4 v, int n_samples, fl
     const float var = resid / ns;
     *logp = var > 0.f ? -0.5f * ns * (1.f + logf(2.f * CSPB_PI_F * var)) : 0.f;
 }
+
+// mean and 1/sigma of the pixels outside radius R (all pixels if the circle covers the box) of one
+// n x n image per CTA — the normalisation of analysis/image.py:320-338,406-417.  Rows are walked by
+// warps with 16-byte loads (no integer division); the second pass re-reads the image from L2.
+__device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, int n, float radius, int normalize, int invert,
+                                                 float *off_out, float *scl_out, float *red /* >= 64 floats */) {
+    __shared__ float s_mean_;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const float sgn = invert ? -1.f : 1.f;
+    if (!normalize) {
+        if (tid == 0) { *off_out = 0.f; *scl_out = sgn; }
+        return;
+    }
+    const float r2lim = radius * radius;
+    const int c = n / 2;
+    const bool use_all = (radius * radius >= 2.f * c * c);
+    const bool vec = (n & 3) == 0;
+    float s = 0.f, cnt = 0.f;
+    for (int y = warp; y < n; y += nw) {
+        const float dy2 = (float)((y - c) * (y - c));
+        const float *row = p + (long long)y * n;
+        if (vec) {
+            for (int x = lane * 4; x < n; x += 128) {
+                const float4 v = *reinterpret_cast<const float4 *>(row + x);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float dx = (float)(x + k - c);
+                    if (use_all || dx * dx + dy2 > r2lim) { s += vv[k]; cnt += 1.f; }
+                }
+            }
+        } else {
+            for (int x = lane; x < n; x += 32) {
+                const float dx = (float)(x - c);
+                if (use_all || dx * dx + dy2 > r2lim) { s += row[x]; cnt += 1.f; }
+            }
+        }
+    }
+    s = block_sum(s, red);
+    cnt = block_sum(cnt, red);
+    if (tid == 0) s_mean_ = cnt > 0.f ? s / cnt : 0.f;
+    __syncthreads();
+    const float mean = s_mean_;
+    float v2 = 0.f;
+    for (int y = warp; y < n; y += nw) {
+        const float dy2 = (float)((y - c) * (y - c));
+        const float *row = p + (long long)y * n;
+        if (vec) {
+            for (int x = lane * 4; x < n; x += 128) {
+                const float4 v = *reinterpret_cast<const float4 *>(row + x);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float dx = (float)(x + k - c);
+                    if (use_all || dx * dx + dy2 > r2lim) { const float d = vv[k] - mean; v2 += d * d; }
+                }
+            }
+        } else {
+            for (int x = lane; x < n; x += 32) {
+                const float dx = (float)(x - c);
+                if (use_all || dx * dx + dy2 > r2lim) { const float d = row[x] - mean; v2 += d * d; }
+            }
+        }
+    }
+    v2 = block_sum(v2, red);
+    if (tid == 0) {
+        const float var = cnt > 0.f ? v2 / cnt : 0.f;
+        *off_out = mean;
+        *scl_out = var > 0.f ? sgn * rsqrtf(var) : sgn;
+    }
+}

@@ -283,38 +283,7 @@ int grid_for(long long total, int block, int sm) {
 __global__ void image_stats_recon_kernel(const float *__restrict__ img, int n, float radius, int normalize, int invert,
                                          float *__restrict__ offs, float *__restrict__ scls) {
     __shared__ float red[64];
-    __shared__ float s_mean;
-    const float *p = img + (long long)blockIdx.x * n * n;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const float sgn = invert ? -1.f : 1.f;
-    if (!normalize) {
-        if (tid == 0) { offs[blockIdx.x] = 0.f; scls[blockIdx.x] = sgn; }
-        return;
-    }
-    const float r2lim = radius * radius;
-    const int c = n / 2;
-    const bool use_all = (radius * radius >= 2.f * c * c);
-    float s = 0.f, cnt = 0.f;
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int x = idx % n - c, y = idx / n - c;
-        if (use_all || (float)(x * x + y * y) > r2lim) { s += p[idx]; cnt += 1.f; }
-    }
-    s = block_sum(s, red);
-    cnt = block_sum(cnt, red);
-    if (tid == 0) s_mean = cnt > 0.f ? s / cnt : 0.f;
-    __syncthreads();
-    const float mean = s_mean;
-    float v = 0.f;
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int x = idx % n - c, y = idx / n - c;
-        if (use_all || (float)(x * x + y * y) > r2lim) { const float d = p[idx] - mean; v += d * d; }
-    }
-    v = block_sum(v, red);
-    if (tid == 0) {
-        const float var = cnt > 0.f ? v / cnt : 0.f;
-        offs[blockIdx.x] = mean;
-        scls[blockIdx.x] = var > 0.f ? sgn * rsqrtf(var) : sgn;
-    }
+    image_edge_stats(img + (long long)blockIdx.x * n * n, n, radius, normalize, invert, offs + blockIdx.x, scls + blockIdx.x, red);
 }
 
 }  // namespace
