@@ -218,9 +218,10 @@ def run_b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n, px, P = a.box, a.pixel, a.particles
+    n, px = a.box, a.pixel
     rcfg, ccfg = workload_cfgs(n, px)
     eng = Engine(local_rank)
+    P = a.particles  # (a wave-aligned count, eng.wave_units x k, was measured: no gain — CTAs do not finish in lockstep)
     eng.refine_configure(rcfg)
     n_sym = eng.set_symmetry(a.sym)
     n_band, n_slots = eng.band_counts()
@@ -398,7 +399,7 @@ def run_b200_arm(a):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"SPA local refine3d+reconstruct3d, {a.sym} symmetry ({n_sym} ops), {n}-px box at {px} A/px (BASELINE configs[1])",
-                   "particles_per_gpu": P, "band": "100A..2.5px", "n_band": n_band, "n_slots": n_slots,
+                   "particles_per_gpu": P, "scorer_wave_units": eng.wave_units, "band": "100A..2.5px", "n_band": n_band, "n_slots": n_slots,
                    "evals_per_particle": evals / (a.steps * P), "l2_policy": f"inputs larger than L2 ({P * n * n * 4 / 1e9:.1f} GB stack per step)",
                    "parallelism": f"particle shards x{world}, NCCL reduce of half-volumes" if world > 1 else "single GPU"},
         "reconstruct3d_particles_per_sec": world * P / ((stage[2] + stage[3]) * 1e-3),

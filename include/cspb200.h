@@ -318,6 +318,9 @@ int cspb_project(cspb_ctx *ctx, float psi, float theta, float phi, float *out_co
  * `window_bytes` — per_cta = 1: every CTA has its own window (L1-resident for <= 64 KB),
  * per_cta = 0: one shared window (L2-resident for tens of MB, HBM for GBs). */
 int cspb_gather_peak(cspb_ctx *ctx, size_t window_bytes, int per_cta, float *gbs_out);
+/* Units (image x <=4 poses, one warp each) of the scoring kernel resident at once on this GPU = one
+ * full wave; stacks whose particle count is a multiple of it lose nothing to wave quantisation. */
+int cspb_wave_units(cspb_ctx *ctx);
 /* Band plan introspection: number of lattice samples inside the band / padded slots. */
 int cspb_band_counts(const cspb_ctx *ctx, int *n_band, int *n_slots);
 

@@ -134,6 +134,7 @@ _SIGNATURES = {
     "cspb_project": (_i, [_vp, _f, _f, _f, _vp]),
     "cspb_band_counts": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "cspb_gather_peak": (_i, [_vp, C.c_size_t, _i, C.POINTER(_f)]),
+    "cspb_wave_units": (_i, [_vp]),
 }
 
 # every symbol include/cspb200.h declares (checked by tests/test_abi.py)

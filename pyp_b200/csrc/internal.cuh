@@ -109,6 +109,7 @@ struct cspb_ctx {
     std::string err;
     int64_t launches = 0;
     int sm_count = 148;
+    int wave_units = 0;  // resident warps of the scoring kernel over the whole GPU (cspb_wave_units)
 
     // refine state
     bool refine_ready = false;
@@ -163,6 +164,7 @@ struct cspb_ctx {
 };
 
 int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...);
+extern "C" int cspb_wave_units(cspb_ctx *ctx);
 // event bracket helpers (no-ops unless profiling is enabled)
 void prof_begin(cspb_ctx *ctx, int kind, int64_t units);
 void prof_end(cspb_ctx *ctx);

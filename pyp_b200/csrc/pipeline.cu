@@ -23,10 +23,10 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     if (n_images == 0) return 0;
     // per-projection work does not depend on the batching (the whitening curve is estimated on the
     // first min(n, 4096) images whatever the chunking), so the results equal those of the staged calls
-    // batch schedule: whole waves of the scorer (W = SMs x 8 CTAs x 4 units) and growing — W, 2W, 4W,
+    // batch schedule: whole waves of the scorer (W = SMs x resident CTAs x 4 units, cspb_wave_units) and growing — W, 2W, 4W,
     // ... — so that the first batch is on the device after a short copy while the later, larger ones
     // lose nothing to wave quantisation; bounded by ~6 GB of staging per buffer
-    const long long W = (long long)ctx->sm_count * 32;
+    const long long W = cspb_wave_units(ctx);
     long long cap = (long long)(((size_t)6 << 30) / ((size_t)n * n * sizeof(float)));
     if (cap > 4 * W) cap = 4 * W;
     if (cap < 1) cap = 1;

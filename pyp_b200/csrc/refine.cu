@@ -701,6 +701,20 @@ extern "C" int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg) 
     return 0;
 }
 
+// units (warps) of the scoring kernel that are resident at once = one full wave over the GPU
+extern "C" int cspb_wave_units(cspb_ctx *ctx) {
+    if (!ctx) return CSPB_E_ARG;
+    if (ctx->wave_units <= 0) {
+        int ctas = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, score_kernel<4, false, false>, 128, 0) != cudaSuccess || ctas <= 0) {
+            cudaGetLastError();
+            ctas = 6;
+        }
+        ctx->wave_units = ctx->sm_count * ctas * 4;
+    }
+    return ctx->wave_units;
+}
+
 extern "C" int cspb_band_counts(const cspb_ctx *ctx, int *n_band, int *n_slots) {
     if (!ctx || !ctx->refine_ready) return CSPB_E_STATE;
     if (n_band) *n_band = ctx->plan.n_band;

@@ -351,6 +351,11 @@ class Engine:
         self._ck(self._l.cspb_ctf_image(self._h, ptr(row), int(n), ptr(out)))
         return out
 
+    @property
+    def wave_units(self):
+        """Units of the scoring kernel resident at once on this GPU (one full wave)."""
+        return int(self._l.cspb_wave_units(self._h))
+
     def gather_peak(self, window_bytes, per_cta=False):
         """GB/s of random 32-byte gathers from a window (roofline denominator of the scorer)."""
         g = C.c_float(0)
