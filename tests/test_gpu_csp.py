@@ -9,6 +9,7 @@ from pyp_b200 import synth
 pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-4
+_STACKS = {}
 
 
 def _case(engine, oracle, n=64, n_part=6, px=1.6, snr=0.3, tilt_angles=(-45, -30, -15, 0, 15, 30, 45)):
@@ -21,6 +22,7 @@ def _case(engine, oracle, n=64, n_part=6, px=1.6, snr=0.3, tilt_angles=(-45, -30
     engine.refine_configure(cfg)
     engine.set_reference(vol)
     engine.load_images(stack)
+    _STACKS["stack"] = stack
     ocfg = oracle.refine_cfg_from(cfg)
     curve = oracle.noise_curve(stack, ocfg)
     specs = oracle.prepare_images(stack, ocfg, curve)
@@ -154,3 +156,39 @@ def test_csp_extract_matches_numpy(engine):
             raw[np.ix_(my, mx)] = imgs[t][np.ix_(ys[my], xs[mx])]
         want = raw.reshape(box // binning, binning, box // binning, binning).mean(axis=(1, 3))
         assert np.abs(got[k] - want).max() < 1e-5, k
+
+
+def test_csp_edge_cases(engine, oracle):
+    """empty selections, windows that exclude everything, single-projection entities"""
+    rows, particles, tilts, specs, ref, ocfg = _case(engine, oracle, n_part=3, tilt_angles=(-20, 0, 20))
+    ccfg = engine.csp_defaults(5)
+    ccfg.window_max, ccfg.iterations = -1, 2
+    # no entity in range: nothing changes, nothing is scored
+    r, p, t, ne = engine.csp_run(rows, particles, tilts, ccfg, first=7, last=9)
+    assert ne == 0 and r.tobytes() == rows.tobytes() and p.tobytes() == particles.tobytes()
+    # a window that excludes every exposure: entities are only re-scored (2 evaluations per projection)
+    ccfg.window_min, ccfg.window_max = 50, 60
+    got = engine.csp_run(rows, particles, tilts, ccfg)
+    want = oracle.csp_run(ref, specs, rows, particles, tilts, ocfg, oracle.csp_cfg_from(ccfg), 0, -1)
+    assert got[3] == want[3] == 2 * rows.size
+    for k in ("psi", "theta", "phi", "shift_x"):
+        assert np.array_equal(got[1][k], particles[k])
+    assert np.allclose(got[0]["score"], want[0]["score"], rtol=SCORE_RTOL)
+    # one projection per entity (a particle seen on a single tilt) still refines and matches the oracle
+    ccfg.window_min, ccfg.window_max, ccfg.iterations = 0, -1, 3
+    one = rows["tind"] == 1
+    engine.load_images(np.ascontiguousarray(_stack_of(engine, rows, one)))
+    sub_rows = rows[one].copy()
+    got = engine.csp_run(sub_rows, particles, tilts, ccfg)
+    want = oracle.csp_run(ref, specs[one], sub_rows, particles, tilts, ocfg, oracle.csp_cfg_from(ccfg), 0, -1)
+    assert got[3] == want[3] == sub_rows.size * (3 * 16 + 2)
+    rel = np.abs(got[0]["score"] - want[0]["score"]) / np.abs(want[0]["score"])
+    assert rel.max() <= 5 * SCORE_RTOL
+    # zero rows
+    engine.load_images(np.zeros((0, 64, 64), np.float32))
+    r, p, t, ne = engine.csp_run(rows[:0], particles, tilts, ccfg)
+    assert ne == 0 and r.size == 0
+
+
+def _stack_of(engine, rows, mask):
+    return _STACKS["stack"][mask]
