@@ -173,8 +173,10 @@ __global__ void csp_candidates_kernel(const OptState *__restrict__ st, const Csp
     for (int m = 0; m < OPT_NP; ++m) params[(long long)idx * 6 + m] = x[m];
 }
 
-// every (list entry, candidate) -> pose of the scorer; units of <= PB candidates per entry
-__global__ void csp_expand_kernel(const CspEntry *__restrict__ list, int n_entries, int nc, int PB, CspTables T, int kind,
+// every (list entry, candidate) -> pose of the scorer; units of <= PB candidates per entry.  The last
+// nS candidates vary pure shifts only (same rotation and CTF as the centre): they form "shared" units
+// scored from one gather.  Unit layout by class as in opt.cuh: [A full][A tail][S full][S tail].
+__global__ void csp_expand_kernel(const CspEntry *__restrict__ list, int n_entries, int nc, int nS, int PB, CspTables T, int kind,
                                   const float *__restrict__ params, float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)n_entries * nc) return;
@@ -185,16 +187,20 @@ __global__ void csp_expand_kernel(const CspEntry *__restrict__ list, int n_entri
     float pose[6];
     csp_member_pose(T, kind, en.row, x, pose);
     for (int m = 0; m < 6; ++m) poses6[idx * 6 + m] = pose[m];
-    if (c % PB == 0) {
-        // count-class layout (launch_score_classes): full units first, one tail unit per entry after them
-        const int nfull = nc / PB, cu = c / PB;
+    const int nA = nc - nS;
+    const bool shared = c >= nA;
+    const int cl = shared ? c - nA : c, ncl = shared ? nS : nA;  // candidate index / count inside its class
+    if (cl % PB == 0) {
+        const int fullA = nA / PB, tailA = nA % PB ? 1 : 0, fullS = nS / PB;
+        const int nfull = ncl / PB, cu = cl / PB;
+        long long base = shared ? (long long)n_entries * (fullA + tailA) : 0;
         ScoreUnit un;
         un.image = en.row;
         un.first_eval = (int)idx;
-        un.count = min(PB, nc - c);
-        un.pad_ = 0;
-        if (cu < nfull) units[(long long)j * nfull + cu] = un;
-        else units[(long long)n_entries * nfull + j] = un;
+        un.count = min(PB, ncl - cl);
+        un.pad_ = shared ? 1 : 0;
+        if (cu < nfull) units[base + (long long)j * nfull + cu] = un;
+        else units[base + (long long)n_entries * (shared ? fullS : fullA) + j] = un;
     }
 }
 
@@ -514,6 +520,13 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
     int n_free = 0;
     for (int m = 0; m < OPT_NP; ++m) n_free += (pl.free_mask >> m) & 1;
     const int NE = 1 + 2 * n_free, PB = 4;
+    // tilt shifts only move the projections in plane: their stencil evaluations share the centre's
+    // rotation -> one gather (measured +9 % in mode 6).  Particle shifts have the same property, but
+    // there the quad reuse of the plain units already removes the loads and the extra unit classes
+    // cost more than they save (measured -10 % in mode 5), so they stay plain.
+    const int shift_mask = pl.kind == 1 ? (pl.free_mask & 0x0C) : 0;
+    int nS = 0;
+    for (int m = 0; m < OPT_NP; ++m) nS += 2 * ((shift_mask >> m) & 1);
     const int iters = n_free > 0 && cfg->iterations > 0 ? cfg->iterations : 0;
     const int late = iters / 2 + 1;
     long long n_cand = 0;
@@ -533,7 +546,7 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
     RESERVE(ctx, ctx->d_out, (size_t)max_evals * sizeof(float4));
     RESERVE(ctx, b_params, (size_t)G * (max_nc + OPT_NL + 2) * 6 * sizeof(float));
     RESERVE(ctx, b_obj, (size_t)G * (max_nc + OPT_NL + 2) * sizeof(float4));
-    RESERVE(ctx, b_dummy, (size_t)G * ((NE + PB - 1) / PB + 1) * sizeof(ScoreUnit));
+    RESERVE(ctx, b_dummy, (size_t)G * ((NE + PB - 1) / PB + 3) * sizeof(ScoreUnit));
     RESERVE(ctx, b_best, (size_t)G * sizeof(CspBest));
     RESERVE(ctx, b_choice, (size_t)G * sizeof(int));
     OptState *st = ctx->d_opt.as<OptState>();
@@ -548,12 +561,12 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
     int64_t evals = 0;
 
     // evaluate `nc` candidates (params[g][c]) of every group over a list, objective -> obj[g][c]
-    auto evaluate = [&](const CspEntry *list, int n_entries, int nc, int use_all) -> int {
+    auto evaluate = [&](const CspEntry *list, int n_entries, int nc, int use_all, int n_shared = 0) -> int {
         if (n_entries > 0) {
             const long long tot = (long long)n_entries * nc;
-            csp_expand_kernel<<<ceil_div(tot, 256), 256, 0, ctx->stream>>>(list, n_entries, nc, PB, T, pl.kind, params, poses, units);
+            csp_expand_kernel<<<ceil_div(tot, 256), 256, 0, ctx->stream>>>(list, n_entries, nc, n_shared, PB, T, pl.kind, params, poses, units);
             KERNEL_CHECK(ctx);
-            int r = launch_score_classes(ctx, units, n_entries, nc, 0, PB, poses, d_ctf, out, ddef);
+            int r = launch_score_classes(ctx, units, n_entries, nc - n_shared, n_shared, PB, poses, d_ctf, out, ddef);
             if (r) return r;
             evals += tot;
         }
@@ -582,9 +595,9 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
         // local stage: refine3d's stencil / Newton / line-search optimiser in entity space
         float *params_ls = params + (size_t)G * NE * 6;
         for (int it = 0; it < iters; ++it) {
-            opt_stencil_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, 0, NE, PB, params, dummy);
+            opt_stencil_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, shift_mask, NE, PB, params, dummy);
             KERNEL_CHECK(ctx);
-            rc = evaluate(b_ls.as<CspEntry>(), n_search, NE, 0);
+            rc = evaluate(b_ls.as<CspEntry>(), n_search, NE, 0, nS);
             if (rc) return rc;
             opt_step_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, NE, obj, params_ls, dummy);
             KERNEL_CHECK(ctx);

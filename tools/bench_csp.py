@@ -39,9 +39,12 @@ def main():
         ccfg.iterations = 5
         eng.csp_run(start_rows, start_p if n_part <= 500 else particles, tilts, ccfg)  # warm-up
         eng.sync()
-        t0 = time.perf_counter()
-        r, p, t, n_ev = eng.csp_run(start_rows, start_p if n_part <= 500 else particles, tilts, ccfg)
-        dt = time.perf_counter() - t0
+        times = []
+        for _ in range(7):
+            t0 = time.perf_counter()
+            r, p, t, n_ev = eng.csp_run(start_rows, start_p if n_part <= 500 else particles, tilts, ccfg)
+            times.append(time.perf_counter() - t0)
+        dt = float(np.median(times))
         out.append({"mode": label, "projections": int(rows.size), "evals": n_ev, "seconds": dt, "scored_projections_per_s": n_ev / dt,
                     "n_band": eng.band_counts()[0]})
     print(json.dumps(out))
