@@ -213,6 +213,10 @@ def run_b200_arm(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # one process per GPU: stay on the GPU's NUMA node (pinned stack, copies)
+        from pyp_b200.dist import bind_to_gpu_numa_node
+
+        bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

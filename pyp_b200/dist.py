@@ -88,6 +88,28 @@ def gather_table(table, dst=0):
     return [b.numpy()[: c * item].view(table.dtype).copy() for b, c in zip(bufs, counts)]
 
 
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: run (and allocate pinned host memory) on the CPUs of the GPU's own NUMA
+    node, so that host->device copies do not cross the socket interconnect.  Uses NVML's ideal CPU
+    affinity of the device; silently does nothing when NVML or sched_setaffinity is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def _dist():
     import torch.distributed as dist
 
