@@ -122,3 +122,15 @@ def merge(paths):
         raise ValueError("No cistem binary file to merge.")
     rows = np.concatenate([read_parameters(p) for p in paths])
     return rows[np.argsort(rows["position_in_stack"], kind="stable")]
+
+
+def merge_with_film_id(paths):
+    """merge_all_binary_with_filmid (cistem_star_file.py:1495-1550): stack the per-film tables in list
+    order, IMAGE_IS_ACTIVE (which pyp re-uses as the film index) = position of the file in the list.
+    Rows stay packed; nothing goes through Python lists."""
+    parts = []
+    for film, p in enumerate(paths):
+        rows = read_parameters(p)
+        rows["image_is_active"] = film
+        parts.append(rows)
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=ROW_DTYPE)

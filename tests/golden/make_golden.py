@@ -22,6 +22,7 @@ What gets pinned:
       outputs of refine_ctf (frealign.py:3133-3154).
   rhref_cases.json (+ rhref_fsc.txt, rhref_res.txt) — high-resolution limits returned by
       pyp.postprocess.get_rhref (postprocess/core.py:16-55) for fixed, scheduled and FSC-driven settings.
+  merge_filmid_by_reference.npy — merge_all_binary_with_filmid over merge_{a,b}.cistem (cistem_star_file.py:1495-1550)
   csp_euler.npy — csp_euler_angles (geometry/core.py:1081-1217): tilt angle, axis, csp angles and
       3DAVG translation in; projection (psi, theta, phi, sx, sy) and the stored particle
       parameters (-ppsi, -ptheta, -pphi, px, py, pz) out.  Pins pyp_b200/csp_geometry.py.
@@ -113,6 +114,10 @@ def main():
     a.to_binary(os.path.join(HERE, "merge_a.cistem")), b.to_binary(os.path.join(HERE, "merge_b.cistem"))
     m = csf.Parameters.merge([os.path.join(HERE, "merge_a.cistem"), os.path.join(HERE, "merge_b.cistem")], [])
     m.to_binary(os.path.join(HERE, "merge_ab.cistem"))
+
+    # per-film merge with film ids (cistem_star_file.py:1495-1550)
+    mf = csf.merge_all_binary_with_filmid([os.path.join(HERE, "merge_a.cistem"), os.path.join(HERE, "merge_b.cistem")])
+    np.save(os.path.join(HERE, "merge_filmid_by_reference.npy"), np.asarray(mf, dtype=np.float64))
 
     from pyp.inout.image import mrc
 

@@ -165,3 +165,12 @@ def test_star_tables_round_trip_and_reference_merge():
         assert np.array_equal(merged_ref[:, k].astype(rows.dtype[name]), rows[name]), name
     back = np.concatenate([star.read_star(os.path.join(G, "rows_a.star")), star.read_star(os.path.join(G, "rows_b.star"))])
     assert back.tobytes() == rows.tobytes()
+
+
+def test_merge_with_film_id_matches_reference():
+    want = np.load(os.path.join(G, "merge_filmid_by_reference.npy"))
+    got = cistem.merge_with_film_id([os.path.join(G, "merge_a.cistem"), os.path.join(G, "merge_b.cistem")])
+    assert got.size == want.shape[0] == 5 and list(got["image_is_active"]) == [0, 0, 0, 1, 1]
+    for k, name in enumerate(got.dtype.names):
+        assert np.array_equal(want[:, k].astype(got.dtype[name]), got[name]), name
+    assert cistem.merge_with_film_id([]).size == 0
