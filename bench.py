@@ -180,7 +180,7 @@ def run_reference_arm(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = a.cpu_sample or 24 * cores
+    sample = a.cpu_sample or 48 * cores  # ~10 s of CPU work per step
     rcfg, _ = workload_cfgs(a.box, a.pixel)
     for _ in range(max(0, min(a.warmup, 1))):
         cpu_reference_run(a.box, a.pixel, a.sym, cores, cores)
@@ -425,7 +425,7 @@ def run_b200_arm(a):
         line["e2e"] = e2e
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = a.cpu_sample or 24 * cores
+        sample = a.cpu_sample or 48 * cores  # ~10 s of CPU work per step
         r = cpu_reference_run(n, px, a.sym, sample, cores)
         line["cpu_baseline"] = {"value": r["evals_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{sample} particles of the same workload, one single-thread process per core, {r['seconds']:.1f} s",
