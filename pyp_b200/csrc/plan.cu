@@ -50,9 +50,14 @@ bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi) {
     const int32_t dummy = (int32_t)CSPB_DUMMY_I;  // i = 0x7FFF, j = 0
     const int n_rings = ring_max - ring_min + 1;
     int slot = 0;
-    for (int r0 = 0; r0 < n_rings; r0 += 4) {
+    // bands of 4 rings are formed from the OUTER end: if the ring count is not a multiple of 4 the
+    // partial band holds the few-sample innermost rings, not the ~300-sample outermost one (a partial
+    // band pads its missing rings to the band length: 5 % of all slots at 256 px otherwise)
+    const int rem = n_rings % 4;
+    for (int r0 = rem ? rem - 4 : 0; r0 < n_rings; r0 += 4) {
         size_t lmax = 0;
-        for (int k = 0; k < 4 && r0 + k < n_rings; ++k) lmax = std::max(lmax, rings[r0 + k].size());
+        for (int k = 0; k < 4; ++k)
+            if (r0 + k >= 0 && r0 + k < n_rings) lmax = std::max(lmax, rings[r0 + k].size());
         if (lmax == 0) continue;
         const int L = (int)((lmax + 7) / 8) * 8;
         BandDesc bd;
@@ -61,7 +66,8 @@ bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi) {
         bd.ring0 = ring_min + r0;
         bd.pad_ = 0;
         plan.slot_ij.resize(slot + 4 * L, dummy);
-        for (int k = 0; k < 4 && r0 + k < n_rings; ++k) {
+        for (int k = 0; k < 4; ++k) {
+            if (r0 + k < 0 || r0 + k >= n_rings) continue;
             const auto &r = rings[r0 + k];
             const int nk = (int)r.size();
             for (int m = 0; m < nk; ++m) {
