@@ -66,6 +66,8 @@ typedef struct cspb_ctx cspb_ctx;
 
 /* ------------------------------------------------------------------ lifecycle */
 int cspb_abi_version(void);
+/* Visible CUDA devices (0 when there is none): the front-ends map particle ranges to GPUs with it. */
+int cspb_device_count(void);
 /* Bind a context to CUDA device `device`. */
 int cspb_create(int device, cspb_ctx **out);
 int cspb_destroy(cspb_ctx *ctx);

@@ -91,6 +91,7 @@ class CspbError(RuntimeError):
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 _SIGNATURES = {
     "cspb_abi_version": (C.c_int, []),
+    "cspb_device_count": (C.c_int, []),
     "cspb_create": (_i, [_i, C.POINTER(_vp)]),
     "cspb_destroy": (_i, [_vp]),
     "cspb_last_error": (C.c_char_p, [_vp]),

@@ -61,9 +61,9 @@ def pick_device(first=1, count=1):
     n = int(os.environ.get("CSPB_NUM_DEVICES", "0"))
     if n <= 0:
         try:
-            import torch
+            from .._lib import lib  # the engine's own count: no framework import in the front-ends
 
-            n = torch.cuda.device_count()
+            n = int(lib().cspb_device_count())
         except Exception:
             n = 1
     n = max(1, n)

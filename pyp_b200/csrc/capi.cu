@@ -6,6 +6,17 @@
 
 static_assert(sizeof(cspb_row) == 128, "cspb_row must match the 128-byte .cistem row");
 
+// number of visible CUDA devices (0 without a driver / GPU); lets the front-ends spread their
+// particle ranges over the GPUs without importing a framework
+extern "C" int cspb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 extern "C" int cspb_abi_version(void) { return CSPB_ABI_VERSION; }
 
 extern "C" int cspb_create(int device, cspb_ctx **out) {
