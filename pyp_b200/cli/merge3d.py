@@ -4,6 +4,7 @@ dump seed 1, dump seed 2, N.  Sums the dumps, computes the resolution statistics
 optimal filter, inverse-transforms, corrects the gridding and writes the three maps.  The log
 ends with the table pyp parses (frealign.py:2558-2567)."""
 import sys
+import time
 
 from ..formats import dump, mrc, statistics
 from .local_merge3d import sum_dumps
@@ -23,16 +24,22 @@ def run(p, out=sys.stdout):
 
     if p["count"] < 1:
         raise ValueError("need at least one dump file")
+    t = [time.perf_counter()]
     eng = Engine(pick_device())
+    t.append(time.perf_counter())
     meta, total = sum_dumps(eng, dump.seed_paths(p["seed1"], p["count"]), dump.seed_paths(p["seed2"], p["count"]))
+    t.append(time.perf_counter())
     vol, h1, h2, st = eng.recon_finalize(p["molecular_mass"], p["outer_radius"])
+    t.append(time.perf_counter())
     mrc.write(p["half1"], h1, meta["pixel_size"])
     mrc.write(p["half2"], h2, meta["pixel_size"])
     mrc.write(p["filtered"], vol, meta["pixel_size"])
     with open(p["statistics"], "w") as f:
         f.write(statistics.HEADER + statistics.format_table(st) + "\n")
+    t.append(time.perf_counter())
     out.write(banner("Merge3D"))
-    out.write(f"\nMerged {p['count']} dump pairs, {total} particles, box {meta['box']}, pixel {meta['pixel_size']}\n\n")
+    out.write(f"\nMerged {p['count']} dump pairs, {total} particles, box {meta['box']}, pixel {meta['pixel_size']}\n")
+    out.write(f"timing: context {t[1] - t[0]:.2f} s, read + sum dumps {t[2] - t[1]:.2f} s, finalise {t[3] - t[2]:.2f} s, write maps {t[4] - t[3]:.2f} s\n\n")
     out.write(statistics.merge3d_log(st))
     eng.close()
     return st

@@ -76,6 +76,7 @@ def main():
     log = open(f"{d}/merge.log").read()
     assert rc == 0 and "Merge3D: Normal termination" in log, log[-2000:]
     out["merge3d_seconds"] = dt
+    out["merge3d_timing"] = [ln for ln in log.splitlines() if ln.startswith("timing:")]
     st = statistics.read_statistics(f"{d}/ds_r01_02_statistics.txt")
     fsc = st[:, 3]
     below = np.nonzero(fsc[1:] < 0.143)[0]
