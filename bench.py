@@ -328,7 +328,12 @@ def run_b200_arm(a):
     # ---- end to end through the host-buffer API (pinned stack, H2D + D2H inside the timed region)
     e2e = None
     if not a.no_e2e:
-        host_stack = torch.empty((P, n, n), dtype=torch.float32, pin_memory=True)
+        pinned = True
+        try:
+            host_stack = torch.empty((P, n, n), dtype=torch.float32, pin_memory=True)
+        except RuntimeError:  # no room for a pinned stack on this host: pageable memory (slower copies), said in the JSON
+            pinned = False
+            host_stack = torch.empty((P, n, n), dtype=torch.float32)
         host_stack.copy_(stack)
         torch.cuda.synchronize()
         hs = host_stack.numpy()
@@ -374,7 +379,8 @@ def run_b200_arm(a):
         h2d = P * n * n * 4 + P * 128                  # every projection is uploaded once (cspb_refine_reconstruct)
         d2h = P * 128 + (3 * n * n * n * 4 if rank == 0 else 0)
         e2e = {"value": world * ev2 / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": k2, "ms_per_step": 1e3 * dt / k2, "ms_each_step_rank0": per_step, "clocks": clocks2}
+               "steps": k2, "ms_per_step": 1e3 * dt / k2, "ms_each_step_rank0": per_step, "clocks": clocks2,
+               "host_memory": "pinned" if pinned else "pageable"}
         del host_stack
 
     if rank != 0:
