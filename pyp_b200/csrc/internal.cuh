@@ -37,15 +37,17 @@ struct DevBuf {
 
 // ---------------------------------------------------------------- band plan
 // The half-plane lattice samples inside the scoring band, re-ordered into "polar patches":
-// ring-bands of 4 consecutive rings; inside a band slot = base + a*4 + k holds the a-th sample
-// (by angle) of ring ring0+k, so a warp's 32 slots are an 8(angle) x 4(ring) patch and lane%4
-// is the ring offset.  Rings are padded to a common length with dummy slots.
+// ring-bands of 4 rings; inside a band slot = base + a*4 + k holds the a-th sample (by angle) of
+// the band's k-th ring, so a warp's 32 slots are an 8(angle) x 4(ring) patch and lane%4 is the
+// ring offset.  Rings are padded to a common length with dummy slots; the 4 rings of a band are
+// neighbours in sample COUNT (rings sorted by count, a local permutation of the radial order:
+// lattice ring counts fluctuate by +-10 around pi*r), which halves the padding of radial bands.
 #define CSPB_DUMMY_I 0x7FFF
 struct BandDesc {
     int slot_start;  // multiple of 32
     int n_iter;      // slots/32
-    int ring0;       // first ring of the band (4 rings per band)
-    int pad_;
+    int rings01;     // ring index of track 0 (low 16 bits) and track 1 (high 16 bits)
+    int rings23;     // tracks 2 and 3
 };
 struct BandPlan {
     int n = 0;

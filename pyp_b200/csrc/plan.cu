@@ -8,6 +8,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "internal.cuh"
 
 int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...) {
@@ -50,25 +52,34 @@ bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi) {
     const int32_t dummy = (int32_t)CSPB_DUMMY_I;  // i = 0x7FFF, j = 0
     const int n_rings = ring_max - ring_min + 1;
     int slot = 0;
-    // bands of 4 rings are formed from the OUTER end: if the ring count is not a multiple of 4 the
-    // partial band holds the few-sample innermost rings, not the ~300-sample outermost one (a partial
-    // band pads its missing rings to the band length: 5 % of all slots at 256 px otherwise)
+    // Bands hold 4 rings of similar sample count: rings are ordered by count (ties by radius) — the
+    // lattice ring counts scatter by about +-10 around pi*r, so radially consecutive rings pad each
+    // other by 10 % at 256 px, count neighbours by 5 % (what is left is the rounding to 8 angles).
+    // CSPB_BAND_ORDER=radial keeps the radial order (A/B measurements).  If the ring count is not a
+    // multiple of 4 the partial band holds the few-sample rings at the head of the order.
+    std::vector<int> order(n_rings);
+    for (int k = 0; k < n_rings; ++k) order[k] = k;
+    const char *env = getenv("CSPB_BAND_ORDER");
+    if (!(env && strcmp(env, "radial") == 0))
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rings[a].size() < rings[b].size(); });
     const int rem = n_rings % 4;
     for (int r0 = rem ? rem - 4 : 0; r0 < n_rings; r0 += 4) {
         size_t lmax = 0;
         for (int k = 0; k < 4; ++k)
-            if (r0 + k >= 0 && r0 + k < n_rings) lmax = std::max(lmax, rings[r0 + k].size());
+            if (r0 + k >= 0) lmax = std::max(lmax, rings[order[r0 + k]].size());
         if (lmax == 0) continue;
         const int L = (int)((lmax + 7) / 8) * 8;
         BandDesc bd;
         bd.slot_start = slot;
         bd.n_iter = 4 * L / 32;
-        bd.ring0 = ring_min + r0;
-        bd.pad_ = 0;
+        int rid[4];
+        for (int k = 0; k < 4; ++k) rid[k] = ring_min + (r0 + k >= 0 ? order[r0 + k] : 0);
+        bd.rings01 = rid[0] | (rid[1] << 16);
+        bd.rings23 = rid[2] | (rid[3] << 16);
         plan.slot_ij.resize(slot + 4 * L, dummy);
         for (int k = 0; k < 4; ++k) {
-            if (r0 + k < 0 || r0 + k >= n_rings) continue;
-            const auto &r = rings[r0 + k];
+            if (r0 + k < 0) continue;
+            const auto &r = rings[order[r0 + k]];
             const int nk = (int)r.size();
             for (int m = 0; m < nk; ++m) {
                 const int a = (int)(((long long)m * L) / nk);  // spread dummies evenly along the arc

@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
                 }
             }
         }
-        const int ring = bd.ring0 + (lane & 3);
+        const int rpair = (lane & 2) ? bd.rings23 : bd.rings01;
+        const int ring = (lane & 1) ? (rpair >> 16) : (rpair & 0xFFFF);
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
             float v = accX[p];
