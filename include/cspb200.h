@@ -118,7 +118,10 @@ typedef struct cspb_refine_cfg {
     int32_t whiten;            /* 1 = whiten with the stack's noise power curve (cisTEM default) */
     int32_t symmetry_order;    /* number of symmetry matrices handed to cspb_set_symmetry (1 = C1) */
     int32_t local_iterations;  /* batched local-optimiser iterations (ours; default 8)         */
-    int32_t reserved[7];
+    int32_t use_priors;        /* prompt 7: restrain X/Y shifts to the data set's distribution     */
+    float prior_mean_x, prior_mean_y; /* Angstrom: row 0 of <name>_stat.cistem (particle_cspt.py:1009-1016) */
+    float prior_var_x, prior_var_y;   /* Angstrom^2: row 1; <= 0 leaves that shift unrestrained     */
+    int32_t reserved[2];
 } cspb_refine_cfg;
 
 /* Fill a config with the defaults pyp passes for a plain local refinement. */

@@ -483,8 +483,24 @@ static float line_step(float f0, const float *fl) {
 
 /* refine one starting pose x[6] in place; returns the final score (x100) and its band sums in o4.
    The better of {refined, start} is kept.  *evals is incremented per objective evaluation. */
+/* Shift restraint of the local refinement (refine3d prompt 7; SEMANTICS.md §7b), in CC units:
+ * (sigma^2 / N_mask) * sum_{k in x,y} (p_k - mean_k)^2 / (2 var_k), sigma = the row's SIGMA column,
+ * N_mask = pixels inside the mask radius.  Angles are not restrained (cisTEM restrains the shifts only). */
+static float prior_pen(const orc_refine_cfg *cfg, const orc_row *row, const float *x) {
+    if (!cfg->use_priors) return 0.f;
+    const float rad = cfg->mask_radius / cfg->pixel_size;
+    float nmask = 3.14159265f * rad * rad;
+    if (nmask < 1.f) nmask = 1.f;
+    const float lam = row->sigma * row->sigma / nmask;
+    const float wx = cfg->prior_var_x > 0.f ? 0.5f / cfg->prior_var_x : 0.f;
+    const float wy = cfg->prior_var_y > 0.f ? 0.5f / cfg->prior_var_y : 0.f;
+    const float dx = x[3] - cfg->prior_mean_x, dy = x[4] - cfg->prior_mean_y;
+    return lam * (wx * dx * dx + wy * dy * dy);
+}
+
+/* returns the score (100 CC) of the pose kept; *obj_out = CC - restraint of that pose */
 static float refine_one(const orc_ref *r, const float *spec, const orc_row *row, float *x, const int *freem,
-                        const orc_refine_cfg *cfg, float *o4, long long *evals, float coarse) {
+                        const orc_refine_cfg *cfg, float *o4, long long *evals, float coarse, float *obj_out) {
     const int n = cfg->box;
     float lo, hi;
     orc_band_limits(cfg, &lo, &hi);
@@ -501,23 +517,23 @@ static float refine_one(const orc_ref *r, const float *spec, const orc_row *row,
     float d[NP], q[NP];
     const float x_start[NP] = {x[0], x[1], x[2], x[3], x[4], x[5]};
     for (int it = 0; it < iters; ++it) {
-        const float f0 = orc_score(r, spec, row, x, cfg, o4) * 0.01f;
+        const float f0 = orc_score(r, spec, row, x, cfg, o4) * 0.01f - prior_pen(cfg, row, x);
         (*evals)++;
         for (int m = 0; m < NP; ++m) {
             d[m] = 0.f;
             if (!freem[m]) continue;
             memcpy(q, x, sizeof q);
             q[m] = x[m] + h[m];
-            const float fp = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+            const float fp = orc_score(r, spec, row, q, cfg, o4) * 0.01f - prior_pen(cfg, row, q);
             q[m] = x[m] - h[m];
-            const float fm = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+            const float fm = orc_score(r, spec, row, q, cfg, o4) * 0.01f - prior_pen(cfg, row, q);
             (*evals) += 2;
             d[m] = newton_step(f0, fp, fm, h[m]);
         }
         float fl[NL];
         for (int l = 0; l < NL; ++l) {
             for (int m = 0; m < NP; ++m) q[m] = x[m] + LS_T[l] * d[m];
-            fl[l] = orc_score(r, spec, row, q, cfg, o4) * 0.01f;
+            fl[l] = orc_score(r, spec, row, q, cfg, o4) * 0.01f - prior_pen(cfg, row, q);
             (*evals)++;
         }
         const float t = line_step(f0, fl);
@@ -530,7 +546,10 @@ static float refine_one(const orc_ref *r, const float *spec, const orc_row *row,
     float sc = orc_score(r, spec, row, x, cfg, o4);
     const float sc_start = orc_score(r, spec, row, x_start, cfg, o4s);
     (*evals) += 2;
-    if (sc < sc_start) { memcpy(x, x_start, sizeof x_start); memcpy(o4, o4s, sizeof o4s); sc = sc_start; }
+    float obj = sc * 0.01f - prior_pen(cfg, row, x);
+    const float obj_start = sc_start * 0.01f - prior_pen(cfg, row, x_start);
+    if (obj < obj_start) { memcpy(x, x_start, sizeof x_start); memcpy(o4, o4s, sizeof o4s); sc = sc_start; obj = obj_start; }
+    if (obj_out) *obj_out = obj;
     return sc;
 }
 
@@ -557,7 +576,7 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
         float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f};
         float o4[4];
         long long ev = 0;
-        const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, 1.f);
+        const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, 1.f, NULL);
         evals += ev;
         write_row(row, x, sc, o4, nband, cfg->refine_defocus);
     }
@@ -684,15 +703,16 @@ long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows,
         long long ev = n_orient;
         /* refine every hit in all five pose parameters; keep the best */
         const int freem[NP] = {1, 1, 1, 1, 1, cfg->refine_defocus};
-        float bestsc = -1e30f, xb[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f}, ob[4] = {0, 0, 0, 0};
+        float bestsc = -1e30f, bestobj = -1e30f, xb[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f}, ob[4] = {0, 0, 0, 0};
         for (int t = 0; t < K; ++t) {
             float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f}, o4[4];
             if (top[t].orient >= 0) {
                 x[0] = angles3[3 * top[t].orient]; x[1] = angles3[3 * top[t].orient + 1]; x[2] = angles3[3 * top[t].orient + 2];
                 x[3] = top[t].sx; x[4] = top[t].sy;
             }
-            const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, hi / r_s);
-            if (sc > bestsc) { bestsc = sc; memcpy(xb, x, sizeof xb); memcpy(ob, o4, sizeof ob); }
+            float obj;
+            const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, hi / r_s, &obj);
+            if (obj > bestobj) { bestobj = obj; bestsc = sc; memcpy(xb, x, sizeof xb); memcpy(ob, o4, sizeof ob); }
         }
         evals += ev;
         write_row(row, xb, bestsc, ob, nband, cfg->refine_defocus);

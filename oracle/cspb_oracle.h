@@ -48,6 +48,10 @@ typedef struct orc_refine_cfg {
     /* global search (prompts 24-28, 36) */
     float search_high_res, search_range_x, search_range_y;
     int32_t best_matches, global_search;
+    /* shift restraint (prompt 7 "use priors"; SEMANTICS.md §7b): mean / variance of X_SHIFT, Y_SHIFT in
+     * Angstrom (rows 0 / 1 of <name>_stat.cistem, particle_cspt.py:1009-1016); variance <= 0: unrestrained */
+    int32_t use_priors;
+    float prior_mean_x, prior_mean_y, prior_var_x, prior_var_y;
 } orc_refine_cfg;
 
 typedef struct orc_recon_cfg {

@@ -40,6 +40,8 @@ class RefineCfg(C.Structure):
         ("whiten", C.c_int32), ("local_iterations", C.c_int32),
         ("search_high_res", C.c_float), ("search_range_x", C.c_float), ("search_range_y", C.c_float),
         ("best_matches", C.c_int32), ("global_search", C.c_int32),
+        ("use_priors", C.c_int32), ("prior_mean_x", C.c_float), ("prior_mean_y", C.c_float),
+        ("prior_var_x", C.c_float), ("prior_var_y", C.c_float),
     ]
 
 
@@ -82,7 +84,7 @@ def refine_cfg_from(gpu_cfg) -> RefineCfg:
     """Copy the shared fields of a pyp_b200 RefineCfg (or any object with those attributes)."""
     o = RefineCfg()
     for name, _ in RefineCfg._fields_:
-        setattr(o, name, getattr(gpu_cfg, name))
+        setattr(o, name, getattr(gpu_cfg, name, 0))
     return o
 
 

@@ -49,7 +49,9 @@ class RefineCfg(C.Structure):
         ("refine_x", C.c_int32), ("refine_y", C.c_int32), ("refine_defocus", C.c_int32),
         ("apply_mask", C.c_int32), ("normalize", C.c_int32), ("invert_contrast", C.c_int32),
         ("whiten", C.c_int32), ("symmetry_order", C.c_int32), ("local_iterations", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("use_priors", C.c_int32), ("prior_mean_x", C.c_float), ("prior_mean_y", C.c_float),
+        ("prior_var_x", C.c_float), ("prior_var_y", C.c_float),
+        ("reserved", C.c_int32 * 2),
     ]
 
 

@@ -72,6 +72,22 @@ def select_rows(rows, first, last):
     return sel[np.argsort(pos[sel], kind="stable")]
 
 
+def shift_prior(p, rows_all):
+    """Mean / variance of X_SHIFT, Y_SHIFT (Angstrom) for the shift restraint of answer 7: rows 0 / 1
+    of the global statistics file (`<name>_stat.cistem` = np.mean / np.var of the merged used rows,
+    src/pyp/refine/csp/particle_cspt.py:1009-1016; handed over at frealign.py:3827-3831) when it
+    exists, else the same statistics of the input parameter file."""
+    stat = p["global_stat"]
+    if stat and stat != "null" and os.path.exists(stat):
+        st = cistem.read_parameters(stat)
+        if st.size >= 2:
+            return (float(st["x_shift"][0]), float(st["y_shift"][0]), float(st["x_shift"][1]), float(st["y_shift"][1]))
+    if rows_all.size == 0:
+        return 0.0, 0.0, 0.0, 0.0
+    x, y = rows_all["x_shift"].astype(np.float64), rows_all["y_shift"].astype(np.float64)
+    return float(x.mean()), float(y.mean()), float(x.var()), float(y.var())
+
+
 def build_cfg(p, box):
     from ..engine import Engine
 
@@ -114,6 +130,9 @@ def run(p, out=sys.stdout):
         raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
     eng = Engine(pick_device(first, last - first + 1))
     cfg = build_cfg(p, box)
+    if p["use_priors"]:
+        cfg.use_priors = 1
+        cfg.prior_mean_x, cfg.prior_mean_y, cfg.prior_var_x, cfg.prior_var_y = shift_prior(p, rows_all)
     eng.refine_configure(cfg)
     if p["use_statistics"] and os.path.exists(p["statistics"]) and os.path.getsize(p["statistics"]) > 0:
         st = statistics.read_statistics(p["statistics"])
@@ -141,7 +160,8 @@ def run(p, out=sys.stdout):
         out.write(f"Mean score {float(refined['score'].mean()):.4f}, mean change {float(changes['score'].mean()):+.4f}, "
                   f"{n_evals} projections scored in {dt:.2f} s\n")
     if p["use_priors"]:
-        out.write("Note: priors (answer 7) are accepted but not applied by cspb200\n")
+        out.write(f"Shift restraint: mean ({cfg.prior_mean_x:.3f}, {cfg.prior_mean_y:.3f}) A, "
+                  f"variance ({cfg.prior_var_x:.3f}, {cfg.prior_var_y:.3f}) A^2\n")
     if p["mask_2d"][3] > 0:
         out.write("Note: the 2-D focus mask (answers 29-32) is accepted but not applied by cspb200\n")
     out.write("\nRefine3D: Normal termination\n")

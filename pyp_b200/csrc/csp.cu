@@ -143,7 +143,7 @@ __global__ void csp_init_kernel(const CspGroup *__restrict__ groups, int n_group
         s.x[0] = t.angle; s.x[1] = t.axis; s.x[2] = t.shift_x; s.x[3] = t.shift_y; s.x[4] = 0.f; s.x[5] = 0.f;
     }
     for (int m = 0; m < OPT_NP; ++m) { s.h[m] = pl.h[m]; s.d[m] = 0.f; s.x0[m] = s.x[m]; }
-    s.f = 0.f; s.pad_[0] = s.pad_[1] = s.pad_[2] = 0.f;
+    s.f = 0.f; s.lam = 0.f; s.pad_[0] = s.pad_[1] = 0.f;
     st[g] = s;
 }
 
@@ -599,13 +599,13 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
             KERNEL_CHECK(ctx);
             rc = evaluate(b_ls.as<CspEntry>(), n_search, NE, 0, nS);
             if (rc) return rc;
-            opt_step_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, NE, obj, params_ls, dummy);
+            opt_step_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, 1, pl.free_mask, NE, obj, params_ls, dummy, OptPrior{});
             KERNEL_CHECK(ctx);
             // the line-search candidates are evaluated from the head of the params buffer
             CU_TRY(ctx, cudaMemcpyAsync(params, params_ls, (size_t)G * OPT_NL * 6 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
             rc = evaluate(b_ls.as<CspEntry>(), n_search, OPT_NL, 0);
             if (rc) return rc;
-            opt_select_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, obj, it + 1 >= late ? 0.6f : 1.f);
+            opt_select_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, obj, it + 1 >= late ? 0.6f : 1.f, OptPrior{});
             KERNEL_CHECK(ctx);
             csp_clamp_kernel<<<gg, 128, 0, ctx->stream>>>(st, G, pl);
             KERNEL_CHECK(ctx);

@@ -15,9 +15,22 @@ struct OptState {
     float h[OPT_NP];
     float d[OPT_NP];
     float x0[OPT_NP];  // starting pose
-    float f;           // CC at the current centre
-    float pad_[3];
+    float f;           // objective at the current centre
+    float lam;         // shift-restraint scale sigma^2 / N_mask of the state's image (0 without priors)
+    float pad_[2];
 };
+
+// Shift restraint (refine3d prompt 7, oracle/SEMANTICS.md §7b): objective = CC - lam * (wx (sx - mx)^2 +
+// wy (sy - my)^2), w = 1 / (2 var).  `on` = 0 (csp, refine3d without priors): the objective is the CC.
+struct OptPrior {
+    int on;
+    float mx, my, wx, wy;
+};
+__device__ __forceinline__ float prior_pen(const OptPrior pr, float lam, float sx, float sy) {
+    if (!pr.on) return 0.f;
+    const float dx = sx - pr.mx, dy = sy - pr.my;
+    return lam * (pr.wx * dx * dx + pr.wy * dy * dy);
+}
 
 __device__ __forceinline__ float wrap360(float a) {
     a = fmodf(a, 360.f);
@@ -119,18 +132,21 @@ __device__ __forceinline__ float line_step(float f0, const float *fl) {
 
 // consume stencil scores, propose the Newton direction, emit line-search poses
 __global__ void opt_step_kernel(OptState *__restrict__ st, int n, int K, int free_mask, int NE, const float4 *__restrict__ sc,
-                                float *__restrict__ poses6_ls, ScoreUnit *__restrict__ units_ls) {
+                                float *__restrict__ poses6_ls, ScoreUnit *__restrict__ units_ls, const OptPrior pr) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     OptState s = st[k];
     const float4 *v = sc + (long long)k * NE;
-    const float f0 = cc_of(v[0]);
+    const float f0 = cc_of(v[0]) - prior_pen(pr, s.lam, s.x[3], s.x[4]);
     int e = 1;
     for (int m = 0; m < OPT_NP; ++m) s.d[m] = 0.f;
     for (int o = 0; o < OPT_NP; ++o) {
         const int m = OPT_ORDER[o];
         if (!((free_mask >> m) & 1)) continue;
-        s.d[m] = newton_step(f0, cc_of(v[e]), cc_of(v[e + 1]), s.h[m]);
+        const float hx = m == 3 ? s.h[m] : 0.f, hy = m == 4 ? s.h[m] : 0.f;
+        const float fp = cc_of(v[e]) - prior_pen(pr, s.lam, s.x[3] + hx, s.x[4] + hy);
+        const float fm = cc_of(v[e + 1]) - prior_pen(pr, s.lam, s.x[3] - hx, s.x[4] - hy);
+        s.d[m] = newton_step(f0, fp, fm, s.h[m]);
         e += 2;
     }
     s.f = f0;
@@ -144,12 +160,15 @@ __global__ void opt_step_kernel(OptState *__restrict__ st, int n, int K, int fre
     units_ls[k] = un;
 }
 
-__global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4 *__restrict__ sc_ls, float shrink) {
+__global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4 *__restrict__ sc_ls, float shrink,
+                                  const OptPrior pr) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     OptState s = st[k];
     float fl[OPT_NL];
-    for (int l = 0; l < OPT_NL; ++l) fl[l] = cc_of(sc_ls[(long long)k * OPT_NL + l]);
+    const float tl[OPT_NL] = {0.5f, 1.f, 2.f};
+    for (int l = 0; l < OPT_NL; ++l)
+        fl[l] = cc_of(sc_ls[(long long)k * OPT_NL + l]) - prior_pen(pr, s.lam, s.x[3] + tl[l] * s.d[3], s.x[4] + tl[l] * s.d[4]);
     const float t = line_step(s.f, fl);
     for (int m = 0; m < OPT_NP; ++m) s.x[m] += t * s.d[m];
     for (int m = 0; m < OPT_NP; ++m) s.h[m] *= shrink;

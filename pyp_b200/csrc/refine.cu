@@ -440,7 +440,7 @@ struct SearchHit {
 // state k belongs to image k / K.  With hits (global search) the state starts at candidate k % K.
 __global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n_states, int K, const SearchHit *__restrict__ hits,
                                 const float *__restrict__ angles3, OptState *__restrict__ st, float h_ang, float h_shift,
-                                float h_def) {
+                                float h_def, float lam_scale) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_states) return;
     const cspb_row row = rows[k / K];
@@ -458,7 +458,7 @@ __global__ void opt_init_kernel(const cspb_row *__restrict__ rows, int n_states,
     s.h[3] = s.h[4] = h_shift;
     s.h[5] = h_def;
     for (int m = 0; m < OPT_NP; ++m) { s.d[m] = 0.f; s.x0[m] = s.x[m]; }
-    s.f = 0.f; s.pad_[0] = s.pad_[1] = s.pad_[2] = 0.f;
+    s.f = 0.f; s.lam = lam_scale * row.sigma * row.sigma; s.pad_[0] = s.pad_[1] = 0.f;
     st[k] = s;
 }
 
@@ -480,12 +480,12 @@ __global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, i
 // the best score; ties keep the earlier candidate
 __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n_images, int K, const float4 *__restrict__ sc,
                                       int n_samples, int refine_defocus, cspb_row *__restrict__ rows,
-                                      cspb_row *__restrict__ changes) {
+                                      cspb_row *__restrict__ changes, const OptPrior pr) {
     const int img = blockIdx.x * blockDim.x + threadIdx.x;
     if (img >= n_images) return;
     cspb_row r = rows[img];
     const cspb_row old = r;
-    float best = -1e30f;
+    float best = -1e30f, best_obj = -1e30f;
     float4 vbest = make_float4(0.f, 0.f, 0.f, 0.f);
     float xb[OPT_NP] = {r.psi, r.theta, r.phi, r.x_shift, r.y_shift, 0.f};
     float start_score = 0.f;
@@ -495,10 +495,14 @@ __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n_ima
         float4 v = sc[2 * k];
         const float4 v0 = sc[2 * k + 1];
         const float *x = s.x;
-        if (100.f * cc_of(v) < 100.f * cc_of(v0)) { v = v0; x = s.x0; }  // never return a worse pose
+        // never return a worse pose (objective = score - shift restraint; the restraint is 0 without priors)
+        if (100.f * cc_of(v) - 100.f * prior_pen(pr, s.lam, s.x[3], s.x[4]) <
+            100.f * cc_of(v0) - 100.f * prior_pen(pr, s.lam, s.x0[3], s.x0[4])) { v = v0; x = s.x0; }
         if (c == 0) start_score = 100.f * cc_of(v0);
         const float f = 100.f * cc_of(v);
-        if (f > best) {
+        const float obj = cc_of(v) - prior_pen(pr, s.lam, x[3], x[4]);
+        if (obj > best_obj) {
+            best_obj = obj;
             best = f;
             vbest = v;
             for (int m = 0; m < OPT_NP; ++m) xb[m] = x[m];
@@ -1132,18 +1136,29 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     const float h_shift = coarse * 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
     const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
     const int g = ceil_div(ns, 128);
-    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, ns, K, d_hits, d_angles, st, h_ang, h_shift, h_def);
+    OptPrior pr{};
+    float lam_scale = 0.f;
+    if (c.use_priors) {
+        const float rad = c.mask_radius / c.pixel_size;
+        const float nmask = fmaxf(3.14159265f * rad * rad, 1.f);
+        lam_scale = 1.f / nmask;
+        pr.on = 1;
+        pr.mx = c.prior_mean_x; pr.my = c.prior_mean_y;
+        pr.wx = c.prior_var_x > 0.f ? 0.5f / c.prior_var_x : 0.f;
+        pr.wy = c.prior_var_y > 0.f ? 0.5f / c.prior_var_y : 0.f;
+    }
+    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, ns, K, d_hits, d_angles, st, h_ang, h_shift, h_def, lam_scale);
     KERNEL_CHECK(ctx);
     for (int it = 0; it < iters; ++it) {
         opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, shift_mask, NE, PB, ev, un);
         KERNEL_CHECK(ctx);
         int rc = launch_score_classes(ctx, un, ns, NE - nS, nS, PB, ev, d_ctf, out, ddef);
         if (rc) return rc;
-        opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, out, ev_ls, un_ls);
+        opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, out, ev_ls, un_ls, pr);
         KERNEL_CHECK(ctx);
         rc = launch_score(ctx, un_ls, ns, OPT_NL, ev_ls, d_ctf, out_ls, ddef, (int64_t)ns * OPT_NL, false);
         if (rc) return rc;
-        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, out_ls, it + 1 >= late ? 0.6f : 1.f);
+        opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, out_ls, it + 1 >= late ? 0.6f : 1.f, pr);
         KERNEL_CHECK(ctx);
         evals += (int64_t)ns * (NE + OPT_NL);
     }
@@ -1152,7 +1167,7 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     int rc = launch_score(ctx, un, ns, 2, ev, d_ctf, out, ddef, 2 * (int64_t)ns, false);
     if (rc) return rc;
     evals += 2 * (int64_t)ns;
-    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes);
+    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes, pr);
     KERNEL_CHECK(ctx);
     if (n_evals_out) *n_evals_out = evals;
     return 0;

@@ -189,3 +189,26 @@ def test_resolution_schedule_matches_reference(tmp_path):
     v = schedule.get_rhref({"refine_rhref": "-8", "refine_dataset": "ds"}, 2, rng=R)
     assert v == pytest.approx(1.0 / (1.0 / 8 + 1.0 / 8 / 25.0))
     assert schedule.get_rhref({"refine_rhref": "0", "refine_dataset": "none"}, 5, maps_dir=str(maps)) == 16
+
+
+def test_refine3d_shift_prior_sources(tmp_path):
+    """Answer 7 'use priors': mean / variance of the shifts come from rows 0 / 1 of the global
+    `_stat.cistem` (particle_cspt.py:1009-1016) when answer 3 names one, else from the input rows."""
+    from pyp_b200._lib import ROW_DTYPE
+    from pyp_b200.formats import cistem
+
+    rng = np.random.default_rng(3)
+    rows = np.zeros(40, dtype=ROW_DTYPE)
+    rows["position_in_stack"] = np.arange(1, 41)
+    rows["x_shift"] = rng.normal(1.0, 2.0, 40)
+    rows["y_shift"] = rng.normal(-0.5, 1.0, 40)
+    mx, my, vx, vy = refine3d.shift_prior({"global_stat": "null"}, rows)
+    assert np.isclose(mx, rows["x_shift"].mean(), atol=1e-5) and np.isclose(vy, rows["y_shift"].astype(np.float64).var(), rtol=1e-5)
+    stat = np.zeros(2, dtype=ROW_DTYPE)
+    stat["x_shift"] = [0.25, 9.0]
+    stat["y_shift"] = [-0.75, 4.0]
+    path = str(tmp_path / "ds_r01_stat.cistem")
+    cistem.write_parameters(path, stat)
+    assert refine3d.shift_prior({"global_stat": path}, rows) == (0.25, -0.75, 9.0, 4.0)
+    assert refine3d.shift_prior({"global_stat": str(tmp_path / "missing.cistem")}, rows)[0] == mx
+    assert refine3d.shift_prior({"global_stat": "null"}, rows[:0]) == (0.0, 0.0, 0.0, 0.0)

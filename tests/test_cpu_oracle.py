@@ -105,6 +105,37 @@ def test_local_refinement_recovers_poses(oracle):
     assert np.allclose(out2["theta"], start["theta"]) and not np.allclose(out2["x_shift"], start["x_shift"])
 
 
+def test_shift_restraint_pulls_towards_the_mean(oracle):
+    """refine3d answer 7 (use priors; frealign.py:3841-3844): objective = CC - (sigma^2 / N_mask) *
+    sum (shift - mean)^2 / (2 var) over x, y (SEMANTICS.md §7b).  Off: the prior fields are inert."""
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=16, snr=0.5)
+    cfg = _cfg(oracle, n, px)
+    specs = oracle.prepare_images(stack, cfg, oracle.noise_curve(stack, cfg))
+    ref = oracle.Reference(vol, 1)
+    start = synth.perturb_rows(rows, 2.0, 1.0).astype(oracle.ROW_DTYPE)
+    start["sigma"] = 10.0
+    free, _ = oracle.refine_local(ref, specs, start, cfg)
+    inert, _ = oracle.refine_local(ref, specs, start, _cfg(oracle, n, px, use_priors=0, prior_mean_x=50.0, prior_var_x=1e-3, prior_var_y=1e-3))
+    assert np.array_equal(free["x_shift"], inert["x_shift"]) and np.array_equal(free["score"], inert["score"])
+    tight, n_ev = oracle.refine_local(ref, specs, start, _cfg(oracle, n, px, use_priors=1, prior_var_x=1.0, prior_var_y=1.0))
+    assert n_ev == rows.size * (8 * (11 + 3) + 2)
+    r_free = np.hypot(free["x_shift"], free["y_shift"])
+    r_tight = np.hypot(tight["x_shift"], tight["y_shift"])
+    assert r_tight.mean() < 0.8 * r_free.mean()
+    assert (tight["score"] <= free["score"] + 1e-3).all()  # SCORE stays the unrestrained correlation
+    # a non-positive variance leaves that shift free: only y is pulled
+    only_y, _ = oracle.refine_local(ref, specs, start, _cfg(oracle, n, px, use_priors=1, prior_var_x=0.0, prior_var_y=1.0))
+    assert np.abs(only_y["x_shift"] - free["x_shift"]).mean() < 0.25 * np.abs(tight["x_shift"] - free["x_shift"]).mean() + 1e-3
+    assert np.abs(only_y["y_shift"]).mean() < 0.8 * np.abs(free["y_shift"]).mean()
+    # zero sigma: the restraint vanishes
+    start0 = start.copy()
+    start0["sigma"] = 0.0
+    a, _ = oracle.refine_local(ref, specs, start0, _cfg(oracle, n, px, use_priors=1, prior_var_x=1.0, prior_var_y=1.0))
+    b, _ = oracle.refine_local(ref, specs, start0, cfg)
+    assert np.array_equal(a["x_shift"], b["x_shift"])
+
+
 def test_reconstruction_recovers_phantom_and_symmetry(oracle):
     from pyp_b200.symmetry import symmetry_matrices
 

@@ -167,6 +167,33 @@ def test_local_refinement_matches_oracle(engine, oracle):
     assert np.allclose(changes["psi"], got["psi"] - start["psi"], atol=1e-4)
 
 
+def test_local_refinement_with_shift_restraint_matches_oracle(engine, oracle):
+    """refine3d answer 7 'use priors' (frealign.py:3841-3844): shift restraint of SEMANTICS.md §7b."""
+    from pyp_b200 import synth
+
+    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(
+        engine, oracle, n_part=48, use_priors=1, prior_mean_x=0.4, prior_mean_y=-0.3, prior_var_x=2.0, prior_var_y=1.0)
+    start = synth.perturb_rows(rows, 2.0, 1.0)
+    start["sigma"] = 10.0
+    got, _, n_ev = engine.refine(start)
+    want, n_ev_o = oracle.refine_local(ref, specs, start.astype(oracle.ROW_DTYPE), ocfg)
+    assert n_ev == n_ev_o
+    ang = angular_distance(got, want)
+    sh = np.hypot(got["x_shift"] - want["x_shift"], got["y_shift"] - want["y_shift"])
+    same = (ang < 2e-2) & (sh < 2e-2)
+    assert same.mean() >= 0.97, (np.sort(ang)[-3:], np.sort(sh)[-3:])
+    rel = np.abs(got["score"] - want["score"]) / np.abs(want["score"])
+    assert rel[same].max() <= SCORE_RTOL
+    # the restraint acts: shifts end closer to the prior mean than without it
+    cfg.use_priors = 0
+    engine.refine_configure(cfg)
+    engine.load_images(stack)
+    free, _, _ = engine.refine(start)
+    d_got = np.hypot(got["x_shift"] - 0.4, got["y_shift"] + 0.3)
+    d_free = np.hypot(free["x_shift"] - 0.4, free["y_shift"] + 0.3)
+    assert d_got.mean() < 0.8 * d_free.mean()
+
+
 def test_global_search_matches_oracle(engine, oracle):
     """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally.
     Same grid, same band, same box reduction on both sides; the best orientation/shift choice must
