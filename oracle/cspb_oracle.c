@@ -553,6 +553,69 @@ static float refine_one(const orc_ref *r, const float *spec, const orc_row *row,
     return sc;
 }
 
+/* ---- 2-D focus mask (refine3d prompts 29-32, 44; SEMANTICS.md §6b).  The sphere centre c (Angstrom from
+ * the corner of the map) is projected with the particle's pose: image axes are the first two columns of
+ * the rotation matrix (the slice geometry of orc_score), so the centre lands at n/2 + (col0.c', col1.c'),
+ * c' = c / pixel - n/2.  LOGP = -N/2 (1 + ln(2 pi var)), var = mean of the squared real-space residual
+ * (shifted image - alpha CTF projection, band-limited like the score) over the N pixels of the disc. */
+void orc_focus_center(const orc_refine_cfg *cfg, const float *pose6, float *cx, float *cy) {
+    float m[9];
+    orc_euler_matrix(pose6[0], pose6[1], pose6[2], m);
+    const float h = (float)(cfg->box / 2);
+    const float x = cfg->focus_x / cfg->pixel_size - h, y = cfg->focus_y / cfg->pixel_size - h, z = cfg->focus_z / cfg->pixel_size - h;
+    *cx = h + m[0] * x + m[3] * y + m[6] * z;
+    *cy = h + m[1] * x + m[4] * y + m[7] * z;
+}
+
+float orc_focus_logp(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                     const float *o4) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    float m[9];
+    orc_euler_matrix(pose6[0], pose6[1], pose6[2], m);
+    const ctfc c = ctf_make(row, n);
+    const float k2 = 2.f * PI_F / ((float)n * row->pixel_size);
+    const float alpha = o4[3] > 0.f ? o4[1] / o4[3] : 0.f;
+    float *D = (float *)calloc((size_t)2 * n * nh, sizeof(float));
+    float *real = (float *)malloc(sizeof(float) * (size_t)n * n);
+    for (int j = -n / 2; j < n / 2; ++j)
+        for (int i = 0; i <= n / 2; ++i) {
+            const float r2 = (float)(i * i + j * j);
+            if (r2 < lo * lo || r2 > hi * hi) continue;
+            const int jj = j < 0 ? j + n : j;
+            const float fr = spec[2 * ((size_t)jj * nh + i)], fim = spec[2 * ((size_t)jj * nh + i) + 1];
+            float pr, pi;
+            ref_interp(r, (m[0] * i + m[1] * j) * r->pad, (m[3] * i + m[4] * j) * r->pad, (m[6] * i + m[7] * j) * r->pad, &pr, &pi);
+            const float ctf = ctf_eval(&c, i, j, pose6[5]);
+            const float ph = (i * pose6[3] + j * pose6[4]) * k2;
+            const float cs = cosf(ph), sn = sinf(ph);
+            const float gr = fr * cs - fim * sn, gi = fr * sn + fim * cs;
+            const float w = ((i + j) & 1) ? -1.f : 1.f; /* back from the centred phase origin to the image corner */
+            D[2 * ((size_t)jj * nh + i)] = w * (gr - alpha * ctf * pr);
+            D[2 * ((size_t)jj * nh + i) + 1] = w * (gi - alpha * ctf * pi);
+        }
+    orc_fft2_c2r(D, n, real);
+    float cx, cy;
+    orc_focus_center(cfg, pose6, &cx, &cy);
+    const float rad = cfg->focus_radius / cfg->pixel_size, inv = 1.f / ((float)n * (float)n);
+    double ss = 0.0;
+    long cnt = 0;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            const float dx = (float)x - cx, dy = (float)y - cy;
+            if (dx * dx + dy * dy > rad * rad) continue;
+            const float v = real[(size_t)y * n + x] * inv;
+            ss += (double)v * v;
+            ++cnt;
+        }
+    free(D);
+    free(real);
+    if (cnt == 0) return 0.f;
+    const float var = (float)(ss / (double)cnt);
+    return var > 0.f ? -0.5f * (float)cnt * (1.f + logf(2.f * PI_F * var)) : 0.f;
+}
+
 static void write_row(orc_row *row, const float *x, float sc, const float *o4, int nband, int refine_defocus) {
     row->psi = wrap360(x[0]);
     row->theta = x[1];
@@ -578,7 +641,9 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
         long long ev = 0;
         const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, 1.f, NULL);
         evals += ev;
+        const orc_row before = *row;
         write_row(row, x, sc, o4, nband, cfg->refine_defocus);
+        if (cfg->focus_radius > 0.f) row->logp = orc_focus_logp(r, spec, &before, x, cfg, o4);
     }
     return evals;
 }
@@ -715,7 +780,9 @@ long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows,
             if (obj > bestobj) { bestobj = obj; bestsc = sc; memcpy(xb, x, sizeof xb); memcpy(ob, o4, sizeof ob); }
         }
         evals += ev;
+        const orc_row before = *row;
         write_row(row, xb, bestsc, ob, nband, cfg->refine_defocus);
+        if (cfg->focus_radius > 0.f) row->logp = orc_focus_logp(r, spec, &before, xb, cfg, ob);
         free(S); free(top); free(G); free(c2m);
     }
     free(Pall); free(si); free(sj);

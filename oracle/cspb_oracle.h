@@ -52,6 +52,9 @@ typedef struct orc_refine_cfg {
      * Angstrom (rows 0 / 1 of <name>_stat.cistem, particle_cspt.py:1009-1016); variance <= 0: unrestrained */
     int32_t use_priors;
     float prior_mean_x, prior_mean_y, prior_var_x, prior_var_y;
+    /* 2-D focus mask (prompts 29-32 + 44, class_focusmask "x,y,z,radius" in Angstrom from the corner of
+     * the map, frealign.py:3845-3848,3883-3885; SEMANTICS.md §6b): LOGP over the projected sphere */
+    float focus_x, focus_y, focus_z, focus_radius;
 } orc_refine_cfg;
 
 typedef struct orc_recon_cfg {
@@ -92,6 +95,11 @@ float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const f
 
 /* ---- batched local refinement of n particles (specs: n prepared spectra).  OpenMP over
  * particles when built with -fopenmp.  Returns number of objective evaluations. */
+/* centre (pixels, image coordinates) of the projected focus sphere for a pose */
+void orc_focus_center(const orc_refine_cfg *cfg, const float *pose6, float *cx, float *cy);
+/* LOGP of the real-space residual inside the projected focus sphere; o4 = band sums of the pose */
+float orc_focus_logp(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                     const float *o4);
 long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, int n,
                            const orc_refine_cfg *cfg);
 

@@ -42,6 +42,7 @@ class RefineCfg(C.Structure):
         ("best_matches", C.c_int32), ("global_search", C.c_int32),
         ("use_priors", C.c_int32), ("prior_mean_x", C.c_float), ("prior_mean_y", C.c_float),
         ("prior_var_x", C.c_float), ("prior_var_y", C.c_float),
+        ("focus_x", C.c_float), ("focus_y", C.c_float), ("focus_z", C.c_float), ("focus_radius", C.c_float),
     ]
 
 
@@ -124,6 +125,8 @@ def lib():
             "orc_prepare_image": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
+            "orc_focus_center": (None, [C.POINTER(RefineCfg), vp, vp, vp]),
+            "orc_focus_logp": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_global_search": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg), vp, i]),
             "orc_csp_compose": (None, [vp, vp, vp, vp, vp, f, f, f, vp]),
             "orc_csp_run": (C.c_longlong, [vp, vp, vp, i, vp, i, vp, i, C.POINTER(RefineCfg), C.POINTER(CspCfg), i, i]),
@@ -232,6 +235,20 @@ def score(ref, spec, row, pose6, cfg):
     o4 = np.zeros(4, dtype=np.float32)
     s = lib().orc_score(ref._h, _p(spec), _p(row), _p(pose), C.byref(cfg), _p(o4))
     return float(s), o4
+
+
+def focus_center(cfg, pose6):
+    pose = _f32(pose6)
+    cx, cy = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    lib().orc_focus_center(C.byref(cfg), _p(pose), _p(cx), _p(cy))
+    return float(cx[0]), float(cy[0])
+
+
+def focus_logp(ref, spec, row, pose6, cfg, o4):
+    spec = np.ascontiguousarray(spec, dtype=np.complex64)
+    row = np.ascontiguousarray(row, dtype=ROW_DTYPE).reshape(1)
+    pose, o4 = _f32(pose6), _f32(o4)
+    return float(lib().orc_focus_logp(ref._h, _p(spec), _p(row), _p(pose), C.byref(cfg), _p(o4)))
 
 
 def refine_local(ref, specs, rows, cfg):

@@ -136,6 +136,57 @@ def test_shift_restraint_pulls_towards_the_mean(oracle):
     assert np.array_equal(a["x_shift"], b["x_shift"])
 
 
+def test_focus_mask_logp_sees_the_missing_density(oracle):
+    """refine3d answers 29-32 + 44 (class_focusmask, frealign.py:3845-3848,3883-3885; SEMANTICS.md §6b):
+    the images hold a blob the reference lacks; the residual inside the projected focus sphere is large
+    when the sphere sits on that blob and small when it sits on the opposite side — which pins the
+    projection geometry, the shift sign and the phase origin of the focus pass in one go."""
+    n, px = 64, 1.35
+    ph = synth.Phantom(n, n_blobs=40, sigma=1.5)
+    k = int(np.argmin(np.abs(np.linalg.norm(ph.centres, axis=1) - 9.0)))  # well inside the soft mask
+    ph.amps[k] = 5.0
+    # small defocus and an 8 A band: the CTF delocalises the blob by lambda * defocus / d ~ 7 px, the disc is 6 px
+    rows = synth.make_rows(8, px, seed=5, shift_px=3.0, defocus=(3000.0, 5000.0))
+    stack = synth.make_stack(ph, rows, snr=20.0, seed=6)
+    full_amp = ph.amps.copy()
+    ph.amps[k] = 0.0
+    vol = ph.volume()  # reference without blob k
+    ph.amps = full_amp
+    c = ph.centres[k]
+    # geometry alone: the projected centre is where the analytic projection puts the blob
+    # (no whitening here: at this SNR the noise curve is the signal spectrum and the whitened image no
+    # longer resembles alpha * CTF * projection anywhere, which would bury the one missing blob)
+    cfg = _cfg(oracle, n, px, whiten=0, high_res_limit=6.0 * px, focus_x=(c[0] + n // 2) * px, focus_y=(c[1] + n // 2) * px,
+               focus_z=(c[2] + n // 2) * px, focus_radius=6.0 * px)
+    for r in rows[:4]:
+        cx, cy = oracle.focus_center(cfg, pose_of(r))
+        want = c @ synth.euler_matrix(r["psi"], r["theta"], r["phi"])
+        assert abs(cx - (n // 2 + want[0])) < 1e-3 and abs(cy - (n // 2 + want[1])) < 1e-3
+    off = _cfg(oracle, n, px, whiten=0, high_res_limit=6.0 * px, focus_x=(-c[0] + n // 2) * px, focus_y=(-c[1] + n // 2) * px,
+               focus_z=(-c[2] + n // 2) * px, focus_radius=6.0 * px)
+    specs = oracle.prepare_images(stack, cfg, None)
+    ref = oracle.Reference(vol, 1)
+    rows = rows.astype(oracle.ROW_DTYPE)
+    n_clear = 0
+    for i in range(rows.size):
+        pose = pose_of(rows[i])
+        _, o4 = oracle.score(ref, specs[i], rows[i], np.array(pose, np.float32), cfg)
+        on = oracle.focus_logp(ref, specs[i], rows[i], pose, cfg, o4)
+        away = oracle.focus_logp(ref, specs[i], rows[i], pose, off, o4)
+        # logp = -N/2 (1 + ln 2 pi var): same N (same radius) -> lower logp = larger residual variance
+        c2 = c @ synth.euler_matrix(rows[i]["psi"], rows[i]["theta"], rows[i]["phi"])
+        if 2 * np.hypot(c2[0], c2[1]) > 9.0:  # blob and mirror point are more than 1.5 disc radii apart in this view
+            assert on < away - 50.0, (i, on, away)
+            n_clear += 1
+    assert n_clear >= 4
+    # the refinement writes the masked value into LOGP, everything else unchanged
+    plain, _ = oracle.refine_local(ref, specs[:2], rows[:2], _cfg(oracle, n, px, local_iterations=2))
+    masked, _ = oracle.refine_local(ref, specs[:2], rows[:2], _cfg(oracle, n, px, local_iterations=2, focus_x=cfg.focus_x,
+                                                                 focus_y=cfg.focus_y, focus_z=cfg.focus_z, focus_radius=cfg.focus_radius))
+    assert np.array_equal(plain["score"], masked["score"]) and np.array_equal(plain["psi"], masked["psi"])
+    assert not np.allclose(plain["logp"], masked["logp"])
+
+
 def test_reconstruction_recovers_phantom_and_symmetry(oracle):
     from pyp_b200.symmetry import symmetry_matrices
 
