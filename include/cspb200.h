@@ -112,7 +112,8 @@ typedef struct cspb_refine_cfg {
     int32_t local_refine;      /* prompt 37                                                    */
     int32_t refine_psi, refine_theta, refine_phi, refine_x, refine_y; /* prompts 38-42         */
     int32_t refine_defocus;    /* prompt 45                                                    */
-    int32_t apply_mask;        /* prompt 44 apply 2-D masking: 0 none, 1 soft circular mask    */
+    int32_t apply_mask;        /* soft circular particle mask of radius mask_radius (default 1);   */
+                               /* prompt 44 switches the FOCUS mask: cspb_refine_set_focus_mask    */
     int32_t normalize;         /* prompt 46 normalise particles                                */
     int32_t invert_contrast;   /* prompt 47                                                    */
     int32_t whiten;            /* 1 = whiten with the stack's noise power curve (cisTEM default) */
@@ -133,6 +134,13 @@ int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg);
 /* Optional per-ring SSNR weights (prompt 5/6, statistics_rNN.txt part_SSNR column mapped to
  * rings of the box); n_rings = box/2+1.  NULL resets to all-ones. */
 int cspb_refine_set_ring_weights(cspb_ctx *ctx, const float *w, int n_rings);
+
+/* 2-D focus mask (prompts 29-32 with prompt 44 = yes; class_focusmask "x,y,z,radius",
+ * frealign.py:3845-3848,3883-3885): sphere centre in Angstrom from the corner of the map and radius in
+ * Angstrom.  With radius > 0 cspb_refine_run* writes into LOGP the log-likelihood of the real-space
+ * residual inside the projected sphere (oracle/SEMANTICS.md 6b) instead of the whole-band value.
+ * radius <= 0 switches it off (default). */
+int cspb_refine_set_focus_mask(cspb_ctx *ctx, float x, float y, float z, float radius);
 
 /* Upload the reference map (prompt 4, n^3 float32, x fastest) and build the padded, centred,
  * band-cropped Fourier half-volume in HBM. */

@@ -138,6 +138,9 @@ def run(p, out=sys.stdout):
         st = statistics.read_statistics(p["statistics"])
         if st.size:
             eng.set_ring_weights(statistics.ring_weights_from_statistics(st, box, p["pixel_size"]))
+    focus = p["apply_2d_masking"] and p["mask_2d"][3] > 0
+    if focus:
+        eng.set_focus_mask(*p["mask_2d"])
     eng.set_symmetry(p["symmetry"])
     if p["global_search"]:
         from ..search_grid import search_grid
@@ -162,8 +165,8 @@ def run(p, out=sys.stdout):
     if p["use_priors"]:
         out.write(f"Shift restraint: mean ({cfg.prior_mean_x:.3f}, {cfg.prior_mean_y:.3f}) A, "
                   f"variance ({cfg.prior_var_x:.3f}, {cfg.prior_var_y:.3f}) A^2\n")
-    if p["mask_2d"][3] > 0:
-        out.write("Note: the 2-D focus mask (answers 29-32) is accepted but not applied by cspb200\n")
+    if focus:
+        out.write("LogP evaluated inside the 2-D focus mask: centre ({:.1f}, {:.1f}, {:.1f}) A, radius {:.1f} A\n".format(*p["mask_2d"]))
     out.write("\nRefine3D: Normal termination\n")
     eng.close()
     return refined

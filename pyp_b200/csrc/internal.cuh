@@ -137,6 +137,10 @@ struct cspb_ctx {
     DevBuf d_sym_lit, d_sym_lat;
     int n_lit = 1, n_lat = 1;
 
+    // 2-D focus mask (cspb_refine_set_focus_mask): sphere centre x, y, z and radius in Angstrom; radius <= 0 = off
+    float focus[4] = {0.f, 0.f, 0.f, 0.f};
+    DevBuf d_alpha;  // per image: signal scale X / B of the pose kept by the refinement
+
     // global-search orientation grid (psi, theta, phi) and hit buffer
     DevBuf d_grid, d_hits;
     int n_grid = 0;

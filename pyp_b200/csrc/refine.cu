@@ -480,7 +480,7 @@ __global__ void opt_finish_eval_kernel(const OptState *__restrict__ st, int n, i
 // the best score; ties keep the earlier candidate
 __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n_images, int K, const float4 *__restrict__ sc,
                                       int n_samples, int refine_defocus, cspb_row *__restrict__ rows,
-                                      cspb_row *__restrict__ changes, const OptPrior pr) {
+                                      cspb_row *__restrict__ changes, const OptPrior pr, float *__restrict__ alpha_out) {
     const int img = blockIdx.x * blockDim.x + threadIdx.x;
     if (img >= n_images) return;
     cspb_row r = rows[img];
@@ -523,6 +523,7 @@ __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n_ima
     r.sigma = sigma;
     r.logp = logp;
     rows[img] = r;
+    if (alpha_out) alpha_out[img] = vbest.w > 0.f ? vbest.y / vbest.w : 0.f;
     if (changes) {
         cspb_row c = r;
         c.psi = r.psi - old.psi; c.theta = r.theta - old.theta; c.phi = r.phi - old.phi;
@@ -1072,6 +1073,124 @@ extern "C" int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, flo
     return cspb_refine_score_poses(ctx, rows, n, idx.data(), poses.data(), n, scores_out);
 }
 
+// ================================================================== 2-D focus mask (prompts 29-32, 44)
+// LOGP over the projected focus sphere (oracle/SEMANTICS.md 6b): residual spectrum (shifted image -
+// alpha CTF slice) on the scoring band -> inverse FFT -> variance inside the disc.
+__global__ void focus_residual_kernel(const float4 *__restrict__ ref4, int sx, int sy, int rc, float padf,
+                                      const int32_t *__restrict__ slot_ij, int n_slots, const float2 *__restrict__ packed,
+                                      const CtfCoef *__restrict__ ctf, const cspb_row *__restrict__ rows,
+                                      const float *__restrict__ alpha, int n, float inv_npx2, float2 *__restrict__ spec) {
+    __shared__ float m[9];
+    const int img = blockIdx.y, nh = n / 2 + 1;
+    const cspb_row row = rows[img];
+    if (threadIdx.x == 0) euler_matrix(row.psi, row.theta, row.phi, m);
+    __syncthreads();
+    const CtfCoef cc = ctf[img];
+    const float a = alpha[img], mx = row.x_shift * inv_npx2, my = row.y_shift * inv_npx2;
+    const float2 *F = packed + (long long)img * n_slots;
+    float2 *o = spec + (long long)img * n * nh;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        const int32_t ij = slot_ij[s];
+        const int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+        if (i == CSPB_DUMMY_I) continue;
+        const float fi = (float)i, fj = (float)j;
+        const float2 P = gather_trilinear(ref4, sx, sy, rc, (m[0] * fi + m[1] * fj) * padf, (m[3] * fi + m[4] * fj) * padf,
+                                          (m[6] * fi + m[7] * fj) * padf);
+        const float cv = -sinpif(ctf_chi(cc, fi, fj, fi * fi + fj * fj) * (1.f / CSPB_PI_F));
+        float sn, cs;
+        sincospif(fi * mx + fj * my, &sn, &cs);
+        const float2 f = F[s];
+        const float gr = f.x * cs - f.y * sn, gi = f.x * sn + f.y * cs;
+        const float w = ((i + j) & 1) ? -1.f : 1.f;  // centred phase origin -> image corner
+        const int jj = j < 0 ? j + n : j;
+        o[jj * nh + i] = make_float2(w * (gr - a * cv * P.x), w * (gi - a * cv * P.y));
+    }
+}
+
+// one CTA per image: variance of the residual inside the projected disc -> LOGP
+__global__ void focus_logp_kernel(const float *__restrict__ real, int n, float pixel, float fx, float fy, float fz, float frad,
+                                  cspb_row *__restrict__ rows, cspb_row *__restrict__ changes) {
+    __shared__ float s_sum[32];
+    __shared__ int s_cnt[32];
+    const int img = blockIdx.x;
+    const cspb_row row = rows[img];
+    float m[9];
+    euler_matrix(row.psi, row.theta, row.phi, m);
+    const float h = (float)(n / 2);
+    const float x = fx / pixel - h, y = fy / pixel - h, z = fz / pixel - h;
+    const float cx = h + m[0] * x + m[3] * y + m[6] * z, cy = h + m[1] * x + m[4] * y + m[7] * z;
+    const float rad = frad / pixel;
+    const int x0 = max(0, (int)floorf(cx - rad)), x1 = min(n - 1, (int)ceilf(cx + rad));
+    const int y0 = max(0, (int)floorf(cy - rad)), y1 = min(n - 1, (int)ceilf(cy + rad));
+    const int wbox = x1 - x0 + 1, hbox = y1 - y0 + 1;
+    const float *p = real + (long long)img * n * n;
+    float ss = 0.f;
+    int cnt = 0;
+    if (wbox > 0 && hbox > 0)
+        for (int t = threadIdx.x; t < wbox * hbox; t += blockDim.x) {
+            const int px = x0 + t % wbox, py = y0 + t / wbox;
+            const float dx = (float)px - cx, dy = (float)py - cy;
+            if (dx * dx + dy * dy > rad * rad) continue;
+            const float v = p[py * n + px];
+            ss += v * v;
+            ++cnt;
+        }
+    ss = warp_sum(ss);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_sum[warp] = ss; s_cnt[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        int c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tot += s_sum[w]; c += s_cnt[w]; }
+        float logp = 0.f;
+        if (c > 0) {
+            const float var = tot / (float)c;
+            if (var > 0.f) logp = -0.5f * (float)c * (1.f + logf(2.f * CSPB_PI_F * var));
+        }
+        if (changes) changes[img].logp += logp - row.logp;
+        rows[img].logp = logp;
+    }
+}
+
+static int focus_logp_enqueue(cspb_ctx *ctx, cspb_row *d_rows, CtfCoef *d_ctf, int n_img, cspb_row *d_changes) {
+    const cspb_refine_cfg &c = ctx->rcfg;
+    const int n = c.box, nh = n / 2 + 1, n_slots = ctx->plan.n_slots;
+    // the rows hold the refined defocus: refresh the CTF coefficients
+    ctf_coef_kernel<<<ceil_div(n_img, 128), 128, 0, ctx->stream>>>(d_rows, n_img, n, d_ctf);
+    KERNEL_CHECK(ctx);
+    int chunk = chunk_images(n, n_img);
+    if (chunk > 2048) chunk = 2048;
+    RESERVE(ctx, ctx->d_work0, (size_t)chunk * n * n * sizeof(float));
+    RESERVE(ctx, ctx->d_work1, (size_t)chunk * n * nh * sizeof(float2));
+    float *real = ctx->d_work0.as<float>();
+    float2 *spec = ctx->d_work1.as<float2>();
+    const float inv_npx2 = 2.f / ((float)n * c.pixel_size);
+    for (int s = 0; s < n_img; s += chunk) {
+        const int cnt = n_img - s < chunk ? n_img - s : chunk;
+        CU_TRY(ctx, cudaMemsetAsync(spec, 0, (size_t)cnt * n * nh * sizeof(float2), ctx->stream));
+        dim3 grid(ceil_div(n_slots, 256), cnt);
+        focus_residual_kernel<<<grid, 256, 0, ctx->stream>>>(
+            ctx->ref.d_ref4.as<float4>(), ctx->ref.sx, ctx->ref.sy, ctx->ref.rc, (float)ctx->ref.pad,
+            ctx->plan.d_slot_ij.as<int32_t>(), n_slots, ctx->d_packed.as<float2>() + (size_t)s * n_slots, d_ctf + s, d_rows + s,
+            ctx->d_alpha.as<float>() + s, n, inv_npx2, spec);
+        KERNEL_CHECK(ctx);
+        int rc = fft2_c2r_dev(ctx, spec, real, n, cnt, 1.f / ((float)n * (float)n));
+        if (rc) return rc;
+        focus_logp_kernel<<<cnt, 256, 0, ctx->stream>>>(real, n, c.pixel_size, ctx->focus[0], ctx->focus[1], ctx->focus[2],
+                                                         ctx->focus[3], d_rows + s, d_changes ? d_changes + s : nullptr);
+        KERNEL_CHECK(ctx);
+    }
+    return 0;
+}
+
+extern "C" int cspb_refine_set_focus_mask(cspb_ctx *ctx, float x, float y, float z, float radius) {
+    if (!ctx) return CSPB_E_ARG;
+    ctx->focus[0] = x; ctx->focus[1] = y; ctx->focus[2] = z; ctx->focus[3] = radius > 0.f ? radius : 0.f;
+    return 0;
+}
+
 int search_enqueue(cspb_ctx *ctx, const CtfCoef *d_ctf, const float *d_angles3, int n_orient, int K, void *d_hits);
 
 // enqueue the whole refinement on the stream; rows/ctf already on the device.  With global search
@@ -1136,6 +1255,8 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     const float h_shift = coarse * 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
     const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
     const int g = ceil_div(ns, 128);
+    const bool focus_on = ctx->focus[3] > 0.f;
+    if (focus_on) RESERVE(ctx, ctx->d_alpha, (size_t)n * sizeof(float));
     OptPrior pr{};
     float lam_scale = 0.f;
     if (c.use_priors) {
@@ -1167,8 +1288,13 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     int rc = launch_score(ctx, un, ns, 2, ev, d_ctf, out, ddef, 2 * (int64_t)ns, false);
     if (rc) return rc;
     evals += 2 * (int64_t)ns;
-    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes, pr);
+    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes, pr,
+                                                                         focus_on ? ctx->d_alpha.as<float>() : nullptr);
     KERNEL_CHECK(ctx);
+    if (focus_on) {
+        rc = focus_logp_enqueue(ctx, d_rows, const_cast<CtfCoef *>(d_ctf), n, d_changes);
+        if (rc) return rc;
+    }
     if (n_evals_out) *n_evals_out = evals;
     return 0;
 }

@@ -135,6 +135,11 @@ class Engine:
             w = np.ascontiguousarray(w, dtype=np.float32)
             self._ck(self._l.cspb_refine_set_ring_weights(self._h, ptr(w), int(w.size)))
 
+    def set_focus_mask(self, x, y, z, radius):
+        """2-D focus mask of refine3d (answers 29-32 + 44; class_focusmask, frealign.py:3845-3848,3883-3885):
+        sphere centre / radius in Angstrom from the corner of the map; radius <= 0 switches it off."""
+        self._ck(self._l.cspb_refine_set_focus_mask(self._h, float(x), float(y), float(z), float(radius)))
+
     def noise_curve(self):
         out = np.zeros(self.box + 1, dtype=np.float32)
         self._ck(self._l.cspb_refine_get_noise_curve(self._h, ptr(out), out.size))

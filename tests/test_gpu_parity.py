@@ -196,6 +196,38 @@ def test_local_refinement_with_shift_restraint_matches_oracle(engine, oracle):
     assert d_got.mean() < 0.8 * d_free.mean()
 
 
+def test_focus_mask_logp_matches_oracle(engine, oracle):
+    """refine3d answers 29-32 + 44 (class_focusmask, frealign.py:3845-3848,3883-3885): LOGP over the
+    projected focus sphere (SEMANTICS.md §6b); poses and scores are untouched by the mask."""
+    from pyp_b200 import synth
+
+    px = 1.35
+    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, n_part=32)
+    start = synth.perturb_rows(rows, 2.0, 1.0)
+    plain, _, _ = engine.refine(start)
+    focus = (38.0 * px, 27.0 * px, 35.0 * px, 7.0 * px)
+    engine.set_focus_mask(*focus)
+    try:
+        got, changes, n_ev = engine.refine(start, want_changes=True)
+    finally:
+        engine.set_focus_mask(0, 0, 0, 0)
+    ocfg.focus_x, ocfg.focus_y, ocfg.focus_z, ocfg.focus_radius = focus
+    want, n_ev_o = oracle.refine_local(ref, specs, start.astype(oracle.ROW_DTYPE), ocfg)
+    assert n_ev == n_ev_o
+    for k in ("psi", "theta", "phi", "x_shift", "y_shift", "score", "sigma"):
+        assert np.array_equal(got[k], plain[k]), k
+    assert not np.allclose(got["logp"], plain["logp"], rtol=1e-2)
+    ang = angular_distance(got, want)
+    sh = np.hypot(got["x_shift"] - want["x_shift"], got["y_shift"] - want["y_shift"])
+    same = (ang < 2e-2) & (sh < 2e-2)
+    assert same.mean() >= 0.95
+    assert np.allclose(got["logp"][same], want["logp"][same], rtol=2e-3), np.abs(got["logp"] / want["logp"] - 1)[same].max()
+    assert np.allclose(changes["logp"], got["logp"] - start["logp"], atol=1e-2)
+    # after switching the mask off the whole-band LOGP is back
+    again, _, _ = engine.refine(start)
+    assert np.array_equal(again["logp"], plain["logp"])
+
+
 def test_global_search_matches_oracle(engine, oracle):
     """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally.
     Same grid, same band, same box reduction on both sides; the best orientation/shift choice must
