@@ -142,6 +142,12 @@ int cspb_refine_set_ring_weights(cspb_ctx *ctx, const float *w, int n_rings);
  * radius <= 0 switches it off (default). */
 int cspb_refine_set_focus_mask(cspb_ctx *ctx, float x, float y, float z, float radius);
 
+/* refine_ctf answer 23 (estimate beam tilt, frealign.py:3995-4041): sum over the loaded images of
+ * G * conj(CTF * slice) on the scoring band at the pose of each row; out_complex = box * (box/2+1)
+ * complex64 (re, im interleaved), zero outside the band.  The host fits the coma phase to it
+ * (pyp_b200/beamtilt.py; oracle/SEMANTICS.md 12). */
+int cspb_refine_phase_sum(cspb_ctx *ctx, const cspb_row *rows, int n_rows, float *out_complex);
+
 /* Upload the reference map (prompt 4, n^3 float32, x fastest) and build the padded, centred,
  * band-cropped Fourier half-volume in HBM. */
 int cspb_set_reference(cspb_ctx *ctx, const float *vol, int n, int loc);

@@ -428,6 +428,39 @@ float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const f
     return den > 0.f ? 100.f * num / sqrtf(den) : 0.f;
 }
 
+/* ================================================================ beam-tilt phase sum (refine_ctf) */
+void orc_phase_sum(const orc_ref *r, const float *specs, const orc_row *rows, int n_img, const orc_refine_cfg *cfg, float *out_c) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    double *acc = (double *)calloc((size_t)2 * n * nh, sizeof(double));
+    for (int k = 0; k < n_img; ++k) {
+        const float *spec = specs + 2 * (size_t)k * n * nh;
+        const orc_row *row = &rows[k];
+        float m[9];
+        orc_euler_matrix(row->psi, row->theta, row->phi, m);
+        const ctfc c = ctf_make(row, n);
+        const float k2 = 2.f * PI_F / ((float)n * row->pixel_size);
+        for (int j = -n / 2; j < n / 2; ++j)
+            for (int i = 0; i <= n / 2; ++i) {
+                const float r2 = (float)(i * i + j * j);
+                if (r2 < lo * lo || r2 > hi * hi) continue;
+                const int jj = j < 0 ? j + n : j;
+                const float fr = spec[2 * ((size_t)jj * nh + i)], fim = spec[2 * ((size_t)jj * nh + i) + 1];
+                float pr, pi;
+                ref_interp(r, (m[0] * i + m[1] * j) * r->pad, (m[3] * i + m[4] * j) * r->pad, (m[6] * i + m[7] * j) * r->pad, &pr, &pi);
+                const float ctf = ctf_eval(&c, i, j, 0.f);
+                const float ph = (i * row->x_shift + j * row->y_shift) * k2;
+                const float cs = cosf(ph), sn = sinf(ph);
+                const float gr = fr * cs - fim * sn, gi = fr * sn + fim * cs;
+                acc[2 * ((size_t)jj * nh + i)] += (double)(ctf * (gr * pr + gi * pi));
+                acc[2 * ((size_t)jj * nh + i) + 1] += (double)(ctf * (gi * pr - gr * pi));
+            }
+    }
+    for (size_t t = 0; t < (size_t)2 * n * nh; ++t) out_c[t] = (float)acc[t];
+    free(acc);
+}
+
 /* ================================================================ local refinement */
 #define NP 6
 #define NL 3

@@ -125,6 +125,7 @@ def lib():
             "orc_prepare_image": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
+            "orc_phase_sum": (None, [vp, vp, vp, i, C.POINTER(RefineCfg), vp]),
             "orc_focus_center": (None, [C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_focus_logp": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_global_search": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg), vp, i]),
@@ -235,6 +236,14 @@ def score(ref, spec, row, pose6, cfg):
     o4 = np.zeros(4, dtype=np.float32)
     s = lib().orc_score(ref._h, _p(spec), _p(row), _p(pose), C.byref(cfg), _p(o4))
     return float(s), o4
+
+
+def phase_sum(ref, specs, rows, cfg):
+    specs = np.ascontiguousarray(specs, dtype=np.complex64)
+    rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+    out = np.zeros((cfg.box, cfg.box // 2 + 1), dtype=np.complex64)
+    lib().orc_phase_sum(ref._h, _p(specs), _p(rows), rows.size, C.byref(cfg), _p(out))
+    return out
 
 
 def focus_center(cfg, pose6):

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "cspb_refine_cfg_default": (_i, [C.POINTER(RefineCfg), _i, _f]),
     "cspb_refine_configure": (_i, [_vp, C.POINTER(RefineCfg)]),
     "cspb_refine_set_ring_weights": (_i, [_vp, _vp, _i]),
+    "cspb_refine_phase_sum": (_i, [_vp, _vp, _i, _vp]),
     "cspb_refine_set_focus_mask": (_i, [_vp, C.c_float, C.c_float, C.c_float, C.c_float]),
     "cspb_set_reference": (_i, [_vp, _vp, _i, _i]),
     "cspb_set_symmetry": (_i, [_vp, _vp, _i]),

@@ -3,8 +3,10 @@
 
 Per-particle defocus refinement with the refine3d scorer (pose fixed, defocus offset free).  Writes
 `<out>_refined_ctf.star` / `<out>_changes.star` (merged by pyp with merge_star,
-frealign.py:3133-3154).  Beam-tilt estimation (answer 23) is NOT implemented: the beam-tilt columns
-pass through unchanged, the three diagnostic images are written as zeros and the log says so.
+frealign.py:3133-3154).  Beam-tilt estimation (answer 23): the GPU sums G * conj(CTF * slice) over
+the particles of the range (`cspb_refine_phase_sum`), the coma phase of a tilted beam is fitted to it
+(`pyp_b200/beamtilt.py`, oracle/SEMANTICS.md §12); BEAM_TILT_X/Y (mrad) and IMAGE_SHIFT_X/Y (Angstrom)
+of every row of the range are set to the fit and the three diagnostic images are written.
 """
 import sys
 import time
@@ -64,7 +66,8 @@ def run(p, out=sys.stdout):
     if vol.shape != (box, box, box):
         raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
     refined, n_evals = rows.copy(), 0
-    if p["refine_defocus"] and rows.size:
+    tilt = None
+    if (p["refine_defocus"] or p["beam_tilt"]) and rows.size:
         eng = Engine(pick_device(first, last - first + 1))
         cfg = Engine.refine_defaults(box, p["pixel_size"])
         cfg.pad = 2 if p["padding"] >= 1.5 else 1
@@ -73,7 +76,7 @@ def run(p, out=sys.stdout):
         cfg.defocus_range, cfg.defocus_step = p["defocus_range"], p["defocus_step"]
         cfg.global_search, cfg.local_refine = 0, 1
         cfg.refine_psi = cfg.refine_theta = cfg.refine_phi = cfg.refine_x = cfg.refine_y = 0
-        cfg.refine_defocus = 1
+        cfg.refine_defocus = int(p["refine_defocus"])
         cfg.normalize, cfg.invert_contrast = int(p["normalize"]), int(p["invert"])
         eng.refine_configure(cfg)
         eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
@@ -81,26 +84,36 @@ def run(p, out=sys.stdout):
         _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max()))
         for s in range(0, rows.size, 16384):
             eng.load_images(np.ascontiguousarray(data[pos[s:s + 16384] - pos.min()]), append=s > 0)
-        refined, _, n_evals = eng.refine(rows)
-        # keep the search inside +- defocus_range of the input (answer 19)
-        if p["defocus_range"] > 0:
-            d = np.clip(refined["defocus_1"] - rows["defocus_1"], -p["defocus_range"], p["defocus_range"])
-            refined["defocus_1"], refined["defocus_2"] = rows["defocus_1"] + d, rows["defocus_2"] + d
+        if p["refine_defocus"]:
+            refined, _, n_evals = eng.refine(rows)
+            # keep the search inside +- defocus_range of the input (answer 19)
+            if p["defocus_range"] > 0:
+                d = np.clip(refined["defocus_1"] - rows["defocus_1"], -p["defocus_range"], p["defocus_range"])
+                refined["defocus_1"], refined["defocus_2"] = rows["defocus_1"] + d, rows["defocus_2"] + d
+        if p["beam_tilt"]:
+            from .. import beamtilt
+
+            S = eng.phase_sum(refined)
+            n_evals += int(rows.size)
+            tilt = beamtilt.fit(S, p["pixel_size"], float(rows["voltage_kv"][0]), float(rows["cs_mm"][0]))
+            refined["beam_tilt_x"], refined["beam_tilt_y"] = tilt["beam_tilt_x"], tilt["beam_tilt_y"]
+            refined["image_shift_x"], refined["image_shift_y"] = tilt["shift_x"], tilt["shift_y"]
         eng.close()
     changes = refined.copy()
-    for k in ("defocus_1", "defocus_2", "score", "logp", "sigma"):
+    for k in ("defocus_1", "defocus_2", "score", "logp", "sigma", "beam_tilt_x", "beam_tilt_y", "image_shift_x", "image_shift_y"):
         changes[k] = refined[k] - rows[k]
     star.write_star(p["out_star"], refined)
     star.write_star(p["out_changes"], changes)
-    zero = np.zeros((1, box, box), dtype=np.float32)
-    for k in ("phase_difference", "beamtilt_image", "difference_image"):
-        mrc.write(p[k], zero, p["pixel_size"])
+    zero = np.zeros((box, box), dtype=np.float32)
+    for k, img in (("phase_difference", "phase"), ("beamtilt_image", "model"), ("difference_image", "difference")):
+        mrc.write(p[k], (tilt[img] if tilt else zero)[None], p["pixel_size"])
     out.write(banner("RefineCTF"))
     out.write(f"\nRefining defocus of particles {first} to {last} ({rows.size} rows), {n_evals} projections scored in {time.time() - t0:.2f} s\n")
     if rows.size:
         out.write(f"Mean defocus change {float(changes['defocus_1'].mean()):+.1f} A, mean score change {float(changes['score'].mean()):+.4f}\n")
-    if p["beam_tilt"]:
-        out.write("Beam tilt estimation is not implemented in cspb200: beam tilt columns unchanged, diagnostic images are zero\n")
+    if tilt:
+        out.write(f"Beam tilt ({tilt['beam_tilt_x']:+.4f}, {tilt['beam_tilt_y']:+.4f}) mrad, particle shift "
+                  f"({tilt['shift_x']:+.4f}, {tilt['shift_y']:+.4f}) A, weighted phase residual {tilt['rms']:.4f} rad\n")
     out.write("\nRefineCTF: Normal termination\n")
     return refined
 

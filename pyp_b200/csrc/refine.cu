@@ -1191,6 +1191,101 @@ extern "C" int cspb_refine_set_focus_mask(cspb_ctx *ctx, float x, float y, float
     return 0;
 }
 
+// ================================================================== beam-tilt phase sum (refine_ctf answer 23)
+// S(i,j) = sum over the images of G * conj(CTF * slice) on the scoring band (oracle/SEMANTICS.md §12): one
+// thread per band slot walks a strided subset of the images (coalesced reads of the packed spectra,
+// one gather per image — the cost of one score evaluation per particle); NG image groups run in
+// parallel and are reduced in a fixed order (deterministic).
+__global__ void pose_matrix_kernel(const cspb_row *__restrict__ rows, int n, float inv_npx2, float *__restrict__ m8) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float r[9];
+    euler_matrix(rows[k].psi, rows[k].theta, rows[k].phi, r);
+    float *o = m8 + (long long)k * 8;
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[3]; o[3] = r[4]; o[4] = r[6]; o[5] = r[7];
+    o[6] = rows[k].x_shift * inv_npx2; o[7] = rows[k].y_shift * inv_npx2;
+}
+
+__global__ void phase_sum_kernel(const float4 *__restrict__ ref4, int sx, int sy, int rc, float padf,
+                                 const int32_t *__restrict__ slot_ij, int n_slots, const float2 *__restrict__ packed,
+                                 const CtfCoef *__restrict__ ctf, const float *__restrict__ m8, int n_img, int NG,
+                                 float2 *__restrict__ partial) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int32_t ij = slot_ij[s];
+    const int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+    float2 acc = make_float2(0.f, 0.f);
+    if (i != CSPB_DUMMY_I) {
+        const float fi = (float)i, fj = (float)j, r2 = fi * fi + fj * fj;
+        for (int img = blockIdx.y; img < n_img; img += NG) {
+            const float4 ma = __ldg(reinterpret_cast<const float4 *>(m8 + (long long)img * 8));
+            const float4 mb = __ldg(reinterpret_cast<const float4 *>(m8 + (long long)img * 8 + 4));
+            const float2 P = gather_trilinear(ref4, sx, sy, rc, (ma.x * fi + ma.y * fj) * padf, (ma.z * fi + ma.w * fj) * padf,
+                                              (mb.x * fi + mb.y * fj) * padf);
+            const float cv = -sinpif(ctf_chi(ctf[img], fi, fj, r2) * (1.f / CSPB_PI_F));
+            float sn, cs;
+            sincospif(fi * mb.z + fj * mb.w, &sn, &cs);
+            const float2 f = __ldcs(packed + (long long)img * n_slots + s);
+            const float gr = f.x * cs - f.y * sn, gi = f.x * sn + f.y * cs;
+            acc.x += cv * (gr * P.x + gi * P.y);
+            acc.y += cv * (gi * P.x - gr * P.y);
+        }
+    }
+    partial[(long long)blockIdx.y * n_slots + s] = acc;
+}
+
+__global__ void phase_sum_scatter_kernel(const float2 *__restrict__ partial, int NG, const int32_t *__restrict__ slot_ij, int n_slots,
+                                         int n, float2 *__restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int32_t ij = slot_ij[s];
+    const int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+    if (i == CSPB_DUMMY_I) return;
+    float2 t = make_float2(0.f, 0.f);
+    for (int g = 0; g < NG; ++g) {
+        const float2 v = partial[(long long)g * n_slots + s];
+        t.x += v.x; t.y += v.y;
+    }
+    const int jj = j < 0 ? j + n : j;
+    out[jj * (n / 2 + 1) + i] = t;
+}
+
+extern "C" int cspb_refine_phase_sum(cspb_ctx *ctx, const cspb_row *rows, int n_rows, float *out_complex) {
+    if (!ctx || !rows || !out_complex || n_rows < 0) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (n_rows != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n_rows, ctx->n_images);
+    const cspb_refine_cfg &c = ctx->rcfg;
+    const int n = c.box, nh = n / 2 + 1, n_slots = ctx->plan.n_slots;
+    const size_t out_bytes = (size_t)n * nh * sizeof(float2);
+    if (n_rows == 0) { memset(out_complex, 0, out_bytes); return 0; }
+    cspb_row *d_rows;
+    CtfCoef *d_ctf;
+    int rc = upload_rows(ctx, rows, n_rows, &d_rows, &d_ctf);
+    if (rc) return rc;
+    int NG = (8 * ctx->sm_count) / ceil_div(n_slots, 256);
+    if (NG < 1) NG = 1;
+    if (NG > n_rows) NG = n_rows;
+    RESERVE(ctx, ctx->d_evals, (size_t)n_rows * 8 * sizeof(float));
+    RESERVE(ctx, ctx->d_out, (size_t)NG * n_slots * sizeof(float2));
+    RESERVE(ctx, ctx->d_work2, out_bytes);
+    float *m8 = ctx->d_evals.as<float>();
+    pose_matrix_kernel<<<ceil_div(n_rows, 128), 128, 0, ctx->stream>>>(d_rows, n_rows, 2.f / ((float)n * c.pixel_size), m8);
+    KERNEL_CHECK(ctx);
+    dim3 grid(ceil_div(n_slots, 256), NG);
+    phase_sum_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->ref.d_ref4.as<float4>(), ctx->ref.sx, ctx->ref.sy, ctx->ref.rc,
+                                                    (float)ctx->ref.pad, ctx->plan.d_slot_ij.as<int32_t>(), n_slots,
+                                                    ctx->d_packed.as<float2>(), d_ctf, m8, n_rows, NG, ctx->d_out.as<float2>());
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_work2.p, 0, out_bytes, ctx->stream));
+    phase_sum_scatter_kernel<<<ceil_div(n_slots, 256), 256, 0, ctx->stream>>>(ctx->d_out.as<float2>(), NG,
+                                                                             ctx->plan.d_slot_ij.as<int32_t>(), n_slots, n,
+                                                                             ctx->d_work2.as<float2>());
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaMemcpyAsync(out_complex, ctx->d_work2.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int search_enqueue(cspb_ctx *ctx, const CtfCoef *d_ctf, const float *d_angles3, int n_orient, int K, void *d_hits);
 
 // enqueue the whole refinement on the stream; rows/ctf already on the device.  With global search

@@ -140,6 +140,14 @@ class Engine:
         sphere centre / radius in Angstrom from the corner of the map; radius <= 0 switches it off."""
         self._ck(self._l.cspb_refine_set_focus_mask(self._h, float(x), float(y), float(z), float(radius)))
 
+    def phase_sum(self, rows):
+        """Beam-tilt input of refine_ctf: sum of G * conj(CTF * slice) over the loaded images at the poses of
+        `rows`, on the (box, box/2+1) half-plane grid (zero outside the scoring band)."""
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        out = np.zeros((self.box, self.box // 2 + 1), dtype=np.complex64)
+        self._ck(self._l.cspb_refine_phase_sum(self._h, ptr(rows), int(rows.size), ptr(out)))
+        return out
+
     def noise_curve(self):
         out = np.zeros(self.box + 1, dtype=np.float32)
         self._ck(self._l.cspb_refine_get_noise_curve(self._h, ptr(out), out.size))

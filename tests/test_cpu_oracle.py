@@ -223,3 +223,30 @@ def test_symmetry_groups_close():
             assert np.min(np.abs(m - p).reshape(order, -1).max(axis=1)) < 1e-5
     with pytest.raises(ValueError):
         symmetry_matrices("X3")
+
+
+def test_beam_tilt_is_recovered_from_the_phase_sum(oracle):
+    """refine_ctf answer 23 (frealign.py:3995-4041): images whose transforms carry the coma phase of a
+    tilted beam -> phase sum over the particles -> least-squares fit gives the tilt back (SEMANTICS.md §12)."""
+    from pyp_b200 import beamtilt
+
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=48, snr=1.0)
+    truth = (2.0, -1.5)  # mrad
+    tilted = beamtilt.apply_to_stack(stack, px, 300.0, 2.7, truth)
+    cfg = _cfg(oracle, n, px, whiten=0)
+    ref = oracle.Reference(vol, 1)
+    rows = rows.astype(oracle.ROW_DTYPE)
+    for data, want in ((tilted, truth), (stack, (0.0, 0.0))):
+        specs = oracle.prepare_images(data, cfg, None)
+        S = oracle.phase_sum(ref, specs, rows, cfg)
+        assert S.shape == (n, n // 2 + 1) and np.count_nonzero(S) >= oracle.band_count(cfg) - 2
+        f = beamtilt.fit(S, px, 300.0, 2.7)
+        assert abs(f["beam_tilt_x"] - want[0]) < 0.25 and abs(f["beam_tilt_y"] - want[1]) < 0.25, f
+        assert abs(f["shift_x"]) < 0.3 and abs(f["shift_y"]) < 0.3
+        assert f["phase"].shape == (n, n) and np.allclose(f["phase"][1:, 1:], -f["phase"][1:, 1:][::-1, ::-1], atol=1e-5)
+    # the fit is exact on its own model
+    gx = beamtilt.tilt_phase(n, px, 300.0, 2.7, (1.0, 0.5), (0.2, -0.1))
+    S = np.exp(1j * gx) * (np.hypot(*np.meshgrid(np.arange(n // 2 + 1), np.fft.fftfreq(n, 1 / n))) < 24)
+    f = beamtilt.fit(S, px, 300.0, 2.7)
+    assert abs(f["beam_tilt_x"] - 1.0) < 1e-6 and abs(f["beam_tilt_y"] - 0.5) < 1e-6 and abs(f["shift_x"] - 0.2) < 1e-6

@@ -172,8 +172,11 @@ def test_refine_ctf_cli_recovers_defocus(tmp_path):
     merges (frealign.py:3133-3154)."""
     from pyp_b200.formats import star
 
+    from pyp_b200 import beamtilt
+
     n, px, n_part = 64, 1.35, 24
     ph, vol, rows, stack = small_case(n=n, n_part=n_part, snr=1.0)
+    stack = beamtilt.apply_to_stack(stack, px, 300.0, 2.7, (1.5, -1.0))  # answer 23: a tilted beam to find
     start = rows.copy()
     start["defocus_1"] += 400.0
     start["defocus_2"] += 400.0
@@ -187,7 +190,7 @@ def test_refine_ctf_cli_recovers_defocus(tmp_path):
          1, n_part, px, 100.0, 0, 0.38 * n * px, 60.0, 4 * px, 1000.0, "50.0", 1, "yes", "yes", "yes", "no", "no", "no", "no"]
     assert sh("refine_ctf", a, d, "ctf.log") == 0
     log = open(f"{d}/ctf.log").read()
-    assert "RefineCTF: Normal termination" in log and "not implemented" in log
+    assert "RefineCTF: Normal termination" in log and "Beam tilt (" in log
     got = star.read_star(f"{d}/ds_r01_0000001_0000024_refined_ctf.star")
     assert got.size == n_part and list(got["position_in_stack"]) == list(range(1, n_part + 1))
     err0 = np.abs(start["defocus_1"] - rows["defocus_1"]).mean()
@@ -196,4 +199,8 @@ def test_refine_ctf_cli_recovers_defocus(tmp_path):
     assert np.array_equal(got["psi"], start["psi"]) and np.allclose(got["defocus_1"] - got["defocus_2"], start["defocus_1"] - start["defocus_2"], atol=1e-2)
     chg = star.read_star(f"{d}/ds_r01_0000001_0000024_changes.star")
     assert np.allclose(chg["defocus_1"], got["defocus_1"] - start["defocus_1"], atol=1e-2)
-    assert os.path.exists(f"{d}/ds_r01_beamtilt_image.mrc")
+    # beam tilt of the range (mrad) in every row, diagnostic images written (24 particles: loose bound)
+    assert np.ptp(got["beam_tilt_x"]) == 0 and abs(got["beam_tilt_x"][0] - 1.5) < 0.5 and abs(got["beam_tilt_y"][0] + 1.0) < 0.5
+    _, model = mrc.read(f"{d}/ds_r01_beamtilt_image.mrc")
+    _, phase = mrc.read(f"{d}/ds_r01_phase_difference.mrc")
+    assert model.shape[-2:] == (n, n) and np.abs(model).max() > 0.05 and np.abs(phase).max() > 0.05

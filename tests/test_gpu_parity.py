@@ -230,6 +230,30 @@ def test_focus_mask_logp_matches_oracle(engine, oracle):
     assert np.array_equal(again["logp"], plain["logp"])
 
 
+def test_phase_sum_matches_oracle_and_gives_the_beam_tilt(engine, oracle):
+    """refine_ctf answer 23 (frealign.py:3995-4041): sum of G * conj(CTF * slice) over the particles,
+    CUDA vs oracle, and the coma fit on it recovers the tilt put into the data (SEMANTICS.md §12)."""
+    from pyp_b200 import beamtilt
+
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=48, snr=1.0)
+    truth = (2.0, -1.5)
+    stack = beamtilt.apply_to_stack(stack, px, 300.0, 2.7, truth)
+    cfg = refine_cfg(n, px)
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    engine.load_images(stack)
+    ocfg = oracle.refine_cfg_from(cfg)
+    specs = oracle.prepare_images(stack, ocfg, oracle.noise_curve(stack, ocfg))
+    ref = oracle.Reference(vol, cfg.pad)
+    got = engine.phase_sum(rows)
+    want = oracle.phase_sum(ref, specs, rows.astype(oracle.ROW_DTYPE), ocfg)
+    assert np.array_equal(got != 0, want != 0)
+    assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()
+    f = beamtilt.fit(got, px, 300.0, 2.7)
+    assert abs(f["beam_tilt_x"] - truth[0]) < 0.25 and abs(f["beam_tilt_y"] - truth[1]) < 0.25, f
+
+
 def test_global_search_matches_oracle(engine, oracle):
     """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally.
     Same grid, same band, same box reduction on both sides; the best orientation/shift choice must
