@@ -566,7 +566,7 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
             const long long tot = (long long)n_entries * nc;
             csp_expand_kernel<<<ceil_div(tot, 256), 256, 0, ctx->stream>>>(list, n_entries, nc, n_shared, PB, T, pl.kind, params, poses, units);
             KERNEL_CHECK(ctx);
-            int r = launch_score_classes(ctx, units, n_entries, nc - n_shared, n_shared, PB, poses, d_ctf, out, ddef);
+            int r = launch_score_classes(ctx, units, n_entries, nc - n_shared, n_shared, PB, poses, d_ctf, out, ddef, false);
             if (r) return r;
             evals += tot;
         }

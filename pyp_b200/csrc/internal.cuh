@@ -205,12 +205,14 @@ int recon_flush_deferred(cspb_ctx *ctx);
 // enqueue the scoring kernel over `n_units` units; poses6 per eval = psi, theta, phi (deg), shift x, y
 // (Angstrom), defocus delta (Angstrom); out per eval = {numerator, signed X, A, B}
 // every unit of the range has exactly `count` poses (one template instance per count, branch free);
-// shared = rotation and CTF of the unit's first pose apply to all its poses (pure shift variations)
+// mode 1 (shared) = rotation and CTF of the unit's first pose apply to all its poses (pure shift variations);
+// mode 2 (same shift) = the shift of the unit's first pose applies to all its poses (pure rotation / defocus variations)
 int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, bool shared);
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, int mode);
 // units in class layout [A full][A tail][S full][S tail] (opt.cuh); nA plain + nS shared evals per group
+// a_same_shift: every pose of an A unit carries the shift of the unit's first pose (refine3d stencils)
 int launch_score_classes(cspb_ctx *ctx, const ScoreUnit *d_units, int n_groups, int nA, int nS, int PB, const float *d_poses6,
-                         const CtfCoef *d_ctf, float4 *d_out, bool ddef);
+                         const CtfCoef *d_ctf, float4 *d_out, bool ddef, bool a_same_shift);
 // upload rows next to their CTF coefficients (ctx->d_rows)
 int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, CtfCoef **d_ctf);
 

@@ -249,11 +249,16 @@ __device__ __forceinline__ void sincospi_fast(float v, float *sn, float *cs) {
 // branch free so that the 4 * PB gathers of a sample are in flight together.
 // 64 registers -> 8 CTAs = 32 warps per SM: the kernel is bound by L2/DRAM latency of the gathers
 // (long-scoreboard stalls), more resident warps measured +10 % over the 72-register build
-template <int PB, bool DDEF, bool SHARED>
+template <int PB, bool DDEF, int MODE>
 #ifndef CSPB_SCORE_MINB
 #define CSPB_SCORE_MINB 6
 #endif
 __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(const ScoreArgs A) {
+    // MODE 0: every pose has its own rotation and shift.  MODE 1 (SHARED): rotation and CTF of pose 0 hold
+    // for all poses (the optimiser's +-x, +-y evaluations): one gather, PB phase ramps.  MODE 2 (SAMESHIFT):
+    // the shift of pose 0 holds for all poses (the centre and the +-angle / +-defocus evaluations): the
+    // image is shifted once per sample, PB gathers.
+    constexpr bool SHARED = MODE == 1, SAMESHIFT = MODE == 2;
     __shared__ float s_pose[4][PB][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int u = blockIdx.x * 4 + warp;
@@ -311,6 +316,14 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
             float ctfv = 0.f;
             if (!DDEF) ctfv = valid ? -sinpif(chi0 * (1.f / CSPB_PI_F)) : 0.f;
             accA += F.x * F.x + F.y * F.y;
+            float g0r = 0.f, g0i = 0.f;
+            if (SAMESHIFT) {
+                const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][0][6]);
+                float sn, cs;
+                sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
+                g0r = F.x * cs - F.y * sn;
+                g0i = F.x * sn + F.y * cs;
+            }
             // SHARED units (the optimiser's +-x, +-y evaluations): rotation and CTF of pose 0 hold for
             // every pose of the unit — one gather, PB phase ramps
             constexpr int NG = SHARED ? 1 : PB;
@@ -359,13 +372,18 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
                 pyv *= cv;
                 accB[p] += pxv * pxv + pyv * pyv;
 #pragma unroll
-                for (int pp = 0; pp < (SHARED ? PB : 1); ++pp) {
-                    const int e = SHARED ? pp : p;
-                    const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][e][6]);
-                    float sn, cs;
-                    sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
-                    const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
-                    accX[e] += gr * pxv + gi * pyv;
+                if (SAMESHIFT) {
+                    accX[p] += g0r * pxv + g0i * pyv;
+                } else {
+#pragma unroll
+                    for (int pp = 0; pp < (SHARED ? PB : 1); ++pp) {
+                        const int e = SHARED ? pp : p;
+                        const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][e][6]);
+                        float sn, cs;
+                        sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
+                        const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
+                        accX[e] += gr * pxv + gi * pyv;
+                    }
                 }
             }
         }
@@ -565,7 +583,7 @@ int grid_for(long long total, int block, int sm) {
 
 // every unit in [d_units, d_units + n_units) has exactly `count` poses (1..4)
 int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, bool shared) {
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, int mode) {
     if (n_units <= 0) return 0;
     if (count < 1 || count > 4) return cspb_fail(ctx, CSPB_E_ARG, "launch_score: bad unit size %d", count);
     ScoreArgs a;
@@ -589,12 +607,15 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count
     prof_begin(ctx, CSPB_PROF_SCORE, n_evals);
 #define CSPB_LAUNCH_SCORE(PB_)                                                              \
     do {                                                                                    \
-        if (shared) {                                                                       \
-            if (ddef) score_kernel<PB_, true, true><<<grid, 128, 0, ctx->stream>>>(a);      \
-            else score_kernel<PB_, false, true><<<grid, 128, 0, ctx->stream>>>(a);          \
+        if (mode == 1) {                                                                    \
+            if (ddef) score_kernel<PB_, true, 1><<<grid, 128, 0, ctx->stream>>>(a);         \
+            else score_kernel<PB_, false, 1><<<grid, 128, 0, ctx->stream>>>(a);             \
+        } else if (mode == 2 && PB_ > 1) {                                                  \
+            if (ddef) score_kernel<PB_, true, 2><<<grid, 128, 0, ctx->stream>>>(a);         \
+            else score_kernel<PB_, false, 2><<<grid, 128, 0, ctx->stream>>>(a);             \
         } else {                                                                            \
-            if (ddef) score_kernel<PB_, true, false><<<grid, 128, 0, ctx->stream>>>(a);     \
-            else score_kernel<PB_, false, false><<<grid, 128, 0, ctx->stream>>>(a);         \
+            if (ddef) score_kernel<PB_, true, 0><<<grid, 128, 0, ctx->stream>>>(a);         \
+            else score_kernel<PB_, false, 0><<<grid, 128, 0, ctx->stream>>>(a);             \
         }                                                                                   \
     } while (0)
     switch (count) {
@@ -612,13 +633,14 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count
 // units in the class layout of opt_stencil_kernel / csp_expand_kernel:
 // [A full: n*(nA/PB)] [A tail: n if nA%PB] [S full: n*(nS/PB)] [S tail: n if nS%PB]; S = shared units
 int launch_score_classes(cspb_ctx *ctx, const ScoreUnit *d_units, int n_groups, int nA, int nS, int PB, const float *d_poses6,
-                         const CtfCoef *d_ctf, float4 *d_out, bool ddef) {
+                         const CtfCoef *d_ctf, float4 *d_out, bool ddef, bool a_same_shift) {
     const int cls[4][2] = {{nA / PB, PB}, {nA % PB ? 1 : 0, nA % PB}, {nS / PB, PB}, {nS % PB ? 1 : 0, nS % PB}};
     size_t off = 0;
     for (int c = 0; c < 4; ++c) {
         const int n_units = n_groups * cls[c][0];
         if (n_units == 0) continue;
-        int rc = launch_score(ctx, d_units + off, n_units, cls[c][1], d_poses6, d_ctf, d_out, ddef, (int64_t)n_units * cls[c][1], c >= 2);
+        int rc = launch_score(ctx, d_units + off, n_units, cls[c][1], d_poses6, d_ctf, d_out, ddef, (int64_t)n_units * cls[c][1],
+                              c >= 2 ? 1 : (a_same_shift ? 2 : 0));
         if (rc) return rc;
         off += n_units;
     }
@@ -1049,7 +1071,7 @@ extern "C" int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int 
     size_t off = 0;
     for (int c = 1; c <= 4; ++c) {
         rc = launch_score(ctx, ctx->d_units.as<ScoreUnit>() + off, (int)units[c].size(), c, ctx->d_evals.as<float>(), d_ctf, d_out, ddef,
-                          (int64_t)units[c].size() * c, false);
+                          (int64_t)units[c].size() * c, 0);
         if (rc) return rc;
         off += units[c].size();
     }
@@ -1350,6 +1372,8 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     const float h_shift = coarse * 0.07f * (float)c.box / r_hi * c.pixel_size;  // Angstrom
     const float h_def = c.defocus_step > 0.f ? c.defocus_step : 50.f;
     const int g = ceil_div(ns, 128);
+    const char *ss_env = getenv("CSPB_SAMESHIFT");  // =0: score the A class with the general kernel (A/B measurements)
+    const bool same_shift = !(ss_env && ss_env[0] == '0');
     const bool focus_on = ctx->focus[3] > 0.f;
     if (focus_on) RESERVE(ctx, ctx->d_alpha, (size_t)n * sizeof(float));
     OptPrior pr{};
@@ -1368,11 +1392,12 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     for (int it = 0; it < iters; ++it) {
         opt_stencil_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, shift_mask, NE, PB, ev, un);
         KERNEL_CHECK(ctx);
-        int rc = launch_score_classes(ctx, un, ns, NE - nS, nS, PB, ev, d_ctf, out, ddef);
+        // the A class (centre, +-angles, +-defocus) keeps the centre's shift: the image is shifted once per sample
+        int rc = launch_score_classes(ctx, un, ns, NE - nS, nS, PB, ev, d_ctf, out, ddef, same_shift);
         if (rc) return rc;
         opt_step_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, free_mask, NE, out, ev_ls, un_ls, pr);
         KERNEL_CHECK(ctx);
-        rc = launch_score(ctx, un_ls, ns, OPT_NL, ev_ls, d_ctf, out_ls, ddef, (int64_t)ns * OPT_NL, false);
+        rc = launch_score(ctx, un_ls, ns, OPT_NL, ev_ls, d_ctf, out_ls, ddef, (int64_t)ns * OPT_NL, 0);
         if (rc) return rc;
         opt_select_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, out_ls, it + 1 >= late ? 0.6f : 1.f, pr);
         KERNEL_CHECK(ctx);
@@ -1380,7 +1405,7 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     }
     opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, ns, K, ev, un);
     KERNEL_CHECK(ctx);
-    int rc = launch_score(ctx, un, ns, 2, ev, d_ctf, out, ddef, 2 * (int64_t)ns, false);
+    int rc = launch_score(ctx, un, ns, 2, ev, d_ctf, out, ddef, 2 * (int64_t)ns, 0);
     if (rc) return rc;
     evals += 2 * (int64_t)ns;
     opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, K, out, ctx->plan.n_band, c.refine_defocus, d_rows, d_changes, pr,
