@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-OUT=../libcspb200.so
+OUT=${OUT:-../libcspb200.so}
 SRCS="capi plan fft refine search recon csp pipeline"
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT

@@ -87,9 +87,8 @@ __host__ __device__ __forceinline__ CtfCoef make_ctf_coef(float d1, float d2, fl
 
 // phase chi at frequency index (fi, fj), r2 = fi^2 + fj^2
 __device__ __forceinline__ float ctf_chi(const CtfCoef &c, float fi, float fj, float r2) {
-    const float inv = r2 > 0.f ? 1.f / r2 : 0.f;
-    const float c2a = (fi * fi - fj * fj) * inv, s2a = 2.f * fi * fj * inv;
-    return r2 * (c.a + c.b * (c2a * c.cos2ast + s2a * c.sin2ast)) + c.c4 * r2 * r2 + c.ph0;
+    // r2 cos 2(alpha) = fi^2 - fj^2 and r2 sin 2(alpha) = 2 fi fj: no division by r2
+    return r2 * c.a + c.b * ((fi * fi - fj * fj) * c.cos2ast + 2.f * fi * fj * c.sin2ast) + c.c4 * r2 * r2 + c.ph0;
 }
 
 // trilinear gather from the cropped centred x-paired reference (Friedel flip for x < 0)

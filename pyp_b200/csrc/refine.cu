@@ -232,6 +232,29 @@ __device__ __forceinline__ void ldg_quad_if(const RefQuad *p, bool take, RefQuad
         : "l"(p), "r"((int)take));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2 / FMUL2 on an aligned register pair).  A complex
+// value lives in one 64-bit register; a trilinear interpolation is 7 FADD2 + 7 FFMA2 instead of 28 scalar
+// instructions, with the same roundings (a + f (b - a) per component).
+typedef unsigned long long f32x2;
+struct QuadP { f32x2 v00, v10, v01, v11; };  // register image of a RefQuad
+__device__ __forceinline__ QuadP ldg_quadp(const RefQuad *p) {
+    QuadP q;
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q.v00), "=l"(q.v10), "=l"(q.v01), "=l"(q.v11) : "l"(p));
+    return q;
+}
+// predicated: lanes with `take` false issue no memory traffic and keep `q`
+__device__ __forceinline__ void ldg_quadp_if(const RefQuad *p, bool take, QuadP &q) {
+    asm("{\n\t.reg .pred t;\n\tsetp.ne.s32 t, %5, 0;\n\t@t ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "+l"(q.v00), "+l"(q.v10), "+l"(q.v01), "+l"(q.v11)
+        : "l"(p), "r"((int)take));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 pack2(float x, float y) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y)); return d; }
+__device__ __forceinline__ float sum2(f32x2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return x + y; }
+__device__ __forceinline__ f32x2 lerp2(f32x2 a, f32x2 b, f32x2 f) { return fma2(f, sub2(b, a), a); }
+
 // sin / cos of pi * v on the MUFU pipe: v is reduced to [-1, 1] first, where sin.approx / cos.approx
 // are good to 2^-21 absolute — the size of the fp32 rounding of the phase itself
 __device__ __forceinline__ void sincospi_fast(float v, float *sn, float *cs) {
@@ -242,16 +265,26 @@ __device__ __forceinline__ void sincospi_fast(float v, float *sn, float *cs) {
     *cs = __cosf(a);
 }
 
+// -sin(chi) of the CTF on the MUFU pipe: chi / pi is reduced to [-1, 1] exactly, sin.approx is good to 2^-21
+// there — below the fp32 rounding of chi itself (chi reaches hundreds of radians at the band edge)
+__device__ __forceinline__ float ctf_from_chi_fast(float chi) {
+    const float v = chi * (1.f / CSPB_PI_F);
+    const float M = 12582912.f;
+    const float k = (v * 0.5f + M) - M;
+    return -__sinf((v - 2.f * k) * CSPB_PI_F);
+}
+
 // One warp per unit = (image, exactly PB poses).  Lanes walk the polar-patch band plan:
-// coalesced 8-byte reads of the packed image, CTF synthesised once per sample and shared by the
-// unit's poses, trilinear gather as 4 x 16-byte loads from the x-paired reference, per-ring sums
-// kept in one register per pose (lane%4 = ring offset inside the 4-ring band).  The pose loop is
-// branch free so that the 4 * PB gathers of a sample are in flight together.
-// 64 registers -> 8 CTAs = 32 warps per SM: the kernel is bound by L2/DRAM latency of the gathers
-// (long-scoreboard stalls), more resident warps measured +10 % over the 72-register build
+// coalesced 8-byte reads of the packed image, CTF synthesised once per sample (MUFU) and shared by the
+// unit's poses, trilinear gather as 2 x 32-byte loads from the quad reference, interpolation in packed
+// fp32x2 (one complex value per register pair), per-ring sums closed with 3 shuffles per ring band
+// (lane%4 = ring offset inside the 4-ring band).  The pose loop is branch free and the slot loop is
+// unrolled twice so that the 4 * PB gathers of two samples are in flight together: the kernel waits on
+// gather latency, and 16 warps x 2 samples in flight (128 registers, r01g) beat 24 warps x 1 sample
+// (80 registers) by 6 %; 3 samples / 12 warps and 2 samples / 20 warps (spills) were slower.
 template <int PB, bool DDEF, int MODE>
 #ifndef CSPB_SCORE_MINB
-#define CSPB_SCORE_MINB 6
+#define CSPB_SCORE_MINB 4
 #endif
 __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(const ScoreArgs A) {
     // MODE 0: every pose has its own rotation and shift.  MODE 1 (SHARED): rotation and CTF of pose 0 hold
@@ -289,24 +322,30 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
     // per-ring-offset running sums {numerator, signed total} live in shared memory (lanes 0..3 of the
     // warp own them): they are touched once per ring band and would otherwise pin 2 PB registers
     __shared__ float2 s_ring[4][PB][4];
-    float accB[PB];
+    f32x2 accB[PB];  // {sum px^2, sum py^2}
 #pragma unroll
     for (int p = 0; p < PB; ++p) {
-        accB[p] = 0.f;
+        accB[p] = 0ull;
         if (lane < 4) s_ring[warp][p][lane] = make_float2(0.f, 0.f);
     }
-    float accA = 0.f;
+    f32x2 accA = 0ull;
 
     for (int b = 0; b < A.n_bands; ++b) {
         const BandDesc bd = A.bands[b];
-        float accX[PB];
+        f32x2 accX[PB];  // {sum gr px, sum gi py}
 #pragma unroll
-        for (int p = 0; p < PB; ++p) accX[p] = 0.f;
-#pragma unroll 1
+        for (int p = 0; p < PB; ++p) accX[p] = 0ull;
+#ifndef CSPB_SCORE_UNROLL
+#define CSPB_SCORE_UNROLL 2
+#endif
+#define CSPB_PRAGMA_(x) _Pragma(#x)
+#define CSPB_UNROLL_(n) CSPB_PRAGMA_(unroll n)
+        CSPB_UNROLL_(CSPB_SCORE_UNROLL)
         for (int it = 0; it < bd.n_iter; ++it) {
             const int slot = bd.slot_start + it * 32 + lane;
             const int32_t ij = __ldg(A.slot_ij + slot);
-            const float2 F = __ldcs(img + slot);  // read once per unit: streaming, keeps the reference in L2
+            const f32x2 Fp = __ldcs(reinterpret_cast<const f32x2 *>(img + slot));  // read once per unit: streaming
+            const float2 F = make_float2(__uint_as_float((unsigned)Fp), __uint_as_float((unsigned)(Fp >> 32)));
             int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
             const bool valid = (i != CSPB_DUMMY_I);
             if (!valid) { i = 0; j = 0; }
@@ -314,15 +353,14 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
             const float r2 = fi * fi + fj * fj;
             const float chi0 = ctf_chi(cc, fi, fj, r2);
             float ctfv = 0.f;
-            if (!DDEF) ctfv = valid ? -sinpif(chi0 * (1.f / CSPB_PI_F)) : 0.f;
-            accA += F.x * F.x + F.y * F.y;
-            float g0r = 0.f, g0i = 0.f;
+            if (!DDEF) ctfv = valid ? ctf_from_chi_fast(chi0) : 0.f;
+            accA = fma2(Fp, Fp, accA);
+            f32x2 G0 = 0ull;
             if (SAMESHIFT) {
                 const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][0][6]);
                 float sn, cs;
                 sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
-                g0r = F.x * cs - F.y * sn;
-                g0i = F.x * sn + F.y * cs;
+                G0 = pack2(F.x * cs - F.y * sn, F.x * sn + F.y * cs);
             }
             // SHARED units (the optimiser's +-x, +-y evaluations): rotation and CTF of pose 0 hold for
             // every pose of the unit — one gather, PB phase ramps
@@ -330,7 +368,7 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
             // The poses of a unit are neighbours (stencil +-h, line search): more often than not pose p
             // lands in the voxel pose 0 already gathered — those lanes reuse its quads and issue no
             // load (predicated), which removes their share of the L1 wavefronts.
-            RefQuad qa0, qa1;  // quads of pose 0, kept for the poses that land in the same voxel
+            QuadP qa0, qa1;  // quads of pose 0, kept for the poses that land in the same voxel
             int off0 = 0;
 #pragma unroll
             for (int p = 0; p < NG; ++p) {
@@ -346,34 +384,30 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
                 const float f = x - (float)ix, fyv = y - (float)iy, fzv = z - (float)iz;
                 const int off = origin + (iz * A.sy + iy) * A.sx + ix;
                 const RefQuad *q = A.ref8 + off;
-                RefQuad q0, q1;
+                QuadP q0, q1;
                 if (p == 0) {
                     off0 = off;
-                    qa0 = ldg_quad(q);
-                    qa1 = ldg_quad(q + 1);
+                    qa0 = ldg_quadp(q);
+                    qa1 = ldg_quadp(q + 1);
                     q0 = qa0;
                     q1 = qa1;
                 } else {
                     q0 = qa0;
                     q1 = qa1;
-                    ldg_quad_if(q, off != off0, q0);
-                    ldg_quad_if(q + 1, off != off0, q1);
+                    ldg_quadp_if(q, off != off0, q0);
+                    ldg_quadp_if(q + 1, off != off0, q1);
                 }
-                const float v00x = q0.v00.x + f * (q1.v00.x - q0.v00.x), v00y = q0.v00.y + f * (q1.v00.y - q0.v00.y);
-                const float v10x = q0.v10.x + f * (q1.v10.x - q0.v10.x), v10y = q0.v10.y + f * (q1.v10.y - q0.v10.y);
-                const float v01x = q0.v01.x + f * (q1.v01.x - q0.v01.x), v01y = q0.v01.y + f * (q1.v01.y - q0.v01.y);
-                const float v11x = q0.v11.x + f * (q1.v11.x - q0.v11.x), v11y = q0.v11.y + f * (q1.v11.y - q0.v11.y);
-                const float v0x = v00x + fyv * (v10x - v00x), v0y = v00y + fyv * (v10y - v00y);
-                const float v1x = v01x + fyv * (v11x - v01x), v1y = v01y + fyv * (v11y - v01y);
-                float pxv = v0x + fzv * (v1x - v0x), pyv = (v0y + fzv * (v1y - v0y)) * sgn;
+                const f32x2 fx2 = pack2(f, f), fy2 = pack2(fyv, fyv), fz2 = pack2(fzv, fzv);
+                const f32x2 v00 = lerp2(q0.v00, q1.v00, fx2), v10 = lerp2(q0.v10, q1.v10, fx2);
+                const f32x2 v01 = lerp2(q0.v01, q1.v01, fx2), v11 = lerp2(q0.v11, q1.v11, fx2);
+                const f32x2 v0 = lerp2(v00, v10, fy2), v1 = lerp2(v01, v11, fy2);
                 float cv = ctfv;
-                if (DDEF) cv = valid ? -sinpif((chi0 + r2 * ddef[p]) * (1.f / CSPB_PI_F)) : 0.f;
-                pxv *= cv;
-                pyv *= cv;
-                accB[p] += pxv * pxv + pyv * pyv;
-#pragma unroll
+                if (DDEF) cv = valid ? ctf_from_chi_fast(chi0 + r2 * ddef[p]) : 0.f;
+                // CTF on both components, Friedel sign on the imaginary one
+                const f32x2 P = mul2(lerp2(v0, v1, fz2), pack2(cv, cv * sgn));
+                accB[p] = fma2(P, P, accB[p]);
                 if (SAMESHIFT) {
-                    accX[p] += g0r * pxv + g0i * pyv;
+                    accX[p] = fma2(G0, P, accX[p]);
                 } else {
 #pragma unroll
                     for (int pp = 0; pp < (SHARED ? PB : 1); ++pp) {
@@ -381,8 +415,7 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
                         const float2 mc = *reinterpret_cast<const float2 *>(&s_pose[warp][e][6]);
                         float sn, cs;
                         sincospi_fast(fi * mc.x + fj * mc.y, &sn, &cs);
-                        const float gr = F.x * cs - F.y * sn, gi = F.x * sn + F.y * cs;
-                        accX[e] += gr * pxv + gi * pyv;
+                        accX[e] = fma2(pack2(F.x * cs - F.y * sn, F.x * sn + F.y * cs), P, accX[e]);
                     }
                 }
             }
@@ -391,7 +424,7 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
         const int ring = (lane & 1) ? (rpair >> 16) : (rpair & 0xFFFF);
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
-            float v = accX[p];
+            float v = sum2(accX[p]);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -403,17 +436,17 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
             }
         }
     }
-    accA = warp_sum(accA);
+    const float asum = warp_sum(sum2(accA));
 #pragma unroll
     for (int p = 0; p < PB; ++p) {
-        const float bsum = warp_sum(accB[SHARED ? 0 : p]);
+        const float bsum = warp_sum(sum2(accB[SHARED ? 0 : p]));
         const float2 t = s_ring[warp][p][lane & 3];
         float nv = t.x, xv = t.y;
         nv += __shfl_xor_sync(0xffffffffu, nv, 1);
         nv += __shfl_xor_sync(0xffffffffu, nv, 2);
         xv += __shfl_xor_sync(0xffffffffu, xv, 1);
         xv += __shfl_xor_sync(0xffffffffu, xv, 2);
-        if (lane == 0) A.out[un.first_eval + p] = make_float4(nv, xv, accA, bsum);
+        if (lane == 0) A.out[un.first_eval + p] = make_float4(nv, xv, asum, bsum);
     }
 }
 
