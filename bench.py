@@ -416,7 +416,7 @@ def run_b200_arm(a):
         "refine3d_scored_projections_per_sec": evals_total / a.steps / ((stage[0] + stage[1]) * 1e-3),
         "stage_ms_per_step": {"preprocess": stage[0], "refine": stage[1], "insert": stage[2], "reduce_finalize": stage[3],
                               "score_kernels": score_ms / a.steps, "insert_kernel": ins_ms / a.steps},
-        "roofline": {"bound": "hbm", "kernel": "score_kernel<4,false>", "achieved": score_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "score_kernel<4,false,2>", "achieved": score_gbs, "peak": peak, "unit": "GB/s",
                      "frac": score_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                      "note": "gather served by L1/L2 (reference volume L2-resident): algorithmic bytes exceed the HBM peak; the kernel's own ceiling is the SM data pipe, measured live as gather_peak_* (random 32-byte gathers); gather_achieved counts the 64 B/sample of the algorithm, of which the kernel really loads about half (neighbouring poses reuse quads, shift evaluations share one gather)",
                      "gather_peak_l2_resident": gather_l2, "gather_peak_l1_resident": gather_l1,
