@@ -394,12 +394,14 @@ def run_b200_arm(a):
         gather_l2, gather_l1 = eng.gather_peak(64 << 20), eng.gather_peak(32 << 10, per_cta=True)
     except Exception:
         gather_l2 = gather_l1 = None
-    traffic = None
+    traffic = l1_frac = None
     try:  # DRAM bytes per launch of the scoring kernel, from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = float(json.load(f)["score_dram_bytes_per_eval"]) * score_units / max(1, score_launches)
+            tj = json.load(f)
+        traffic = float(tj["score_dram_bytes_per_eval"]) * score_units / max(1, score_launches)
+        l1_frac = tj.get("score_l1_data_pipe_frac")
     except Exception:
-        traffic = None
+        traffic = l1_frac = None
     bytes_per_eval = 72.0 * n_band                       # 64 B gather + 8 B image per band sample
     score_gbs = (bytes_per_eval * score_units) / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
     ins_bytes = 96.0 * (ccfg.pad ** 2) * _recon_band(n)  # per projection per literally inserted operator
@@ -421,6 +423,7 @@ def run_b200_arm(a):
                      "note": "gather served by L1/L2 (reference volume L2-resident): algorithmic bytes exceed the HBM peak; the kernel's own ceiling is the SM data pipe, measured live as gather_peak_* (random 32-byte gathers); gather_achieved counts the 64 B/sample of the algorithm, of which the kernel really loads about half (neighbouring poses reuse quads, shift evaluations share one gather)",
                      "gather_peak_l2_resident": gather_l2, "gather_peak_l1_resident": gather_l1,
                      "gather_achieved": score_gbs * 64.0 / 72.0, "gather_frac": (score_gbs * 64.0 / 72.0 / gather_l2) if gather_l2 else None,
+                     "l1_data_pipe_frac_ncu": l1_frac,  # the binding unit of this kernel, from the committed ncu capture
                      "bytes_per_unit": bytes_per_eval, "units_per_launch": score_units / max(1, score_launches),
                      "avg_launch_ms": score_ms / max(1, score_launches)},
         "roofline_insert": {"bound": "hbm", "kernel": "insert_kernel", "achieved": ins_gbs, "peak": peak, "unit": "GB/s",
