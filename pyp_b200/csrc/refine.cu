@@ -993,7 +993,9 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
     const int n = c.box, nh = n / 2 + 1, n_slots = ctx->plan.n_slots;
     const int base = append ? ctx->n_images : 0;
     const int total = base + n_images;
-    if (total > ctx->img_capacity) {
+    // capacity is kept in images of the CURRENT band plan: a reconfiguration (other box or band) changes
+    // n_slots, so the byte size is checked as well
+    if (total > ctx->img_capacity || (size_t)total * n_slots * sizeof(float2) > ctx->d_packed.bytes) {
         const int cap = append ? (total * 3 / 2 > 1024 ? total * 3 / 2 : 1024) : total;
         DevBuf nb;
         RESERVE(ctx, nb, (size_t)cap * n_slots * sizeof(float2));

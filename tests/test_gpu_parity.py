@@ -255,6 +255,25 @@ def test_phase_sum_matches_oracle_and_gives_the_beam_tilt(engine, oracle):
     assert abs(f["beam_tilt_x"] - truth[0]) < 0.25 and abs(f["beam_tilt_y"] - truth[1]) < 0.25, f
 
 
+def test_reconfigure_to_a_larger_box_reallocates_the_packed_images(engine, oracle):
+    """Regression (r01h, tools/check_configs.py C1 -> C4): the packed-image buffer was sized in images of the
+    previous band plan; a context reconfigured from a small box to a larger one with fewer images wrote
+    past it.  Scores after the reconfiguration must equal the oracle's."""
+    _setup(engine, oracle, n=64, n_part=32)
+    n, px = 128, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=12)
+    cfg = refine_cfg(n, px)
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    engine.load_images(stack)
+    ocfg = oracle.refine_cfg_from(cfg)
+    specs = oracle.prepare_images(stack, ocfg, oracle.noise_curve(stack, ocfg))
+    ref = oracle.Reference(vol, cfg.pad)
+    got = engine.score(rows)
+    want = np.array([oracle.score(ref, specs[k], rows[k], pose_of(rows[k]), ocfg)[0] for k in range(rows.size)])
+    assert np.abs(got - want).max() <= SCORE_RTOL * np.abs(want).max()
+
+
 def test_global_search_matches_oracle(engine, oracle):
     """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally.
     Same grid, same band, same box reduction on both sides; the best orientation/shift choice must
