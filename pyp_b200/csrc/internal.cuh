@@ -60,7 +60,7 @@ struct BandPlan {
     std::vector<BandDesc> bands;
     DevBuf d_slot_ij, d_bands;
 };
-bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi);
+bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi, bool radial_order = false);
 
 // ---------------------------------------------------------------- reference volume (scoring)
 // Cropped, centred (y,z shifted by +rc), x-paired Fourier half-volume:

@@ -745,7 +745,10 @@ extern "C" int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg) 
     float r_lo = npx / cfg->low_res_limit, r_hi = npx / cfg->high_res_limit;
     const float r_cap = (float)(cfg->box / 2 - 2);  // keep every trilinear corner below Nyquist
     if (r_hi > r_cap) r_hi = r_cap;
-    if (!build_band_plan(ctx->plan, cfg->box, r_lo, r_hi)) return cspb_fail(ctx, CSPB_E_ARG, "empty band");
+    // the half-sphere of 32-byte quads the scorer touches: beyond the L2 (126 MB) the band keeps the radial ring order
+    const double rc_q = ceil((cfg->pad >= 2 ? 2.0 : 1.0) * r_hi) + 2.0;
+    const bool radial = (2.0 / 3.0) * 3.14159265 * rc_q * rc_q * rc_q * 32.0 > 110e6;
+    if (!build_band_plan(ctx->plan, cfg->box, r_lo, r_hi, radial)) return cspb_fail(ctx, CSPB_E_ARG, "empty band");
     BandPlan &pl = ctx->plan;
     RESERVE(ctx, pl.d_slot_ij, pl.slot_ij.size() * sizeof(int32_t));
     RESERVE(ctx, pl.d_bands, pl.bands.size() * sizeof(BandDesc));
