@@ -26,12 +26,39 @@ def test_shape_scores_matches_reference(tag):
     assert got.tobytes() == want.tobytes()                      # every other column untouched, bit for bit
 
 
+def test_bimodal_cutoff_matches_reference():
+    """reconstruct_cutoff = 0 (scores.py:438-465): threshold = 1.075 x the crossing of the two fitted score
+    populations (statistics.py:10-148).  Fixture by tests/golden/make_golden_bimodal.py from the reference's
+    own functions (seed-independent there by construction)."""
+    pytest.importorskip("sklearn")
+    rows = cistem.read_parameters(os.path.join(G, "shape_bimodal_in.cistem"))
+    want = cistem.read_parameters(os.path.join(G, "shape_bimodal_out.cistem"))
+    ref = json.load(open(os.path.join(G, "shape_bimodal_threshold.json")))
+    thr = select.optimal_threshold(rows["score"])
+    assert abs(thr - ref["optimal_threshold"]) < 1e-6 * abs(ref["optimal_threshold"])
+    for seed in (1, 7):  # the fit does not depend on its k-means start on this table
+        assert abs(select.optimal_threshold(rows["score"], random_state=seed) - thr) < 1e-9
+    got = select.shape_scores(rows, np.zeros(rows.size), 0.0)
+    assert np.array_equal(got["occupancy"], want["occupancy"])
+    assert got.tobytes() == want.tobytes()
+    dropped = got["occupancy"] == 0
+    assert 0.3 < dropped.mean() < 0.5 and rows["score"][dropped].max() < ref["scale"] * thr <= rows["score"][~dropped].min()
+    # degenerate inputs: constant scores -> threshold 1 (statistics.py:19-21); <= 20 values -> no threshold at all
+    assert select.optimal_threshold(np.full(50, 3.0)) == 1.0
+    few = select.shape_scores(rows[:15], np.zeros(15), 0.0)
+    assert (few["occupancy"] == 100).all()
+    # one population: falls back to mean - 3 sigma of a single Gaussian
+    one = np.random.default_rng(3).normal(20.0, 1.0, 2000)
+    t1 = select.optimal_threshold(one)
+    assert t1 < one.mean() - 2.0
+
+
 def test_shape_scores_edges():
     rows = cistem.read_parameters(os.path.join(G, "shape_spa_in.cistem"))
     keep_all = select.shape_scores(rows, np.zeros(rows.size), 1.0)
     assert (keep_all["occupancy"] == 100).all()
     with pytest.raises(ValueError):
-        select.shape_scores(rows, np.zeros(rows.size), 0.0)      # bimodal-fit cutoff is not implemented
+        select.shape_scores(rows, np.zeros(rows.size), 5.0)      # absolute-count cutoffs are not implemented
     with pytest.raises(ValueError):
         select.shape_scores(rows, np.zeros(3), 0.5)
     assert select.shape_scores(rows[:0], np.zeros(0), 0.5).size == 0
