@@ -1,0 +1,83 @@
+"""Table bookkeeping pyp does around the `csp` calls, vectorised over the packed rows:
+
+  * ``update_particle_score`` — after the csp processes are merged, every particle's SCORE becomes the
+    mean SCORE of its projections inside the exposure window (TIND range) or a tilt-angle range;
+    particles with no projection in the window get score -1 and occupancy 0
+    (src/pyp/inout/metadata/cistem_star_file.py:936-986; called at src/pyp/align/core.py:1204 and
+    src/pyp/analysis/scores.py:929);
+  * ``sync_particle_occ`` — copy occupancies between the particle table and the projection rows
+    (cistem_star_file.py:988-1013; align/core.py:912, scores.py:975).
+
+Pinned against the reference's own methods by tests/golden/tables_* (tests/golden/make_golden_tables.py).
+"""
+import numpy as np
+
+
+def _groups(keys):
+    order = np.argsort(keys, kind="stable")
+    sk = keys[order]
+    starts = np.flatnonzero(np.r_[True, sk[1:] != sk[:-1]])
+    return order, sk[starts], starts, np.r_[starts[1:], sk.size]
+
+
+def update_particle_score(rows, particles, tilts=None, tind_range=(0, -1), tiltang_range=(-90, 90)):
+    """Return a copy of `particles` (PARTICLE_DTYPE) with score / occ updated from `rows` (ROW_DTYPE).
+    A non-empty `tind_range` (min, max; max = -1: open) wins over `tiltang_range`, as in the reference."""
+    use_tind, use_ang = len(tind_range) > 0, len(tiltang_range) > 0
+    if not (use_tind or use_ang):
+        raise ValueError("give a TIND range or a tilt-angle range")
+    out = particles.copy()
+    tind = rows["tind"].astype(np.int64)
+    if use_tind:
+        lo, hi = int(tind_range[0]), int(tind_range[1])
+        inside = ~((tind < lo) | ((tind > hi) & (hi != -1)))
+    else:
+        lo, hi = float(tiltang_range[0]), float(tiltang_range[1])
+        if lo > hi:
+            raise ValueError(f"min angle ({lo}) should be smaller than max angle ({hi})")
+        if tilts is None:
+            raise ValueError("a tilt-angle range needs the tilt table")
+        key = {(int(t["tind"]), int(t["rind"])): float(t["angle"]) for t in tilts}
+        ang = np.array([key[(int(a), int(b))] for a, b in zip(rows["tind"], rows["rind"])], dtype=np.float64)
+        inside = (ang >= lo) & (ang <= hi)
+    score = rows["score"].astype(np.float64)[inside]
+    pind = rows["pind"].astype(np.int64)[inside]
+    mean = {}
+    if pind.size:
+        order, ids, starts, ends = _groups(pind)
+        s = score[order]
+        for k, a, b in zip(ids, starts, ends):
+            mean[int(k)] = np.mean(s[a:b])  # np.mean per particle, as the reference (float64 pairwise sum)
+    for i in range(out.size):
+        m = mean.get(int(out["pind"][i]))
+        if m is None:
+            out["score"][i] = -1.0
+            out["occ"][i] = 0.0
+        else:
+            out["score"][i] = m
+    return out
+
+
+def sync_particle_occ(rows, particles, ptl_to_prj=True):
+    """ptl_to_prj: projections take their particle's occupancy; else particles take the mean occupancy of
+    their projections.  Returns (rows, particles) copies; entries without a partner are left alone."""
+    rows, particles = rows.copy(), particles.copy()
+    if ptl_to_prj:
+        ids = particles["pind"].astype(np.int64)
+        order = np.argsort(ids, kind="stable")
+        pos = np.searchsorted(ids[order], rows["pind"].astype(np.int64))
+        pos = np.clip(pos, 0, max(ids.size - 1, 0))
+        if ids.size:
+            hit = ids[order][pos] == rows["pind"]
+            rows["occupancy"][hit] = particles["occ"][order][pos][hit]
+    else:
+        pind = rows["pind"].astype(np.int64)
+        if pind.size:
+            order, gid, starts, ends = _groups(pind)
+            occ = rows["occupancy"].astype(np.float64)[order]
+            mean = {int(k): np.mean(occ[a:b]) for k, a, b in zip(gid, starts, ends)}
+            for i in range(particles.size):
+                m = mean.get(int(particles["pind"][i]))
+                if m is not None:
+                    particles["occ"][i] = m
+    return rows, particles

@@ -1,0 +1,73 @@
+"""Golden fixtures for pyp_b200/tables.py: the REFERENCE's Parameters.update_particle_score and
+Parameters.sync_particle_occ (src/pyp/inout/metadata/cistem_star_file.py:936-1013) applied to a small
+tilt-series table.  Run in the build container only (imports /root/reference):
+
+    python tests/golden/make_golden_tables.py
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden  # noqa: E402,F401  (stubs the absent third-party modules, sets sys.path)
+
+import numpy as np  # noqa: E402
+
+from pyp.inout.metadata import cistem_star_file as csf  # noqa: E402
+
+
+def build():
+    rng = np.random.default_rng(77)
+    n_part, n_tilt = 9, 7
+    n = n_part * n_tilt - 5                                 # ragged: the last particle misses tilts
+    data = np.zeros((n, 32), dtype=np.float64)
+    data[:, 0] = np.arange(1, n + 1)
+    data[:, 1:4] = rng.uniform(0, 360, (n, 3))
+    data[:, 6:8] = rng.uniform(10000, 30000, (n, 2))
+    data[:, 11] = rng.choice([0.0, 50.0, 100.0], n)
+    data[:, 14] = rng.uniform(0, 30, n)
+    data[:, 15] = 1.35
+    data[:, 26] = np.arange(n) // n_tilt                    # PIND
+    data[:, 27] = np.arange(n) % n_tilt                     # TIND
+    data[:, 28] = 0
+    keep = np.ones(n, bool)
+    keep[(data[:, 26] == 4) & (data[:, 27] < 5)] = False    # particle 4 only has tilts 5, 6
+    data = data[keep]
+    data = data.astype(np.float32).astype(np.float64)       # what pyp holds after reading a .cistem file (float32 columns)
+    particles = {p: csf.Particle(p, *rng.uniform(-5, 5, 3), *rng.uniform(0, 360, 3), *rng.uniform(0, 500, 3), 3.25, 100.0)
+                 for p in range(n_part + 1)}                # particle 9 has no projection at all
+    tilts = {t: {0: csf.Tilt(t, 0, 0.5 * t, -0.25 * t, -45.0 + 15.0 * t, 85.0)} for t in range(n_tilt)}
+    return data, particles, tilts
+
+
+def fresh(data, particles, tilts):
+    import copy
+
+    ext = csf.ExtendedParameters()
+    ext.set_data(particles=copy.deepcopy(particles), tilts=copy.deepcopy(tilts))
+    p = csf.Parameters()
+    p.set_data(data=data.copy(), extended_parameters=ext)
+    return p
+
+
+def main():
+    data, particles, tilts = build()
+    fresh(data, particles, tilts).to_binary(os.path.join(HERE, "tables_in.cistem"))
+    cases = {"tind_0_4": dict(tind_range=[0, 4]), "tind_2_open": dict(tind_range=[2, -1]),
+             "angle": dict(tind_range=[], tiltang_range=[-20.0, 20.0])}
+    for tag, kw in cases.items():
+        p = fresh(data, particles, tilts)
+        p.update_particle_score(**kw)
+        p.to_binary(os.path.join(HERE, f"tables_score_{tag}.cistem"))
+    p = fresh(data, particles, tilts)
+    p.update_particle_score(tind_range=[0, 4])              # gives particle 4 and 9 occupancy 0
+    p.sync_particle_occ()
+    p.to_binary(os.path.join(HERE, "tables_sync_to_prj.cistem"))
+    p = fresh(data, particles, tilts)
+    p.sync_particle_occ(ptl_to_prj=False)
+    p.to_binary(os.path.join(HERE, "tables_sync_to_ptl.cistem"))
+    print("written", sorted(f for f in os.listdir(HERE) if f.startswith("tables_")))
+
+
+if __name__ == "__main__":
+    main()

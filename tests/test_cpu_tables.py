@@ -1,0 +1,54 @@
+"""pyp_b200/tables.py against the reference's own Parameters.update_particle_score / sync_particle_occ
+(src/pyp/inout/metadata/cistem_star_file.py:936-1013); fixtures by tests/golden/make_golden_tables.py."""
+import os
+
+import numpy as np
+import pytest
+
+from pyp_b200 import tables
+from pyp_b200.formats import cistem
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(tag):
+    path = os.path.join(G, f"tables_{tag}.cistem")
+    rows = cistem.read_parameters(path)
+    particles, tilts = cistem.read_extended(cistem.extended_path(path))
+    return rows, particles, tilts
+
+
+@pytest.mark.parametrize("tag,kw", [("tind_0_4", dict(tind_range=(0, 4))), ("tind_2_open", dict(tind_range=(2, -1))),
+                                    ("angle", dict(tind_range=(), tiltang_range=(-20.0, 20.0)))])
+def test_update_particle_score_matches_reference(tag, kw):
+    rows, particles, tilts = _load("in")
+    w_rows, w_particles, w_tilts = _load(f"score_{tag}")
+    got = tables.update_particle_score(rows, particles, tilts, **kw)
+    assert got.tobytes() == w_particles.tobytes()           # every particle column, bit for bit
+    assert rows.tobytes() == w_rows.tobytes() and tilts.tobytes() == w_tilts.tobytes()
+    empty = got["score"] == -1
+    assert empty.any() and (got["occ"][empty] == 0).all() and (got["score"][~empty] >= 0).all()
+
+
+def test_sync_particle_occ_matches_reference():
+    rows, particles, tilts = _load("in")
+    w_rows, w_particles, _ = _load("sync_to_prj")
+    scored = tables.update_particle_score(rows, particles, tilts, tind_range=(0, 4))
+    g_rows, g_particles = tables.sync_particle_occ(rows, scored)
+    assert g_rows.tobytes() == w_rows.tobytes() and g_particles.tobytes() == w_particles.tobytes()
+    assert (g_rows["occupancy"][g_rows["pind"] == 4] == 0).all()   # particle 4 has no tilt inside 0..4
+    w_rows, w_particles, _ = _load("sync_to_ptl")
+    g_rows, g_particles = tables.sync_particle_occ(rows, particles, ptl_to_prj=False)
+    assert g_rows.tobytes() == w_rows.tobytes() and g_particles.tobytes() == w_particles.tobytes()
+
+
+def test_edges():
+    rows, particles, tilts = _load("in")
+    with pytest.raises(ValueError):
+        tables.update_particle_score(rows, particles, tilts, tind_range=(), tiltang_range=())
+    with pytest.raises(ValueError):
+        tables.update_particle_score(rows, particles, tilts, tind_range=(), tiltang_range=(10.0, -10.0))
+    none = tables.update_particle_score(rows[:0], particles, tilts)
+    assert (none["score"] == -1).all() and (none["occ"] == 0).all()
+    r2, p2 = tables.sync_particle_occ(rows[:0], particles)
+    assert r2.size == 0 and p2.tobytes() == particles.tobytes()
