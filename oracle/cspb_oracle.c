@@ -293,9 +293,12 @@ static float cos_edge(float r, float radius, float width) {
 }
 
 /* mean / std of the pixels outside `radius` (analysis/image.py:320-338,406-417 convention) */
+/* mean / variance of the pixels farther than `radius` (pixels) from the box centre n/2 — the background of
+ * src/pyp/analysis/image.py:320-338 (extract_background): a radius beyond the half box is clamped to it */
 static void edge_stats(const float *img, int n, float radius, double *mean, double *var) {
     const int c = n / 2;
-    const int use_all = radius * radius >= 2.f * c * c;
+    if (radius > 0.5f * (float)n) radius = 0.5f * (float)n;
+    const int use_all = 0;
     double s = 0, cnt = 0;
     for (int y = 0; y < n; ++y)
         for (int x = 0; x < n; ++x)
@@ -318,6 +321,12 @@ static void normalized_copy(const float *img, int n, float radius, int normalize
         if (v > 0) scl *= (float)(1.0 / sqrt(v));
     }
     for (int k = 0; k < n * n; ++k) out[k] = (img[k] - off) * scl;
+}
+
+/* image.py:406-417 normalize_image: (image - background mean) / background std (population std; a zero std
+ * leaves the scale alone); `invert` multiplies by -1 (refine3d prompt 47) */
+void orc_normalize(const float *img, int n, float radius_px, int normalize, int invert, float *out) {
+    normalized_copy(img, n, radius_px, normalize, invert, out);
 }
 
 void orc_noise_curve(const float *imgs, int count, const orc_refine_cfg *cfg, float *curve) {

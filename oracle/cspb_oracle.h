@@ -98,6 +98,8 @@ float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const f
 /* refine_ctf beam-tilt input (frealign.py:3995-4041, answer 23): sum over the images of
  * G * conj(CTF * slice) on the scoring band at the pose of each row (G = shifted prepared spectrum of
  * orc_score); out_c = n * (n/2+1) complex, zero outside the band (SEMANTICS.md §12) */
+/* particle normalisation of src/pyp/analysis/image.py:320-338,406-417 (radius in pixels) */
+void orc_normalize(const float *img, int n, float radius_px, int normalize, int invert, float *out);
 void orc_phase_sum(const orc_ref *r, const float *specs, const orc_row *rows, int n_img, const orc_refine_cfg *cfg, float *out_c);
 /* centre (pixels, image coordinates) of the projected focus sphere for a pose */
 void orc_focus_center(const orc_refine_cfg *cfg, const float *pose6, float *cx, float *cy);

@@ -125,6 +125,7 @@ def lib():
             "orc_prepare_image": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
+            "orc_normalize": (None, [vp, i, f, i, i, vp]),
             "orc_phase_sum": (None, [vp, vp, vp, i, C.POINTER(RefineCfg), vp]),
             "orc_focus_center": (None, [C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_focus_logp": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
@@ -236,6 +237,13 @@ def score(ref, spec, row, pose6, cfg):
     o4 = np.zeros(4, dtype=np.float32)
     s = lib().orc_score(ref._h, _p(spec), _p(row), _p(pose), C.byref(cfg), _p(o4))
     return float(s), o4
+
+
+def normalize(img, radius_px, normalize=1, invert=0):
+    img = _f32(img)
+    out = np.zeros_like(img)
+    lib().orc_normalize(_p(img), img.shape[-1], float(radius_px), int(normalize), int(invert), _p(out))
+    return out
 
 
 def phase_sum(ref, specs, rows, cfg):

@@ -126,7 +126,7 @@ __host__ __device__ __forceinline__ void score_stats(float4 v, int n_samples, fl
     *logp = var > 0.f ? -0.5f * ns * (1.f + logf(2.f * CSPB_PI_F * var)) : 0.f;
 }
 
-// mean and 1/sigma of the pixels outside radius R (all pixels if the circle covers the box) of one
+// mean and 1/sigma of the pixels outside radius R (clamped to the half box, as the reference does) of one
 // n x n image per CTA — the normalisation of analysis/image.py:320-338,406-417.  Rows are walked by
 // warps with 16-byte loads (no integer division); the second pass re-reads the image from L2.
 __device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, int n, float radius, int normalize, int invert,
@@ -138,9 +138,11 @@ __device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, in
         if (tid == 0) { *off_out = 0.f; *scl_out = sgn; }
         return;
     }
+    // a radius beyond the half box is clamped to it (analysis/image.py:324-331): the corners are the background
+    if (radius > 0.5f * (float)n) radius = 0.5f * (float)n;
     const float r2lim = radius * radius;
     const int c = n / 2;
-    const bool use_all = (radius * radius >= 2.f * c * c);
+    const bool use_all = false;
     const bool vec = (n & 3) == 0;
     float s = 0.f, cnt = 0.f;
     for (int y = warp; y < n; y += nw) {

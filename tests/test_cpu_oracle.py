@@ -250,3 +250,20 @@ def test_beam_tilt_is_recovered_from_the_phase_sum(oracle):
     S = np.exp(1j * gx) * (np.hypot(*np.meshgrid(np.arange(n // 2 + 1), np.fft.fftfreq(n, 1 / n))) < 24)
     f = beamtilt.fit(S, px, 300.0, 2.7)
     assert abs(f["beam_tilt_x"] - 1.0) < 1e-6 and abs(f["beam_tilt_y"] - 0.5) < 1e-6 and abs(f["shift_x"] - 0.2) < 1e-6
+
+
+def test_normalisation_matches_reference_normalize_image(oracle):
+    """(image - background mean) / background std over the pixels outside the particle radius,
+    a radius beyond the half box clamped to it — against the reference's pyp.analysis.image.normalize_image
+    (image.py:320-338,406-417; fixture by tests/golden/make_golden_normalize.py)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "normalize_image.npz"))
+    img, px = g["image"], float(g["pixel"])
+    for r_a, want in zip(g["radii_angstrom"], g["normalized"]):
+        got = oracle.normalize(img, r_a / px)
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), r_a
+    # clamped radii give one and the same result; invert flips the sign; normalize = 0 is the identity
+    assert np.array_equal(oracle.normalize(img, 30.0), oracle.normalize(img, 100.0))
+    assert np.array_equal(oracle.normalize(img, 12.0, invert=1), -oracle.normalize(img, 12.0))
+    assert np.array_equal(oracle.normalize(img, 12.0, normalize=0), img)

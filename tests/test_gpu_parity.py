@@ -99,7 +99,8 @@ def test_noise_curve(engine, oracle):
     assert np.abs(got[m] - curve[m]).max() / curve[m].max() < 1e-5
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(apply_mask=0), dict(whiten=0, normalize=0), dict(pad=2), dict(signed_cc_limit=0.0), dict(invert_contrast=1)])
+@pytest.mark.parametrize("kw", [dict(), dict(apply_mask=0), dict(whiten=0, normalize=0), dict(pad=2), dict(signed_cc_limit=0.0), dict(invert_contrast=1),
+                                dict(mask_radius=0.62 * 64 * 1.35)])  # beyond the half box: normalisation radius clamped (image.py:324-331)
 def test_score_matches_oracle(engine, oracle, kw):
     ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, **kw)
     got = engine.score(rows)
