@@ -8,6 +8,10 @@
   * ``sync_particle_occ`` — copy occupancies between the particle table and the projection rows
     (cistem_star_file.py:988-1013; align/core.py:912, scores.py:975).
 
+  * ``global_weights`` / ``write_global_weights`` — the external dose-weighting file reconstruct3d reads when
+    prompt 22 is "yes": one value per scan-order index (TIND) = mean SCORE of the projections with
+    OCCUPANCY > 0 at that index, -1 where there is none (src/pyp/inout/metadata/core.py:3039-3075).
+
 Pinned against the reference's own methods by tests/golden/tables_* (tests/golden/make_golden_tables.py).
 """
 import numpy as np
@@ -81,3 +85,23 @@ def sync_particle_occ(rows, particles, ptl_to_prj=True):
                 if m is not None:
                     particles["occ"][i] = m
     return rows, particles
+
+
+def global_weights(rows):
+    """Mean SCORE per scan-order index over the projections with occupancy > 0; -1 for unused indices below
+    the largest used one (core.py:3039-3071)."""
+    used = rows[rows["occupancy"] > 0.0]
+    if used.size == 0:
+        return np.zeros(0, dtype=np.float64)
+    tind = used["tind"].astype(np.int64)
+    total = np.bincount(tind, weights=used["score"].astype(np.float64))
+    count = np.bincount(tind)
+    out = np.full(total.size, -1.0)
+    out[count > 0] = total[count > 0] / count[count > 0]
+    return out
+
+
+def write_global_weights(path, weights):
+    """One Python-float repr per line, no trailing newline (core.py:3073-3074)."""
+    with open(path, "w") as f:
+        f.write("\n".join(str(float(w)) for w in weights))

@@ -66,6 +66,15 @@ def main():
     p = fresh(data, particles, tilts)
     p.sync_particle_occ(ptl_to_prj=False)
     p.to_binary(os.path.join(HERE, "tables_sync_to_ptl.cistem"))
+    # external dose weights (inout/metadata/core.py:3039-3075) from the same table; scan-order index 3 unused
+    os.environ.setdefault("PYP_DIR", "/root/reference")
+    from pyp.inout.metadata import core as MC
+
+    d2 = data.copy()
+    d2[d2[:, 27] == 3, 11] = 0.0
+    q = fresh(d2, particles, tilts)
+    q.to_binary(os.path.join(HERE, "tables_weights_in.cistem"))
+    MC.compute_global_weights(q.get_data(), os.path.join(HERE, "tables_global_weight.txt"))
     print("written", sorted(f for f in os.listdir(HERE) if f.startswith("tables_")))
 
 

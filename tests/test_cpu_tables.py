@@ -52,3 +52,20 @@ def test_edges():
     assert (none["score"] == -1).all() and (none["occ"] == 0).all()
     r2, p2 = tables.sync_particle_occ(rows[:0], particles)
     assert r2.size == 0 and p2.tobytes() == particles.tobytes()
+
+
+def test_global_weights_match_reference(tmp_path):
+    """External dose weights of reconstruct3d answer 22 (inout/metadata/core.py:3039-3075): file text identical
+    to the reference's compute_global_weights."""
+    rows = cistem.read_parameters(os.path.join(G, "tables_weights_in.cistem"))
+    w = tables.global_weights(rows)
+    assert w[3] == -1.0 and (np.delete(w, 3) > 0).all()
+    out = str(tmp_path / "global_weight.txt")
+    tables.write_global_weights(out, w)
+    assert open(out).read() == open(os.path.join(G, "tables_global_weight.txt")).read()
+    assert tables.global_weights(rows[:0]).size == 0
+    # the reconstruct3d front-end reads the same file
+    from pyp_b200.cli import reconstruct3d
+
+    dw = reconstruct3d.dose_weights({"dose_weighting": True, "dose_weights_file": out}, rows)
+    assert dw.shape == (rows.size,) and dw.max() == 1.0 and (dw[rows["tind"] == 3] == 0).all()
