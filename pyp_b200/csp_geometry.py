@@ -70,3 +70,21 @@ def compose_pose(particle, tilt):
 def compose_shift(pshift, tilt):
     """2-D shift (same unit as pshift) that the 3-D particle shift induces on a tilt image."""
     return tilt_projector(tilt[0], tilt[1]) @ (-np.asarray(pshift, dtype=np.float64))
+
+
+def defocus_offset_from_center(particle_xyz, tomo_center_xyz, tilt_angle_deg, specimen_z_offset, handedness=-1):
+    """Height difference (tomogram voxels) between a particle and the tilt-series centre along the beam at
+    one tilt — the per-particle, per-tilt defocus offset of tilt-series CTF (defocus += offset x pixel).
+    Closed form of src/pyp/analysis/geometry/core.py:686-773 (`DefocusOffsetFromCenter`): the chain
+    toRaw . T^-1 . Ry(tilt) . toOrigin applied to the particle and to the centre lifted by the specimen
+    offset; the in-plane alignment T^-1 leaves z alone, so with d = particle - centre
+
+        offset = -sin(tilt) d_x + cos(tilt) (d_z - specimen_z_offset),   times -1 for handedness = -1.
+
+    Pinned against the reference's function in tests/golden/defocus_offset.npy."""
+    if handedness not in (1, -1):
+        raise ValueError("handedness must be 1 or -1")
+    d = np.asarray(particle_xyz, dtype=np.float64) - np.asarray(tomo_center_xyz, dtype=np.float64)
+    a = np.radians(tilt_angle_deg)
+    off = -np.sin(a) * d[..., 0] + np.cos(a) * (d[..., 2] - specimen_z_offset)
+    return -off if handedness == -1 else off

@@ -187,3 +187,24 @@ def test_csp_cli_host_logic(tmp_path, monkeypatch):
     import io
     out = io.StringIO()
     assert cli.main(["a", "b"], out=out) == 1 and "PYP (cspswarm) failed" in out.getvalue()
+
+
+def test_defocus_offset_matches_reference():
+    """Per-particle, per-tilt defocus offset (geometry/core.py:686-773 DefocusOffsetFromCenter) — closed form
+    against the reference's 4x4 chain; fixture by tests/golden/make_golden_defocus.py."""
+    import os
+
+    from pyp_b200 import csp_geometry as cg
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "defocus_offset.npy"))
+    for r in g:
+        p, c, tilt, zo, h, want = r[0:3], r[3:6], r[6], r[13], int(r[14]), r[15]
+        got = cg.defocus_offset_from_center(p, c, tilt, zo, handedness=h)
+        assert abs(got - want) < 1e-9 * max(1.0, abs(want))
+    # vectorised over particles; handedness is a pure sign
+    P = g[:, 0:3]
+    a = cg.defocus_offset_from_center(P, g[0, 3:6], 30.0, 5.0, handedness=1)
+    b = cg.defocus_offset_from_center(P, g[0, 3:6], 30.0, 5.0, handedness=-1)
+    assert a.shape == (g.shape[0],) and np.array_equal(a, -b)
+    with pytest.raises(ValueError):
+        cg.defocus_offset_from_center(P[0], g[0, 3:6], 0.0, 0.0, handedness=0)
