@@ -199,6 +199,10 @@ def main(argv=None, out=sys.stdout):
         mode = int(float(mode))
         first, last = int(first), int(last)
         out.write(banner("CSP"))
+        if images.endswith(".txt"):
+            # `images` = frames_csp.txt: per-frame (movie) refinement, local_run.py:337-404,434-439 — not built;
+            # fail loudly instead of treating the frame list as a tilt series
+            raise PromptError("csp: frame (movie) refinement (images = a frame list) is not implemented in cspb200")
         config = load_config()
         if mode == -1:
             pass

@@ -208,3 +208,18 @@ def test_defocus_offset_matches_reference():
     assert a.shape == (g.shape[0],) and np.array_equal(a, -b)
     with pytest.raises(ValueError):
         cg.defocus_offset_from_center(P[0], g[0, 3:6], 0.0, 0.0, handedness=0)
+
+
+def test_csp_cli_refuses_frame_lists(capsys):
+    """Frame (movie) refinement hands `frames_csp.txt` as the images argument (local_run.py:434-439): not built —
+    the front-end must fail loudly with the token pyp greps for (particle_cspt.py:1663), not run a tilt mode."""
+    import io
+
+    from pyp_b200.cli import csp
+
+    out = io.StringIO()
+    rc = csp.main(["a.cistem", "a_extended.cistem", "3", "0", "0", "0", "frames_csp.txt", "stack.mrc"], out=out)
+    assert rc == 1 and "PYP (cspswarm) failed" in out.getvalue()
+    assert "not implemented" in capsys.readouterr().err
+    rc = csp.main(["too", "few"], out=io.StringIO())
+    assert rc == 1
