@@ -108,13 +108,33 @@ def run(p, out=sys.stdout):
     cfg.average_score = float(used["score"].mean()) if used.size else 0.0
     eng.set_symmetry(p["symmetry"])
     eng.recon_begin(cfg)
+    n_band = 0
+    if p["likelihood_blurring"] and rows.size:
+        # answer 34: the fan of in-plane rotations is scored against the input reconstruction (answer 4)
+        from .. import blur
+
+        _, vol = mrc.read(p["reference"])
+        if vol.shape != (box, box, box):
+            raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
+        rcfg = Engine.refine_defaults(box, p["pixel_size"])
+        rcfg.pad = cfg.pad
+        rcfg.mask_radius = p["outer_mask_radius"]
+        rcfg.high_res_limit = p["resolution_limit"] if p["resolution_limit"] > 0 else 2.0 * p["pixel_size"]
+        rcfg.normalize, rcfg.invert_contrast = int(p["normalize"]), int(p["invert"])
+        eng.refine_configure(rcfg)
+        eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+        n_band = eng.band_counts()[0]
     if rows.size:
         pos = rows["position_in_stack"].astype(np.int64)
         _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max()))
         chunk = 8192
         for s in range(0, rows.size, chunk):
             e = min(rows.size, s + chunk)
-            eng.recon_insert(np.ascontiguousarray(data[pos[s:e] - pos.min()]), rows[s:e])
+            imgs = np.ascontiguousarray(data[pos[s:e] - pos.min()])
+            if n_band:
+                blur.insert_blurred(eng, imgs, rows[s:e], n_band)
+            else:
+                eng.recon_insert(imgs, rows[s:e])
     n_used = int(used.size)
     if p["dump"]:
         for h, path in ((0, p["dump1"]), (1, p["dump2"])):
@@ -131,6 +151,9 @@ def run(p, out=sys.stdout):
     out.write(banner("Reconstruct3D"))
     out.write(f"\nInserted {n_used} of {rows.size} particles ({first}..{last}), symmetry {p['symmetry']}, "
               f"box {box}, padding {cfg.pad}, {time.time() - t0:.2f} s\n")
+    if n_band:
+        out.write(f"Likelihood blurring: {blur.LBLUR_NROT} in-plane rotations from {blur.LBLUR_START:+.0f} deg in steps of "
+                  f"{blur.LBLUR_STEP:.0f} deg, LogP range {blur.LBLUR_RANGE:.0f}\n")
     out.write("\nReconstruct3D: Normal termination\n")
     eng.close()
 

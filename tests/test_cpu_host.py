@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from pyp_b200 import dist as pd
+from pyp_b200._lib import ROW_DTYPE as ROW_DTYPE_
 from pyp_b200.cli import local_merge3d, merge3d, prompts, reconstruct3d, refine3d
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -212,3 +213,30 @@ def test_refine3d_shift_prior_sources(tmp_path):
     assert refine3d.shift_prior({"global_stat": path}, rows) == (0.25, -0.75, 9.0, 4.0)
     assert refine3d.shift_prior({"global_stat": str(tmp_path / "missing.cistem")}, rows)[0] == mx
     assert refine3d.shift_prior({"global_stat": "null"}, rows[:0]) == (0.0, 0.0, 0.0, 0.0)
+
+
+def test_likelihood_blurring_weights():
+    """reconstruct3d answer 34 (frealign.py:1772,1817; legacy fan frealign.py:766-770): weights follow
+    exp(LogP_k - LogP_max) with the LOGP law of SEMANTICS.md §6, members beyond the range are dropped."""
+    from pyp_b200 import blur
+
+    d = blur.offsets()
+    assert d.size == 21 and d[0] == -10.0 and d[10] == 0.0 and d[-1] == 10.0
+    ns = 4168
+    cc = np.array([[0.30 - 0.002 * abs(k) for k in d], [0.05] * 21, [-0.1] * 21, [0.2 if k == 3 else 0.0 for k in d]])
+    w = blur.weights(100 * cc, ns)
+    assert np.allclose(w.sum(axis=1), 1.0) and (w >= 0).all()
+    # law: ratio of two members = ((1 - cc_a^2) / (1 - cc_b^2))^(-ns/2)
+    want = ((1 - cc[0, 10] ** 2) / (1 - cc[0, 9] ** 2)) ** (0.5 * ns)
+    assert np.isclose(w[0, 9] / w[0, 10], want, rtol=1e-9)
+    assert np.argmax(w[0]) == 10 and np.allclose(w[0], w[0][::-1])          # peaked at the refined psi, symmetric
+    assert (w[0][np.abs(d) >= 8] == 0).all()                                 # > 20 LogP units below the best
+    assert np.allclose(w[1], 1.0 / 21)                                        # flat likelihood: uniform fan
+    assert w[2, 10] == 1.0 and w[2].sum() == 1.0                              # nothing correlates: refined pose only
+    assert w[3, 13] == 1.0
+    rows = np.zeros(2, dtype=ROW_DTYPE_)
+    rows["psi"] = [355.0, 3.0]
+    rows["theta"] = [10.0, 20.0]
+    poses, idx = blur.fan_poses(rows, d)
+    assert poses.shape == (42, 6) and list(idx[:21]) == [0] * 21 and poses[20, 0] == 5.0 and poses[21, 0] == 353.0
+    assert (poses[:21, 1] == 10.0).all() and (poses[:, 5] == 0).all()

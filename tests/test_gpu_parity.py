@@ -371,6 +371,42 @@ def test_insertion_matches_oracle(engine, oracle, sym, kw):
     engine.set_symmetry("C1")
 
 
+def test_likelihood_blurred_insertion(engine, oracle):
+    """reconstruct3d answer 34 (frealign.py:1772,1817): fan of 21 in-plane rotations weighted by likelihood
+    (pyp_b200/blur.py, SEMANTICS.md §8b).  The accumulators equal the oracle's insertion of every fan member
+    with the same weights, the CTF^2 weight is conserved, and the weights peak at the true in-plane angle."""
+    from pyp_b200 import blur
+
+    n, px = 32, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=12, n_blobs=20, snr=2.0)
+    cfg, ocfg = _recon_cfgs(oracle, n, px)
+    engine.set_symmetry("C1")
+    engine.refine_configure(refine_cfg(n, px))
+    engine.set_reference(vol)
+    n_band = engine.band_counts()[0]
+    engine.recon_begin(cfg)
+    engine.recon_insert(stack, rows)
+    plain = [engine.recon_get_dump(h) for h in (0, 1)]
+    engine.recon_begin(cfg)
+    w = blur.insert_blurred(engine, stack, rows, n_band)
+    assert w.shape == (rows.size, 21) and np.allclose(w.sum(axis=1), 1.0)
+    assert (np.abs(np.argmax(w, axis=1) - 10) <= 2).mean() >= 0.75      # true poses in: the fan peaks near delta = 0
+    rc = oracle.Recon(ocfg)
+    mats = np.eye(3, dtype=np.float32)[None]
+    for k, d in enumerate(blur.offsets()):
+        if (w[:, k] > 0).any():
+            member = rows.copy()
+            member["psi"] = np.mod(rows["psi"].astype(np.float64) + d, 360.0)
+            member["occupancy"] = rows["occupancy"] * w[:, k]
+            rc.insert(stack, member.astype(oracle.ROW_DTYPE), mats)
+    for h in (0, 1):
+        raw = engine.recon_get_dump(h)
+        got, want = fold_x0(raw), fold_x0(rc.dump(h))
+        assert np.abs(got - want).max() <= 5e-5 * np.abs(want).max()
+        # an in-plane rotation moves a sample inside its ring: the total CTF^2 weight does not change
+        assert abs(float(raw[..., 2].sum()) - float(plain[h][..., 2].sum())) <= 1e-4 * float(plain[h][..., 2].sum())
+
+
 def test_reconstruction_fsc(engine, oracle):
     """reconstruct3d + merge3d: FSC >= 0.999 against the oracle's maps at every shell, and the
     reconstruction resembles the phantom."""
