@@ -1,0 +1,78 @@
+"""Golden fixtures for the stdin contracts: the command strings the REFERENCE itself assembles for
+`refine3d` and `refine_ctf` (src/pyp/refine/frealign/frealign.py:3771-4043 `mrefine_version`), for a local
+refinement, a global search with focus mask / priors, and the beam-tilt variant.  The heredoc between
+`<< eot` and `eot` is what our front-ends must parse.  Run in the build container only:
+
+    python tests/golden/make_golden_prompts.py
+"""
+import json
+import os
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden  # noqa: E402,F401
+
+os.environ["PYP_DIR"] = "/root/reference"
+from pyp.refine.frealign import frealign as F  # noqa: E402
+from pyp.system import project_params  # noqa: E402
+
+
+class Loud(dict):
+    """A parameter table that names the key the reference asks for when it is missing."""
+
+    def __missing__(self, key):
+        raise KeyError(f"reference asked for parameter {key!r}")
+
+
+def base_mp():
+    return Loud(
+        data_set="T20S", refine_dataset="T20S", scope_pixel=1.35, data_bin=1, extract_bin=1, scope_mag=10000, scope_voltage=300.0,
+        scope_cs=2.7, scope_wgh=0.07, reconstruct_rrec="0", refine_mask="1,1,1,1,1", class_num=1, refine_global_stat=False,
+        refine_fssnr=True, refine_priors=False, class_focusmask="0,0,0,0", refine_fdef="F", csp_ToleranceMicrographDefocus1=2000,
+        refine_fmatch="F", refine_invert=False, refine_mode="1", refine_srad=0, particle_rad=80.0, refine_fboost=False,
+        refine_fboostlim=25.0, extract_fmt="frealign", data_mode="spr", reconstruct_norm=True, particle_sym="O", particle_mw=700.0,
+        refine_rlref="100.0", refine_rhref="8.0", class_rhcls="8.0", refine_dang="20.0", refine_searchx="0", refine_searchy="0",
+        refine_iblow="1", refine_beamtilt=False, refine_metric="cc3m", refine_iter=2, refine_maxiter=8, refine_skip=False)
+
+
+def heredoc(cmd):
+    body = cmd.split("<< eot", 1)[1]
+    body = body.split("\n", 1)[1]
+    return body.rsplit("eot", 1)[0]
+
+
+def main():
+    cases = {
+        "local": {},
+        "global_focus_priors": dict(refine_mode="4", refine_priors=True, class_focusmask="120.5,98.0,77.25,45.0", refine_mask="1,0,1,1,0",
+                                    refine_fboost=True, refine_srad=110.0, refine_fdef="T", refine_invert=True),
+        "beamtilt": dict(_beam=True),
+    }
+    out = {}
+    tmp = tempfile.mkdtemp()
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    os.environ["PYP_SCRATCH"] = tmp
+    open("statistics_r01.txt", "w").write("C header\n   1.00000   50.00000   0.90000   0.99000   0.98000   30.00000   2.00000\n")
+    try:
+        for tag, kw in cases.items():
+            mp = base_mp()
+            kw = dict(kw)
+            beam = kw.pop("_beam", False)
+            mp.update(kw)
+            F.project_params.load_pyp_parameters = lambda path=".", _mp=mp: _mp
+            cmd = F.mrefine_version(mp, 1, 100, 3, 1, tmp, "T20S_r01", "0000001_0000100", "refine.log", tmp, refine_beam_tilt=beam)
+            out[tag] = {"program": cmd.split(" << eot")[0].split("/")[-1].strip(),
+                        "heredoc": heredoc(cmd).replace(tmp, "$SCRATCH"),
+                        "parameters": {k: mp[k] for k in sorted(mp)}}
+    finally:
+        os.chdir(cwd)
+    json.dump(out, open(os.path.join(HERE, "prompts_refine.json"), "w"), indent=1)
+    for k, v in out.items():
+        print(k, v["program"], len(v["heredoc"].splitlines()), "answers")
+
+
+if __name__ == "__main__":
+    main()

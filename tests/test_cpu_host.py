@@ -240,3 +240,38 @@ def test_likelihood_blurring_weights():
     poses, idx = blur.fan_poses(rows, d)
     assert poses.shape == (42, 6) and list(idx[:21]) == [0] * 21 and poses[20, 0] == 5.0 and poses[21, 0] == 353.0
     assert (poses[:21, 1] == 10.0).all() and (poses[:, 5] == 0).all()
+
+
+def test_front_ends_parse_the_reference_s_own_heredocs():
+    """The stdin text is produced by the REFERENCE's command builder (frealign.py:3771-4043 mrefine_version,
+    run in the build container: tests/golden/make_golden_prompts.py), not transcribed by hand."""
+    import json
+
+    from pyp_b200.cli import refine_ctf
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prompts_refine.json")))
+    assert g["local"]["program"] == "refine3d" and g["beamtilt"]["program"] == "refine_ctf"
+    a = prompts.Answers(g["local"]["heredoc"], "refine3d")
+    p = refine3d.parse(a)
+    assert a.done()                                                  # every answer consumed, none missing
+    assert p["stack"] == "../T20S_stack.mrc" and p["global_stat"] == "null" and p["use_statistics"] is True and p["use_priors"] is False
+    assert (p["symmetry"], p["first"], p["last"], p["percent_used"]) == ("O", 1, 100, 1)
+    assert (p["pixel_size"], p["molecular_mass"], p["outer_mask_radius"]) == (1.35, 700.0, 80.0)
+    assert (p["low_res_limit"], p["high_res_limit"], p["signed_cc_limit"], p["search_mask_radius"]) == (100.0, 8.0, 30.0, 120.0)
+    assert p["mask_2d"] == [0, 0, 0, 0] and p["apply_2d_masking"] is False and p["defocus_range"] == 500 and p["defocus_step"] == 50.0
+    assert (p["global_search"], p["local_refine"]) == (False, True)
+    assert [p[f"refine_{k}"] for k in ("psi", "theta", "phi", "x", "y")] == [True] * 5
+    assert p["refine_defocus"] is False and p["normalize"] is True and p["invert"] is False
+    a = prompts.Answers(g["global_focus_priors"]["heredoc"], "refine3d")
+    p = refine3d.parse(a)
+    assert a.done() and p["use_priors"] is True and (p["global_search"], p["local_refine"]) == (True, False)
+    assert p["mask_2d"] == [120.5, 98.0, 77.25, 45.0] and p["apply_2d_masking"] is True
+    assert p["signed_cc_limit"] == 25.0 and p["search_mask_radius"] == 110.0 and p["defocus_range"] == 2000 and p["refine_defocus"] is True
+    # refine_mask "1,0,1,1,0": the reference takes phi's flag from entry 1 (frealign.py:3814-3817)
+    assert [p[f"refine_{k}"] for k in ("psi", "theta", "phi", "x", "y")] == [True, False, False, True, False]
+    assert p["invert"] is True
+    a = prompts.Answers(g["beamtilt"]["heredoc"], "refine_ctf")
+    p = refine_ctf.parse(a)
+    assert a.done() and p["beam_tilt"] is True and p["refine_defocus"] is False
+    assert p["out_star"].endswith("_refined_ctf.star") and p["beamtilt_image"] == "T20S_r01_beamtilt_image.mrc"
+    assert (p["first"], p["last"], p["pixel_size"], p["outer_mask_radius"], p["high_res_limit"]) == (1, 100, 1.35, 80.0, 8.0)
