@@ -72,6 +72,33 @@ def main():
     json.dump(out, open(os.path.join(HERE, "prompts_refine.json"), "w"), indent=1)
     for k, v in out.items():
         print(k, v["program"], len(v["heredoc"].splitlines()), "answers")
+    # ---- reconstruct3d: frealign.py:1622-1835 split_reconstruction(run=False) returns the command
+    rec = {}
+    rcases = {
+        "plain": {},
+        "dose_blur_split": dict(reconstruct_dose_weighting_enable=True, reconstruct_dose_weighting_weights="",
+                                reconstruct_dose_weighting_multiply=True, reconstruct_dose_weighting_fraction=4,
+                                reconstruct_dose_weighting_transition=0.75, reconstruct_lblur=True,
+                                reconstruct_per_particle_splitting=True, refine_score_weighting=True, reconstruct_apply_symmetry=False),
+    }
+    os.chdir(tmp)
+    os.makedirs(os.path.join(tmp, "log"), exist_ok=True)
+    try:
+        for tag, kw in rcases.items():
+            mp = base_mp()
+            mp.update(slurm_tasks=7, reconstruct_radrec="0", extract_box=128, reconstruct_dose_weighting_enable=False,
+                      refine_score_weighting=False, reconstruct_per_particle_splitting=False, reconstruct_lblur=False,
+                      reconstruct_apply_symmetry=True, refine_bsc=2.0, reconstruct_cutoff="1", reconstruct_norm=True,
+                      refine_adjust="F", refine_crop="F", reconstruct_scratch_copy_stack=False)
+            mp.update(kw)
+            cmd = F.split_reconstruction(mp, 1, 50, 3, 1, 1, 0, 0, dump_intermediate="yes", num_frames=1, run=False)
+            rec[tag] = {"program": cmd.split(" << eot")[0].split("/")[-1].strip(), "heredoc": heredoc(cmd).replace(tmp, "$SCRATCH"),
+                        "parameters": {k: mp[k] for k in sorted(mp)}}
+    finally:
+        os.chdir(cwd)
+    json.dump(rec, open(os.path.join(HERE, "prompts_reconstruct.json"), "w"), indent=1)
+    for k, v in rec.items():
+        print(k, v["program"], len(v["heredoc"].splitlines()), "answers")
 
 
 if __name__ == "__main__":

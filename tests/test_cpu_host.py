@@ -275,3 +275,29 @@ def test_front_ends_parse_the_reference_s_own_heredocs():
     assert a.done() and p["beam_tilt"] is True and p["refine_defocus"] is False
     assert p["out_star"].endswith("_refined_ctf.star") and p["beamtilt_image"] == "T20S_r01_beamtilt_image.mrc"
     assert (p["first"], p["last"], p["pixel_size"], p["outer_mask_radius"], p["high_res_limit"]) == (1, 100, 1.35, 80.0, 8.0)
+
+
+def test_reconstruct3d_parses_the_reference_s_own_heredocs():
+    """frealign.py:1622-1835 split_reconstruction(run=False) assembled these answers
+    (tests/golden/make_golden_prompts.py): plain, and dose weighting + likelihood blurring + per-particle split."""
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prompts_reconstruct.json")))
+    a = prompts.Answers(g["plain"]["heredoc"], "reconstruct3d")
+    p = reconstruct3d.parse(a)
+    assert a.done() and g["plain"]["program"] == "reconstruct3d"
+    assert p["parameters"] == "../T20S_r01_used.cistem" and p["reference"] == "../T20S_r01.mrc" and p["global_stat"] == "null"
+    assert (p["symmetry"], p["first"], p["last"]) == ("O", 1, 50)
+    assert (p["pixel_size"], p["outer_mask_radius"], p["resolution_limit"], p["score_bfactor"]) == (1.35, 86.4, 2.7, 2.0)
+    assert p["score_weighting"] is False and p["dose_weighting"] is False and p["score_threshold"] == 0 and p["padding"] == 1
+    assert p["normalize"] is True and p["split_even_odd"] is True and p["per_particle_split"] is False
+    assert p["likelihood_blurring"] is False and p["dump"] is True and p["dump1"].endswith("T20S_r01_map1_n1.mrc") and p["max_threads"] == 1
+    a = prompts.Answers(g["dose_blur_split"]["heredoc"], "reconstruct3d")
+    p = reconstruct3d.parse(a)
+    assert a.done() and p["symmetry"] == "C1"                        # reconstruct_apply_symmetry off (frealign.py:1775-1778)
+    assert p["score_weighting"] is True and p["dose_weighting"] is True and p["dose_weights_file"] == "/scratch/not_provided"
+    assert p["dose_multiply"] is True and p["dose_fraction"] == 4 and p["dose_transition"] == 0.75
+    assert p["per_particle_split"] is True and p["likelihood_blurring"] is True
+    # a weights file that does not exist leaves the occupancies alone
+    rows = np.zeros(3, dtype=ROW_DTYPE_)
+    assert reconstruct3d.dose_weights(p, rows) is None
