@@ -99,6 +99,45 @@ def main():
     json.dump(rec, open(os.path.join(HERE, "prompts_reconstruct.json"), "w"), indent=1)
     for k, v in rec.items():
         print(k, v["program"], len(v["heredoc"].splitlines()), "answers")
+    # ---- merge3d / local_merge3d: the functions run their command; the executor is replaced by a recorder
+    class Captured(Exception):
+        pass
+
+    def recorder(command, *a, **k):
+        raise Captured(command)
+
+    mer = {}
+    F.local_run.stream_shell_command = recorder
+    F.local_run.run_shell_command = recorder
+    work = os.path.join(tmp, "merge")
+    os.makedirs(os.path.join(work, "swarm"), exist_ok=True)
+    os.makedirs(os.path.join(work, "log"), exist_ok=True)
+    os.environ["PYP_SCRATCH"] = os.path.join(work, "scratch")
+    os.makedirs(os.environ["PYP_SCRATCH"], exist_ok=True)
+    for k in (1, 2, 3):
+        for h in (1, 2):
+            open(os.path.join(os.environ["PYP_SCRATCH"], f"T20S_r01_map{h}_n{k}.mrc"), "w").close()
+            open(os.path.join(work, "swarm", f"T20S_r01_02_map{h}_n{k}.mrc"), "w").close()
+    os.chdir(os.path.join(work, "swarm"))
+    try:
+        mp = base_mp()
+        mp.update(refine_metric="new", reconstruct_radrec="0", extract_box=128, reconstruct_num_frames="1", refine_merge_normalize=False)
+        try:
+            F.merge_reconstructions(mp, 3, 1)
+        except Captured as e:
+            cmd = str(e)
+            mer["merge3d"] = {"program": cmd.split(" << eot")[0].split("/")[-1].strip(),
+                              "heredoc": heredoc(cmd).replace(os.environ["PYP_SCRATCH"], "$SCRATCH")}
+        try:
+            F.local_merge_reconstruction()
+        except Captured as e:
+            cmd = str(e)
+            mer["local_merge3d"] = {"program": cmd.split(" << eot")[0].split("/")[-1].strip(), "heredoc": heredoc(cmd)}
+    finally:
+        os.chdir(cwd)
+    json.dump(mer, open(os.path.join(HERE, "prompts_merge.json"), "w"), indent=1)
+    for k, v in mer.items():
+        print(k, v["program"], v["heredoc"].splitlines())
 
 
 if __name__ == "__main__":

@@ -301,3 +301,20 @@ def test_reconstruct3d_parses_the_reference_s_own_heredocs():
     # a weights file that does not exist leaves the occupancies alone
     rows = np.zeros(3, dtype=ROW_DTYPE_)
     assert reconstruct3d.dose_weights(p, rows) is None
+
+
+def test_merge_front_ends_parse_the_reference_s_own_heredocs():
+    """frealign.py:1910-2136 merge_reconstructions and :1838-1903 local_merge_reconstruction, run with a recording
+    executor (tests/golden/make_golden_prompts.py)."""
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prompts_merge.json")))
+    assert g["merge3d"]["program"] == "merge3d" and g["local_merge3d"]["program"] == "local_merge3d"
+    a = prompts.Answers(g["merge3d"]["heredoc"], "merge3d")
+    p = merge3d.parse(a)
+    assert a.done() and p["filtered"] == "T20S_r01_03.mrc" and p["molecular_mass"] == 700.0 and p["outer_radius"] == 86.4 and p["count"] == 3
+    assert p["seed1"].endswith("T20S_r01_map1_n.mrc") and p["seed2"].endswith("T20S_r01_map2_n.mrc")
+    a = prompts.Answers(g["local_merge3d"]["heredoc"], "local_merge3d")
+    p = local_merge3d.parse(a)
+    assert a.done() and p == {"out1": "dumpfile_map1.mrc", "out2": "dumpfile_map2.mrc", "seed1": "temp_map1_n.mrc",
+                              "seed2": "temp_map2_n.mrc", "count": 3}
