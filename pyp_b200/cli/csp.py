@@ -190,14 +190,21 @@ def run_refine(par, ext, mode, first, last, stack, config, out):
               f"{n_evals} projections scored in {dt:.2f} s\n")
 
 
+def parse_argv(argv):
+    """The eight arguments pyp hands over (src/pyp/system/local_run.py:306-467 create_csp_split_commands):
+    parameter file, extended file, mode, first, last, flag (extract_frame / refine_frames), images, stack."""
+    if len(argv) != 8:
+        raise PromptError("usage: csp <par.cistem> <par_extended.cistem> <mode> <first> <last> <flag> <images> <stack>")
+    par, ext, mode, first, last, flag, images, stack = argv
+    return {"par": par, "ext": ext, "mode": int(float(mode)), "first": int(first), "last": int(last), "flag": int(float(flag)),
+            "images": images, "stack": stack}
+
+
 def main(argv=None, out=sys.stdout):
     argv = list(sys.argv[1:] if argv is None else argv)
     try:
-        if len(argv) != 8:
-            raise PromptError("usage: csp <par.cistem> <par_extended.cistem> <mode> <first> <last> <flag> <images> <stack>")
-        par, ext, mode, first, last, _flag, images, stack = argv
-        mode = int(float(mode))
-        first, last = int(first), int(last)
+        a = parse_argv(argv)
+        par, ext, mode, first, last, images, stack = a["par"], a["ext"], a["mode"], a["first"], a["last"], a["images"], a["stack"]
         out.write(banner("CSP"))
         if images.endswith(".txt"):
             # `images` = frames_csp.txt: per-frame (movie) refinement, local_run.py:337-404,434-439 — not built;

@@ -135,6 +135,25 @@ def main():
             mer["local_merge3d"] = {"program": cmd.split(" << eot")[0].split("/")[-1].strip(), "heredoc": heredoc(cmd)}
     finally:
         os.chdir(cwd)
+    # ---- csp argv: src/pyp/system/local_run.py:306-467 create_csp_split_commands returns the command lines
+    from pyp.system import local_run as LR
+    import pyp.inout.image.core as IC
+
+    IC.get_image_dimensions = lambda path: [512, 512, 5]      # the tilt series / a movie: only sizes the chunks
+    os.chdir(tmp)
+    open("frames_csp.txt", "w").write("TS_01_000.tif\n")
+
+    cp = Loud(extract_box=128, slurm_tasks=4, slurm_memory_per_task=16, csp_NumberOfRandomIterations=0, csp_frame_refinement=False)
+    ptl, scan = list(range(0, 9)), list(range(0, 5))
+    csp = {}
+    for tag, mode, frames in (("extract", -2, False), ("particles", 2, False), ("micrographs", 3, False), ("frames", 3, True)):
+        cmds, count, movies = LR.create_csp_split_commands("$PYP_DIR/external/CSP/csp", "TS_01_r01_02.cistem", mode, 4, "TS_01_r01",
+                                                           "TS_01_stack.mrc", ptl, scan, [0], cp, use_frames=frames)
+        csp[tag] = {"driver_mode": mode, "commands": cmds}
+    os.chdir(cwd)
+    json.dump(csp, open(os.path.join(HERE, "prompts_csp.json"), "w"), indent=1)
+    for k, v in csp.items():
+        print(k, len(v["commands"]), v["commands"][0])
     json.dump(mer, open(os.path.join(HERE, "prompts_merge.json"), "w"), indent=1)
     for k, v in mer.items():
         print(k, v["program"], v["heredoc"].splitlines())

@@ -223,3 +223,36 @@ def test_csp_cli_refuses_frame_lists(capsys):
     assert "not implemented" in capsys.readouterr().err
     rc = csp.main(["too", "few"], out=io.StringIO())
     assert rc == 1
+
+
+def test_csp_argv_as_the_reference_builds_it():
+    """Command lines from the reference's create_csp_split_commands (src/pyp/system/local_run.py:306-467;
+    tests/golden/make_golden_prompts.py): eight arguments, driver modes 2 / 3 arrive as 5 / 6, extraction as -2
+    with a per-range output stack, frame refinement as mode 3 with flag 0 and a frame list."""
+    import io
+    import json
+    import os
+    import shlex
+
+    from pyp_b200.cli import csp
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "prompts_csp.json")))
+    want = {"extract": (-2, 1, "frealign/TS_01.mrc"), "particles": (5, 1, "frealign/TS_01.mrc"),
+            "micrographs": (6, 1, "frealign/TS_01.mrc"), "frames": (3, 0, "frames_csp.txt")}
+    for tag, (mode, flag, images) in want.items():
+        cmds = g[tag]["commands"]
+        covered = []
+        for c in cmds:
+            argv = shlex.split(c.split(" > ")[0])[1:]
+            a = csp.parse_argv(argv)
+            assert (a["mode"], a["flag"], a["images"]) == (mode, flag, images)
+            assert a["par"] == "TS_01_r01_02.cistem" and a["ext"] == "TS_01_r01_02_extended.cistem"
+            assert a["stack"] == ("frealign/TS_01_stack_%04d_%04d.mrc" % (a["first"], a["last"]) if mode == -2 else "TS_01_stack.mrc")
+            covered += list(range(a["first"], a["last"] + 1))
+        n = 5 if tag == "micrographs" else 9
+        assert covered == list(range(n))                       # contiguous inclusive ranges over particles / tilts
+        assert cmds[0].endswith("_csp_000000_%06d.log" % csp.parse_argv(shlex.split(cmds[0].split(" > ")[0])[1:])["last"])
+        assert all(c.endswith("> /dev/null") for c in cmds[1:])   # only the first range logs (local_run.py:447)
+    # the frame-list command is refused loudly (not built)
+    argv = shlex.split(g["frames"]["commands"][0].split(" > ")[0])[1:]
+    assert csp.main(argv, out=io.StringIO()) == 1
