@@ -4,6 +4,11 @@ box, so the outputs are committed next to this script; re-run only when the refe
 
     python tests/golden/make_golden.py
 
+Companion generators (same import stubs, one topic each): make_golden_bimodal.py (automatic score cutoff),
+make_golden_tables.py (particle score / occupancy bookkeeping, dose-weight file), make_golden_normalize.py
+(particle normalisation), make_golden_defocus.py (per-tilt defocus offset), make_golden_prompts.py (stdin heredocs
+and csp command lines assembled by the reference's own command builders).
+
 What gets pinned:
   params_5x32.cistem / params_5x32_extended.cistem  — written by
       pyp.inout.metadata.cistem_star_file.Parameters.to_binary (cistem_star_file.py:734-776)
