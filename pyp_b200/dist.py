@@ -167,6 +167,27 @@ def allreduce_noise_curve(ring_sums, n_images):
     return (t[:-1] / max(t[-1], 1.0)).astype(np.float32)
 
 
+def allreduce_parameter_statistics(rows):
+    """`<name>_stat.cistem` over the rows of ALL ranks (a 2 x 32 float allreduce): every rank
+    contributes per-column (count, sum, sum of squares) of its shard in float64; all ranks get the same two
+    rows (means, variances) as `tables.parameter_statistics` would give on the merged table."""
+    import torch
+
+    from . import tables
+
+    names = rows.dtype.names
+    m = np.zeros(2 * len(names) + 1, dtype=np.float64)
+    for k, name in enumerate(names):
+        col = rows[name].astype(np.float64)
+        m[k], m[len(names) + k] = col.sum(), (col * col).sum()
+    m[-1] = rows.size
+    t = torch.as_tensor(m)
+    if world()[1] > 1:
+        _dist().all_reduce(t, op=_dist().ReduceOp.SUM)
+    m = t.numpy()
+    return tables.statistics_from_moments(rows.dtype, m[-1], m[:len(names)], m[len(names):-1])
+
+
 def device_tensor(ptr, nfloats, device):
     """torch float32 view of an engine-owned device buffer (for NCCL on the accumulators)."""
     import torch

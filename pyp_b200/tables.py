@@ -12,6 +12,10 @@
     prompt 22 is "yes": one value per scan-order index (TIND) = mean SCORE of the projections with
     OCCUPANCY > 0 at that index, -1 where there is none (src/pyp/inout/metadata/core.py:3039-3075).
 
+  * ``parameter_statistics`` — the two rows of ``<name>_stat.cistem``: column means and variances of the
+    merged used rows (src/pyp/refine/csp/particle_cspt.py:1009-1016), which refine3d / reconstruct3d get as
+    answer 3 and the shift restraint of refine3d reads (oracle/SEMANTICS.md §7b).
+
 Pinned against the reference's own methods by tests/golden/tables_* (tests/golden/make_golden_tables.py).
 """
 import numpy as np
@@ -105,3 +109,29 @@ def write_global_weights(path, weights):
     """One Python-float repr per line, no trailing newline (core.py:3073-3074)."""
     with open(path, "w") as f:
         f.write("\n".join(str(float(w)) for w in weights))
+
+
+def parameter_statistics(rows):
+    """Rows 0 / 1 of `<name>_stat.cistem`: np.mean / np.var (population) of every column, in float64, stored
+    through the column types of the table like any other row (particle_cspt.py:1009-1016)."""
+    out = np.zeros(2, dtype=rows.dtype)
+    if rows.size == 0:
+        return out
+    for name in rows.dtype.names:
+        col = rows[name].astype(np.float64)
+        out[name][0] = np.mean(col)
+        out[name][1] = np.var(col)
+    return out
+
+
+def statistics_from_moments(dtype, count, sums, sums_sq):
+    """The same two rows from per-column (count, sum x, sum x^2) — what the ranks of a multi-GPU run add up
+    (`dist.allreduce_parameter_statistics`); equal to `parameter_statistics` up to float64 rounding."""
+    out = np.zeros(2, dtype=dtype)
+    if count <= 0:
+        return out
+    for k, name in enumerate(np.dtype(dtype).names):
+        mean = sums[k] / count
+        out[name][0] = mean
+        out[name][1] = max(sums_sq[k] / count - mean * mean, 0.0)
+    return out

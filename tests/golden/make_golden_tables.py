@@ -75,6 +75,11 @@ def main():
     q = fresh(d2, particles, tilts)
     q.to_binary(os.path.join(HERE, "tables_weights_in.cistem"))
     MC.compute_global_weights(q.get_data(), os.path.join(HERE, "tables_global_weight.txt"))
+    # <name>_stat.cistem exactly as particle_cspt.py:1009-1016 writes it: mean / variance of the used rows
+    used = q.get_data()
+    stat = csf.Parameters()
+    stat.set_data(np.vstack((np.mean(used, axis=0), np.var(used, axis=0))))
+    stat.to_binary(os.path.join(HERE, "tables_stat.cistem"))
     print("written", sorted(f for f in os.listdir(HERE) if f.startswith("tables_")))
 
 

@@ -136,6 +136,17 @@ if rank == 0:
     assert np.allclose(merged["psi"], 10.0 + np.arange(7))
 want = sum((r + 1) * (pd.shard_range(1, n, r, ws)[1] - pd.shard_range(1, n, r, ws)[0] + 1) for r in range(ws)) / n
 assert np.allclose(curve, want), (curve, want)
+# <name>_stat.cistem over the shards of all ranks = the statistics of the merged table (particle_cspt.py:1009-1016)
+from pyp_b200 import tables
+rows["x_shift"] = np.sin(rows["position_in_stack"].astype(np.float64)) * 3.0
+stat = pd.allreduce_parameter_statistics(rows)
+full = np.zeros(n, ROW_DTYPE)
+full["position_in_stack"] = np.arange(1, n + 1)
+full["score"] = full["position_in_stack"] * 1.5
+full["x_shift"] = np.sin(full["position_in_stack"].astype(np.float64)) * 3.0
+ref = tables.parameter_statistics(full)
+for name in ("score", "x_shift"):
+    assert np.allclose(stat[name], ref[name], rtol=1e-5, atol=1e-5), (name, stat[name], ref[name])
 dist.destroy_process_group()
 print("ok", rank)
 '''

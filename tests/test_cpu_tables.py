@@ -69,3 +69,26 @@ def test_global_weights_match_reference(tmp_path):
 
     dw = reconstruct3d.dose_weights({"dose_weighting": True, "dose_weights_file": out}, rows)
     assert dw.shape == (rows.size,) and dw.max() == 1.0 and (dw[rows["tind"] == 3] == 0).all()
+
+
+def test_parameter_statistics_match_reference(tmp_path):
+    """`<name>_stat.cistem` = np.mean / np.var of the used rows written as a two-row table
+    (src/pyp/refine/csp/particle_cspt.py:1009-1016): byte-identical file."""
+    rows = cistem.read_parameters(os.path.join(G, "tables_weights_in.cistem"))
+    stat = tables.parameter_statistics(rows)
+    out = str(tmp_path / "x_stat.cistem")
+    cistem.write_parameters(out, stat)
+    assert open(out, "rb").read() == open(os.path.join(G, "tables_stat.cistem"), "rb").read()
+    # the moment form used across ranks agrees to float32 resolution
+    names = rows.dtype.names
+    sums = np.array([rows[n].astype(np.float64).sum() for n in names])
+    sq = np.array([(rows[n].astype(np.float64) ** 2).sum() for n in names])
+    mom = tables.statistics_from_moments(rows.dtype, rows.size, sums, sq)
+    for n in ("x_shift", "score", "defocus_1", "psi"):
+        assert np.allclose(mom[n], stat[n], rtol=1e-4, atol=1e-4)
+    assert tables.parameter_statistics(rows[:0]).size == 2
+    # refine3d's shift restraint reads these two rows
+    from pyp_b200.cli import refine3d
+
+    mx, my, vx, vy = refine3d.shift_prior({"global_stat": out}, rows)
+    assert (mx, vx) == (float(stat["x_shift"][0]), float(stat["x_shift"][1]))
