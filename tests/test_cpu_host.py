@@ -329,3 +329,29 @@ def test_merge_front_ends_parse_the_reference_s_own_heredocs():
     p = local_merge3d.parse(a)
     assert a.done() and p == {"out1": "dumpfile_map1.mrc", "out2": "dumpfile_map2.mrc", "seed1": "temp_map1_n.mrc",
                               "seed2": "temp_map2_n.mrc", "count": 3}
+
+
+def test_append_stacks_drop_in(tmp_path):
+    """external/cistem2/append_stacks as mrc.merge_fast drives it (src/pyp/inout/image/mrc.py:643-696): two
+    answers on stdin, the first stack grows, `Error:` in the output on a dimension mismatch."""
+    from pyp_b200.formats import mrc
+
+    rng = np.random.default_rng(0)
+    a, b, c = (rng.normal(size=(k, 12, 12)).astype(np.float32) for k in (3, 5, 2))
+    pa, pb, pc, pd_ = (str(tmp_path / f"{n}.mrc") for n in "abcd")
+    mrc.write(pa, a, 1.35)
+    mrc.write(pb, b, 1.35)
+    mrc.write(pc, c, 1.35)
+    mrc.write(pd_, rng.normal(size=(2, 8, 8)).astype(np.float32), 1.35)
+    exe = os.path.join(ROOT, "bin", "append_stacks")
+    for second in (pb, pc):
+        r = subprocess.run([exe], input=f"{pa}\n{second}\n", capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "Error:" not in r.stdout and "Normal termination" in r.stdout, r.stdout + r.stderr
+    h, data = mrc.read(pa)
+    assert (h["nx"], h["ny"], h["nz"]) == (12, 12, 10) and np.array_equal(np.asarray(data), np.concatenate([a, b, c]))
+    assert os.path.getsize(pa) == 1024 + 10 * 12 * 12 * 4
+    r = subprocess.run([exe], input=f"{pa}\n{pd_}\n", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Error:" in r.stdout            # what merge_fast looks for (mrc.py:685-686)
+    assert mrc.read_header(pa)["nz"] == 10                        # untouched
+    r = subprocess.run([exe], input=f"{pa}\n", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Error:" in r.stdout
