@@ -124,6 +124,40 @@ def merge(paths):
     return rows[np.argsort(rows["position_in_stack"], kind="stable")]
 
 
+def merge_extended(paths):
+    """The extended half of Parameters.merge (cistem_star_file.py:674-686): particle and tilt tables of the
+    files are overlaid in list order with dict.update semantics — a later file replaces the entries it holds
+    (by PIND, by (TIND, RIND)), new entries are appended, the order of first appearance is kept.  pyp passes
+    the un-refined table first and the csp outputs after it (particle_cspt.py:122-128)."""
+    if not paths:
+        raise ValueError("No cistem extended binary file to merge.")
+
+    def overlay(tables, keys):
+        order, latest = [], {}
+        for t in tables:
+            for row in t:
+                k = tuple(int(row[name]) for name in keys)
+                if k not in latest:
+                    order.append(k)
+                latest[k] = row
+        if not order:
+            return tables[0][:0].copy()
+        return np.array([latest[k] for k in order], dtype=tables[0].dtype)
+
+    both = [read_extended(p) for p in paths]
+    particles = overlay([b[0] for b in both], ("pind",))
+    tilts = [b[1] for b in both]
+    # tilts: dict of dicts — outer order by first appearance of TIND, inner by first appearance of RIND
+    merged = overlay(tilts, ("tind", "rind"))
+    if merged.size:
+        first_seen = {}
+        for k, t in enumerate(merged["tind"]):
+            first_seen.setdefault(int(t), k)
+        rank = np.array([first_seen[int(t)] for t in merged["tind"]])
+        merged = merged[np.argsort(rank, kind="stable")]
+    return particles, merged
+
+
 def merge_with_film_id(paths):
     """merge_all_binary_with_filmid (cistem_star_file.py:1495-1550): stack the per-film tables in list
     order, IMAGE_IS_ACTIVE (which pyp re-uses as the film index) = position of the file in the list.

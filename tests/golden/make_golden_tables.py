@@ -80,6 +80,34 @@ def main():
     stat = csf.Parameters()
     stat.set_data(np.vstack((np.mean(used, axis=0), np.var(used, axis=0))))
     stat.to_binary(os.path.join(HERE, "tables_stat.cistem"))
+    # Parameters.merge with extended files (cistem_star_file.py:656-692) as merge_alignment_parameters calls it
+    # (particle_cspt.py:95-138): un-refined extended table first, then the outputs of two csp ranges
+    import copy
+
+    base = fresh(data, particles, tilts)
+    base.to_binary(os.path.join(HERE, "tables_merge_base.cistem"))
+    outs = []
+    for tag, sel_p in (("000000_000003", range(0, 4)), ("000004_000008", range(4, 9))):
+        rows_k = data[np.isin(data[:, 26], list(sel_p))].copy()
+        rows_k[:, 14] += 1.0
+        pk = {p: copy.deepcopy(particles[p]) for p in sel_p}
+        for p in pk.values():
+            p.psi += 0.5
+            p.score = 20.0 + p.particle_index
+        tk = {}
+        if tag.startswith("000004"):                      # the second range also rewrites two tilts and adds one
+            tk = {2: {0: csf.Tilt(2, 0, 9.0, 9.5, -15.25, 84.0)}, 6: {0: csf.Tilt(6, 0, 7.0, 7.5, 45.5, 86.0)},
+                  9: {0: csf.Tilt(9, 0, 1.0, 2.0, 60.0, 85.0)}}
+        ext = csf.ExtendedParameters()
+        ext.set_data(particles=pk, tilts=tk)
+        pr = csf.Parameters()
+        pr.set_data(data=rows_k, extended_parameters=ext)
+        path = os.path.join(HERE, f"tables_merge_{tag}.cistem")
+        pr.to_binary(path)
+        outs.append(path)
+    merged = csf.Parameters.merge(outs[::-1], [os.path.join(HERE, "tables_merge_base_extended.cistem")] +
+                                  [o.replace(".cistem", "_extended.cistem") for o in outs])
+    merged.to_binary(os.path.join(HERE, "tables_merge_result.cistem"))
     print("written", sorted(f for f in os.listdir(HERE) if f.startswith("tables_")))
 
 

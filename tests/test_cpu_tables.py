@@ -92,3 +92,22 @@ def test_parameter_statistics_match_reference(tmp_path):
 
     mx, my, vx, vy = refine3d.shift_prior({"global_stat": out}, rows)
     assert (mx, vx) == (float(stat["x_shift"][0]), float(stat["x_shift"][1]))
+
+
+def test_merge_of_csp_outputs_matches_reference():
+    """What pyp does with the files `csp` leaves behind (particle_cspt.py:95-138 -> Parameters.merge,
+    cistem_star_file.py:656-692): rows stacked and sorted by POSITION_IN_STACK, extended tables overlaid on
+    the un-refined one with dict.update semantics."""
+    outs = [os.path.join(G, f"tables_merge_{t}.cistem") for t in ("000000_000003", "000004_000008")]
+    want_rows = cistem.read_parameters(os.path.join(G, "tables_merge_result.cistem"))
+    want_p, want_t = cistem.read_extended(os.path.join(G, "tables_merge_result_extended.cistem"))
+    got_rows = cistem.merge(outs[::-1])
+    assert got_rows.tobytes() == want_rows.tobytes()
+    got_p, got_t = cistem.merge_extended([os.path.join(G, "tables_merge_base_extended.cistem")] +
+                                         [cistem.extended_path(o) for o in outs])
+    assert got_p.tobytes() == want_p.tobytes() and got_t.tobytes() == want_t.tobytes()
+    base_p, base_t = cistem.read_extended(os.path.join(G, "tables_merge_base_extended.cistem"))
+    assert got_p.size == base_p.size and got_t.size == base_t.size + 1          # one tilt added by the second range
+    assert (got_p["score"][:9] == 20.0 + np.arange(9)).all() and got_p["score"][9] == base_p["score"][9]
+    with pytest.raises(ValueError):
+        cistem.merge_extended([])
