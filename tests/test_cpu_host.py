@@ -355,3 +355,112 @@ def test_append_stacks_drop_in(tmp_path):
     assert mrc.read_header(pa)["nz"] == 10                        # untouched
     r = subprocess.run([exe], input=f"{pa}\n", capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Error:" in r.stdout
+
+
+class _FakeEngine:
+    """Stand-in for pyp_b200.engine.Engine on a box without a GPU: records the calls of the front-ends and
+    returns inert results, so that every host-side branch of the CLIs runs in the CPU suite (the numerics
+    behind these calls are the subject of the -m gpu tests)."""
+    calls = []
+
+    def __init__(self, device=0):
+        type(self).calls.append(("init", device))
+        self.box = None
+
+    @staticmethod
+    def refine_defaults(box, px):
+        from pyp_b200.engine import Engine_real
+
+        return Engine_real.refine_defaults(box, px)
+
+    @staticmethod
+    def recon_defaults(box, px):
+        from pyp_b200.engine import Engine_real
+
+        return Engine_real.recon_defaults(box, px)
+
+    def __getattr__(self, name):
+        def record(*a, **k):
+            type(self).calls.append((name, a, k))
+            if name == "refine":
+                rows = a[0].copy()
+                rows["score"] = 12.5
+                return rows, rows.copy(), 114 * rows.size
+            if name == "band_counts":
+                return 4168, 4672
+            if name == "score_poses":
+                idx = np.asarray(a[1])
+                return np.full(idx.size, 20.0, dtype=np.float32)
+            if name == "recon_get_dump":
+                n = self.box * self.pad
+                return np.zeros((n, n, n // 2 + 1, 4), dtype=np.float32)
+            if name == "refine_configure":
+                self.box = a[0].box
+            if name == "recon_begin":
+                self.box, self.pad = a[0].box, a[0].pad
+            return None
+        return record
+
+
+def test_front_end_branches_run_without_a_gpu(tmp_path, monkeypatch):
+    """refine3d with priors + focus mask and reconstruct3d with likelihood blurring + dose weights, end to end
+    through file I/O with the engine replaced by a recorder: the answers arrive at the engine as the C-ABI
+    expects them."""
+    import json
+
+    import pyp_b200.engine as E
+    from pyp_b200 import tables
+    from pyp_b200.formats import cistem, mrc
+
+    monkeypatch.setattr(E, "Engine_real", E.Engine, raising=False)
+    monkeypatch.setattr(E, "Engine", _FakeEngine)
+    monkeypatch.setenv("CSPB_DEVICE", "0")
+    _FakeEngine.calls = []
+    n, px, P = 16, 1.35, 6
+    rng = np.random.default_rng(0)
+    rows = np.zeros(P, dtype=ROW_DTYPE_)
+    rows["position_in_stack"] = np.arange(1, P + 1)
+    rows["x_shift"], rows["y_shift"] = rng.normal(0, 2, P), rng.normal(0, 1, P)
+    rows["occupancy"], rows["pixel_size"], rows["score"], rows["tind"] = 100.0, px, 10.0, np.arange(P) % 3
+    d = tmp_path
+    mrc.write(str(d / "T20S_stack.mrc"), rng.normal(size=(P, n, n)).astype(np.float32), px)
+    mrc.write(str(d / "T20S_r01.mrc"), rng.normal(size=(n, n, n)).astype(np.float32), px)
+    cistem.write_parameters(str(d / "T20S_r01.cistem"), rows)
+    cistem.write_parameters(str(d / "T20S_r01_stat.cistem"), tables.parameter_statistics(rows))
+    (d / "statistics_r01.txt").write_text("")
+    monkeypatch.chdir(d)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prompts_refine.json")))
+    text = g["global_focus_priors"]["heredoc"].replace("../T20S_stack.mrc", "T20S_stack.mrc").replace("\nnull\n", "\nT20S_r01_stat.cistem\n", 1)
+    text = text.replace("\n1\n100\n", f"\n1\n{P}\n", 1).replace("\nO\n", "\nC1\n", 1)
+    p = refine3d.parse(prompts.Answers(text, "refine3d"))
+    import io
+
+    log = io.StringIO()
+    refine3d.run(p, out=log)
+    names = [c[0] for c in _FakeEngine.calls]
+    assert names.count("set_focus_mask") == 1 and "set_search_grid" in names and "refine" in names and names[-1] == "close"
+    cfg = next(c for c in _FakeEngine.calls if c[0] == "refine_configure")[1][0]
+    st = tables.parameter_statistics(rows)
+    assert cfg.use_priors == 1 and np.isclose(cfg.prior_mean_x, st["x_shift"][0]) and np.isclose(cfg.prior_var_y, st["y_shift"][1])
+    assert (cfg.refine_psi, cfg.refine_theta, cfg.refine_phi, cfg.refine_x, cfg.refine_y) == (1, 0, 0, 1, 0) and cfg.global_search == 1
+    assert next(c for c in _FakeEngine.calls if c[0] == "set_focus_mask")[1] == (120.5, 98.0, 77.25, 45.0)
+    assert "Shift restraint" in log.getvalue() and "focus mask" in log.getvalue() and "Normal termination" in log.getvalue()
+    out_rows = cistem.read_parameters("T20S_r01_0000001_0000100.cistem")
+    assert out_rows.size == P and (out_rows["score"] == 12.5).all()
+    # ---- reconstruct3d: dose weights + likelihood blurring + dumps
+    _FakeEngine.calls = []
+    cistem.write_parameters(str(d / "T20S_r01_used.cistem"), rows)
+    tables.write_global_weights(str(d / "global_weight.txt"), tables.global_weights(rows))
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prompts_reconstruct.json")))
+    text = g["dose_blur_split"]["heredoc"].replace("../T20S_stack.mrc", "T20S_stack.mrc").replace("../T20S_r01", "T20S_r01")
+    text = text.replace("/scratch/not_provided", "global_weight.txt").replace("$SCRATCH/", "").replace("\n1\n50\n", f"\n1\n{P}\n", 1)
+    p = reconstruct3d.parse(prompts.Answers(text, "reconstruct3d"))
+    log = io.StringIO()
+    reconstruct3d.run(p, out=log)
+    names = [c[0] for c in _FakeEngine.calls]
+    assert names.count("recon_insert") == 21 and names.count("score_poses") == 1 and "set_reference" in names   # the fan
+    ins = [c for c in _FakeEngine.calls if c[0] == "recon_insert"]
+    total_occ = sum(c[1][1]["occupancy"].astype(np.float64) for c in ins)
+    dw = reconstruct3d.dose_weights(p, rows)
+    assert np.allclose(total_occ, rows["occupancy"] * dw, rtol=1e-5)          # flat scores: uniform fan, weights sum to 1
+    assert "Likelihood blurring" in log.getvalue() and os.path.exists("T20S_r01_map1_n1.mrc")
