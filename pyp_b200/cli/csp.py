@@ -150,9 +150,10 @@ def run_refine(par, ext, mode, first, last, stack, config, out):
     idx = entity_rows(rows_all, particles, tilts, mode, first, last)
     out_par, out_ext = out_paths(par, first, last)
     if idx.size == 0:
-        cistem.write_parameters(out_par, rows_all[:0])
-        cistem.write_extended(out_ext, particles[:0], tilts[:0])
-        out.write(f"csp: nothing to refine for {first}..{last}\n")
+        # no file for an empty range: the reference's reader raises 'Binary file is broken.' on a zero-row payload
+        # and its writer asserts rows > 0 (cistem_star_file.py:694-776), and merge_alignment_parameters loads every
+        # `*_??????_??????.cistem` it globs (particle_cspt.py:113-138) — an empty file would crash pyp's merge
+        out.write(f"csp: nothing to refine for {first}..{last}; no output written\n")
         return
     rows = rows_all[idx]
     order = np.argsort(rows["position_in_stack"], kind="stable")

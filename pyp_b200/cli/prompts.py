@@ -70,6 +70,17 @@ def pick_device(first=1, count=1):
     return ((int(first) - 1) // max(1, int(count))) % n
 
 
+def write_notes(out, program, items):
+    """One log line per answer that was read but does not change the computation (DESIGN.md §7,
+    oracle/SEMANTICS.md §8): `items` = [(condition, text), ...].  Returns the number of notes written."""
+    n = 0
+    for cond, text in items:
+        if cond:
+            out.write(f"{program}: note: {text}\n")
+            n += 1
+    return n
+
+
 def banner(name):
     return (f"\n        **   Welcome to {name}   **\n\n"
             "            Version : cspb200 0.1.0 (B200-native drop-in)\n"

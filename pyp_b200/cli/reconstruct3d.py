@@ -7,7 +7,7 @@ import time
 import numpy as np
 
 from ..formats import cistem, dump, mrc
-from .prompts import Answers, PromptError, banner, pick_device
+from .prompts import Answers, PromptError, banner, pick_device, write_notes
 from .refine3d import select_rows
 
 
@@ -58,6 +58,23 @@ def parse(ans: Answers):
     p["dump2"] = ans.text("output dump filename for even particles")
     p["max_threads"] = ans.integer("max threads") if not ans.done() else 1
     return p
+
+
+def ignored_answers(p):
+    """Answers of the list that this implementation reads and does not act on (each gets a log line)."""
+    return [
+        (p["inner_mask_radius"] != 0, f"inner mask radius {p['inner_mask_radius']:g} A accepted and ignored (pyp always passes 0)"),
+        (p["resolution_ref"] != 0, f"resolution limit of reference {p['resolution_ref']:g} A accepted and ignored"),
+        (p["min_tilt_score"] != 0 or p["max_tilt_score"] != -1,
+         f"tilt-particle score window {p['min_tilt_score']:g}..{p['max_tilt_score']:g} accepted and ignored: OCCUPANCY > 0 selects the projections (frealign.py:1762-1765)"),
+        (p["smoothing"] != 1, f"smoothing factor {p['smoothing']:g} accepted and ignored"),
+        (p["adjust_scores"], "adjust scores for defocus dependence = yes accepted and ignored: scores are used as given"),
+        (p["exclude_edges"], "exclude images with blank edges = yes accepted and ignored"),
+        (p["crop"], "crop particle images = yes accepted and ignored: images are inserted at their full box"),
+        (not p["split_even_odd"], "FSC with even/odd particles = no accepted and ignored: the halves are always odd / even POSITION_IN_STACK (or PIND)"),
+        (p["center_mass"], "center mass = yes accepted and ignored"),
+        (p["threshold_input"], "threshold input reconstruction = yes accepted and ignored"),
+    ]
 
 
 def dose_weights(p, rows):
@@ -154,6 +171,7 @@ def run(p, out=sys.stdout):
     if n_band:
         out.write(f"Likelihood blurring: {blur.LBLUR_NROT} in-plane rotations from {blur.LBLUR_START:+.0f} deg in steps of "
                   f"{blur.LBLUR_STEP:.0f} deg, LogP range {blur.LBLUR_RANGE:.0f}\n")
+    write_notes(out, "reconstruct3d", ignored_answers(p))
     out.write("\nReconstruct3D: Normal termination\n")
     eng.close()
 

@@ -13,7 +13,7 @@ import time
 import numpy as np
 
 from ..formats import cistem, mrc, statistics
-from .prompts import Answers, PromptError, banner, pick_device
+from .prompts import Answers, PromptError, banner, pick_device, write_notes
 
 
 def parse(ans: Answers):
@@ -88,6 +88,20 @@ def shift_prior(p, rows_all):
     return float(x.mean()), float(y.mean()), float(x.var()), float(y.var())
 
 
+def ignored_answers(p):
+    """Answers of the list that this implementation reads and does not act on (each gets a log line)."""
+    return [
+        (abs(p["percent_used"] - 1.0) > 1e-6, f"percent of particles to use = {p['percent_used']:g} accepted and ignored: every particle of the range is refined"),
+        (p["inner_mask_radius"] != 0, f"inner mask radius {p['inner_mask_radius']:g} A accepted and ignored (pyp always passes 0)"),
+        (p["class_res_limit"] > 0 and abs(p["class_res_limit"] - p["high_res_limit"]) > 1e-6,
+         f"resolution limit for classification {p['class_res_limit']:g} A accepted and ignored: LOGP is computed on the scoring band"),
+        (p["global_search"], f"mask radius for global search {p['search_mask_radius']:g} A accepted and ignored: the search uses the outer mask radius"),
+        (p["exclude_edges"], "exclude images with blank edges = yes accepted and ignored"),
+        (p["normalize_rec"], "normalize input reconstruction = yes accepted and ignored: the reference is used as given"),
+        (p["threshold_rec"], "threshold input reconstruction = yes accepted and ignored: the reference is used as given"),
+    ]
+
+
 def build_cfg(p, box):
     from ..engine import Engine
 
@@ -154,8 +168,9 @@ def run(p, out=sys.stdout):
     for s in range(0, rows.size, chunk):
         eng.load_images(images[s:s + chunk], append=s > 0)
     refined, changes, n_evals = eng.refine(rows, want_changes=True) if rows.size else (rows, rows.copy(), 0)
-    cistem.write_parameters(p["out_parameters"], refined)
-    cistem.write_parameters(p["out_changes"], changes)
+    if rows.size:  # no zero-row files: the reference's reader rejects an empty payload (cistem_star_file.py:694-776)
+        cistem.write_parameters(p["out_parameters"], refined)
+        cistem.write_parameters(p["out_changes"], changes)
     dt = time.time() - t0
     out.write(banner("Refine3D"))
     out.write(f"\nRefining particles {first} to {last} ({rows.size} rows), box {box}, pixel {p['pixel_size']}\n")
@@ -167,6 +182,7 @@ def run(p, out=sys.stdout):
                   f"variance ({cfg.prior_var_x:.3f}, {cfg.prior_var_y:.3f}) A^2\n")
     if focus:
         out.write("LogP evaluated inside the 2-D focus mask: centre ({:.1f}, {:.1f}, {:.1f}) A, radius {:.1f} A\n".format(*p["mask_2d"]))
+    write_notes(out, "refine3d", ignored_answers(p))
     out.write("\nRefine3D: Normal termination\n")
     eng.close()
     return refined

@@ -64,6 +64,7 @@ extern "C" int cspb_destroy(cspb_ctx *ctx) {
 extern "C" const char *cspb_last_error(const cspb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 extern "C" int cspb_sync(cspb_ctx *ctx) {
+    CSPB_ENTER(ctx);
     if (!ctx) return CSPB_E_ARG;
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -78,6 +79,7 @@ extern "C" int cspb_stream(cspb_ctx *ctx, void **stream_out) {
 extern "C" int64_t cspb_launch_count(const cspb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int cspb_fft2_r2c(cspb_ctx *ctx, const float *in, float *out_complex, int n, int batch, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !in || !out_complex || n < 2 || batch < 1) return CSPB_E_ARG;
     const int nh = n / 2 + 1;
     const size_t in_b = (size_t)batch * n * n * sizeof(float), out_b = (size_t)batch * n * nh * sizeof(float2);
@@ -93,6 +95,7 @@ extern "C" int cspb_fft2_r2c(cspb_ctx *ctx, const float *in, float *out_complex,
 }
 
 extern "C" int cspb_fft2_c2r(cspb_ctx *ctx, const float *in_complex, float *out, int n, int batch, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !in_complex || !out || n < 2 || batch < 1) return CSPB_E_ARG;
     const int nh = n / 2 + 1;
     const size_t out_b = (size_t)batch * n * n * sizeof(float), in_b = (size_t)batch * n * nh * sizeof(float2);
@@ -110,6 +113,7 @@ extern "C" int cspb_fft2_c2r(cspb_ctx *ctx, const float *in_complex, float *out,
 
 // cuFFT twin of cspb_fft2_r2c: comparison baseline for tests / bench only.
 extern "C" int cspb_cufft2_r2c(cspb_ctx *ctx, const float *in, float *out_complex, int n, int batch, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !in || !out_complex || n < 2 || batch < 1) return CSPB_E_ARG;
     const int nh = n / 2 + 1;
     const size_t in_b = (size_t)batch * n * n * sizeof(float), out_b = (size_t)batch * n * nh * sizeof(float2);
@@ -160,6 +164,7 @@ void prof_end(cspb_ctx *ctx) {
 }
 
 extern "C" int cspb_profile_enable(cspb_ctx *ctx, int on) {
+    CSPB_ENTER(ctx);
     if (!ctx) return CSPB_E_ARG;
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->prof) {
@@ -172,6 +177,7 @@ extern "C" int cspb_profile_enable(cspb_ctx *ctx, int on) {
 }
 
 extern "C" int cspb_profile_get(cspb_ctx *ctx, int kind, double *total_ms, int64_t *launches, int64_t *units) {
+    CSPB_ENTER(ctx);
     if (!ctx || kind < 0 || kind >= CSPB_PROF_KINDS) return CSPB_E_ARG;
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     double t = 0.0;

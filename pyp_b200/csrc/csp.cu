@@ -442,6 +442,7 @@ extern "C" int cspb_csp_compose(const cspb_particle *p, const cspb_particle *p0,
 
 extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_particle *particles, int n_particles,
                             cspb_tilt *tilts, int n_tilts, const cspb_csp_cfg *cfg, int first, int last, int64_t *n_evals_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !rows || !particles || !tilts || !cfg || n_rows < 0 || n_particles < 0 || n_tilts < 0) return CSPB_E_ARG;
     if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
     if (n_rows != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n_rows, ctx->n_images);
@@ -634,6 +635,7 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
 
 extern "C" int cspb_csp_extract(cspb_ctx *ctx, const float *images, int nx, int ny, int n_tilt, const cspb_row *rows,
                                 int n_rows, int box_in, int bin, float *stack_out, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !images || !rows || !stack_out || nx <= 0 || ny <= 0 || n_tilt <= 0 || n_rows < 0) return CSPB_E_ARG;
     if (box_in <= 0 || bin <= 0 || box_in % bin) return cspb_fail(ctx, CSPB_E_ARG, "box %d must be a multiple of bin %d", box_in, bin);
     if (n_rows == 0) return 0;

@@ -169,6 +169,21 @@ struct cspb_ctx {
     int64_t recon_inserted = 0;
 };
 
+// The current CUDA device is per host thread and other code in the process (torch, a second context on
+// another GPU) may change it: every C-ABI entry that allocates or launches makes the context's device
+// current for the duration of the call and restores the caller's afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const cspb_ctx *ctx) {
+        if (!ctx) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) switched = prev >= 0;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define CSPB_ENTER(ctx) DeviceGuard cspb_device_guard_(ctx)
+
 int cspb_fail(cspb_ctx *ctx, int code, const char *fmt, ...);
 extern "C" int cspb_wave_units(cspb_ctx *ctx);
 // event bracket helpers (no-ops unless profiling is enabled)

@@ -38,6 +38,8 @@ __device__ __forceinline__ float wrap360(float a) {
     return a;
 }
 
+__device__ __forceinline__ float wrap180(float d) { return d - 360.f * rintf(d * (1.f / 360.f)); }
+
 // Stencil evaluation order of the parameters: pure in-plane shifts last, so that the evaluations
 // which share the centre's rotation and CTF are consecutive and can be scored from ONE gather.
 __device__ __constant__ const int OPT_ORDER[OPT_NP] = {0, 1, 2, 5, 3, 4};

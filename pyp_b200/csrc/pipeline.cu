@@ -12,6 +12,7 @@
 
 extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images, int flags,
                                        int64_t *n_evals_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !images_host || !rows_host || n_images < 0) return CSPB_E_ARG;
     const bool do_refine = flags & CSPB_DO_REFINE, do_insert = flags & CSPB_DO_INSERT;
     if (!do_refine && !do_insert) return cspb_fail(ctx, CSPB_E_ARG, "nothing to do (flags = %d)", flags);

@@ -307,6 +307,7 @@ extern "C" int cspb_recon_cfg_default(cspb_recon_cfg *cfg, int box, float pixel_
 }
 
 extern "C" int cspb_recon_begin(cspb_ctx *ctx, const cspb_recon_cfg *cfg) {
+    CSPB_ENTER(ctx);
     if (!ctx || !cfg) return CSPB_E_ARG;
     if (cfg->box < 16 || (cfg->box & 1) || (cfg->pad != 1 && cfg->pad != 2) || cfg->pixel_size <= 0.f)
         return cspb_fail(ctx, CSPB_E_ARG, "bad recon box/pad/pixel");
@@ -357,6 +358,7 @@ extern "C" int cspb_recon_dims(const cspb_ctx *ctx, int *np_out, int64_t *floats
 }
 
 extern "C" int cspb_recon_device_ptr(cspb_ctx *ctx, int half, void **ptr_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->recon_ready || half < 0 || half > 1 || !ptr_out) return CSPB_E_ARG;
     int rcf = recon_flush_deferred(ctx);
     if (rcf) return rcf;
@@ -365,6 +367,7 @@ extern "C" int cspb_recon_device_ptr(cspb_ctx *ctx, int half, void **ptr_out) {
 }
 
 extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_row *rows, int n_images, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !images || !rows || n_images < 0) return CSPB_E_ARG;
     if (!ctx->recon_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_recon_begin first");
     const cspb_recon_cfg &c = ctx->ccfg;
@@ -427,6 +430,7 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
 }
 
 extern "C" int cspb_recon_get_dump(cspb_ctx *ctx, int half, float *out, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->recon_ready || half < 0 || half > 1 || !out) return CSPB_E_ARG;
     int rcf = recon_flush_deferred(ctx);
     if (rcf) return rcf;
@@ -438,6 +442,7 @@ extern "C" int cspb_recon_get_dump(cspb_ctx *ctx, int half, float *out, int loc)
 }
 
 extern "C" int cspb_recon_add_dump(cspb_ctx *ctx, int half, const float *in, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->recon_ready || half < 0 || half > 1 || !in) return CSPB_E_ARG;
     const int np = ctx->rnp, xh = np / 2 + 1;
     const long long nvox = (long long)xh * np * np;
@@ -455,6 +460,7 @@ extern "C" int cspb_recon_add_dump(cspb_ctx *ctx, int half, const float *in, int
 
 extern "C" int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, float outer_radius_a, float *half1,
                                    float *half2, float *map, float *stats, int n_shells, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->recon_ready) return CSPB_E_STATE;
     const cspb_recon_cfg &c = ctx->ccfg;
     const int n = c.box, np = ctx->rnp, xh = np / 2 + 1;
@@ -511,6 +517,7 @@ extern "C" int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, floa
 }
 
 extern "C" int cspb_recon_end(cspb_ctx *ctx) {
+    CSPB_ENTER(ctx);
     if (!ctx) return CSPB_E_ARG;
     ctx->d_acc[0].release();
     ctx->d_acc[1].release();

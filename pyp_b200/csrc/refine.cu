@@ -577,7 +577,8 @@ __global__ void opt_write_rows_kernel(const OptState *__restrict__ st, int n_ima
     if (alpha_out) alpha_out[img] = vbest.w > 0.f ? vbest.y / vbest.w : 0.f;
     if (changes) {
         cspb_row c = r;
-        c.psi = r.psi - old.psi; c.theta = r.theta - old.theta; c.phi = r.phi - old.phi;
+        // angular changes wrapped into [-180, 180): a refinement that crosses 0/360 is a small change
+        c.psi = wrap180(r.psi - old.psi); c.theta = wrap180(r.theta - old.theta); c.phi = wrap180(r.phi - old.phi);
         c.x_shift = r.x_shift - old.x_shift; c.y_shift = r.y_shift - old.y_shift;
         c.defocus_1 = r.defocus_1 - old.defocus_1; c.defocus_2 = r.defocus_2 - old.defocus_2;
         c.score = r.score - start_score;
@@ -735,6 +736,7 @@ extern "C" int cspb_refine_cfg_default(cspb_refine_cfg *cfg, int box, float pixe
 }
 
 extern "C" int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg) {
+    CSPB_ENTER(ctx);
     if (!ctx || !cfg) return CSPB_E_ARG;
     if (cfg->box < 16 || (cfg->box & 1) || cfg->pixel_size <= 0.f || (cfg->pad != 1 && cfg->pad != 2))
         return cspb_fail(ctx, CSPB_E_ARG, "bad box/pixel/pad");
@@ -787,6 +789,7 @@ extern "C" int cspb_band_counts(const cspb_ctx *ctx, int *n_band, int *n_slots) 
 }
 
 extern "C" int cspb_refine_set_ring_weights(cspb_ctx *ctx, const float *w, int n_rings) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->refine_ready) return CSPB_E_STATE;
     if (!w) { ctx->have_ring_w = false; return 0; }
     const int need = ctx->rcfg.box + 1;
@@ -808,6 +811,7 @@ static bool is_lattice_op(const float *m) {
 }
 
 extern "C" int cspb_set_symmetry(cspb_ctx *ctx, const float *mats, int n_mats) {
+    CSPB_ENTER(ctx);
     if (!ctx || !mats || n_mats < 1) return CSPB_E_ARG;
     if (ctx->recon_ready && ctx->raw_dirty) {
         int rc = recon_flush_deferred(ctx);  // pending inserts belong to the previous group
@@ -876,6 +880,7 @@ extern "C" int cspb_set_symmetry(cspb_ctx *ctx, const float *mats, int n_mats) {
 }
 
 extern "C" int cspb_set_reference(cspb_ctx *ctx, const float *vol, int n, int loc) {
+    CSPB_ENTER(ctx);
     if (!ctx || !vol) return CSPB_E_ARG;
     if (!ctx->refine_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_refine_configure first");
     if (n != ctx->rcfg.box) return cspb_fail(ctx, CSPB_E_ARG, "reference edge %d != box %d", n, ctx->rcfg.box);
@@ -967,6 +972,7 @@ static int estimate_noise_from_spectra(cspb_ctx *ctx, const float2 *spec, int co
 }
 
 extern "C" int cspb_refine_set_noise_curve(cspb_ctx *ctx, const float *curve, int n_rings) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->refine_ready) return CSPB_E_STATE;
     const int need = ctx->rcfg.box + 1;
     if (!curve || n_rings != need) return cspb_fail(ctx, CSPB_E_ARG, "noise curve needs box+1 = %d rings", need);
@@ -981,6 +987,7 @@ extern "C" int cspb_refine_set_noise_curve(cspb_ctx *ctx, const float *curve, in
 }
 
 extern "C" int cspb_refine_get_noise_curve(cspb_ctx *ctx, float *curve_out, int n_rings) {
+    CSPB_ENTER(ctx);
     if (!ctx || !ctx->refine_ready || !ctx->have_noise) return CSPB_E_STATE;
     if (!curve_out || n_rings != ctx->rcfg.box + 1) return CSPB_E_ARG;
     memcpy(curve_out, ctx->noise_curve.data(), n_rings * sizeof(float));
@@ -990,6 +997,7 @@ extern "C" int cspb_refine_get_noise_curve(cspb_ctx *ctx, float *curve_out, int 
 extern "C" int cspb_refine_num_images(const cspb_ctx *ctx) { return ctx ? ctx->n_images : 0; }
 
 extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n_images, int loc, int append) {
+    CSPB_ENTER(ctx);
     if (!ctx || !images || n_images < 0) return CSPB_E_ARG;
     if (!ctx->refine_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_refine_configure first");
     const cspb_refine_cfg &c = ctx->rcfg;
@@ -1081,6 +1089,7 @@ int upload_rows(cspb_ctx *ctx, const cspb_row *rows, int n, cspb_row **d_rows, C
 
 extern "C" int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int n_rows, const int32_t *image_index,
                                        const float *poses6, int n_evals, float *scores_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !rows || !image_index || !poses6 || !scores_out || n_evals < 0) return CSPB_E_ARG;
     if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
     if (n_rows != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n_rows, ctx->n_images);
@@ -1121,6 +1130,7 @@ extern "C" int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int 
 }
 
 extern "C" int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, float *scores_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !rows || !scores_out || n < 0) return CSPB_E_ARG;
     std::vector<int32_t> idx(n);
     std::vector<float> poses((size_t)n * 6);
@@ -1311,6 +1321,7 @@ __global__ void phase_sum_scatter_kernel(const float2 *__restrict__ partial, int
 }
 
 extern "C" int cspb_refine_phase_sum(cspb_ctx *ctx, const cspb_row *rows, int n_rows, float *out_complex) {
+    CSPB_ENTER(ctx);
     if (!ctx || !rows || !out_complex || n_rows < 0) return CSPB_E_ARG;
     if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
     if (n_rows != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n_rows, ctx->n_images);
@@ -1458,6 +1469,7 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
 }
 
 extern "C" int cspb_refine_set_search_grid(cspb_ctx *ctx, const float *angles3, int n_orient) {
+    CSPB_ENTER(ctx);
     if (!ctx || (!angles3 && n_orient > 0) || n_orient < 0) return CSPB_E_ARG;
     ctx->n_grid = n_orient;
     if (n_orient == 0) return 0;
@@ -1468,6 +1480,7 @@ extern "C" int cspb_refine_set_search_grid(cspb_ctx *ctx, const float *angles3, 
 }
 
 extern "C" int cspb_refine_run_device(cspb_ctx *ctx, cspb_row *rows_dev, int n, int64_t *n_evals_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !rows_dev) return CSPB_E_ARG;
     if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
     if (n != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n, ctx->n_images);
@@ -1479,6 +1492,7 @@ extern "C" int cspb_refine_run_device(cspb_ctx *ctx, cspb_row *rows_dev, int n, 
 }
 
 extern "C" int cspb_refine_run(cspb_ctx *ctx, cspb_row *rows, int n, cspb_row *changes_out, int64_t *n_evals_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !rows) return CSPB_E_ARG;
     if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
     if (n != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n, ctx->n_images);
@@ -1500,6 +1514,7 @@ extern "C" int cspb_refine_run(cspb_ctx *ctx, cspb_row *rows, int n, cspb_row *c
 
 // ================================================================== building blocks
 extern "C" int cspb_ctf_image(cspb_ctx *ctx, const cspb_row *row, int n, float *out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !row || !out || n < 2) return CSPB_E_ARG;
     const int nh = n / 2 + 1;
     RESERVE(ctx, ctx->d_work2, (size_t)n * nh * sizeof(float));
@@ -1513,6 +1528,7 @@ extern "C" int cspb_ctf_image(cspb_ctx *ctx, const cspb_row *row, int n, float *
 }
 
 extern "C" int cspb_project(cspb_ctx *ctx, float psi, float theta, float phi, float *out_complex) {
+    CSPB_ENTER(ctx);
     if (!ctx || !out_complex) return CSPB_E_ARG;
     if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
     const int n = ctx->rcfg.box, nh = n / 2 + 1;
@@ -1553,6 +1569,7 @@ __global__ void __launch_bounds__(128, 8) gather_peak_kernel(const RefQuad *__re
 }  // namespace
 
 extern "C" int cspb_gather_peak(cspb_ctx *ctx, size_t window_bytes, int per_cta, float *gbs_out) {
+    CSPB_ENTER(ctx);
     if (!ctx || !gbs_out || window_bytes < 4096) return CSPB_E_ARG;
     const size_t buf_bytes = per_cta ? ((size_t)256 << 20) : window_bytes;
     DevBuf buf, sink;

@@ -35,9 +35,12 @@ def new_rows(n, pixel_size=1.0, voltage_kv=300.0, cs_mm=2.7, amplitude_contrast=
 
 
 def _loc_ptr(a):
-    """(pointer, location) of a numpy array (host) or torch CUDA tensor (device)."""
+    """(pointer, location) of a numpy array (host) or torch CUDA tensor (device).  The pointer holds no
+    reference: the caller keeps `a` alive through the C call, so a numpy array must already be C-contiguous
+    (a silent copy here would be freed before the library reads it)."""
     if isinstance(a, np.ndarray):
-        return ptr(np.ascontiguousarray(a)), HOST
+        assert a.flags["C_CONTIGUOUS"], "pass a C-contiguous array (np.ascontiguousarray bound to a local)"
+        return ptr(a), HOST
     if hasattr(a, "data_ptr"):  # torch tensor
         assert a.is_contiguous()
         return C.c_void_p(a.data_ptr()), (DEVICE if a.is_cuda else HOST)
@@ -118,9 +121,11 @@ class Engine:
         return a.value, b.value
 
     def set_reference(self, vol):
-        p, loc = _loc_ptr(vol if not isinstance(vol, np.ndarray) else np.ascontiguousarray(vol, dtype=np.float32))
+        if isinstance(vol, np.ndarray):
+            vol = np.ascontiguousarray(vol, dtype=np.float32)  # bound to a local: alive through the C call
         n = vol.shape[0]
         assert tuple(vol.shape) == (n, n, n)
+        p, loc = _loc_ptr(vol)
         self._ck(self._l.cspb_set_reference(self._h, p, n, loc))
 
     def set_symmetry(self, symbol_or_mats):
