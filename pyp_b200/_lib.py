@@ -102,6 +102,8 @@ _SIGNATURES = {
     "cspb_launch_count": (_i64, [_vp]),
     "cspb_profile_enable": (_i, [_vp, _i]),
     "cspb_profile_get": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
+    "cspb_profile_count_loads": (_i, [_vp, _i]),
+    "cspb_profile_get_loads": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "cspb_refine_cfg_default": (_i, [C.POINTER(RefineCfg), _i, _f]),
     "cspb_refine_configure": (_i, [_vp, C.POINTER(RefineCfg)]),
     "cspb_refine_set_ring_weights": (_i, [_vp, _vp, _i]),

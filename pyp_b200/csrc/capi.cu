@@ -194,3 +194,29 @@ extern "C" int cspb_profile_get(cspb_ctx *ctx, int kind, double *total_ms, int64
     if (units) *units = u;
     return 0;
 }
+
+// Census of the scorer's gather loads (see score_census_kernel): while on, every scorer launch is followed
+// by a counting launch over the same units.  For roofline bookkeeping only — switch it off before timing.
+extern "C" int cspb_profile_count_loads(cspb_ctx *ctx, int on) {
+    CSPB_ENTER(ctx);
+    if (!ctx) return CSPB_E_ARG;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (on) {
+        RESERVE(ctx, ctx->d_load_count, sizeof(unsigned long long));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_load_count.p, 0, sizeof(unsigned long long), ctx->stream));
+        ctx->census_evals = 0;
+    }
+    ctx->count_loads = on != 0;
+    return 0;
+}
+
+extern "C" int cspb_profile_get_loads(cspb_ctx *ctx, int64_t *quad_loads, int64_t *evals) {
+    CSPB_ENTER(ctx);
+    if (!ctx || !ctx->d_load_count.p) return CSPB_E_STATE;
+    unsigned long long v = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&v, ctx->d_load_count.p, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (quad_loads) *quad_loads = (int64_t)v;
+    if (evals) *evals = ctx->census_evals;
+    return 0;
+}

@@ -105,6 +105,10 @@ struct ProfRec {
 struct cspb_ctx {
     bool prof_on = false;
     std::vector<ProfRec> prof;
+    // gather-load census of the scorer (cspb_profile_count_loads): quad loads the launches issue
+    bool count_loads = false;
+    DevBuf d_load_count;
+    int64_t census_evals = 0;
 
     int device = 0;
     cudaStream_t stream = nullptr;

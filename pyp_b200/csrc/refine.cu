@@ -450,6 +450,52 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
     }
 }
 
+// Gather-load census of one scorer launch (roofline bookkeeping, never on the product path): the same
+// units and address arithmetic as score_kernel, no loads — counts the 32-byte quad loads that kernel
+// issues per lane (2 for the unit's first pose, 2 more for every other pose that leaves its voxel;
+// shared-gather units gather once).  bench.py runs one untimed step with the census on and reports
+// loaded bytes / s against the measured gather peak.
+__global__ void __launch_bounds__(128) score_census_kernel(const ScoreArgs A, int PB, int mode, unsigned long long *__restrict__ total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = blockIdx.x * 4 + warp;
+    if (u >= A.n_units) return;
+    const ScoreUnit un = A.units[u];
+    __shared__ float s_m[4][4][6];
+    if (lane < PB) {
+        const float *q = A.poses6 + (long long)(un.first_eval + lane) * 6;
+        float r[9];
+        euler_matrix(q[0], q[1], q[2], r);
+        s_m[warp][lane][0] = r[0] * A.padf; s_m[warp][lane][1] = r[1] * A.padf;
+        s_m[warp][lane][2] = r[3] * A.padf; s_m[warp][lane][3] = r[4] * A.padf;
+        s_m[warp][lane][4] = r[6] * A.padf; s_m[warp][lane][5] = r[7] * A.padf;
+    }
+    __syncwarp();
+    const int origin = (A.rc * A.sy + A.rc) * A.sx;
+    const int NG = mode == 1 ? 1 : PB;
+    unsigned cnt = 0;
+    for (int b = 0; b < A.n_bands; ++b) {
+        const BandDesc bd = A.bands[b];
+        for (int it = 0; it < bd.n_iter; ++it) {
+            const int32_t ij = A.slot_ij[bd.slot_start + it * 32 + lane];
+            int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+            if (i == CSPB_DUMMY_I) { i = 0; j = 0; }
+            const float fi = (float)i, fj = (float)j;
+            int off0 = 0;
+            for (int p = 0; p < NG; ++p) {
+                const float *m = s_m[warp][p];
+                float x = m[0] * fi + m[1] * fj, y = m[2] * fi + m[3] * fj, z = m[4] * fi + m[5] * fj;
+                const float sgn = x < 0.f ? -1.f : 1.f;
+                x = fabsf(x); y *= sgn; z *= sgn;
+                const int off = origin + (__float2int_rd(z) * A.sy + __float2int_rd(y)) * A.sx + __float2int_rd(x);
+                if (p == 0) { off0 = off; cnt += 2; }
+                else if (off != off0) cnt += 2;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) atomicAdd(total, (unsigned long long)cnt);
+}
+
 // central slice on the full half-plane grid (building block / test helper)
 __global__ void project_kernel(const float4 *__restrict__ ref4, int sx, int sy, int rc, float padf, int n,
                                float r_hi, float psi, float theta, float phi, float2 *__restrict__ out) {
@@ -661,6 +707,11 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count
 #undef CSPB_LAUNCH_SCORE
     prof_end(ctx);
     KERNEL_CHECK(ctx);
+    if (ctx->count_loads) {
+        score_census_kernel<<<grid, 128, 0, ctx->stream>>>(a, count, (mode == 2 && count == 1) ? 0 : mode, ctx->d_load_count.as<unsigned long long>());
+        KERNEL_CHECK(ctx);
+        ctx->census_evals += n_evals;
+    }
     return 0;
 }
 

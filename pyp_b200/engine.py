@@ -101,6 +101,16 @@ class Engine:
         self._ck(self._l.cspb_profile_get(self._h, int(kind), C.byref(t), C.byref(n), C.byref(u)))
         return t.value, int(n.value), int(u.value)
 
+    def count_loads(self, on=True):
+        """Switch the scorer's gather-load census on / off (roofline bookkeeping, untimed steps only)."""
+        self._ck(self._l.cspb_profile_count_loads(self._h, 1 if on else 0))
+
+    def loads(self):
+        """(32-byte reference loads issued by the scorer, evaluations covered) since the census was switched on."""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self._l.cspb_profile_get_loads(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     # ------------------------------------------------------------------ refine3d
     @staticmethod
     def refine_defaults(box, pixel_size):

@@ -464,3 +464,70 @@ def test_front_end_branches_run_without_a_gpu(tmp_path, monkeypatch):
     dw = reconstruct3d.dose_weights(p, rows)
     assert np.allclose(total_occ, rows["occupancy"] * dw, rtol=1e-5)          # flat scores: uniform fan, weights sum to 1
     assert "Likelihood blurring" in log.getvalue() and os.path.exists("T20S_r01_map1_n1.mrc")
+
+
+def test_tier_a_probe_and_answer_builders_match_the_reference_heredocs(tmp_path, monkeypatch):
+    """oracle/tier_a.py: no real binaries in this tree -> tier B; an ELF of the right
+    name and size under $PYP_DIR/external is found; the answer lists the runner feeds to the binaries equal the
+    heredocs the reference's own builders produce (tests/golden/prompts_*.json)."""
+    import json
+
+    from oracle import tier_a
+
+    GOLDEN = os.path.join(ROOT, "tests", "golden")
+    monkeypatch.delenv("CSPB_TIER_A_DIR", raising=False)
+    monkeypatch.setenv("PYP_DIR", "/nonexistent")
+    assert tier_a.find_binaries() == {} and tier_a.probe_report()["tier"] == "B"
+    ext = tmp_path / "external" / "cistem2"
+    ext.mkdir(parents=True)
+    (ext / "refine3d").write_bytes(b"version https://git-lfs.github.com/spec/v1\noid sha256:1865b0c3\nsize 43818480\n")  # an LFS stub
+    (ext / "merge3d").write_bytes(b"\x7fELF" + b"\0" * (2 << 20))
+    monkeypatch.setenv("PYP_DIR", str(tmp_path))
+    rep = tier_a.probe_report()
+    assert set(rep["binaries"]) == {"merge3d"} and rep["tier"] == "B" and any("refine3d" in s for s in rep["stubs"])
+    g = json.load(open(os.path.join(GOLDEN, "prompts_refine.json")))
+    a = tier_a.refine3d_answers("../T20S_stack.mrc", "T20S_r01.cistem", "T20S_r01.mrc", "statistics_r01.txt", "T20S_r01", 1, 100, 1.35, 700.0, 80.0,
+                                "100.0", "8.0", symmetry="O", use_statistics=True, class_rhcls="8.0", search_radius=120.0, search_rhref="8.0")
+    assert tier_a.heredoc(a) == g["local"]["heredoc"]
+    a = tier_a.refine3d_answers("../T20S_stack.mrc", "T20S_r01.cistem", "T20S_r01.mrc", "statistics_r01.txt", "T20S_r01", 1, 100, 1.35, 700.0, 80.0,
+                                "100.0", "8.0", symmetry="O", use_statistics=True, use_priors=True, signed_cc_limit="25.0", class_rhcls="8.0",
+                                search_radius=110.0, search_rhref="8.0", focus=("120.5", "98.0", "77.25", "45.0"), defocus_range=2000,
+                                global_search=True, local=False, mask=(1, 0, 1, 1, 0), focus_mask=True, refine_defocus=True, invert=True)
+    assert tier_a.heredoc(a) == g["global_focus_priors"]["heredoc"]
+    g = json.load(open(os.path.join(GOLDEN, "prompts_reconstruct.json")))
+    a = tier_a.reconstruct3d_answers("../T20S_stack.mrc", "../T20S_r01_used.cistem", "../T20S_r01.mrc", "T20S_r01", 1, 50, 1.35, 700.0, 86.4, 2.7,
+                                     "$SCRATCH/T20S_r01_map1_n1.mrc", "$SCRATCH/T20S_r01_map2_n1.mrc", symmetry="O")
+    assert tier_a.heredoc(a) == g["plain"]["heredoc"]
+    a = tier_a.reconstruct3d_answers("../T20S_stack.mrc", "../T20S_r01_used.cistem", "../T20S_r01.mrc", "T20S_r01", 1, 50, 1.35, 700.0, 86.4, 2.7,
+                                     "$SCRATCH/T20S_r01_map1_n1.mrc", "$SCRATCH/T20S_r01_map2_n1.mrc", score_weighting=True,
+                                     dose=("/scratch/not_provided", True, 4, 0.75), per_particle=True, blurring=True)
+    assert tier_a.heredoc(a) == g["dose_blur_split"]["heredoc"]
+    g = json.load(open(os.path.join(GOLDEN, "prompts_merge.json")))
+    a = tier_a.merge3d_answers("T20S_r01_03", 700.0, 86.4, "$SCRATCH/T20S_r01_map1_n.mrc", "$SCRATCH/T20S_r01_map2_n.mrc", 3)
+    assert tier_a.heredoc(a) == g["merge3d"]["heredoc"]
+    # the range split is the reference's (local_run.py:507-516)
+    assert tier_a.split_ranges(100, 8) == pd.split_ranges(100, 8)
+
+
+def test_bench_workload_parameters_equal_the_library_defaults():
+    """bench.py builds the workload's refine3d / reconstruct3d parameters as plain dicts so that the reference arm
+    never loads libcspb200.so; they must be the library's own defaults apart from the benchmark band."""
+    import bench
+    from pyp_b200.engine import Engine
+
+    for name, c in bench.CONFIGS.items():
+        rp, lib_cfg = bench.refine_params(c), Engine.refine_defaults(c["box"], c["pixel"])
+        differ = {k for k, v in rp.items() if abs(float(getattr(lib_cfg, k)) - float(v)) > 1e-4 * max(1.0, abs(float(v)))}
+        allowed = {"mask_radius", "search_mask_radius"} | ({"global_search", "search_high_res", "search_range_x", "search_range_y"} if c.get("global_search") else set())
+        assert differ <= allowed, (name, differ)
+        cp, lib_rc = bench.recon_params(c), Engine.recon_defaults(c["box"], c["pixel"])
+        assert {k for k, v in cp.items() if abs(float(getattr(lib_rc, k)) - float(v)) > 1e-5 * max(1.0, abs(float(v)))} <= {"pad"}, name
+    # n_band of SURVEY.md §8d
+    assert bench.band_count(128, 1.35, 100.0, 2.5 * 1.35) == 4168 and bench.band_count(256, 1.0, 100.0, 2.5) == 16558
+    assert bench.band_count(384, 1.35, 100.0, 2.5 * 1.35) == 37174
+    # reconstruct3d inserts r <= n/2 - 1 (no weight on the Nyquist planes): a few % below SURVEY's (pi/8) n^2 figure
+    assert [bench.recon_band(n) for n in (128, 256, 512)] == [6227, 25309, 102135]
+    # both arms print the same config object
+    a = bench.parse_args(["--config", "C2"])
+    b = bench.parse_args(["--config", "C2", "--impl", "reference"])
+    assert bench.workload_config(a, 32768) == bench.workload_config(b, 32768)

@@ -1,21 +1,42 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full capture of the hot kernels.
-# Usage (from the repo root, on the GPU box): bash tools/gpu_round.sh [tag]
-TAG=${1:-r01}
+# One GPU-box visit: machine facts, parity tests, smoke, bench (both arms, every config), ncu launch list + full
+# captures of the hot kernels.  Usage (from the repo root, on the GPU box): bash tools/gpu_round.sh <tag> [sections]
+# sections (default "facts tests smoke bench ref configs launches ncu"): any subset, space separated.
+TAG=${1:-r02}
+SECTIONS=${2:-"facts tests smoke bench ref configs launches ncu"}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> $OUT/pytest_gpu.log
-timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1
-timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err
-timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
-# launch list of the bench command (one metric, no clock control): shares of the step
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
-  --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
-# full capture of the dominant kernels (smaller resident stack: ncu replays each launch ~40x)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_kernel --launch-skip 8 -c 3 \
-  -o $OUT/score_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline > $OUT/ncu_score.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:insert_kernel -c 2 \
-  -o $OUT/insert_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline > $OUT/ncu_insert.log 2>&1
+has() { [[ " $SECTIONS " == *" $1 "* ]]; }
+if has facts; then
+  { nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv; nproc; free -g; cat /sys/fs/cgroup/memory.max 2>/dev/null;
+    lscpu | head -25; nvidia-smi topo -m; numactl -H 2>/dev/null | head; } > $OUT/facts.txt 2>&1
+fi
+if has tests; then
+  ( time timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 ) > $OUT/pytest_gpu.log 2>&1
+  echo "pytest exit $?" >> $OUT/pytest_gpu.log
+fi
+if has smoke; then timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; fi
+if has bench; then timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; fi
+if has ref; then ( time timeout 600 python bench.py --impl reference --steps 20 --warmup 3 ) > $OUT/bench_ref.json 2> $OUT/bench_ref.err; fi
+if has configs; then
+  for C in C1 C3 C4 C5; do
+    timeout 900 python bench.py --config $C --steps 3 --warmup 3 > $OUT/bench_$C.json 2> $OUT/bench_$C.err
+  done
+fi
+if has launches; then
+  # launch list of the bench command (one metric, no clock control): shares of the step
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
+    --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-strong > $OUT/bench_under_ncu.log 2>&1
+fi
+if has ncu; then
+  # full capture of the dominant kernels (smaller resident stack: ncu replays each launch ~40x)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_kernel --launch-skip 8 -c 3 \
+    -o $OUT/score_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_score.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:insert_kernel -c 2 \
+    -o $OUT/insert_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_insert.log 2>&1
+fi
+if has ncu_c4; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_kernel --launch-skip 8 -c 2 \
+    -o $OUT/score_c4_full -f python bench.py --config C4 --steps 1 --warmup 1 --particles 512 --no-e2e --no-cpu-baseline > $OUT/ncu_score_c4.log 2>&1
+fi
 ls -la $OUT
