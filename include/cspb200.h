@@ -136,6 +136,9 @@ int cspb_refine_cfg_default(cspb_refine_cfg *cfg, int box, float pixel_size);
 
 /* Configure the scorer; builds the polar-patch band plan for (box, low_res, high_res). */
 int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg);
+/* Drop the loaded images, the whitening curve and the ring weights; the configuration and the transformed
+ * reference stay.  For a resident engine serving several front-end invocations against one reference. */
+int cspb_refine_reset_images(cspb_ctx *ctx);
 
 /* Optional per-ring SSNR weights (prompt 5/6, statistics_rNN.txt part_SSNR column mapped to
  * rings of the box); n_rings = box/2+1.  NULL resets to all-ones. */

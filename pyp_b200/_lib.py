@@ -106,6 +106,7 @@ _SIGNATURES = {
     "cspb_profile_get_loads": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "cspb_refine_cfg_default": (_i, [C.POINTER(RefineCfg), _i, _f]),
     "cspb_refine_configure": (_i, [_vp, C.POINTER(RefineCfg)]),
+    "cspb_refine_reset_images": (_i, [_vp]),
     "cspb_refine_set_ring_weights": (_i, [_vp, _vp, _i]),
     "cspb_refine_phase_sum": (_i, [_vp, _vp, _i, _vp]),
     "cspb_refine_set_focus_mask": (_i, [_vp, C.c_float, C.c_float, C.c_float, C.c_float]),

@@ -118,8 +118,10 @@ def entity_rows(rows, particles, tilts, mode, first, last):
     return np.nonzero(sel)[0]
 
 
-def run_extract(par, mode, first, last, images, stack, config, out):
-    from ..engine import Engine
+def run_extract(par, mode, first, last, images, stack, config, out, session=None):
+    from .session import Session
+
+    session = session or Session()
 
     rows_all = cistem.read_parameters(par)
     idx = entity_rows(rows_all, None, None, -2, first, last)
@@ -133,16 +135,18 @@ def run_extract(par, mode, first, last, images, stack, config, out):
         out.write(f"csp: no projections for particles {first}..{last}; nothing extracted\n")
         return
     _, series = mrc.read(images)
-    eng = Engine(pick_device(first + 1, max(1, last - first + 1)))
+    eng = session.engine(first + 1, max(1, last - first + 1))
     got = eng.csp_extract(np.ascontiguousarray(series, dtype=np.float32), rows, box * binning, binning)
-    eng.close()
+    session.release()
     os.makedirs(os.path.dirname(stack) or ".", exist_ok=True)
     mrc.write(stack, got, pixel_size=float(rows["pixel_size"][0]))
     out.write(f"Extracted {rows.size} projections of particles {first}..{last} into {stack} ({box} px, bin {binning})\n")
 
 
-def run_refine(par, ext, mode, first, last, stack, config, out):
-    from ..engine import Engine
+def run_refine(par, ext, mode, first, last, stack, config, out, session=None):
+    from .session import Session
+
+    session = session or Session()
 
     t0 = time.time()
     rows_all = cistem.read_parameters(par)
@@ -162,22 +166,17 @@ def run_refine(par, ext, mode, first, last, stack, config, out):
     box = hdr["nx"]
     pixel = float(rows["pixel_size"][0])
     ref_path = reference_path(config)
-    _, vol = mrc.read(ref_path)
-    if vol.shape != (box, box, box):
-        raise ValueError(f"reference {ref_path} {vol.shape} does not match the {box}-pixel stack")
-    eng = Engine(pick_device(first + 1, max(1, last - first + 1)))
-    eng.refine_configure(refine_cfg_from(config, box, pixel))
-    eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+    eng = session.engine(first + 1, max(1, last - first + 1))
+    eng.ensure_reference(refine_cfg_from(config, box, pixel), ref_path, lambda: mrc.read(ref_path)[1])
     pos = rows["position_in_stack"].astype(np.int64)
     if pos.min() < 1 or pos.max() > hdr["nz"]:
         raise ValueError(f"POSITION_IN_STACK {pos.min()}..{pos.max()} outside the stack (1..{hdr['nz']})")
-    _, data = mrc.read(stack, first=int(pos.min()), last=int(pos.max()))
     chunk = 16384
     for s in range(0, rows.size, chunk):
-        eng.load_images(np.ascontiguousarray(data[pos[s:s + chunk] - pos.min()]), append=s > 0)
+        eng.load_images(session.images(stack, pos[s:s + chunk]), append=s > 0)
     ccfg = csp_cfg_from(config, mode)
     new_rows, new_p, new_t, n_evals = eng.csp_run(rows, particles, tilts, ccfg, first, last)
-    eng.close()
+    session.release()
     cistem.write_parameters(out_par, new_rows)
     if mode in (1, 2, 5):
         sel = (particles["pind"] >= first) & ((particles["pind"] <= last) if last >= 0 else True)

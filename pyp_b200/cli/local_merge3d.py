@@ -14,7 +14,9 @@ def parse(ans: Answers):
 
 def sum_dumps(eng, paths1, paths2):
     """Load the dump pairs into a fresh accumulator pair; returns (meta, total inserted)."""
-    from ..engine import Engine
+    from .session import Session
+
+    session = session or Session()
 
     meta = None
     total = 0
@@ -34,18 +36,19 @@ def sum_dumps(eng, paths1, paths2):
     return meta, total
 
 
-def run(p, out=sys.stdout):
+def run(p, out=sys.stdout, session=None):
     from ..engine import Engine
 
     if p["count"] < 1:
         raise ValueError("need at least one dump file")
-    eng = Engine(pick_device())
+    eng = session.engine()
     meta, total = sum_dumps(eng, dump.seed_paths(p["seed1"], p["count"]), dump.seed_paths(p["seed2"], p["count"]))
     for h, path in ((0, p["out1"]), (1, p["out2"])):
         dump.write(path, eng.recon_get_dump(h), meta["box"], meta["pad"], h, meta["pixel_size"], total)
     out.write(banner("LocalMerge3D"))
     out.write(f"\nMerged {p['count']} dump pairs ({total} particles)\n\nLocalMerge3D: Normal termination\n")
-    eng.close()
+    eng.recon_end()
+    session.release()
 
 
 def main(argv=None):

@@ -19,13 +19,15 @@ def parse(ans: Answers):
             "seed2": ans.text("input dump seed 2"), "count": ans.integer("number of dump files")}
 
 
-def run(p, out=sys.stdout):
-    from ..engine import Engine
+def run(p, out=sys.stdout, session=None):
+    from .session import Session
+
+    session = session or Session()
 
     if p["count"] < 1:
         raise ValueError("need at least one dump file")
     t = [time.perf_counter()]
-    eng = Engine(pick_device())
+    eng = session.engine()
     t.append(time.perf_counter())
     meta, total = sum_dumps(eng, dump.seed_paths(p["seed1"], p["count"]), dump.seed_paths(p["seed2"], p["count"]))
     t.append(time.perf_counter())
@@ -41,7 +43,8 @@ def run(p, out=sys.stdout):
     out.write(f"\nMerged {p['count']} dump pairs, {total} particles, box {meta['box']}, pixel {meta['pixel_size']}\n")
     out.write(f"timing: context {t[1] - t[0]:.2f} s, read + sum dumps {t[2] - t[1]:.2f} s, finalise {t[3] - t[2]:.2f} s, write maps {t[4] - t[3]:.2f} s\n\n")
     out.write(statistics.merge3d_log(st))
-    eng.close()
+    eng.recon_end()
+    session.release()
     return st
 
 

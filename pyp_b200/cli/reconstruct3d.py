@@ -96,9 +96,11 @@ def dose_weights(p, rows):
     return np.clip(out, 0.0, 1.0).astype(np.float32)
 
 
-def run(p, out=sys.stdout):
+def run(p, out=sys.stdout, session=None):
     from ..engine import Engine
+    from .session import Session
 
+    session = session or Session()
     t0 = time.time()
     hdr = mrc.read_header(p["stack"])
     box = hdr["nx"]
@@ -111,7 +113,7 @@ def run(p, out=sys.stdout):
     dw = dose_weights(p, rows)
     if dw is not None:
         rows["occupancy"] = rows["occupancy"] * dw if p.get("dose_multiply", True) else np.where(dw > 0, rows["occupancy"], 0)
-    eng = Engine(pick_device(first, last - first + 1))
+    eng = session.engine(first, last - first + 1)
     cfg = Engine.recon_defaults(box, p["pixel_size"])
     cfg.pad = 2 if p["padding"] >= 1.5 else 1
     cfg.mask_radius = p["outer_mask_radius"]
@@ -130,24 +132,19 @@ def run(p, out=sys.stdout):
         # answer 34: the fan of in-plane rotations is scored against the input reconstruction (answer 4)
         from .. import blur
 
-        _, vol = mrc.read(p["reference"])
-        if vol.shape != (box, box, box):
-            raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
         rcfg = Engine.refine_defaults(box, p["pixel_size"])
         rcfg.pad = cfg.pad
         rcfg.mask_radius = p["outer_mask_radius"]
         rcfg.high_res_limit = p["resolution_limit"] if p["resolution_limit"] > 0 else 2.0 * p["pixel_size"]
         rcfg.normalize, rcfg.invert_contrast = int(p["normalize"]), int(p["invert"])
-        eng.refine_configure(rcfg)
-        eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+        eng.ensure_reference(rcfg, p["reference"], lambda: mrc.read(p["reference"])[1])
         n_band = eng.band_counts()[0]
     if rows.size:
         pos = rows["position_in_stack"].astype(np.int64)
-        _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max()))
         chunk = 8192
         for s in range(0, rows.size, chunk):
             e = min(rows.size, s + chunk)
-            imgs = np.ascontiguousarray(data[pos[s:e] - pos.min()])
+            imgs = session.images(p["stack"], pos[s:e])
             if n_band:
                 blur.insert_blurred(eng, imgs, rows[s:e], n_band)
             else:
@@ -173,7 +170,8 @@ def run(p, out=sys.stdout):
                   f"{blur.LBLUR_STEP:.0f} deg, LogP range {blur.LBLUR_RANGE:.0f}\n")
     write_notes(out, "reconstruct3d", ignored_answers(p))
     out.write("\nReconstruct3D: Normal termination\n")
-    eng.close()
+    eng.recon_end()
+    session.release()
 
 
 def main(argv=None):

@@ -125,9 +125,10 @@ def build_cfg(p, box):
     return cfg
 
 
-def run(p, out=sys.stdout):
-    from ..engine import Engine
+def run(p, out=sys.stdout, session=None):
+    from .session import Session
 
+    session = session or Session()
     t0 = time.time()
     hdr = mrc.read_header(p["stack"])
     box = hdr["nx"]
@@ -139,34 +140,27 @@ def run(p, out=sys.stdout):
     rows_all = cistem.read_parameters(p["parameters"])
     sel = select_rows(rows_all, first, last)
     rows = rows_all[sel]
-    _, vol = mrc.read(p["reference"])
-    if vol.shape != (box, box, box):
-        raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
-    eng = Engine(pick_device(first, last - first + 1))
+    eng = session.engine(first, last - first + 1)
     cfg = build_cfg(p, box)
     if p["use_priors"]:
         cfg.use_priors = 1
         cfg.prior_mean_x, cfg.prior_mean_y, cfg.prior_var_x, cfg.prior_var_y = shift_prior(p, rows_all)
-    eng.refine_configure(cfg)
+    reused = eng.ensure_reference(cfg, p["reference"], lambda: mrc.read(p["reference"])[1])
     if p["use_statistics"] and os.path.exists(p["statistics"]) and os.path.getsize(p["statistics"]) > 0:
         st = statistics.read_statistics(p["statistics"])
         if st.size:
             eng.set_ring_weights(statistics.ring_weights_from_statistics(st, box, p["pixel_size"]))
     focus = p["apply_2d_masking"] and p["mask_2d"][3] > 0
-    if focus:
-        eng.set_focus_mask(*p["mask_2d"])
+    eng.set_focus_mask(*(p["mask_2d"] if focus else (0, 0, 0, 0)))
     eng.set_symmetry(p["symmetry"])
     if p["global_search"]:
         from ..search_grid import search_grid
 
         eng.set_search_grid(search_grid(p["angular_step"], p["symmetry"]))
-    eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
     pos = rows["position_in_stack"].astype(np.int64)
-    _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max())) if rows.size else (None, np.zeros((0, box, box), np.float32))
-    images = np.ascontiguousarray(data[pos - pos.min()]) if rows.size else data
     chunk = 16384
     for s in range(0, rows.size, chunk):
-        eng.load_images(images[s:s + chunk], append=s > 0)
+        eng.load_images(session.images(p["stack"], pos[s:s + chunk]), append=s > 0)
     refined, changes, n_evals = eng.refine(rows, want_changes=True) if rows.size else (rows, rows.copy(), 0)
     if rows.size:  # no zero-row files: the reference's reader rejects an empty payload (cistem_star_file.py:694-776)
         cistem.write_parameters(p["out_parameters"], refined)
@@ -182,9 +176,11 @@ def run(p, out=sys.stdout):
                   f"variance ({cfg.prior_var_x:.3f}, {cfg.prior_var_y:.3f}) A^2\n")
     if focus:
         out.write("LogP evaluated inside the 2-D focus mask: centre ({:.1f}, {:.1f}, {:.1f}) A, radius {:.1f} A\n".format(*p["mask_2d"]))
+    if reused:
+        out.write("Reference transform reused from the resident engine\n")
     write_notes(out, "refine3d", ignored_answers(p))
     out.write("\nRefine3D: Normal termination\n")
-    eng.close()
+    session.release()
     return refined
 
 

@@ -51,8 +51,11 @@ def parse(ans: Answers):
     return p
 
 
-def run(p, out=sys.stdout):
+def run(p, out=sys.stdout, session=None):
     from ..engine import Engine
+    from .session import Session
+
+    session = session or Session()
 
     t0 = time.time()
     hdr = mrc.read_header(p["stack"])
@@ -62,13 +65,10 @@ def run(p, out=sys.stdout):
         raise ValueError(f"particle range {first}..{last} outside the stack (1..{hdr['nz']})")
     rows_all = cistem.read_parameters(p["parameters"])
     rows = rows_all[select_rows(rows_all, first, last)]
-    _, vol = mrc.read(p["reference"])
-    if vol.shape != (box, box, box):
-        raise ValueError(f"reference {vol.shape} does not match the {box}-pixel stack")
     refined, n_evals = rows.copy(), 0
     tilt = None
     if (p["refine_defocus"] or p["beam_tilt"]) and rows.size:
-        eng = Engine(pick_device(first, last - first + 1))
+        eng = session.engine(first, last - first + 1)
         cfg = Engine.refine_defaults(box, p["pixel_size"])
         cfg.pad = 2 if p["padding"] >= 1.5 else 1
         cfg.mask_radius = p["outer_mask_radius"]
@@ -78,12 +78,10 @@ def run(p, out=sys.stdout):
         cfg.refine_psi = cfg.refine_theta = cfg.refine_phi = cfg.refine_x = cfg.refine_y = 0
         cfg.refine_defocus = int(p["refine_defocus"])
         cfg.normalize, cfg.invert_contrast = int(p["normalize"]), int(p["invert"])
-        eng.refine_configure(cfg)
-        eng.set_reference(np.ascontiguousarray(vol, dtype=np.float32))
+        eng.ensure_reference(cfg, p["reference"], lambda: mrc.read(p["reference"])[1])
         pos = rows["position_in_stack"].astype(np.int64)
-        _, data = mrc.read(p["stack"], first=int(pos.min()), last=int(pos.max()))
         for s in range(0, rows.size, 16384):
-            eng.load_images(np.ascontiguousarray(data[pos[s:s + 16384] - pos.min()]), append=s > 0)
+            eng.load_images(session.images(p["stack"], pos[s:s + 16384]), append=s > 0)
         if p["refine_defocus"]:
             refined, _, n_evals = eng.refine(rows)
             # keep the search inside +- defocus_range of the input (answer 19)
@@ -98,7 +96,7 @@ def run(p, out=sys.stdout):
             tilt = beamtilt.fit(S, p["pixel_size"], float(rows["voltage_kv"][0]), float(rows["cs_mm"][0]))
             refined["beam_tilt_x"], refined["beam_tilt_y"] = tilt["beam_tilt_x"], tilt["beam_tilt_y"]
             refined["image_shift_x"], refined["image_shift_y"] = tilt["shift_x"], tilt["shift_y"]
-        eng.close()
+        session.release()
     changes = refined.copy()
     for k in ("defocus_1", "defocus_2", "score", "logp", "sigma", "beam_tilt_x", "beam_tilt_y", "image_shift_x", "image_shift_y"):
         changes[k] = refined[k] - rows[k]

@@ -818,6 +818,18 @@ extern "C" int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg) 
     return 0;
 }
 
+// Forget the loaded images, the whitening curve and the ring weights but keep the band plan and the
+// transformed reference: what a resident engine does between two front-end calls that share a reference
+// (a fresh process would re-estimate the whitening curve from its own images — so must the next call).
+extern "C" int cspb_refine_reset_images(cspb_ctx *ctx) {
+    if (!ctx) return CSPB_E_ARG;
+    if (!ctx->refine_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_refine_configure first");
+    ctx->n_images = 0;
+    ctx->have_noise = false;
+    ctx->have_ring_w = false;
+    return 0;
+}
+
 // units (warps) of the scoring kernel that are resident at once = one full wave over the GPU
 extern "C" int cspb_wave_units(cspb_ctx *ctx) {
     if (!ctx) return CSPB_E_ARG;

@@ -121,9 +121,36 @@ class Engine:
         return cfg
 
     def refine_configure(self, cfg: RefineCfg):
+        self._ref_key = None
         self._ck(self._l.cspb_refine_configure(self._h, C.byref(cfg)))
         self.box = cfg.box
         self.rcfg = cfg
+
+    def refine_reset_images(self):
+        """Forget images, whitening curve and ring weights; keep the configuration and the reference."""
+        self._ck(self._l.cspb_refine_reset_images(self._h))
+
+    def ensure_reference(self, cfg: RefineCfg, ref_path, loader):
+        """Configure + set the reference unless the context already holds exactly this configuration and this
+        reference file (same path, size and mtime): a resident engine then skips the 3-D FFT of the map and only
+        forgets the previous call's images.  `loader()` returns the (n, n, n) float32 volume.  Returns True when
+        the cached reference was reused."""
+        import os
+
+        st = os.stat(ref_path)
+        key = (bytes(cfg), os.path.abspath(ref_path), st.st_size, st.st_mtime_ns)
+        if getattr(self, "_ref_key", None) == key:
+            self.refine_reset_images()
+            self.rcfg = cfg
+            return True
+        self._ref_key = None
+        self.refine_configure(cfg)
+        vol = np.ascontiguousarray(loader(), dtype=np.float32)
+        if vol.shape != (cfg.box,) * 3:
+            raise ValueError(f"reference {ref_path} {vol.shape} does not match the {cfg.box}-pixel stack")
+        self.set_reference(vol)
+        self._ref_key = key
+        return False
 
     def band_counts(self):
         a, b = C.c_int(), C.c_int()
@@ -296,9 +323,18 @@ class Engine:
             images = np.ascontiguousarray(images, dtype=np.float32)
             rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
             self._ck(self._l.cspb_recon_insert(self._h, ptr(images), ptr(rows), int(images.shape[0]), HOST))
-        else:  # torch CUDA tensors; rows = device pointer (int) or uint8 tensor of packed rows
+        else:  # torch CUDA tensors; rows = device pointer (int), uint8 tensor of packed rows, or a host table (uploaded here)
+            keep = None
+            if isinstance(rows, np.ndarray):
+                import torch
+
+                keep = torch.from_numpy(np.ascontiguousarray(rows, dtype=ROW_DTYPE).view(np.uint8).reshape(-1, 128)).to(images.device)
+                torch.cuda.current_stream(images.device).synchronize()  # the engine runs on its own stream
+                rows = keep
             rp = rows if isinstance(rows, int) else rows.data_ptr()
             self._ck(self._l.cspb_recon_insert(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(rp), int(images.shape[0]), DEVICE))
+            if keep is not None:
+                self.sync()
 
     def recon_dims(self):
         npad, nf = C.c_int(), C.c_int64()

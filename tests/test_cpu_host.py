@@ -394,8 +394,11 @@ class _FakeEngine:
             if name == "recon_get_dump":
                 n = self.box * self.pad
                 return np.zeros((n, n, n // 2 + 1, 4), dtype=np.float32)
-            if name == "refine_configure":
+            if name in ("refine_configure", "ensure_reference"):
                 self.box = a[0].box
+                if name == "ensure_reference":
+                    a[2]()  # the front-end's loader reads the reference map
+                    return False
             if name == "recon_begin":
                 self.box, self.pad = a[0].box, a[0].pad
             return None
@@ -439,7 +442,7 @@ def test_front_end_branches_run_without_a_gpu(tmp_path, monkeypatch):
     refine3d.run(p, out=log)
     names = [c[0] for c in _FakeEngine.calls]
     assert names.count("set_focus_mask") == 1 and "set_search_grid" in names and "refine" in names and names[-1] == "close"
-    cfg = next(c for c in _FakeEngine.calls if c[0] == "refine_configure")[1][0]
+    cfg = next(c for c in _FakeEngine.calls if c[0] == "ensure_reference")[1][0]
     st = tables.parameter_statistics(rows)
     assert cfg.use_priors == 1 and np.isclose(cfg.prior_mean_x, st["x_shift"][0]) and np.isclose(cfg.prior_var_y, st["y_shift"][1])
     assert (cfg.refine_psi, cfg.refine_theta, cfg.refine_phi, cfg.refine_x, cfg.refine_y) == (1, 0, 0, 1, 0) and cfg.global_search == 1
@@ -458,7 +461,7 @@ def test_front_end_branches_run_without_a_gpu(tmp_path, monkeypatch):
     log = io.StringIO()
     reconstruct3d.run(p, out=log)
     names = [c[0] for c in _FakeEngine.calls]
-    assert names.count("recon_insert") == 21 and names.count("score_poses") == 1 and "set_reference" in names   # the fan
+    assert names.count("recon_insert") == 21 and names.count("score_poses") == 1 and "ensure_reference" in names   # the fan
     ins = [c for c in _FakeEngine.calls if c[0] == "recon_insert"]
     total_occ = sum(c[1][1]["occupancy"].astype(np.float64) for c in ins)
     dw = reconstruct3d.dose_weights(p, rows)
