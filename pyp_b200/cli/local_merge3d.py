@@ -14,9 +14,7 @@ def parse(ans: Answers):
 
 def sum_dumps(eng, paths1, paths2):
     """Load the dump pairs into a fresh accumulator pair; returns (meta, total inserted)."""
-    from .session import Session
-
-    session = session or Session()
+    from ..engine import Engine
 
     meta = None
     total = 0
@@ -37,7 +35,9 @@ def sum_dumps(eng, paths1, paths2):
 
 
 def run(p, out=sys.stdout, session=None):
-    from ..engine import Engine
+    from .session import Session
+
+    session = session or Session()
 
     if p["count"] < 1:
         raise ValueError("need at least one dump file")

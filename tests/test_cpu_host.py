@@ -394,6 +394,11 @@ class _FakeEngine:
             if name == "recon_get_dump":
                 n = self.box * self.pad
                 return np.zeros((n, n, n // 2 + 1, 4), dtype=np.float32)
+            if name == "recon_finalize":
+                n = self.box
+                st = np.zeros((n // 2 + 1, 7), dtype=np.float32)
+                st[:, 0] = np.arange(n // 2 + 1)
+                return np.zeros((n, n, n), np.float32), np.zeros((n, n, n), np.float32), np.zeros((n, n, n), np.float32), st
             if name in ("refine_configure", "ensure_reference"):
                 self.box = a[0].box
                 if name == "ensure_reference":
@@ -467,6 +472,16 @@ def test_front_end_branches_run_without_a_gpu(tmp_path, monkeypatch):
     dw = reconstruct3d.dose_weights(p, rows)
     assert np.allclose(total_occ, rows["occupancy"] * dw, rtol=1e-5)          # flat scores: uniform fan, weights sum to 1
     assert "Likelihood blurring" in log.getvalue() and os.path.exists("T20S_r01_map1_n1.mrc")
+    # ---- local_merge3d and merge3d over that dump pair (host-side paths of both front-ends)
+    _FakeEngine.calls = []
+    log = io.StringIO()
+    local_merge3d.run(local_merge3d.parse(prompts.Answers("sum1.mrc\nsum2.mrc\nT20S_r01_map1_n.mrc\nT20S_r01_map2_n.mrc\n1\n", "local_merge3d")), out=log)
+    assert os.path.exists("sum1.mrc") and "LocalMerge3D: Normal termination" in log.getvalue()
+    log = io.StringIO()
+    merge3d.run(merge3d.parse(prompts.Answers("h1.mrc\nh2.mrc\nm.mrc\nst.txt\n700.0\n0\n86.4\nT20S_r01_map1_n.mrc\nT20S_r01_map2_n.mrc\n1\n", "merge3d")), out=log)
+    names = [c[0] for c in _FakeEngine.calls]
+    assert names.count("recon_add_dump") == 4 and "recon_finalize" in names and names[-1] == "close"
+    assert os.path.exists("m.mrc") and os.path.exists("st.txt") and "Merge3D: Normal termination" in log.getvalue()
 
 
 def test_tier_a_probe_and_answer_builders_match_the_reference_heredocs(tmp_path, monkeypatch):

@@ -19,7 +19,10 @@ BIN = os.path.join(ROOT, "bin")
 
 def sh(prog, answers, cwd, log):
     cmd = f"{BIN}/{prog} << eot >> {log} 2>&1\n" + "\n".join(str(a) for a in answers) + "\neot\n"
-    return subprocess.run(cmd, shell=True, cwd=cwd, timeout=600).returncode
+    rc = subprocess.run(cmd, shell=True, cwd=cwd, timeout=600).returncode
+    if rc != 0:
+        print(open(os.path.join(cwd, log), errors="replace").read()[-2000:])  # shown by pytest on failure
+    return rc
 
 
 def test_refine_reconstruct_merge_chain(tmp_path):

@@ -12,7 +12,7 @@ if has facts; then
     lscpu | head -25; nvidia-smi topo -m; numactl -H 2>/dev/null | head; } > $OUT/facts.txt 2>&1
 fi
 if has tests; then
-  ( time timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 ) > $OUT/pytest_gpu.log 2>&1
+  ( time timeout 1500 python -m pytest tests -m gpu -q --durations=15 ) > $OUT/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> $OUT/pytest_gpu.log
 fi
 if has smoke; then timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; fi
