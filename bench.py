@@ -63,11 +63,13 @@ def parse_args(argv=None):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-size (strong scaling) leg of C2")
+    ap.add_argument("--optimizer", default="analytic", choices=["analytic", "stencil"],
+                    help="local optimiser: analytic gradient + Gauss-Newton (default, SEMANTICS.md 7c) or the central-difference stencil (7)")
     return ap.parse_args(argv)
 
 
 # ------------------------------------------------------------------------------ workload definition (both arms)
-def refine_params(c):
+def refine_params(c, optimizer="analytic"):
     """refine3d configuration of the workload as a plain dict (no library involved): the defaults of
     cspb_refine_cfg_default (tests/test_cpu_host.py checks they agree) with the benchmark's band."""
     box, px = c["box"], c["pixel"]
@@ -77,7 +79,7 @@ def refine_params(c):
              search_range_x=0.125 * box * px, search_range_y=0.125 * box * px, defocus_range=500.0, defocus_step=50.0,
              global_search=0, local_refine=1, refine_psi=1, refine_theta=1, refine_phi=1, refine_x=1, refine_y=1, refine_defocus=0,
              apply_mask=1, normalize=1, invert_contrast=0, whiten=1, symmetry_order=1, local_iterations=8,
-             use_priors=0, prior_mean_x=0.0, prior_mean_y=0.0, prior_var_x=0.0, prior_var_y=0.0)
+             use_priors=0, prior_mean_x=0.0, prior_mean_y=0.0, prior_var_x=0.0, prior_var_y=0.0, optimizer=1 if optimizer == "stencil" else 0)
     if c.get("global_search"):  # a compact particle searched to 30 A: refine_dang's default 20 degree grid is ~2x the angular resolution of the search band
         p.update(global_search=1, search_high_res=30.0, search_range_x=20.0, search_range_y=20.0)
     return p
@@ -124,7 +126,8 @@ def workload_config(a, P):
            "l2_policy": f"inputs larger than L2 ({P * c.get('tilts', 1) * c['box'] ** 2 * 4 / 1e9:.2f} GB stack per GPU per step, read once)"}
     if c["kind"] == "spa":
         cfg["search"] = ("global: 20 deg grid + FFT shift search, top-20 hits refined locally (8 iterations)" if c.get("global_search")
-                         else "local: 8 iterations of stencil + Newton + 3-point line search (114 evaluations per particle)")
+                         else ("local: 8 iterations of the central-difference stencil optimiser (114 evaluations per particle)" if getattr(a, "optimizer", "analytic") == "stencil"
+                               else "local: 8 coarse-to-fine iterations of the analytic-gradient optimiser (one gradient + one trial evaluation each, 18 evaluations per particle)"))
     elif c["kind"] == "tomo":
         cfg["search"] = f"csp mode 5 (particle angles + shifts), {c['tilts']} tilts per particle, exposure window 0..20, 5 optimiser iterations"
     else:
@@ -245,7 +248,7 @@ class CpuArm:
         self.kind, self.sample, self.cores = kind, sample, cores
         ph = synth.Phantom(box, n_blobs=40, seed=seed, sigma=4.0 if c.get("global_search") else 2.0, radius_frac=0.15 if c.get("global_search") else 0.35)
         vol = ph.volume()
-        rd = refine_params(c) if kind != "recon" else None
+        rd = refine_params(c, a.optimizer) if kind != "recon" else None
         cd = recon_params(c) if kind != "tomo" else None
         mats = symmetry_matrices(c["sym"])
         extra_all = {}
@@ -403,10 +406,11 @@ def _run_tier_a(a, probe, cores, reps):
             r = tier_a.run_iteration(probe["binaries"], d, ph.volume(), stack, start, px, c["sym"], mw=440.0, cores=cores)
             secs.append(r["refine_s"] + r["reconstruct_s"] + r["merge_s"])
     s = float(np.mean(secs))
-    # a closed binary does not report its evaluation count: quote its particles/s at our optimiser's 114 evaluations per particle
-    return {"value": 114.0 * sample / s, "seconds": s, "particles_per_s": sample / s,
+    # a closed binary does not report its evaluation count: quote its particles/s at our optimiser's evaluations per particle
+    epp = 114.0 if a.optimizer == "stencil" else 18.0
+    return {"value": epp * sample / s, "seconds": s, "particles_per_s": sample / s,
             "sample": f"{sample} particles through {sorted(probe['binaries'])} as pyp runs them ({cores} concurrent single-thread ranges), wall clock; "
-                      f"scored projections/s = particles/s x 114 (the evaluation count of our optimiser; the binary reports none)"}
+                      f"scored projections/s = particles/s x {epp:.0f} (the evaluation count of our optimiser; the binary reports none)"}
 
 
 # ------------------------------------------------------------------------------ B200 arm
@@ -436,7 +440,7 @@ def run_b200_arm(a):
     P = a.particles or c["per_gpu"]          # particles per GPU (tomo: particles, each with `tilts` projections)
     n_tilt = c.get("tilts", 1) if kind == "tomo" else 1
     eng = Engine(local_rank)
-    rcfg = fill(Engine.refine_defaults(n, px), refine_params(c)) if kind != "recon" else None
+    rcfg = fill(Engine.refine_defaults(n, px), refine_params(c, a.optimizer)) if kind != "recon" else None
     ccfg = fill(Engine.recon_defaults(n, px), recon_params(c)) if kind != "tomo" else None
     n_band = n_slots = 0
     if rcfg is not None:
@@ -605,6 +609,29 @@ def run_b200_arm(a):
         eng.count_loads(False)
         loads_per_eval = q / max(1, ev_c)
 
+    # ---- the two local optimisers on the same resident stack (untimed for `value`): final mean score, evaluations and
+    # refinement time of each — the algorithmic gain of the analytic optimiser at a matched final score
+    opt_cmp = None
+    if kind == "spa" and not glob and rank == 0:
+        opt_cmp = {}
+        for name, code in (("analytic", 0), ("stencil", 1)):
+            cfg2 = fill(Engine.refine_defaults(n, px), refine_params(c, name))
+            eng.refine_configure(cfg2)
+            eng.set_reference(vol)
+            eng.load_images(stack)
+            rows_dev_all[:n_proj].copy_(rows_init_all[:n_proj])
+            torch.cuda.synchronize()
+            t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_a.record(ext)
+            n_ev = eng.refine_device(rows_dev_all.data_ptr(), n_proj)
+            t_b.record(ext)
+            eng.sync()
+            out_rows = rows_dev_all[:n_proj].cpu().numpy().view(ROW_DTYPE).reshape(-1)
+            opt_cmp[name] = {"mean_final_score": float(out_rows["score"].mean()), "evals_per_particle": n_ev / n_proj,
+                             "refine_ms": t_a.elapsed_time(t_b), "particles_per_s_refine_only": n_proj / (t_a.elapsed_time(t_b) * 1e-3)}
+        eng.refine_configure(rcfg)
+        eng.set_reference(vol)
+
     # ---- strong-scaling leg: the config's fixed 100 000-particle job over `world` ranks
     strong_line = None
     if strong:
@@ -749,6 +776,8 @@ def run_b200_arm(a):
         line["roofline_insert"] = ins_roof
     if strong_line:
         line["strong_scaling"] = strong_line
+    if opt_cmp:
+        line["optimizers"] = opt_cmp
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not a.no_cpu_baseline:

@@ -128,7 +128,10 @@ typedef struct cspb_refine_cfg {
     int32_t use_priors;        /* prompt 7: restrain X/Y shifts to the data set's distribution     */
     float prior_mean_x, prior_mean_y; /* Angstrom: row 0 of <name>_stat.cistem (particle_cspt.py:1009-1016) */
     float prior_var_x, prior_var_y;   /* Angstrom^2: row 1; <= 0 leaves that shift unrestrained     */
-    int32_t reserved[2];
+    int32_t optimizer;         /* local optimiser (ours): 0 = analytic gradient + Gauss-Newton step, coarse to fine (SEMANTICS.md
+                                  §7c; plain local refinement of the pose), 1 = central-difference stencil (§7; always used for
+                                  the defocus refinement and for the hits of a global search) */
+    int32_t reserved[1];
 } cspb_refine_cfg;
 
 /* Fill a config with the defaults pyp passes for a plain local refinement. */
@@ -181,6 +184,11 @@ int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, float *scores_
 int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int n_rows,
                             const int32_t *image_index, const float *poses6, int n_evals,
                             float *scores_out);
+/* Value and analytic derivatives of the score at the poses of `rows` (the evaluation the default local optimiser is
+ * built on, oracle/SEMANTICS.md §7c): out28 = 28 floats per row {num, X, A, B, d num / d (psi, theta, phi per degree,
+ * x, y per Angstrom), d B / d angles, the 15 entries of the upper triangle of J^T J, 0}.  ring_cut > 0 restricts the
+ * sums to the rings <= ring_cut (coarse-to-fine stages); 0 = the whole band. */
+int cspb_refine_score_grad(cspb_ctx *ctx, const cspb_row *rows, int n, int ring_cut, float *out28);
 
 /* Orientation grid of the global search (prompt 36/25): n_orient x {psi, theta, phi} degrees.
  * The host builds it from the angular step and the symmetry symbol (pyp_b200/search_grid.py),

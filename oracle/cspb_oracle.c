@@ -395,7 +395,13 @@ void orc_prepare_image(const float *img, const orc_refine_cfg *cfg, const float 
 }
 
 /* ================================================================ score */
+/* `ring_cut`: only the rings floor(r) <= ring_cut enter the sums (coarse-to-fine stages of §7c); INT_MAX = the whole band */
+static float score_cut(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg, float *out4, int ring_cut);
 float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg, float *out4) {
+    return score_cut(r, spec, row, pose6, cfg, out4, 0x7fffffff);
+}
+
+static float score_cut(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg, float *out4, int ring_cut) {
     const int n = cfg->box, nh = n / 2 + 1;
     float lo, hi;
     orc_band_limits(cfg, &lo, &hi);
@@ -411,6 +417,7 @@ float orc_score(const orc_ref *r, const float *spec, const orc_row *row, const f
             const float r2 = (float)(i * i + j * j);
             if (r2 < lo * lo || r2 > hi * hi) continue;
             const int bin = (int)sqrtf(r2);
+            if (bin > ring_cut) continue;
             const int jj = j < 0 ? j + n : j;
             const float fr = spec[2 * ((size_t)jj * nh + i)], fim = spec[2 * ((size_t)jj * nh + i) + 1];
             float pr, pi;
@@ -595,6 +602,290 @@ static float refine_one(const orc_ref *r, const float *spec, const orc_row *row,
     return sc;
 }
 
+/* ================================================================ analytic-gradient local refinement (SEMANTICS.md §7c)
+ * One evaluation gives the score AND its derivatives: the eight corners of the trilinear interpolant yield the
+ * value and the spatial gradient of the slice sample, the chain rule through R(psi, theta, phi) gives dP/dangle,
+ * the phase ramp gives d/dshift.  Besides the gradient the evaluation accumulates J^T J (J = dP/dparameters): for data
+ * G = alpha P(p*) + noise the curvature of CC around p* is -(CC / B) J^T J (Gauss-Newton: second derivatives of the
+ * interpolant dropped), which is the Hessian the step uses. */
+#define NG 5
+#define NJ 15 /* upper triangle of the 5x5 J^T J, row major: (0,0) (0,1) ... (0,4) (1,1) ... (4,4) */
+
+static void euler_derivatives(float psi, float theta, float phi, float *dth6) {
+    /* first two columns of dR/dtheta (rows x, y, z), per radian; dR/dpsi and dR/dphi need no table:
+       d(x,y,z)/dpsi = R (-j, i, 0)^T and d(x,y,z)/dphi = (-y, x, 0) */
+    const float d2r = PI_F / 180.f;
+    const float cps = cosf(psi * d2r), sps = sinf(psi * d2r);
+    const float cth = cosf(theta * d2r), sth = sinf(theta * d2r);
+    const float cph = cosf(phi * d2r), sph = sinf(phi * d2r);
+    dth6[0] = -cph * sth * cps; dth6[1] = cph * sth * sps;
+    dth6[2] = -sph * sth * cps; dth6[3] = sph * sth * sps;
+    dth6[4] = -cth * cps;       dth6[5] = cth * sps;
+}
+
+/* trilinear value and spatial gradient at (x >= 0 after the Friedel flip done by the caller) */
+static void ref_interp_grad(const orc_ref *r, float x, float y, float z, float *v /*2*/, float *gx, float *gy, float *gz) {
+    const int x0 = (int)floorf(x), y0 = (int)floorf(y), z0 = (int)floorf(z);
+    const float fx = x - x0, fy = y - y0, fz = z - z0;
+    float c[2][2][2][2];
+    for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) ref_at(r, x0 + dx, y0 + dy, z0 + dz, &c[dz][dy][dx][0], &c[dz][dy][dx][1]);
+    for (int k = 0; k < 2; ++k) {
+        /* along x first (the GPU's order): a = c0 + fx (c1 - c0) */
+        float a[2][2], d[2][2];
+        for (int dz = 0; dz < 2; ++dz)
+            for (int dy = 0; dy < 2; ++dy) {
+                d[dz][dy] = c[dz][dy][1][k] - c[dz][dy][0][k];
+                a[dz][dy] = c[dz][dy][0][k] + fx * d[dz][dy];
+            }
+        const float dx0 = d[0][0] + fy * (d[0][1] - d[0][0]), dx1 = d[1][0] + fy * (d[1][1] - d[1][0]);
+        gx[k] = dx0 + fz * (dx1 - dx0);
+        const float dy0 = a[0][1] - a[0][0], dy1 = a[1][1] - a[1][0];
+        const float v0 = a[0][0] + fy * dy0, v1 = a[1][0] + fy * dy1;
+        gy[k] = dy0 + fz * (dy1 - dy0);
+        gz[k] = v1 - v0;
+        v[k] = v0 + fz * gz[k];
+    }
+}
+
+/* score (x100) with derivatives.  out4 = {num, X, A, B}; dnum[5] = d num / d (psi, theta, phi [deg], x, y [A]) with the
+ * signed / absolute ring rule applied; dB[3] = d B / d angles [deg]; jtj[15] = J^T J in the same units. */
+static float score_grad_cut(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                            float *out4, float *dnum, float *dB, float *jtj, int ring_cut);
+float orc_score_grad_cut(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                         float *out4, float *dnum, float *dB, float *jtj, int ring_cut) {
+    return score_grad_cut(r, spec, row, pose6, cfg, out4, dnum, dB, jtj, ring_cut > 0 ? ring_cut : 0x7fffffff);
+}
+float orc_score_grad(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                     float *out4, float *dnum, float *dB, float *jtj) {
+    return score_grad_cut(r, spec, row, pose6, cfg, out4, dnum, dB, jtj, 0x7fffffff);
+}
+
+static float score_grad_cut(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                            float *out4, float *dnum, float *dB, float *jtj, int ring_cut) {
+    const int n = cfg->box, nh = n / 2 + 1;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    const int nb = 2 * n;
+    float *ring = (float *)calloc((size_t)nb * (1 + NG), sizeof(float)); /* per ring: X and its five derivatives */
+    float suma = 0.f, sumb = 0.f;
+    float m[9], dth[6];
+    orc_euler_matrix(pose6[0], pose6[1], pose6[2], m);
+    euler_derivatives(pose6[0], pose6[1], pose6[2], dth);
+    const ctfc c = ctf_make(row, n);
+    const float k2 = 2.f * PI_F / ((float)n * row->pixel_size);
+    const float d2r = PI_F / 180.f, pad = (float)r->pad;
+    for (int a = 0; a < 3; ++a) dB[a] = 0.f;
+    for (int a = 0; a < NJ; ++a) jtj[a] = 0.f;
+    for (int j = -n / 2; j < n / 2; ++j)
+        for (int i = 0; i <= n / 2; ++i) {
+            const float r2 = (float)(i * i + j * j);
+            if (r2 < lo * lo || r2 > hi * hi) continue;
+            const int bin = (int)sqrtf(r2);
+            if (bin > ring_cut) continue;
+            const int jj = j < 0 ? j + n : j;
+            const float fr = spec[2 * ((size_t)jj * nh + i)], fim = spec[2 * ((size_t)jj * nh + i) + 1];
+            const float fi = (float)i, fj = (float)j;
+            float x = (m[0] * fi + m[1] * fj) * pad, y = (m[3] * fi + m[4] * fj) * pad, z = (m[6] * fi + m[7] * fj) * pad;
+            /* coordinate velocities per radian of psi, theta, phi */
+            float vel[3][3] = {{(m[1] * fi - m[0] * fj) * pad, (m[4] * fi - m[3] * fj) * pad, (m[7] * fi - m[6] * fj) * pad},
+                               {(dth[0] * fi + dth[1] * fj) * pad, (dth[2] * fi + dth[3] * fj) * pad, (dth[4] * fi + dth[5] * fj) * pad},
+                               {-y, x, 0.f}};
+            const float sg = x < 0.f ? -1.f : 1.f; /* Friedel mate for the negative half space */
+            x *= sg; y *= sg; z *= sg;
+            float v[2], gx[2], gy[2], gz[2];
+            ref_interp_grad(r, x, y, z, v, gx, gy, gz);
+            const float ctf = ctf_eval(&c, i, j, 0.f);
+            const float pr = ctf * v[0], pi = ctf * sg * v[1];
+            float dp[NG][2]; /* dP / d parameter; the shift columns are those of the equivalent projection shift */
+            for (int a = 0; a < 3; ++a) {
+                const float dre = gx[0] * vel[a][0] + gy[0] * vel[a][1] + gz[0] * vel[a][2];
+                const float dim = gx[1] * vel[a][0] + gy[1] * vel[a][1] + gz[1] * vel[a][2];
+                dp[a][0] = ctf * sg * dre * d2r; /* coordinates move by sg * vel */
+                dp[a][1] = ctf * dim * d2r;
+            }
+            dp[3][0] = k2 * fi * pi; dp[3][1] = -k2 * fi * pr; /* -i k P: shifting the image by +s = shifting P by -s */
+            dp[4][0] = k2 * fj * pi; dp[4][1] = -k2 * fj * pr;
+            const float ph = (fi * pose6[3] + fj * pose6[4]) * k2;
+            const float cs = cosf(ph), sn = sinf(ph);
+            const float gr = fr * cs - fim * sn, gi = fr * sn + fim * cs;
+            float *rg = ring + (size_t)bin * (1 + NG);
+            rg[0] += gr * pr + gi * pi;
+            for (int a = 0; a < NG; ++a) rg[1 + a] += gr * dp[a][0] + gi * dp[a][1];
+            suma += fr * fr + fim * fim;
+            sumb += pr * pr + pi * pi;
+            for (int a = 0; a < 3; ++a) dB[a] += 2.f * (pr * dp[a][0] + pi * dp[a][1]);
+            int t = 0;
+            for (int a = 0; a < NG; ++a)
+                for (int b = a; b < NG; ++b) jtj[t++] += dp[a][0] * dp[b][0] + dp[a][1] * dp[b][1];
+        }
+    const int limit = cfg->signed_cc_limit > 0.f ? (int)floorf((float)n * cfg->pixel_size / cfg->signed_cc_limit) : 0x7fffffff;
+    float num = 0.f, xs = 0.f;
+    for (int a = 0; a < NG; ++a) dnum[a] = 0.f;
+    for (int b = 0; b < nb; ++b) {
+        const float *rg = ring + (size_t)b * (1 + NG);
+        xs += rg[0];
+        const float s = (b > limit && rg[0] < 0.f) ? -1.f : 1.f;
+        num += s * rg[0];
+        for (int a = 0; a < NG; ++a) dnum[a] += s * rg[1 + a];
+    }
+    free(ring);
+    if (out4) { out4[0] = num; out4[1] = xs; out4[2] = suma; out4[3] = sumb; }
+    const float den = suma * sumb;
+    return den > 0.f ? 100.f * num / sqrtf(den) : 0.f;
+}
+
+/* solve the symmetric positive definite 5x5 system H d = g (Cholesky, fp32); returns 0 if H is not positive definite */
+static int solve_spd5(const float *H /*25*/, const float *g, float *d) {
+    float L[NG][NG];
+    memset(L, 0, sizeof L);
+    for (int i = 0; i < NG; ++i)
+        for (int j = 0; j <= i; ++j) {
+            float s = H[i * NG + j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+            if (i == j) {
+                if (!(s > 0.f)) return 0;
+                L[i][i] = sqrtf(s);
+            } else
+                L[i][j] = s / L[j][j];
+        }
+    float yv[NG];
+    for (int i = 0; i < NG; ++i) {
+        float s = g[i];
+        for (int k = 0; k < i; ++k) s -= L[i][k] * yv[k];
+        yv[i] = s / L[i][i];
+    }
+    for (int i = NG - 1; i >= 0; --i) {
+        float s = yv[i];
+        for (int k = i + 1; k < NG; ++k) s -= L[k][i] * d[k];
+        d[i] = s / L[i][i];
+    }
+    return 1;
+}
+
+/* Levenberg-Marquardt-style step from one gradient evaluation (continuous in its inputs: no accept / reject).
+ * o4, dnum, dB, jtj as returned by orc_score_grad; lam / prior as in prior_pen.  Returns f0 (objective at x); writes the
+ * step d[5] (trust region applied) and *slope = directional derivative of the objective along d. */
+#define LM_DAMP 0.05f
+#define LM_CC_FLOOR 0.01f
+static float lm_step(const float *o4, const float *dnum, const float *dB, const float *jtj, const int *freem, const float *trust,
+                     const orc_refine_cfg *cfg, const orc_row *row, const float *x, float *d, float *slope) {
+    const float A = o4[2], B = o4[3];
+    const float den = A * B;
+    const float rs = den > 0.f ? 1.f / sqrtf(den) : 0.f;
+    const float cc = o4[0] * rs;
+    float g[NG], H[NG * NG];
+    for (int a = 0; a < NG; ++a) g[a] = dnum[a] * rs - (a < 3 && B > 0.f ? 0.5f * cc * dB[a] / B : 0.f);
+    const float cce = cc > LM_CC_FLOOR ? cc : LM_CC_FLOOR;
+    const float hs = B > 0.f ? cce / B : 0.f;
+    int t = 0;
+    for (int a = 0; a < NG; ++a)
+        for (int b = a; b < NG; ++b) { H[a * NG + b] = H[b * NG + a] = hs * jtj[t]; ++t; }
+    float f0 = cc;
+    if (cfg->use_priors) { /* restraint: value, gradient and (exact) curvature */
+        const float rad = cfg->mask_radius / cfg->pixel_size;
+        float nmask = 3.14159265f * rad * rad;
+        if (nmask < 1.f) nmask = 1.f;
+        const float lam = row->sigma * row->sigma / nmask;
+        const float w[2] = {cfg->prior_var_x > 0.f ? 0.5f / cfg->prior_var_x : 0.f, cfg->prior_var_y > 0.f ? 0.5f / cfg->prior_var_y : 0.f};
+        const float dx[2] = {x[3] - cfg->prior_mean_x, x[4] - cfg->prior_mean_y};
+        for (int k = 0; k < 2; ++k) {
+            f0 -= lam * w[k] * dx[k] * dx[k];
+            g[3 + k] -= 2.f * lam * w[k] * dx[k];
+            H[(3 + k) * NG + 3 + k] += 2.f * lam * w[k];
+        }
+    }
+    for (int a = 0; a < NG; ++a) {
+        if (!freem[a]) {
+            for (int b = 0; b < NG; ++b) H[a * NG + b] = H[b * NG + a] = 0.f;
+            H[a * NG + a] = 1.f;
+            g[a] = 0.f;
+        }
+    }
+    for (int a = 0; a < NG; ++a) H[a * NG + a] *= 1.f + LM_DAMP;
+    if (!solve_spd5(H, g, d))
+        for (int a = 0; a < NG; ++a) d[a] = H[a * NG + a] > 0.f ? g[a] / H[a * NG + a] : 0.f;
+    float worst = 1.f; /* trust region: scale the whole step so that no component exceeds its radius */
+    for (int a = 0; a < NG; ++a) {
+        const float q = fabsf(d[a]) / trust[a];
+        if (q > worst) worst = q;
+    }
+    *slope = 0.f;
+    for (int a = 0; a < NG; ++a) {
+        d[a] /= worst;
+        *slope += g[a] * d[a];
+    }
+    return f0;
+}
+
+/* step length from f(0), f'(0) along d and f(1): parabola through the three, maximiser clamped to [0, 2] */
+static float lm_line(float f0, float slope, float f1) {
+    const float c = f1 - f0 - slope;
+    if (c < 0.f) {
+        float t = -slope / (2.f * c);
+        if (t < 0.f) t = 0.f;
+        if (t > 2.f) t = 2.f;
+        return t;
+    }
+    return f1 > f0 ? 2.f : 0.f;
+}
+
+/* resolution stage of iteration `it`: returns f >= 1 and the last ring used (INT_MAX for the full band) */
+static float lm_stage(int it, int iters, float r_lo, float r_hi, int *ring_cut) {
+    const int ramp = iters - 3;
+    float f = 1.f;
+    if (ramp > 0 && it < ramp) f = powf(6.f, 1.f - (float)it / (float)ramp);
+    *ring_cut = 0x7fffffff;
+    if (f > 1.f) {
+        int rc = (int)floorf(r_hi / f);
+        int least = (int)floorf(r_lo) + 4; /* never fewer than a handful of rings, nor below 12 Fourier pixels */
+        if (least < 12) least = 12;
+        if (rc < least) rc = least;
+        if ((float)rc >= r_hi) { f = 1.f; } else { *ring_cut = rc; f = r_hi / (float)rc; }
+    }
+    return f;
+}
+
+/* refine_one with the analytic optimiser: per iteration ONE gradient evaluation and ONE trial evaluation */
+static float refine_one_lm(const orc_ref *r, const float *spec, const orc_row *row, float *x, const int *freem, const orc_refine_cfg *cfg,
+                           float *o4, long long *evals, float *obj_out) {
+    const int n = cfg->box;
+    float lo, hi;
+    orc_band_limits(cfg, &lo, &hi);
+    int n_free = 0;
+    for (int m = 0; m < NG; ++m) n_free += freem[m] ? 1 : 0;
+    const int iters = n_free > 0 ? (cfg->local_iterations > 0 ? cfg->local_iterations : 8) : 0;
+    const float x_start[NP] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+    for (int it = 0; it < iters; ++it) {
+        /* coarse to fine: stage `it` scores the rings up to r_hi / f, f falling geometrically from 6 to 1 over the first
+           iters - 3 stages (frequency marching: a wide basin first, the full band for the last three); the trust region
+           follows the resolution of the stage */
+        int ring_cut;
+        const float f = lm_stage(it, iters, lo, hi, &ring_cut);
+        const float h_ang = 0.35f * 57.29578f * f / hi, h_shift = 0.07f * (float)n * f / hi * cfg->pixel_size;
+        const float trust[NG] = {16.f * h_ang, 16.f * h_ang, 16.f * h_ang, 16.f * h_shift, 16.f * h_shift};
+        float dnum[NG], dB[3], jtj[NJ], d[NG], slope, q[NP];
+        score_grad_cut(r, spec, row, x, cfg, o4, dnum, dB, jtj, ring_cut);
+        const float f0 = lm_step(o4, dnum, dB, jtj, freem, trust, cfg, row, x, d, &slope);
+        memcpy(q, x, sizeof q);
+        for (int m = 0; m < NG; ++m) q[m] = x[m] + d[m];
+        const float f1 = score_cut(r, spec, row, q, cfg, o4, ring_cut) * 0.01f - prior_pen(cfg, row, q);
+        (*evals) += 2;
+        const float t = lm_line(f0, slope, f1);
+        for (int m = 0; m < NG; ++m) x[m] += t * d[m];
+    }
+    float o4s[4];
+    float sc = orc_score(r, spec, row, x, cfg, o4);
+    const float sc_start = orc_score(r, spec, row, x_start, cfg, o4s);
+    (*evals) += 2;
+    float obj = sc * 0.01f - prior_pen(cfg, row, x);
+    const float obj_start = sc_start * 0.01f - prior_pen(cfg, row, x_start);
+    if (obj < obj_start) { memcpy(x, x_start, sizeof x_start); memcpy(o4, o4s, sizeof o4s); sc = sc_start; obj = obj_start; }
+    if (obj_out) *obj_out = obj;
+    return sc;
+}
+
 /* ---- 2-D focus mask (refine3d prompts 29-32, 44; SEMANTICS.md §6b).  The sphere centre c (Angstrom from
  * the corner of the map) is projected with the particle's pose: image axes are the first two columns of
  * the rotation matrix (the slice geometry of orc_score), so the centre lands at n/2 + (col0.c', col1.c'),
@@ -681,7 +972,11 @@ long long orc_refine_local(const orc_ref *r, const float *specs, orc_row *rows, 
         float x[NP] = {row->psi, row->theta, row->phi, row->x_shift, row->y_shift, 0.f};
         float o4[4];
         long long ev = 0;
-        const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, 1.f, NULL);
+        /* optimiser 0 (default): analytic gradient + Gauss-Newton step (SEMANTICS.md §7c) for the five pose parameters;
+           the stencil optimiser of §7 when asked for (optimizer = 1) or when the defocus is refined as well */
+        const int analytic = cfg->optimizer == 0 && !cfg->refine_defocus;
+        const float sc = analytic ? refine_one_lm(r, spec, row, x, freem, cfg, o4, &ev, NULL)
+                                  : refine_one(r, spec, row, x, freem, cfg, o4, &ev, 1.f, NULL);
         evals += ev;
         const orc_row before = *row;
         write_row(row, x, sc, o4, nband, cfg->refine_defocus);

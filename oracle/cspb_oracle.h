@@ -55,6 +55,9 @@ typedef struct orc_refine_cfg {
     /* 2-D focus mask (prompts 29-32 + 44, class_focusmask "x,y,z,radius" in Angstrom from the corner of
      * the map, frealign.py:3845-3848,3883-3885; SEMANTICS.md §6b): LOGP over the projected sphere */
     float focus_x, focus_y, focus_z, focus_radius;
+    /* local optimiser: 0 = analytic gradient + Gauss-Newton step (SEMANTICS.md §7c; used when the defocus is not
+     * refined), 1 = central-difference stencil (§7) */
+    int32_t optimizer;
 } orc_refine_cfg;
 
 typedef struct orc_recon_cfg {
@@ -78,6 +81,12 @@ void orc_euler_matrix(float psi, float theta, float phi, float *r9);
 void orc_ctf_image(const orc_row *row, int n, float *out /* n*(n/2+1) */);
 float orc_band_limits(const orc_refine_cfg *cfg, float *r_lo, float *r_hi); /* returns r_hi; also n_band via orc_band_count */
 int orc_band_count(const orc_refine_cfg *cfg);
+/* score with analytic derivatives: dnum[5] (psi, theta, phi per degree; x, y per Angstrom), dB[3], jtj[15] (upper triangle) */
+float orc_score_grad(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                     float *out4, float *dnum, float *dB, float *jtj);
+/* the same restricted to the rings <= ring_cut (ring_cut <= 0: the whole band) */
+float orc_score_grad_cut(const orc_ref *r, const float *spec, const orc_row *row, const float *pose6, const orc_refine_cfg *cfg,
+                         float *out4, float *dnum, float *dB, float *jtj, int ring_cut);
 
 /* ---- reference */
 orc_ref *orc_ref_create(const float *vol, int n, int pad);

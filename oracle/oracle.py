@@ -43,6 +43,7 @@ class RefineCfg(C.Structure):
         ("use_priors", C.c_int32), ("prior_mean_x", C.c_float), ("prior_mean_y", C.c_float),
         ("prior_var_x", C.c_float), ("prior_var_y", C.c_float),
         ("focus_x", C.c_float), ("focus_y", C.c_float), ("focus_z", C.c_float), ("focus_radius", C.c_float),
+        ("optimizer", C.c_int32),
     ]
 
 
@@ -124,6 +125,8 @@ def lib():
             "orc_noise_curve": (None, [vp, i, C.POINTER(RefineCfg), vp]),
             "orc_prepare_image": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
+            "orc_score_grad": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp, vp, vp, vp]),
+            "orc_score_grad_cut": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp, vp, vp, vp, i]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
             "orc_normalize": (None, [vp, i, f, i, i, vp]),
             "orc_phase_sum": (None, [vp, vp, vp, i, C.POINTER(RefineCfg), vp]),
@@ -237,6 +240,17 @@ def score(ref, spec, row, pose6, cfg):
     o4 = np.zeros(4, dtype=np.float32)
     s = lib().orc_score(ref._h, _p(spec), _p(row), _p(pose), C.byref(cfg), _p(o4))
     return float(s), o4
+
+
+def score_grad(ref, spec, row, pose6, cfg, ring_cut=0):
+    """(score x100, out4, dnum[5], dB[3], jtj[15]) — analytic derivatives of SEMANTICS.md §7c; ring_cut > 0 keeps the
+    rings <= ring_cut only (coarse-to-fine stages)."""
+    spec = np.ascontiguousarray(spec, dtype=np.complex64)
+    row = np.ascontiguousarray(row, dtype=ROW_DTYPE).reshape(1)
+    pose = _f32(pose6)
+    o4, dn, db, jj = np.zeros(4, np.float32), np.zeros(5, np.float32), np.zeros(3, np.float32), np.zeros(15, np.float32)
+    s = lib().orc_score_grad_cut(ref._h, _p(spec), _p(row), _p(pose), C.byref(cfg), _p(o4), _p(dn), _p(db), _p(jj), int(ring_cut))
+    return float(s), o4, dn, db, jj
 
 
 def normalize(img, radius_px, normalize=1, invert=0):

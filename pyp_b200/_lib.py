@@ -51,7 +51,8 @@ class RefineCfg(C.Structure):
         ("whiten", C.c_int32), ("symmetry_order", C.c_int32), ("local_iterations", C.c_int32),
         ("use_priors", C.c_int32), ("prior_mean_x", C.c_float), ("prior_mean_y", C.c_float),
         ("prior_var_x", C.c_float), ("prior_var_y", C.c_float),
-        ("reserved", C.c_int32 * 2),
+        ("optimizer", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -116,6 +117,7 @@ _SIGNATURES = {
     "cspb_refine_num_images": (_i, [_vp]),
     "cspb_refine_score": (_i, [_vp, _vp, _i, _vp]),
     "cspb_refine_score_poses": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "cspb_refine_score_grad": (_i, [_vp, _vp, _i, _i, _vp]),
     "cspb_refine_set_search_grid": (_i, [_vp, _vp, _i]),
     "cspb_refine_run": (_i, [_vp, _vp, _i, _vp, C.POINTER(_i64)]),
     "cspb_refine_run_device": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),

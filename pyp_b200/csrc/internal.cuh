@@ -226,8 +226,9 @@ int recon_flush_deferred(cspb_ctx *ctx);
 // every unit of the range has exactly `count` poses (one template instance per count, branch free);
 // mode 1 (shared) = rotation and CTF of the unit's first pose apply to all its poses (pure shift variations);
 // mode 2 (same shift) = the shift of the unit's first pose applies to all its poses (pure rotation / defocus variations)
+// ring_cut != INT_MAX (coarse-to-fine stages of the analytic optimiser): only rings <= ring_cut are scored; single-pose units only
 int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, int mode);
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, int mode, int ring_cut = 0x7fffffff);
 // units in class layout [A full][A tail][S full][S tail] (opt.cuh); nA plain + nS shared evals per group
 // a_same_shift: every pose of an A unit carries the shift of the unit's first pose (refine3d stencils)
 int launch_score_classes(cspb_ctx *ctx, const ScoreUnit *d_units, int n_groups, int nA, int nS, int PB, const float *d_poses6,

@@ -177,4 +177,126 @@ __global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4
     st[k] = s;
 }
 
+// ------------------------------------------------------------------ analytic optimiser (oracle/SEMANTICS.md §7c)
+// Same arithmetic, in the same order, as lm_step / lm_line / solve_spd5 of oracle/cspb_oracle.c.
+#define LM_NG 5
+#define LM_GOUT 28
+#define LM_DAMP 0.05f
+#define LM_CC_FLOOR 0.01f
+
+// one gradient evaluation per state at its current pose
+__global__ void lm_pose_kernel(const OptState *__restrict__ st, int n, int K, float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    for (int m = 0; m < OPT_NP; ++m) poses6[(long long)k * 6 + m] = st[k].x[m];
+    ScoreUnit un;
+    un.image = k / K; un.first_eval = k; un.count = 1; un.pad_ = 0;
+    units[k] = un;
+}
+
+__device__ __forceinline__ bool lm_solve_spd5(const float *H, const float *g, float *d) {
+    float L[LM_NG][LM_NG];
+    for (int i = 0; i < LM_NG; ++i)
+        for (int j = 0; j < LM_NG; ++j) L[i][j] = 0.f;
+    for (int i = 0; i < LM_NG; ++i)
+        for (int j = 0; j <= i; ++j) {
+            float s = H[i * LM_NG + j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+            if (i == j) {
+                if (!(s > 0.f)) return false;
+                L[i][i] = sqrtf(s);
+            } else
+                L[i][j] = s / L[j][j];
+        }
+    float y[LM_NG];
+    for (int i = 0; i < LM_NG; ++i) {
+        float s = g[i];
+        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+        y[i] = s / L[i][i];
+    }
+    for (int i = LM_NG - 1; i >= 0; --i) {
+        float s = y[i];
+        for (int k = i + 1; k < LM_NG; ++k) s -= L[k][i] * d[k];
+        d[i] = s / L[i][i];
+    }
+    return true;
+}
+
+// consume the gradient evaluation: Gauss-Newton step with damping and trust region, trial pose x + d
+__global__ void lm_step_kernel(OptState *__restrict__ st, int n, int K, int free_mask, const float *__restrict__ gout, float trust_ang,
+                               float trust_shift, float *__restrict__ poses6, ScoreUnit *__restrict__ units, const OptPrior pr) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    OptState s = st[k];
+    const float *o = gout + (long long)k * LM_GOUT;
+    const float A = o[2], B = o[3];
+    const float den = A * B;
+    const float rs = den > 0.f ? 1.f / sqrtf(den) : 0.f;
+    const float cc = o[0] * rs;
+    float g[LM_NG], H[LM_NG * LM_NG], d[LM_NG];
+    for (int a = 0; a < LM_NG; ++a) g[a] = o[4 + a] * rs - (a < 3 && B > 0.f ? 0.5f * cc * o[9 + a] / B : 0.f);
+    const float cce = cc > LM_CC_FLOOR ? cc : LM_CC_FLOOR;
+    const float hs = B > 0.f ? cce / B : 0.f;
+    int t = 0;
+    for (int a = 0; a < LM_NG; ++a)
+        for (int b = a; b < LM_NG; ++b) { H[a * LM_NG + b] = H[b * LM_NG + a] = hs * o[12 + t]; ++t; }
+    float f0 = cc;
+    if (pr.on) {
+        const float w[2] = {pr.wx, pr.wy};
+        const float dx[2] = {s.x[3] - pr.mx, s.x[4] - pr.my};
+        for (int q = 0; q < 2; ++q) {
+            f0 -= s.lam * w[q] * dx[q] * dx[q];
+            g[3 + q] -= 2.f * s.lam * w[q] * dx[q];
+            H[(3 + q) * LM_NG + 3 + q] += 2.f * s.lam * w[q];
+        }
+    }
+    for (int a = 0; a < LM_NG; ++a)
+        if (!((free_mask >> a) & 1)) {
+            for (int b = 0; b < LM_NG; ++b) H[a * LM_NG + b] = H[b * LM_NG + a] = 0.f;
+            H[a * LM_NG + a] = 1.f;
+            g[a] = 0.f;
+        }
+    for (int a = 0; a < LM_NG; ++a) H[a * LM_NG + a] *= 1.f + LM_DAMP;
+    if (!lm_solve_spd5(H, g, d))
+        for (int a = 0; a < LM_NG; ++a) d[a] = H[a * LM_NG + a] > 0.f ? g[a] / H[a * LM_NG + a] : 0.f;
+    float worst = 1.f;
+    for (int a = 0; a < LM_NG; ++a) {
+        const float q = fabsf(d[a]) / (a < 3 ? trust_ang : trust_shift);
+        if (q > worst) worst = q;
+    }
+    float slope = 0.f;
+    for (int a = 0; a < LM_NG; ++a) {
+        d[a] /= worst;
+        slope += g[a] * d[a];
+    }
+    for (int a = 0; a < LM_NG; ++a) s.d[a] = d[a];
+    s.d[5] = 0.f;
+    s.f = f0;
+    s.pad_[0] = slope;
+    st[k] = s;
+    float *q = poses6 + (long long)k * 6;
+    for (int m = 0; m < OPT_NP; ++m) q[m] = s.x[m] + s.d[m];
+    ScoreUnit un;
+    un.image = k / K; un.first_eval = k; un.count = 1; un.pad_ = 0;
+    units[k] = un;
+}
+
+// consume the trial evaluation: parabola through f(0), f'(0), f(1); maximiser clamped to [0, 2]
+__global__ void lm_select_kernel(OptState *__restrict__ st, int n, const float4 *__restrict__ sc, const OptPrior pr) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    OptState s = st[k];
+    const float f1 = cc_of(sc[k]) - prior_pen(pr, s.lam, s.x[3] + s.d[3], s.x[4] + s.d[4]);
+    const float slope = s.pad_[0];
+    const float c = f1 - s.f - slope;
+    float t;
+    if (c < 0.f) {
+        t = -slope / (2.f * c);
+        t = fminf(fmaxf(t, 0.f), 2.f);
+    } else
+        t = f1 > s.f ? 2.f : 0.f;
+    for (int m = 0; m < LM_NG; ++m) s.x[m] += t * s.d[m];
+    st[k] = s;
+}
+
 }  // namespace

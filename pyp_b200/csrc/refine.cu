@@ -211,7 +211,9 @@ struct ScoreArgs {
     const float *poses6;  // per eval: psi, theta, phi (deg), shift x, y (Angstrom), defocus delta (Angstrom)
     float inv_npx2;       // 2 / (n * pixel): shift (A) * frequency index -> phase in units of pi
     int limit_ring;       // rings above use |X_r| (signed-CC limit); INT_MAX = always signed
+    int ring_cut;         // coarse-to-fine stages (CUT kernels): rings above do not enter the sums; INT_MAX = whole band
     float4 *out;          // per eval: {numerator, signed X total, A, B}
+    float *gout;          // score_grad_kernel: 28 floats per eval {num, X, A, B, dnum[5], dB[3], jtj[15], 0}
 };
 
 // one 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100+)
@@ -282,7 +284,7 @@ __device__ __forceinline__ float ctf_from_chi_fast(float chi) {
 // unrolled twice so that the 4 * PB gathers of two samples are in flight together: the kernel waits on
 // gather latency, and 16 warps x 2 samples in flight (128 registers, r01g) beat 24 warps x 1 sample
 // (80 registers) by 6 %; 3 samples / 12 warps and 2 samples / 20 warps (spills) were slower.
-template <int PB, bool DDEF, int MODE>
+template <int PB, bool DDEF, int MODE, bool CUT = false>
 #ifndef CSPB_SCORE_MINB
 #define CSPB_SCORE_MINB 4
 #endif
@@ -332,6 +334,13 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
 
     for (int b = 0; b < A.n_bands; ++b) {
         const BandDesc bd = A.bands[b];
+        // CUT (coarse-to-fine stages of the analytic optimiser): this lane's ring is in or out for the whole band
+        bool ring_on = true;
+        if (CUT) {
+            const int rp_ = (lane & 2) ? bd.rings23 : bd.rings01;
+            ring_on = ((lane & 1) ? (rp_ >> 16) : (rp_ & 0xFFFF)) <= A.ring_cut;
+            if (!__any_sync(0xffffffffu, ring_on)) continue;
+        }
         f32x2 accX[PB];  // {sum gr px, sum gi py}
 #pragma unroll
         for (int p = 0; p < PB; ++p) accX[p] = 0ull;
@@ -344,10 +353,11 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
         for (int it = 0; it < bd.n_iter; ++it) {
             const int slot = bd.slot_start + it * 32 + lane;
             const int32_t ij = __ldg(A.slot_ij + slot);
-            const f32x2 Fp = __ldcs(reinterpret_cast<const f32x2 *>(img + slot));  // read once per unit: streaming
+            f32x2 Fp = __ldcs(reinterpret_cast<const f32x2 *>(img + slot));  // read once per unit: streaming
+            if (CUT && !ring_on) Fp = 0ull;
             const float2 F = make_float2(__uint_as_float((unsigned)Fp), __uint_as_float((unsigned)(Fp >> 32)));
             int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
-            const bool valid = (i != CSPB_DUMMY_I);
+            const bool valid = (i != CSPB_DUMMY_I) && (!CUT || ring_on);
             if (!valid) { i = 0; j = 0; }
             const float fi = (float)i, fj = (float)j;
             const float r2 = fi * fi + fj * fj;
@@ -450,6 +460,169 @@ __global__ void __launch_bounds__(128, DDEF ? 4 : CSPB_SCORE_MINB) score_kernel(
     }
 }
 
+// ---- analytic-gradient evaluation (oracle/SEMANTICS.md §7c; CPU restatement: orc_score_grad).
+// One warp per (image, pose).  The eight corners a sample gathers give the value AND the spatial gradient of the
+// trilinear interpolant; the chain rule through R(psi, theta, phi) and the phase ramp turn them into
+// dP/d(psi, theta, phi, x, y).  Besides the score sums the warp accumulates d num / d p (with the signed / absolute ring
+// rule, hence per ring), d B / d angles and the 15 entries of J^T J — everything the Gauss-Newton step needs from ONE
+// gather per sample instead of the 11 evaluations of the central-difference stencil.  Constant factors (degrees,
+// 2 pi / (n pixel)) are applied once at the end.
+#define CSPB_GOUT 28
+__global__ void __launch_bounds__(128, 3) score_grad_kernel(const ScoreArgs A) {
+    __shared__ float s_pose[4][16];     // 0..5 first two columns of pad*R, 6..11 of pad*dR/dtheta, 12..13 shift phase per index
+    __shared__ float s_tot[4][4][8];    // per warp and ring track: {num, X, dnum[5]} running totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = blockIdx.x * 4 + warp;
+    if (u >= A.n_units) return;
+    const ScoreUnit un = A.units[u];
+    const CtfCoef cc = A.ctf[un.image];
+    if (lane == 0) {
+        const float *q = A.poses6 + (long long)un.first_eval * 6;
+        float r[9];
+        euler_matrix(q[0], q[1], q[2], r);
+        float sps, cps, sth, cth, sph, cph;
+        sincosf(q[0] * (CSPB_PI_F / 180.f), &sps, &cps);
+        sincosf(q[1] * (CSPB_PI_F / 180.f), &sth, &cth);
+        sincosf(q[2] * (CSPB_PI_F / 180.f), &sph, &cph);
+        float *o = s_pose[warp];
+        o[0] = r[0] * A.padf; o[1] = r[1] * A.padf; o[2] = r[3] * A.padf; o[3] = r[4] * A.padf; o[4] = r[6] * A.padf; o[5] = r[7] * A.padf;
+        o[6] = -cph * sth * cps * A.padf; o[7] = cph * sth * sps * A.padf;
+        o[8] = -sph * sth * cps * A.padf; o[9] = sph * sth * sps * A.padf;
+        o[10] = -cth * cps * A.padf;      o[11] = cth * sps * A.padf;
+        o[12] = q[3] * A.inv_npx2; o[13] = q[4] * A.inv_npx2;
+    }
+    if (lane < 4)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_tot[warp][lane][k] = 0.f;
+    __syncwarp();
+    const float *sp = s_pose[warp];
+    const float m0 = sp[0], m1 = sp[1], m2 = sp[2], m3 = sp[3], m4 = sp[4], m5 = sp[5];
+    const float t0 = sp[6], t1 = sp[7], t2 = sp[8], t3 = sp[9], t4 = sp[10], t5 = sp[11];
+    const float mx = sp[12], my = sp[13];
+    const float2 *img = A.packed + (long long)un.image * A.n_slots;
+    const int origin = (A.rc * A.sy + A.rc) * A.sx;
+    f32x2 aA = 0ull, aB = 0ull, adB[3] = {0ull, 0ull, 0ull}, aJ[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) aJ[k] = 0ull;
+    for (int b = 0; b < A.n_bands; ++b) {
+        const BandDesc bd = A.bands[b];
+        const int rpair = (lane & 2) ? bd.rings23 : bd.rings01;
+        const int ring = (lane & 1) ? (rpair >> 16) : (rpair & 0xFFFF);
+        const bool ring_on = ring <= A.ring_cut;
+        if (!__any_sync(0xffffffffu, ring_on)) continue;
+        f32x2 aX = 0ull, adX[3] = {0ull, 0ull, 0ull}, aSx = 0ull, aSy = 0ull;
+        for (int it = 0; it < bd.n_iter; ++it) {
+            const int slot = bd.slot_start + it * 32 + lane;
+            const int32_t ij = __ldg(A.slot_ij + slot);
+            f32x2 Fp = __ldcs(reinterpret_cast<const f32x2 *>(img + slot));
+            if (!ring_on) Fp = 0ull;
+            const float2 F = make_float2(__uint_as_float((unsigned)Fp), __uint_as_float((unsigned)(Fp >> 32)));
+            int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+            const bool valid = (i != CSPB_DUMMY_I) && ring_on;
+            if (i == CSPB_DUMMY_I) { i = 0; j = 0; }
+            const float fi = (float)i, fj = (float)j;
+            const float r2 = fi * fi + fj * fj;
+            const float cv = valid ? ctf_from_chi_fast(ctf_chi(cc, fi, fj, r2)) : 0.f;
+            float x = m0 * fi + m1 * fj, y = m2 * fi + m3 * fj, z = m4 * fi + m5 * fj;
+            // coordinate velocities per radian (before the Friedel flip): psi = R (-j, i), theta = dR/dtheta (i, j), phi = (-y, x, 0)
+            const float vpx = m1 * fi - m0 * fj, vpy = m3 * fi - m2 * fj, vpz = m5 * fi - m4 * fj;
+            const float vtx = t0 * fi + t1 * fj, vty = t2 * fi + t3 * fj, vtz = t4 * fi + t5 * fj;
+            const float vfx = -y, vfy = x;
+            const float sgn = __int_as_float((__float_as_int(x) & 0x80000000) | 0x3f800000);
+            x = fabsf(x); y *= sgn; z *= sgn;
+            const int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
+            const float f = x - (float)ix, fyv = y - (float)iy, fzv = z - (float)iz;
+            const RefQuad *q = A.ref8 + origin + (iz * A.sy + iy) * A.sx + ix;
+            const QuadP q0 = ldg_quadp(q), q1 = ldg_quadp(q + 1);
+            const f32x2 fx2 = pack2(f, f), fy2 = pack2(fyv, fyv), fz2 = pack2(fzv, fzv);
+            // along x first: a = c0 + fx (c1 - c0); the four x-differences interpolate to dT/dx
+            const f32x2 d00 = sub2(q1.v00, q0.v00), d10 = sub2(q1.v10, q0.v10), d01 = sub2(q1.v01, q0.v01), d11 = sub2(q1.v11, q0.v11);
+            const f32x2 a00 = fma2(fx2, d00, q0.v00), a10 = fma2(fx2, d10, q0.v10), a01 = fma2(fx2, d01, q0.v01), a11 = fma2(fx2, d11, q0.v11);
+            const f32x2 dx0 = lerp2(d00, d10, fy2), dx1 = lerp2(d01, d11, fy2);
+            const f32x2 gx = lerp2(dx0, dx1, fz2);
+            const f32x2 dy0 = sub2(a10, a00), dy1 = sub2(a11, a01);
+            const f32x2 v0 = fma2(fy2, dy0, a00), v1 = fma2(fy2, dy1, a01);
+            const f32x2 gy = lerp2(dy0, dy1, fz2);
+            const f32x2 gz = sub2(v1, v0);
+            const f32x2 val = fma2(fz2, gz, v0);
+            const f32x2 cP = pack2(cv, cv * sgn), cD = pack2(cv * sgn, cv);
+            const f32x2 P = mul2(val, cP);
+            const f32x2 dPp = mul2(fma2(gz, pack2(vpz, vpz), fma2(gy, pack2(vpy, vpy), mul2(gx, pack2(vpx, vpx)))), cD);
+            const f32x2 dPt = mul2(fma2(gz, pack2(vtz, vtz), fma2(gy, pack2(vty, vty), mul2(gx, pack2(vtx, vtx)))), cD);
+            const f32x2 dPf = mul2(fma2(gy, pack2(vfy, vfy), mul2(gx, pack2(vfx, vfx))), cD);
+            float sn, cs;
+            sincospi_fast(fi * mx + fj * my, &sn, &cs);
+            const f32x2 G = pack2(F.x * cs - F.y * sn, F.x * sn + F.y * cs);
+            // Q = -i P: d/dshift of the equivalent projection shift (up to 2 pi / (n pixel) times the index)
+            const float Pre = __uint_as_float((unsigned)P), Pim = __uint_as_float((unsigned)(P >> 32));
+            const f32x2 Q = pack2(Pim, -Pre);
+            const f32x2 fi2 = pack2(fi, fi), fj2 = pack2(fj, fj);
+            aA = fma2(Fp, Fp, aA);
+            aB = fma2(P, P, aB);
+            aX = fma2(G, P, aX);
+            adX[0] = fma2(G, dPp, adX[0]); adX[1] = fma2(G, dPt, adX[1]); adX[2] = fma2(G, dPf, adX[2]);
+            const f32x2 GQ = mul2(G, Q);
+            aSx = fma2(fi2, GQ, aSx); aSy = fma2(fj2, GQ, aSy);
+            adB[0] = fma2(P, dPp, adB[0]); adB[1] = fma2(P, dPt, adB[1]); adB[2] = fma2(P, dPf, adB[2]);
+            // J^T J, upper triangle row major over (psi, theta, phi, x, y)
+            const f32x2 Qx = mul2(Q, fi2), Qy = mul2(Q, fj2);
+            aJ[0] = fma2(dPp, dPp, aJ[0]); aJ[1] = fma2(dPp, dPt, aJ[1]); aJ[2] = fma2(dPp, dPf, aJ[2]); aJ[3] = fma2(dPp, Qx, aJ[3]); aJ[4] = fma2(dPp, Qy, aJ[4]);
+            aJ[5] = fma2(dPt, dPt, aJ[5]); aJ[6] = fma2(dPt, dPf, aJ[6]); aJ[7] = fma2(dPt, Qx, aJ[7]); aJ[8] = fma2(dPt, Qy, aJ[8]);
+            aJ[9] = fma2(dPf, dPf, aJ[9]); aJ[10] = fma2(dPf, Qx, aJ[10]); aJ[11] = fma2(dPf, Qy, aJ[11]);
+            aJ[12] = fma2(Qx, Qx, aJ[12]); aJ[13] = fma2(Qx, Qy, aJ[13]); aJ[14] = fma2(Qy, Qy, aJ[14]);
+        }
+        // close the band: ring sums of X and its five derivatives (lanes with the same lane % 4 share a ring)
+        float rs[6] = {sum2(aX), sum2(adX[0]), sum2(adX[1]), sum2(adX[2]), sum2(aSx), sum2(aSy)};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            rs[k] += __shfl_xor_sync(0xffffffffu, rs[k], 4);
+            rs[k] += __shfl_xor_sync(0xffffffffu, rs[k], 8);
+            rs[k] += __shfl_xor_sync(0xffffffffu, rs[k], 16);
+        }
+        if (lane < 4) {
+            const float sg = (ring > A.limit_ring && rs[0] < 0.f) ? -1.f : 1.f;
+            float *t = s_tot[warp][lane];
+            t[0] += sg * rs[0];
+            t[1] += rs[0];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) t[2 + k] += sg * rs[1 + k];
+        }
+    }
+    __syncwarp();
+    float o[CSPB_GOUT];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        float v = s_tot[warp][lane & 3][k];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        o[k < 2 ? k : k + 2] = v;  // num, X, then dnum at 4..8
+    }
+    o[2] = warp_sum(sum2(aA));
+    o[3] = warp_sum(sum2(aB));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[9 + k] = warp_sum(sum2(adB[k]));
+#pragma unroll
+    for (int k = 0; k < 15; ++k) o[12 + k] = warp_sum(sum2(aJ[k]));
+    o[27] = 0.f;
+    if (lane == 0) {
+        // units: angles per degree, shifts per Angstrom (phase = pi * inv_npx2 * index * shift)
+        const float d2r = CSPB_PI_F / 180.f, k2 = CSPB_PI_F * A.inv_npx2;
+        const float su[5] = {d2r, d2r, d2r, k2, k2};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) o[4 + k] *= su[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o[9 + k] *= 2.f * d2r;
+        int t = 12;
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int b2 = a; b2 < 5; ++b2) o[t++] *= su[a] * su[b2];
+        float4 *dst = reinterpret_cast<float4 *>(A.gout + (long long)un.first_eval * CSPB_GOUT);
+#pragma unroll
+        for (int k = 0; k < CSPB_GOUT / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+}
+
 // Gather-load census of one scorer launch (roofline bookkeeping, never on the product path): the same
 // units and address arithmetic as score_kernel, no loads — counts the 32-byte quad loads that kernel
 // issues per lane (2 for the unit's first pose, 2 more for every other pose that leaves its voxel;
@@ -475,6 +648,8 @@ __global__ void __launch_bounds__(128) score_census_kernel(const ScoreArgs A, in
     unsigned cnt = 0;
     for (int b = 0; b < A.n_bands; ++b) {
         const BandDesc bd = A.bands[b];
+        const int rp_ = (lane & 2) ? bd.rings23 : bd.rings01;
+        if (!__any_sync(0xffffffffu, ((lane & 1) ? (rp_ >> 16) : (rp_ & 0xFFFF)) <= A.ring_cut)) continue;  // band above the stage's cut
         for (int it = 0; it < bd.n_iter; ++it) {
             const int32_t ij = A.slot_ij[bd.slot_start + it * 32 + lane];
             int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
@@ -662,10 +837,55 @@ int grid_for(long long total, int block, int sm) {
 }  // namespace
 
 // every unit in [d_units, d_units + n_units) has exactly `count` poses (1..4)
+static void fill_score_args(cspb_ctx *ctx, ScoreArgs &a, const ScoreUnit *d_units, int n_units, const float *d_poses6, const CtfCoef *d_ctf);
+
+// analytic-gradient evaluation of one pose per unit (score_grad_kernel); gout: CSPB_GOUT floats per evaluation
+int launch_score_grad(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, const float *d_poses6, const CtfCoef *d_ctf, float *d_gout,
+                      int ring_cut) {
+    if (n_units <= 0) return 0;
+    ScoreArgs a;
+    fill_score_args(ctx, a, d_units, n_units, d_poses6, d_ctf);
+    a.ring_cut = ring_cut;
+    a.out = nullptr;
+    a.gout = d_gout;
+    prof_begin(ctx, CSPB_PROF_SCORE, n_units);
+    score_grad_kernel<<<ceil_div(n_units, 4), 128, 0, ctx->stream>>>(a);
+    prof_end(ctx);
+    KERNEL_CHECK(ctx);
+    if (ctx->count_loads) {  // one gather (two quad loads) per lane and slot of the bands inside the cut
+        score_census_kernel<<<ceil_div(n_units, 4), 128, 0, ctx->stream>>>(a, 1, 0, ctx->d_load_count.as<unsigned long long>());
+        KERNEL_CHECK(ctx);
+        ctx->census_evals += n_units;
+    }
+    return 0;
+}
+
+static void fill_score_args(cspb_ctx *ctx, ScoreArgs &a, const ScoreUnit *d_units, int n_units, const float *d_poses6, const CtfCoef *d_ctf) {
+    a.ref8 = ctx->ref.d_ref8.as<RefQuad>();
+    a.sx = ctx->ref.sx8; a.sy = ctx->ref.sy; a.rc = ctx->ref.rc;
+    a.padf = (float)ctx->ref.pad;
+    a.slot_ij = ctx->plan.d_slot_ij.as<int32_t>();
+    a.bands = ctx->plan.d_bands.as<BandDesc>();
+    a.n_bands = ctx->plan.n_bands;
+    a.n_slots = ctx->plan.n_slots;
+    a.packed = ctx->d_packed.as<float2>();
+    a.ctf = d_ctf;
+    a.units = d_units;
+    a.n_units = n_units;
+    a.poses6 = d_poses6;
+    a.inv_npx2 = 2.f / ((float)ctx->rcfg.box * ctx->rcfg.pixel_size);
+    const float lim = ctx->rcfg.signed_cc_limit;
+    a.limit_ring = lim > 0.f ? (int)floorf((float)ctx->rcfg.box * ctx->rcfg.pixel_size / lim) : 0x7fffffff;
+    a.ring_cut = 0x7fffffff;
+    a.out = nullptr;
+    a.gout = nullptr;
+}
+
 int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count, const float *d_poses6,
-                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, int mode) {
+                 const CtfCoef *d_ctf, float4 *d_out, bool ddef, int64_t n_evals, int mode, int ring_cut) {
     if (n_units <= 0) return 0;
     if (count < 1 || count > 4) return cspb_fail(ctx, CSPB_E_ARG, "launch_score: bad unit size %d", count);
+    if (ring_cut != 0x7fffffff && (count != 1 || ddef || mode == 1)) return cspb_fail(ctx, CSPB_E_ARG, "launch_score: ring cut needs single-pose units");
     ScoreArgs a;
     a.ref8 = ctx->ref.d_ref8.as<RefQuad>();
     a.sx = ctx->ref.sx8; a.sy = ctx->ref.sy; a.rc = ctx->ref.rc;
@@ -682,9 +902,14 @@ int launch_score(cspb_ctx *ctx, const ScoreUnit *d_units, int n_units, int count
     a.inv_npx2 = 2.f / ((float)ctx->rcfg.box * ctx->rcfg.pixel_size);
     const float lim = ctx->rcfg.signed_cc_limit;
     a.limit_ring = lim > 0.f ? (int)floorf((float)ctx->rcfg.box * ctx->rcfg.pixel_size / lim) : 0x7fffffff;
+    a.ring_cut = ring_cut;
     a.out = d_out;
+    a.gout = nullptr;
     const int grid = ceil_div(n_units, 4);
     prof_begin(ctx, CSPB_PROF_SCORE, n_evals);
+    if (ring_cut != 0x7fffffff) {
+        score_kernel<1, false, 0, true><<<grid, 128, 0, ctx->stream>>>(a);
+    } else
 #define CSPB_LAUNCH_SCORE(PB_)                                                              \
     do {                                                                                    \
         if (mode == 1) {                                                                    \
@@ -1206,6 +1431,38 @@ extern "C" int cspb_refine_score(cspb_ctx *ctx, const cspb_row *rows, int n, flo
     return cspb_refine_score_poses(ctx, rows, n, idx.data(), poses.data(), n, scores_out);
 }
 
+// building block of the analytic optimiser (oracle/SEMANTICS.md §7c): value and derivatives at the poses of the rows;
+// out = 28 floats per row {num, X, A, B, d num / d (psi, theta, phi [deg], x, y [A]), d B / d angles, J^T J upper triangle, 0}
+extern "C" int cspb_refine_score_grad(cspb_ctx *ctx, const cspb_row *rows, int n, int ring_cut, float *out28) {
+    CSPB_ENTER(ctx);
+    if (!ctx || !rows || !out28 || n < 0) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (n != ctx->n_images) return cspb_fail(ctx, CSPB_E_ARG, "rows (%d) != loaded images (%d)", n, ctx->n_images);
+    if (n == 0) return 0;
+    cspb_row *d_rows;
+    CtfCoef *d_ctf;
+    int rc = upload_rows(ctx, rows, n, &d_rows, &d_ctf);
+    if (rc) return rc;
+    std::vector<float> poses((size_t)n * 6);
+    std::vector<ScoreUnit> units(n);
+    for (int k = 0; k < n; ++k) {
+        float *q = &poses[(size_t)k * 6];
+        q[0] = rows[k].psi; q[1] = rows[k].theta; q[2] = rows[k].phi; q[3] = rows[k].x_shift; q[4] = rows[k].y_shift; q[5] = 0.f;
+        units[k].image = k; units[k].first_eval = k; units[k].count = 1; units[k].pad_ = 0;
+    }
+    RESERVE(ctx, ctx->d_evals, poses.size() * sizeof(float));
+    RESERVE(ctx, ctx->d_units, units.size() * sizeof(ScoreUnit));
+    RESERVE(ctx, ctx->d_out, (size_t)n * CSPB_GOUT * sizeof(float));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_evals.p, poses.data(), poses.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), units.size() * sizeof(ScoreUnit), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_score_grad(ctx, ctx->d_units.as<ScoreUnit>(), n, ctx->d_evals.as<float>(), d_ctf, ctx->d_out.as<float>(),
+                           ring_cut > 0 ? ring_cut : 0x7fffffff);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out28, ctx->d_out.p, (size_t)n * CSPB_GOUT * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ================================================================== 2-D focus mask (prompts 29-32, 44)
 // LOGP over the projected focus sphere (oracle/SEMANTICS.md 6b): residual spectrum (shifted image -
 // alpha CTF slice) on the scoring band -> inverse FFT -> variance inside the disc.
@@ -1422,6 +1679,88 @@ extern "C" int cspb_refine_phase_sum(cspb_ctx *ctx, const cspb_row *rows, int n_
 
 int search_enqueue(cspb_ctx *ctx, const CtfCoef *d_ctf, const float *d_angles3, int n_orient, int K, void *d_hits);
 
+// resolution stage of iteration `it` of the analytic optimiser (same code as lm_stage in oracle/cspb_oracle.c):
+// returns f >= 1 and the last ring scored (INT_MAX for the full band)
+static float lm_stage(int it, int iters, float r_lo, float r_hi, int *ring_cut) {
+    const int ramp = iters - 3;
+    float f = 1.f;
+    if (ramp > 0 && it < ramp) f = powf(6.f, 1.f - (float)it / (float)ramp);
+    *ring_cut = 0x7fffffff;
+    if (f > 1.f) {
+        int rc = (int)floorf(r_hi / f);
+        int least = (int)floorf(r_lo) + 4;
+        if (least < 12) least = 12;
+        if (rc < least) rc = least;
+        if ((float)rc >= r_hi) { f = 1.f; } else { *ring_cut = rc; f = r_hi / (float)rc; }
+    }
+    return f;
+}
+
+// local refinement with the analytic optimiser (oracle/SEMANTICS.md §7c): per iteration ONE gradient evaluation
+// (score_grad_kernel) and ONE trial evaluation per state, coarse to fine over the rings of the band
+static int refine_lm_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_ctf, int n, cspb_row *d_changes, int free_mask,
+                             int64_t *n_evals_out) {
+    const cspb_refine_cfg &c = ctx->rcfg;
+    const int iters = (free_mask & 31) ? (c.local_iterations > 0 ? c.local_iterations : 8) : 0;
+    RESERVE(ctx, ctx->d_opt, (size_t)n * sizeof(OptState));
+    RESERVE(ctx, ctx->d_evals, (size_t)n * 2 * 6 * sizeof(float));
+    RESERVE(ctx, ctx->d_units, (size_t)n * sizeof(ScoreUnit));
+    RESERVE(ctx, ctx->d_out, (size_t)n * (2 * sizeof(float4) + CSPB_GOUT * sizeof(float)));
+    OptState *st = ctx->d_opt.as<OptState>();
+    float *ev = ctx->d_evals.as<float>();
+    ScoreUnit *un = ctx->d_units.as<ScoreUnit>();
+    float4 *out = ctx->d_out.as<float4>();
+    float *gout = reinterpret_cast<float *>(out + (size_t)2 * n);
+    const float r_hi = ctx->plan.r_hi, r_lo = ctx->plan.r_lo;
+    const int g = ceil_div(n, 128);
+    const bool focus_on = ctx->focus[3] > 0.f;
+    if (focus_on) RESERVE(ctx, ctx->d_alpha, (size_t)n * sizeof(float));
+    OptPrior pr{};
+    float lam_scale = 0.f;
+    if (c.use_priors) {
+        const float rad = c.mask_radius / c.pixel_size;
+        const float nmask = fmaxf(3.14159265f * rad * rad, 1.f);
+        lam_scale = 1.f / nmask;
+        pr.on = 1;
+        pr.mx = c.prior_mean_x; pr.my = c.prior_mean_y;
+        pr.wx = c.prior_var_x > 0.f ? 0.5f / c.prior_var_x : 0.f;
+        pr.wy = c.prior_var_y > 0.f ? 0.5f / c.prior_var_y : 0.f;
+    }
+    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, n, 1, nullptr, nullptr, st, 0.f, 0.f, 0.f, lam_scale);
+    KERNEL_CHECK(ctx);
+    int64_t evals = 0;
+    for (int it = 0; it < iters; ++it) {
+        int ring_cut;
+        const float f = lm_stage(it, iters, r_lo, r_hi, &ring_cut);
+        const float h_ang = 0.35f * 57.29578f * f / r_hi, h_shift = 0.07f * (float)c.box * f / r_hi * c.pixel_size;
+        lm_pose_kernel<<<g, 128, 0, ctx->stream>>>(st, n, 1, ev, un);
+        KERNEL_CHECK(ctx);
+        int rc = launch_score_grad(ctx, un, n, ev, d_ctf, gout, ring_cut);
+        if (rc) return rc;
+        lm_step_kernel<<<g, 128, 0, ctx->stream>>>(st, n, 1, free_mask, gout, 16.f * h_ang, 16.f * h_shift, ev, un, pr);
+        KERNEL_CHECK(ctx);
+        rc = launch_score(ctx, un, n, 1, ev, d_ctf, out, false, n, 0, ring_cut);
+        if (rc) return rc;
+        lm_select_kernel<<<g, 128, 0, ctx->stream>>>(st, n, out, pr);
+        KERNEL_CHECK(ctx);
+        evals += 2 * (int64_t)n;
+    }
+    opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, n, 1, ev, un);
+    KERNEL_CHECK(ctx);
+    int rc = launch_score(ctx, un, n, 2, ev, d_ctf, out, false, 2 * (int64_t)n, 0);
+    if (rc) return rc;
+    evals += 2 * (int64_t)n;
+    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, 1, out, ctx->plan.n_band, 0, d_rows, d_changes, pr,
+                                                                         focus_on ? ctx->d_alpha.as<float>() : nullptr);
+    KERNEL_CHECK(ctx);
+    if (focus_on) {
+        rc = focus_logp_enqueue(ctx, d_rows, const_cast<CtfCoef *>(d_ctf), n, d_changes);
+        if (rc) return rc;
+    }
+    if (n_evals_out) *n_evals_out = evals;
+    return 0;
+}
+
 // enqueue the whole refinement on the stream; rows/ctf already on the device.  With global search
 // the grid is searched first and the K best hits per image are refined as separate states.
 static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_ctf, int n, cspb_row *d_changes,
@@ -1434,6 +1773,10 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     if (c.refine_x) free_mask |= 8;
     if (c.refine_y) free_mask |= 16;
     if (c.refine_defocus) free_mask |= 32;
+    // optimiser 0 (default): analytic gradient + Gauss-Newton step for a plain local refinement of the pose; the stencil
+    // optimiser below serves the defocus refinement, the hits of a global search and optimizer = 1
+    if (c.optimizer == 0 && !c.global_search && !c.refine_defocus && c.local_refine)
+        return refine_lm_enqueue(ctx, d_rows, d_ctf, n, d_changes, free_mask, n_evals_out);
     int64_t evals = 0;
     int K = 1;
     const SearchHit *d_hits = nullptr;

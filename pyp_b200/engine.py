@@ -226,6 +226,13 @@ class Engine:
         self._ck(self._l.cspb_refine_score_poses(self._h, ptr(rows), rows.size, ptr(idx), ptr(poses), idx.size, ptr(out)))
         return out
 
+    def score_grad(self, rows, ring_cut=0):
+        """Value + analytic derivatives at the poses of `rows`: (n, 28) array {num, X, A, B, dnum[5], dB[3], jtj[15], 0}."""
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        out = np.zeros((rows.size, 28), dtype=np.float32)
+        self._ck(self._l.cspb_refine_score_grad(self._h, ptr(rows), rows.size, int(ring_cut), ptr(out)))
+        return out
+
     def set_search_grid(self, angles3):
         """Global-search orientation grid: (n, 3) array of (psi, theta, phi) in degrees."""
         a = np.ascontiguousarray(angles3, dtype=np.float32).reshape(-1, 3)

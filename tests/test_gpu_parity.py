@@ -143,14 +143,39 @@ def test_empty_and_bad_inputs(engine):
         engine.set_reference(np.zeros((32, 32, 32), np.float32))  # wrong box
 
 
-def test_local_refinement_matches_oracle(engine, oracle):
+@pytest.mark.parametrize("ring_cut", [0, 13])
+def test_score_gradient_matches_oracle(engine, oracle, ring_cut):
+    """The analytic-gradient evaluation (score_grad_kernel, SEMANTICS.md §7c) against orc_score_grad: the four score sums,
+    d num / d pose, d B / d angles and the 15 entries of J^T J, on the whole band and on a coarse-to-fine stage."""
     from pyp_b200 import synth
 
-    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, n_part=48)
+    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, n_part=24)
+    start = synth.perturb_rows(rows, 1.5, 0.7)
+    got = engine.score_grad(start, ring_cut)
+    for k in range(start.size):
+        r = start[k].astype(oracle.ROW_DTYPE)
+        s, o4, dnum, dB, jtj = oracle.score_grad(ref, specs[k], r, pose_of(start[k]), ocfg, ring_cut)
+        g = got[k]
+        assert np.allclose(g[:4], o4, rtol=2e-5), (k, g[:4], o4)
+        # derivatives are sums of signed terms: compare against the scale of the vector, not entry by entry
+        assert np.abs(g[4:9] - dnum).max() <= 2e-4 * np.abs(dnum).max() + 1e-3 * np.abs(o4[0]) * 1e-3, (k, g[4:9], dnum)
+        assert np.abs(g[9:12] - dB).max() <= 2e-4 * np.abs(dB).max() + 1e-6 * o4[3], (k, g[9:12], dB)
+        assert np.abs(g[12:27] - jtj).max() <= 2e-4 * np.abs(jtj).max(), (k, g[12:27], jtj)
+        assert g[27] == 0
+    if ring_cut:
+        full = engine.score_grad(start, 0)
+        assert (got[:, 2] < full[:, 2]).all()  # fewer rings, smaller sums
+
+
+@pytest.mark.parametrize("optimizer,evals", [(0, 18), (1, 114)])
+def test_local_refinement_matches_oracle(engine, oracle, optimizer, evals):
+    from pyp_b200 import synth
+
+    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, n_part=48, optimizer=optimizer)
     start = synth.perturb_rows(rows, 2.0, 1.0)
     got, changes, n_ev = engine.refine(start, want_changes=True)
     want, n_ev_o = oracle.refine_local(ref, specs, start.astype(oracle.ROW_DTYPE), ocfg)
-    assert n_ev == n_ev_o
+    assert n_ev == n_ev_o == evals * rows.size
     ang = angular_distance(got, want)
     sh = np.hypot(got["x_shift"] - want["x_shift"], got["y_shift"] - want["y_shift"])
     # "identical choice" for a continuous optimiser: same optimum to 0.02 deg / 0.02 A, i.e. ~1 % of
@@ -165,7 +190,8 @@ def test_local_refinement_matches_oracle(engine, oracle):
     s0 = engine.score(start)
     assert (got["score"] >= s0 - 1e-3).all()
     assert angular_distance(got, rows).mean() < angular_distance(start, rows).mean()
-    assert np.allclose(changes["psi"], got["psi"] - start["psi"], atol=1e-4)
+    dpsi = got["psi"] - start["psi"]
+    assert np.allclose(changes["psi"], dpsi - 360.0 * np.rint(dpsi / 360.0), atol=1e-4)  # changes are wrapped into [-180, 180)
 
 
 def test_local_refinement_with_shift_restraint_matches_oracle(engine, oracle):

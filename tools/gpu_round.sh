@@ -35,6 +35,10 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:insert_kernel -c 2 \
     -o $OUT/insert_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_insert.log 2>&1
 fi
+if has ncu_grad; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_grad_kernel --launch-skip 6 -c 3 \
+    -o $OUT/grad_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_grad.log 2>&1
+fi
 if has ncu_c4; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_kernel --launch-skip 8 -c 2 \
     -o $OUT/score_c4_full -f python bench.py --config C4 --steps 1 --warmup 1 --particles 512 --no-e2e --no-cpu-baseline > $OUT/ncu_score_c4.log 2>&1
