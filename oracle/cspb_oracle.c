@@ -819,16 +819,21 @@ static float lm_step(const float *o4, const float *dnum, const float *dB, const 
     return f0;
 }
 
-/* step length from f(0), f'(0) along d and f(1): parabola through the three, maximiser clamped to [0, 2] */
+/* step length from f(0), f'(0) along d and f(1): parabola through the three, maximiser clamped to [0, 2] — blended
+ * towards the plain Gauss-Newton step t = 1 as the predicted gain `slope` falls to the rounding noise of the scores
+ * (weight slope^2 / (slope^2 + tau^2), tau = 2e-5 in CC units): a converged state takes t = 1 instead of a fit to noise */
+#define LM_TAU 2e-5f
 static float lm_line(float f0, float slope, float f1) {
     const float c = f1 - f0 - slope;
+    float t;
     if (c < 0.f) {
-        float t = -slope / (2.f * c);
+        t = -slope / (2.f * c);
         if (t < 0.f) t = 0.f;
         if (t > 2.f) t = 2.f;
-        return t;
-    }
-    return f1 > f0 ? 2.f : 0.f;
+    } else
+        t = f1 > f0 ? 2.f : 0.f;
+    const float w = slope * slope / (slope * slope + LM_TAU * LM_TAU);
+    return 1.f + w * (t - 1.f);
 }
 
 /* resolution stage of iteration `it`: returns f >= 1 and the last ring used (INT_MAX for the full band) */

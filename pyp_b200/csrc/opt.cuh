@@ -183,6 +183,7 @@ __global__ void opt_select_kernel(OptState *__restrict__ st, int n, const float4
 #define LM_GOUT 28
 #define LM_DAMP 0.05f
 #define LM_CC_FLOOR 0.01f
+#define LM_TAU 2e-5f
 
 // one gradient evaluation per state at its current pose
 __global__ void lm_pose_kernel(const OptState *__restrict__ st, int n, int K, float *__restrict__ poses6, ScoreUnit *__restrict__ units) {
@@ -295,6 +296,9 @@ __global__ void lm_select_kernel(OptState *__restrict__ st, int n, const float4 
         t = fminf(fmaxf(t, 0.f), 2.f);
     } else
         t = f1 > s.f ? 2.f : 0.f;
+    // towards the plain Gauss-Newton step as the predicted gain falls to the rounding noise of the scores
+    const float w = slope * slope / (slope * slope + LM_TAU * LM_TAU);
+    t = 1.f + w * (t - 1.f);
     for (int m = 0; m < LM_NG; ++m) s.x[m] += t * s.d[m];
     st[k] = s;
 }
