@@ -600,14 +600,14 @@ def run_b200_arm(a):
     reduce_ms = float(np.mean([x.elapsed_time(y) for x, y in reduce_events])) if reduce_events else 0.0
 
     # ---- gather-load census: one untimed step with the counting launches on (scorer configs only)
-    loads_per_eval = None
+    loads_per_eval = slots_per_eval = None
     if rcfg is not None:
         eng.count_loads(True)
         device_step()
         eng.sync()
-        q, ev_c = eng.loads()
+        q, sl, ev_c = eng.loads()
         eng.count_loads(False)
-        loads_per_eval = q / max(1, ev_c)
+        loads_per_eval, slots_per_eval = q / max(1, ev_c), sl / max(1, ev_c)
 
     # ---- the two local optimisers on the same resident stack (untimed for `value`): final mean score, evaluations and
     # refinement time of each — the algorithmic gain of the analytic optimiser at a matched final score
@@ -732,16 +732,20 @@ def run_b200_arm(a):
             pass
         alg_bytes = 72.0 * n_band                                   # 64 B gather + 8 B image per band sample
         alg_gbs = alg_bytes * score_units / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
-        loaded_bytes = 32.0 * loads_per_eval + 8.0 * n_slots       # per evaluation: reference quads really loaded + the packed image
+        loaded_bytes = 32.0 * loads_per_eval + 8.0 * slots_per_eval  # per evaluation: reference quads really loaded + the packed image slots read
         loaded_gbs = loaded_bytes * score_units / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
-        bound = "l1_data_pipe/l2_gather" if touched <= (100 << 20) else "hbm_gather"
-        roof = {"bound": bound, "kernel": "score_kernel<PB,DDEF,MODE> (all scorer launches of the step)",
-                "achieved": loaded_gbs, "peak": g_ref, "unit": "GB/s", "frac": (loaded_gbs / g_ref) if g_ref else None,
+        # the binding unit in both regimes is the SM's L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 72-80 % for the plain
+        # scorer at 256 px AND at 384 px where the reference exceeds the L2 — profiles/r02_notes.md): the ceiling is the
+        # L1-resident gather peak; the peak from a window of the reference's size is the random-access (no locality) figure
+        roof = {"bound": "l1_data_pipe", "kernel": "score_grad_kernel + score_kernel<PB,DDEF,MODE> (all scorer launches of the step)",
+                "achieved": loaded_gbs, "peak": g_l1, "unit": "GB/s", "frac": (loaded_gbs / g_l1) if g_l1 else None,
                 "traffic": traffic,
-                "peak_source": f"live cspb_gather_peak: random 32-byte gathers, 32 warps/SM, window = the {touched / 1e6:.0f} MB of reference the band touches",
+                "peak_source": "live cspb_gather_peak: random 32-byte gathers by 32 warps/SM from an L1-resident window (one 32-byte wavefront per clock and SM)",
+                "gather_peak_reference_sized_window": g_ref, "reference_touched_mb": touched / 1e6,
                 "achieved_source": "live: (32 B x quad loads counted by the census launch + 8 B x band slots) per evaluation x evaluations / summed CUDA-event time of the scorer launches",
-                "loaded_bytes_per_unit": loaded_bytes, "quad_loads_per_sample_pose": loads_per_eval / max(1, n_slots),
-                "gather_peak_l1_resident": g_l1, "frac_of_l1_resident_peak": (loaded_gbs / g_l1) if g_l1 else None,
+                "loaded_bytes_per_unit": loaded_bytes, "quad_loads_per_slot_read": loads_per_eval / max(1.0, slots_per_eval),
+                "band_fraction_per_evaluation": slots_per_eval / max(1, n_slots),
+                "frac_of_reference_window_peak": (loaded_gbs / g_ref) if g_ref else None,
                 "l1_data_pipe_frac_ncu": l1_frac,
                 "algorithmic": {"bytes_per_unit": alg_bytes, "gbs": alg_gbs, "x_hbm_peak": alg_gbs / peak,
                                 "note": "SURVEY.md §8d counts 64 B of gather per band sample and pose; the kernel loads less (poses of a unit share voxels, shift evaluations share one gather) and those bytes are served by L1/L2, not HBM"},

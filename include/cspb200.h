@@ -89,10 +89,11 @@ int cspb_profile_enable(cspb_ctx *ctx, int on);
 int cspb_profile_get(cspb_ctx *ctx, int kind, double *total_ms, int64_t *launches, int64_t *units);
 /* Gather-load census of the scoring kernel (roofline bookkeeping): while on, every scorer launch is
  * followed by a counting launch over the same units that adds up the 32-byte reference loads the scorer
- * issues.  cspb_profile_get_loads returns that count and the evaluations it covers since the census was
- * switched on.  Run it on an untimed step; it has no reference counterpart. */
+ * issues and the 8-byte reads of the packed image spectra (one per lane and band slot visited).
+ * cspb_profile_get_loads returns both counts and the evaluations they cover since the census was switched on.
+ * Run it on an untimed step; it has no reference counterpart. */
 int cspb_profile_count_loads(cspb_ctx *ctx, int on);
-int cspb_profile_get_loads(cspb_ctx *ctx, int64_t *quad_loads, int64_t *evals);
+int cspb_profile_get_loads(cspb_ctx *ctx, int64_t *quad_loads, int64_t *slot_reads, int64_t *evals);
 
 /* ------------------------------------------------------------------ refine3d
  * Replaces the numerics of external/cistem2/refine3d as driven by

@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 
 #define PI_D 3.14159265358979323846
 #define PI_F 3.14159265358979323846f
@@ -609,6 +610,7 @@ static float refine_one(const orc_ref *r, const float *spec, const orc_row *row,
  * G = alpha P(p*) + noise the curvature of CC around p* is -(CC / B) J^T J (Gauss-Newton: second derivatives of the
  * interpolant dropped), which is the Hessian the step uses. */
 #define NG 5
+#define LM_SOFT 0.02f
 #define NJ 15 /* upper triangle of the 5x5 J^T J, row major: (0,0) (0,1) ... (0,4) (1,1) ... (4,4) */
 
 static void euler_derivatives(float psi, float theta, float phi, float *dth6) {
@@ -668,7 +670,7 @@ static float score_grad_cut(const orc_ref *r, const float *spec, const orc_row *
     float lo, hi;
     orc_band_limits(cfg, &lo, &hi);
     const int nb = 2 * n;
-    float *ring = (float *)calloc((size_t)nb * (1 + NG), sizeof(float)); /* per ring: X and its five derivatives */
+    float *ring = (float *)calloc((size_t)nb * (3 + NG), sizeof(float)); /* per ring: X, its five derivatives, A_r, B_r */
     float suma = 0.f, sumb = 0.f;
     float m[9], dth[6];
     orc_euler_matrix(pose6[0], pose6[1], pose6[2], m);
@@ -710,9 +712,11 @@ static float score_grad_cut(const orc_ref *r, const float *spec, const orc_row *
             const float ph = (fi * pose6[3] + fj * pose6[4]) * k2;
             const float cs = cosf(ph), sn = sinf(ph);
             const float gr = fr * cs - fim * sn, gi = fr * sn + fim * cs;
-            float *rg = ring + (size_t)bin * (1 + NG);
+            float *rg = ring + (size_t)bin * (3 + NG);
             rg[0] += gr * pr + gi * pi;
             for (int a = 0; a < NG; ++a) rg[1 + a] += gr * dp[a][0] + gi * dp[a][1];
+            rg[1 + NG] += fr * fr + fim * fim;
+            rg[2 + NG] += pr * pr + pi * pi;
             suma += fr * fr + fim * fim;
             sumb += pr * pr + pi * pi;
             for (int a = 0; a < 3; ++a) dB[a] += 2.f * (pr * dp[a][0] + pi * dp[a][1]);
@@ -724,11 +728,18 @@ static float score_grad_cut(const orc_ref *r, const float *spec, const orc_row *
     float num = 0.f, xs = 0.f;
     for (int a = 0; a < NG; ++a) dnum[a] = 0.f;
     for (int b = 0; b < nb; ++b) {
-        const float *rg = ring + (size_t)b * (1 + NG);
+        const float *rg = ring + (size_t)b * (3 + NG);
         xs += rg[0];
-        const float s = (b > limit && rg[0] < 0.f) ? -1.f : 1.f;
-        num += s * rg[0];
-        for (int a = 0; a < NG; ++a) dnum[a] += s * rg[1 + a];
+        num += (b > limit) ? fabsf(rg[0]) : rg[0];
+        /* derivative of |X_r| with a soft sign X_r / sqrt(X_r^2 + eps_r^2), eps_r = 0.02 sqrt(A_r B_r): a ring whose
+           correlation is below 0.02 (far inside its noise) contributes in proportion instead of flipping with the
+           rounding noise of X_r — the gradient stays continuous where the objective has its kinks */
+        float sg = 1.f;
+        if (b > limit) {
+            const float q = rg[0] * rg[0] + LM_SOFT * LM_SOFT * rg[1 + NG] * rg[2 + NG];
+            sg = q > 0.f ? rg[0] / sqrtf(q) : 0.f;
+        }
+        for (int a = 0; a < NG; ++a) dnum[a] += sg * rg[1 + a];
     }
     free(ring);
     if (out4) { out4[0] = num; out4[1] = xs; out4[2] = suma; out4[3] = sumb; }
@@ -878,6 +889,9 @@ static float refine_one_lm(const orc_ref *r, const float *spec, const orc_row *r
         const float f1 = score_cut(r, spec, row, q, cfg, o4, ring_cut) * 0.01f - prior_pen(cfg, row, q);
         (*evals) += 2;
         const float t = lm_line(f0, slope, f1);
+        if (getenv("ORC_LM_DEBUG"))
+            fprintf(stderr, "lm it %d cut %d f0 %.7f f1 %.7f slope %.3e c %.3e t %.4f d %.5f %.5f %.5f %.5f %.5f x %.5f %.5f %.5f %.5f %.5f\n", it, ring_cut, f0, f1, slope,
+                    f1 - f0 - slope, t, d[0], d[1], d[2], d[3], d[4], x[0], x[1], x[2], x[3], x[4]);
         for (int m = 0; m < NG; ++m) x[m] += t * d[m];
     }
     float o4s[4];

@@ -104,7 +104,7 @@ _SIGNATURES = {
     "cspb_profile_enable": (_i, [_vp, _i]),
     "cspb_profile_get": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "cspb_profile_count_loads": (_i, [_vp, _i]),
-    "cspb_profile_get_loads": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "cspb_profile_get_loads": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "cspb_refine_cfg_default": (_i, [C.POINTER(RefineCfg), _i, _f]),
     "cspb_refine_configure": (_i, [_vp, C.POINTER(RefineCfg)]),
     "cspb_refine_reset_images": (_i, [_vp]),

@@ -202,21 +202,22 @@ extern "C" int cspb_profile_count_loads(cspb_ctx *ctx, int on) {
     if (!ctx) return CSPB_E_ARG;
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (on) {
-        RESERVE(ctx, ctx->d_load_count, sizeof(unsigned long long));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_load_count.p, 0, sizeof(unsigned long long), ctx->stream));
+        RESERVE(ctx, ctx->d_load_count, 2 * sizeof(unsigned long long));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_load_count.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
         ctx->census_evals = 0;
     }
     ctx->count_loads = on != 0;
     return 0;
 }
 
-extern "C" int cspb_profile_get_loads(cspb_ctx *ctx, int64_t *quad_loads, int64_t *evals) {
+extern "C" int cspb_profile_get_loads(cspb_ctx *ctx, int64_t *quad_loads, int64_t *slot_reads, int64_t *evals) {
     CSPB_ENTER(ctx);
     if (!ctx || !ctx->d_load_count.p) return CSPB_E_STATE;
-    unsigned long long v = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&v, ctx->d_load_count.p, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long v[2] = {0, 0};
+    CU_TRY(ctx, cudaMemcpyAsync(v, ctx->d_load_count.p, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (quad_loads) *quad_loads = (int64_t)v;
+    if (quad_loads) *quad_loads = (int64_t)v[0];
+    if (slot_reads) *slot_reads = (int64_t)v[1];
     if (evals) *evals = ctx->census_evals;
     return 0;
 }

@@ -510,7 +510,11 @@ __global__ void __launch_bounds__(128, 3) score_grad_kernel(const ScoreArgs A) {
         const int ring = (lane & 1) ? (rpair >> 16) : (rpair & 0xFFFF);
         const bool ring_on = ring <= A.ring_cut;
         if (!__any_sync(0xffffffffu, ring_on)) continue;
-        f32x2 aX = 0ull, adX[3] = {0ull, 0ull, 0ull}, aSx = 0ull, aSy = 0ull;
+        f32x2 aX = 0ull, adX[3] = {0ull, 0ull, 0ull}, aSx = 0ull, aSy = 0ull, aAr = 0ull, aBr = 0ull;
+#ifndef CSPB_GRAD_UNROLL
+#define CSPB_GRAD_UNROLL 1
+#endif
+        CSPB_UNROLL_(CSPB_GRAD_UNROLL)
         for (int it = 0; it < bd.n_iter; ++it) {
             const int slot = bd.slot_start + it * 32 + lane;
             const int32_t ij = __ldg(A.slot_ij + slot);
@@ -557,8 +561,8 @@ __global__ void __launch_bounds__(128, 3) score_grad_kernel(const ScoreArgs A) {
             const float Pre = __uint_as_float((unsigned)P), Pim = __uint_as_float((unsigned)(P >> 32));
             const f32x2 Q = pack2(Pim, -Pre);
             const f32x2 fi2 = pack2(fi, fi), fj2 = pack2(fj, fj);
-            aA = fma2(Fp, Fp, aA);
-            aB = fma2(P, P, aB);
+            aAr = fma2(Fp, Fp, aAr);
+            aBr = fma2(P, P, aBr);
             aX = fma2(G, P, aX);
             adX[0] = fma2(G, dPp, adX[0]); adX[1] = fma2(G, dPt, adX[1]); adX[2] = fma2(G, dPf, adX[2]);
             const f32x2 GQ = mul2(G, Q);
@@ -571,18 +575,27 @@ __global__ void __launch_bounds__(128, 3) score_grad_kernel(const ScoreArgs A) {
             aJ[9] = fma2(dPf, dPf, aJ[9]); aJ[10] = fma2(dPf, Qx, aJ[10]); aJ[11] = fma2(dPf, Qy, aJ[11]);
             aJ[12] = fma2(Qx, Qx, aJ[12]); aJ[13] = fma2(Qx, Qy, aJ[13]); aJ[14] = fma2(Qy, Qy, aJ[14]);
         }
-        // close the band: ring sums of X and its five derivatives (lanes with the same lane % 4 share a ring)
-        float rs[6] = {sum2(aX), sum2(adX[0]), sum2(adX[1]), sum2(adX[2]), sum2(aSx), sum2(aSy)};
+        // close the band: ring sums of X, its five derivatives, A_r and B_r (lanes with the same lane % 4 share a ring)
+        float rs[8] = {sum2(aX), sum2(adX[0]), sum2(adX[1]), sum2(adX[2]), sum2(aSx), sum2(aSy), sum2(aAr), sum2(aBr)};
+        aA = pack2(__uint_as_float((unsigned)aA) + rs[6], __uint_as_float((unsigned)(aA >> 32)));
+        aB = pack2(__uint_as_float((unsigned)aB) + rs[7], __uint_as_float((unsigned)(aB >> 32)));
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 8; ++k) {
             rs[k] += __shfl_xor_sync(0xffffffffu, rs[k], 4);
             rs[k] += __shfl_xor_sync(0xffffffffu, rs[k], 8);
             rs[k] += __shfl_xor_sync(0xffffffffu, rs[k], 16);
         }
         if (lane < 4) {
-            const float sg = (ring > A.limit_ring && rs[0] < 0.f) ? -1.f : 1.f;
+            // |X_r| above the signed-CC limit; its derivative with the soft sign X_r / sqrt(X_r^2 + (0.02)^2 A_r B_r)
+            // (SEMANTICS.md §7c): continuous where the objective has its kinks
+            float sg = 1.f;
+            const bool absr = ring > A.limit_ring;
+            if (absr) {
+                const float q = rs[0] * rs[0] + 4e-4f * rs[6] * rs[7];
+                sg = q > 0.f ? rs[0] * rsqrtf(q) : 0.f;
+            }
             float *t = s_tot[warp][lane];
-            t[0] += sg * rs[0];
+            t[0] += absr ? fabsf(rs[0]) : rs[0];
             t[1] += rs[0];
 #pragma unroll
             for (int k = 0; k < 5; ++k) t[2 + k] += sg * rs[1 + k];
@@ -645,7 +658,7 @@ __global__ void __launch_bounds__(128) score_census_kernel(const ScoreArgs A, in
     __syncwarp();
     const int origin = (A.rc * A.sy + A.rc) * A.sx;
     const int NG = mode == 1 ? 1 : PB;
-    unsigned cnt = 0;
+    unsigned cnt = 0, slots = 0;
     for (int b = 0; b < A.n_bands; ++b) {
         const BandDesc bd = A.bands[b];
         const int rp_ = (lane & 2) ? bd.rings23 : bd.rings01;
@@ -656,6 +669,7 @@ __global__ void __launch_bounds__(128) score_census_kernel(const ScoreArgs A, in
             if (i == CSPB_DUMMY_I) { i = 0; j = 0; }
             const float fi = (float)i, fj = (float)j;
             int off0 = 0;
+            ++slots;  // one 8-byte read of the packed image per lane and slot
             for (int p = 0; p < NG; ++p) {
                 const float *m = s_m[warp][p];
                 float x = m[0] * fi + m[1] * fj, y = m[2] * fi + m[3] * fj, z = m[4] * fi + m[5] * fj;
@@ -667,8 +681,14 @@ __global__ void __launch_bounds__(128) score_census_kernel(const ScoreArgs A, in
             }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) atomicAdd(total, (unsigned long long)cnt);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        slots += __shfl_xor_sync(0xffffffffu, slots, o);
+    }
+    if (lane == 0) {
+        atomicAdd(total, (unsigned long long)cnt);
+        atomicAdd(total + 1, (unsigned long long)slots);
+    }
 }
 
 // central slice on the full half-plane grid (building block / test helper)

@@ -106,10 +106,11 @@ class Engine:
         self._ck(self._l.cspb_profile_count_loads(self._h, 1 if on else 0))
 
     def loads(self):
-        """(32-byte reference loads issued by the scorer, evaluations covered) since the census was switched on."""
-        a, b = C.c_int64(), C.c_int64()
-        self._ck(self._l.cspb_profile_get_loads(self._h, C.byref(a), C.byref(b)))
-        return int(a.value), int(b.value)
+        """(32-byte reference loads issued by the scorer, 8-byte image slot reads, evaluations covered) since the
+        census was switched on."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self._l.cspb_profile_get_loads(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
 
     # ------------------------------------------------------------------ refine3d
     @staticmethod

@@ -35,6 +35,16 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:insert_kernel -c 2 \
     -o $OUT/insert_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_insert.log 2>&1
 fi
+if has variants; then
+  # A/B of kernel build variants on the same box: alternative libraries through CSPB_LIB (pyp_b200/_lib.py)
+  for L in libcspb200.so libcspb200_gu2.so; do
+    [ -f pyp_b200/$L ] || continue
+    CSPB_LIB=$PWD/pyp_b200/$L timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline --no-strong > $OUT/variant_$L.json 2> $OUT/variant_$L.err
+  done
+fi
+if has e2e_debug; then
+  CSPB_PIPE_DEBUG=1 timeout 600 python tools/time_e2e.py 32768 > $OUT/time_e2e.log 2>&1
+fi
 if has ncu_grad; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_grad_kernel --launch-skip 6 -c 3 \
     -o $OUT/grad_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_grad.log 2>&1

@@ -7,7 +7,9 @@ from pyp_b200._lib import ROW_DTYPE
 from pyp_b200.engine import Engine
 P, n, px = int(sys.argv[1]) if len(sys.argv) > 1 else 8192, 256, 1.0
 dev = torch.device("cuda", 0)
-rcfg, ccfg = bench.workload_cfgs(n, px)
+c = bench.CONFIGS["C2"]
+rcfg = bench.fill(Engine.refine_defaults(n, px), bench.refine_params(c))
+ccfg = bench.fill(Engine.recon_defaults(n, px), bench.recon_params(c))
 eng = Engine(0); eng.refine_configure(rcfg); eng.set_symmetry("O")
 centres, amps, sigma = synth_torch.symmetric_phantom(n, "O")
 vol = synth_torch.volume(n, centres, amps, sigma, dev)
