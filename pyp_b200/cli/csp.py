@@ -200,7 +200,7 @@ def parse_argv(argv):
             "images": images, "stack": stack}
 
 
-def main(argv=None, out=sys.stdout):
+def main(argv=None, out=sys.stdout, session=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     try:
         a = parse_argv(argv)
@@ -214,9 +214,9 @@ def main(argv=None, out=sys.stdout):
         if mode == -1:
             pass
         elif mode == -2:
-            run_extract(par, mode, first, last, images, stack, config, out)
+            run_extract(par, mode, first, last, images, stack, config, out, session)
         elif mode in (0, 1, 2, 3, 4, 5, 6):
-            run_refine(par, ext, mode, first, last, stack, config, out)
+            run_refine(par, ext, mode, first, last, stack, config, out, session)
         else:
             raise PromptError(f"csp: unknown mode {mode}")
         out.write("\nCSP: Normal termination\n")

@@ -31,7 +31,6 @@ struct InsertArgs {
     int n_sym;
     float4 *acc0, *acc1;
     int tiles;            // tiles per image
-    int half_sel;         // insert only particles of this half (keeps the touched accumulator L2-resident)
 };
 
 __device__ __forceinline__ void add_corner(float4 *acc, int np, int xh, int x, int y, int z, float w, float re,
@@ -46,11 +45,16 @@ __device__ __forceinline__ void add_corner(float4 *acc, int np, int xh, int x, i
 __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     __shared__ float s_mat[INSERT_MAX_SYM][6];  // first two columns of pad * S_k * M
     __shared__ CtfCoef s_ctf;
-    const int img = blockIdx.x / A.tiles, tile = blockIdx.x - img * A.tiles;
+    // one launch covers both halves without idle CTAs: the grid walks the even-indexed images of the chunk first and the
+    // odd-indexed ones after, so that with the usual alternating split (odd / even POSITION_IN_STACK) the first half of the
+    // launch touches one accumulator and the second half the other — each half-sphere (70 MB at 256 px) stays L2-resident
+    // while it is being hit, as with one pass per half, at half the CTAs
+    const int k = blockIdx.x / A.tiles, tile = blockIdx.x - k * A.tiles;
+    const int n_even = (A.count + 1) >> 1;
+    const int img = k < n_even ? 2 * k : 2 * (k - n_even) + 1;
     const cspb_row row = A.rows[img];
     if (!(row.occupancy > 0.f) || row.score < A.score_threshold) return;
     const int half = A.per_particle ? (row.pind & 1) : ((row.position_in_stack & 1u) ? 0 : 1);
-    if (half != A.half_sel) return;
     const int n = A.n, nh = n / 2 + 1;
     if (threadIdx.x < A.n_sym) {
         float m[9];
@@ -413,15 +417,12 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
         a.acc0 = (deferred ? ctx->d_raw[0] : ctx->d_acc[0]).as<float4>();
         a.acc1 = (deferred ? ctx->d_raw[1] : ctx->d_acc[1]).as<float4>();
         a.tiles = ceil_div((long long)n * nh, 256);
-        // one pass per half: the voxels one half touches (a half-sphere of radius np/2, 16 B each)
-        // then fit in L2 and the vector atomics stop spilling to HBM
-        for (int h = 0; h < 2; ++h) {
-            a.half_sel = h;
-            prof_begin(ctx, CSPB_PROF_INSERT, h == 0 ? (int64_t)cnt * ctx->n_lit : 0);
-            insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
-            prof_end(ctx);
-            KERNEL_CHECK(ctx);
-        }
+        // one launch, ordered by half (see insert_kernel): the voxels one half touches (a half-sphere of radius np/2,
+        // 16 B each) fit in L2 and the vector atomics do not spill to HBM
+        prof_begin(ctx, CSPB_PROF_INSERT, (int64_t)cnt * ctx->n_lit);
+        insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
+        prof_end(ctx);
+        KERNEL_CHECK(ctx);
         if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (deferred && n_images > 0) ctx->raw_dirty = true;

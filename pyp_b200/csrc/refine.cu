@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(128, 3) score_grad_kernel(const ScoreArgs A) {
         if (!__any_sync(0xffffffffu, ring_on)) continue;
         f32x2 aX = 0ull, adX[3] = {0ull, 0ull, 0ull}, aSx = 0ull, aSy = 0ull, aAr = 0ull, aBr = 0ull;
 #ifndef CSPB_GRAD_UNROLL
-#define CSPB_GRAD_UNROLL 1
+#define CSPB_GRAD_UNROLL 2  // two samples in flight per lane at 159 registers / 12 warps per SM: 5 % faster than one at 126 / 16 (r02e)
 #endif
         CSPB_UNROLL_(CSPB_GRAD_UNROLL)
         for (int it = 0; it < bd.n_iter; ++it) {

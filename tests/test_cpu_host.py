@@ -549,3 +549,78 @@ def test_bench_workload_parameters_equal_the_library_defaults():
     a = bench.parse_args(["--config", "C2"])
     b = bench.parse_args(["--config", "C2", "--impl", "reference"])
     assert bench.workload_config(a, 32768) == bench.workload_config(b, 32768)
+
+
+def test_resident_server_protocol_with_a_recording_engine(tmp_path, monkeypatch):
+    """pyp_b200/server.py + cli/front.py without a GPU: the daemon (here in a thread, on a recording engine) serves the
+    stdlib-only client started the way bin/refine3d starts it; the files a stand-alone invocation would write appear, the
+    log comes back on the client's stdout, errors come back with the word `caught` and a non-zero exit status, and the
+    second request finds the reference of the first one still in place."""
+    import io
+    import json
+    import threading
+
+    import pyp_b200.engine as E
+    from pyp_b200 import server, tables
+    from pyp_b200.formats import cistem, mrc
+
+    class _Resident(_FakeEngine):
+        def ensure_reference(self, cfg, path, loader):
+            key = (bytes(cfg), path)
+            reused = getattr(self, "_key", None) == key
+            type(self).calls.append(("ensure_reference", (cfg, path), {"reused": reused}))
+            if not reused:
+                loader()
+            self._key, self.box = key, cfg.box
+            return reused
+
+    monkeypatch.setattr(E, "Engine_real", E.Engine, raising=False)
+    monkeypatch.setattr(E, "Engine", _Resident)
+    monkeypatch.setenv("CSPB_SOCKET_DIR", str(tmp_path))
+    _FakeEngine.calls = []
+    n, px, P = 16, 1.35, 12
+    rng = np.random.default_rng(0)
+    rows = np.zeros(P, dtype=ROW_DTYPE_)
+    rows["position_in_stack"] = np.arange(1, P + 1)
+    rows["occupancy"], rows["pixel_size"], rows["score"] = 100.0, px, 10.0
+    d = tmp_path / "work"
+    d.mkdir()
+    mrc.write(str(d / "T20S_stack.mrc"), rng.normal(size=(P, n, n)).astype(np.float32), px)
+    mrc.write(str(d / "T20S_r01.mrc"), rng.normal(size=(n, n, n)).astype(np.float32), px)
+    cistem.write_parameters(str(d / "T20S_r01.cistem"), rows)
+    (d / "statistics_r01.txt").write_text("")
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prompts_refine.json")))
+    text = g["local"]["heredoc"].replace("../T20S_stack.mrc", "T20S_stack.mrc").replace("\nO\n", "\nC1\n", 1)
+    th = threading.Thread(target=server.serve, args=(0, 0.0, 0.0), daemon=True)
+    th.start()
+    sock = server.socket_path(0)
+    for _ in range(100):
+        if os.path.exists(sock):
+            break
+        import time
+        time.sleep(0.05)
+    env = dict(os.environ, CSPB_SERVER="1", CSPB_DEVICE="0", CSPB_SOCKET_DIR=str(tmp_path), PYTHONPATH=ROOT)
+
+    def client(stdin_text, first, last):
+        t = stdin_text.replace("\n1\n100\n", f"\n{first}\n{last}\n", 1).replace("0000001_0000100", "%07d_%07d" % (first, last))
+        return subprocess.run([sys.executable, "-S", "-m", "pyp_b200.cli.front", "refine3d"], input=t.encode(), cwd=str(d), env=env,
+                              capture_output=True, timeout=60)
+
+    r1 = client(text, 1, 6)
+    assert r1.returncode == 0 and b"Refine3D: Normal termination" in r1.stdout, r1.stderr
+    r2 = client(text, 7, 12)
+    assert r2.returncode == 0 and b"Reference transform reused" in r2.stdout
+    out = cistem.merge([str(d / "T20S_r01_0000001_0000006.cistem"), str(d / "T20S_r01_0000007_0000012.cistem")])
+    assert list(out["position_in_stack"]) == list(range(1, P + 1)) and (out["score"] == 12.5).all()
+    reuse = [c[2]["reused"] for c in _FakeEngine.calls if c[0] == "ensure_reference"]
+    assert reuse == [False, True] and [c[0] for c in _FakeEngine.calls].count("init") == 1  # one context for both requests
+    bad = client(text.replace("T20S_r01.cistem", "missing.cistem", 1), 1, 6)
+    assert bad.returncode == 1 and b"caught" in bad.stderr
+    # shutdown request
+    import socket as S
+    s = S.socket(S.AF_UNIX, S.SOCK_STREAM)
+    s.connect(sock)
+    s.sendall(b'{"prog": "shutdown"}\n')
+    assert b"served 3 requests" in s.makefile("rb").readline()
+    th.join(timeout=10)
+    assert not th.is_alive() and not os.path.exists(sock)
