@@ -35,6 +35,21 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:insert_kernel -c 2 \
     -o $OUT/insert_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_insert.log 2>&1
 fi
+if has multi; then
+  # needs gpurun --gpus N: 2-GPU equality test of the product entry, H2D scaling of the platform, bench at every N
+  NG=$(nvidia-smi -L | wc -l)
+  ( time timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q ) > $OUT/pytest_multi.log 2>&1
+  for N in 1 2 4 8; do
+    [ $N -le $NG ] || continue
+    if [ $N -eq 1 ]; then
+      timeout 300 python tools/h2d_scaling.py > $OUT/h2d_$N.json 2>&1
+    else
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/h2d_scaling.py > $OUT/h2d_$N.json 2>&1
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 > $OUT/bench_N$N.json 2> $OUT/bench_N$N.err
+    fi
+  done
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $NG --steps 5 --warmup 3 > $OUT/bench_ref_N$NG.json 2> $OUT/bench_ref_N$NG.err
+fi
 if has variants; then
   # A/B of kernel build variants on the same box: alternative libraries through CSPB_LIB (pyp_b200/_lib.py)
   for L in libcspb200.so libcspb200_gu2.so; do
