@@ -339,6 +339,43 @@ enum { CSPB_DO_REFINE = 1, CSPB_DO_INSERT = 2 };
 int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images,
                             int flags, int64_t *n_evals_out);
 
+/* ------------------------------------------------------------------ between the stages
+ * Score shaping and class occupancies on device-resident tables, so that refine -> select -> reconstruct never leaves
+ * the GPU.  Replaces the host step pyp runs between its two binaries:
+ *   src/pyp/analysis/scores.py:300-761 shape_phase_residuals (as called at :766-825 and particle_cspt.py:747-755):
+ *   OCCUPANCY := 0 for projections below the score threshold of `cutoff` (SPA: that quantile of the scores; tilt series
+ *   — any |tilt| > 0 — the same quantile of the per-particle mean scores over |tilt| <= 12, applied to the means over
+ *   |tilt| < 10), outside the min/max score, defocus, azimuth, frame and tilt windows; POSITION_IN_STACK := 1..n;
+ *   src/pyp/analysis/occupancies.py:173-208 occupancy_extended.
+ * The host restatement pyp_b200/select.py is pinned bit for bit against the reference's outputs (tests/golden/shape_*). */
+typedef struct cspb_select_cfg {
+    float cutoff;              /* reconstruct_cutoff as a fraction in (0, 1]; 1 keeps everything                       */
+    float mindef, maxdef;      /* Angstrom (scores.py:646-650)                                                         */
+    int32_t firstframe, lastframe; /* TIND window, lastframe < 0 = off (:672-680)                                      */
+    float mintilt, maxtilt;    /* degrees (:682-690)                                                                   */
+    float minazh, maxazh;      /* THETA mod 180 window, [0, 180] = off (:652-670)                                      */
+    float minscore, maxscore;  /* fractions of the score range when <= 1, absolute scores otherwise (:519-530)          */
+    int32_t renumber;          /* rewrite POSITION_IN_STACK = 1..n like `_used.cistem` files (:757-759)                */
+    float threshold_override;  /* not NaN: use this threshold (the automatic two-Gaussian cutoff, reconstruct_cutoff = 0,
+                                  is fitted on the host: pyp_b200/select.py optimal_threshold)                         */
+    int32_t reserved[4];
+} cspb_select_cfg;
+int cspb_select_cfg_default(cspb_select_cfg *cfg);
+/* rows: n projection rows (device or host per `loc`), tilt_angle: per-row tilt angle in degrees or NULL (single
+ * particle: all zero).  threshold_out (may be NULL) receives the threshold used (NaN if none). */
+int cspb_select_scores(cspb_ctx *ctx, cspb_row *rows, int n, const float *tilt_angle, const cspb_select_cfg *cfg, int loc,
+                       double *threshold_out);
+/* LogP -> occupancy over K classes: logp, sigma (K x n, class major), K previous mean occupancies ->
+ * occ_out (K x n, percent) and sigma_out (n). */
+int cspb_class_occupancies(cspb_ctx *ctx, const float *logp, const float *sigma, const double *class_average_occ, int n_classes,
+                           int n, float *occ_out, float *sigma_out, int loc);
+/* refine3d -> score shaping -> reconstruct3d in one call over a HOST stack: every projection is uploaded once into a
+ * resident device buffer and refined as its batch arrives (as cspb_refine_reconstruct); when all rows are refined the
+ * selection runs on the device table and the whole stack is inserted with the shaped occupancies.  Needs
+ * cspb_refine_configure + cspb_set_reference + cspb_recon_begin.  rows_host returns the refined, shaped rows. */
+int cspb_refine_select_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images,
+                                   const cspb_select_cfg *cfg, int64_t *n_evals_out, double *threshold_out);
+
 /* ------------------------------------------------------------------ building blocks
  * Exposed for parity tests against the oracle and cuFFT. */
 /* Batched 2-D real-to-complex FFT, unnormalised, output n*(n/2+1) complex per image. */

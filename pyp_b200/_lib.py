@@ -87,6 +87,16 @@ class CspCfg(C.Structure):
     ]
 
 
+class SelectCfg(C.Structure):
+    """Score shaping between refine3d and reconstruct3d (include/cspb200.h cspb_select_cfg; scores.py:300-761)."""
+    _fields_ = [
+        ("cutoff", C.c_float), ("mindef", C.c_float), ("maxdef", C.c_float), ("firstframe", C.c_int32), ("lastframe", C.c_int32),
+        ("mintilt", C.c_float), ("maxtilt", C.c_float), ("minazh", C.c_float), ("maxazh", C.c_float),
+        ("minscore", C.c_float), ("maxscore", C.c_float), ("renumber", C.c_int32), ("threshold_override", C.c_float),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
 class CspbError(RuntimeError):
     pass
 
@@ -128,6 +138,10 @@ _SIGNATURES = {
     "cspb_csp_compose": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
     "cspb_csp_extract": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i]),
     "cspb_refine_reconstruct": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
+    "cspb_select_cfg_default": (_i, [C.POINTER(SelectCfg)]),
+    "cspb_select_scores": (_i, [_vp, _vp, _i, _vp, C.POINTER(SelectCfg), _i, C.POINTER(C.c_double)]),
+    "cspb_class_occupancies": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
+    "cspb_refine_select_reconstruct": (_i, [_vp, _vp, _vp, _i, C.POINTER(SelectCfg), C.POINTER(_i64), C.POINTER(C.c_double)]),
     "cspb_recon_cfg_default": (_i, [C.POINTER(ReconCfg), _i, _f]),
     "cspb_recon_begin": (_i, [_vp, C.POINTER(ReconCfg)]),
     "cspb_recon_insert": (_i, [_vp, _vp, _vp, _i, _i]),

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=${OUT:-../libcspb200.so}
-SRCS="capi plan fft refine search recon csp pipeline"
+SRCS="capi plan fft refine search recon csp pipeline select"
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function $EXTRA_NVCC_FLAGS"

@@ -161,6 +161,7 @@ struct cspb_ctx {
     cudaStream_t pipe_copy = nullptr;
     cudaEvent_t pipe_ready[2] = {nullptr, nullptr}, pipe_freed[2] = {nullptr, nullptr};
     DevBuf pipe_stage[2], pipe_rows;
+    DevBuf pipe_all;  // resident stack of cspb_refine_select_reconstruct
 
     // recon state
     bool recon_ready = false;

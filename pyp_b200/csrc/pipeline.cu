@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <chrono>
+#include <math.h>
 #include <vector>
 #include "internal.cuh"
 
@@ -101,6 +102,82 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     cudaStreamSynchronize(P.copy);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (dbg) fprintf(stderr, "pipe: all done at %.1f ms\n", ms_since());
+    if (n_evals_out) *n_evals_out = evals;
+    return rc;
+}
+
+
+// refine3d -> score shaping (select.cu) -> reconstruct3d without leaving the device.  The score
+// threshold is a quantile over ALL rows, so insertion cannot start before the last batch is refined: the stack is
+// uploaded once into a resident buffer (no double buffering, the copy stream never waits for the kernels), batches are
+// refined as they land, then the table is shaped and the whole resident stack inserted.
+extern "C" int cspb_refine_select_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images,
+                                              const cspb_select_cfg *cfg, int64_t *n_evals_out, double *threshold_out) {
+    CSPB_ENTER(ctx);
+    if (!ctx || !images_host || !rows_host || !cfg || n_images < 0) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (!ctx->recon_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_recon_begin first");
+    if (ctx->ccfg.box != ctx->rcfg.box) return cspb_fail(ctx, CSPB_E_ARG, "refine and reconstruct boxes differ");
+    if (n_evals_out) *n_evals_out = 0;
+    if (threshold_out) *threshold_out = NAN;
+    if (n_images == 0) return 0;
+    const int n = ctx->rcfg.box;
+    const size_t img_bytes = (size_t)n * n * sizeof(float);
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    if ((size_t)n_images * img_bytes > ctx->pipe_all.bytes && (size_t)n_images * img_bytes + ((size_t)8 << 30) > free_b + ctx->pipe_all.bytes)
+        return cspb_fail(ctx, CSPB_E_NOMEM, "a resident stack of %d images (%.1f GB) does not fit the device: use smaller ranges", n_images,
+                         (double)n_images * img_bytes / 1e9);
+    RESERVE(ctx, ctx->pipe_all, (size_t)n_images * img_bytes);
+    RESERVE(ctx, ctx->pipe_rows, (size_t)n_images * sizeof(cspb_row));
+    if (!ctx->pipe_copy) {
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_freed[k], cudaEventDisableTiming));
+        }
+    }
+    float *d_all = ctx->pipe_all.as<float>();
+    cspb_row *d_rows = ctx->pipe_rows.as<cspb_row>();
+    CU_TRY(ctx, cudaMemcpyAsync(d_rows, rows_host, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
+    // batches: the first holds the whitening sample (4 096 images), then whole multiples of a scorer wave
+    const long long W = cspb_wave_units(ctx);
+    std::vector<int> sizes;
+    {
+        long long rem = n_images, s = W > 4096 ? W : 4096;
+        while (rem > 0) {
+            long long take = s < rem ? s : rem;
+            if (rem - take < W / 2) take = rem;
+            sizes.push_back((int)take);
+            rem -= take;
+            s = 4 * W;
+        }
+    }
+    std::vector<cudaEvent_t> ready(sizes.size());
+    int64_t evals = 0;
+    int rc = 0;
+    size_t off = 0;
+    for (size_t k = 0; k < sizes.size(); ++k) {  // all copies are queued up front: the copy engine runs back to back
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+        CU_TRY(ctx, cudaMemcpyAsync(d_all + off * n * n, images_host + off * n * n, (size_t)sizes[k] * img_bytes, cudaMemcpyHostToDevice, ctx->pipe_copy));
+        CU_TRY(ctx, cudaEventRecord(ready[k], ctx->pipe_copy));
+        off += sizes[k];
+    }
+    off = 0;
+    for (size_t k = 0; k < sizes.size() && !rc; ++k) {
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ready[k], 0));
+        rc = cspb_refine_load_images(ctx, d_all + off * n * n, sizes[k], CSPB_DEVICE, 0);
+        int64_t ev = 0;
+        if (!rc) rc = cspb_refine_run_device(ctx, d_rows + off, sizes[k], &ev);
+        evals += ev;
+        off += sizes[k];
+    }
+    if (!rc) rc = cspb_select_scores(ctx, d_rows, n_images, nullptr, cfg, CSPB_DEVICE, threshold_out);
+    if (!rc) rc = cspb_recon_insert(ctx, d_all, d_rows, n_images, CSPB_DEVICE);
+    if (!rc) CU_TRY(ctx, cudaMemcpyAsync(rows_host, d_rows, (size_t)n_images * sizeof(cspb_row), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaStreamSynchronize(ctx->pipe_copy);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto e : ready) cudaEventDestroy(e);
     if (n_evals_out) *n_evals_out = evals;
     return rc;
 }

@@ -12,10 +12,10 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import DEVICE, HOST, PARTICLE_DTYPE, ROW_DTYPE, TILT_DTYPE, CspbError, CspCfg, ReconCfg, RefineCfg, ptr
+from ._lib import DEVICE, HOST, PARTICLE_DTYPE, ROW_DTYPE, TILT_DTYPE, CspbError, CspCfg, ReconCfg, RefineCfg, SelectCfg, ptr
 from .symmetry import symmetry_matrices
 
-__all__ = ["Engine", "ROW_DTYPE", "PARTICLE_DTYPE", "TILT_DTYPE", "RefineCfg", "ReconCfg", "CspCfg", "CspbError", "HOST", "DEVICE", "new_rows"]
+__all__ = ["Engine", "ROW_DTYPE", "PARTICLE_DTYPE", "TILT_DTYPE", "RefineCfg", "ReconCfg", "CspCfg", "SelectCfg", "CspbError", "HOST", "DEVICE", "new_rows"]
 
 
 def new_rows(n, pixel_size=1.0, voltage_kv=300.0, cs_mm=2.7, amplitude_contrast=0.07):
@@ -267,6 +267,44 @@ class Engine:
         flags = (self.DO_REFINE if refine else 0) | (self.DO_INSERT if insert else 0)
         self._ck(self._l.cspb_refine_reconstruct(self._h, ptr(images), ptr(rows), rows.size, flags, C.byref(ne)))
         return rows, int(ne.value)
+
+    # ------------------------------------------------------------------ between the stages: score shaping, occupancies
+    @staticmethod
+    def select_defaults(cutoff=1.0):
+        cfg = SelectCfg()
+        rc = _lib.lib().cspb_select_cfg_default(C.byref(cfg))
+        if rc != 0:
+            raise CspbError(f"cspb_select_cfg_default failed: {rc}")
+        cfg.cutoff = float(cutoff)
+        return cfg
+
+    def select_scores(self, rows, cfg: SelectCfg, tilt_angle=None):
+        """shape_phase_residuals on the device (scores.py:300-761): returns (shaped copy of rows, threshold)."""
+        rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+        tilt = None if tilt_angle is None else np.ascontiguousarray(tilt_angle, dtype=np.float32)
+        thr = C.c_double(float("nan"))
+        self._ck(self._l.cspb_select_scores(self._h, ptr(rows), rows.size, ptr(tilt), C.byref(cfg), HOST, C.byref(thr)))
+        return rows, thr.value
+
+    def class_occupancies(self, logp, sigma, class_average_occ):
+        """occupancy_extended on the device (occupancies.py:173-208): (occ (K, n) percent, sigma (n,))."""
+        logp = np.ascontiguousarray(logp, dtype=np.float32)
+        sigma = np.ascontiguousarray(sigma, dtype=np.float32)
+        avg = np.ascontiguousarray(class_average_occ, dtype=np.float64)
+        K, n = logp.shape
+        occ, sg = np.zeros((K, n), dtype=np.float32), np.zeros(n, dtype=np.float32)
+        self._ck(self._l.cspb_class_occupancies(self._h, ptr(logp), ptr(sigma), ptr(avg), K, n, ptr(occ), ptr(sg), HOST))
+        return occ, sg
+
+    def refine_select_reconstruct(self, images, rows, cfg: SelectCfg):
+        """refine3d -> score shaping -> reconstruct3d insertion over a host stack without leaving the device.
+        Returns (refined + shaped rows, n_evals, threshold)."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+        assert images.shape[0] == rows.size
+        ne, thr = C.c_int64(0), C.c_double(float("nan"))
+        self._ck(self._l.cspb_refine_select_reconstruct(self._h, ptr(images), ptr(rows), rows.size, C.byref(cfg), C.byref(ne), C.byref(thr)))
+        return rows, int(ne.value), thr.value
 
     # ------------------------------------------------------------------ csp (external/CSP/csp)
     @staticmethod

@@ -40,8 +40,10 @@ def _parse_args(argv):
     ap.add_argument("--merge", help="file with merge3d's stdin answers (its dump seeds are ignored: the sum happens over NVLink)")
     ap.add_argument("--cutoff", type=float, default=None, help="score shaping between the stages: reconstruct_cutoff fraction (e.g. 0.75)")
     ap.add_argument("--keep-dumps", action="store_true", help="with --merge: also write reconstruct3d's dump pair (answers 37/38)")
-    ap.add_argument("--log", default=None, help="log file of rank 0 (default: stdout)")
-    ap.add_argument("--master-port", type=int, default=29533)
+    # option names must not be prefixes of torchrun's own options (--log-dir, --master-port ...): the relaunch below hands
+    # this argv to `python -m torch.distributed.run ... -m pyp_b200.run <argv>` whose parser matches prefixes
+    ap.add_argument("--out-log", default=None, help="log file of rank 0 (default: stdout)")
+    ap.add_argument("--port", type=int, default=29533, help="rendezvous port of the relaunch under torchrun")
     return ap.parse_args(argv)
 
 
@@ -58,7 +60,7 @@ def main(argv=None):
         return 2
     if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", str(a.master_port), "-m", "pyp_b200.run"] + argv
+               "--master-port", str(a.port), "-m", "pyp_b200.run"] + argv
         return subprocess.call(cmd)
     try:
         return _worker(a)
@@ -185,7 +187,11 @@ def _worker(a):
                     tdist.broadcast(total, src=0)
                 occ = torch.zeros(int(total[0]), dtype=torch.float32)
                 if rank == 0:
-                    shaped = select.shape_scores(gathered, np.zeros(gathered.size), a.cutoff, renumber=False)
+                    scfg = Engine.select_defaults(a.cutoff)
+                    scfg.renumber = 0
+                    if a.cutoff == 0:  # automatic cutoff: the two-Gaussian fit of the score populations stays on the host
+                        scfg.threshold_override = 1.075 * select.optimal_threshold(gathered["score"]) if gathered.size > 20 else float("nan")
+                    shaped, _ = eng.select_scores(gathered, scfg)  # select.cu: the same decisions as scores.py:300-761
                     occ = torch.from_numpy(np.ascontiguousarray(shaped["occupancy"], dtype=np.float32))
                 if world > 1:
                     tdist.broadcast(occ, src=0)
@@ -263,8 +269,8 @@ def _worker(a):
     if rank == 0:
         log.write(f"pyp_b200.run: {world} GPU(s), {time.time() - t0:.2f} s, stages {timing}\n")
         text = log.getvalue()
-        if a.log:
-            with open(a.log, "a") as f:
+        if a.out_log:
+            with open(a.out_log, "a") as f:
                 f.write(text)
         else:
             sys.stdout.write(text)

@@ -26,7 +26,7 @@ def _n_gpus():
 def _launch(gpus, d, extra=()):
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     cmd = [sys.executable, "-m", "pyp_b200.run", "--gpus", str(gpus), "--refine", "refine.in", "--reconstruct", "reconstruct.in",
-           "--merge", "merge.in", "--keep-dumps", "--log", "run.log", *extra]
+           "--merge", "merge.in", "--keep-dumps", "--out-log", "run.log", *extra]
     r = subprocess.run(cmd, cwd=d, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     return open(os.path.join(d, "run.log")).read()
