@@ -310,6 +310,12 @@ int cspb_recon_begin(cspb_ctx *ctx, const cspb_recon_cfg *cfg);
  * CTF^2 weight accumulation, for every symmetry matrix set with cspb_set_symmetry. */
 int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_row *rows, int n_images,
                       int loc);
+/* The same with the data-driven dose weighting of prompt 22 (frealign.py:1731-1753; oracle/SEMANTICS.md §10): weight_cut
+ * holds two floats per projection {weight, cut radius in Fourier pixels}; the projection's samples are weighted by
+ * `weight` and, beyond the cut radius, by a raised-cosine edge of width 0.05 * box (cut radius <= 0: no low-pass).
+ * The pairs come from pyp_b200.tables.dose_weight_pairs (host). weight_cut lives where `loc` says; NULL = cspb_recon_insert. */
+int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, const cspb_row *rows, int n_images, int loc,
+                               const float *weight_cut);
 
 /* Accumulator geometry: voxels = (np/2+1)*np*np, 4 floats per voxel. */
 int cspb_recon_dims(const cspb_ctx *ctx, int *np_out, int64_t *floats_per_half_out);

@@ -1510,6 +1510,14 @@ static void add_corner(orc_recon *rc, float *acc, int x, int y, int z, float w, 
 }
 
 void orc_recon_insert(orc_recon *rc, const float *imgs, const orc_row *rows, int count, const float *sym, int n_sym) {
+    orc_recon_insert_weighted(rc, imgs, rows, count, sym, n_sym, NULL);
+}
+
+/* `aux` (may be NULL): two floats per row {weight, cut radius in Fourier pixels} of the data-driven dose weighting
+ * (SEMANTICS.md §10): the row's samples are weighted by `weight` and, beyond the cut radius, by a raised-cosine edge of
+ * width DOSE_EDGE * n/2 centred on it (cut radius <= 0: no low-pass) */
+#define DOSE_EDGE 0.1f
+void orc_recon_insert_weighted(orc_recon *rc, const float *imgs, const orc_row *rows, int count, const float *sym, int n_sym, const float *aux) {
     /* cisTEM Reconstruct3D::InsertSliceWithCTF shape: i = 0 column only for j >= 0 */
     const orc_recon_cfg *c = &rc->cfg;
     const int n = c->box, nh = n / 2 + 1;
@@ -1543,6 +1551,10 @@ void orc_recon_insert(orc_recon *rc, const float *imgs, const orc_row *rows, int
                 const float ctf = ctf_eval(&cc, i, j, 0.f);
                 float w = row->occupancy * 0.01f;
                 if (bk != 0.f) w *= expf(-bk * (c->average_score - row->score) * r2);
+                if (aux) {
+                    w *= aux[2 * k];
+                    if (aux[2 * k + 1] > 0.f) w *= cos_edge(sqrtf(r2), aux[2 * k + 1], DOSE_EDGE * 0.5f * (float)n);
+                }
                 const float ph = (i * row->x_shift + j * row->y_shift) * k2;
                 const float cs = cosf(ph), sn = sinf(ph);
                 const float re = (fr * cs - fim * sn) * ctf, im = (fr * sn + fim * cs) * ctf;

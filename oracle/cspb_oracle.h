@@ -159,6 +159,8 @@ orc_recon *orc_recon_create(const orc_recon_cfg *cfg);
 void orc_recon_free(orc_recon *rc);
 void orc_recon_insert(orc_recon *rc, const float *imgs, const orc_row *rows, int count,
                       const float *sym /* n_sym*9 */, int n_sym);
+/* the same with the per-row {weight, cut radius} pairs of the dose weighting (SEMANTICS.md §10); aux may be NULL */
+void orc_recon_insert_weighted(orc_recon *rc, const float *imgs, const orc_row *rows, int count, const float *sym, int n_sym, const float *aux);
 /* raw accumulators, same layout as the GPU dump: [z][y][x] float4 {re, im, w, 0}, centred y,z */
 void orc_recon_get_dump(const orc_recon *rc, int half, float *out);
 void orc_recon_finalize(orc_recon *rc, float molecular_mass_kda, float outer_radius_a, float *half1,

@@ -138,6 +138,7 @@ def lib():
             "orc_recon_create": (vp, [C.POINTER(ReconCfg)]),
             "orc_recon_free": (None, [vp]),
             "orc_recon_insert": (None, [vp, vp, vp, i, vp, i]),
+            "orc_recon_insert_weighted": (None, [vp, vp, vp, i, vp, i, vp]),
             "orc_recon_get_dump": (None, [vp, i, vp]),
             "orc_recon_finalize": (None, [vp, f, f, vp, vp, vp, vp]),
             "orc_fsc": (None, [vp, vp, i, vp]),
@@ -332,14 +333,13 @@ class Recon:
             lib().orc_recon_free(self._h)
             self._h = None
 
-    def insert(self, imgs, rows, sym=None):
+    def insert(self, imgs, rows, sym=None, aux=None):
+        """aux: optional (n, 2) float32 {weight, cut radius in Fourier pixels} per row (dose weighting, SEMANTICS.md §10)."""
         imgs = _f32(imgs)
         rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
-        if sym is None:
-            lib().orc_recon_insert(self._h, _p(imgs), _p(rows), rows.size, None, 0)
-        else:
-            sym = _f32(sym)
-            lib().orc_recon_insert(self._h, _p(imgs), _p(rows), rows.size, _p(sym), sym.shape[0])
+        sym = None if sym is None else _f32(sym)
+        aux = None if aux is None else _f32(aux).reshape(rows.size, 2)
+        lib().orc_recon_insert_weighted(self._h, _p(imgs), _p(rows), rows.size, _p(sym), 0 if sym is None else sym.shape[0], _p(aux))
 
     def dump(self, half):
         npad = self.cfg.box * self.cfg.pad

@@ -145,6 +145,7 @@ _SIGNATURES = {
     "cspb_recon_cfg_default": (_i, [C.POINTER(ReconCfg), _i, _f]),
     "cspb_recon_begin": (_i, [_vp, C.POINTER(ReconCfg)]),
     "cspb_recon_insert": (_i, [_vp, _vp, _vp, _i, _i]),
+    "cspb_recon_insert_weighted": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "cspb_recon_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64)]),
     "cspb_recon_device_ptr": (_i, [_vp, _i, C.POINTER(_vp)]),
     "cspb_recon_get_dump": (_i, [_vp, _i, _vp, _i]),

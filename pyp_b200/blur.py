@@ -43,7 +43,7 @@ def fan_poses(rows, deltas):
     return poses.reshape(-1, 6), np.repeat(np.arange(n, dtype=np.int32), K)
 
 
-def insert_blurred(eng, images, rows, n_samples, deltas=None, logp_range=LBLUR_RANGE):
+def insert_blurred(eng, images, rows, n_samples, deltas=None, logp_range=LBLUR_RANGE, weight_cut=None):
     """Score the fan on the scorer side of `eng` (configured, reference set) and insert every member with its
     weight.  Returns the (n, K) weights."""
     deltas = offsets() if deltas is None else np.asarray(deltas, dtype=np.float64)
@@ -57,5 +57,8 @@ def insert_blurred(eng, images, rows, n_samples, deltas=None, logp_range=LBLUR_R
         member = rows.copy()
         member["psi"] = np.mod(rows["psi"].astype(np.float64) + d, 360.0)
         member["occupancy"] = rows["occupancy"] * w[:, k]
-        eng.recon_insert(images, member)
+        if weight_cut is None:
+            eng.recon_insert(images, member)
+        else:
+            eng.recon_insert(images, member, weight_cut)
     return w

@@ -77,23 +77,34 @@ def ignored_answers(p):
     ]
 
 
-def dose_weights(p, rows):
-    """Per-projection multiplicative weights from the external file: one float per scan-order
-    (tilt) index = mean SCORE of that index, -1 if none (inout/metadata/core.py:3039-3075).
-    w = 1 for the best `fraction` of indices, falling off over `transition` (ours, SEMANTICS.md)."""
+def dose_weights(p, rows, rows_all, box):
+    """Per-projection {weight, cut radius} pairs of the data-driven dose weighting (prompt 22 + its four extra answers,
+    frealign.py:1731-1753) or None.  The external file holds one float per scan-order (tilt) index = the mean SCORE of
+    that index, -1 if none (inout/metadata/core.py:3039-3075); pyp passes the placeholder `/scratch/not_provided` when
+    no file was configured — the weights are then inferred from the parameter file itself, which is what its own
+    `compute_global_weights` would have written.  Law: tables.dose_weight_pairs (oracle/SEMANTICS.md §10).
+    Returns (pairs, description)."""
+    from .. import tables
+
     if not p.get("dose_weighting"):
-        return None
+        return None, ""
+    path = p.get("dose_weights_file", "")
+    source = path
     try:
-        w = np.loadtxt(p["dose_weights_file"], ndmin=1)
-    except OSError:
-        return None
-    valid = w >= 0
-    if not valid.any():
-        return None
-    rel = np.where(valid, w / w[valid].max(), 0.0)
-    idx = np.clip(rows["tind"].astype(np.int64), 0, w.size - 1)
-    out = rel[idx]
-    return np.clip(out, 0.0, 1.0).astype(np.float32)
+        w = np.loadtxt(path, ndmin=1)
+    except (OSError, ValueError):
+        w = tables.global_weights(rows_all)
+        source = f"the parameter file itself ({path!r} is not a readable weights file)"
+    if w.size == 0 or not (w >= 0).any():
+        return None, f"dose weighting requested but {source} holds no valid weight: skipped"
+    res = p["resolution_limit"] if p["resolution_limit"] > 0 else 2.0 * p["pixel_size"]
+    r_rec = min(box * p["pixel_size"] / res, box / 2 - 1)
+    pairs = tables.dose_weight_pairs(rows["tind"], w, p.get("dose_fraction", 4), p.get("dose_transition", 0.75), p.get("dose_multiply", True), r_rec)
+    n_valid = int((w >= 0).sum())
+    keep = max(1, int(np.ceil(n_valid / max(1.0, float(p.get("dose_fraction", 4))))))
+    return pairs, (f"Dose weighting from {source}: {n_valid} scan-order indices, the best {keep} at full resolution, the others "
+                   f"low-passed at {p.get('dose_transition', 0.75):g} x {r_rec:.1f} Fourier pixels, weights "
+                   f"{'scaled to mean 1' if p.get('dose_multiply', True) else 'normalised to sum 1'}")
 
 
 def run(p, out=sys.stdout, session=None):
@@ -110,9 +121,9 @@ def run(p, out=sys.stdout, session=None):
     rows_all = cistem.read_parameters(p["parameters"])
     sel = select_rows(rows_all, first, last)
     rows = rows_all[sel].copy()
-    dw = dose_weights(p, rows)
+    dw, dw_note = dose_weights(p, rows, rows_all, box)
     if dw is not None:
-        rows["occupancy"] = rows["occupancy"] * dw if p.get("dose_multiply", True) else np.where(dw > 0, rows["occupancy"], 0)
+        rows["occupancy"] = np.where(dw[:, 0] > 0, rows["occupancy"], 0)  # indices without a weight are not inserted
     eng = session.engine(first, last - first + 1)
     cfg = Engine.recon_defaults(box, p["pixel_size"])
     cfg.pad = 2 if p["padding"] >= 1.5 else 1
@@ -146,9 +157,9 @@ def run(p, out=sys.stdout, session=None):
             e = min(rows.size, s + chunk)
             imgs = session.images(p["stack"], pos[s:e])
             if n_band:
-                blur.insert_blurred(eng, imgs, rows[s:e], n_band)
+                blur.insert_blurred(eng, imgs, rows[s:e], n_band, weight_cut=None if dw is None else dw[s:e])
             else:
-                eng.recon_insert(imgs, rows[s:e])
+                eng.recon_insert(imgs, rows[s:e], None if dw is None else dw[s:e])
     n_used = int(used.size)
     if p["dump"]:
         for h, path in ((0, p["dump1"]), (1, p["dump2"])):
@@ -165,6 +176,8 @@ def run(p, out=sys.stdout, session=None):
     out.write(banner("Reconstruct3D"))
     out.write(f"\nInserted {n_used} of {rows.size} particles ({first}..{last}), symmetry {p['symmetry']}, "
               f"box {box}, padding {cfg.pad}, {time.time() - t0:.2f} s\n")
+    if dw_note:
+        out.write(dw_note + "\n")
     if n_band:
         out.write(f"Likelihood blurring: {blur.LBLUR_NROT} in-plane rotations from {blur.LBLUR_START:+.0f} deg in steps of "
                   f"{blur.LBLUR_STEP:.0f} deg, LogP range {blur.LBLUR_RANGE:.0f}\n")

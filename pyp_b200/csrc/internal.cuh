@@ -171,6 +171,7 @@ struct cspb_ctx {
     DevBuf d_raw[2];      // deferred-symmetry accumulators (only when n_lat > 1)
     bool raw_dirty = false;
     DevBuf d_shell;  // per-shell sums, Wiener terms, statistics rows
+    DevBuf d_aux;    // per-row {weight, cut radius} of the dose weighting (host callers)
     int64_t recon_inserted = 0;
 };
 

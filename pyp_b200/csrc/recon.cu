@@ -31,6 +31,8 @@ struct InsertArgs {
     int n_sym;
     float4 *acc0, *acc1;
     int tiles;            // tiles per image
+    const float2 *aux;    // optional per row {weight, cut radius in Fourier pixels}: data-driven dose weighting (SEMANTICS.md §10)
+    float aux_width;      // width of the raised-cosine edge at the cut radius
 };
 
 __device__ __forceinline__ void add_corner(float4 *acc, int np, int xh, int x, int y, int z, float w, float re,
@@ -86,6 +88,11 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     const float ctf = -sinpif(ctf_chi(s_ctf, fi, fj, r2) * (1.f / CSPB_PI_F));
     float w = row.occupancy * 0.01f;
     if (A.bfac_k != 0.f) w *= expf(-A.bfac_k * (A.avg_score - row.score) * r2);
+    if (A.aux) {
+        const float2 wc = A.aux[img];
+        w *= wc.x;
+        if (wc.y > 0.f) w *= cosine_edge(sqrtf(r2), wc.y, A.aux_width);
+    }
     // undo the particle shift: multiply by exp(+2 pi i (i sx + j sy) / n), shifts in pixels
     const float k2 = 2.f / ((float)n * row.pixel_size);
     float sn, cs;
@@ -371,6 +378,11 @@ extern "C" int cspb_recon_device_ptr(cspb_ctx *ctx, int half, void **ptr_out) {
 }
 
 extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_row *rows, int n_images, int loc) {
+    return cspb_recon_insert_weighted(ctx, images, rows, n_images, loc, nullptr);
+}
+
+extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, const cspb_row *rows, int n_images, int loc,
+                                          const float *weight_cut) {
     CSPB_ENTER(ctx);
     if (!ctx || !images || !rows || n_images < 0) return CSPB_E_ARG;
     if (!ctx->recon_ready) return cspb_fail(ctx, CSPB_E_STATE, "cspb_recon_begin first");
@@ -390,6 +402,15 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
             d_img = ctx->d_stage.as<float>();
             CU_TRY(ctx, cudaMemcpyAsync(ctx->d_rows.p, d_rows, (size_t)cnt * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
             d_rows = ctx->d_rows.as<cspb_row>();
+        }
+        const float2 *d_aux = nullptr;
+        if (weight_cut) {
+            d_aux = reinterpret_cast<const float2 *>(weight_cut) + s;
+            if (loc == CSPB_HOST) {
+                RESERVE(ctx, ctx->d_aux, (size_t)chunk * sizeof(float2));
+                CU_TRY(ctx, cudaMemcpyAsync(ctx->d_aux.p, d_aux, (size_t)cnt * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+                d_aux = ctx->d_aux.as<float2>();
+            }
         }
         RESERVE(ctx, ctx->d_stats, (size_t)2 * chunk * sizeof(float));
         float *offs = ctx->d_stats.as<float>(), *scls = offs + cnt;
@@ -417,6 +438,8 @@ extern "C" int cspb_recon_insert(cspb_ctx *ctx, const float *images, const cspb_
         a.acc0 = (deferred ? ctx->d_raw[0] : ctx->d_acc[0]).as<float4>();
         a.acc1 = (deferred ? ctx->d_raw[1] : ctx->d_acc[1]).as<float4>();
         a.tiles = ceil_div((long long)n * nh, 256);
+        a.aux = d_aux;
+        a.aux_width = 0.1f * 0.5f * (float)n;
         // one launch, ordered by half (see insert_kernel): the voxels one half touches (a half-sphere of radius np/2,
         // 16 B each) fit in L2 and the vector atomics do not spill to HBM
         prof_begin(ctx, CSPB_PROF_INSERT, (int64_t)cnt * ctx->n_lit);

@@ -364,11 +364,14 @@ class Engine:
         self._ck(self._l.cspb_recon_begin(self._h, C.byref(cfg)))
         self.ccfg = cfg
 
-    def recon_insert(self, images, rows):
+    def recon_insert(self, images, rows, weight_cut=None):
+        """weight_cut: optional (n, 2) float32 {weight, cut radius in Fourier pixels} per projection — the data-driven
+        dose weighting of reconstruct3d's prompt 22 (tables.dose_weight_pairs)."""
         if isinstance(images, np.ndarray):
             images = np.ascontiguousarray(images, dtype=np.float32)
             rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
-            self._ck(self._l.cspb_recon_insert(self._h, ptr(images), ptr(rows), int(images.shape[0]), HOST))
+            wc = None if weight_cut is None else np.ascontiguousarray(weight_cut, dtype=np.float32).reshape(rows.size, 2)
+            self._ck(self._l.cspb_recon_insert_weighted(self._h, ptr(images), ptr(rows), int(images.shape[0]), HOST, ptr(wc)))
         else:  # torch CUDA tensors; rows = device pointer (int), uint8 tensor of packed rows, or a host table (uploaded here)
             keep = None
             if isinstance(rows, np.ndarray):
@@ -378,8 +381,15 @@ class Engine:
                 torch.cuda.current_stream(images.device).synchronize()  # the engine runs on its own stream
                 rows = keep
             rp = rows if isinstance(rows, int) else rows.data_ptr()
-            self._ck(self._l.cspb_recon_insert(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(rp), int(images.shape[0]), DEVICE))
-            if keep is not None:
+            keep_w = None
+            if weight_cut is not None:
+                import torch
+
+                keep_w = torch.from_numpy(np.ascontiguousarray(weight_cut, dtype=np.float32).reshape(-1, 2)).to(images.device)
+                torch.cuda.current_stream(images.device).synchronize()
+            self._ck(self._l.cspb_recon_insert_weighted(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(rp), int(images.shape[0]), DEVICE,
+                                                        None if keep_w is None else C.c_void_p(keep_w.data_ptr())))
+            if keep is not None or keep_w is not None:
                 self.sync()
 
     def recon_dims(self):

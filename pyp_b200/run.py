@@ -204,9 +204,14 @@ def _worker(a):
             lo, hi = dist.shard_range(0, rng_rows.size - 1, rank, world)
             rows = rng_rows[lo:hi + 1].copy()
         # dose weights and the average score are properties of the WHOLE range: computed before sharding matters
-        dw = rc_cli.dose_weights(p, rows)
+        all_for_weights = used_all if used_all is not None else (dist.gather_rows(rows) if world > 1 else rows)
+        if world > 1 and used_all is None:  # the weights are a property of the whole table: every rank needs it
+            holder = [all_for_weights]
+            tdist.broadcast_object_list(holder, src=0)
+            all_for_weights = holder[0]
+        dw, dw_note = rc_cli.dose_weights(p, rows, all_for_weights, box)
         if dw is not None:
-            rows["occupancy"] = rows["occupancy"] * dw if p.get("dose_multiply", True) else np.where(dw > 0, rows["occupancy"], 0)
+            rows["occupancy"] = np.where(dw[:, 0] > 0, rows["occupancy"], 0)
         used = rows[rows["occupancy"] > 0]
         mom = torch.tensor([float(used["score"].astype(np.float64).sum()), float(used.size), float(rows.size)], dtype=torch.float64)
         if world > 1:
@@ -225,7 +230,7 @@ def _worker(a):
         pos = rows["position_in_stack"].astype(np.int64)
         for s in range(0, rows.size, 8192):
             e = min(rows.size, s + 8192)
-            eng.recon_insert(images_of(p["stack"], pos[s:e]), rows[s:e])
+            eng.recon_insert(images_of(p["stack"], pos[s:e]), rows[s:e], None if dw is None else dw[s:e])
         timing["insert_s"] = time.time() - t1
         if world > 1:
             nfloats = eng.recon_dims()[1]
@@ -237,6 +242,8 @@ def _worker(a):
             n_used = int(mom[1])
             log.write(prompts.banner("Reconstruct3D") + f"\nInserted {n_used} of {int(mom[2])} particles ({first}..{last}) on {world} GPU(s), "
                       f"symmetry {p['symmetry']}, box {box}, padding {cfg.pad}\n")
+            if dw_note:
+                log.write(dw_note + "\n")
             prompts.write_notes(log, "reconstruct3d", rc_cli.ignored_answers(p))
             if a.merge and a.keep_dumps:
                 for h, path in ((0, p["dump1"]), (1, p["dump2"])):

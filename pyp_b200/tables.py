@@ -111,6 +111,36 @@ def write_global_weights(path, weights):
         f.write("\n".join(str(float(w)) for w in weights))
 
 
+def dose_weight_pairs(tind, weights, fraction, transition, multiply, r_rec):
+    """Per-projection {weight, cut radius} of reconstruct3d's data-driven dose weighting (prompt 22, frealign.py:1731-1753;
+    the fork's law is not public — this is oracle/SEMANTICS.md §10).
+
+    `weights` = one value per scan-order index (TIND): the mean SCORE at that index, -1 where unused (`global_weights`).
+    The valid weights are normalised to sum 1 and, with `multiply`, scaled by their number ("multiply by number of
+    frames"): a flat series gives weight 1 everywhere.  The best ceil(n / fraction) indices contribute at every
+    resolution ("larger values contribute fewer frames to high resolution"); the others are low-passed at
+    `transition` x `r_rec` (Fourier pixels; the insertion kernel applies a raised-cosine edge there).  Projections
+    whose TIND has no valid weight get weight 0.  Returns an (n_rows, 2) float32 array."""
+    w = np.asarray(weights, dtype=np.float64).ravel()
+    tind = np.asarray(tind, dtype=np.int64)
+    out = np.zeros((tind.size, 2), dtype=np.float32)
+    valid = w >= 0
+    if not valid.any() or tind.size == 0:
+        return out
+    n_valid = int(valid.sum())
+    norm = np.where(valid, w / w[valid].sum() * (n_valid if multiply else 1.0), 0.0)
+    keep = max(1, int(np.ceil(n_valid / max(1.0, float(fraction)))))
+    order = np.argsort(-np.where(valid, w, -np.inf), kind="stable")
+    full_band = np.zeros(w.size, dtype=bool)
+    full_band[order[:keep]] = True
+    cut = np.where(full_band | ~valid, 0.0, float(transition) * float(r_rec))
+    inside = (tind >= 0) & (tind < w.size)
+    idx = np.clip(tind, 0, w.size - 1)
+    out[:, 0] = np.where(inside, norm[idx], 0.0)
+    out[:, 1] = np.where(inside, cut[idx], 0.0)
+    return out
+
+
 def parameter_statistics(rows):
     """Rows 0 / 1 of `<name>_stat.cistem`: np.mean / np.var (population) of every column, in float64, stored
     through the column types of the table like any other row (particle_cspt.py:1009-1016)."""

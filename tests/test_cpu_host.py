@@ -309,9 +309,18 @@ def test_reconstruct3d_parses_the_reference_s_own_heredocs():
     assert p["score_weighting"] is True and p["dose_weighting"] is True and p["dose_weights_file"] == "/scratch/not_provided"
     assert p["dose_multiply"] is True and p["dose_fraction"] == 4 and p["dose_transition"] == 0.75
     assert p["per_particle_split"] is True and p["likelihood_blurring"] is True
-    # a weights file that does not exist leaves the occupancies alone
-    rows = np.zeros(3, dtype=ROW_DTYPE_)
-    assert reconstruct3d.dose_weights(p, rows) is None
+    # pyp's placeholder for "no external file" (frealign.py:1735): the weights are inferred from the parameter file itself
+    rows = np.zeros(6, dtype=ROW_DTYPE_)
+    rows["occupancy"], rows["tind"], rows["score"] = 100.0, [0, 0, 1, 1, 2, 2], [10, 12, 20, 22, 5, 7]
+    p["pixel_size"], p["resolution_limit"] = 1.35, 2.7
+    dw, note = reconstruct3d.dose_weights(p, rows, rows, 64)
+    assert "the parameter file itself" in note and dw.shape == (6, 2)
+    # fraction 4 of 3 indices: the best one (TIND 1) keeps the full band, the others are low-passed at 0.75 x r_rec = 0.75 x 31
+    assert np.allclose(dw[:, 1], [23.25, 23.25, 0, 0, 23.25, 23.25]) and np.allclose(dw[:, 0], np.array([11, 11, 21, 21, 6, 6]) / 38 * 3)
+    # without any scored projection there is nothing to weight with: said in the log, occupancies left alone
+    rows["occupancy"] = 0
+    dw, note = reconstruct3d.dose_weights(p, rows, rows, 64)
+    assert dw is None and "skipped" in note
 
 
 def test_merge_front_ends_parse_the_reference_s_own_heredocs():
@@ -469,8 +478,10 @@ def test_front_end_branches_run_without_a_gpu(tmp_path, monkeypatch):
     assert names.count("recon_insert") == 21 and names.count("score_poses") == 1 and "ensure_reference" in names   # the fan
     ins = [c for c in _FakeEngine.calls if c[0] == "recon_insert"]
     total_occ = sum(c[1][1]["occupancy"].astype(np.float64) for c in ins)
-    dw = reconstruct3d.dose_weights(p, rows)
-    assert np.allclose(total_occ, rows["occupancy"] * dw, rtol=1e-5)          # flat scores: uniform fan, weights sum to 1
+    dw, note = reconstruct3d.dose_weights(p, rows, rows, n)
+    assert np.allclose(total_occ, rows["occupancy"], rtol=1e-5)               # flat scores: uniform fan, weights sum to 1
+    assert all(np.allclose(c[1][2], dw) for c in ins) and np.allclose(dw[:, 0], 1.0)  # every fan member carries the dose pairs
+    assert "Dose weighting from global_weight.txt" in log.getvalue()
     assert "Likelihood blurring" in log.getvalue() and os.path.exists("T20S_r01_map1_n1.mrc")
     # ---- local_merge3d and merge3d over that dump pair (host-side paths of both front-ends)
     _FakeEngine.calls = []

@@ -67,8 +67,18 @@ def test_global_weights_match_reference(tmp_path):
     # the reconstruct3d front-end reads the same file
     from pyp_b200.cli import reconstruct3d
 
-    dw = reconstruct3d.dose_weights({"dose_weighting": True, "dose_weights_file": out}, rows)
-    assert dw.shape == (rows.size,) and dw.max() == 1.0 and (dw[rows["tind"] == 3] == 0).all()
+    p = {"dose_weighting": True, "dose_weights_file": out, "dose_fraction": 4, "dose_transition": 0.75, "dose_multiply": True,
+         "resolution_limit": 0.0, "pixel_size": 1.0}
+    dw, note = reconstruct3d.dose_weights(p, rows, rows, 64)
+    assert dw.shape == (rows.size, 2) and (dw[rows["tind"] == 3] == 0).all() and out in note
+    valid = w[w >= 0]
+    assert np.allclose(dw[rows["tind"] == 0, 0], w[0] / valid.sum() * valid.size)      # normalised to mean 1 over the valid indices
+    n_full = int(np.ceil(valid.size / 4))
+    assert len({int(t) for t in rows["tind"][dw[:, 1] == 0]} - {3}) == n_full           # the best quarter keeps the whole band
+    assert np.allclose(dw[(dw[:, 1] > 0), 1], 0.75 * 31.0)
+    # multiply = no: the same weights normalised to sum 1
+    dw2, _ = reconstruct3d.dose_weights(dict(p, dose_multiply=False), rows, rows, 64)
+    assert np.allclose(dw2[:, 0] * valid.size, dw[:, 0])
 
 
 def test_parameter_statistics_match_reference(tmp_path):

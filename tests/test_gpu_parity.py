@@ -405,6 +405,34 @@ def test_insertion_matches_oracle(engine, oracle, sym, kw):
     engine.set_symmetry("C1")
 
 
+def test_dose_weighted_insertion_matches_oracle(engine, oracle):
+    """reconstruct3d prompt 22 with its four extra answers (frealign.py:1731-1753; SEMANTICS.md §10): per-projection
+    {weight, cut radius} pairs from the scan-order weights — CUDA accumulators against the oracle's, and the law does what
+    it says (the low-passed projections leave the outer shells to the others)."""
+    from pyp_b200 import tables
+
+    n, px = 32, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=24, n_blobs=20)
+    rows["tind"] = np.arange(rows.size) % 6
+    rows["score"] = 10.0 + 3.0 * rows["tind"]
+    w = tables.global_weights(rows)
+    pairs = tables.dose_weight_pairs(rows["tind"], w, 3, 0.6, True, n / 2 - 1)
+    assert (pairs[:, 1] == 0).sum() == 2 * 4 and np.isclose(pairs[:, 0].mean(), 1.0)   # ceil(6 / 3) = 2 indices at full resolution
+    cfg, ocfg = _recon_cfgs(oracle, n, px)
+    engine.set_symmetry("C1")
+    engine.recon_begin(cfg)
+    engine.recon_insert(stack, rows, pairs)
+    rc = oracle.Recon(ocfg)
+    rc.insert(stack, rows.astype(oracle.ROW_DTYPE), None, pairs)
+    plain = oracle.Recon(ocfg)
+    plain.insert(stack, rows.astype(oracle.ROW_DTYPE))
+    for h in (0, 1):
+        got, want = fold_x0(engine.recon_get_dump(h)), fold_x0(rc.dump(h))
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+        assert np.abs(want - fold_x0(plain.dump(h))).max() > 1e-2 * np.abs(want).max()   # the weights act
+    engine.recon_end()
+
+
 def test_likelihood_blurred_insertion(engine, oracle):
     """reconstruct3d answer 34 (frealign.py:1772,1817): fan of 21 in-plane rotations weighted by likelihood
     (pyp_b200/blur.py, SEMANTICS.md §8b).  The accumulators equal the oracle's insertion of every fan member
