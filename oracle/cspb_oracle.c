@@ -98,6 +98,12 @@ void orc_fft2_r2c(const float *img, int n, float *out_c) {
     free(d);
 }
 
+/* the 2-D transforms of the particle preprocessing and of the insertion go through these hooks: cspb_oracle_fast.c points
+ * them at its single-precision iterative FFT for the optimised CPU leg; everything else keeps the double-precision ones */
+static void (*g_fft2_r2c)(const float *, int, float *) = orc_fft2_r2c;
+void orc_fft2_c2r(const float *in_c, int n, float *out);
+static void (*g_fft2_c2r)(const float *, int, float *) = orc_fft2_c2r;
+
 void orc_fft2_c2r(const float *in_c, int n, float *out) {
     const int nh = n / 2 + 1;
     cd *d = (cd *)malloc(sizeof(cd) * (size_t)n * n);
@@ -362,7 +368,7 @@ void orc_prepare_image(const float *img, const orc_refine_cfg *cfg, const float 
     const int n = cfg->box, nh = n / 2 + 1;
     float *tmp = (float *)malloc(sizeof(float) * (size_t)n * n);
     normalized_copy(img, n, cfg->mask_radius / cfg->pixel_size, cfg->normalize, cfg->invert_contrast, tmp);
-    orc_fft2_r2c(tmp, n, spec);
+    g_fft2_r2c(tmp, n, spec);
     const int whiten = cfg->whiten && noise_curve;
     if (whiten)
         for (int jj = 0; jj < n; ++jj)
@@ -374,7 +380,7 @@ void orc_prepare_image(const float *img, const orc_refine_cfg *cfg, const float 
                 spec[2 * ((size_t)jj * nh + i) + 1] *= w;
             }
     if (cfg->apply_mask) {
-        orc_fft2_c2r(spec, n, tmp);
+        g_fft2_c2r(spec, n, tmp);
         const float rad = cfg->mask_radius / cfg->pixel_size, wid = 20.f / cfg->pixel_size;
         const float sc = 1.f / ((float)n * (float)n);
         for (int y = 0; y < n; ++y)
@@ -382,7 +388,7 @@ void orc_prepare_image(const float *img, const orc_refine_cfg *cfg, const float 
                 const float r = sqrtf((float)((x - n / 2) * (x - n / 2) + (y - n / 2) * (y - n / 2)));
                 tmp[y * n + x] *= sc * cos_edge(r, rad, wid);
             }
-        orc_fft2_r2c(tmp, n, spec);
+        g_fft2_r2c(tmp, n, spec);
     }
     for (int jj = 0; jj < n; ++jj)
         for (int i = 0; i < nh; ++i) {
@@ -1533,7 +1539,7 @@ void orc_recon_insert_weighted(orc_recon *rc, const float *imgs, const orc_row *
         const orc_row *row = &rows[k];
         if (!(row->occupancy > 0.f) || row->score < c->score_threshold) continue;
         normalized_copy(imgs + (size_t)k * n * n, n, c->mask_radius / c->pixel_size, c->normalize, c->invert_contrast, tmp);
-        orc_fft2_r2c(tmp, n, spec);
+        g_fft2_r2c(tmp, n, spec);
         const ctfc cc = ctf_make(row, n);
         float m[9];
         orc_euler_matrix(row->psi, row->theta, row->phi, m);

@@ -169,6 +169,13 @@ void orc_recon_finalize(orc_recon *rc, float molecular_mass_kda, float outer_rad
 /* FSC curve between two real n^3 volumes (n/2+1 shells, nearest-integer shells) */
 void orc_fsc(const float *a, const float *b, int n, float *fsc_out);
 
+/* ---- optimised CPU leg (cspb_oracle_fast.c): the same algorithms, production-style; results equal the functions above */
+long long orc_refine_local_fast(const orc_ref *r, const float *specs, orc_row *rows, int n_img, const orc_refine_cfg *cfg);
+void orc_recon_insert_fast(orc_recon *rc, const float *imgs, const orc_row *rows, int count, const float *sym, int n_sym, int finish);
+void orc_recon_finish_fast(orc_recon *rc);
+void orc_recon_discard_fast(orc_recon *rc);
+void orc_prepare_image_fast(const float *img, const orc_refine_cfg *cfg, const float *noise_curve, const float *ring_weights, float *spec);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,9 +124,14 @@ def lib():
             "orc_project": (None, [vp, f, f, f, f, vp]),
             "orc_noise_curve": (None, [vp, i, C.POINTER(RefineCfg), vp]),
             "orc_prepare_image": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
+            "orc_prepare_image_fast": (None, [vp, C.POINTER(RefineCfg), vp, vp, vp]),
             "orc_score": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp]),
             "orc_score_grad": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp, vp, vp, vp]),
             "orc_score_grad_cut": (f, [vp, vp, vp, vp, C.POINTER(RefineCfg), vp, vp, vp, vp, i]),
+            "orc_refine_local_fast": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
+            "orc_recon_insert_fast": (None, [vp, vp, vp, i, vp, i, i]),
+            "orc_recon_finish_fast": (None, [vp]),
+            "orc_recon_discard_fast": (None, [vp]),
             "orc_refine_local": (C.c_longlong, [vp, vp, vp, i, C.POINTER(RefineCfg)]),
             "orc_normalize": (None, [vp, i, f, i, i, vp]),
             "orc_phase_sum": (None, [vp, vp, vp, i, C.POINTER(RefineCfg), vp]),
@@ -223,14 +228,16 @@ def noise_curve(imgs, cfg):
     return out
 
 
-def prepare_images(imgs, cfg, curve=None, ring_weights=None):
+def prepare_images(imgs, cfg, curve=None, ring_weights=None, fast=False):
+    """fast=True: the optimised CPU leg's single-precision transforms (cspb_oracle_fast.c), results equal to ~1e-6."""
     imgs = _f32(imgs)
     n = cfg.box
     out = np.zeros((imgs.shape[0], n, n // 2 + 1), dtype=np.complex64)
     curve = None if curve is None else _f32(curve)
     rw = None if ring_weights is None else _f32(ring_weights)
+    fn = lib().orc_prepare_image_fast if fast else lib().orc_prepare_image
     for k in range(imgs.shape[0]):
-        lib().orc_prepare_image(_p(imgs[k]), C.byref(cfg), _p(curve), _p(rw), C.c_void_p(out[k].ctypes.data))
+        fn(_p(imgs[k]), C.byref(cfg), _p(curve), _p(rw), C.c_void_p(out[k].ctypes.data))
     return out
 
 
@@ -290,6 +297,14 @@ def refine_local(ref, specs, rows, cfg):
     return rows, int(ne)
 
 
+def refine_local_fast(ref, specs, rows, cfg):
+    """refine_local through the optimised CPU leg (cspb_oracle_fast.c): same algorithm, same results."""
+    specs = np.ascontiguousarray(specs, dtype=np.complex64)
+    rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
+    ne = lib().orc_refine_local_fast(ref._h, _p(specs), _p(rows), rows.size, C.byref(cfg))
+    return rows, int(ne)
+
+
 def global_search(ref, specs, rows, cfg, angles3):
     specs = np.ascontiguousarray(specs, dtype=np.complex64)
     rows = np.array(rows, dtype=ROW_DTYPE, copy=True)
@@ -330,6 +345,7 @@ class Recon:
 
     def __del__(self):
         if getattr(self, "_h", None):
+            lib().orc_recon_finish_fast(self._h)  # releases a pending raw accumulator pair of insert_fast
             lib().orc_recon_free(self._h)
             self._h = None
 
@@ -340,6 +356,20 @@ class Recon:
         sym = None if sym is None else _f32(sym)
         aux = None if aux is None else _f32(aux).reshape(rows.size, 2)
         lib().orc_recon_insert_weighted(self._h, _p(imgs), _p(rows), rows.size, _p(sym), 0 if sym is None else sym.shape[0], _p(aux))
+
+    def insert_fast(self, imgs, rows, sym=None, finish=True):
+        """insert through the optimised CPU leg: only the coset representatives of the lattice-preserving symmetry
+        subgroup are inserted per sample; `finish` (or finish_fast later) applies the lattice operators once to the sums."""
+        imgs = _f32(imgs)
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        sym = None if sym is None else _f32(sym)
+        lib().orc_recon_insert_fast(self._h, _p(imgs), _p(rows), rows.size, _p(sym), 0 if sym is None else sym.shape[0], 1 if finish else 0)
+
+    def finish_fast(self):
+        lib().orc_recon_finish_fast(self._h)
+
+    def discard_fast(self):
+        lib().orc_recon_discard_fast(self._h)
 
     def dump(self, half):
         npad = self.cfg.box * self.cfg.pad

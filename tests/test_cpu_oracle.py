@@ -325,3 +325,32 @@ def test_normalisation_matches_reference_normalize_image(oracle):
     assert np.array_equal(oracle.normalize(img, 30.0), oracle.normalize(img, 100.0))
     assert np.array_equal(oracle.normalize(img, 12.0, invert=1), -oracle.normalize(img, 12.0))
     assert np.array_equal(oracle.normalize(img, 12.0, normalize=0), img)
+
+
+def test_optimised_cpu_leg_equals_the_restatement(oracle):
+    """oracle/cspb_oracle_fast.c (the CPU arm bench.py times: band list, CTF once per particle, cropped reference,
+    single-precision iterative FFT, lattice symmetry applied once to the sums) gives the results of cspb_oracle.c."""
+    from pyp_b200.symmetry import symmetry_matrices
+    from test_gpu_parity import fold_x0
+
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=24, snr=0.3)
+    cfg = _cfg(oracle, n, px)
+    curve = oracle.noise_curve(stack, cfg)
+    a = oracle.prepare_images(stack, cfg, curve)
+    b = oracle.prepare_images(stack, cfg, curve, fast=True)
+    assert np.abs(a - b).max() <= 3e-6 * np.abs(a).max()
+    ref = oracle.Reference(vol, 1)
+    start = synth.perturb_rows(rows, 2.0, 1.0).astype(oracle.ROW_DTYPE)
+    r1, e1 = oracle.refine_local(ref, a, start, cfg)
+    r2, e2 = oracle.refine_local_fast(ref, a, start, cfg)
+    assert e1 == e2 and angular_distance(r1, r2).max() < 0.05 and np.abs(r1["score"] - r2["score"]).max() <= 2e-4 * r1["score"].max()
+    rcfg = oracle.ReconCfg(box=n, pad=1, pixel_size=px, mask_radius=px * n / 2, resolution_limit=2 * px, score_bfactor=2.0, normalize=1)
+    for sym in ("O", "D2", "I"):
+        mats = symmetry_matrices(sym)
+        x, y = oracle.Recon(rcfg), oracle.Recon(rcfg)
+        x.insert(stack[:8], rows[:8].astype(oracle.ROW_DTYPE), mats)
+        y.insert_fast(stack[:8], rows[:8].astype(oracle.ROW_DTYPE), mats)
+        for h in (0, 1):
+            d = fold_x0(x.dump(h))
+            assert np.abs(d - fold_x0(y.dump(h))).max() <= 2e-5 * np.abs(d).max(), sym
