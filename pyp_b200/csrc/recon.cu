@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     }
 }
 
-// ---- pull-based insertion (default): one RED per touched voxel instead of eight per sample.
+// ---- pull-based insertion (CSPB_INSERT=pull; NOT the default, see cspb_recon_insert_weighted): one RED per touched voxel
+// instead of eight per sample.
 // A central slice is a plane through the lattice: seen along its dominant axis w (the largest component of the plane
 // normal) it is a height field over the (u, v) lattice, and every (u, v) column receives weight on at most six
 // consecutive w levels around the plane.  One CTA owns a 16 x 16 tile of columns of one (projection, operator) plane:
@@ -616,8 +617,12 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         // one launch, ordered by half (see insert_kernel): the voxels one half touches (a half-sphere of radius np/2,
         // 16 B each) fit in L2 and the vector atomics do not spill to HBM
         prof_begin(ctx, CSPB_PROF_INSERT, (int64_t)cnt * ctx->n_lit);
-        static const bool push = getenv("CSPB_INSERT") && !strcmp(getenv("CSPB_INSERT"), "push");  // the per-sample 8-RED kernel, for A/B runs
-        if (push) {
+        // default: the per-sample kernel (8 vector REDs per sample).  CSPB_INSERT=pull selects the pull-based kernel below for
+        // A/B runs: it issues ~3x fewer L2 atomics but measured 2.3x SLOWER (r02k: 67.9 vs 29.2 ms per 32 768 particles) — the
+        // staging redundancy (every sample is prepared by ~2.7 tiles), the candidate walks and the rejected tiles cost more
+        // than the atomics they save; profiles/r02_notes.md
+        static const bool pull = getenv("CSPB_INSERT") && !strcmp(getenv("CSPB_INSERT"), "pull");
+        if (!pull) {
             insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
         } else {
             const int rb = (int)ceilf(rmax * (float)c.pad) + 1;        // columns -rb .. rb hold every trilinear footprint
