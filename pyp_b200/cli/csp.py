@@ -9,6 +9,10 @@ driver re-saves right before every mode (src/pyp/align/core.py:1055); the refere
 
 Modes (align/core.py:1015-1023 after the mapping at local_run.py:332-335,411-431):
   -2  extract particles first..last from the tilt series `images` into `stack`
+   3 with flag 0 and a frame list as `images`: frame (movie) refinement of the projections of particles first..last
+      (run_frame_shifts); every other mode with a frame list runs as below on the stack — the patch-based region commands
+      of local_run.py:337-404 hand region parameter files with mapped modes, refine_frames as flag and last = -1 for all
+      micrographs of the patch
    0/3/6  tilt angle+axis / tilt shifts / both, for TIND first..last (last = -1: all)
    1/2/5  particle angles / shifts / both, for PIND first..last
    4  per-tilt defocus offset
@@ -190,6 +194,53 @@ def run_refine(par, ext, mode, first, last, stack, config, out, session=None):
               f"{n_evals} projections scored in {dt:.2f} s\n")
 
 
+def run_frame_shifts(par, ext, first, last, stack, config, out, session=None):
+    """Frame (movie) refinement as pyp drives it without patches: `csp <par> <ext> 3 <p> <p> 0 frames_csp.txt <stack>`, one
+    particle per process (local_run.py:434-439).  The stack then holds one projection per (particle, tilt, frame) and the
+    rows carry FIND and FSHIFT_X/Y.  Ours (SEMANTICS.md §11, the closed binary's model is not public): for the rows of
+    particles first..last every projection's in-plane shift is refined on the scorer with the angles held (the local
+    optimiser of §7c restricted to x, y) within +-csp_ToleranceMicrographShifts of its input; the shift found goes to
+    X_SHIFT / Y_SHIFT and its change is added to FSHIFT_X / FSHIFT_Y.  Tables of the extended file are untouched."""
+    from .session import Session
+
+    session = session or Session()
+    t0 = time.time()
+    rows_all = cistem.read_parameters(par)
+    idx = entity_rows(rows_all, None, None, 5, first, last)
+    out_par, out_ext = out_paths(par, first, last)
+    if idx.size == 0:
+        out.write(f"csp: no projections of particles {first}..{last}; no output written\n")
+        return
+    rows = rows_all[idx]
+    rows = rows[np.argsort(rows["position_in_stack"], kind="stable")]
+    hdr = mrc.read_header(stack)
+    box, pixel = hdr["nx"], float(rows["pixel_size"][0])
+    ref_path = reference_path(config)
+    eng = session.engine(first + 1, max(1, last - first + 1))
+    cfg = refine_cfg_from(config, box, pixel)
+    cfg.refine_psi = cfg.refine_theta = cfg.refine_phi = 0
+    cfg.refine_x = cfg.refine_y = 1
+    eng.ensure_reference(cfg, ref_path, lambda: mrc.read(ref_path)[1])
+    pos = rows["position_in_stack"].astype(np.int64)
+    if pos.min() < 1 or pos.max() > hdr["nz"]:
+        raise ValueError(f"POSITION_IN_STACK {pos.min()}..{pos.max()} outside the stack (1..{hdr['nz']})")
+    for s in range(0, rows.size, 16384):
+        eng.load_images(session.images(stack, pos[s:s + 16384]), append=s > 0)
+    refined, _, n_evals = eng.refine(rows)
+    session.release()
+    tol = float(config["csp_ToleranceMicrographShifts"])
+    new = refined.copy()
+    for k, f in (("x_shift", "fshift_x"), ("y_shift", "fshift_y")):
+        d = np.clip(refined[k] - rows[k], -tol, tol)
+        new[k] = rows[k] + d
+        new[f] = rows[f] + d
+    cistem.write_parameters(out_par, new)
+    p_tab, t_tab = cistem.read_extended(ext)
+    cistem.write_extended(out_ext, p_tab[:0], t_tab[:0])
+    out.write(f"frame shifts: particles {first}..{last}, {rows.size} projections (frames), tolerance {tol:g} A\n")
+    out.write(f"mean score {float(rows['score'].mean()):.4f} -> {float(new['score'].mean()):.4f}, {n_evals} projections scored in {time.time() - t0:.2f} s\n")
+
+
 def parse_argv(argv):
     """The eight arguments pyp hands over (src/pyp/system/local_run.py:306-467 create_csp_split_commands):
     parameter file, extended file, mode, first, last, flag (extract_frame / refine_frames), images, stack."""
@@ -206,13 +257,17 @@ def main(argv=None, out=sys.stdout, session=None):
         a = parse_argv(argv)
         par, ext, mode, first, last, images, stack = a["par"], a["ext"], a["mode"], a["first"], a["last"], a["images"], a["stack"]
         out.write(banner("CSP"))
-        if images.endswith(".txt"):
-            # `images` = frames_csp.txt: per-frame (movie) refinement, local_run.py:337-404,434-439 — not built;
-            # fail loudly instead of treating the frame list as a tilt series
-            raise PromptError("csp: frame (movie) refinement (images = a frame list) is not implemented in cspb200")
+        frames = images.endswith(".txt")  # `images` = frames_csp.txt: frame (movie) refinement, local_run.py:320-323
         config = load_config()
         if mode == -1:
             pass
+        elif frames and mode == -2:
+            # cutting boxes out of movie frames needs the frame files behind the list, whose layout only the closed
+            # binary knows: fail loudly instead of treating the list as a tilt series
+            raise PromptError("csp: extraction (mode -2) from a frame list is not implemented in cspb200")
+        elif frames and mode == 3 and a["flag"] == 0:
+            # global frame refinement, one particle per process (local_run.py:434-439)
+            run_frame_shifts(par, ext, first, last, stack, config, out, session)
         elif mode == -2:
             run_extract(par, mode, first, last, images, stack, config, out, session)
         elif mode in (0, 1, 2, 3, 4, 5, 6):

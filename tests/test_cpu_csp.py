@@ -210,17 +210,21 @@ def test_defocus_offset_matches_reference():
         cg.defocus_offset_from_center(P[0], g[0, 3:6], 0.0, 0.0, handedness=0)
 
 
-def test_csp_cli_refuses_frame_lists(capsys):
-    """Frame (movie) refinement hands `frames_csp.txt` as the images argument (local_run.py:434-439): not built —
-    the front-end must fail loudly with the token pyp greps for (particle_cspt.py:1663), not run a tilt mode."""
+def test_csp_cli_frame_lists(capsys):
+    """Frame (movie) refinement hands `frames_csp.txt` as the images argument (local_run.py:320-323,434-439).  Extraction from a
+    frame list is refused loudly with the token pyp greps for (particle_cspt.py:1663); refinement modes run on the stack
+    (a missing parameter file is then the first error, not the frame list)."""
     import io
 
     from pyp_b200.cli import csp
 
     out = io.StringIO()
-    rc = csp.main(["a.cistem", "a_extended.cistem", "3", "0", "0", "0", "frames_csp.txt", "stack.mrc"], out=out)
+    rc = csp.main(["a.cistem", "a_extended.cistem", "-2", "0", "0", "0", "frames_csp.txt", "stack.mrc"], out=out)
     assert rc == 1 and "PYP (cspswarm) failed" in out.getvalue()
     assert "not implemented" in capsys.readouterr().err
+    out = io.StringIO()
+    rc = csp.main(["a.cistem", "a_extended.cistem", "3", "0", "0", "0", "frames_csp.txt", "stack.mrc"], out=out)
+    assert rc == 1 and "a.cistem" in capsys.readouterr().err   # reached the files: the frame list itself is accepted
     rc = csp.main(["too", "few"], out=io.StringIO())
     assert rc == 1
 
@@ -253,6 +257,6 @@ def test_csp_argv_as_the_reference_builds_it():
         assert covered == list(range(n))                       # contiguous inclusive ranges over particles / tilts
         assert cmds[0].endswith("_csp_000000_%06d.log" % csp.parse_argv(shlex.split(cmds[0].split(" > ")[0])[1:])["last"])
         assert all(c.endswith("> /dev/null") for c in cmds[1:])   # only the first range logs (local_run.py:447)
-    # the frame-list command is refused loudly (not built)
+    # the frame-list command is parsed like the others (mode 3, flag 0: run_frame_shifts); here its files do not exist
     argv = shlex.split(g["frames"]["commands"][0].split(" > ")[0])[1:]
     assert csp.main(argv, out=io.StringIO()) == 1

@@ -164,6 +164,29 @@ def test_csp_cli_extract_and_refine(tmp_path):
     p6, t6 = cistem.read_extended(f"{d}/frealign/maps/ts_r01_02_000002_000002_extended.cistem")
     assert p6.size == 0 and t6.size == 1 and int(t6["tind"][0]) == 2 and set(r6["tind"]) == {2} and r6.size == n_part
     assert abs(t6["angle"][0] - tilts["angle"][2]) <= 1.5 + 1e-4  # csp_ToleranceMicrographTiltAngles
+    # frame (movie) refinement as pyp drives it without patches (local_run.py:434-439): mode 3, flag 0, a frame list as
+    # `images`, one particle per process — the in-plane shift of every projection (frame) of the particle is refined
+    frames = rows.copy()                                   # true poses; every projection displaced by a known per-frame drift
+    rng = np.random.default_rng(3)
+    drift = rng.uniform(-2.5, 2.5, (rows.size, 2)).astype(np.float32)
+    frames["x_shift"] += drift[:, 0]
+    frames["y_shift"] += drift[:, 1]
+    frames["find"] = frames["tind"]
+    cistem.write_parameters(f"{d}/{par}", frames)
+    cistem.write_extended(f"{d}/{ext}", particles, tilts)
+    open(f"{d}/frames_csp.txt", "w").write("frame_000.mrc\n")
+    assert csp(par, ext, 3, 1, 1, 0, "frames_csp.txt", "frealign/ts_stack.mrc", log="frames.log") == 0
+    assert "frame shifts: particles 1..1" in open(f"{d}/frames.log").read()
+    rf = cistem.read_parameters(f"{d}/frealign/maps/ts_r01_02_000001_000001.cistem")
+    pf, tf = cistem.read_extended(f"{d}/frealign/maps/ts_r01_02_000001_000001_extended.cistem")
+    assert pf.size == 0 and tf.size == 0 and set(rf["pind"]) == {1} and rf.size == tilts.size
+    sel = rows["pind"] == 1
+    err0 = np.hypot(frames["x_shift"][sel] - rows["x_shift"][sel], frames["y_shift"][sel] - rows["y_shift"][sel])
+    err1 = np.hypot(rf["x_shift"] - rows["x_shift"][sel], rf["y_shift"] - rows["y_shift"][sel])
+    assert err1.mean() < 0.5 * err0.mean()                                           # the drift is taken out
+    assert np.allclose(rf["fshift_x"], rf["x_shift"] - frames["x_shift"][sel], atol=1e-4)   # and recorded in FSHIFT_X / Y
+    assert np.allclose(rf["psi"], frames["psi"][sel]) and (rf["score"] >= 0).all()
+    assert csp(par, ext, -2, 0, 0, 0, "frames_csp.txt", "frealign/x.mrc", log="bad_frames.log") != 0   # extraction from frames: refused
     # an unknown mode fails loudly with pyp's failure token
     assert csp(par, ext, 9, 0, 0, 1, "frealign/ts.mrc", "frealign/ts_stack.mrc", log="bad.log") != 0
     assert "PYP (cspswarm) failed" in open(f"{d}/bad.log").read()
