@@ -190,6 +190,10 @@ int cspb_refine_score_poses(cspb_ctx *ctx, const cspb_row *rows, int n_rows,
  * x, y per Angstrom), d B / d angles, the 15 entries of the upper triangle of J^T J, 0}.  ring_cut > 0 restricts the
  * sums to the rings <= ring_cut (coarse-to-fine stages); 0 = the whole band. */
 int cspb_refine_score_grad(cspb_ctx *ctx, const cspb_row *rows, int n, int ring_cut, float *out28);
+/* Matching projections (refine3d answers 8 and 43, `<name>_match.mrc_<first>_<last>`, frealign.py:3929-3931): for every
+ * row the CTF-multiplied projection of the reference at the row's pose, displaced by the row's shift into the frame of
+ * the particle image, band limited at the scoring limit; out_images = n_rows * box * box floats (host). */
+int cspb_refine_matching_projections(cspb_ctx *ctx, const cspb_row *rows, int n_rows, float *out_images);
 
 /* Orientation grid of the global search (prompt 36/25): n_orient x {psi, theta, phi} degrees.
  * The host builds it from the angular step and the symmetry symbol (pyp_b200/search_grid.py),

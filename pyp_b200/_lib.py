@@ -128,6 +128,7 @@ _SIGNATURES = {
     "cspb_refine_score": (_i, [_vp, _vp, _i, _vp]),
     "cspb_refine_score_poses": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
     "cspb_refine_score_grad": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cspb_refine_matching_projections": (_i, [_vp, _vp, _i, _vp]),
     "cspb_refine_set_search_grid": (_i, [_vp, _vp, _i]),
     "cspb_refine_run": (_i, [_vp, _vp, _i, _vp, C.POINTER(_i64)]),
     "cspb_refine_run_device": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),

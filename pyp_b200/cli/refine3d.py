@@ -165,6 +165,8 @@ def run(p, out=sys.stdout, session=None):
     if rows.size:  # no zero-row files: the reference's reader rejects an empty payload (cistem_star_file.py:694-776)
         cistem.write_parameters(p["out_parameters"], refined)
         cistem.write_parameters(p["out_changes"], changes)
+        if p["calc_matching"]:  # answers 8 / 43: `<name>_match.mrc_<range>`, one matching projection per refined row
+            mrc.write(p["matching_out"], eng.matching_projections(refined), p["pixel_size"])
     dt = time.time() - t0
     out.write(banner("Refine3D"))
     out.write(f"\nRefining particles {first} to {last} ({rows.size} rows), box {box}, pixel {p['pixel_size']}\n")
@@ -176,6 +178,8 @@ def run(p, out=sys.stdout, session=None):
                   f"variance ({cfg.prior_var_x:.3f}, {cfg.prior_var_y:.3f}) A^2\n")
     if focus:
         out.write("LogP evaluated inside the 2-D focus mask: centre ({:.1f}, {:.1f}, {:.1f}) A, radius {:.1f} A\n".format(*p["mask_2d"]))
+    if p["calc_matching"] and rows.size:
+        out.write(f"Matching projections written to {p['matching_out']}\n")
     if reused:
         out.write("Reference transform reused from the resident engine\n")
     write_notes(out, "refine3d", ignored_answers(p))

@@ -1564,6 +1564,66 @@ __global__ void focus_logp_kernel(const float *__restrict__ real, int n, float p
     }
 }
 
+// matching projections (refine3d answers 8 / 43, frealign.py:3929-3931): the CTF-multiplied central slice at the pose of
+// every row, moved by the row's shift into the frame of the particle image, on the half plane up to the scoring limit
+__global__ void match_spectrum_kernel(const float4 *__restrict__ ref4, int sx, int sy, int rc, float padf, const CtfCoef *__restrict__ ctf,
+                                      const cspb_row *__restrict__ rows, int n, float r_hi, float inv_npx2, float2 *__restrict__ spec) {
+    __shared__ float m[9];
+    const int img = blockIdx.y, nh = n / 2 + 1;
+    const cspb_row row = rows[img];
+    if (threadIdx.x == 0) euler_matrix(row.psi, row.theta, row.phi, m);
+    __syncthreads();
+    const CtfCoef cc = ctf[img];
+    const float mx = row.x_shift * inv_npx2, my = row.y_shift * inv_npx2;
+    float2 *o = spec + (long long)img * n * nh;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * nh; idx += gridDim.x * blockDim.x) {
+        const int i = idx % nh;
+        int j = idx / nh;
+        if (j >= n / 2) j -= n;
+        float2 v = make_float2(0.f, 0.f);
+        const float fi = (float)i, fj = (float)j, r2 = fi * fi + fj * fj;
+        if (r2 <= r_hi * r_hi && j != -n / 2) {
+            const float2 P = gather_trilinear(ref4, sx, sy, rc, (m[0] * fi + m[1] * fj) * padf, (m[3] * fi + m[4] * fj) * padf,
+                                              (m[6] * fi + m[7] * fj) * padf);
+            const float cv = -sinpif(ctf_chi(cc, fi, fj, r2) * (1.f / CSPB_PI_F));
+            float sn, cs;
+            sincospif(fi * mx + fj * my, &sn, &cs);   // the image is moved by +shift onto the reference: the projection goes back by -shift
+            const float w = ((i + j) & 1) ? -cv : cv;  // centred phase origin -> image corner
+            v = make_float2(w * (P.x * cs + P.y * sn), w * (P.y * cs - P.x * sn));
+        }
+        o[idx] = v;
+    }
+}
+
+extern "C" int cspb_refine_matching_projections(cspb_ctx *ctx, const cspb_row *rows, int n_rows, float *out_images) {
+    CSPB_ENTER(ctx);
+    if (!ctx || !rows || !out_images || n_rows < 0) return CSPB_E_ARG;
+    if (!ctx->refine_ready || !ctx->ref.ready) return cspb_fail(ctx, CSPB_E_STATE, "configure + set_reference first");
+    if (n_rows == 0) return 0;
+    const cspb_refine_cfg &c = ctx->rcfg;
+    const int n = c.box, nh = n / 2 + 1;
+    int chunk = chunk_images(n, n_rows);
+    if (chunk > 2048) chunk = 2048;
+    RESERVE(ctx, ctx->d_work0, (size_t)chunk * n * n * sizeof(float));
+    RESERVE(ctx, ctx->d_work1, (size_t)chunk * n * nh * sizeof(float2));
+    for (int s = 0; s < n_rows; s += chunk) {
+        const int cnt = n_rows - s < chunk ? n_rows - s : chunk;
+        cspb_row *d_rows;
+        CtfCoef *d_ctf;
+        int rc = upload_rows(ctx, rows + s, cnt, &d_rows, &d_ctf);
+        if (rc) return rc;
+        dim3 grid(ceil_div(n * nh, 256) < 64 ? ceil_div(n * nh, 256) : 64, cnt);
+        match_spectrum_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->ref.d_ref4.as<float4>(), ctx->ref.sx, ctx->ref.sy, ctx->ref.rc, (float)ctx->ref.pad,
+                                                             d_ctf, d_rows, n, ctx->plan.r_hi, 2.f / ((float)n * c.pixel_size), ctx->d_work1.as<float2>());
+        KERNEL_CHECK(ctx);
+        rc = fft2_c2r_dev(ctx, ctx->d_work1.as<float2>(), ctx->d_work0.as<float>(), n, cnt, 1.f / ((float)n * (float)n));
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(out_images + (size_t)s * n * n, ctx->d_work0.p, (size_t)cnt * n * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
 static int focus_logp_enqueue(cspb_ctx *ctx, cspb_row *d_rows, CtfCoef *d_ctf, int n_img, cspb_row *d_changes) {
     const cspb_refine_cfg &c = ctx->rcfg;
     const int n = c.box, nh = n / 2 + 1, n_slots = ctx->plan.n_slots;

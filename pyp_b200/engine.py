@@ -234,6 +234,14 @@ class Engine:
         self._ck(self._l.cspb_refine_score_grad(self._h, ptr(rows), rows.size, int(ring_cut), ptr(out)))
         return out
 
+    def matching_projections(self, rows):
+        """CTF-multiplied projections of the reference at the poses of `rows`, in the frame of the particle images
+        (refine3d's `_match.mrc_<range>` stack): (n_rows, box, box) float32."""
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        out = np.zeros((rows.size, self.box, self.box), dtype=np.float32)
+        self._ck(self._l.cspb_refine_matching_projections(self._h, ptr(rows), rows.size, ptr(out)))
+        return out
+
     def set_search_grid(self, angles3):
         """Global-search orientation grid: (n, 3) array of (psi, theta, phi) in degrees."""
         a = np.ascontiguousarray(angles3, dtype=np.float32).reshape(-1, 3)

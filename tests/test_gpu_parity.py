@@ -290,6 +290,34 @@ def test_phase_sum_matches_oracle_and_gives_the_beam_tilt(engine, oracle):
     assert abs(f["beam_tilt_x"] - truth[0]) < 0.25 and abs(f["beam_tilt_y"] - truth[1]) < 0.25, f
 
 
+def test_matching_projections(engine, oracle):
+    """refine3d answers 8 / 43: CTF x central slice at the row's pose, displaced into the particle's frame — against the
+    oracle's slice and CTF put together with numpy, and against the noise-free particle it must resemble."""
+    from pyp_b200 import synth
+
+    n, px = 64, 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=6, snr=None)   # noise-free particles
+    cfg = refine_cfg(n, px)
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    engine.load_images(stack)
+    got = engine.matching_projections(rows)
+    ocfg = oracle.refine_cfg_from(cfg)
+    _, r_hi = oracle.band_limits(ocfg)
+    ref = oracle.Reference(vol, 1)
+    i = np.arange(n // 2 + 1)[None, :]
+    j = np.fft.fftfreq(n, 1.0 / n)[:, None]
+    for k, r in enumerate(rows):
+        P = ref.project(r["psi"], r["theta"], r["phi"], r_hi)
+        c = oracle.ctf_image(r.astype(oracle.ROW_DTYPE), n)
+        ph_ = np.exp(-2j * np.pi * (i * r["x_shift"] + j * r["y_shift"]) / (n * px))
+        spec = P * c * ph_ * np.where((i + j) % 2 == 0, 1.0, -1.0)
+        spec[n // 2, :] = 0
+        want = np.fft.irfft2(spec, s=(n, n))
+        assert np.abs(got[k] - want).max() <= 2e-4 * np.abs(want).max(), k
+        assert np.corrcoef(got[k].ravel(), stack[k].ravel())[0, 1] > 0.8   # band-limited copy of the particle itself
+
+
 def test_reconfigure_to_a_larger_box_reallocates_the_packed_images(engine, oracle):
     """Regression (r01h, tools/check_configs.py C1 -> C4): the packed-image buffer was sized in images of the
     previous band plan; a context reconfigured from a small box to a larger one with fewer images wrote
