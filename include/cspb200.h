@@ -286,6 +286,15 @@ int cspb_csp_compose(const cspb_particle *p, const cspb_particle *p0, const cspb
 int cspb_csp_extract(cspb_ctx *ctx, const float *images, int nx, int ny, int n_tilt, const cspb_row *rows,
                      int n_rows, int box_in, int bin, float *stack_out, int loc);
 
+/* SPA box cutting (src/pyp/extract/core.py:360-511, one micrograph): n boxes of edge `box` from image (ny rows of nx
+ * float32), box k starting at floor(coords_xy[2k + {0,1}] / coordinate_binning - floor(box / 2)) along x / y; a box that
+ * leaves the micrograph is padded with the mean of its inside part (the reference's clipping rule to the letter), a box
+ * entirely outside is zero, a constant box is replaced by reproducible unit white noise (image.py:461-471).  The particles
+ * are NOT normalised here — cspb_refine_load_images / cspb_recon_insert fuse normalize_image (image.py:320-417) into their
+ * first FFT pass — so with out_loc = CSPB_DEVICE the boxes go from the micrograph to the scorer without a stack on the host. */
+int cspb_spa_extract(cspb_ctx *ctx, const float *image, int nx, int ny, const float *coords_xy, int n, int box,
+                     float coordinate_binning, float *stack_out, int image_loc, int out_loc);
+
 /* ------------------------------------------------------------------ reconstruct3d
  * Replaces external/cistem2/reconstruct3d as driven by frealign.py:1780-1824
  * (SURVEY.md Appendix A.3). */

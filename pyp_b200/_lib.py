@@ -138,6 +138,7 @@ _SIGNATURES = {
     "cspb_csp_run": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, C.POINTER(CspCfg), _i, _i, C.POINTER(_i64)]),
     "cspb_csp_compose": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp]),
     "cspb_csp_extract": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i]),
+    "cspb_spa_extract": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _f, _vp, _i, _i]),
     "cspb_refine_reconstruct": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_i64)]),
     "cspb_select_cfg_default": (_i, [C.POINTER(SelectCfg)]),
     "cspb_select_scores": (_i, [_vp, _vp, _i, _vp, C.POINTER(SelectCfg), _i, C.POINTER(C.c_double)]),

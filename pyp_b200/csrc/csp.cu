@@ -662,3 +662,94 @@ extern "C" int cspb_csp_extract(cspb_ctx *ctx, const float *images, int nx, int 
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+
+// ================================================================== SPA particle extraction
+// Box cutting of src/pyp/extract/core.py:360-511 (extract_particles_non_mpi, one micrograph): the box of particle k starts
+// at floor(coord / coordinate_binning - floor(box / 2)) on both axes; a box that leaves the micrograph is padded with the
+// mean of its inside part, a box entirely outside is zero.  The reference's clipping is kept to the letter, including
+// its treatment of the upper edge: a box whose end reaches nx (maxX >= nx) loses its last line even when it fits exactly
+// (core.py:471-483).  Empty boxes (constant, or < 1 % of the pixels different from the median — approximated by "constant")
+// are replaced by unit white noise; the reference draws it from an unseeded generator (image.py:461-471), here it comes from
+// a counter-based hash of (particle, pixel) so that runs repeat.  Normalisation (image.py:320-417) is NOT done here: the
+// loader fuses it into the first FFT pass (fft.cu), so extraction -> normalisation -> FFT never writes a normalised stack.
+namespace {
+__device__ __forceinline__ float hash_normal(unsigned a, unsigned b) {
+    unsigned x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA6Bu;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    unsigned y = x * 0x9E3779B1u + 0x6A09E667u;
+    y ^= y >> 16; y *= 0x7FEB352Du; y ^= y >> 15; y *= 0x846CA68Bu; y ^= y >> 16;
+    const float u1 = ((float)(x >> 8) + 1.f) * (1.f / 16777217.f), u2 = (float)(y >> 8) * (1.f / 16777216.f);
+    return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__global__ void __launch_bounds__(256) spa_extract_kernel(const float *__restrict__ img, int nx, int ny, const float *__restrict__ xy, int box,
+                                                          float cbin, float *__restrict__ out) {
+    __shared__ float red[34];
+    __shared__ float s_lo, s_hi;
+    const int k = blockIdx.x;
+    float *o = out + (long long)k * box * box;
+    // reference names: X runs over the rows of the array (coordinate y), Y over its columns (coordinate x)
+    int minX = (int)floorf(xy[2 * k + 1] / cbin - floorf((float)box / 2.f)), minY = (int)floorf(xy[2 * k] / cbin - floorf((float)box / 2.f));
+    int maxX = minX + box, maxY = minY + box;
+    int minx = 0, miny = 0, maxx = box, maxy = box;
+    if (minX < 0) { minx = -minX; minX = 0; } else if (maxX >= ny) { maxx = box - (maxX - ny + 1); maxX = ny - 1; }
+    if (minY < 0) { miny = -minY; minY = 0; } else if (maxY >= nx) { maxy = box - (maxY - nx + 1); maxY = nx - 1; }
+    const int h = maxX - minX, w = maxY - minY;  // inside part as the reference slices it
+    const bool any = h > 0 && w > 0 && minX < ny && minY < nx;
+    float sum = 0.f, lo = INFINITY, hi = -INFINITY;
+    if (any)
+        for (int t = threadIdx.x; t < h * w; t += blockDim.x) {
+            const float v = __ldg(img + (long long)(minX + t / w) * nx + minY + t % w);
+            sum += v; lo = fminf(lo, v); hi = fmaxf(hi, v);
+        }
+    sum = block_sum(sum, red);
+    for (int q = 16; q > 0; q >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, q)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, q)); }
+    __shared__ float w_lo[8], w_hi[8];
+    if ((threadIdx.x & 31) == 0) { w_lo[threadIdx.x >> 5] = lo; w_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = w_lo[0], b = w_hi[0];
+        for (int q = 1; q < 8; ++q) { a = fminf(a, w_lo[q]); b = fmaxf(b, w_hi[q]); }
+        s_lo = a; s_hi = b;
+    }
+    __syncthreads();
+    const float fill = any ? sum / (float)(h * w) : 0.f;
+    // an empty frame (image.py:461-471: constant, or hardly any pixel off the median — taken here as "constant inside part")
+    const bool empty = any && s_lo == s_hi;
+    for (int t = threadIdx.x; t < box * box; t += blockDim.x) {
+        const int r = t / box, c = t % box;
+        float v = fill;
+        if (any && r >= minx && r < maxx && c >= miny && c < maxy) v = __ldg(img + (long long)(minX + r - minx) * nx + minY + c - miny);
+        if (empty) v = hash_normal((unsigned)k, (unsigned)t);
+        o[t] = v;
+    }
+}
+}  // namespace
+
+extern "C" int cspb_spa_extract(cspb_ctx *ctx, const float *image, int nx, int ny, const float *coords_xy, int n, int box,
+                                float coordinate_binning, float *stack_out, int image_loc, int out_loc) {
+    CSPB_ENTER(ctx);
+    if (!ctx || !image || !coords_xy || !stack_out || nx <= 0 || ny <= 0 || n < 0 || box <= 0 || !(coordinate_binning > 0.f)) return CSPB_E_ARG;
+    if (n == 0) return 0;
+    const size_t img_bytes = (size_t)nx * ny * sizeof(float), out_bytes = (size_t)n * box * box * sizeof(float);
+    DevBuf b_img, b_out, b_xy;
+    const float *d_img = image;
+    float *d_out = stack_out;
+    if (image_loc == CSPB_HOST) {
+        RESERVE(ctx, b_img, img_bytes);
+        CU_TRY(ctx, cudaMemcpyAsync(b_img.p, image, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_img = b_img.as<float>();
+    }
+    if (out_loc == CSPB_HOST) {
+        RESERVE(ctx, b_out, out_bytes);
+        d_out = b_out.as<float>();
+    }
+    RESERVE(ctx, b_xy, (size_t)n * 2 * sizeof(float));
+    CU_TRY(ctx, cudaMemcpyAsync(b_xy.p, coords_xy, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    spa_extract_kernel<<<n, 256, 0, ctx->stream>>>(d_img, nx, ny, b_xy.as<float>(), box, coordinate_binning, d_out);
+    KERNEL_CHECK(ctx);
+    if (out_loc == CSPB_HOST) CU_TRY(ctx, cudaMemcpyAsync(stack_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -350,13 +350,45 @@ class Engine:
 
     def csp_extract(self, images, rows, box_in, binning=1):
         """csp mode -2: cut (and bin) the particle boxes of `rows` out of a tilt series
-        (n_tilt, ny, nx) float32; returns the stack (n_rows, box_in/bin, box_in/bin)."""
+        (n_tilt, ny, nx) float32; returns the stack (n_rows, box_in/bin, box_in/bin).  With a CUDA tensor as `images`
+        the stack is returned as a CUDA tensor: tilt series -> boxes -> load_images without a stack on the host (the
+        54 GB stack of BASELINE configs[2] never has to exist)."""
+        if hasattr(images, "is_cuda") and images.is_cuda:
+            import torch
+
+            rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+            nt, ny, nx = (int(v) for v in images.shape)
+            bo = int(box_in) // int(binning)
+            out = torch.empty((rows.size, bo, bo), dtype=torch.float32, device=images.device)
+            torch.cuda.current_stream(images.device).synchronize()
+            self._ck(self._l.cspb_csp_extract(self._h, C.c_void_p(images.data_ptr()), nx, ny, nt, ptr(rows), rows.size, int(box_in), int(binning),
+                                              C.c_void_p(out.data_ptr()), DEVICE))
+            return out
         images = np.ascontiguousarray(images, dtype=np.float32)
         rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
         nt, ny, nx = images.shape
         bo = int(box_in) // int(binning)
         out = np.zeros((rows.size, bo, bo), dtype=np.float32)
         self._ck(self._l.cspb_csp_extract(self._h, ptr(images), nx, ny, nt, ptr(rows), rows.size, int(box_in), int(binning), ptr(out), HOST))
+        return out
+
+    def spa_extract(self, micrograph, coords_xy, box, coordinate_binning=1.0, to_device=False):
+        """Box cutting of extract_particles_non_mpi (extract/core.py:360-511) from one micrograph (ny, nx) float32 at the
+        (x, y) coordinates `coords_xy` (n, 2).  Returns the (n, box, box) stack — a CUDA tensor with `to_device` (the boxes
+        then go to load_images / recon_insert without ever existing on the host)."""
+        mic = np.ascontiguousarray(micrograph, dtype=np.float32)
+        xy = np.ascontiguousarray(coords_xy, dtype=np.float32).reshape(-1, 2)
+        ny, nx = mic.shape
+        n = xy.shape[0]
+        if to_device:
+            import torch
+
+            out = torch.empty((n, int(box), int(box)), dtype=torch.float32, device=torch.device("cuda", self.device))
+            torch.cuda.current_stream(out.device).synchronize()
+            self._ck(self._l.cspb_spa_extract(self._h, ptr(mic), nx, ny, ptr(xy), n, int(box), float(coordinate_binning), C.c_void_p(out.data_ptr()), HOST, DEVICE))
+            return out
+        out = np.zeros((n, int(box), int(box)), dtype=np.float32)
+        self._ck(self._l.cspb_spa_extract(self._h, ptr(mic), nx, ny, ptr(xy), n, int(box), float(coordinate_binning), ptr(out), HOST, HOST))
         return out
 
     # ------------------------------------------------------------------ reconstruct3d / merge3d
