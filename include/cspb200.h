@@ -388,6 +388,11 @@ int cspb_select_scores(cspb_ctx *ctx, cspb_row *rows, int n, const float *tilt_a
  * occ_out (K x n, percent) and sigma_out (n). */
 int cspb_class_occupancies(cspb_ctx *ctx, const float *logp, const float *sigma, const double *class_average_occ, int n_classes,
                            int n, float *occ_out, float *sigma_out, int loc);
+/* Data-driven dose weights: mean SCORE per scan-order index (TIND) over the projections with
+ * OCCUPANCY > 0, -1 where there is none — the content of pyp's global_weight.txt (src/pyp/inout/metadata/core.py:3039-3075)
+ * that reconstruct3d's prompt 22 reads, computed on the rows the scorer left on the device.  weights_out: n_idx doubles;
+ * *n_used_out = 1 + the largest index with projections (the length of the file). */
+int cspb_global_weights(cspb_ctx *ctx, const cspb_row *rows, int n, int loc, double *weights_out, int n_idx, int *n_used_out);
 /* refine3d -> score shaping -> reconstruct3d in one call over a HOST stack: every projection is uploaded once into a
  * resident device buffer and refined as its batch arrives (as cspb_refine_reconstruct); when all rows are refined the
  * selection runs on the device table and the whole stack is inserted with the shaped occupancies.  Needs

@@ -143,6 +143,7 @@ _SIGNATURES = {
     "cspb_select_cfg_default": (_i, [C.POINTER(SelectCfg)]),
     "cspb_select_scores": (_i, [_vp, _vp, _i, _vp, C.POINTER(SelectCfg), _i, C.POINTER(C.c_double)]),
     "cspb_class_occupancies": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i]),
+    "cspb_global_weights": (_i, [_vp, _vp, _i, _i, _vp, _i, C.POINTER(_i)]),
     "cspb_refine_select_reconstruct": (_i, [_vp, _vp, _vp, _i, C.POINTER(SelectCfg), C.POINTER(_i64), C.POINTER(C.c_double)]),
     "cspb_recon_cfg_default": (_i, [C.POINTER(ReconCfg), _i, _f]),
     "cspb_recon_begin": (_i, [_vp, C.POINTER(ReconCfg)]),

@@ -132,7 +132,53 @@ __global__ void occ_kernel(const float *__restrict__ logp, const float *__restri
     sig_out[k] = (float)sg;
 }
 
+// per scan-order index: float64 sum of the scores and count of the projections with OCCUPANCY > 0
+__global__ void weights_kernel(const cspb_row *__restrict__ rows, int n, int n_idx, double *__restrict__ sums, int *__restrict__ cnt) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cspb_row r = rows[k];
+    if (!(r.occupancy > 0.f) || r.tind < 0 || r.tind >= n_idx) return;
+    atomicAdd(sums + r.tind, (double)r.score);
+    atomicAdd(cnt + r.tind, 1);
+}
+
 }  // namespace
+
+// Data-driven dose weights: mean SCORE per scan-order index (TIND) over the projections with
+// OCCUPANCY > 0, -1 where none — what pyp's compute_global_weights writes to global_weight.txt
+// (src/pyp/inout/metadata/core.py:3039-3075) for reconstruct3d's prompt 22, here on the device-resident rows the scorer
+// just produced.  weights_out: n_idx doubles; *n_used_out = 1 + the largest index that has projections (the file's length).
+extern "C" int cspb_global_weights(cspb_ctx *ctx, const cspb_row *rows, int n, int loc, double *weights_out, int n_idx, int *n_used_out) {
+    CSPB_ENTER(ctx);
+    if (!ctx || !rows || !weights_out || n < 0 || n_idx <= 0) return CSPB_E_ARG;
+    const cspb_row *d_rows = rows;
+    DevBuf b_rows, b_sums, b_cnt;
+    if (loc == CSPB_HOST && n > 0) {
+        RESERVE(ctx, b_rows, (size_t)n * sizeof(cspb_row));
+        CU_TRY(ctx, cudaMemcpyAsync(b_rows.p, rows, (size_t)n * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
+        d_rows = b_rows.as<cspb_row>();
+    }
+    RESERVE(ctx, b_sums, (size_t)n_idx * sizeof(double));
+    RESERVE(ctx, b_cnt, (size_t)n_idx * sizeof(int));
+    CU_TRY(ctx, cudaMemsetAsync(b_sums.p, 0, (size_t)n_idx * sizeof(double), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(b_cnt.p, 0, (size_t)n_idx * sizeof(int), ctx->stream));
+    if (n > 0) {
+        weights_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_rows, n, n_idx, b_sums.as<double>(), b_cnt.as<int>());
+        KERNEL_CHECK(ctx);
+    }
+    std::vector<double> hs(n_idx);
+    std::vector<int> hc(n_idx);
+    CU_TRY(ctx, cudaMemcpyAsync(hs.data(), b_sums.p, (size_t)n_idx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(hc.data(), b_cnt.p, (size_t)n_idx * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int used = 0;
+    for (int t = 0; t < n_idx; ++t) {
+        weights_out[t] = hc[t] > 0 ? hs[t] / (double)hc[t] : -1.0;
+        if (hc[t] > 0) used = t + 1;
+    }
+    if (n_used_out) *n_used_out = used;
+    return 0;
+}
 
 extern "C" int cspb_select_cfg_default(cspb_select_cfg *c) {
     if (!c) return CSPB_E_ARG;

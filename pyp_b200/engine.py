@@ -304,6 +304,15 @@ class Engine:
         self._ck(self._l.cspb_class_occupancies(self._h, ptr(logp), ptr(sigma), ptr(avg), K, n, ptr(occ), ptr(sg), HOST))
         return occ, sg
 
+    def global_weights(self, rows, n_idx=None):
+        """Mean SCORE per scan-order index over the projections with occupancy > 0, -1 where none (pyp's global_weight.txt,
+        inout/metadata/core.py:3039-3075) — on the device; equals tables.global_weights."""
+        rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+        n_idx = int(n_idx or (int(rows["tind"].max()) + 1 if rows.size else 1))
+        out, used = np.zeros(n_idx, dtype=np.float64), C.c_int(0)
+        self._ck(self._l.cspb_global_weights(self._h, ptr(rows), rows.size, HOST, ptr(out), n_idx, C.byref(used)))
+        return out[: used.value]
+
     def refine_select_reconstruct(self, images, rows, cfg: SelectCfg):
         """refine3d -> score shaping -> reconstruct3d insertion over a host stack without leaving the device.
         Returns (refined + shaped rows, n_evals, threshold)."""

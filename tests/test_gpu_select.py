@@ -81,6 +81,19 @@ def test_device_class_occupancies(engine):
     assert np.allclose(occ.sum(axis=0), 100.0, atol=1e-3)
 
 
+def test_device_global_weights_equal_the_reference_file(engine, tmp_path):
+    """Dose weights per scan-order index on the device == tables.global_weights == the reference's global_weight.txt."""
+    from pyp_b200 import tables
+
+    rows = cistem.read_parameters(os.path.join(G, "tables_weights_in.cistem"))
+    w = engine.global_weights(rows)
+    assert np.array_equal(w, tables.global_weights(rows))
+    out = str(tmp_path / "global_weight.txt")
+    tables.write_global_weights(out, w)
+    assert open(out).read() == open(os.path.join(G, "tables_global_weight.txt")).read()
+    assert engine.global_weights(rows[:0]).size == 0
+
+
 def test_refine_select_reconstruct_in_one_call(engine):
     """cspb_refine_select_reconstruct == refine3d -> shape_phase_residuals on the host -> reconstruct3d."""
     n, px = 64, 1.35
