@@ -75,7 +75,15 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
         s_ctf = make_ctf_coef(row.defocus_1, row.defocus_2, row.defocus_angle, row.phase_shift, row.pixel_size,
                               row.voltage_kv, row.cs_mm, row.amplitude_contrast, n);
     __syncthreads();
-    const int idx = tile * blockDim.x + threadIdx.x;
+#ifndef CSPB_INSERT_PAIR
+#define CSPB_INSERT_PAIR 1
+#endif
+    // CSPB_INSERT_PAIR: two lanes per sample, lane parity = the x corner (x0 / x0 + 1).  The two float4 accumulator cells of an
+    // x pair are neighbours in memory: when x0 is even they share a 32-byte sector, and issued by adjacent lanes of ONE RED
+    // instruction they reach the L2 as one sector operation instead of two (the kernel is L2-atomic bound: one sector per
+    // RED without pairing, r01 ncu).  The per-sample arithmetic is done twice; the atomics per lane halve.
+    const int lane_dx = CSPB_INSERT_PAIR ? (threadIdx.x & 1) : 0;
+    const int idx = CSPB_INSERT_PAIR ? tile * (blockDim.x >> 1) + (threadIdx.x >> 1) : tile * blockDim.x + threadIdx.x;
     if (idx >= n * nh) return;
     const int i = idx % nh;
     int j = idx / nh;
@@ -110,14 +118,23 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
         const float fx = x - x0f, fy = y - y0f, fz = z - z0f;
         const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
         const float wx0 = 1.f - fx, wy0 = 1.f - fy, wz0 = 1.f - fz;
-        add_corner(acc, A.np, A.xh, x0, y0, z0, w * wx0 * wy0 * wz0, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0 + 1, y0, z0, w * fx * wy0 * wz0, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0, y0 + 1, z0, w * wx0 * fy * wz0, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0 + 1, y0 + 1, z0, w * fx * fy * wz0, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0, y0, z0 + 1, w * wx0 * wy0 * fz, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0 + 1, y0, z0 + 1, w * fx * wy0 * fz, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0, y0 + 1, z0 + 1, w * wx0 * fy * fz, re, vim, wt);
-        add_corner(acc, A.np, A.xh, x0 + 1, y0 + 1, z0 + 1, w * fx * fy * fz, re, vim, wt);
+        if (CSPB_INSERT_PAIR) {
+            const float wx = w * (lane_dx ? fx : wx0);
+            const int xc = x0 + lane_dx;
+            add_corner(acc, A.np, A.xh, xc, y0, z0, wx * wy0 * wz0, re, vim, wt);
+            add_corner(acc, A.np, A.xh, xc, y0 + 1, z0, wx * fy * wz0, re, vim, wt);
+            add_corner(acc, A.np, A.xh, xc, y0, z0 + 1, wx * wy0 * fz, re, vim, wt);
+            add_corner(acc, A.np, A.xh, xc, y0 + 1, z0 + 1, wx * fy * fz, re, vim, wt);
+        } else {
+            add_corner(acc, A.np, A.xh, x0, y0, z0, w * wx0 * wy0 * wz0, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0 + 1, y0, z0, w * fx * wy0 * wz0, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0, y0 + 1, z0, w * wx0 * fy * wz0, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0 + 1, y0 + 1, z0, w * fx * fy * wz0, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0, y0, z0 + 1, w * wx0 * wy0 * fz, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0 + 1, y0, z0 + 1, w * fx * wy0 * fz, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0, y0 + 1, z0 + 1, w * wx0 * fy * fz, re, vim, wt);
+            add_corner(acc, A.np, A.xh, x0 + 1, y0 + 1, z0 + 1, w * fx * fy * fz, re, vim, wt);
+        }
     }
 }
 
@@ -611,7 +628,7 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         a.n_sym = ctx->n_lit;
         a.acc0 = (deferred ? ctx->d_raw[0] : ctx->d_acc[0]).as<float4>();
         a.acc1 = (deferred ? ctx->d_raw[1] : ctx->d_acc[1]).as<float4>();
-        a.tiles = ceil_div((long long)n * nh, 256);
+        a.tiles = ceil_div((long long)n * nh, CSPB_INSERT_PAIR ? 128 : 256);
         a.aux = d_aux;
         a.aux_width = 0.1f * 0.5f * (float)n;
         // one launch, ordered by half (see insert_kernel): the voxels one half touches (a half-sphere of radius np/2,

@@ -52,7 +52,7 @@ if has multi; then
 fi
 if has variants; then
   # A/B of kernel build variants on the same box: alternative libraries through CSPB_LIB (pyp_b200/_lib.py)
-  for L in libcspb200.so libcspb200_gu2.so; do
+  for L in $(cd pyp_b200 && ls libcspb200*.so); do
     [ -f pyp_b200/$L ] || continue
     CSPB_LIB=$PWD/pyp_b200/$L timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline --no-strong > $OUT/variant_$L.json 2> $OUT/variant_$L.err
   done
