@@ -76,12 +76,12 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
                               row.voltage_kv, row.cs_mm, row.amplitude_contrast, n);
     __syncthreads();
 #ifndef CSPB_INSERT_PAIR
-#define CSPB_INSERT_PAIR 1
+#define CSPB_INSERT_PAIR 0
 #endif
-    // CSPB_INSERT_PAIR: two lanes per sample, lane parity = the x corner (x0 / x0 + 1).  The two float4 accumulator cells of an
-    // x pair are neighbours in memory: when x0 is even they share a 32-byte sector, and issued by adjacent lanes of ONE RED
-    // instruction they reach the L2 as one sector operation instead of two (the kernel is L2-atomic bound: one sector per
-    // RED without pairing, r01 ncu).  The per-sample arithmetic is done twice; the atomics per lane halve.
+    // CSPB_INSERT_PAIR=1 (A/B build, not the default): two lanes per sample, lane parity = the x corner (x0 / x0 + 1), so that
+    // the two neighbouring float4 cells of an x pair leave in ONE RED instruction.  Measured slower (r02m: 32.4 vs 29.3 ms per
+    // 32 768 particles): vector REDs of adjacent lanes are not merged into one sector operation, and the doubled per-sample
+    // arithmetic is not free.
     const int lane_dx = CSPB_INSERT_PAIR ? (threadIdx.x & 1) : 0;
     const int idx = CSPB_INSERT_PAIR ? tile * (blockDim.x >> 1) + (threadIdx.x >> 1) : tile * blockDim.x + threadIdx.x;
     if (idx >= n * nh) return;
