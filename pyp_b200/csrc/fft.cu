@@ -299,6 +299,190 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_fast_kernel(const float2 *__
     }
 }
 
+// ---- fused passes of the particle preprocessing (refine.cu, cspb_refine_load_images): the whitening and masking round
+// trips stay on the SM.  Same butterflies in the same order as the separate passes above — results are bit-identical —
+// with one more exchange through shared memory where a forward transform hands over to an inverse one (the second stage
+// leaves element u + R1 k2 in thread u, the first stage of the next transform wants element t + R2 r in thread t).
+
+// columns: forward FFT -> radial filter (whitening) -> inverse FFT, in place
+template <int R1, int R2>
+__global__ void __launch_bounds__(256, 3) fft_cols_filter_fast_kernel(float2 *__restrict__ data, long long estride, int ninner, long long ostride,
+                                                                   int ntiles, const float2 *__restrict__ tw_g, const float *__restrict__ filt,
+                                                                   int filt_w) {
+    constexpr int N = R1 * R2, TL = FastTile<R2>::TL, P = N + (N >> 4) + 1, NT = TL * (R2 < 16 ? 16 : R2);
+    __shared__ float2 S[TL * P];
+    __shared__ float2 tw[N];
+    const int tid = threadIdx.x;
+    const int l = tid % TL, t = tid / TL;
+    const int outer = blockIdx.x / ntiles;
+    const int t0 = (blockIdx.x - outer * ntiles) * TL;
+    const bool live = t0 + l < ninner;
+    float2 *base = data + (long long)outer * ostride + t0 + l;
+    for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
+    float2 v[R1 > R2 ? R1 : R2];
+    if (t < R2) {
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = live ? base[(long long)(t + R2 * r) * estride] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    if (t < R2) fftfast::stage1<R1, R2, -1>(v, t, S + l * P, tw);
+    __syncthreads();
+    if (t < R1) fftfast::stage2<R1, R2, -1>(v, t, S + l * P);
+    __syncthreads();
+    if (t < R1) {
+        const int i = (t0 + l) % filt_w;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+            const int e = t + R1 * k2;
+            const int j = e >= N / 2 ? e - N : e;
+            const float s = filt[(int)(sqrtf((float)(i * i + j * j)) + 0.5f)];
+            v[k2] = make_float2(__fmul_rn(v[k2].x, s), __fmul_rn(v[k2].y, s));  // rounded product, as the separate passes store it
+            if (R1 != R2) S[l * P + fftsm::skew(e)] = v[k2];
+        }
+    }
+    if (R1 != R2) {  // square factorisation: thread t already holds elements t + R2 r, the inverse transform's input
+        __syncthreads();
+        if (t < R2) {
+#pragma unroll
+            for (int r = 0; r < R1; ++r) v[r] = S[l * P + fftsm::skew(t + R2 * r)];
+        }
+        __syncthreads();
+    }
+    if (t < R2) fftfast::stage1<R1, R2, +1>(v, t, S + l * P, tw);
+    __syncthreads();
+    if (t < R1) {
+        fftfast::stage2<R1, R2, +1>(v, t, S + l * P);
+        if (live) {
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) base[(long long)(t + R1 * k2) * estride] = v[k2];
+        }
+    }
+}
+
+// rows: half spectrum -> real (inverse) -> x scale x soft circular mask -> half spectrum (forward), in place
+template <int R1, int R2>
+__global__ void __launch_bounds__(256, R2 <= 16 ? 4 : 3) fft_rows_mask_fast_kernel(float2 *__restrict__ data, long long n_rows, const float2 *__restrict__ tw_g,
+                                                                 float scale, float mask_radius, float mask_width) {
+    constexpr int N = R1 * R2, PR = 256 / R2, P = N + (N >> 4) + 1, NH = N / 2 + 1, NT = PR * R2;
+    __shared__ float2 S[PR * P];
+    __shared__ float2 tw[N];
+    const int tid = threadIdx.x;
+    const int t = tid % R2, p = tid / R2;
+    const long long pair = (long long)blockIdx.x * PR + p;
+    const bool live = pair < n_rows / 2;
+    for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
+    for (int idx = tid; idx < PR * NH; idx += NT) {
+        const int pp = idx / NH, k = idx - pp * NH;
+        const long long pr = (long long)blockIdx.x * PR + pp;
+        if (pr >= n_rows / 2) break;
+        float2 fa = data[pr * 2 * NH + k], fb = data[(pr * 2 + 1) * NH + k];
+        if (k == 0 || 2 * k == N) {
+            fa.y = 0.f;
+            fb.y = 0.f;
+        }
+        S[pp * P + fftsm::skew(k)] = make_float2(fa.x - fb.y, fa.y + fb.x);
+        if (k > 0 && 2 * k < N) S[pp * P + fftsm::skew(N - k)] = make_float2(fa.x + fb.y, -fa.y + fb.x);
+    }
+    __syncthreads();
+    float2 v[R1 > R2 ? R1 : R2];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) v[r] = live ? S[p * P + fftsm::skew(t + R2 * r)] : make_float2(0.f, 0.f);
+    __syncthreads();
+    fftfast::stage1<R1, R2, +1>(v, t, S + p * P, tw);
+    __syncthreads();
+    if (t < R1) fftfast::stage2<R1, R2, +1>(v, t, S + p * P);
+    __syncthreads();
+    if (t < R1) {  // the two real rows of the pair sit in .x / .y: scale, mask, hand over to the forward transform
+        const int ya = (int)((pair * 2) % N) - N / 2, yb = ya + 1;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+            const int e = t + R1 * k2;
+            const float x = (float)(e - N / 2);
+            const float sa = scale * cosine_edge(sqrtf(x * x + (float)(ya * ya)), mask_radius, mask_width);
+            const float sb = scale * cosine_edge(sqrtf(x * x + (float)(yb * yb)), mask_radius, mask_width);
+            v[k2] = make_float2(__fmul_rn(v[k2].x, sa), __fmul_rn(v[k2].y, sb));
+            if (R1 != R2) S[p * P + fftsm::skew(e)] = v[k2];
+        }
+    }
+    if (R1 != R2) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = S[p * P + fftsm::skew(t + R2 * r)];
+        __syncthreads();
+    }
+    fftfast::stage1<R1, R2, -1>(v, t, S + p * P, tw);
+    __syncthreads();
+    if (t < R1) fftfast::stage2<R1, R2, -1>(v, t, S + p * P);
+    __syncthreads();
+    if (t < R1) {
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) S[p * P + fftsm::skew(t + R1 * k2)] = v[k2];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < PR * NH; idx += NT) {
+        const int pp = idx / NH, k = idx - pp * NH;
+        const long long pr = (long long)blockIdx.x * PR + pp;
+        if (pr >= n_rows / 2) break;
+        const float2 za = S[pp * P + fftsm::skew(k)];
+        float2 zb = S[pp * P + fftsm::skew(k ? N - k : 0)];
+        zb.y = -zb.y;
+        const float2 fa = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y + zb.y));
+        const float2 df = make_float2(za.x - zb.x, za.y - zb.y);
+        const float2 fb = make_float2(0.5f * df.y, -0.5f * df.x);
+        data[pr * 2 * NH + k] = fa;
+        data[(pr * 2 + 1) * NH + k] = fb;
+    }
+}
+
+// columns: forward FFT, then the band samples go straight to their slots of the packed image (slot_of: n * nh table,
+// -1 outside the band); sign of the centred origin and the optional per-ring weight applied on the way
+template <int R1, int R2>
+__global__ void __launch_bounds__(256) fft_cols_pack_fast_kernel(const float2 *__restrict__ data, long long estride, int ninner, long long ostride,
+                                                                 int ntiles, const float2 *__restrict__ tw_g, const int32_t *__restrict__ slot_of,
+                                                                 const float *__restrict__ ringw, float2 *__restrict__ packed, int n_slots) {
+    constexpr int N = R1 * R2, TL = FastTile<R2>::TL, P = N + (N >> 4) + 1, NT = TL * (R2 < 16 ? 16 : R2);
+    __shared__ float2 S[TL * P];
+    __shared__ float2 tw[N];
+    const int tid = threadIdx.x;
+    const int l = tid % TL, t = tid / TL;
+    const int outer = blockIdx.x / ntiles;
+    const int t0 = (blockIdx.x - outer * ntiles) * TL;
+    const bool live = t0 + l < ninner;
+    const float2 *base = data + (long long)outer * ostride + t0 + l;
+    for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
+    float2 v[R1 > R2 ? R1 : R2];
+    if (t < R2) {
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = live ? base[(long long)(t + R2 * r) * estride] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    if (t < R2) fftfast::stage1<R1, R2, -1>(v, t, S + l * P, tw);
+    __syncthreads();
+    if (t < R1) {
+        fftfast::stage2<R1, R2, -1>(v, t, S + l * P);
+        if (live) {
+            const int i = t0 + l;
+            float2 *o = packed + (long long)outer * n_slots;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int e = t + R1 * k2;
+                const int slot = __ldg(slot_of + e * ninner + i);
+                if (slot < 0) continue;
+                const int j = e >= N / 2 ? e - N : e;
+                float w = ((i + j) & 1) ? -1.f : 1.f;
+                if (ringw) w *= ringw[(int)sqrtf((float)(i * i + j * j))];
+                o[slot] = make_float2(v[k2].x * w, v[k2].y * w);
+            }
+        }
+    }
+}
+
+__global__ void zero_slots_kernel(float2 *__restrict__ packed, int n_slots, const int32_t *__restrict__ list, int n_list, int count) {
+    const long long total = (long long)n_list * count;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
+        packed[(k / n_list) * n_slots + list[k % n_list]] = make_float2(0.f, 0.f);
+}
+
 int pick_tile(int n) {
     // keep 2 buffers of T lines within ~96 KB so two CTAs fit per SM
     int T = 16;
@@ -454,6 +638,48 @@ int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch, f
     int rc = launch_lines(ctx, inout_c, n, nh, nh, (long long)n * nh, batch, +1, 1.f, 0, nh);
     if (rc) return rc;
     return launch_rows_c2r(ctx, inout_c, out, n, (long long)batch * n, scale, mask_radius, mask_width);
+}
+
+// The whole particle preprocessing of the fast path in four passes (refine.cu): rows r2c with normalisation | columns
+// forward x whitening x inverse | rows inverse x 1/n^2 x mask x forward | columns forward + band pack.  `spec` = work buffer
+// of batch half spectra; dummy slots of the band plan are zeroed from `dummy_list`.
+int fft2_whiten_mask_pack_dev(cspb_ctx *ctx, const float *in, float2 *spec, int n, int batch, const float *offs, const float *scls,
+                              const float *radial_filter, float scale, float mask_radius, float mask_width, const int32_t *slot_of,
+                              const float *ringw, const int32_t *dummy_list, int n_dummy, float2 *packed, int n_slots) {
+    if (!fft_has_fast_path(n)) return cspb_fail(ctx, CSPB_E_ARG, "fused preprocessing needs the fast FFT path");
+    int rc = launch_rows_r2c(ctx, in, spec, n, (long long)batch * n, n, offs, scls);
+    if (rc) return rc;
+    const float2 *tw;
+    if ((rc = fft_get_twiddles(ctx, n, &tw))) return rc;
+    const int nh = n / 2 + 1;
+    const int TL = n == 512 ? 8 : (n == 384 ? 10 : 16), nthreads = n == 384 ? 240 : 256;
+    const int ntiles = ceil_div(nh, TL);
+    const unsigned grid = (unsigned)((long long)ntiles * batch);
+    const long long n_pairs = (long long)batch * n / 2;
+    const long long ostride = (long long)n * nh;
+#define CSPB_FUSED(R1_, R2_, PR_)                                                                                                        \
+    do {                                                                                                                                 \
+        fft_cols_filter_fast_kernel<R1_, R2_><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, radial_filter, nh); \
+        KERNEL_CHECK(ctx);                                                                                                               \
+        fft_rows_mask_fast_kernel<R1_, R2_><<<ceil_div(n_pairs, PR_), nthreads, 0, ctx->stream>>>(spec, (long long)batch * n, tw, scale, \
+                                                                                                 mask_radius, mask_width);              \
+        KERNEL_CHECK(ctx);                                                                                                               \
+        fft_cols_pack_fast_kernel<R1_, R2_><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, slot_of, ringw, packed, \
+                                                                               n_slots);                                                \
+        KERNEL_CHECK(ctx);                                                                                                               \
+    } while (0)
+    if (n == 512) CSPB_FUSED(16, 32, 8);
+    else if (n == 384) CSPB_FUSED(16, 24, 10);
+    else if (n == 256) CSPB_FUSED(16, 16, 16);
+    else if (n == 128) CSPB_FUSED(8, 16, 16);
+    else CSPB_FUSED(8, 8, 32);
+#undef CSPB_FUSED
+    if (n_dummy > 0) {
+        zero_slots_kernel<<<ceil_div((long long)n_dummy * batch, 256) < 1024 ? ceil_div((long long)n_dummy * batch, 256) : 1024, 256, 0, ctx->stream>>>(
+            packed, n_slots, dummy_list, n_dummy, batch);
+        KERNEL_CHECK(ctx);
+    }
+    return 0;
 }
 
 int fft3_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int np) {

@@ -59,6 +59,9 @@ struct BandPlan {
     std::vector<int32_t> slot_ij;  // i | (j << 16)
     std::vector<BandDesc> bands;
     DevBuf d_slot_ij, d_bands;
+    DevBuf d_slot_of;   // inverse map of the band plan: (row jj, column i) of the half spectrum -> slot, -1 outside the band
+    DevBuf d_dummy;     // the padding slots of the plan
+    int n_dummy = 0;
 };
 bool build_band_plan(BandPlan &plan, int n, float r_lo, float r_hi, bool radial_order = false);
 
@@ -250,6 +253,10 @@ int fft2_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int n, int batch,
 int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch, float scale = 1.f,
                  float mask_radius = 0.f, float mask_width = 0.f);
 bool fft_has_fast_path(int n);
+// fused preprocessing of the fast path (fft.cu): normalise + r2c | whiten round trip | mask round trip | pack; see refine.cu
+int fft2_whiten_mask_pack_dev(cspb_ctx *ctx, const float *in, float2 *spec, int n, int batch, const float *offs, const float *scls,
+                              const float *radial_filter, float scale, float mask_radius, float mask_width, const int32_t *slot_of,
+                              const float *ringw, const int32_t *dummy_list, int n_dummy, float2 *packed, int n_slots);
 // 3-D R2C / C2R of an np^3 volume (in-place complex work buffer of (np/2+1)*np*np)
 int fft3_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int np);
 int fft3_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int np);

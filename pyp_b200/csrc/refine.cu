@@ -1054,6 +1054,22 @@ extern "C" int cspb_refine_configure(cspb_ctx *ctx, const cspb_refine_cfg *cfg) 
                                 cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(pl.d_bands.p, pl.bands.data(), pl.bands.size() * sizeof(BandDesc),
                                 cudaMemcpyHostToDevice, ctx->stream));
+    {   // inverse map of the band plan for the fused preprocessing (fft2_whiten_mask_pack_dev)
+        const int n = cfg->box, nh = n / 2 + 1;
+        std::vector<int32_t> slot_of((size_t)n * nh, -1), dummy;
+        for (size_t sl = 0; sl < pl.slot_ij.size(); ++sl) {
+            const int32_t ij = pl.slot_ij[sl];
+            const int i = (int)(short)(ij & 0xFFFF), j = (int)(short)(ij >> 16);
+            if (i == CSPB_DUMMY_I) { dummy.push_back((int32_t)sl); continue; }
+            slot_of[(size_t)(j < 0 ? j + n : j) * nh + i] = (int32_t)sl;
+        }
+        pl.n_dummy = (int)dummy.size();
+        RESERVE(ctx, pl.d_slot_of, slot_of.size() * sizeof(int32_t));
+        RESERVE(ctx, pl.d_dummy, (dummy.size() + 1) * sizeof(int32_t));
+        CU_TRY(ctx, cudaMemcpyAsync(pl.d_slot_of.p, slot_of.data(), slot_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (!dummy.empty())
+            CU_TRY(ctx, cudaMemcpyAsync(pl.d_dummy.p, dummy.data(), dummy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->refine_ready = true;
     ctx->ref.ready = false;
@@ -1344,6 +1360,35 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         // the noise curve is already known (every chunk but the very first)
         const bool fast = fft_has_fast_path(n);
         const bool fused_filt = fast && c.whiten && ctx->have_noise;
+        const char *fuse_env = getenv("CSPB_PREP_FUSED");  // "0": the separate passes (A/B and the bit-identity test)
+        const bool no_fuse = fuse_env && fuse_env[0] == '0';
+        if (fused_filt && c.apply_mask && !no_fuse) {
+            // the common case (every batch but the one the whitening curve is estimated on): four passes instead of seven,
+            // the whitening and masking round trips never leave the SM and the band pack rides on the last column pass
+            // CSPB_PREP_SUB=<images>: sub-chunks whose half spectra stay in the L2 from one pass to the next — measured SLOWER
+            // (profiles/r02_notes.md: the passes are not DRAM bound and every dependent launch costs ~11 us), so the default
+            // is one set of launches per chunk
+            const char *sub_env = getenv("CSPB_PREP_SUB");
+            int sub = sub_env ? atoi(sub_env) : cnt;
+            if (sub < 8) sub = 8;
+            RESERVE(ctx, ctx->d_stats, (size_t)2 * cnt * sizeof(float));
+            RESERVE(ctx, ctx->d_work1, (size_t)(sub < cnt ? sub : cnt) * n * nh * sizeof(float2));
+            for (int q = 0; q < cnt; q += sub) {
+                const int m = cnt - q < sub ? cnt - q : sub;
+                float *offs = ctx->d_stats.as<float>() + 2 * q, *scls = offs + m;
+                const float *img_q = d_img + (size_t)q * n * n;
+                image_stats_kernel<<<m, 256, 0, ctx->stream>>>(img_q, n, c.mask_radius / c.pixel_size, c.normalize, c.invert_contrast, offs, scls);
+                KERNEL_CHECK(ctx);
+                int rc = fft2_whiten_mask_pack_dev(ctx, img_q, ctx->d_work1.as<float2>(), n, m, offs, scls, ctx->d_noise.as<float>(),
+                                                   1.f / ((float)n * (float)n), c.mask_radius / c.pixel_size, 20.f / c.pixel_size,
+                                                   ctx->plan.d_slot_of.as<int32_t>(), ctx->have_ring_w ? ctx->d_ring_w.as<float>() : nullptr,
+                                                   ctx->plan.d_dummy.as<int32_t>(), ctx->plan.n_dummy,
+                                                   ctx->d_packed.as<float2>() + (size_t)(base + s + q) * n_slots, n_slots);
+                if (rc) return rc;
+            }
+            if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            continue;
+        }
         int rc = preprocess_chunk(ctx, d_img, cnt, &spec, fused_filt ? ctx->d_noise.as<float>() : nullptr);
         if (rc) return rc;
         if (c.whiten && !ctx->have_noise) {

@@ -109,6 +109,24 @@ def test_score_matches_oracle(engine, oracle, kw):
     assert np.all(want > 5.0)  # the true poses correlate
 
 
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_fused_preprocessing_is_bit_identical_to_the_separate_passes(engine, oracle, n, monkeypatch):
+    """Once the whitening curve is known the preprocessing runs in four fused passes (fft2_whiten_mask_pack_dev); same
+    butterflies in the same order as the seven separate ones, so the packed images — seen through the scores — do not
+    change by a bit, and both agree with the oracle."""
+    ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, n=n, n_part=9 if n > 64 else 24)
+    first = engine.score(rows)  # first load: curve estimated on this stack, separate passes
+    engine.load_images(stack)  # curve known: fused passes
+    fused = engine.score(rows)
+    monkeypatch.setenv("CSPB_PREP_FUSED", "0")
+    engine.load_images(stack)
+    separate = engine.score(rows)
+    assert np.array_equal(fused, separate)
+    assert np.abs(fused - first).max() <= 1e-6 * np.abs(first).max()
+    want = np.array([oracle.score(ref, specs[k], rows[k], pose_of(rows[k]), ocfg)[0] for k in range(rows.size)])
+    assert np.abs(fused - want).max() <= SCORE_RTOL * np.abs(want).max()
+
+
 def test_score_poses_grouping_and_defocus(engine, oracle):
     ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(engine, oracle, n_part=7)
     rng = np.random.default_rng(5)

@@ -35,6 +35,11 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:insert_kernel -c 2 \
     -o $OUT/insert_full -f python bench.py --steps 1 --warmup 1 --particles 8192 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_insert.log 2>&1
 fi
+if has ncu_prep; then
+  # the preprocessing passes (fused path: the second and later chunks)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fft_|image_stats|zero_slots" --launch-skip 12 -c 8 \
+    -o $OUT/prep_full -f python bench.py --steps 1 --warmup 1 --particles 16384 --no-e2e --no-cpu-baseline --no-strong > $OUT/ncu_prep.log 2>&1
+fi
 if has multi; then
   # needs gpurun --gpus N: 2-GPU equality test of the product entry, H2D scaling of the platform, bench at every N
   NG=$(nvidia-smi -L | wc -l)
