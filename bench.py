@@ -539,6 +539,7 @@ def run_b200_arm(a):
         mark()
         n_ev = 0
         if rcfg is not None:
+            eng.keep_spectra(ccfg is not None)  # the resident stack reaches recon_insert unchanged: one forward FFT per projection
             eng.load_images(st)
         mark()
         if kind == "spa":
@@ -631,6 +632,7 @@ def run_b200_arm(a):
             cfg2 = fill(Engine.refine_defaults(n, px), refine_params(c, name))
             eng.refine_configure(cfg2)
             eng.set_reference(vol)
+            eng.keep_spectra(False)  # refinement only in this leg
             eng.load_images(stack)
             rows_dev_all[:n_proj].copy_(rows_init_all[:n_proj])
             torch.cuda.synchronize()

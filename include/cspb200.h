@@ -172,6 +172,15 @@ int cspb_set_symmetry(cspb_ctx *ctx, const float *mats, int n_mats);
  * normalise -> FFT -> whiten -> mask -> band-pack.  `images` is n_images*box*box float32.
  * May be called repeatedly with append=1 to stream a stack in chunks. */
 int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n_images, int loc, int append);
+
+/* One forward transform per projection for refine3d AND reconstruct3d (the reference's two programs each read and
+ * transform the stack: frealign.py:3918-3994, 1780-1824).  on != 0: a device-resident, non-appending
+ * cspb_refine_load_images also keeps the plain forward transforms and their normalisation (264 KB per 256-px image, skipped
+ * silently when the device lacks the room); a later cspb_recon_insert[_weighted] whose `images` pointer lies inside that
+ * same device buffer rescales them to its own normalisation (the transform is linear: factor scl_r/scl_f, DC term
+ * scl_r (off_f - off_r) n^2) instead of transforming again.  THE CALLER PROMISES the pixels have not changed in between.
+ * Any other load, or on = 0, drops what was kept.  The streamed pipelines below do this internally. */
+int cspb_refine_keep_spectra(cspb_ctx *ctx, int on);
 int cspb_refine_num_images(const cspb_ctx *ctx);
 
 /* Score every loaded image at the pose in its row (one evaluation per image).

@@ -150,6 +150,9 @@ __device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, in
         const float *row = p + (long long)y * n;
         if (vec) {
             for (int x = lane * 4; x < n; x += 128) {
+                // four pixels wholly inside the radius are not loaded at all (dx^2 is convex: the end pixels decide)
+                const float dxa = (float)(x - c), dxb = (float)(x + 3 - c);
+                if (!use_all && fmaxf(dxa * dxa, dxb * dxb) + dy2 <= r2lim) continue;
                 const float4 v = *reinterpret_cast<const float4 *>(row + x);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -176,6 +179,8 @@ __device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, in
         const float *row = p + (long long)y * n;
         if (vec) {
             for (int x = lane * 4; x < n; x += 128) {
+                const float dxa = (float)(x - c), dxb = (float)(x + 3 - c);
+                if (!use_all && fmaxf(dxa * dxa, dxb * dxb) + dy2 <= r2lim) continue;
                 const float4 v = *reinterpret_cast<const float4 *>(row + x);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll

@@ -305,10 +305,10 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_fast_kernel(const float2 *__
 // leaves element u + R1 k2 in thread u, the first stage of the next transform wants element t + R2 r in thread t).
 
 // columns: forward FFT -> radial filter (whitening) -> inverse FFT, in place
-template <int R1, int R2>
+template <int R1, int R2, bool KEEP>
 __global__ void __launch_bounds__(256, 3) fft_cols_filter_fast_kernel(float2 *__restrict__ data, long long estride, int ninner, long long ostride,
                                                                    int ntiles, const float2 *__restrict__ tw_g, const float *__restrict__ filt,
-                                                                   int filt_w) {
+                                                                   int filt_w, float2 *__restrict__ keep) {
     constexpr int N = R1 * R2, TL = FastTile<R2>::TL, P = N + (N >> 4) + 1, NT = TL * (R2 < 16 ? 16 : R2);
     __shared__ float2 S[TL * P];
     __shared__ float2 tw[N];
@@ -336,6 +336,8 @@ __global__ void __launch_bounds__(256, 3) fft_cols_filter_fast_kernel(float2 *__
             const int e = t + R1 * k2;
             const int j = e >= N / 2 ? e - N : e;
             const float s = filt[(int)(sqrtf((float)(i * i + j * j)) + 0.5f)];
+            // KEEP: the plain forward transform goes to a second buffer, for the insertion (cspb_refine_keep_spectra)
+            if (KEEP && live) keep[(long long)outer * ostride + t0 + l + (long long)e * estride] = v[k2];
             v[k2] = make_float2(__fmul_rn(v[k2].x, s), __fmul_rn(v[k2].y, s));  // rounded product, as the separate passes store it
             if (R1 != R2) S[l * P + fftsm::skew(e)] = v[k2];
         }
@@ -645,7 +647,7 @@ int fft2_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int n, int batch, f
 // of batch half spectra; dummy slots of the band plan are zeroed from `dummy_list`.
 int fft2_whiten_mask_pack_dev(cspb_ctx *ctx, const float *in, float2 *spec, int n, int batch, const float *offs, const float *scls,
                               const float *radial_filter, float scale, float mask_radius, float mask_width, const int32_t *slot_of,
-                              const float *ringw, const int32_t *dummy_list, int n_dummy, float2 *packed, int n_slots) {
+                              const float *ringw, const int32_t *dummy_list, int n_dummy, float2 *packed, int n_slots, float2 *keep_forward) {
     if (!fft_has_fast_path(n)) return cspb_fail(ctx, CSPB_E_ARG, "fused preprocessing needs the fast FFT path");
     int rc = launch_rows_r2c(ctx, in, spec, n, (long long)batch * n, n, offs, scls);
     if (rc) return rc;
@@ -659,7 +661,12 @@ int fft2_whiten_mask_pack_dev(cspb_ctx *ctx, const float *in, float2 *spec, int 
     const long long ostride = (long long)n * nh;
 #define CSPB_FUSED(R1_, R2_, PR_)                                                                                                        \
     do {                                                                                                                                 \
-        fft_cols_filter_fast_kernel<R1_, R2_><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, radial_filter, nh); \
+        if (keep_forward)                                                                                                                \
+            fft_cols_filter_fast_kernel<R1_, R2_, true><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, radial_filter, \
+                                                                                            nh, keep_forward);                          \
+        else                                                                                                                             \
+            fft_cols_filter_fast_kernel<R1_, R2_, false><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, radial_filter, \
+                                                                                             nh, nullptr);                              \
         KERNEL_CHECK(ctx);                                                                                                               \
         fft_rows_mask_fast_kernel<R1_, R2_><<<ceil_div(n_pairs, PR_), nthreads, 0, ctx->stream>>>(spec, (long long)batch * n, tw, scale, \
                                                                                                  mask_radius, mask_width);              \

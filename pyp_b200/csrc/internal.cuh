@@ -165,6 +165,17 @@ struct cspb_ctx {
     cudaEvent_t pipe_ready[2] = {nullptr, nullptr}, pipe_freed[2] = {nullptr, nullptr};
     DevBuf pipe_stage[2], pipe_rows;
     DevBuf pipe_all;  // resident stack of cspb_refine_select_reconstruct
+    // forward transforms kept for the insertion (cspb_refine_keep_spectra): half spectra of the images of the last
+    // device-resident, non-appending cspb_refine_load_images, normalised as for refinement, plus that normalisation
+    // (offset, scale per image); cspb_recon_insert of the same pixels rescales them instead of transforming again
+    bool keep_on = false;
+    DevBuf d_keep_spec, d_keep_stats, d_keep_scale;
+    const float *keep_src = nullptr;
+    int keep_count = 0, keep_box = 0, keep_total = 0;   // images kept so far / box / images of the span (stats layout)
+    const float *keep_span_src = nullptr;               // pipeline.cu: the loads that follow are consecutive pieces of this
+    int keep_span_count = 0;                            // resident stack (kept spectra accumulate instead of being replaced)
+    float keep_radius = 0.f;          // normalisation of the kept spectra: radius in pixels, normalize, invert
+    int keep_normalize = 0, keep_invert = 0;
 
     // recon state
     bool recon_ready = false;
@@ -256,7 +267,8 @@ bool fft_has_fast_path(int n);
 // fused preprocessing of the fast path (fft.cu): normalise + r2c | whiten round trip | mask round trip | pack; see refine.cu
 int fft2_whiten_mask_pack_dev(cspb_ctx *ctx, const float *in, float2 *spec, int n, int batch, const float *offs, const float *scls,
                               const float *radial_filter, float scale, float mask_radius, float mask_width, const int32_t *slot_of,
-                              const float *ringw, const int32_t *dummy_list, int n_dummy, float2 *packed, int n_slots);
+                              const float *ringw, const int32_t *dummy_list, int n_dummy, float2 *packed, int n_slots,
+                              float2 *keep_forward = nullptr);
 // 3-D R2C / C2R of an np^3 volume (in-place complex work buffer of (np/2+1)*np*np)
 int fft3_r2c_dev(cspb_ctx *ctx, const float *in, float2 *out, int np);
 int fft3_c2r_dev(cspb_ctx *ctx, float2 *inout_c, float *out, int np);

@@ -11,6 +11,26 @@
 #include <vector>
 #include "internal.cuh"
 
+namespace {
+// restores the kept-spectra switches on every way out of a pipeline call
+struct KeepScope {
+    cspb_ctx *c;
+    bool was;
+    KeepScope(cspb_ctx *ctx, bool on, const float *span, int span_count) : c(ctx), was(ctx->keep_on) {
+        c->keep_on = on;
+        c->keep_span_src = span;
+        c->keep_span_count = span_count;
+    }
+    ~KeepScope() {
+        c->keep_on = was;
+        c->keep_span_src = nullptr;
+        c->keep_span_count = 0;
+        c->keep_count = 0;  // the buffers the spectra were made from are about to be reused
+        c->keep_src = nullptr;
+    }
+};
+}  // namespace
+
 extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images, int flags,
                                        int64_t *n_evals_out) {
     CSPB_ENTER(ctx);
@@ -74,6 +94,8 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     CU_TRY(ctx, cudaMemcpyAsync(P.rows.p, rows_host, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
     int64_t evals = 0;
     int rc = 0, idx = 0;
+    // refine and insert see the same staged pixels: one forward transform per projection (cspb_refine_keep_spectra)
+    KeepScope keep_scope(ctx, do_refine && do_insert, nullptr, 0);
     for (int s = 0; idx < (int)sizes.size() && !rc; s += sizes[idx], ++idx) {
         const int b = idx & 1;
         const int cnt = sizes[idx];
@@ -164,6 +186,8 @@ extern "C" int cspb_refine_select_reconstruct(cspb_ctx *ctx, const float *images
         off += sizes[k];
     }
     off = 0;
+    // the batches are consecutive pieces of the resident stack: their forward transforms are kept for the insertion
+    KeepScope keep_scope(ctx, true, d_all, n_images);
     for (size_t k = 0; k < sizes.size() && !rc; ++k) {
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ready[k], 0));
         rc = cspb_refine_load_images(ctx, d_all + off * n * n, sizes[k], CSPB_DEVICE, 0);

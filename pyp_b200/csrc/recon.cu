@@ -34,6 +34,7 @@ struct InsertArgs {
     int tiles;            // tiles per image
     const float2 *aux;    // optional per row {weight, cut radius in Fourier pixels}: data-driven dose weighting (SEMANTICS.md §10)
     float aux_width;      // width of the raised-cosine edge at the cut radius
+    const float2 *rescale; // optional per row {factor, DC term}: `spec` holds transforms normalised for refinement (kept spectra)
 };
 
 __device__ __forceinline__ void add_corner(float4 *acc, int np, int xh, int x, int y, int z, float w, float re,
@@ -93,6 +94,12 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A) {
     const float r2 = fi * fi + fj * fj;
     if (r2 > A.rmax2) return;
     float2 F = __ldcs(A.spec + (long long)img * n * nh + idx);  // streamed once: do not displace the accumulators in L2
+    if (A.rescale) {  // F_recon = (scl_r / scl_f) F_refine + scl_r (off_f - off_r) n^2 delta(0): the transform is linear
+        const float2 rs = A.rescale[img];
+        F.x *= rs.x;
+        F.y *= rs.x;
+        if (idx == 0) F.x += rs.y;
+    }
     if ((i + j) & 1) { F.x = -F.x; F.y = -F.y; }  // box centre at n/2
     const float ctf = -sinpif(ctf_chi(s_ctf, fi, fj, r2) * (1.f / CSPB_PI_F));
     float w = row.occupancy * 0.01f;
@@ -482,6 +489,15 @@ int grid_for(long long total, int block, int sm) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// kept spectra (cspb_refine_keep_spectra): per image the factor and the DC term that turn the refinement normalisation
+// (off_f, scl_f) into the reconstruction's (off_r, scl_r)
+__global__ void keep_rescale_kernel(const float *__restrict__ off_r, const float *__restrict__ scl_r, const float *__restrict__ off_f,
+                                    const float *__restrict__ scl_f, int count, float n2, float2 *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    out[k] = make_float2(scl_r[k] / scl_f[k], scl_r[k] * (off_f[k] - off_r[k]) * n2);
+}
+
 __global__ void image_stats_recon_kernel(const float *__restrict__ img, int n, float radius, int normalize, int invert,
                                          float *__restrict__ offs, float *__restrict__ scls) {
     __shared__ float red[64];
@@ -582,6 +598,21 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
     const int chunk = chunk_images(n, n_images);
     if (ctx->n_lit > INSERT_MAX_SYM) return cspb_fail(ctx, CSPB_E_ARG, "more than %d symmetry operators", INSERT_MAX_SYM);
     const bool deferred = ctx->n_lat > 1;
+    static const bool pull = getenv("CSPB_INSERT") && !strcmp(getenv("CSPB_INSERT"), "pull");
+    // the same pixels cspb_refine_load_images has just transformed (cspb_refine_keep_spectra): no second transform
+    const float2 *kept = nullptr;
+    long long kept0 = 0;
+    if (loc == CSPB_DEVICE && !pull && ctx->keep_count > 0 && ctx->keep_box == n && images >= ctx->keep_src) {
+        const size_t d = (size_t)(images - ctx->keep_src), per = (size_t)n * n;
+        if (d % per == 0 && d / per + (size_t)n_images <= (size_t)ctx->keep_count) {
+            kept0 = (long long)(d / per);
+            kept = ctx->d_keep_spec.as<float2>() + kept0 * n * nh;
+        }
+    }
+    float r_norm = c.mask_radius / c.pixel_size;
+    if (r_norm > 0.5f * (float)n) r_norm = 0.5f * (float)n;  // the clamp of image_edge_stats
+    const bool same_norm = kept && r_norm == ctx->keep_radius && (c.normalize != 0) == (ctx->keep_normalize != 0) &&
+                           (c.invert_contrast != 0) == (ctx->keep_invert != 0);
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;
@@ -605,14 +636,29 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         }
         RESERVE(ctx, ctx->d_stats, (size_t)2 * chunk * sizeof(float));
         float *offs = ctx->d_stats.as<float>(), *scls = offs + cnt;
-        image_stats_recon_kernel<<<cnt, 256, 0, ctx->stream>>>(d_img, n, c.mask_radius / c.pixel_size, c.normalize,
-                                                             c.invert_contrast, offs, scls);
-        KERNEL_CHECK(ctx);
-        RESERVE(ctx, ctx->d_work1, (size_t)chunk * n * nh * sizeof(float2));
-        int rc = fft2_r2c_dev(ctx, d_img, ctx->d_work1.as<float2>(), n, cnt, offs, scls);
-        if (rc) return rc;
+        const float2 *rescale = nullptr;
+        if (!same_norm) {
+            image_stats_recon_kernel<<<cnt, 256, 0, ctx->stream>>>(d_img, n, c.mask_radius / c.pixel_size, c.normalize,
+                                                                 c.invert_contrast, offs, scls);
+            KERNEL_CHECK(ctx);
+        }
+        if (kept) {
+            if (!same_norm) {
+                RESERVE(ctx, ctx->d_keep_scale, (size_t)chunk * sizeof(float2));
+                const float *ks = ctx->d_keep_stats.as<float>();
+                keep_rescale_kernel<<<ceil_div(cnt, 256), 256, 0, ctx->stream>>>(offs, scls, ks + kept0 + s, ks + ctx->keep_total + kept0 + s, cnt,
+                                                                               (float)n * (float)n, ctx->d_keep_scale.as<float2>());
+                KERNEL_CHECK(ctx);
+                rescale = ctx->d_keep_scale.as<float2>();
+            }
+        } else {
+            RESERVE(ctx, ctx->d_work1, (size_t)chunk * n * nh * sizeof(float2));
+            int rc = fft2_r2c_dev(ctx, d_img, ctx->d_work1.as<float2>(), n, cnt, offs, scls);
+            if (rc) return rc;
+        }
         InsertArgs a;
-        a.spec = ctx->d_work1.as<float2>();
+        a.spec = kept ? kept + (long long)s * n * nh : ctx->d_work1.as<float2>();
+        a.rescale = rescale;
         a.rows = d_rows;
         a.n = n; a.count = cnt; a.np = np; a.xh = xh;
         a.padf = (float)c.pad;
@@ -638,7 +684,6 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         // A/B runs: it issues ~3x fewer L2 atomics but measured 2.3x SLOWER (r02k: 67.9 vs 29.2 ms per 32 768 particles) — the
         // staging redundancy (every sample is prepared by ~2.7 tiles), the candidate walks and the rejected tiles cost more
         // than the atomics they save; profiles/r02_notes.md
-        static const bool pull = getenv("CSPB_INSERT") && !strcmp(getenv("CSPB_INSERT"), "pull");
         if (!pull) {
             insert_kernel<<<(unsigned)((long long)cnt * a.tiles), 256, 0, ctx->stream>>>(a);
         } else {

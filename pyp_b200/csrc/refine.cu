@@ -1345,6 +1345,36 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         nb.bytes = 0;
         ctx->img_capacity = cap;
     }
+    // cspb_refine_keep_spectra: the plain forward transforms (and their normalisation) stay on the device for the insertion
+    const float *span_src = images;
+    int span_count = n_images;
+    long long span_off = 0;
+    if (ctx->keep_span_src && loc == CSPB_DEVICE && images >= ctx->keep_span_src) {
+        const size_t d = (size_t)(images - ctx->keep_span_src), per = (size_t)n * n;
+        if (d % per == 0 && d / per + (size_t)n_images <= (size_t)ctx->keep_span_count) {
+            span_src = ctx->keep_span_src;
+            span_count = ctx->keep_span_count;
+            span_off = (long long)(d / per);
+        }
+    }
+    const bool continuing = span_off > 0 && ctx->keep_src == span_src && ctx->keep_count == span_off && ctx->keep_box == n;
+    if (!continuing) {
+        ctx->keep_count = 0;
+        ctx->keep_src = nullptr;
+    }
+    bool keep = ctx->keep_on && loc == CSPB_DEVICE && !append && n_images > 0 && (span_off == 0 || continuing);
+    if (keep) {
+        const size_t need = (size_t)span_count * n * nh * sizeof(float2);
+        if (need > ctx->d_keep_spec.bytes) {  // an optimisation only: never at the price of the memory the caller needs
+            size_t free_b = 0, total_b = 0;
+            CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+            if (continuing || need + ((size_t)8 << 30) > free_b + ctx->d_keep_spec.bytes) keep = false;
+        }
+        if (keep) {
+            RESERVE(ctx, ctx->d_keep_spec, need);
+            RESERVE(ctx, ctx->d_keep_stats, (size_t)2 * span_count * sizeof(float));
+        }
+    }
     const int chunk = chunk_images(n, n_images);
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
@@ -1376,6 +1406,10 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
             for (int q = 0; q < cnt; q += sub) {
                 const int m = cnt - q < sub ? cnt - q : sub;
                 float *offs = ctx->d_stats.as<float>() + 2 * q, *scls = offs + m;
+                if (keep) {  // the normalisation goes where the insertion finds it
+                    offs = ctx->d_keep_stats.as<float>() + span_off + s + q;
+                    scls = offs + span_count;
+                }
                 const float *img_q = d_img + (size_t)q * n * n;
                 image_stats_kernel<<<m, 256, 0, ctx->stream>>>(img_q, n, c.mask_radius / c.pixel_size, c.normalize, c.invert_contrast, offs, scls);
                 KERNEL_CHECK(ctx);
@@ -1383,7 +1417,8 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
                                                    1.f / ((float)n * (float)n), c.mask_radius / c.pixel_size, 20.f / c.pixel_size,
                                                    ctx->plan.d_slot_of.as<int32_t>(), ctx->have_ring_w ? ctx->d_ring_w.as<float>() : nullptr,
                                                    ctx->plan.d_dummy.as<int32_t>(), ctx->plan.n_dummy,
-                                                   ctx->d_packed.as<float2>() + (size_t)(base + s + q) * n_slots, n_slots);
+                                                   ctx->d_packed.as<float2>() + (size_t)(base + s + q) * n_slots, n_slots,
+                                                   keep ? ctx->d_keep_spec.as<float2>() + (size_t)(span_off + s + q) * n * nh : nullptr);
                 if (rc) return rc;
             }
             if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1391,6 +1426,15 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         }
         int rc = preprocess_chunk(ctx, d_img, cnt, &spec, fused_filt ? ctx->d_noise.as<float>() : nullptr);
         if (rc) return rc;
+        if (keep && fused_filt) keep = false;  // the whitening rode on the forward pass: no plain transform to keep
+        if (keep) {
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_keep_spec.as<float2>() + (size_t)(span_off + s) * n * nh, spec, (size_t)cnt * n * nh * sizeof(float2),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+            float *ks = ctx->d_keep_stats.as<float>() + span_off + s;
+            CU_TRY(ctx, cudaMemcpyAsync(ks, ctx->d_stats.as<float>(), (size_t)cnt * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU_TRY(ctx, cudaMemcpyAsync(ks + span_count, ctx->d_stats.as<float>() + cnt, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+        }
         if (c.whiten && !ctx->have_noise) {
             rc = estimate_noise_from_spectra(ctx, spec, cnt);
             if (rc) return rc;
@@ -1427,6 +1471,29 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
     }
     ctx->n_images = total;
+    if (!keep) {
+        ctx->keep_count = 0;
+        ctx->keep_src = nullptr;
+    } else {
+        ctx->keep_src = span_src;
+        ctx->keep_count = (int)span_off + n_images;
+        ctx->keep_total = span_count;
+        ctx->keep_box = n;
+        ctx->keep_radius = c.mask_radius / c.pixel_size;
+        if (ctx->keep_radius > 0.5f * (float)n) ctx->keep_radius = 0.5f * (float)n;
+        ctx->keep_normalize = c.normalize;
+        ctx->keep_invert = c.invert_contrast;
+    }
+    return 0;
+}
+
+extern "C" int cspb_refine_keep_spectra(cspb_ctx *ctx, int on) {
+    if (!ctx) return CSPB_E_ARG;
+    ctx->keep_on = on != 0;
+    if (!on) {
+        ctx->keep_count = 0;
+        ctx->keep_src = nullptr;
+    }
     return 0;
 }
 

@@ -208,6 +208,11 @@ class Engine:
         assert tuple(images.shape[1:]) == (self.box, self.box)
         self._ck(self._l.cspb_refine_load_images(self._h, p, n_img, loc, 1 if append else 0))
 
+    def keep_spectra(self, on=True):
+        """One forward transform per projection for refinement and insertion (cspb_refine_keep_spectra): the device tensor
+        passed to load_images must reach recon_insert unchanged."""
+        self._ck(self._l.cspb_refine_keep_spectra(self._h, 1 if on else 0))
+
     @property
     def num_images(self):
         return int(self._l.cspb_refine_num_images(self._h))

@@ -577,6 +577,50 @@ def test_streamed_pipeline_equals_staged_calls(engine, oracle):
     assert np.abs(engine.recon_get_dump(0) - want[0]).max() <= 1e-5 * np.abs(want[0]).max()
 
 
+@pytest.mark.parametrize("n,same_radius", [(64, False), (128, False), (128, True)])
+def test_kept_spectra_insertion_equals_a_second_transform(engine, oracle, n, same_radius):
+    """cspb_refine_keep_spectra: the insertion rescales the forward transforms the refinement made (other normalisation
+    radius: factor + DC term per image; same radius: used as they are) — accumulators equal those of its own transform."""
+    import torch
+
+    px = 1.35
+    ph, vol, rows, stack = small_case(n=n, n_part=21)
+    cfg = refine_cfg(n, px)
+    rc = engine.recon_defaults(n, px)
+    if same_radius:
+        rc.mask_radius = cfg.mask_radius
+    engine.set_symmetry("C1")
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    dev = torch.from_numpy(stack).cuda()
+    engine.keep_spectra(False)
+    engine.load_images(dev)  # whitening curve estimated here (separate passes)
+    engine.recon_begin(rc)
+    engine.recon_insert(dev, rows)
+    want = [engine.recon_get_dump(h) for h in (0, 1)]
+    want_scores = engine.score(rows)
+    for _ in range(2):  # curve known: fused passes, the column pass writes the plain transform beside its own output
+        engine.keep_spectra(True)
+        engine.load_images(dev)
+        assert np.abs(engine.score(rows) - want_scores).max() <= 1e-6 * np.abs(want_scores).max()
+        engine.recon_begin(rc)
+        engine.recon_insert(dev[3:17], rows[3:17])  # a sub-range of the kept buffer
+        engine.recon_insert(dev[:3], rows[:3])
+        engine.recon_insert(dev[17:], rows[17:])
+        for h in (0, 1):
+            got = engine.recon_get_dump(h)
+            assert np.abs(got - want[h]).max() <= 2e-6 * np.abs(want[h]).max()
+    # a fresh configuration: the first load (curve unknown, separate passes) keeps its transforms too
+    engine.refine_configure(cfg)
+    engine.set_reference(vol)
+    engine.load_images(dev)
+    engine.recon_begin(rc)
+    engine.recon_insert(dev, rows)
+    for h in (0, 1):
+        assert np.abs(engine.recon_get_dump(h) - want[h]).max() <= 2e-6 * np.abs(want[h]).max()
+    engine.keep_spectra(False)
+
+
 def test_full_size_properties_o_symmetry_256(engine):
     """BASELINE configs[1] sizes (256-px box, O symmetry): properties that do not need the oracle.
     (1) a symmetric reference scores symmetry-related poses identically; (2) insertion is additive
