@@ -125,7 +125,9 @@ def workload_config(a, P):
            "n_band": band_count(c["box"], c["pixel"], rp["low_res_limit"], rp["high_res_limit"]),
            "l2_policy": f"inputs larger than L2 ({P * c.get('tilts', 1) * c['box'] ** 2 * 4 / 1e9:.2f} GB stack per GPU per step, read once)"}
     if c["kind"] == "spa":
-        cfg["search"] = ("global: 20 deg grid + FFT shift search, top-20 hits refined locally (8 iterations)" if c.get("global_search")
+        stencil = getattr(a, "optimizer", "analytic") == "stencil"
+        cfg["search"] = (f"global: 20 deg grid + FFT shift search, top-20 hits refined locally (8 iterations of the {'stencil' if stencil else 'analytic-gradient'} "
+                         f"optimiser, {114 if stencil else 18} evaluations per hit)" if c.get("global_search")
                          else ("local: 8 iterations of the central-difference stencil optimiser (114 evaluations per particle)" if getattr(a, "optimizer", "analytic") == "stencil"
                                else "local: 8 coarse-to-fine iterations of the analytic-gradient optimiser (one gradient + one trial evaluation each, 18 evaluations per particle)"))
     elif c["kind"] == "tomo":

@@ -1138,7 +1138,10 @@ long long orc_global_search(const orc_ref *r, const float *specs, orc_row *rows,
                 x[3] = top[t].sx; x[4] = top[t].sy;
             }
             float obj;
-            const float sc = refine_one(r, spec, row, x, freem, cfg, o4, &ev, hi / r_s, &obj);
+            /* the default optimiser refines the hits too (SEMANTICS.md §7c); stencil optimiser with steps widened to the search
+               resolution for optimizer = 1 or a defocus refinement */
+            const float sc = cfg->optimizer == 0 && !cfg->refine_defocus ? refine_one_lm(r, spec, row, x, freem, cfg, o4, &ev, &obj)
+                                                                         : refine_one(r, spec, row, x, freem, cfg, o4, &ev, hi / r_s, &obj);
             if (obj > bestobj) { bestobj = obj; bestsc = sc; memcpy(xb, x, sizeof xb); memcpy(ob, o4, sizeof ob); }
         }
         evals += ev;

@@ -1890,10 +1890,15 @@ static float lm_stage(int it, int iters, float r_lo, float r_hi, int *ring_cut) 
 
 // local refinement with the analytic optimiser (oracle/SEMANTICS.md §7c): per iteration ONE gradient evaluation
 // (score_grad_kernel) and ONE trial evaluation per state, coarse to fine over the rings of the band
-static int refine_lm_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_ctf, int n, cspb_row *d_changes, int free_mask,
-                             int64_t *n_evals_out) {
+// With hits (global search: K states per image, state k starts at candidate k % K of image k / K) every hit is refined and
+// opt_write_rows_kernel keeps the best; the first, coarse stages (rings below r_hi / 6, trust region 16 stencil steps of
+// that resolution) span the half grid step a hit may sit away from its optimum.
+static int refine_lm_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_ctf, int n_img, cspb_row *d_changes, int free_mask,
+                             int64_t *n_evals_out, int K = 1, const SearchHit *d_hits = nullptr, const float *d_angles = nullptr,
+                             int64_t evals_before = 0) {
     const cspb_refine_cfg &c = ctx->rcfg;
     const int iters = (free_mask & 31) ? (c.local_iterations > 0 ? c.local_iterations : 8) : 0;
+    const int n = n_img * K;  // optimiser states
     RESERVE(ctx, ctx->d_opt, (size_t)n * sizeof(OptState));
     RESERVE(ctx, ctx->d_evals, (size_t)n * 2 * 6 * sizeof(float));
     RESERVE(ctx, ctx->d_units, (size_t)n * sizeof(ScoreUnit));
@@ -1906,7 +1911,7 @@ static int refine_lm_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_c
     const float r_hi = ctx->plan.r_hi, r_lo = ctx->plan.r_lo;
     const int g = ceil_div(n, 128);
     const bool focus_on = ctx->focus[3] > 0.f;
-    if (focus_on) RESERVE(ctx, ctx->d_alpha, (size_t)n * sizeof(float));
+    if (focus_on) RESERVE(ctx, ctx->d_alpha, (size_t)n_img * sizeof(float));
     OptPrior pr{};
     float lam_scale = 0.f;
     if (c.use_priors) {
@@ -1918,18 +1923,18 @@ static int refine_lm_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_c
         pr.wx = c.prior_var_x > 0.f ? 0.5f / c.prior_var_x : 0.f;
         pr.wy = c.prior_var_y > 0.f ? 0.5f / c.prior_var_y : 0.f;
     }
-    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, n, 1, nullptr, nullptr, st, 0.f, 0.f, 0.f, lam_scale);
+    opt_init_kernel<<<g, 128, 0, ctx->stream>>>(d_rows, n, K, d_hits, d_angles, st, 0.f, 0.f, 0.f, lam_scale);
     KERNEL_CHECK(ctx);
-    int64_t evals = 0;
+    int64_t evals = evals_before;
     for (int it = 0; it < iters; ++it) {
         int ring_cut;
         const float f = lm_stage(it, iters, r_lo, r_hi, &ring_cut);
         const float h_ang = 0.35f * 57.29578f * f / r_hi, h_shift = 0.07f * (float)c.box * f / r_hi * c.pixel_size;
-        lm_pose_kernel<<<g, 128, 0, ctx->stream>>>(st, n, 1, ev, un);
+        lm_pose_kernel<<<g, 128, 0, ctx->stream>>>(st, n, K, ev, un);
         KERNEL_CHECK(ctx);
         int rc = launch_score_grad(ctx, un, n, ev, d_ctf, gout, ring_cut);
         if (rc) return rc;
-        lm_step_kernel<<<g, 128, 0, ctx->stream>>>(st, n, 1, free_mask, gout, 16.f * h_ang, 16.f * h_shift, ev, un, pr);
+        lm_step_kernel<<<g, 128, 0, ctx->stream>>>(st, n, K, free_mask, gout, 16.f * h_ang, 16.f * h_shift, ev, un, pr);
         KERNEL_CHECK(ctx);
         rc = launch_score(ctx, un, n, 1, ev, d_ctf, out, false, n, 0, ring_cut);
         if (rc) return rc;
@@ -1937,16 +1942,16 @@ static int refine_lm_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *d_c
         KERNEL_CHECK(ctx);
         evals += 2 * (int64_t)n;
     }
-    opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, n, 1, ev, un);
+    opt_finish_eval_kernel<<<g, 128, 0, ctx->stream>>>(st, n, K, ev, un);
     KERNEL_CHECK(ctx);
     int rc = launch_score(ctx, un, n, 2, ev, d_ctf, out, false, 2 * (int64_t)n, 0);
     if (rc) return rc;
     evals += 2 * (int64_t)n;
-    opt_write_rows_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(st, n, 1, out, ctx->plan.n_band, 0, d_rows, d_changes, pr,
+    opt_write_rows_kernel<<<ceil_div(n_img, 128), 128, 0, ctx->stream>>>(st, n_img, K, out, ctx->plan.n_band, 0, d_rows, d_changes, pr,
                                                                          focus_on ? ctx->d_alpha.as<float>() : nullptr);
     KERNEL_CHECK(ctx);
     if (focus_on) {
-        rc = focus_logp_enqueue(ctx, d_rows, const_cast<CtfCoef *>(d_ctf), n, d_changes);
+        rc = focus_logp_enqueue(ctx, d_rows, const_cast<CtfCoef *>(d_ctf), n_img, d_changes);
         if (rc) return rc;
     }
     if (n_evals_out) *n_evals_out = evals;
@@ -1965,8 +1970,8 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
     if (c.refine_x) free_mask |= 8;
     if (c.refine_y) free_mask |= 16;
     if (c.refine_defocus) free_mask |= 32;
-    // optimiser 0 (default): analytic gradient + Gauss-Newton step for a plain local refinement of the pose; the stencil
-    // optimiser below serves the defocus refinement, the hits of a global search and optimizer = 1
+    // optimiser 0 (default): analytic gradient + Gauss-Newton step for the five pose parameters — plain local refinement
+    // here, the hits of a global search below; the stencil optimiser serves the defocus refinement and optimizer = 1
     if (c.optimizer == 0 && !c.global_search && !c.refine_defocus && c.local_refine)
         return refine_lm_enqueue(ctx, d_rows, d_ctf, n, d_changes, free_mask, n_evals_out);
     int64_t evals = 0;
@@ -1984,6 +1989,8 @@ static int refine_local_enqueue(cspb_ctx *ctx, cspb_row *d_rows, const CtfCoef *
         d_hits = ctx->d_hits.as<SearchHit>();
         evals += (int64_t)n * ctx->n_grid;
         free_mask |= 31;  // the hits are refined in all five pose parameters
+        if (c.optimizer == 0 && !c.refine_defocus)
+            return refine_lm_enqueue(ctx, d_rows, d_ctf, n, d_changes, free_mask, n_evals_out, K, d_hits, d_angles, evals);
     }
     int n_free = 0;
     for (int m = 0; m < OPT_NP; ++m) n_free += (free_mask >> m) & 1;

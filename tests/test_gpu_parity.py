@@ -355,8 +355,10 @@ def test_reconfigure_to_a_larger_box_reallocates_the_packed_images(engine, oracl
     assert np.abs(got - want).max() <= SCORE_RTOL * np.abs(want).max()
 
 
-def test_global_search_matches_oracle(engine, oracle):
-    """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally.
+@pytest.mark.parametrize("optimizer,evals", [(0, 18), (1, 8 * 14 + 2)])
+def test_global_search_matches_oracle(engine, oracle, optimizer, evals):
+    """refine3d 'global search yes': grid search with FFT shift search, top-K hits refined locally (default: the analytic
+    optimiser, 18 evaluations per hit; optimizer = 1: the stencil optimiser, 114).
     Same grid, same band, same box reduction on both sides; the best orientation/shift choice must
     be identical for >= 99.9 % of the particles."""
     from pyp_b200.search_grid import search_grid
@@ -364,7 +366,7 @@ def test_global_search_matches_oracle(engine, oracle):
     px = 1.35
     ph, vol, rows, stack, cfg, ocfg, specs, ref, curve = _setup(
         engine, oracle, n_part=24, global_search=1, local_refine=0, search_high_res=8 * px, search_range_x=6 * px,
-        search_range_y=6 * px, best_matches=5)
+        search_range_y=6 * px, best_matches=5, optimizer=optimizer)
     grid = search_grid(20.0, "C1")
     engine.set_search_grid(grid)
     start = rows.copy()
@@ -372,7 +374,7 @@ def test_global_search_matches_oracle(engine, oracle):
         start[k] = 0
     got, _, n_ev = engine.refine(start)
     want, n_ev_o = oracle.global_search(ref, specs, start.astype(oracle.ROW_DTYPE), ocfg, grid)
-    assert n_ev == n_ev_o == rows.size * (grid.shape[0] + 5 * (8 * 14 + 2))
+    assert n_ev == n_ev_o == rows.size * (grid.shape[0] + 5 * evals)
     ang = angular_distance(got, want)
     sh = np.hypot(got["x_shift"] - want["x_shift"], got["y_shift"] - want["y_shift"])
     # the discrete choices (grid orientation, integer shift peak, which hit wins) are identical; the

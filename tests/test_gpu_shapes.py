@@ -143,7 +143,8 @@ def test_c3_41_tilts_128px_csp_matches_oracle(engine, oracle, mode):
         assert np.array_equal(got[2][12:], bad_t[12:])
 
 
-def test_c4_384px_global_search_radial_band_matches_oracle(engine, oracle):
+@pytest.mark.parametrize("optimizer,evals", [("analytic", 18), ("stencil", 114)])
+def test_c4_384px_global_search_radial_band_matches_oracle(engine, oracle, optimizer, evals):
     """BASELINE configs[3]: 384-px box at 1.35 A/px, global search on the 20 degree grid, hits refined on the band
     100 A..2.5 px (n_band 37 174).  The half-sphere of reference quads the band touches (254 MB) exceeds the L2, so
     the band plan keeps the radial ring order (refine.cu, cspb_refine_configure) — the branch no small test reaches."""
@@ -152,7 +153,7 @@ def test_c4_384px_global_search_radial_band_matches_oracle(engine, oracle):
     P, K = 8, 4
     c, vol, rows, stack = _synthetic("C4", P, snr=0.1, seed=41)
     n, px = c["box"], c["pixel"]
-    cfg = bench.fill(Engine.refine_defaults(n, px), bench.refine_params(c))
+    cfg = bench.fill(Engine.refine_defaults(n, px), bench.refine_params(c, optimizer))
     cfg.best_matches = K
     engine.refine_configure(cfg)
     assert engine.band_counts()[0] == 37174
@@ -173,7 +174,7 @@ def test_c4_384px_global_search_radial_band_matches_oracle(engine, oracle):
         start[k] = 0
     g, _, n_ev = engine.refine(start)
     w, n_ev_o = oracle.global_search(ref, specs, start.astype(oracle.ROW_DTYPE), ocfg, grid)
-    assert n_ev == n_ev_o == P * (grid.shape[0] + K * 114)
+    assert n_ev == n_ev_o == P * (grid.shape[0] + K * evals)
     # discrete choices identical; the hits start up to half a grid step away, so the continuous refinement amplifies
     # fp32 summation-order noise more than a local refinement (same radius as test_global_search_matches_oracle)
     same, ang, sh = _same_optimum(g, w, 1e-1, 1e-1)
