@@ -129,9 +129,9 @@ typedef struct cspb_refine_cfg {
     int32_t use_priors;        /* prompt 7: restrain X/Y shifts to the data set's distribution     */
     float prior_mean_x, prior_mean_y; /* Angstrom: row 0 of <name>_stat.cistem (particle_cspt.py:1009-1016) */
     float prior_var_x, prior_var_y;   /* Angstrom^2: row 1; <= 0 leaves that shift unrestrained     */
-    int32_t optimizer;         /* local optimiser (ours): 0 = analytic gradient + Gauss-Newton step, coarse to fine (SEMANTICS.md
-                                  §7c; plain local refinement of the pose), 1 = central-difference stencil (§7; always used for
-                                  the defocus refinement and for the hits of a global search) */
+    int32_t optimizer;         /* local optimiser (ours), also for the hits of a global search: 0 = analytic gradient +
+                                  Gauss-Newton step, coarse to fine (SEMANTICS.md §7c), 1 = central-difference stencil (§7;
+                                  always used for the defocus refinement) */
     int32_t reserved[1];
 } cspb_refine_cfg;
 
