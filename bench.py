@@ -800,6 +800,9 @@ def run_b200_arm(a):
     if opt_cmp:
         line["optimizers"] = opt_cmp
     if e2e:
+        # how much of the device-resident rate survives the host-to-device copy; the copy-bound ceiling is
+        # h2d_bytes / the pinned H2D bandwidth of the platform at this N (tools/h2d_scaling.py)
+        e2e["e2e_efficiency"] = ms_per_step / e2e["ms_per_step"]
         line["e2e"] = e2e
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
