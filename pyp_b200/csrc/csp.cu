@@ -89,9 +89,7 @@ __host__ __device__ __forceinline__ void csp_compose(const cspb_particle &p, con
     q[0] = c * cb; q[1] = c * sb; q[2] = -s;
     q[3] = -sb;    q[4] = cb;     q[5] = 0.f;
     q[6] = s * cb; q[7] = s * sb; q[8] = c;
-#pragma unroll
     for (int a = 0; a < 3; ++a)
-#pragma unroll
         for (int b = 0; b < 3; ++b) m[3 * a + b] = e[3 * a] * q[b] + e[3 * a + 1] * q[3 + b] + e[3 * a + 2] * q[6 + b];
     csp_decode(m, &out5[0], &out5[1], &out5[2]);
     float A[6], A0[6];

@@ -225,15 +225,6 @@ __device__ __forceinline__ RefQuad ldg_quad(const RefQuad *p) {
     return q;
 }
 
-// predicated variant: lanes with `take` false issue no memory traffic and keep `q` (the quad the
-// unit's first pose already gathered from the same voxel)
-__device__ __forceinline__ void ldg_quad_if(const RefQuad *p, bool take, RefQuad &q) {
-    asm("{\n\t.reg .pred t;\n\tsetp.ne.s32 t, %9, 0;\n\t"
-        "@t ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
-        : "+f"(q.v00.x), "+f"(q.v00.y), "+f"(q.v10.x), "+f"(q.v10.y), "+f"(q.v01.x), "+f"(q.v01.y), "+f"(q.v11.x), "+f"(q.v11.y)
-        : "l"(p), "r"((int)take));
-}
-
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2 / FMUL2 on an aligned register pair).  A complex
 // value lives in one 64-bit register; a trilinear interpolation is 7 FADD2 + 7 FFMA2 instead of 28 scalar
 // instructions, with the same roundings (a + f (b - a) per component).
@@ -1385,7 +1376,7 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
                                         cudaMemcpyHostToDevice, ctx->stream));
             d_img = ctx->d_stage.as<float>();
         }
-        float2 *spec;
+        float2 *spec = nullptr;
         // whitening filter and soft mask ride on the FFT passes when the box has the fast path and
         // the noise curve is already known (every chunk but the very first)
         const bool fast = fft_has_fast_path(n);

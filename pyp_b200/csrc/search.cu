@@ -89,8 +89,6 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
     int *pos = reinterpret_cast<int *>(c2m + S.n_ss);                    // n_ss: index into bufa
     Hit *top = reinterpret_cast<Hit *>(pos + S.n_ss);                    // K
     __shared__ float red[64];
-    __shared__ float s_best;
-    __shared__ int s_bidx;
     const int tid = threadIdx.x, nt = blockDim.x, p = blockIdx.x;
     for (int k = tid; k < nb; k += nt) tw[k] = tw_g[k];
     for (int s = tid; s < S.n_ss; s += nt) {
@@ -155,8 +153,6 @@ __global__ void __launch_bounds__(256) search_kernel(SearchDev S, Radices rad, c
         if (tid == 0) {
             for (int w = 1; w < (nt >> 5); ++w)
                 if (wbest[w] > best || (wbest[w] == best && widx[w] < bidx)) { best = wbest[w]; bidx = widx[w]; }
-            s_best = best;
-            s_bidx = bidx;
             // parabolic sub-pixel fit along x and y
             const int dy = bidx / wxs - S.wy, dx = bidx % wxs - S.wx;
             auto at = [&](int ddx, int ddy) {
