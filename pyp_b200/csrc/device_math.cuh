@@ -129,22 +129,23 @@ __host__ __device__ __forceinline__ void score_stats(float4 v, int n_samples, fl
 // mean and 1/sigma of the pixels outside radius R (clamped to the half box, as the reference does) of one
 // n x n image per CTA — the normalisation of analysis/image.py:320-338,406-417.  Rows are walked by
 // warps with 16-byte loads (no integer division); the second pass re-reads the image from L2.
-__device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, int n, float radius, int normalize, int invert,
-                                                 float *off_out, float *scl_out, float *red /* >= 64 floats */) {
-    __shared__ float s_mean_;
+// DUAL: the same two passes also give the statistics for a second radius (the reconstruction's, when the forward
+// transforms are kept for it: cspb_refine_keep_spectra) — own accumulators in the same order, so each pair of results is
+// bit-identical to a single-radius call.
+template <bool DUAL>
+__device__ __forceinline__ void image_edge_stats_t(const float *__restrict__ p, int n, float radius, float radius2, int invert, int invert2,
+                                                   float *off_out, float *scl_out, float *off2_out, float *scl2_out,
+                                                   float *red /* >= 64 floats */) {
+    __shared__ float s_mean_[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const float sgn = invert ? -1.f : 1.f;
-    if (!normalize) {
-        if (tid == 0) { *off_out = 0.f; *scl_out = sgn; }
-        return;
-    }
     // a radius beyond the half box is clamped to it (analysis/image.py:324-331): the corners are the background
     if (radius > 0.5f * (float)n) radius = 0.5f * (float)n;
-    const float r2lim = radius * radius;
+    if (radius2 > 0.5f * (float)n) radius2 = 0.5f * (float)n;
+    const float r2lim = radius * radius, r2lim2 = radius2 * radius2;
+    const float r2skip = DUAL ? fminf(r2lim, r2lim2) : r2lim;  // groups wholly inside every radius are never loaded
     const int c = n / 2;
-    const bool use_all = false;
     const bool vec = (n & 3) == 0;
-    float s = 0.f, cnt = 0.f;
+    float s = 0.f, cnt = 0.f, s2 = 0.f, cnt2 = 0.f;
     for (int y = warp; y < n; y += nw) {
         const float dy2 = (float)((y - c) * (y - c));
         const float *row = p + (long long)y * n;
@@ -152,54 +153,82 @@ __device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, in
             for (int x = lane * 4; x < n; x += 128) {
                 // four pixels wholly inside the radius are not loaded at all (dx^2 is convex: the end pixels decide)
                 const float dxa = (float)(x - c), dxb = (float)(x + 3 - c);
-                if (!use_all && fmaxf(dxa * dxa, dxb * dxb) + dy2 <= r2lim) continue;
+                if (fmaxf(dxa * dxa, dxb * dxb) + dy2 <= r2skip) continue;
                 const float4 v = *reinterpret_cast<const float4 *>(row + x);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float dx = (float)(x + k - c);
-                    if (use_all || dx * dx + dy2 > r2lim) { s += vv[k]; cnt += 1.f; }
+                    if (dx * dx + dy2 > r2lim) { s += vv[k]; cnt += 1.f; }
+                    if (DUAL && dx * dx + dy2 > r2lim2) { s2 += vv[k]; cnt2 += 1.f; }
                 }
             }
         } else {
             for (int x = lane; x < n; x += 32) {
                 const float dx = (float)(x - c);
-                if (use_all || dx * dx + dy2 > r2lim) { s += row[x]; cnt += 1.f; }
+                if (dx * dx + dy2 > r2lim) { s += row[x]; cnt += 1.f; }
+                if (DUAL && dx * dx + dy2 > r2lim2) { s2 += row[x]; cnt2 += 1.f; }
             }
         }
     }
     s = block_sum(s, red);
     cnt = block_sum(cnt, red);
-    if (tid == 0) s_mean_ = cnt > 0.f ? s / cnt : 0.f;
+    if (DUAL) {
+        s2 = block_sum(s2, red);
+        cnt2 = block_sum(cnt2, red);
+    }
+    if (tid == 0) {
+        s_mean_[0] = cnt > 0.f ? s / cnt : 0.f;
+        s_mean_[1] = cnt2 > 0.f ? s2 / cnt2 : 0.f;
+    }
     __syncthreads();
-    const float mean = s_mean_;
-    float v2 = 0.f;
+    const float mean = s_mean_[0], mean2 = s_mean_[1];
+    float v2 = 0.f, w2 = 0.f;
     for (int y = warp; y < n; y += nw) {
         const float dy2 = (float)((y - c) * (y - c));
         const float *row = p + (long long)y * n;
         if (vec) {
             for (int x = lane * 4; x < n; x += 128) {
                 const float dxa = (float)(x - c), dxb = (float)(x + 3 - c);
-                if (!use_all && fmaxf(dxa * dxa, dxb * dxb) + dy2 <= r2lim) continue;
+                if (fmaxf(dxa * dxa, dxb * dxb) + dy2 <= r2skip) continue;
                 const float4 v = *reinterpret_cast<const float4 *>(row + x);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float dx = (float)(x + k - c);
-                    if (use_all || dx * dx + dy2 > r2lim) { const float d = vv[k] - mean; v2 += d * d; }
+                    if (dx * dx + dy2 > r2lim) { const float d = vv[k] - mean; v2 += d * d; }
+                    if (DUAL && dx * dx + dy2 > r2lim2) { const float d = vv[k] - mean2; w2 += d * d; }
                 }
             }
         } else {
             for (int x = lane; x < n; x += 32) {
                 const float dx = (float)(x - c);
-                if (use_all || dx * dx + dy2 > r2lim) { const float d = row[x] - mean; v2 += d * d; }
+                if (dx * dx + dy2 > r2lim) { const float d = row[x] - mean; v2 += d * d; }
+                if (DUAL && dx * dx + dy2 > r2lim2) { const float d = row[x] - mean2; w2 += d * d; }
             }
         }
     }
     v2 = block_sum(v2, red);
+    if (DUAL) w2 = block_sum(w2, red);
     if (tid == 0) {
+        const float sgn = invert ? -1.f : 1.f;
         const float var = cnt > 0.f ? v2 / cnt : 0.f;
         *off_out = mean;
         *scl_out = var > 0.f ? sgn * rsqrtf(var) : sgn;
+        if (DUAL) {
+            const float sgn2 = invert2 ? -1.f : 1.f;
+            const float var2 = cnt2 > 0.f ? w2 / cnt2 : 0.f;
+            *off2_out = mean2;
+            *scl2_out = var2 > 0.f ? sgn2 * rsqrtf(var2) : sgn2;
+        }
     }
+}
+
+__device__ __forceinline__ void image_edge_stats(const float *__restrict__ p, int n, float radius, int normalize, int invert,
+                                                 float *off_out, float *scl_out, float *red /* >= 64 floats */) {
+    if (!normalize) {
+        if (threadIdx.x == 0) { *off_out = 0.f; *scl_out = invert ? -1.f : 1.f; }
+        return;
+    }
+    image_edge_stats_t<false>(p, n, radius, radius, invert, invert, off_out, scl_out, nullptr, nullptr, red);
 }

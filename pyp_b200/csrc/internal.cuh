@@ -176,6 +176,9 @@ struct cspb_ctx {
     int keep_span_count = 0;                            // resident stack (kept spectra accumulate instead of being replaced)
     float keep_radius = 0.f;          // normalisation of the kept spectra: radius in pixels, normalize, invert
     int keep_normalize = 0, keep_invert = 0;
+    bool keep_recon_valid = false;    // d_keep_stats also holds the reconstruction's normalisation (same image pass), made for
+    float keep_recon_radius = 0.f;    // this radius / contrast sign
+    int keep_recon_invert = 0;
 
     // recon state
     bool recon_ready = false;

@@ -613,6 +613,9 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
     if (r_norm > 0.5f * (float)n) r_norm = 0.5f * (float)n;  // the clamp of image_edge_stats
     const bool same_norm = kept && r_norm == ctx->keep_radius && (c.normalize != 0) == (ctx->keep_normalize != 0) &&
                            (c.invert_contrast != 0) == (ctx->keep_invert != 0);
+    // the refinement's pass over the pixels already produced this normalisation (image_stats_dual_kernel)
+    const bool have_stats = kept && ctx->keep_recon_valid && c.normalize && r_norm == ctx->keep_recon_radius &&
+                            (c.invert_contrast != 0) == (ctx->keep_recon_invert != 0);
     for (int s = 0; s < n_images; s += chunk) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;
@@ -637,7 +640,11 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         RESERVE(ctx, ctx->d_stats, (size_t)2 * chunk * sizeof(float));
         float *offs = ctx->d_stats.as<float>(), *scls = offs + cnt;
         const float2 *rescale = nullptr;
-        if (!same_norm) {
+        const float *ks = ctx->d_keep_stats.as<float>();
+        if (have_stats && !same_norm) {
+            offs = const_cast<float *>(ks) + 2 * (long long)ctx->keep_total + kept0 + s;
+            scls = offs + ctx->keep_total;
+        } else if (!same_norm) {
             image_stats_recon_kernel<<<cnt, 256, 0, ctx->stream>>>(d_img, n, c.mask_radius / c.pixel_size, c.normalize,
                                                                  c.invert_contrast, offs, scls);
             KERNEL_CHECK(ctx);
@@ -645,7 +652,6 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         if (kept) {
             if (!same_norm) {
                 RESERVE(ctx, ctx->d_keep_scale, (size_t)chunk * sizeof(float2));
-                const float *ks = ctx->d_keep_stats.as<float>();
                 keep_rescale_kernel<<<ceil_div(cnt, 256), 256, 0, ctx->stream>>>(offs, scls, ks + kept0 + s, ks + ctx->keep_total + kept0 + s, cnt,
                                                                                (float)n * (float)n, ctx->d_keep_scale.as<float2>());
                 KERNEL_CHECK(ctx);

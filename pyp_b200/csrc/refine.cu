@@ -106,6 +106,15 @@ __global__ void image_stats_kernel(const float *__restrict__ img, int n, float r
     image_edge_stats(img + (long long)blockIdx.x * n * n, n, radius, normalize, invert, offs + blockIdx.x, scls + blockIdx.x, red);
 }
 
+// the same, plus the statistics for a second radius from the same two passes (kept spectra: the reconstruction's radius)
+__global__ void image_stats_dual_kernel(const float *__restrict__ img, int n, float radius, float radius2, int invert, int invert2,
+                                        float *__restrict__ offs, float *__restrict__ scls, float *__restrict__ offs2,
+                                        float *__restrict__ scls2) {
+    __shared__ float red[64];
+    image_edge_stats_t<true>(img + (long long)blockIdx.x * n * n, n, radius, radius2, invert, invert2, offs + blockIdx.x, scls + blockIdx.x,
+                             offs2 + blockIdx.x, scls2 + blockIdx.x, red);
+}
+
 // per-image ring power: one warp per ring walks a host-built CSR list of the half-plane samples
 // (deterministic order).  ring = nearest integer radius.  out[img*n_rings + ring] = sum |F|^2
 __global__ void ring_power_kernel(const float2 *__restrict__ spec, int n, int img_step, const int *__restrict__ ring_off,
@@ -1363,8 +1372,18 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         }
         if (keep) {
             RESERVE(ctx, ctx->d_keep_spec, need);
-            RESERVE(ctx, ctx->d_keep_stats, (size_t)2 * span_count * sizeof(float));
+            RESERVE(ctx, ctx->d_keep_stats, (size_t)4 * span_count * sizeof(float));  // offs, scls (refine) | offs, scls (recon)
         }
+    }
+    // ... and, when the reconstruction is already configured, its normalisation comes out of the same pass over the pixels
+    float recon_radius = 0.f;
+    bool dual = keep && ctx->recon_ready && ctx->ccfg.box == n && c.normalize && ctx->ccfg.normalize;
+    if (dual) {
+        recon_radius = ctx->ccfg.mask_radius / ctx->ccfg.pixel_size;
+        if (recon_radius > 0.5f * (float)n) recon_radius = 0.5f * (float)n;
+        if (continuing && !(ctx->keep_recon_valid && ctx->keep_recon_radius == recon_radius &&
+                            (ctx->keep_recon_invert != 0) == (ctx->ccfg.invert_contrast != 0)))
+            dual = false;
     }
     const int chunk = chunk_images(n, n_images);
     for (int s = 0; s < n_images; s += chunk) {
@@ -1402,7 +1421,12 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
                     scls = offs + span_count;
                 }
                 const float *img_q = d_img + (size_t)q * n * n;
-                image_stats_kernel<<<m, 256, 0, ctx->stream>>>(img_q, n, c.mask_radius / c.pixel_size, c.normalize, c.invert_contrast, offs, scls);
+                if (dual)
+                    image_stats_dual_kernel<<<m, 256, 0, ctx->stream>>>(img_q, n, c.mask_radius / c.pixel_size, recon_radius, c.invert_contrast,
+                                                                        ctx->ccfg.invert_contrast, offs, scls, offs + 2 * span_count,
+                                                                        scls + 2 * span_count);
+                else
+                    image_stats_kernel<<<m, 256, 0, ctx->stream>>>(img_q, n, c.mask_radius / c.pixel_size, c.normalize, c.invert_contrast, offs, scls);
                 KERNEL_CHECK(ctx);
                 int rc = fft2_whiten_mask_pack_dev(ctx, img_q, ctx->d_work1.as<float2>(), n, m, offs, scls, ctx->d_noise.as<float>(),
                                                    1.f / ((float)n * (float)n), c.mask_radius / c.pixel_size, 20.f / c.pixel_size,
@@ -1418,6 +1442,7 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         int rc = preprocess_chunk(ctx, d_img, cnt, &spec, fused_filt ? ctx->d_noise.as<float>() : nullptr);
         if (rc) return rc;
         if (keep && fused_filt) keep = false;  // the whitening rode on the forward pass: no plain transform to keep
+        dual = false;                          // separate passes: the insertion computes its own normalisation
         if (keep) {
             CU_TRY(ctx, cudaMemcpyAsync(ctx->d_keep_spec.as<float2>() + (size_t)(span_off + s) * n * nh, spec, (size_t)cnt * n * nh * sizeof(float2),
                                         cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1474,6 +1499,9 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
         if (ctx->keep_radius > 0.5f * (float)n) ctx->keep_radius = 0.5f * (float)n;
         ctx->keep_normalize = c.normalize;
         ctx->keep_invert = c.invert_contrast;
+        ctx->keep_recon_valid = dual;
+        ctx->keep_recon_radius = recon_radius;
+        ctx->keep_recon_invert = ctx->ccfg.invert_contrast;
     }
     return 0;
 }
