@@ -50,7 +50,7 @@ extern "C" int cspb_destroy(cspb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->pipe_copy) {
         cudaStreamSynchronize(ctx->pipe_copy);
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < CSPB_PIPE_STAGES; ++k) {
             if (ctx->pipe_ready[k]) cudaEventDestroy(ctx->pipe_ready[k]);
             if (ctx->pipe_freed[k]) cudaEventDestroy(ctx->pipe_freed[k]);
         }

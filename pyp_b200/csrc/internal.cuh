@@ -105,6 +105,8 @@ struct ProfRec {
 };
 
 // ---------------------------------------------------------------- context
+#define CSPB_PIPE_STAGES 3
+
 struct cspb_ctx {
     bool prof_on = false;
     std::vector<ProfRec> prof;
@@ -162,8 +164,10 @@ struct cspb_ctx {
     // streamed host pipeline (pipeline.cu): copy stream, events, two staging buffers, device rows — kept
     // between calls (allocating and freeing ~10 GB per call costs tens of milliseconds)
     cudaStream_t pipe_copy = nullptr;
-    cudaEvent_t pipe_ready[2] = {nullptr, nullptr}, pipe_freed[2] = {nullptr, nullptr};
-    DevBuf pipe_stage[2], pipe_rows;
+    // three staging buffers: with two, the copy of batch k+2 waits for the kernels of batch k, and a large batch followed by
+    // smaller ones leaves the copy engine idle (r03a timeline: copies done at 168-180 ms instead of 155)
+    cudaEvent_t pipe_ready[CSPB_PIPE_STAGES] = {}, pipe_freed[CSPB_PIPE_STAGES] = {};
+    DevBuf pipe_stage[CSPB_PIPE_STAGES], pipe_rows;
     DevBuf pipe_all;  // resident stack of cspb_refine_select_reconstruct
     // forward transforms kept for the insertion (cspb_refine_keep_spectra): half spectra of the images of the last
     // device-resident, non-appending cspb_refine_load_images, normalised as for refinement, plus that normalisation

@@ -45,33 +45,33 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     if (n_images == 0) return 0;
     // per-projection work does not depend on the batching (the whitening curve is estimated on the
     // first min(n, 4096) images whatever the chunking), so the results equal those of the staged calls
-    // batch schedule: whole waves of the scorer (W = SMs x resident CTAs x 4 units, cspb_wave_units) and growing — W, 2W, 4W,
-    // ... — so that the first batch is on the device after a short copy while the later, larger ones
-    // lose nothing to wave quantisation; bounded by ~6 GB of staging per buffer
+    // batch schedule: whole waves of the scorer (W = SMs x resident CTAs x 4 units, cspb_wave_units), 2W per batch — the kernels
+    // need ~0.63 of a batch's copy time, so every batch is done before the next has landed — after a first batch that holds the
+    // 4 096 images the whitening curve is estimated on (estimate_noise_from_spectra: the curve, and with it every result,
+    // equals that of the staged calls whatever the batching), shrinking 2W, W, W/2 at the end: the call ends one
+    // batch-processing time after the last copy lands.  r03b timeline: with 4W batches in the middle the 9 472-image batch
+    // landed at 103 ms, took 30 ms and pushed the end of the call 19 ms behind the last copy.
     const long long W = cspb_wave_units(ctx);
     long long cap = (long long)(((size_t)6 << 30) / ((size_t)n * n * sizeof(float)));
-    if (cap > 4 * W) cap = 4 * W;
+    const long long want = 2 * W > 4096 ? 2 * W : 4096;
+    if (cap > want) cap = want;
     if (cap < 1) cap = 1;
     std::vector<int> sizes;
     {
-        // grow W, 2W, 4W from the front (the first batch is on the device after a short copy) and shrink 2W, W towards the
-        // end: once the kernels are faster than the PCIe copy the call ends one batch-processing time after the last copy
-        // lands, so the last batch is a single wave (r02e: 30 ms of tail with a 6 720-image last batch, 155 ms of copies)
         std::vector<int> tail;
         long long rem = n_images;
-        if (rem >= 6 * W && 2 * W <= cap) { tail = {(int)(2 * W), (int)W}; rem -= 3 * W; }
+        if (rem >= 8 * W && 2 * W <= cap && W >= 64) { tail = {(int)W, (int)(W / 2)}; rem -= W + W / 2; }
         else if (rem >= 3 * W) { tail = {(int)W}; rem -= W; }
-        // the first batch holds the 4 096 images the whitening curve is estimated on (estimate_noise_from_spectra), so
-        // that the curve — and with it every result — equals that of the staged calls whatever the batching
-        long long s = W > 4096 ? W : 4096;
-        if (s > cap) s = cap;
-        while (rem > 0) {
-            long long take = s < rem ? s : rem;
-            if (rem - take < W / 2 && rem <= cap + W / 2) take = rem;  // no crumbs: the remainder rides on the last growing batch
-            sizes.push_back((int)take);
-            rem -= take;
-            s = 2 * s < cap ? 2 * s : cap;
-        }
+        long long first = W > 4096 ? W : 4096;
+        if (first > cap) first = cap;
+        if (first > rem) first = rem;
+        rem -= first;
+        const long long full = cap < 2 * W ? cap : 2 * W;
+        const long long odd = rem % full;  // what the full batches leave over goes second (no crumbs: onto the first batch)
+        if (odd > 0 && odd < W / 2) first += odd;
+        sizes.push_back((int)first);
+        if (odd >= W / 2) sizes.push_back((int)odd);
+        for (long long k = 0; k < rem / full; ++k) sizes.push_back((int)full);
         sizes.insert(sizes.end(), tail.begin(), tail.end());
     }
     int chunk = 0;
@@ -83,12 +83,12 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     if (!P.copy) {
         CU_TRY(ctx, cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < CSPB_PIPE_STAGES; ++k) {
             CU_TRY(ctx, cudaEventCreateWithFlags(&P.ready[k], cudaEventDisableTiming));
             CU_TRY(ctx, cudaEventCreateWithFlags(&P.freed[k], cudaEventDisableTiming));
         }
     }
-    for (int k = 0; k < 2; ++k) RESERVE(ctx, P.stage[k], (size_t)chunk * n * n * sizeof(float));
+    for (int k = 0; k < CSPB_PIPE_STAGES; ++k) RESERVE(ctx, P.stage[k], (size_t)chunk * n * n * sizeof(float));
     RESERVE(ctx, P.rows, (size_t)n_images * sizeof(cspb_row));
     if (dbg) fprintf(stderr, "pipe: buffers ready at %.1f ms\n", ms_since());
     CU_TRY(ctx, cudaMemcpyAsync(P.rows.p, rows_host, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
@@ -97,9 +97,9 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     // refine and insert see the same staged pixels: one forward transform per projection (cspb_refine_keep_spectra)
     KeepScope keep_scope(ctx, do_refine && do_insert, nullptr, 0);
     for (int s = 0; idx < (int)sizes.size() && !rc; s += sizes[idx], ++idx) {
-        const int b = idx & 1;
+        const int b = idx % CSPB_PIPE_STAGES;
         const int cnt = sizes[idx];
-        if (idx >= 2) CU_TRY(ctx, cudaStreamWaitEvent(P.copy, P.freed[b], 0));
+        if (idx >= CSPB_PIPE_STAGES) CU_TRY(ctx, cudaStreamWaitEvent(P.copy, P.freed[b], 0));
         CU_TRY(ctx, cudaMemcpyAsync(P.stage[b].p, images_host + (size_t)s * n * n, (size_t)cnt * n * n * sizeof(float),
                                     cudaMemcpyHostToDevice, P.copy));
         CU_TRY(ctx, cudaEventRecord(P.ready[b], P.copy));
@@ -154,7 +154,7 @@ extern "C" int cspb_refine_select_reconstruct(cspb_ctx *ctx, const float *images
     RESERVE(ctx, ctx->pipe_rows, (size_t)n_images * sizeof(cspb_row));
     if (!ctx->pipe_copy) {
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < CSPB_PIPE_STAGES; ++k) {
             CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming));
             CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_freed[k], cudaEventDisableTiming));
         }
