@@ -48,7 +48,7 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     // batch schedule: whole waves of the scorer (W = SMs x resident CTAs x 4 units, cspb_wave_units), 2W per batch — the kernels
     // need ~0.63 of a batch's copy time, so every batch is done before the next has landed — after a first batch that holds the
     // 4 096 images the whitening curve is estimated on (estimate_noise_from_spectra: the curve, and with it every result,
-    // equals that of the staged calls whatever the batching), shrinking 2W, W, W/2 at the end: the call ends one
+    // equals that of the staged calls whatever the batching), shrinking W, W, W/2 at the end: the call ends one
     // batch-processing time after the last copy lands.  r03b timeline: with 4W batches in the middle the 9 472-image batch
     // landed at 103 ms, took 30 ms and pushed the end of the call 19 ms behind the last copy.
     const long long W = cspb_wave_units(ctx);
@@ -60,7 +60,8 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     {
         std::vector<int> tail;
         long long rem = n_images;
-        if (rem >= 8 * W && 2 * W <= cap && W >= 64) { tail = {(int)W, (int)(W / 2)}; rem -= W + W / 2; }
+        // (a 2W batch straight before W, W/2 leaves the kernels 4 ms behind the copies when the last one lands: W, W, W/2)
+        if (rem >= 8 * W && 2 * W <= cap && W >= 64) { tail = {(int)W, (int)W, (int)(W / 2)}; rem -= 2 * W + W / 2; }
         else if (rem >= 3 * W) { tail = {(int)W}; rem -= W; }
         long long first = W > 4096 ? W : 4096;
         if (first > cap) first = cap;
