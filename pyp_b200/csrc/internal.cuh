@@ -165,7 +165,7 @@ struct cspb_ctx {
     // between calls (allocating and freeing ~10 GB per call costs tens of milliseconds)
     cudaStream_t pipe_copy = nullptr;
     // three staging buffers: with two, the copy of batch k+2 waits for the kernels of batch k, and a large batch followed by
-    // smaller ones leaves the copy engine idle (r03a timeline: copies done at 168-180 ms instead of 155)
+    // smaller ones leaves the copy engine idle (r02za timeline: copies done at 168-180 ms instead of 155)
     cudaEvent_t pipe_ready[CSPB_PIPE_STAGES] = {}, pipe_freed[CSPB_PIPE_STAGES] = {};
     DevBuf pipe_stage[CSPB_PIPE_STAGES], pipe_rows;
     DevBuf pipe_all;  // resident stack of cspb_refine_select_reconstruct

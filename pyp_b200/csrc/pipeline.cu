@@ -49,7 +49,7 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     // need ~0.63 of a batch's copy time, so every batch is done before the next has landed — after a first batch that holds the
     // 4 096 images the whitening curve is estimated on (estimate_noise_from_spectra: the curve, and with it every result,
     // equals that of the staged calls whatever the batching), shrinking W, W, W/2 at the end: the call ends one
-    // batch-processing time after the last copy lands.  r03b timeline: with 4W batches in the middle the 9 472-image batch
+    // batch-processing time after the last copy lands.  r02zb timeline: with 4W batches in the middle the 9 472-image batch
     // landed at 103 ms, took 30 ms and pushed the end of the call 19 ms behind the last copy.
     const long long W = cspb_wave_units(ctx);
     long long cap = (long long)(((size_t)6 << 30) / ((size_t)n * n * sizeof(float)));
