@@ -304,59 +304,83 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_fast_kernel(const float2 *__
 // with one more exchange through shared memory where a forward transform hands over to an inverse one (the second stage
 // leaves element u + R1 k2 in thread u, the first stage of the next transform wants element t + R2 r in thread t).
 
-// columns: forward FFT -> radial filter (whitening) -> inverse FFT, in place
+// columns: forward FFT -> radial filter (whitening) -> inverse FFT, in place.  Persistent CTAs (grid = a multiple of the SM
+// count) walk the column tiles; the loads of the NEXT tile are issued into a second register set before the current tile is
+// transformed, so that every CTA has a tile's worth of DRAM reads in flight all the time (the one-tile-per-CTA version was
+// latency bound at 2.8 TB/s of traffic: profiles/r02p_prep_ncu.txt).
 template <int R1, int R2, bool KEEP>
-__global__ void __launch_bounds__(256, 3) fft_cols_filter_fast_kernel(float2 *__restrict__ data, long long estride, int ninner, long long ostride,
-                                                                   int ntiles, const float2 *__restrict__ tw_g, const float *__restrict__ filt,
-                                                                   int filt_w, float2 *__restrict__ keep) {
+__global__ void __launch_bounds__(256, 2) fft_cols_filter_fast_kernel(float2 *__restrict__ data, long long estride, int ninner, long long ostride,
+                                                                   int ntiles, int total_tiles, const float2 *__restrict__ tw_g,
+                                                                   const float *__restrict__ filt, int filt_w, float2 *__restrict__ keep) {
     constexpr int N = R1 * R2, TL = FastTile<R2>::TL, P = N + (N >> 4) + 1, NT = TL * (R2 < 16 ? 16 : R2);
     __shared__ float2 S[TL * P];
     __shared__ float2 tw[N];
     const int tid = threadIdx.x;
     const int l = tid % TL, t = tid / TL;
-    const int outer = blockIdx.x / ntiles;
-    const int t0 = (blockIdx.x - outer * ntiles) * TL;
-    const bool live = t0 + l < ninner;
-    float2 *base = data + (long long)outer * ostride + t0 + l;
     for (int i = tid; i < N; i += NT) tw[i] = tw_g[i];
-    float2 v[R1 > R2 ? R1 : R2];
-    if (t < R2) {
-#pragma unroll
-        for (int r = 0; r < R1; ++r) v[r] = live ? base[(long long)(t + R2 * r) * estride] : make_float2(0.f, 0.f);
-    }
-    __syncthreads();
-    if (t < R2) fftfast::stage1<R1, R2, -1>(v, t, S + l * P, tw);
-    __syncthreads();
-    if (t < R1) fftfast::stage2<R1, R2, -1>(v, t, S + l * P);
-    __syncthreads();
-    if (t < R1) {
-        const int i = (t0 + l) % filt_w;
-#pragma unroll
-        for (int k2 = 0; k2 < R2; ++k2) {
-            const int e = t + R1 * k2;
-            const int j = e >= N / 2 ? e - N : e;
-            const float s = filt[(int)(sqrtf((float)(i * i + j * j)) + 0.5f)];
-            // KEEP: the plain forward transform goes to a second buffer, for the insertion (cspb_refine_keep_spectra)
-            if (KEEP && live) keep[(long long)outer * ostride + t0 + l + (long long)e * estride] = v[k2];
-            v[k2] = make_float2(__fmul_rn(v[k2].x, s), __fmul_rn(v[k2].y, s));  // rounded product, as the separate passes store it
-            if (R1 != R2) S[l * P + fftsm::skew(e)] = v[k2];
-        }
-    }
-    if (R1 != R2) {  // square factorisation: thread t already holds elements t + R2 r, the inverse transform's input
-        __syncthreads();
+    float2 v[R1 > R2 ? R1 : R2], vn[R1];
+    int tile = blockIdx.x;
+    {
+        const int outer = tile / ntiles, t0 = (tile - outer * ntiles) * TL;
+        const float2 *b = data + (long long)outer * ostride + t0 + l;
         if (t < R2) {
 #pragma unroll
-            for (int r = 0; r < R1; ++r) v[r] = S[l * P + fftsm::skew(t + R2 * r)];
+            for (int r = 0; r < R1; ++r) vn[r] = (tile < total_tiles && t0 + l < ninner) ? b[(long long)(t + R2 * r) * estride] : make_float2(0.f, 0.f);
         }
-        __syncthreads();
     }
-    if (t < R2) fftfast::stage1<R1, R2, +1>(v, t, S + l * P, tw);
-    __syncthreads();
-    if (t < R1) {
-        fftfast::stage2<R1, R2, +1>(v, t, S + l * P);
-        if (live) {
+    for (; tile < total_tiles; tile += gridDim.x) {
+        const int outer = tile / ntiles;
+        const int t0 = (tile - outer * ntiles) * TL;
+        const bool live = t0 + l < ninner;
+        float2 *base = data + (long long)outer * ostride + t0 + l;
 #pragma unroll
-            for (int k2 = 0; k2 < R2; ++k2) base[(long long)(t + R1 * k2) * estride] = v[k2];
+        for (int r = 0; r < R1; ++r) v[r] = vn[r];
+        {   // prefetch
+            const int nt_ = tile + gridDim.x;
+            const int no = nt_ / ntiles, n0 = (nt_ - no * ntiles) * TL;
+            const float2 *b = data + (long long)no * ostride + n0 + l;
+            if (t < R2 && nt_ < total_tiles && n0 + l < ninner) {
+#pragma unroll
+                for (int r = 0; r < R1; ++r) vn[r] = b[(long long)(t + R2 * r) * estride];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R1; ++r) vn[r] = make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();  // tw loaded (first tile) / the previous tile's last reads of S are done
+        if (t < R2) fftfast::stage1<R1, R2, -1>(v, t, S + l * P, tw);
+        __syncthreads();
+        if (t < R1) fftfast::stage2<R1, R2, -1>(v, t, S + l * P);
+        __syncthreads();
+        if (t < R1) {
+            const int i = (t0 + l) % filt_w;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int e = t + R1 * k2;
+                const int j = e >= N / 2 ? e - N : e;
+                const float s = filt[(int)(sqrtf((float)(i * i + j * j)) + 0.5f)];
+                // KEEP: the plain forward transform goes to a second buffer, for the insertion (cspb_refine_keep_spectra)
+                if (KEEP && live) keep[(long long)outer * ostride + t0 + l + (long long)e * estride] = v[k2];
+                v[k2] = make_float2(__fmul_rn(v[k2].x, s), __fmul_rn(v[k2].y, s));  // rounded product, as the separate passes store it
+                if (R1 != R2) S[l * P + fftsm::skew(e)] = v[k2];
+            }
+        }
+        if (R1 != R2) {  // square factorisation: thread t already holds elements t + R2 r, the inverse transform's input
+            __syncthreads();
+            if (t < R2) {
+#pragma unroll
+                for (int r = 0; r < R1; ++r) v[r] = S[l * P + fftsm::skew(t + R2 * r)];
+            }
+            __syncthreads();
+        }
+        if (t < R2) fftfast::stage1<R1, R2, +1>(v, t, S + l * P, tw);
+        __syncthreads();
+        if (t < R1) {
+            fftfast::stage2<R1, R2, +1>(v, t, S + l * P);
+            if (live) {
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) base[(long long)(t + R1 * k2) * estride] = v[k2];
+            }
         }
     }
 }
@@ -659,14 +683,15 @@ int fft2_whiten_mask_pack_dev(cspb_ctx *ctx, const float *in, float2 *spec, int 
     const unsigned grid = (unsigned)((long long)ntiles * batch);
     const long long n_pairs = (long long)batch * n / 2;
     const long long ostride = (long long)n * nh;
+    const unsigned pgrid = grid < (unsigned)(2 * ctx->sm_count) ? grid : (unsigned)(2 * ctx->sm_count);  // persistent: 2 CTAs per SM
 #define CSPB_FUSED(R1_, R2_, PR_)                                                                                                        \
     do {                                                                                                                                 \
         if (keep_forward)                                                                                                                \
-            fft_cols_filter_fast_kernel<R1_, R2_, true><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, radial_filter, \
-                                                                                            nh, keep_forward);                          \
+            fft_cols_filter_fast_kernel<R1_, R2_, true><<<pgrid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, (int)grid, tw,    \
+                                                                                             radial_filter, nh, keep_forward);          \
         else                                                                                                                             \
-            fft_cols_filter_fast_kernel<R1_, R2_, false><<<grid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, tw, radial_filter, \
-                                                                                             nh, nullptr);                              \
+            fft_cols_filter_fast_kernel<R1_, R2_, false><<<pgrid, nthreads, 0, ctx->stream>>>(spec, nh, nh, ostride, ntiles, (int)grid, tw,   \
+                                                                                              radial_filter, nh, nullptr);              \
         KERNEL_CHECK(ctx);                                                                                                               \
         fft_rows_mask_fast_kernel<R1_, R2_><<<ceil_div(n_pairs, PR_), nthreads, 0, ctx->stream>>>(spec, (long long)batch * n, tw, scale, \
                                                                                                  mask_radius, mask_width);              \
