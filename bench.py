@@ -636,13 +636,14 @@ def run_b200_arm(a):
             eng.set_reference(vol)
             eng.keep_spectra(False)  # refinement only in this leg
             eng.load_images(stack)
-            rows_dev_all[:n_proj].copy_(rows_init_all[:n_proj])
-            torch.cuda.synchronize()
-            t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t_a.record(ext)
-            n_ev = eng.refine_device(rows_dev_all.data_ptr(), n_proj)
-            t_b.record(ext)
-            eng.sync()
+            for timed_pass in (False, True):  # the first pass sizes the optimiser's work buffers (cudaMalloc), the second is timed
+                rows_dev_all[:n_proj].copy_(rows_init_all[:n_proj])
+                torch.cuda.synchronize()
+                t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t_a.record(ext)
+                n_ev = eng.refine_device(rows_dev_all.data_ptr(), n_proj)
+                t_b.record(ext)
+                eng.sync()
             out_rows = rows_dev_all[:n_proj].cpu().numpy().view(ROW_DTYPE).reshape(-1)
             opt_cmp[name] = {"mean_final_score": float(out_rows["score"].mean()), "evals_per_particle": n_ev / n_proj,
                              "refine_ms": t_a.elapsed_time(t_b), "particles_per_s_refine_only": n_proj / (t_a.elapsed_time(t_b) * 1e-3)}
