@@ -504,7 +504,10 @@ extern "C" int cspb_csp_run(cspb_ctx *ctx, cspb_row *rows, int n_rows, cspb_part
     CtfCoef *d_ctf;
     int rc = upload_rows(ctx, rows, n_rows, &d_rows, &d_ctf);
     if (rc) return rc;
-    DevBuf b_rows_out, b_part, b_part_out, b_tilt, b_tilt_out, b_rp, b_rt, b_groups, b_ls, b_la, b_best, b_choice, b_params, b_obj, b_dummy;
+    DevBuf *const cb = ctx->csp_buf;  // persistent: no allocation in the steady state
+    DevBuf &b_rows_out = cb[0], &b_part = cb[1], &b_part_out = cb[2], &b_tilt = cb[3], &b_tilt_out = cb[4], &b_rp = cb[5], &b_rt = cb[6],
+           &b_groups = cb[7], &b_ls = cb[8], &b_la = cb[9], &b_best = cb[10], &b_choice = cb[11], &b_params = cb[12], &b_obj = cb[13],
+           &b_dummy = cb[14];
     RESERVE(ctx, b_rows_out, (size_t)n_rows * sizeof(cspb_row));
     CU_TRY(ctx, cudaMemcpyAsync(b_rows_out.p, d_rows, (size_t)n_rows * sizeof(cspb_row), cudaMemcpyDeviceToDevice, ctx->stream));
     std::vector<cspb_particle> vp(particles, particles + n_particles);

@@ -169,6 +169,8 @@ struct cspb_ctx {
     cudaEvent_t pipe_ready[CSPB_PIPE_STAGES] = {}, pipe_freed[CSPB_PIPE_STAGES] = {};
     DevBuf pipe_stage[CSPB_PIPE_STAGES], pipe_rows;
     DevBuf pipe_all;  // resident stack of cspb_refine_select_reconstruct
+    DevBuf csp_buf[15];  // tables and work buffers of cspb_csp_run, kept between calls (cudaMalloc / cudaFree per call cost
+                         // up to hundreds of ms of jitter per step: r02zp)
     // forward transforms kept for the insertion (cspb_refine_keep_spectra): half spectra of the images of the last
     // device-resident, non-appending cspb_refine_load_images, normalised as for refinement, plus that normalisation
     // (offset, scale per image); cspb_recon_insert of the same pixels rescales them instead of transforming again

@@ -609,6 +609,26 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
             kept = ctx->d_keep_spec.as<float2>() + kept0 * n * nh;
         }
     }
+    if (loc == CSPB_HOST && n_images > 0) {
+        // host stack: rows (and dose weights) go up once; chunk k+1 of the images is copied on the copy stream into the next
+        // staging buffer while chunk k is transformed and inserted
+        if (!ctx->pipe_copy) {
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
+            for (int k = 0; k < CSPB_PIPE_STAGES; ++k) {
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_freed[k], cudaEventDisableTiming));
+            }
+        }
+        const int n_buf = n_images > chunk ? CSPB_PIPE_STAGES : 1;
+        for (int k = 0; k < n_buf; ++k) RESERVE(ctx, ctx->pipe_stage[k], (size_t)chunk * n * n * sizeof(float));
+        RESERVE(ctx, ctx->d_rows, (size_t)n_images * sizeof(cspb_row));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // whoever used the staging buffers before this call is done
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_rows.p, rows, (size_t)n_images * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
+        if (weight_cut) {
+            RESERVE(ctx, ctx->d_aux, (size_t)n_images * sizeof(float2));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_aux.p, weight_cut, (size_t)n_images * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
     float r_norm = c.mask_radius / c.pixel_size;
     if (r_norm > 0.5f * (float)n) r_norm = 0.5f * (float)n;  // the clamp of image_edge_stats
     const bool same_norm = kept && r_norm == ctx->keep_radius && (c.normalize != 0) == (ctx->keep_normalize != 0) &&
@@ -616,27 +636,22 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
     // the refinement's pass over the pixels already produced this normalisation (image_stats_dual_kernel)
     const bool have_stats = kept && ctx->keep_recon_valid && c.normalize && r_norm == ctx->keep_recon_radius &&
                             (c.invert_contrast != 0) == (ctx->keep_recon_invert != 0);
-    for (int s = 0; s < n_images; s += chunk) {
+    int chunk_index = 0;
+    for (int s = 0; s < n_images; s += chunk, ++chunk_index) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;
         const cspb_row *d_rows = rows + s;
-        RESERVE(ctx, ctx->d_rows, (size_t)chunk * sizeof(cspb_row));
+        const int sb = chunk_index % CSPB_PIPE_STAGES;
         if (loc == CSPB_HOST) {
-            RESERVE(ctx, ctx->d_stage, (size_t)chunk * n * n * sizeof(float));
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage.p, d_img, (size_t)cnt * n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-            d_img = ctx->d_stage.as<float>();
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_rows.p, d_rows, (size_t)cnt * sizeof(cspb_row), cudaMemcpyHostToDevice, ctx->stream));
-            d_rows = ctx->d_rows.as<cspb_row>();
+            if (chunk_index >= CSPB_PIPE_STAGES) CU_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_freed[sb], 0));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->pipe_stage[sb].p, d_img, (size_t)cnt * n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->pipe_copy));
+            CU_TRY(ctx, cudaEventRecord(ctx->pipe_ready[sb], ctx->pipe_copy));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_ready[sb], 0));
+            d_img = ctx->pipe_stage[sb].as<float>();
+            d_rows = ctx->d_rows.as<cspb_row>() + s;
         }
         const float2 *d_aux = nullptr;
-        if (weight_cut) {
-            d_aux = reinterpret_cast<const float2 *>(weight_cut) + s;
-            if (loc == CSPB_HOST) {
-                RESERVE(ctx, ctx->d_aux, (size_t)chunk * sizeof(float2));
-                CU_TRY(ctx, cudaMemcpyAsync(ctx->d_aux.p, d_aux, (size_t)cnt * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-                d_aux = ctx->d_aux.as<float2>();
-            }
-        }
+        if (weight_cut) d_aux = (loc == CSPB_HOST ? ctx->d_aux.as<float2>() : reinterpret_cast<const float2 *>(weight_cut)) + s;
         RESERVE(ctx, ctx->d_stats, (size_t)2 * chunk * sizeof(float));
         float *offs = ctx->d_stats.as<float>(), *scls = offs + cnt;
         const float2 *rescale = nullptr;
@@ -699,7 +714,11 @@ extern "C" int cspb_recon_insert_weighted(cspb_ctx *ctx, const float *images, co
         }
         prof_end(ctx);
         KERNEL_CHECK(ctx);
-        if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (loc == CSPB_HOST) CU_TRY(ctx, cudaEventRecord(ctx->pipe_freed[sb], ctx->stream));
+    }
+    if (loc == CSPB_HOST && n_images > 0) {  // the caller's host buffers are free again
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->pipe_copy));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (deferred && n_images > 0) ctx->raw_dirty = true;
     ctx->recon_inserted += n_images;

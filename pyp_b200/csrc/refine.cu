@@ -1386,14 +1386,30 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
             dual = false;
     }
     const int chunk = chunk_images(n, n_images);
-    for (int s = 0; s < n_images; s += chunk) {
+    if (loc == CSPB_HOST && n_images > 0) {
+        // host stack: chunk k+1 is copied on the copy stream into the next staging buffer while chunk k is preprocessed
+        if (!ctx->pipe_copy) {
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
+            for (int k = 0; k < CSPB_PIPE_STAGES; ++k) {
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_freed[k], cudaEventDisableTiming));
+            }
+        }
+        const int n_buf = n_images > chunk ? CSPB_PIPE_STAGES : 1;
+        for (int k = 0; k < n_buf; ++k) RESERVE(ctx, ctx->pipe_stage[k], (size_t)chunk * n * n * sizeof(float));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // whoever used the staging buffers before this call is done
+    }
+    int chunk_index = 0;
+    for (int s = 0; s < n_images; s += chunk, ++chunk_index) {
         const int cnt = n_images - s < chunk ? n_images - s : chunk;
         const float *d_img = images + (size_t)s * n * n;
+        const int sb = chunk_index % CSPB_PIPE_STAGES;
         if (loc == CSPB_HOST) {
-            RESERVE(ctx, ctx->d_stage, (size_t)chunk * n * n * sizeof(float));
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage.p, d_img, (size_t)cnt * n * n * sizeof(float),
-                                        cudaMemcpyHostToDevice, ctx->stream));
-            d_img = ctx->d_stage.as<float>();
+            if (chunk_index >= CSPB_PIPE_STAGES) CU_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_freed[sb], 0));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->pipe_stage[sb].p, d_img, (size_t)cnt * n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->pipe_copy));
+            CU_TRY(ctx, cudaEventRecord(ctx->pipe_ready[sb], ctx->pipe_copy));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_ready[sb], 0));
+            d_img = ctx->pipe_stage[sb].as<float>();
         }
         float2 *spec = nullptr;
         // whitening filter and soft mask ride on the FFT passes when the box has the fast path and
@@ -1436,7 +1452,7 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
                                                    keep ? ctx->d_keep_spec.as<float2>() + (size_t)(span_off + s + q) * n * nh : nullptr);
                 if (rc) return rc;
             }
-            if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (loc == CSPB_HOST) CU_TRY(ctx, cudaEventRecord(ctx->pipe_freed[sb], ctx->stream));
             continue;
         }
         int rc = preprocess_chunk(ctx, d_img, cnt, &spec, fused_filt ? ctx->d_noise.as<float>() : nullptr);
@@ -1484,7 +1500,11 @@ extern "C" int cspb_refine_load_images(cspb_ctx *ctx, const float *images, int n
                                                    ctx->have_ring_w ? ctx->d_ring_w.as<float>() : nullptr,
                                                    ctx->d_packed.as<float2>() + (size_t)(base + s) * n_slots);
         KERNEL_CHECK(ctx);
-        if (loc == CSPB_HOST) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+        if (loc == CSPB_HOST) CU_TRY(ctx, cudaEventRecord(ctx->pipe_freed[sb], ctx->stream));  // staging buffer reuse
+    }
+    if (loc == CSPB_HOST && n_images > 0) {  // the caller's host buffer is free again, the packed images are complete
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->pipe_copy));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     ctx->n_images = total;
     if (!keep) {
