@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Drive the drop-in executables at the benchmark's shape (256-px box, O symmetry) the way pyp does:
-refine3d over two ranges, reconstruct3d over two ranges with dumps, merge3d.  Reports wall times,
-the pose error against the truth and the FSC = 0.143 crossing of the merged half maps."""
+refine3d over R ranges, reconstruct3d over R ranges with dumps, merge3d.  Reports wall times (total and per range),
+the pose error against the truth and the FSC = 0.143 crossing of the merged half maps.
+Usage: cli_chain_check.py [particles=4096] [ranges=2]; with CSPB_SERVER=auto in the environment the executables are clients
+of the resident per-GPU engine (pyp_b200/server.py), which is shut down at the end."""
 import json
 import os
 import subprocess
@@ -42,10 +44,12 @@ def main():
     mrc.write(f"{d}/ds_r01.mrc", vol, px)
     cistem.write_parameters(f"{d}/ds_r01.cistem", start)
     open(f"{d}/statistics_r01.txt", "w").close()
-    out = {"particles": P, "box": n, "symmetry": sym}
-    outs, t_ref = [], 0.0
-    half = P // 2
-    for first, last in [(1, half), (half + 1, P)]:
+    R = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    out = {"particles": P, "box": n, "symmetry": sym, "ranges": R, "resident_engine": os.environ.get("CSPB_SERVER", "")}
+    outs, t_ref, t_each = [], 0.0, []
+    edges = [round(k * P / R) for k in range(R + 1)]
+    ranges = [(edges[k] + 1, edges[k + 1]) for k in range(R)]
+    for first, last in ranges:
         ranger = "%07d_%07d" % (first, last)
         a = ["ds_stack.mrc", "ds_r01.cistem", "null", "ds_r01.mrc", "statistics_r01.txt", "no", "no", f"ds_r01_match.mrc_{ranger}",
              f"ds_r01_{ranger}.cistem", f"ds_r01_{ranger}_changes.cistem", sym, first, last, 1, px, 440.0, 0, 0.38 * n * px, 100.0, 2.5 * px,
@@ -54,24 +58,28 @@ def main():
         rc, dt = sh("refine3d", a, d, "refine.log")
         assert rc == 0, open(f"{d}/refine.log").read()[-2000:]
         t_ref += dt
+        t_each.append(round(dt, 3))
         outs.append(f"{d}/ds_r01_{ranger}.cistem")
     refined = cistem.merge(outs)
-    out["refine3d_seconds_2_ranges"] = t_ref
+    out["refine3d_seconds_all_ranges"] = t_ref
+    out["refine3d_seconds_each_range"] = t_each
     out["median_angular_error_deg_start"] = float(np.median(angular_distance(start, rows)))
     out["median_angular_error_deg_refined"] = float(np.median(angular_distance(refined, rows)))
     cistem.write_parameters(f"{d}/ds_r01_used.cistem", refined)
     os.makedirs(f"{d}/scratch", exist_ok=True)
-    t_rec = 0.0
-    for k, (first, last) in enumerate([(1, half), (half + 1, P)], start=1):
+    t_rec, t_each = 0.0, []
+    for k, (first, last) in enumerate(ranges, start=1):
         a = ["ds_stack.mrc", "ds_r01_used.cistem", "null", "ds_r01.mrc", "ds_r01_map1.mrc", "ds_r01_map2.mrc", "output.mrc", f"ds_r01_n{first}.res",
              sym, first, last, px, 440.0, 0, px * n / 2, 2 * px, 0, 2.0, "no", 0, -1, "no", 0, 1, 1, "yes", "no", "no", "no", "no", "yes", "no",
              "no", "no", "no", "yes", f"scratch/ds_r01_map1_n{k}.mrc", f"scratch/ds_r01_map2_n{k}.mrc", 1]
         rc, dt = sh("reconstruct3d", a, d, "recon.log")
         assert rc == 0 and "caught" not in open(f"{d}/recon.log").read()
         t_rec += dt
-    out["reconstruct3d_seconds_2_ranges"] = t_rec
+        t_each.append(round(dt, 3))
+    out["reconstruct3d_seconds_all_ranges"] = t_rec
+    out["reconstruct3d_seconds_each_range"] = t_each
     a = ["ds_r01_02_half1.mrc", "ds_r01_02_half2.mrc", "ds_r01_02.mrc", "ds_r01_02_statistics.txt", 440.0, 0, px * n / 2,
-         "scratch/ds_r01_map1_n.mrc", "scratch/ds_r01_map2_n.mrc", 2]
+         "scratch/ds_r01_map1_n.mrc", "scratch/ds_r01_map2_n.mrc", R]
     rc, dt = sh("merge3d", a, d, "merge.log")
     log = open(f"{d}/merge.log").read()
     assert rc == 0 and "Merge3D: Normal termination" in log, log[-2000:]
@@ -87,5 +95,25 @@ def main():
     subprocess.run(["rm", "-rf", d])
 
 
+def stop_daemons():
+    """stop the resident engines the front-ends started (CSPB_SERVER=auto)"""
+    import socket
+
+    from pyp_b200 import server
+
+    for g in range(torch.cuda.device_count()):
+        try:
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(server.socket_path(g))
+            c.sendall(b'{"prog": "shutdown"}\n')
+            c.makefile("rb").readline()
+        except OSError:
+            pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        if os.environ.get("CSPB_SERVER"):
+            stop_daemons()
