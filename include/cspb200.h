@@ -356,6 +356,10 @@ int cspb_recon_finalize(cspb_ctx *ctx, float molecular_mass_kda, float outer_rad
                         int loc);
 int cspb_recon_end(cspb_ctx *ctx);
 
+/* Batch sizes the streamed pipeline below uses for a stack of n_images of `box` pixels when the scorer's wave is wave_units
+ * (cspb_wave_units): returns their number and writes up to max_sizes of them.  Host-only (no device needed). */
+int cspb_pipeline_batches(int n_images, int box, int wave_units, int *sizes_out, int max_sizes);
+
 /* ------------------------------------------------------------------ streamed host pipeline
  * refine3d and / or reconstruct3d over a HOST stack (pinned memory for full overlap) with ONE upload
  * per projection: chunk k+1 is copied on a second stream while chunk k is preprocessed, refined

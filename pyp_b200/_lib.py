@@ -125,6 +125,7 @@ _SIGNATURES = {
     "cspb_set_symmetry": (_i, [_vp, _vp, _i]),
     "cspb_refine_load_images": (_i, [_vp, _vp, _i, _i, _i]),
     "cspb_refine_keep_spectra": (_i, [_vp, _i]),
+    "cspb_pipeline_batches": (_i, [_i, _i, _i, _vp, _i]),
     "cspb_refine_num_images": (_i, [_vp]),
     "cspb_refine_score": (_i, [_vp, _vp, _i, _vp]),
     "cspb_refine_score_poses": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),

@@ -31,6 +31,48 @@ struct KeepScope {
 };
 }  // namespace
 
+// Batch schedule of the streamed pipeline.  Per-projection work does not depend on the batching (the whitening curve is
+// estimated on the first min(n, 4096) images whatever the chunking), so the results equal those of the staged calls.
+// Whole waves of the scorer (W = SMs x resident CTAs x 4 units, cspb_wave_units), 2W per batch — the kernels need ~0.65 of a
+// batch's copy time, so every batch is done before the next has landed — after a first batch that holds the 4 096 images the
+// whitening curve is estimated on, shrinking W, W, W/2 at the end: the call ends one batch-processing time after the last
+// copy lands (a 2W batch straight before W, W/2 leaves the kernels 4 ms behind the copies).  r02zb timeline: with 4W batches
+// in the middle the 9 472-image batch landed at 103 ms, took 30 ms and pushed the end of the call 19 ms behind the last copy.
+// Bounded by ~6 GB of staging per buffer.
+static std::vector<int> pipeline_batches(long long n_images, int n, long long W) {
+    std::vector<int> sizes;
+    if (n_images <= 0) return sizes;
+    if (W < 1) W = 1;
+    long long cap = (long long)(((size_t)6 << 30) / ((size_t)n * n * sizeof(float)));
+    const long long want = 2 * W > 4096 ? 2 * W : 4096;
+    if (cap > want) cap = want;
+    if (cap < 1) cap = 1;
+    std::vector<int> tail;
+    long long rem = n_images;
+    if (rem >= 8 * W && 2 * W <= cap && W >= 64) { tail = {(int)W, (int)W, (int)(W / 2)}; rem -= 2 * W + W / 2; }
+    else if (rem >= 3 * W && W <= cap) { tail = {(int)W}; rem -= W; }
+    long long first = W > 4096 ? W : 4096;
+    if (first > cap) first = cap;
+    if (first > rem) first = rem;
+    rem -= first;
+    const long long full = cap < 2 * W ? cap : 2 * W;
+    const long long odd = rem % full;  // what the full batches leave over goes second (no crumbs: onto the first batch)
+    if (odd > 0 && odd < W / 2) first += odd;
+    sizes.push_back((int)first);
+    if (odd >= W / 2) sizes.push_back((int)odd);
+    for (long long k = 0; k < rem / full; ++k) sizes.push_back((int)full);
+    sizes.insert(sizes.end(), tail.begin(), tail.end());
+    return sizes;
+}
+
+// the schedule above for a given stack, box and scorer wave (no device needed: exposed for the host-side tests)
+extern "C" int cspb_pipeline_batches(int n_images, int box, int wave_units, int *sizes_out, int max_sizes) {
+    if (n_images < 0 || box < 2 || wave_units < 1 || (!sizes_out && max_sizes > 0)) return CSPB_E_ARG;
+    const std::vector<int> s = pipeline_batches(n_images, box, wave_units);
+    for (int k = 0; k < (int)s.size() && k < max_sizes; ++k) sizes_out[k] = s[k];
+    return (int)s.size();
+}
+
 extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, cspb_row *rows_host, int n_images, int flags,
                                        int64_t *n_evals_out) {
     CSPB_ENTER(ctx);
@@ -43,38 +85,7 @@ extern "C" int cspb_refine_reconstruct(cspb_ctx *ctx, const float *images_host, 
     if (do_refine && do_insert && ctx->ccfg.box != ctx->rcfg.box) return cspb_fail(ctx, CSPB_E_ARG, "refine and reconstruct boxes differ");
     if (n_evals_out) *n_evals_out = 0;
     if (n_images == 0) return 0;
-    // per-projection work does not depend on the batching (the whitening curve is estimated on the
-    // first min(n, 4096) images whatever the chunking), so the results equal those of the staged calls
-    // batch schedule: whole waves of the scorer (W = SMs x resident CTAs x 4 units, cspb_wave_units), 2W per batch — the kernels
-    // need ~0.63 of a batch's copy time, so every batch is done before the next has landed — after a first batch that holds the
-    // 4 096 images the whitening curve is estimated on (estimate_noise_from_spectra: the curve, and with it every result,
-    // equals that of the staged calls whatever the batching), shrinking W, W, W/2 at the end: the call ends one
-    // batch-processing time after the last copy lands.  r02zb timeline: with 4W batches in the middle the 9 472-image batch
-    // landed at 103 ms, took 30 ms and pushed the end of the call 19 ms behind the last copy.
-    const long long W = cspb_wave_units(ctx);
-    long long cap = (long long)(((size_t)6 << 30) / ((size_t)n * n * sizeof(float)));
-    const long long want = 2 * W > 4096 ? 2 * W : 4096;
-    if (cap > want) cap = want;
-    if (cap < 1) cap = 1;
-    std::vector<int> sizes;
-    {
-        std::vector<int> tail;
-        long long rem = n_images;
-        // (a 2W batch straight before W, W/2 leaves the kernels 4 ms behind the copies when the last one lands: W, W, W/2)
-        if (rem >= 8 * W && 2 * W <= cap && W >= 64) { tail = {(int)W, (int)W, (int)(W / 2)}; rem -= 2 * W + W / 2; }
-        else if (rem >= 3 * W) { tail = {(int)W}; rem -= W; }
-        long long first = W > 4096 ? W : 4096;
-        if (first > cap) first = cap;
-        if (first > rem) first = rem;
-        rem -= first;
-        const long long full = cap < 2 * W ? cap : 2 * W;
-        const long long odd = rem % full;  // what the full batches leave over goes second (no crumbs: onto the first batch)
-        if (odd > 0 && odd < W / 2) first += odd;
-        sizes.push_back((int)first);
-        if (odd >= W / 2) sizes.push_back((int)odd);
-        for (long long k = 0; k < rem / full; ++k) sizes.push_back((int)full);
-        sizes.insert(sizes.end(), tail.begin(), tail.end());
-    }
+    const std::vector<int> sizes = pipeline_batches(n_images, n, cspb_wave_units(ctx));
     int chunk = 0;
     for (int v : sizes) chunk = v > chunk ? v : chunk;
     struct { cudaStream_t &copy; cudaEvent_t *ready, *freed; DevBuf *stage; DevBuf &rows; } P = {

@@ -635,3 +635,40 @@ def test_resident_server_protocol_with_a_recording_engine(tmp_path, monkeypatch)
     assert b"served 3 requests" in s.makefile("rb").readline()
     th.join(timeout=10)
     assert not th.is_alive() and not os.path.exists(sock)
+
+
+def test_streamed_pipeline_batch_schedule():
+    """cspb_pipeline_batches (pipeline.cu): the batches cover the stack exactly; the first one holds the 4 096 images the
+    whitening curve is estimated on (or the whole stack); the middle ones are two scorer waves; the tail shrinks W, W, W/2;
+    nothing smaller than half a wave except a stack that is itself smaller; a buffer never exceeds ~6 GB."""
+    import ctypes as C
+
+    from pyp_b200 import _lib
+
+    lib = _lib.lib()
+    W = 2368
+
+    def sched(n_images, box=256, wave=W):
+        buf = (C.c_int * 4096)()
+        k = lib.cspb_pipeline_batches(n_images, box, wave, buf, 4096)
+        assert 0 <= k <= 4096
+        return list(buf[:k])
+
+    assert sched(0) == []
+    assert sched(100) == [100] and sched(4096) == [4096] and sched(5000) == [5000]
+    assert sched(32768) == [4096, 3808, 4736, 4736, 4736, 4736, 2368, 2368, 1184]
+    for n_images in list(range(1, 300, 7)) + [4095, 4097, 7103, 7104, 7105, 8192, 12500, 18943, 18944, 20000, 50000, 100000, 262144, 1000003]:
+        s = sched(n_images)
+        assert sum(s) == n_images and all(v > 0 for v in s)
+        assert s[0] >= min(n_images, 4096)
+        assert max(s) <= max(2 * W, 4096) + W // 2  # staging stays bounded
+        if n_images >= 8 * W:
+            assert s[-3:] == [W, W, W // 2]
+            assert all(v == 2 * W for v in s[2:-3]) and (len(s) < 5 or s[1] == 2 * W or W // 2 <= s[1] < 2 * W)
+        if len(s) > 1:
+            assert min(s) >= W // 2
+    # big boxes: the 6 GB staging bound wins over the wave
+    for box, n_images in ((512, 20000), (1024, 3000), (384, 2048)):
+        s = sched(n_images, box)
+        assert sum(s) == n_images and max(s) * box * box * 4 <= (6 << 30) + W * box * box * 4
+    assert lib.cspb_pipeline_batches(-1, 256, W, None, 0) < 0
